@@ -1,0 +1,529 @@
+// Fused per-event OF1x1 kernel: real FFT -> x phi -> inverse real FFT -> windowed
+// argmax, chi-square by Parseval, low-frequency chi-square; one HBM read per trace.
+//
+// Replaces, per event: qp.OFBase.update_signal(calc_fft=True) + calc_signal_filt +
+// calc_signal_filt_td (reference detprocess/process/processing_data.py:763-772) and
+// qp.OF1x1.calc / get_result_* (reference detprocess/core/algorithms.py:331-341,
+// 410-421, 533-558).
+//
+// Algorithm (all indices refer to the packed complex sequence c[m] = x[2m] + i x[2m+1],
+// m < M = N/2; for P = 2 the complex FFT is split once more, z_p[m'] = c[2m'+p], and
+// the outer radix-2 is merged into the point-wise stage):
+//   M' = M/P = 512*R1 = R1 * 32 * 16      (R1 = 2..32),  NT = 16*R1 threads per CTA
+//   fwd pass 1  radix R1, stride 512 : global -> registers -> DFT -> twiddle -> smem
+//   fwd pass 2  radix 32, stride 16  : smem -> DFT -> twiddle -> smem (in place)
+//   fwd pass 3  radix 16, stride 1   : smem -> DFT -> registers.  Each thread owns the
+//               two butterflies that hold Z[k] and Z[M'-k] for 16 k's, so the
+//               real-FFT untangle, the filter multiply, chi0 and the inverse
+//               untangle are thread-local (no exchange, no mirror tables).
+//   inverse     mirrored passes 3',2',1'; the last pass leaves the amplitude-vs-delay
+//               samples in registers where the windowed arg-max runs.
+// Shared memory holds ONE complex array of M' elements (+1/16 padding): element p
+// lives at p + (p >> 4), which makes every access pattern above bank-conflict free
+// for 8- and 16-byte elements.
+#pragma once
+#include "dp_fft.cuh"
+
+#define DP_MAX_TEMPLATES 4
+#define DP_MAX_SLOTS 8
+#define DP_NLOW_MAX 512
+#define DP_SLOT_NOUT 5  // amp, ind, chi2, lowchi2, timeres
+
+struct DpSlot {
+    int templ;    // template index within the channel
+    int lo, hi;   // candidate rolled delay indices [lo, hi)
+    int outside;  // 1: candidates are the complement of [lo, hi)
+};
+
+template <class T> struct DpTemplDev {
+    const cx<T>* phi;    // [32*P][NT] thread-order filter
+    cx<T> phi_nyq;       // filter at k = N/2
+    const cx<T>* s_low;  // [nlow] scaled template spectrum, natural order
+    double norm;         // QETpy OF norm
+    double tsum;         // sum((2 pi f)^2 |s|^2 / J) * df
+    int pretrigger;      // roll applied to the delay axis
+    int pad_;
+};
+
+template <class T> struct DpChanDev {
+    const T* wj;      // [32*P][NT] thread-order chi0 weights
+    const T* wj_low;  // [nlow] natural order
+    T wj_nyq;
+    int n_templ;
+    int n_slots;
+    int out_base;  // offset (doubles) of this channel's block in an event's output row
+    DpTemplDev<T> templ[DP_MAX_TEMPLATES];
+    DpSlot slots[DP_MAX_SLOTS];
+};
+
+template <class T> struct DpOfParams {
+    const void* traces;      // [n_rows][row_stride] samples (in_dtype)
+    long long row_stride;    // elements
+    int n_rows;              // events * n_chan; row r belongs to channel r % n_chan
+    int n_chan;
+    const DpChanDev<T>* chans;
+    const cx<T>* tw1;   // [512]  exp(-2 pi i m / M')
+    const cx<T>* tw2;   // [16]   exp(-2 pi i m2 / 512)
+    const cx<T>* twn;   // [NT]   exp(-2 pi i K12(t) / N)   thread order
+    const cx<T>* twp;   // [NT]   exp(-2 pi i K12(t) / M)   thread order (P = 2 only)
+    cx<T>* scratch;     // [grid][scratch_per_cta] thread-private spill (P = 2 / multi-template)
+    long long scratch_per_cta;
+    double* out;        // [n_events][n_out]
+    int n_out;
+    int nlow;           // number of low-frequency bins (k < nlow) in lowchi2
+    double scale;       // power-of-two pre-scale applied to the trace (fp32 range safety)
+    int subtract_first; // 1: subtract sample 0 before conversion (fp32 mode, AC coupling)
+    int in_dtype;       // 0: f64, 1: f32, 2: i16
+};
+
+// ------------------------------------------------------------------- geometry
+template <int R1> struct DpGeom {
+    static constexpr int MS = 512 * R1;  // sub-FFT size M'
+    static constexpr int NT = 16 * R1;   // threads per CTA
+    static constexpr int NB1 = 32 / R1;  // pass-1 butterflies per thread
+    static constexpr int KQ = 32 * R1;   // MS/16: k-stride between elements of a pass-3 butterfly
+    static DP_HD int phys(int p) { return p + (p >> 4); }
+    static constexpr int SMEM_ELEMS = MS + MS / 16;
+    // thread t -> (K12, butterflies A and B).  A holds k = K12 + KQ*r, B holds
+    // k = K12' + KQ*r with K12' = KQ - K12, so A[r] pairs with B[15-r].
+    // t == 0 owns the two self-paired butterflies K12 = 0 and K12 = KQ/2.
+    static DP_HD void map(int t, int& K12, int& bA, int& bB) {
+        const int k1 = t >> 4, k2 = t & 15;
+        K12 = k1 + R1 * k2;
+        bA = k1 * 32 + k2;
+        int k1p, k2p;
+        if (k1 != 0) {
+            k1p = R1 - k1;
+            k2p = 31 - k2;
+        } else if (k2 != 0) {
+            k1p = 0;
+            k2p = 32 - k2;
+        } else {
+            k1p = 0;
+            k2p = 16;
+        }
+        bB = k1p * 32 + k2p;
+    }
+};
+
+// ------------------------------------------------------------------ reductions
+DP_DEV double dp_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the CTA; result returned to every thread.  red: >= 33 doubles of smem.
+template <int NT> DP_DEV double dp_block_sum(double v, double* red) {
+    constexpr int NW = (NT + 31) / 32;
+    v = dp_warp_sum(v);
+    const int tid = threadIdx.x;
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        double s = (tid < NW) ? red[tid] : 0.0;
+        s = dp_warp_sum(s);
+        if (tid == 0) red[32] = s;
+    }
+    __syncthreads();
+    const double r = red[32];
+    __syncthreads();
+    return r;
+}
+
+// arg-max of key with smallest-index tie break; (key, idx, val) of the winner is
+// returned to every thread.  idx < 0 means "no candidate".
+template <class T> struct DpBest {
+    T key;
+    T val;
+    int idx;
+};
+template <class T> DP_DEV void dp_best_merge(DpBest<T>& a, const DpBest<T>& b) {
+    const bool take = (b.idx >= 0) && (a.idx < 0 || b.key > a.key || (b.key == a.key && b.idx < a.idx));
+    if (take) a = b;
+}
+template <class T> DP_DEV DpBest<T> dp_warp_best(DpBest<T> a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        DpBest<T> b;
+        b.key = __shfl_xor_sync(0xffffffffu, a.key, o);
+        b.val = __shfl_xor_sync(0xffffffffu, a.val, o);
+        b.idx = __shfl_xor_sync(0xffffffffu, a.idx, o);
+        dp_best_merge(a, b);
+    }
+    return a;
+}
+
+// ------------------------------------------------------------------ trace loads
+// element j of the packed complex sequence: (x[2j], x[2j+1]) - offset, scaled
+template <class T> DP_DEV cx<T> dp_load_pair(const void* row, int in_dtype, long long j, double x0, double sc) {
+    if (in_dtype == 0) {
+        const double2 d = __ldg(reinterpret_cast<const double2*>(row) + j);
+        return cx<T>{(T)((d.x - x0) * sc), (T)((d.y - x0) * sc)};
+    } else if (in_dtype == 1) {
+        const float2 d = __ldg(reinterpret_cast<const float2*>(row) + j);
+        return cx<T>{(T)(((double)d.x - x0) * sc), (T)(((double)d.y - x0) * sc)};
+    } else {
+        const short2* p = reinterpret_cast<const short2*>(row) + j;
+        const short2 d = __ldg(p);
+        return cx<T>{(T)(((double)d.x - x0) * sc), (T)(((double)d.y - x0) * sc)};
+    }
+}
+DP_DEV double dp_load_first(const void* row, int in_dtype) {
+    if (in_dtype == 0) return __ldg(reinterpret_cast<const double*>(row));
+    if (in_dtype == 1) return (double)__ldg(reinterpret_cast<const float*>(row));
+    return (double)__ldg(reinterpret_cast<const short*>(row));
+}
+
+// ------------------------------------------------------------- forward sub-FFT
+// Loads sub-sequence z[j] = c[P*j + p] from global, runs passes 1..3 and leaves
+// Z[K12 + KQ*r] in za[r], Z[K12' + KQ*r] in zb[r].
+template <class T, int R1, int P>
+DP_DEV void dp_fwd_subfft(const void* row, int in_dtype, int p, double x0, double sc, cx<T>* buf,
+                          const cx<T>* DP_RESTRICT tw1, const cx<T>* DP_RESTRICT tw2, int bA, int bB,
+                          cx<T> (&za)[16], cx<T> (&zb)[16]) {
+    using G = DpGeom<R1>;
+    const int tid = threadIdx.x;
+    // pass 1: radix R1 over n1 (stride 512)
+#pragma unroll
+    for (int i = 0; i < G::NB1; ++i) {
+        const int m = tid + i * G::NT;
+        cx<T> v[R1];
+#pragma unroll
+        for (int n = 0; n < R1; ++n) v[n] = dp_load_pair<T>(row, in_dtype, (long long)P * (m + n * 512) + p, x0, sc);
+        dp_dft<R1, -1, T>::run(v);
+        dp_twiddle<R1, false, T>(v, __ldg(tw1 + m));
+#pragma unroll
+        for (int k = 0; k < R1; ++k) buf[G::phys(k * 512 + m)] = v[k];
+    }
+    __syncthreads();
+    // pass 2: radix 32 over n2 (stride 16) inside block k1
+    {
+        const int base = (tid >> 4) * 512 + (tid & 15);
+        cx<T> v[32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n) v[n] = buf[G::phys(base + n * 16)];
+        dp_dft<32, -1, T>::run(v);
+        dp_twiddle<32, false, T>(v, __ldg(tw2 + (tid & 15)));
+#pragma unroll
+        for (int k = 0; k < 32; ++k) buf[G::phys(base + k * 16)] = v[k];
+    }
+    __syncthreads();
+    // pass 3: radix 16 over n3 (stride 1), two butterflies per thread, kept in registers
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        za[n] = buf[G::phys(16 * bA + n)];
+        zb[n] = buf[G::phys(16 * bB + n)];
+    }
+    dp_dft<16, -1, T>::run(za);
+    dp_dft<16, -1, T>::run(zb);
+}
+
+// ------------------------------------------------------------- inverse sub-FFT
+// Consumes Z' in (za, zb); calls sink(j, value) for every element z'[j] of the
+// sub-sequence (j = m + 512*n1).  Starts with a barrier-free in-place store (own
+// positions) and ends without a barrier: the caller must __syncthreads() before the
+// next store into buf.
+template <class T, int R1, class Sink>
+DP_DEV void dp_inv_subfft(cx<T>* buf, const cx<T>* DP_RESTRICT tw1, const cx<T>* DP_RESTRICT tw2, int bA, int bB,
+                          cx<T> (&za)[16], cx<T> (&zb)[16], Sink&& sink) {
+    using G = DpGeom<R1>;
+    const int tid = threadIdx.x;
+    dp_dft<16, +1, T>::run(za);
+    dp_dft<16, +1, T>::run(zb);
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        buf[G::phys(16 * bA + n)] = za[n];
+        buf[G::phys(16 * bB + n)] = zb[n];
+    }
+    __syncthreads();
+    {
+        const int base = (tid >> 4) * 512 + (tid & 15);
+        cx<T> v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = buf[G::phys(base + k * 16)];
+        dp_twiddle<32, true, T>(v, __ldg(tw2 + (tid & 15)));
+        dp_dft<32, +1, T>::run(v);
+#pragma unroll
+        for (int n = 0; n < 32; ++n) buf[G::phys(base + n * 16)] = v[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < G::NB1; ++i) {
+        const int m = tid + i * G::NT;
+        cx<T> v[R1];
+#pragma unroll
+        for (int k = 0; k < R1; ++k) v[k] = buf[G::phys(k * 512 + m)];
+        dp_twiddle<R1, true, T>(v, __ldg(tw1 + m));
+        dp_dft<R1, +1, T>::run(v);
+#pragma unroll
+        for (int n = 0; n < R1; ++n) sink(m + n * 512, v[n]);
+    }
+}
+
+// --------------------------------------------------------- point-wise helpers
+// Real-FFT untangle of the pair (k, M-k):  Zk = C[k], Zm = C[M-k], w = exp(-2 pi i k/N).
+// Returns 2*X[k] and 2*X[M-k] (the factor 2 is folded into the tables).
+template <class T> DP_DEV void dp_untangle(cx<T> Zk, cx<T> Zm, cx<T> w, cx<T>& Xk, cx<T>& Xm) {
+    const cx<T> E2 = cx<T>{Zk.re + Zm.re, Zk.im - Zm.im};  // Zk + conj(Zm)
+    const cx<T> D = cx<T>{Zk.re - Zm.re, Zk.im + Zm.im};   // Zk - conj(Zm)
+    const cx<T> G = cmuli(cmul(w, D));                      // i*w*D
+    Xk = csub(E2, G);
+    Xm = cconj(cadd(E2, G));
+}
+// Inverse: from F[k], F[M-k] to C'[k], C'[M-k].
+template <class T> DP_DEV void dp_retangle(cx<T> Fk, cx<T> Fm, cx<T> w, cx<T>& Ck, cx<T>& Cm) {
+    const cx<T> E = cx<T>{Fk.re + Fm.re, Fk.im - Fm.im};  // Fk + conj(Fm)
+    const cx<T> D = cx<T>{Fk.re - Fm.re, Fk.im + Fm.im};  // Fk - conj(Fm)
+    const cx<T> O = cmuli(cmulc(D, w));                    // i * D * conj(w)
+    Ck = cadd(E, O);
+    Cm = cconj(csub(E, O));
+}
+
+// ======================================================================== kernel
+template <class T, int R1, int P> struct DpOfKernel {
+    using G = DpGeom<R1>;
+    static constexpr int NT = G::NT;
+    static constexpr int NE = 32 * P;  // table entries (and X values) per thread
+    static constexpr int N = 2 * P * G::MS;
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (G::SMEM_ELEMS + DP_NLOW_MAX) + sizeof(double) * 40 +
+                                         sizeof(DpBest<T>) * 32 * DP_MAX_SLOTS + 64;
+
+    struct Smem {
+        cx<T>* buf;
+        cx<T>* stash;
+        double* red;
+        DpBest<T>* best;  // [DP_MAX_SLOTS][32]
+    };
+    static DP_DEV Smem carve(unsigned char* raw) {
+        Smem s;
+        s.buf = reinterpret_cast<cx<T>*>(raw);
+        s.stash = s.buf + G::SMEM_ELEMS;
+        s.red = reinterpret_cast<double*>(s.stash + DP_NLOW_MAX);
+        s.best = reinterpret_cast<DpBest<T>*>(s.red + 40);
+        return s;
+    }
+
+    static DP_DEV void run(const DpOfParams<T>& prm, unsigned char* smem_raw);
+};
+
+// The body is long; keep it out of the class for readability.
+template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const DpOfParams<T>& prm, unsigned char* smem_raw) {
+    static_assert(P == 1 || P == 2, "P");
+    const Smem sm = carve(smem_raw);
+    const int tid = threadIdx.x;
+    int K12, bA, bB;
+    G::map(tid, K12, bA, bB);
+    const cx<T> wn = __ldg(prm.twn + tid);  // exp(-2 pi i K12 / N)
+    cx<T>* scr = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
+
+    for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
+        const int chan = row % prm.n_chan;
+        const int ev = row / prm.n_chan;
+        const DpChanDev<T>& ch = prm.chans[chan];
+        const void* xrow;
+        {
+            const size_t esz = prm.in_dtype == 0 ? 8 : (prm.in_dtype == 1 ? 4 : 2);
+            xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * esz;
+        }
+        const double x0 = prm.subtract_first ? dp_load_first(xrow, prm.in_dtype) : 0.0;
+        const double sc = prm.scale;
+
+        cx<T> za[16], zb[16];
+        T chi = (T)0;
+
+        if constexpr (P == 1) {
+            dp_fwd_subfft<T, R1, 1>(xrow, prm.in_dtype, 0, x0, sc, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+            // ---- untangle: (za, zb) <- 2*X ---------------------------------------------
+            if (tid != 0) {
+                // A[r] (k = K12 + KQ r) pairs with B[15-r] (k' = M - k);  w = wn * W_32^r
+#define DP_XP(r)                                                                                         \
+    {                                                                                                    \
+        cx<T> Xk, Xm;                                                                                    \
+        dp_untangle(za[r], zb[15 - r], cmul(wn, dp_w64<T, 2 * r, -1>()), Xk, Xm);                        \
+        chi = dp_fma(__ldg(ch.wj + r * NT + tid), cnorm2(Xk), chi);                                      \
+        chi = dp_fma(__ldg(ch.wj + (16 + 15 - r) * NT + tid), cnorm2(Xm), chi);                          \
+        za[r] = Xk;                                                                                      \
+        zb[15 - r] = Xm;                                                                                 \
+    }
+                DP_XP(0) DP_XP(1) DP_XP(2) DP_XP(3) DP_XP(4) DP_XP(5) DP_XP(6) DP_XP(7)
+                DP_XP(8) DP_XP(9) DP_XP(10) DP_XP(11) DP_XP(12) DP_XP(13) DP_XP(14) DP_XP(15)
+#undef DP_XP
+            } else {
+                // thread 0: A = K12 0 (k = KQ r, pairs r <-> 16-r; r = 0 is DC/Nyquist, r = 8 is k = M/2)
+                //           B = K12 KQ/2 (k = KQ/2 + KQ r, pairs r <-> 15-r)
+#define DP_XA(r, rp)                                                                                     \
+    {                                                                                                    \
+        cx<T> Xk, Xm;                                                                                    \
+        dp_untangle(za[r], za[rp], dp_w64<T, 2 * r, -1>(), Xk, Xm);                                      \
+        chi = dp_fma(__ldg(ch.wj + r * NT), cnorm2(Xk), chi);                                            \
+        if (r == 0) chi = dp_fma(ch.wj_nyq, cnorm2(Xm), chi);                                            \
+        else if (r != rp) chi = dp_fma(__ldg(ch.wj + rp * NT), cnorm2(Xm), chi);                         \
+        za[r] = Xk;                                                                                      \
+        if (r != rp) za[rp] = Xm;                                                                        \
+        if (r == 0) sm.stash[DP_NLOW_MAX - 1] = Xm; /* Nyquist X kept for the filter step */             \
+    }
+                DP_XA(0, 0) DP_XA(1, 15) DP_XA(2, 14) DP_XA(3, 13) DP_XA(4, 12) DP_XA(5, 11) DP_XA(6, 10)
+                DP_XA(7, 9) DP_XA(8, 8)
+#undef DP_XA
+#define DP_XB(r)                                                                                         \
+    {                                                                                                    \
+        cx<T> Xk, Xm;                                                                                    \
+        dp_untangle(zb[r], zb[15 - r], dp_w64<T, 1 + 2 * r, -1>(), Xk, Xm);                              \
+        chi = dp_fma(__ldg(ch.wj + (16 + r) * NT), cnorm2(Xk), chi);                                     \
+        chi = dp_fma(__ldg(ch.wj + (16 + 15 - r) * NT), cnorm2(Xm), chi);                                \
+        zb[r] = Xk;                                                                                      \
+        zb[15 - r] = Xm;                                                                                 \
+    }
+                DP_XB(0) DP_XB(1) DP_XB(2) DP_XB(3) DP_XB(4) DP_XB(5) DP_XB(6) DP_XB(7)
+#undef DP_XB
+            }
+            // low-frequency bins for lowchi2: k = K12 < nlow lives in A[0]
+            if (K12 < prm.nlow) sm.stash[K12] = za[0];
+        }
+
+        // chi0 (block sum) -- also the barrier that publishes the stash
+        const double chi0 = dp_block_sum<NT>((double)chi, sm.red);
+
+        // multi-template: X must survive the in-place inverse of the previous template
+        const bool spill_x = ch.n_templ > 1;
+        if (spill_x) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                scr[r * NT + tid] = za[r];
+                scr[(16 + r) * NT + tid] = zb[r];
+            }
+        }
+
+        for (int it = 0; it < ch.n_templ; ++it) {
+            const DpTemplDev<T>& tp = ch.templ[it];
+            if (it > 0) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    za[r] = scr[r * NT + tid];
+                    zb[r] = scr[(16 + r) * NT + tid];
+                }
+            }
+            // ---- filter + inverse untangle: (za, zb) <- Z' -----------------------------
+            if constexpr (P == 1) {
+                if (tid != 0) {
+#define DP_FP(r)                                                                                         \
+    {                                                                                                    \
+        const cx<T> Fk = cmul(__ldg(tp.phi + r * NT + tid), za[r]);                                      \
+        const cx<T> Fm = cmul(__ldg(tp.phi + (16 + 15 - r) * NT + tid), zb[15 - r]);                     \
+        dp_retangle(Fk, Fm, cmul(wn, dp_w64<T, 2 * r, -1>()), za[r], zb[15 - r]);                        \
+    }
+                    DP_FP(0) DP_FP(1) DP_FP(2) DP_FP(3) DP_FP(4) DP_FP(5) DP_FP(6) DP_FP(7)
+                    DP_FP(8) DP_FP(9) DP_FP(10) DP_FP(11) DP_FP(12) DP_FP(13) DP_FP(14) DP_FP(15)
+#undef DP_FP
+                } else {
+#define DP_FA(r, rp)                                                                                     \
+    {                                                                                                    \
+        const cx<T> Fk = cmul(__ldg(tp.phi + r * NT), za[r]);                                            \
+        const cx<T> Fm = (r == 0) ? cmul(tp.phi_nyq, sm.stash[DP_NLOW_MAX - 1])                          \
+                                  : cmul(__ldg(tp.phi + rp * NT), za[rp]);                               \
+        cx<T> Ck, Cm;                                                                                    \
+        dp_retangle(Fk, Fm, dp_w64<T, 2 * r, -1>(), Ck, Cm);                                             \
+        za[r] = Ck;                                                                                      \
+        if (r != rp) za[rp] = Cm;                                                                        \
+    }
+                    DP_FA(0, 0) DP_FA(1, 15) DP_FA(2, 14) DP_FA(3, 13) DP_FA(4, 12) DP_FA(5, 11) DP_FA(6, 10)
+                    DP_FA(7, 9) DP_FA(8, 8)
+#undef DP_FA
+#define DP_FB(r)                                                                                         \
+    {                                                                                                    \
+        const cx<T> Fk = cmul(__ldg(tp.phi + (16 + r) * NT), zb[r]);                                     \
+        const cx<T> Fm = cmul(__ldg(tp.phi + (16 + 15 - r) * NT), zb[15 - r]);                           \
+        dp_retangle(Fk, Fm, dp_w64<T, 1 + 2 * r, -1>(), zb[r], zb[15 - r]);                              \
+    }
+                    DP_FB(0) DP_FB(1) DP_FB(2) DP_FB(3) DP_FB(4) DP_FB(5) DP_FB(6) DP_FB(7)
+#undef DP_FB
+                }
+            }
+
+            // ---- inverse + windowed arg-max ---------------------------------------------
+            DpBest<T> best[DP_MAX_SLOTS];
+#pragma unroll
+            for (int s = 0; s < DP_MAX_SLOTS; ++s) best[s] = DpBest<T>{(T)0, (T)0, -1};
+            const int pre = tp.pretrigger;
+            auto sink = [&](int j, cx<T> v) {
+                // c'[j] -> real samples n = 2j, 2j+1; rolled index r = (n + pre) mod N
+                const int r0 = (2 * j + pre) & (N - 1);
+                const int r1 = (2 * j + 1 + pre) & (N - 1);
+#pragma unroll
+                for (int s = 0; s < DP_MAX_SLOTS; ++s) {
+                    if (s < ch.n_slots && ch.slots[s].templ == it) {
+                        const DpSlot sl = ch.slots[s];
+                        const unsigned len = (unsigned)(sl.hi - sl.lo);
+                        const bool in0 = (((unsigned)(r0 - sl.lo) < len) != (sl.outside != 0));
+                        const bool in1 = (((unsigned)(r1 - sl.lo) < len) != (sl.outside != 0));
+                        if (in0) dp_best_merge(best[s], DpBest<T>{v.re * v.re, v.re, r0});
+                        if (in1) dp_best_merge(best[s], DpBest<T>{v.im * v.im, v.im, r1});
+                    }
+                }
+            };
+            if constexpr (P == 1) dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, sink);
+
+            // ---- block arg-max per slot, lowchi2, outputs -------------------------------
+#pragma unroll
+            for (int s = 0; s < DP_MAX_SLOTS; ++s) {
+                if (s < ch.n_slots && ch.slots[s].templ == it) {
+                    DpBest<T> b = dp_warp_best(best[s]);
+                    if ((tid & 31) == 0) sm.best[s * 32 + (tid >> 5)] = b;
+                }
+            }
+            __syncthreads();
+            for (int s = 0; s < ch.n_slots; ++s) {
+                if (ch.slots[s].templ != it) continue;
+                DpBest<T> b = sm.best[s * 32];
+                for (int w = 1; w < (NT + 31) / 32; ++w) dp_best_merge(b, sm.best[s * 32 + w]);
+                // low-frequency chi2 at (amp, delay)
+                const int d = b.idx - pre;
+                double part = 0.0;
+                for (int k = tid; k < prm.nlow; k += NT) {
+                    const int ph = (int)(((long long)k * (long long)d) % N + N) % N;  // exp(-2 pi i k d / N)
+                    T sn, cs;
+                    if constexpr (sizeof(T) == 8) {
+                        double s_, c_;
+                        sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
+                        sn = (T)s_;
+                        cs = (T)c_;
+                    } else {
+                        float s_, c_;
+                        sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
+                        sn = (T)s_;
+                        cs = (T)c_;
+                    }
+                    const cx<T> e = cx<T>{cs, -sn};
+                    const cx<T> S = __ldg(tp.s_low + k);
+                    const cx<T> mdl = cmul(e, S);
+                    const cx<T> X = sm.stash[k];
+                    const cx<T> R = cx<T>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
+                    part += (double)(__ldg(ch.wj_low + k) * cnorm2(R));
+                }
+                const double low = dp_block_sum<NT>(part, sm.red);
+                if (tid == 0) {
+                    double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
+                    o[0] = chi0;
+                    double* os = o + 1 + s * DP_SLOT_NOUT;
+                    const double amp = (double)b.val;
+                    os[0] = amp;
+                    os[1] = (double)b.idx;
+                    os[2] = chi0 - amp * amp * tp.norm;
+                    os[3] = low;
+                    os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
+                }
+            }
+            __syncthreads();  // buf / best / stash reuse
+        }
+        if (ch.n_slots == 0 && tid == 0) prm.out[(long long)ev * prm.n_out + ch.out_base] = chi0;
+    }
+}
+
+#ifndef DP_HOST_EMU
+template <class T, int R1, int P>
+__global__ void __launch_bounds__(DpGeom<R1>::NT, 1) dp_of_kernel(const DpOfParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char dp_smem_raw[];
+    DpOfKernel<T, R1, P>::run(prm, dp_smem_raw);
+}
+#endif

@@ -1,0 +1,88 @@
+"""
+Synthetic TES-like inputs (template, two-sided PSD, coloured-noise traces with
+injected pulses) of the shapes BASELINE.json names.  numpy only; used by the
+tests, ``bench.py`` and ``__graft_entry__.smoke()``.  There is no network and no
+HDF5 library in this environment, so every measurement runs on these arrays
+(SURVEY.md 8(d)).
+"""
+
+import numpy as np
+
+__all__ = ['make_template', 'make_psd', 'make_noise', 'make_traces', 'SynthSetup']
+
+FS_DEFAULT = 1.25e6
+SEED_DEFAULT = 12345
+
+
+def make_template(nb_samples, fs=FS_DEFAULT, nb_pretrigger=None,
+                  tau_rise=20e-6, tau_fall=200e-6):
+    """Two-pole pulse, peak normalised to 1, baseline 0, onset at nb_pretrigger."""
+    if nb_pretrigger is None:
+        nb_pretrigger = nb_samples // 2
+    t = (np.arange(nb_samples) - nb_pretrigger) / fs
+    tp = np.where(t > 0, t, 0.0)
+    pulse = np.where(t > 0, np.exp(-tp / tau_fall) - np.exp(-tp / tau_rise), 0.0)
+    return pulse / pulse.max()
+
+
+def make_glitch_template(nb_samples, fs=FS_DEFAULT, nb_pretrigger=None):
+    return make_template(nb_samples, fs, nb_pretrigger, tau_rise=2e-6, tau_fall=10e-6)
+
+
+def make_psd(nb_samples, fs=FS_DEFAULT, sigma=1e-11, f_corner=1e3):
+    """Two-sided PSD [N] in A^2/Hz (fftfreq order): white + 1/f, even in f, > 0."""
+    f = np.abs(np.fft.fftfreq(nb_samples, d=1.0 / fs))
+    df = fs / nb_samples
+    return sigma ** 2 * (1.0 + f_corner / np.maximum(f, df))
+
+
+def make_noise(nb_events, psd, fs=FS_DEFAULT, rng=None):
+    """Gaussian noise traces [B, N] whose two-sided PSD expectation is ``psd``."""
+    rng = np.random.default_rng(SEED_DEFAULT) if rng is None else rng
+    n = psd.shape[-1]
+    nh = n // 2 + 1
+    # E|fft(x)|^2 = psd * N * fs  (calc_psd convention: |fft|^2/(N fs))
+    amp = np.sqrt(psd[:nh] * n * fs / 2.0)
+    spec = (rng.standard_normal((nb_events, nh)) + 1j * rng.standard_normal((nb_events, nh))) * amp
+    spec[:, 0] = spec[:, 0].real * np.sqrt(2.0)
+    if n % 2 == 0:
+        spec[:, -1] = spec[:, -1].real * np.sqrt(2.0)
+    return np.fft.irfft(spec, n=n, axis=-1)
+
+
+def make_traces(nb_events, template, psd, fs=FS_DEFAULT, rng=None,
+                amp_max=2e-7, max_delay=300, pulse_fraction=0.9, offset=0.0,
+                return_truth=False):
+    """
+    Noise + template*A rolled by an integer delay d on ``pulse_fraction`` of the
+    events (A ~ U(0, amp_max), d ~ U{-max_delay..max_delay}); the rest noise only.
+    """
+    rng = np.random.default_rng(SEED_DEFAULT) if rng is None else rng
+    traces = make_noise(nb_events, psd, fs, rng)
+    has = rng.random(nb_events) < pulse_fraction
+    amps = np.where(has, rng.random(nb_events) * amp_max, 0.0)
+    delays = np.where(has, rng.integers(-max_delay, max_delay + 1, nb_events), 0)
+    for i in np.nonzero(has)[0]:
+        traces[i] += amps[i] * np.roll(template, int(delays[i]))
+    if offset:
+        traces += offset
+    if return_truth:
+        return traces, amps, delays
+    return traces
+
+
+class SynthSetup:
+    """Template(s) + PSD + trace factory for one (N, pretrigger) shape."""
+
+    def __init__(self, nb_samples=32768, fs=FS_DEFAULT, nb_pretrigger=None, seed=SEED_DEFAULT):
+        self.nb_samples = int(nb_samples)
+        self.fs = float(fs)
+        self.nb_pretrigger = self.nb_samples // 2 if nb_pretrigger is None else int(nb_pretrigger)
+        self.seed = seed
+        self.template = make_template(self.nb_samples, fs, self.nb_pretrigger)
+        self.template_glitch = make_glitch_template(self.nb_samples, fs, self.nb_pretrigger)
+        self.psd = make_psd(self.nb_samples, fs)
+
+    def traces(self, nb_events, rank=0, **kwargs):
+        rng = np.random.default_rng(self.seed + rank)
+        return make_traces(nb_events, self.template, self.psd, self.fs, rng, **kwargs)

@@ -1,0 +1,44 @@
+"""Helper: drive the host emulator of the OF kernel and compare with the oracle."""
+import os, struct, subprocess, tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EXE = os.path.join(HERE, '_build', 'emu_of')
+
+
+def build(tsan=False):
+    os.makedirs(os.path.join(HERE, '_build'), exist_ok=True)
+    exe = EXE + ('_tsan' if tsan else '')
+    src = os.path.join(HERE, 'emu_of.cpp')
+    deps = [src] + [os.path.join(HERE, '../../detprocess_b200/csrc', f) for f in
+                    ('dp_of_kernel.cuh', 'dp_fft.cuh', 'dp_platform.cuh', 'dp_plan.hpp')]
+    if os.path.exists(exe) and all(os.path.getmtime(exe) > os.path.getmtime(d) for d in deps):
+        return exe
+    cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-o', exe, src]
+    if tsan:
+        cmd[3:3] = ['-fsanitize=thread', '-g']
+    subprocess.check_call(cmd)
+    return exe
+
+
+def run(traces, psd, templates, fits, fs, fcut=10000.0, precision='f64', ac=True,
+        subtract_first=False, scale=1.0, tsan=False):
+    """templates: list of (template, pretrigger, integralnorm); fits: list of (templ, lo, hi, outside)."""
+    exe = build(tsan)
+    traces = np.ascontiguousarray(traces, dtype=np.float64)
+    nev, n = traces.shape
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fin, 'wb') as f:
+            f.write(struct.pack('<6i', n, nev, len(templates), len(fits), int(ac), int(subtract_first)))
+            f.write(struct.pack('<3d', fs, fcut, scale))
+            f.write(np.asarray(psd, dtype=np.float64).tobytes())
+            for tpl, pre, inorm in templates:
+                f.write(struct.pack('<2i', pre, int(inorm)))
+                f.write(np.asarray(tpl, dtype=np.float64).tobytes())
+            for ft in fits:
+                f.write(struct.pack('<4i', *ft))
+            f.write(traces.tobytes())
+        subprocess.check_call([exe, fin, fout, precision])
+        out = np.fromfile(fout, dtype=np.float64).reshape(nev, 1 + 5 * len(fits))
+    return out
