@@ -1,0 +1,286 @@
+"""
+Thin Python objects over the C-ABI plans (include/detprocess_b200.h).
+
+``OFPlan``     <-> ``dp_of_plan``      (one per reference ``qp.OFBase`` object)
+``ReducePlan`` <-> ``dp_reduce_plan``  (the trace-window features of one config)
+
+PyTorch is used only as the owner of device memory and streams: tensors are passed
+to the library as raw device pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .._lib import lib, check
+
+_PREC = {'f64': _lib.DP_PREC_F64, 'fp64': _lib.DP_PREC_F64, 'float64': _lib.DP_PREC_F64,
+         'f32': _lib.DP_PREC_F32, 'fp32': _lib.DP_PREC_F32, 'float32': _lib.DP_PREC_F32}
+_OPS = {'baseline': _lib.DP_OP_BASELINE, 'integral': _lib.DP_OP_INTEGRAL,
+        'maximum': _lib.DP_OP_MAXIMUM, 'minimum': _lib.DP_OP_MINIMUM}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _in_dtype_of(t):
+    torch = _torch()
+    if isinstance(t, np.ndarray):
+        m = {np.dtype('float64'): _lib.DP_IN_F64, np.dtype('float32'): _lib.DP_IN_F32,
+             np.dtype('int16'): _lib.DP_IN_I16}
+        if t.dtype not in m:
+            raise ValueError(f'unsupported trace dtype {t.dtype}')
+        return m[t.dtype]
+    m = {torch.float64: _lib.DP_IN_F64, torch.float32: _lib.DP_IN_F32, torch.int16: _lib.DP_IN_I16}
+    if t.dtype not in m:
+        raise ValueError(f'unsupported trace dtype {t.dtype}')
+    return m[t.dtype]
+
+
+def _stream_ptr(device):
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class OFPlan:
+    """Batched OF1x1 plan: PSD + templates + delay-search fits for ``n_chan`` channels."""
+
+    def __init__(self, nb_samples, sample_rate, n_chan=1, precision='f64'):
+        if precision not in _PREC:
+            raise ValueError(f'unknown precision "{precision}"')
+        self.nb_samples = int(nb_samples)
+        self.sample_rate = float(sample_rate)
+        self.n_chan = int(n_chan)
+        self.precision = 'f32' if _PREC[precision] == _lib.DP_PREC_F32 else 'f64'
+        self._h = C.c_void_p()
+        check(lib.dp_of_plan_create(C.byref(self._h), self.nb_samples, self.sample_rate,
+                                    self.n_chan, _PREC[precision]))
+        self.finalized = False
+        self.device = None
+        self.pretriggers = {}   # (chan, templ) -> pretrigger
+        self.fits = {}          # (chan, fit) -> (templ, lo, hi, outside)
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            lib.dp_of_plan_destroy(h)
+            self._h = C.c_void_p()
+
+    # ---- setup ---------------------------------------------------------------
+    def set_psd(self, chan, psd, coupling='AC'):
+        psd = np.ascontiguousarray(np.real(np.asarray(psd)).reshape(-1), dtype=np.float64)
+        if psd.shape[0] != self.nb_samples:
+            raise ValueError(f'Number of samples is not consistent between raw data '
+                             f'(={self.nb_samples}) and csd (={psd.shape[0]})')
+        check(lib.dp_of_plan_set_psd(self._h, int(chan), psd.ctypes.data, 1 if coupling == 'AC' else 0))
+
+    def add_template(self, chan, template, pretrigger_samples=None, integralnorm=False):
+        template = np.ascontiguousarray(np.asarray(template).reshape(-1), dtype=np.float64)
+        if template.shape[0] != self.nb_samples:
+            raise ValueError('Number of samples is not consistent between raw data and template')
+        if pretrigger_samples is None:
+            pretrigger_samples = self.nb_samples // 2
+        idx = C.c_int(-1)
+        check(lib.dp_of_plan_add_template(self._h, int(chan), template.ctypes.data,
+                                          int(pretrigger_samples), int(bool(integralnorm)), C.byref(idx)))
+        self.pretriggers[(int(chan), idx.value)] = int(pretrigger_samples)
+        return idx.value
+
+    def add_fit(self, chan, templ, window_lo=None, window_hi=None, outside=False):
+        lo = 0 if window_lo is None else int(window_lo)
+        hi = self.nb_samples if window_hi is None else int(window_hi)
+        idx = C.c_int(-1)
+        check(lib.dp_of_plan_add_fit(self._h, int(chan), int(templ), lo, hi, int(bool(outside)), C.byref(idx)))
+        self.fits[(int(chan), idx.value)] = (int(templ), lo, hi, bool(outside))
+        return idx.value
+
+    def add_fit_nodelay(self, chan, templ):
+        pre = self.pretriggers[(int(chan), int(templ))]
+        return self.add_fit(chan, templ, pre, pre + 1)
+
+    def set_lowchi2_fcutoff(self, fcutoff):
+        check(lib.dp_of_plan_set_lowchi2_fcutoff(self._h, float(fcutoff)))
+
+    def finalize(self, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.DetprocessB200Error('no CUDA device: detprocess_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        check(lib.dp_of_plan_finalize(self._h, device.index or 0))
+        self.device = device
+        self.finalized = True
+        n = C.c_int()
+        check(lib.dp_of_plan_n_out(self._h, C.byref(n)))
+        self.n_out = n.value
+        return self
+
+    # ---- layout ----------------------------------------------------------------
+    def fit_offset(self, chan, fit):
+        o = C.c_int()
+        check(lib.dp_of_plan_fit_offset(self._h, int(chan), int(fit), C.byref(o)))
+        return o.value
+
+    def chi0_offset(self, chan):
+        o = C.c_int()
+        check(lib.dp_of_plan_chi0_offset(self._h, int(chan), C.byref(o)))
+        return o.value
+
+    def phi(self, chan, templ):
+        out = np.empty((self.nb_samples, 2), dtype=np.float64)
+        check(lib.dp_of_plan_get_phi(self._h, int(chan), int(templ), out.ctypes.data))
+        return out[:, 0] + 1j * out[:, 1]
+
+    def template_fft(self, chan, templ):
+        out = np.empty((self.nb_samples, 2), dtype=np.float64)
+        check(lib.dp_of_plan_get_template_fft(self._h, int(chan), int(templ), out.ctypes.data))
+        return out[:, 0] + 1j * out[:, 1]
+
+    def norm(self, chan, templ):
+        v = C.c_double()
+        check(lib.dp_of_plan_get_norm(self._h, int(chan), int(templ), C.byref(v)))
+        return v.value
+
+    # ---- hot calls -------------------------------------------------------------
+    def _shape(self, traces):
+        if traces.ndim == 2:
+            if self.n_chan != 1:
+                raise ValueError('expected traces [n_events, n_chan, nb_samples]')
+            nev = traces.shape[0]
+        elif traces.ndim == 3:
+            if traces.shape[1] != self.n_chan:
+                raise ValueError(f'expected {self.n_chan} channels, got {traces.shape[1]}')
+            nev = traces.shape[0]
+        else:
+            raise ValueError('traces must be [n_events, nb_samples] or [n_events, n_chan, nb_samples]')
+        if traces.shape[-1] != self.nb_samples:
+            raise ValueError('ERROR: signal length != template/psd length')
+        return nev
+
+    def run(self, traces, out=None):
+        """traces: CUDA tensor [B, (C,) N] (f64 / f32 / i16).  Returns CUDA f64 [B, n_out]. Async."""
+        torch = _torch()
+        if not self.finalized:
+            raise _lib.DetprocessB200Error('plan not finalized')
+        if not traces.is_cuda:
+            raise ValueError('run() takes device tensors; use run_host() for host arrays')
+        nev = self._shape(traces)
+        traces = traces.contiguous()
+        if out is None:
+            out = torch.empty((nev, self.n_out), dtype=torch.float64, device=traces.device)
+        check(lib.dp_of1x1_batch(self._h, C.c_void_p(traces.data_ptr()), _in_dtype_of(traces), nev,
+                                 self.nb_samples, C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
+        return out
+
+    def run_host(self, traces, out=None):
+        """traces: host ndarray or (pinned) CPU tensor.  Returns ndarray [B, n_out].  Synchronous."""
+        torch = _torch()
+        if not self.finalized:
+            raise _lib.DetprocessB200Error('plan not finalized')
+        if isinstance(traces, np.ndarray):
+            traces = np.ascontiguousarray(traces)
+            ptr = traces.ctypes.data
+        else:
+            if traces.is_cuda:
+                raise ValueError('run_host() takes host buffers')
+            traces = traces.contiguous()
+            ptr = traces.data_ptr()
+        nev = self._shape(traces)
+        if out is None:
+            out = np.empty((nev, self.n_out), dtype=np.float64)
+        optr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        check(lib.dp_of1x1_batch_host(self._h, C.c_void_p(ptr), _in_dtype_of(traces), nev,
+                                      self.nb_samples, C.c_void_p(optr)))
+        return out
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(lib.dp_of_plan_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_longlong()
+        check(lib.dp_of_plan_launch_count(self._h, C.byref(n)))
+        return n.value
+
+
+class ReducePlan:
+    """Bit-exact windowed baseline / integral / maximum / minimum for ``n_chan`` channels."""
+
+    def __init__(self, nb_samples, sample_rate, n_chan=1):
+        self.nb_samples = int(nb_samples)
+        self.sample_rate = float(sample_rate)
+        self.n_chan = int(n_chan)
+        self._h = C.c_void_p()
+        check(lib.dp_reduce_plan_create(C.byref(self._h), self.nb_samples, self.sample_rate, self.n_chan))
+        self.finalized = False
+        self._added = []  # (chan, feat_index)
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            lib.dp_reduce_plan_destroy(h)
+            self._h = C.c_void_p()
+
+    def add(self, chan, op, window_min_index=None, window_max_index=None):
+        """Same defaults as the reference extractors: a=0, b=len-1 (algorithms.py:691-696)."""
+        if isinstance(op, str):
+            op = _OPS[op]
+        a = 0 if window_min_index is None else int(window_min_index)
+        b = self.nb_samples - 1 if window_max_index is None else int(window_max_index)
+        idx = C.c_int(-1)
+        check(lib.dp_reduce_plan_add(self._h, int(chan), int(op), a, b, C.byref(idx)))
+        self._added.append((int(chan), idx.value))
+        return len(self._added) - 1
+
+    def finalize(self, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.DetprocessB200Error('no CUDA device: detprocess_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        check(lib.dp_reduce_plan_finalize(self._h, device.index or 0))
+        self.device = device
+        n = C.c_int()
+        check(lib.dp_reduce_plan_n_out(self._h, C.byref(n)))
+        self.n_out = n.value
+        self.columns = []
+        for chan, fi in self._added:
+            c = C.c_int()
+            check(lib.dp_reduce_plan_column(self._h, chan, fi, C.byref(c)))
+            self.columns.append(c.value)
+        self.finalized = True
+        return self
+
+    def column(self, handle):
+        return self.columns[handle]
+
+    def run(self, traces, out=None):
+        torch = _torch()
+        if not self.finalized:
+            raise _lib.DetprocessB200Error('plan not finalized')
+        if not traces.is_cuda or traces.dtype != torch.float64:
+            raise ValueError('run() takes float64 CUDA tensors')
+        if traces.ndim == 2 and self.n_chan == 1:
+            nev = traces.shape[0]
+        elif traces.ndim == 3 and traces.shape[1] == self.n_chan:
+            nev = traces.shape[0]
+        else:
+            raise ValueError('traces must be [n_events, n_chan, nb_samples]')
+        if traces.shape[-1] != self.nb_samples:
+            raise ValueError('trace length != plan nb_samples')
+        traces = traces.contiguous()
+        if out is None:
+            out = torch.empty((nev, self.n_out), dtype=torch.float64, device=traces.device)
+        check(lib.dp_window_reduce_batch(self._h, C.c_void_p(traces.data_ptr()), nev, self.nb_samples,
+                                         C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
+        return out
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(lib.dp_reduce_plan_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value

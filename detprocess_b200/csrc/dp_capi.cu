@@ -1,0 +1,621 @@
+// C-ABI of libdetprocess_b200.so (see include/detprocess_b200.h).
+// Host side: plan objects (one per reference qp.OFBase / per reduction feature set),
+// device-table upload, persistent-grid launches of the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/detprocess_b200.h"
+#include "dp_plan.hpp"
+#include "dp_reduce_plan.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define DP_CUDA(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(DP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t n = 0;
+};
+
+template <class V> int upload(std::vector<void*>& owned, const std::vector<V>& h, const V** out) {
+    void* d = nullptr;
+    const size_t bytes = std::max<size_t>(sizeof(V) * h.size(), 16);
+    DP_CUDA(cudaMalloc(&d, bytes));
+    owned.push_back(d);
+    if (!h.empty()) DP_CUDA(cudaMemcpy(d, h.data(), sizeof(V) * h.size(), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const V*>(d);
+    return DP_OK;
+}
+
+}  // namespace
+
+// ============================================================================ OF plan
+struct dp_of_plan {
+    int N = 0;
+    double fs = 0;
+    int n_chan = 0;
+    int precision = DP_PREC_F64;
+    double fcut = 10000.0;
+    std::vector<dpplan::Channel> chans;
+    bool finalized = false;
+    int device = 0;
+    dpplan::Geometry geom;
+    // device state
+    std::vector<void*> owned;
+    const void* d_chans = nullptr;
+    const void *tw1 = nullptr, *tw2 = nullptr, *twn = nullptr, *twp = nullptr;
+    void* scratch = nullptr;
+    long long scratch_per_cta = 0;
+    int grid_max = 0;
+    size_t smem = 0;
+    int n_out = 0;
+    std::vector<int> chan_out_base;
+    int nlow = 0;
+    double scale = 1.0;
+    int subtract_first = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    long long launches = 0;
+    // staging for dp_of1x1_batch_host
+    void* stage_dev[2] = {nullptr, nullptr};
+    double* stage_out[2] = {nullptr, nullptr};
+    long long stage_events = 0;
+    int stage_dtype = -1;
+    long long stage_stride = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+template <class T, int R1, int P> int of_setup_kernel(dp_of_plan* p) {
+    using K = DpOfKernel<T, R1, P>;
+    auto kern = dp_of_kernel<T, R1, P>;
+    p->smem = K::SMEM_BYTES;
+    DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
+    int occ = 0;
+    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::NT, K::SMEM_BYTES));
+    if (occ < 1) return fail(DP_ERR_CUDA, "OF kernel does not fit on an SM");
+    int sms = 0;
+    DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+    p->grid_max = sms * occ;
+    return DP_OK;
+}
+
+template <class T, int R1, int P> int of_launch_kernel(dp_of_plan* p, const DpOfParams<T>& prm, int grid, cudaStream_t st) {
+    dp_of_kernel<T, R1, P><<<grid, DpGeom<R1>::NT, p->smem, st>>>(prm);
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+#define DP_DISPATCH_R1(T, P, r1, FN, ...)                                   \
+    switch (r1) {                                                           \
+        case 2: return FN<T, 2, P>(__VA_ARGS__);                            \
+        case 4: return FN<T, 4, P>(__VA_ARGS__);                            \
+        case 8: return FN<T, 8, P>(__VA_ARGS__);                            \
+        case 16: return FN<T, 16, P>(__VA_ARGS__);                          \
+        case 32: return FN<T, 32, P>(__VA_ARGS__);                          \
+        default: return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");\
+    }
+
+template <class T> int of_setup(dp_of_plan* p) {
+    if (p->geom.P != 1) return fail(DP_ERR_UNSUPPORTED, "trace length needs the split (P=2) path, not built yet");
+    DP_DISPATCH_R1(T, 1, p->geom.R1, of_setup_kernel, p)
+}
+template <class T> int of_launch(dp_of_plan* p, const DpOfParams<T>& prm, int grid, cudaStream_t st) {
+    DP_DISPATCH_R1(T, 1, p->geom.R1, of_launch_kernel, p, prm, grid, st)
+}
+
+template <class T> int of_finalize(dp_of_plan* p) {
+    dpplan::DeviceTables<T> dt;
+    try {
+        dt = dpplan::build_tables<T>(p->geom, p->fs, p->chans, p->fcut, p->scale);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_INVALID, e.what());
+    }
+    p->nlow = dt.nlow;
+    int rc;
+    const cx<T>* d;
+    if ((rc = upload(p->owned, dt.tw1, &d))) return rc;
+    p->tw1 = d;
+    if ((rc = upload(p->owned, dt.tw2, &d))) return rc;
+    p->tw2 = d;
+    if ((rc = upload(p->owned, dt.twn, &d))) return rc;
+    p->twn = d;
+    if ((rc = upload(p->owned, dt.twp, &d))) return rc;
+    p->twp = d;
+    std::vector<DpChanDev<T>> cd(p->n_chan);
+    p->chan_out_base.assign(p->n_chan, 0);
+    int base = 0;
+    for (int c = 0; c < p->n_chan; ++c) {
+        DpChanDev<T>& dc = cd[c];
+        std::memset(&dc, 0, sizeof(dc));
+        const T* w;
+        if ((rc = upload(p->owned, dt.chans[c].wj, &w))) return rc;
+        dc.wj = w;
+        if ((rc = upload(p->owned, dt.chans[c].wj_low, &w))) return rc;
+        dc.wj_low = w;
+        dc.wj_nyq = dt.chans[c].wj_nyq;
+        dc.n_templ = (int)p->chans[c].templ.size();
+        dc.n_slots = (int)p->chans[c].fits.size();
+        dc.out_base = base;
+        p->chan_out_base[c] = base;
+        base += 1 + DP_SLOT_NOUT * dc.n_slots;
+        for (int i = 0; i < dc.n_templ; ++i) {
+            auto& h = dt.chans[c].templ[i];
+            const cx<T>* ph;
+            if ((rc = upload(p->owned, h.phi, &ph))) return rc;
+            dc.templ[i].phi = ph;
+            if ((rc = upload(p->owned, h.s_low, &ph))) return rc;
+            dc.templ[i].s_low = ph;
+            dc.templ[i].phi_nyq = h.phi_nyq;
+            dc.templ[i].norm = h.norm;
+            dc.templ[i].tsum = h.tsum;
+            dc.templ[i].pretrigger = h.pretrigger;
+        }
+        for (int i = 0; i < dc.n_slots; ++i) {
+            const auto& f = p->chans[c].fits[i];
+            dc.slots[i] = DpSlot{f.templ, f.lo, f.hi, f.outside};
+        }
+    }
+    p->n_out = base;
+    const DpChanDev<T>* dcd;
+    if ((rc = upload(p->owned, cd, &dcd))) return rc;
+    p->d_chans = dcd;
+    if ((rc = of_setup<T>(p))) return rc;
+    p->scratch_per_cta = 64LL * p->geom.NT;
+    DP_CUDA(cudaMalloc(&p->scratch, sizeof(cx<T>) * (size_t)p->scratch_per_cta * (size_t)p->grid_max));
+    p->owned.push_back(p->scratch);
+    return DP_OK;
+}
+
+template <class T>
+int of_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride, double* out_dev,
+           cudaStream_t st, bool timed) {
+    DpOfParams<T> prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.traces = traces_dev;
+    prm.row_stride = row_stride;
+    prm.n_rows = (int)(n_events * p->n_chan);
+    prm.n_chan = p->n_chan;
+    prm.chans = reinterpret_cast<const DpChanDev<T>*>(p->d_chans);
+    prm.tw1 = reinterpret_cast<const cx<T>*>(p->tw1);
+    prm.tw2 = reinterpret_cast<const cx<T>*>(p->tw2);
+    prm.twn = reinterpret_cast<const cx<T>*>(p->twn);
+    prm.twp = reinterpret_cast<const cx<T>*>(p->twp);
+    prm.scratch = reinterpret_cast<cx<T>*>(p->scratch);
+    prm.scratch_per_cta = p->scratch_per_cta;
+    prm.out = out_dev;
+    prm.n_out = p->n_out;
+    prm.nlow = p->nlow;
+    prm.scale = p->scale;
+    prm.subtract_first = p->subtract_first;
+    prm.in_dtype = in_dtype;
+    const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
+    if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
+    int rc = of_launch<T>(p, prm, grid, st);
+    if (rc) return rc;
+    if (timed) DP_CUDA(cudaEventRecord(p->ev1, st));
+    p->timed = timed;
+    p->launches += 1;
+    return DP_OK;
+}
+
+int of_check(const dp_of_plan* p, int chan) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (chan < 0 || chan >= p->n_chan) return fail(DP_ERR_INVALID, "channel index out of range");
+    return DP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dp_last_error(void) { return g_err.c_str(); }
+int dp_version(void) { return 100; }
+int dp_device_count(int* count) {
+    DP_CUDA(cudaGetDeviceCount(count));
+    return DP_OK;
+}
+
+int dp_of_plan_create(dp_of_plan** plan, int nb_samples, double sample_rate, int n_chan, int precision) {
+    if (!plan) return fail(DP_ERR_INVALID, "null plan pointer");
+    if (n_chan < 1) return fail(DP_ERR_INVALID, "n_chan must be >= 1");
+    if (!(sample_rate > 0)) return fail(DP_ERR_INVALID, "sample_rate must be > 0");
+    if (precision != DP_PREC_F64 && precision != DP_PREC_F32) return fail(DP_ERR_INVALID, "unknown precision");
+    auto p = std::make_unique<dp_of_plan>();
+    try {
+        p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_UNSUPPORTED, e.what());
+    }
+    p->N = nb_samples;
+    p->fs = sample_rate;
+    p->n_chan = n_chan;
+    p->precision = precision;
+    p->chans.resize(n_chan);
+    *plan = p.release();
+    return DP_OK;
+}
+
+void dp_of_plan_destroy(dp_of_plan* p) {
+    if (!p) return;
+    for (void* d : p->owned) cudaFree(d);
+    for (int i = 0; i < 2; ++i) {
+        if (p->stage_dev[i]) cudaFree(p->stage_dev[i]);
+        if (p->stage_out[i]) cudaFree(p->stage_out[i]);
+        if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+    }
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+int dp_of_plan_set_psd(dp_of_plan* p, int chan, const double* psd, int coupling_ac) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    if (!psd) return fail(DP_ERR_INVALID, "null psd");
+    auto& ch = p->chans[chan];
+    if (!ch.templ.empty()) return fail(DP_ERR_STATE, "set the psd before adding templates");
+    ch.J.assign(psd, psd + p->N);
+    for (int i = 0; i < p->N; ++i)
+        if (!(ch.J[i] > 0)) return fail(DP_ERR_INVALID, "psd must be strictly positive");
+    if (coupling_ac) ch.J[0] = std::numeric_limits<double>::infinity();
+    return DP_OK;
+}
+
+int dp_of_plan_add_template(dp_of_plan* p, int chan, const double* templ, int pretrigger_samples, int integralnorm,
+                            int* templ_index) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    if (!templ) return fail(DP_ERR_INVALID, "null template");
+    auto& ch = p->chans[chan];
+    if ((int)ch.J.size() != p->N) return fail(DP_ERR_STATE, "set the psd before adding templates");
+    if ((int)ch.templ.size() >= DP_MAX_TEMPLATES) return fail(DP_ERR_UNSUPPORTED, "too many templates for one channel");
+    if (pretrigger_samples < 0 || pretrigger_samples >= p->N) return fail(DP_ERR_INVALID, "pretrigger_samples out of range");
+    dpplan::Template tp;
+    tp.trace.assign(templ, templ + p->N);
+    tp.pretrigger = pretrigger_samples;
+    tp.integralnorm = integralnorm != 0;
+    dpplan::finalize_template(tp, ch.J, p->fs);
+    if (!(tp.norm > 0)) return fail(DP_ERR_INVALID, "template has zero optimal-filter norm");
+    ch.templ.push_back(std::move(tp));
+    if (templ_index) *templ_index = (int)ch.templ.size() - 1;
+    return DP_OK;
+}
+
+int dp_of_plan_add_fit(dp_of_plan* p, int chan, int templ_index, int window_lo, int window_hi, int outside, int* fit_index) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    auto& ch = p->chans[chan];
+    if (templ_index < 0 || templ_index >= (int)ch.templ.size()) return fail(DP_ERR_INVALID, "template index out of range");
+    if ((int)ch.fits.size() >= DP_MAX_SLOTS) return fail(DP_ERR_UNSUPPORTED, "too many fits for one channel");
+    window_lo = std::min(std::max(window_lo, 0), p->N);
+    window_hi = std::min(std::max(window_hi, 0), p->N);
+    const int ncand = outside ? p->N - std::max(0, window_hi - window_lo) : window_hi - window_lo;
+    if (ncand <= 0) return fail(DP_ERR_INVALID, "empty OF delay window");
+    ch.fits.push_back(dpplan::Fit{templ_index, window_lo, window_hi, outside ? 1 : 0});
+    if (fit_index) *fit_index = (int)ch.fits.size() - 1;
+    return DP_OK;
+}
+
+int dp_of_plan_set_lowchi2_fcutoff(dp_of_plan* p, double fcutoff_hz) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    p->fcut = fcutoff_hz;
+    return DP_OK;
+}
+
+int dp_of_plan_finalize(dp_of_plan* p, int device) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    bool all_ac = true;
+    double jsum = 0;
+    long long jn = 0;
+    for (auto& ch : p->chans) {
+        if ((int)ch.J.size() != p->N) return fail(DP_ERR_STATE, "a channel has no psd");
+        if (ch.templ.empty()) return fail(DP_ERR_STATE, "a channel has no template");
+        if (std::isfinite(ch.J[0])) all_ac = false;
+        for (int i = 1; i < p->N; ++i)
+            if (std::isfinite(ch.J[i])) {
+                jsum += ch.J[i];
+                ++jn;
+            }
+    }
+    p->device = device;
+    DP_CUDA(cudaSetDevice(device));
+    if (p->precision == DP_PREC_F32) {
+        // power-of-two pre-scale so fp32 sees O(1) samples; exact, undone in the tables
+        const double rms = std::sqrt(std::max(jsum / std::max<long long>(jn, 1) * p->fs, 1e-300));
+        p->scale = std::exp2(-std::round(std::log2(rms)));
+        p->subtract_first = all_ac ? 1 : 0;
+    } else {
+        p->scale = 1.0;
+        p->subtract_first = 0;
+    }
+    int rc = (p->precision == DP_PREC_F32) ? of_finalize<float>(p) : of_finalize<double>(p);
+    if (rc) return rc;
+    DP_CUDA(cudaEventCreate(&p->ev0));
+    DP_CUDA(cudaEventCreate(&p->ev1));
+    p->finalized = true;
+    return DP_OK;
+}
+
+int dp_of_plan_n_out(const dp_of_plan* p, int* n_out) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    *n_out = p->n_out;
+    return DP_OK;
+}
+int dp_of_plan_chi0_offset(const dp_of_plan* p, int chan, int* offset) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (!p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    *offset = p->chan_out_base[chan];
+    return DP_OK;
+}
+int dp_of_plan_fit_offset(const dp_of_plan* p, int chan, int fit_index, int* offset) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (!p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (fit_index < 0 || fit_index >= (int)p->chans[chan].fits.size()) return fail(DP_ERR_INVALID, "fit index out of range");
+    *offset = p->chan_out_base[chan] + 1 + DP_SLOT_NOUT * fit_index;
+    return DP_OK;
+}
+int dp_of_plan_get_phi(const dp_of_plan* p, int chan, int ti, double* out) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (ti < 0 || ti >= (int)p->chans[chan].templ.size()) return fail(DP_ERR_INVALID, "template index out of range");
+    const auto& phi = p->chans[chan].templ[ti].phi;
+    for (int i = 0; i < p->N; ++i) {
+        out[2 * i] = phi[i].real();
+        out[2 * i + 1] = phi[i].imag();
+    }
+    return DP_OK;
+}
+int dp_of_plan_get_template_fft(const dp_of_plan* p, int chan, int ti, double* out) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (ti < 0 || ti >= (int)p->chans[chan].templ.size()) return fail(DP_ERR_INVALID, "template index out of range");
+    const auto& s = p->chans[chan].templ[ti].s;
+    for (int i = 0; i < p->N; ++i) {
+        out[2 * i] = s[i].real();
+        out[2 * i + 1] = s[i].imag();
+    }
+    return DP_OK;
+}
+int dp_of_plan_get_norm(const dp_of_plan* p, int chan, int ti, double* norm) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (ti < 0 || ti >= (int)p->chans[chan].templ.size()) return fail(DP_ERR_INVALID, "template index out of range");
+    *norm = p->chans[chan].templ[ti].norm;
+    return DP_OK;
+}
+
+int dp_of1x1_batch(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride,
+                   double* out_dev, void* stream) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
+    if (n_events == 0) return DP_OK;
+    if (!traces_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
+    if (row_stride < p->N || (row_stride & 1)) return fail(DP_ERR_INVALID, "row_stride must be even and >= nb_samples");
+    const size_t esz = in_dtype == DP_IN_F64 ? 8 : (in_dtype == DP_IN_F32 ? 4 : 2);
+    if ((reinterpret_cast<uintptr_t>(traces_dev) % (2 * esz)) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
+    if (n_events * p->n_chan > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p->precision == DP_PREC_F32) return of_run<float>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, true);
+    return of_run<double>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, true);
+}
+
+int dp_of_plan_last_kernel_ms(dp_of_plan* p, float* ms) {
+    if (!p || !p->finalized || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
+    DP_CUDA(cudaEventSynchronize(p->ev1));
+    DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return DP_OK;
+}
+int dp_of_plan_launch_count(const dp_of_plan* p, long long* n) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    *n = p->launches;
+    return DP_OK;
+}
+
+int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, long long n_events, long long row_stride,
+                        double* out_host) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (n_events <= 0) return n_events == 0 ? DP_OK : fail(DP_ERR_INVALID, "negative n_events");
+    if (!traces_host || !out_host) return fail(DP_ERR_INVALID, "null buffer");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
+    if (row_stride < p->N || (row_stride & 1)) return fail(DP_ERR_INVALID, "row_stride must be even and >= nb_samples");
+    DP_CUDA(cudaSetDevice(p->device));
+    const size_t esz = in_dtype == DP_IN_F64 ? 8 : (in_dtype == DP_IN_F32 ? 4 : 2);
+    const size_t ev_bytes = (size_t)p->n_chan * (size_t)row_stride * esz;
+    // chunk: ~256 MiB of traces per stage
+    long long chunk = std::max<long long>(1, (256LL << 20) / (long long)ev_bytes);
+    chunk = std::min(chunk, n_events);
+    if (p->stage_events < chunk || p->stage_dtype != in_dtype || p->stage_stride != row_stride) {
+        for (int i = 0; i < 2; ++i) {
+            if (p->stage_dev[i]) cudaFree(p->stage_dev[i]);
+            if (p->stage_out[i]) cudaFree(p->stage_out[i]);
+            p->stage_dev[i] = nullptr;
+            p->stage_out[i] = nullptr;
+            DP_CUDA(cudaMalloc(&p->stage_dev[i], ev_bytes * (size_t)chunk));
+            DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->stage_out[i]), sizeof(double) * (size_t)p->n_out * (size_t)chunk));
+            if (!p->streams[i]) DP_CUDA(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+        }
+        p->stage_events = chunk;
+        p->stage_dtype = in_dtype;
+        p->stage_stride = row_stride;
+    }
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(traces_host);
+    int k = 0;
+    for (long long e0 = 0; e0 < n_events; e0 += chunk, k ^= 1) {
+        const long long ne = std::min(chunk, n_events - e0);
+        cudaStream_t st = p->streams[k];
+        DP_CUDA(cudaMemcpyAsync(p->stage_dev[k], src + (size_t)e0 * ev_bytes, ev_bytes * (size_t)ne, cudaMemcpyHostToDevice, st));
+        int rc = (p->precision == DP_PREC_F32)
+                     ? of_run<float>(p, p->stage_dev[k], in_dtype, ne, row_stride, p->stage_out[k], st, false)
+                     : of_run<double>(p, p->stage_dev[k], in_dtype, ne, row_stride, p->stage_out[k], st, false);
+        if (rc) return rc;
+        DP_CUDA(cudaMemcpyAsync(out_host + (size_t)e0 * p->n_out, p->stage_out[k], sizeof(double) * (size_t)p->n_out * (size_t)ne,
+                                cudaMemcpyDeviceToHost, st));
+    }
+    DP_CUDA(cudaStreamSynchronize(p->streams[0]));
+    DP_CUDA(cudaStreamSynchronize(p->streams[1]));
+    return DP_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================= reduce plan
+struct dp_reduce_plan {
+    dpred::Plan plan;
+    int n_chan = 0;
+    bool finalized = false;
+    int device = 0;
+    std::vector<void*> owned;
+    const DpRedChan* d_chans = nullptr;
+    const DpLeaf* d_leaves = nullptr;
+    const DpNode* d_nodes = nullptr;
+    const int* d_level_off = nullptr;
+    const DpRedFeat* d_feats = nullptr;
+    int grid_max = 0;
+    size_t smem = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+extern "C" {
+
+int dp_reduce_plan_create(dp_reduce_plan** plan, int nb_samples, double sample_rate, int n_chan) {
+    if (!plan) return fail(DP_ERR_INVALID, "null plan pointer");
+    if (nb_samples < 1 || n_chan < 1 || !(sample_rate > 0)) return fail(DP_ERR_INVALID, "bad plan arguments");
+    auto p = std::make_unique<dp_reduce_plan>();
+    p->plan.nb_samples = nb_samples;
+    p->plan.fs = sample_rate;
+    p->plan.chan_feats.resize(n_chan);
+    p->n_chan = n_chan;
+    *plan = p.release();
+    return DP_OK;
+}
+void dp_reduce_plan_destroy(dp_reduce_plan* p) {
+    if (!p) return;
+    for (void* d : p->owned) cudaFree(d);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+int dp_reduce_plan_add(dp_reduce_plan* p, int chan, int op, int window_lo, int window_hi, int* feat_index) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    if (chan < 0 || chan >= p->n_chan) return fail(DP_ERR_INVALID, "channel index out of range");
+    if (op < DP_OP_BASELINE || op > DP_OP_MINIMUM) return fail(DP_ERR_INVALID, "unknown op");
+    // python slice semantics of trace[a:b]
+    const int n = p->plan.nb_samples;
+    auto clampi = [n](int v) { return v < 0 ? std::max(0, v + n) : std::min(v, n); };
+    int lo = clampi(window_lo), hi = clampi(window_hi);
+    if (hi < lo) hi = lo;
+    if ((op == DP_OP_MAXIMUM || op == DP_OP_MINIMUM) && hi == lo)
+        return fail(DP_ERR_INVALID, "zero-size array to reduction operation maximum/minimum which has no identity");
+    p->plan.chan_feats[chan].push_back(dpred::Feat{op, lo, hi});
+    if (feat_index) *feat_index = (int)p->plan.chan_feats[chan].size() - 1;
+    return DP_OK;
+}
+int dp_reduce_plan_column(const dp_reduce_plan* p, int chan, int feat_index, int* column) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (chan < 0 || chan >= p->n_chan) return fail(DP_ERR_INVALID, "channel index out of range");
+    if (feat_index < 0 || feat_index >= (int)p->plan.chan_feats[chan].size()) return fail(DP_ERR_INVALID, "feature index out of range");
+    int col = 0;
+    for (int c = 0; c < chan; ++c) col += (int)p->plan.chan_feats[c].size();
+    *column = col + feat_index;
+    return DP_OK;
+}
+int dp_reduce_plan_finalize(dp_reduce_plan* p, int device) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    try {
+        dpred::finalize(p->plan);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_INVALID, e.what());
+    }
+    p->device = device;
+    DP_CUDA(cudaSetDevice(device));
+    int rc;
+    if ((rc = upload(p->owned, p->plan.chans, &p->d_chans))) return rc;
+    if ((rc = upload(p->owned, p->plan.leaves, &p->d_leaves))) return rc;
+    if ((rc = upload(p->owned, p->plan.nodes, &p->d_nodes))) return rc;
+    if ((rc = upload(p->owned, p->plan.level_off, &p->d_level_off))) return rc;
+    if ((rc = upload(p->owned, p->plan.feats, &p->d_feats))) return rc;
+    p->smem = sizeof(double) * (size_t)(p->plan.max_nodes + 64);
+    int occ = 0, sms = 0;
+    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_reduce_kernel<256>, 256, p->smem));
+    DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    p->grid_max = sms * std::max(occ, 1);
+    DP_CUDA(cudaEventCreate(&p->ev0));
+    DP_CUDA(cudaEventCreate(&p->ev1));
+    p->finalized = true;
+    return DP_OK;
+}
+int dp_reduce_plan_n_out(const dp_reduce_plan* p, int* n_out) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    *n_out = p->plan.n_out;
+    return DP_OK;
+}
+int dp_window_reduce_batch(dp_reduce_plan* p, const double* traces_dev, long long n_events, long long row_stride,
+                           double* out_dev, void* stream) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
+    if (n_events == 0 || p->plan.n_out == 0) return DP_OK;
+    if (!traces_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if (row_stride < p->plan.nb_samples) return fail(DP_ERR_INVALID, "row_stride < nb_samples");
+    if (n_events * p->n_chan > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    DpReduceParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.traces = traces_dev;
+    prm.row_stride = row_stride;
+    prm.n_rows = (int)(n_events * p->n_chan);
+    prm.n_chan = p->n_chan;
+    prm.chans = p->d_chans;
+    prm.leaves = p->d_leaves;
+    prm.nodes = p->d_nodes;
+    prm.level_off = p->d_level_off;
+    prm.feats = p->d_feats;
+    prm.out = out_dev;
+    prm.n_out = p->plan.n_out;
+    prm.fs = p->plan.fs;
+    prm.max_nodes = p->plan.max_nodes;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
+    DP_CUDA(cudaEventRecord(p->ev0, st));
+    dp_reduce_kernel<256><<<grid, 256, p->smem, st>>>(prm);
+    DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaEventRecord(p->ev1, st));
+    p->timed = true;
+    return DP_OK;
+}
+int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* p, float* ms) {
+    if (!p || !p->finalized || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
+    DP_CUDA(cudaEventSynchronize(p->ev1));
+    DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return DP_OK;
+}
+
+}  // extern "C"

@@ -24,6 +24,18 @@ template <class T> DP_HD cx<T> cmuli(cx<T> a) { return cx<T>{-a.im, a.re}; }    
 template <class T> DP_HD cx<T> cmulni(cx<T> a) { return cx<T>{a.im, -a.re}; }   // -i*a
 template <class T> DP_HD T cnorm2(cx<T> a) { return dp_fma(a.re, a.re, a.im * a.im); }
 
+// read-only-path loads
+template <class T> DP_DEV cx<T> dp_ldg(const cx<T>* p) {
+#ifdef DP_HOST_EMU
+    return *p;
+#else
+    const typename dp_vec2<T>::type v = __ldg(reinterpret_cast<const typename dp_vec2<T>::type*>(p));
+    return cx<T>{v.x, v.y};
+#endif
+}
+DP_DEV float dp_ldg(const float* p) { return __ldg(p); }
+DP_DEV double dp_ldg(const double* p) { return __ldg(p); }
+
 // --------------------------------------------------------- compile-time twiddles
 // cos(2*pi*j/64), j = 0..16
 DP_HD constexpr double dp_cos64_q(int j) {
@@ -110,33 +122,47 @@ template <int SIGN, class T> struct dp_dft<2, SIGN, T> {
 };
 
 // ------------------------------------------------------------- twiddle powers
-// p[k] = w^k for k = 0..R-1 with a log-depth product tree (error ~ log2(R) ulp).
-template <int R, class T> struct dp_powers {
-    template <int K> static DP_HD void fill(cx<T> (&p)[R]) {
-        if constexpr (K < R) {
-            if constexpr (K % 2 == 0) {
-                const cx<T> h = p[K / 2];
-                p[K] = cx<T>{dp_fma(h.re, h.re, -(h.im * h.im)), (T)2 * h.re * h.im};
-            } else {
-                p[K] = cmul(p[K / 2], p[K - K / 2]);
+// x[k] *= w^k, k = 1..R-1 (CONJ: conj(w)^k).  Powers are built level by level,
+// p[k] = p[k/2] * p[k - k/2] (log-depth => ~log2(R) ulp), and applied as soon as they
+// exist; only the previous level (<= R/4 + 1 values) stays live, the last level is
+// never stored -- this keeps the radix-32 passes inside the register budget.
+template <int R, int LO, class T> struct dp_tw_level {
+    // prev holds p[LO/2 .. LO] (LO/2 + 1 values); this level produces p[LO .. 2*LO-1]
+    static DP_HD void run(cx<T> (&x)[R], const cx<T> (&prev)[LO / 2 + 1]) {
+        if constexpr (2 * LO >= R) {
+            // last level: compute, apply, forget
+#pragma unroll
+            for (int k = LO; k < R; ++k) {
+                const int h = k / 2, g = k - h;
+                const cx<T> a = prev[h - LO / 2], b = prev[g - LO / 2];
+                const cx<T> p = (h == g) ? cx<T>{dp_fma(a.re, a.re, -(a.im * a.im)), (T)2 * a.re * a.im} : cmul(a, b);
+                x[k] = cmul(x[k], p);
             }
-            fill<K + 1>(p);
+        } else {
+            cx<T> cur[LO + 1];  // p[LO .. 2*LO]
+#pragma unroll
+            for (int k = LO; k <= 2 * LO; ++k) {
+                const int h = k / 2, g = k - h;
+                const cx<T> a = prev[h - LO / 2], b = prev[g - LO / 2];
+                cur[k - LO] = (h == g) ? cx<T>{dp_fma(a.re, a.re, -(a.im * a.im)), (T)2 * a.re * a.im} : cmul(a, b);
+            }
+#pragma unroll
+            for (int k = LO; k < 2 * LO; ++k) x[k] = cmul(x[k], cur[k - LO]);
+            dp_tw_level<R, 2 * LO, T>::run(x, cur);
         }
-    }
-    static DP_HD void run(cx<T> w, cx<T> (&p)[R]) {
-        p[0] = cx<T>{(T)1, (T)0};
-        if constexpr (R > 1) p[1] = w;
-        fill<2>(p);
     }
 };
 
-// x[k] *= w^k (k = 1..R-1);  CONJ: x[k] *= conj(w)^k
 template <int R, bool CONJ, class T> DP_HD void dp_twiddle(cx<T> (&x)[R], cx<T> w) {
     if constexpr (R > 1) {
         if (CONJ) w.im = -w.im;
-        cx<T> p[R];
-        dp_powers<R, T>::run(w, p);
-#pragma unroll
-        for (int k = 1; k < R; ++k) x[k] = cmul(x[k], p[k]);
+        x[1] = cmul(x[1], w);
+        if constexpr (R > 2) {
+            // level LO = 2 needs prev = p[1..2]
+            cx<T> prev[2];
+            prev[0] = w;
+            prev[1] = cx<T>{dp_fma(w.re, w.re, -(w.im * w.im)), (T)2 * w.re * w.im};
+            dp_tw_level<R, 2, T>::run(x, prev);
+        }
     }
 }

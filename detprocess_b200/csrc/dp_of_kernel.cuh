@@ -192,7 +192,7 @@ DP_DEV void dp_fwd_subfft(const void* row, int in_dtype, int p, double x0, doubl
 #pragma unroll
         for (int n = 0; n < R1; ++n) v[n] = dp_load_pair<T>(row, in_dtype, (long long)P * (m + n * 512) + p, x0, sc);
         dp_dft<R1, -1, T>::run(v);
-        dp_twiddle<R1, false, T>(v, __ldg(tw1 + m));
+        dp_twiddle<R1, false, T>(v, dp_ldg(tw1 + m));
 #pragma unroll
         for (int k = 0; k < R1; ++k) buf[G::phys(k * 512 + m)] = v[k];
     }
@@ -204,7 +204,7 @@ DP_DEV void dp_fwd_subfft(const void* row, int in_dtype, int p, double x0, doubl
 #pragma unroll
         for (int n = 0; n < 32; ++n) v[n] = buf[G::phys(base + n * 16)];
         dp_dft<32, -1, T>::run(v);
-        dp_twiddle<32, false, T>(v, __ldg(tw2 + (tid & 15)));
+        dp_twiddle<32, false, T>(v, dp_ldg(tw2 + (tid & 15)));
 #pragma unroll
         for (int k = 0; k < 32; ++k) buf[G::phys(base + k * 16)] = v[k];
     }
@@ -242,7 +242,7 @@ DP_DEV void dp_inv_subfft(cx<T>* buf, const cx<T>* DP_RESTRICT tw1, const cx<T>*
         cx<T> v[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = buf[G::phys(base + k * 16)];
-        dp_twiddle<32, true, T>(v, __ldg(tw2 + (tid & 15)));
+        dp_twiddle<32, true, T>(v, dp_ldg(tw2 + (tid & 15)));
         dp_dft<32, +1, T>::run(v);
 #pragma unroll
         for (int n = 0; n < 32; ++n) buf[G::phys(base + n * 16)] = v[n];
@@ -254,7 +254,7 @@ DP_DEV void dp_inv_subfft(cx<T>* buf, const cx<T>* DP_RESTRICT tw1, const cx<T>*
         cx<T> v[R1];
 #pragma unroll
         for (int k = 0; k < R1; ++k) v[k] = buf[G::phys(k * 512 + m)];
-        dp_twiddle<R1, true, T>(v, __ldg(tw1 + m));
+        dp_twiddle<R1, true, T>(v, dp_ldg(tw1 + m));
         dp_dft<R1, +1, T>::run(v);
 #pragma unroll
         for (int n = 0; n < R1; ++n) sink(m + n * 512, v[n]);
@@ -314,7 +314,7 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
     const int tid = threadIdx.x;
     int K12, bA, bB;
     G::map(tid, K12, bA, bB);
-    const cx<T> wn = __ldg(prm.twn + tid);  // exp(-2 pi i K12 / N)
+    const cx<T> wn = dp_ldg(prm.twn + tid);  // exp(-2 pi i K12 / N)
     cx<T>* scr = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
 
     for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
@@ -341,8 +341,8 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
     {                                                                                                    \
         cx<T> Xk, Xm;                                                                                    \
         dp_untangle(za[r], zb[15 - r], cmul(wn, dp_w64<T, 2 * r, -1>()), Xk, Xm);                        \
-        chi = dp_fma(__ldg(ch.wj + r * NT + tid), cnorm2(Xk), chi);                                      \
-        chi = dp_fma(__ldg(ch.wj + (16 + 15 - r) * NT + tid), cnorm2(Xm), chi);                          \
+        chi = dp_fma(dp_ldg(ch.wj + r * NT + tid), cnorm2(Xk), chi);                                      \
+        chi = dp_fma(dp_ldg(ch.wj + (16 + 15 - r) * NT + tid), cnorm2(Xm), chi);                          \
         za[r] = Xk;                                                                                      \
         zb[15 - r] = Xm;                                                                                 \
     }
@@ -356,9 +356,9 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
     {                                                                                                    \
         cx<T> Xk, Xm;                                                                                    \
         dp_untangle(za[r], za[rp], dp_w64<T, 2 * r, -1>(), Xk, Xm);                                      \
-        chi = dp_fma(__ldg(ch.wj + r * NT), cnorm2(Xk), chi);                                            \
+        chi = dp_fma(dp_ldg(ch.wj + r * NT), cnorm2(Xk), chi);                                            \
         if (r == 0) chi = dp_fma(ch.wj_nyq, cnorm2(Xm), chi);                                            \
-        else if (r != rp) chi = dp_fma(__ldg(ch.wj + rp * NT), cnorm2(Xm), chi);                         \
+        else if (r != rp) chi = dp_fma(dp_ldg(ch.wj + rp * NT), cnorm2(Xm), chi);                         \
         za[r] = Xk;                                                                                      \
         if (r != rp) za[rp] = Xm;                                                                        \
         if (r == 0) sm.stash[DP_NLOW_MAX - 1] = Xm; /* Nyquist X kept for the filter step */             \
@@ -370,8 +370,8 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
     {                                                                                                    \
         cx<T> Xk, Xm;                                                                                    \
         dp_untangle(zb[r], zb[15 - r], dp_w64<T, 1 + 2 * r, -1>(), Xk, Xm);                              \
-        chi = dp_fma(__ldg(ch.wj + (16 + r) * NT), cnorm2(Xk), chi);                                     \
-        chi = dp_fma(__ldg(ch.wj + (16 + 15 - r) * NT), cnorm2(Xm), chi);                                \
+        chi = dp_fma(dp_ldg(ch.wj + (16 + r) * NT), cnorm2(Xk), chi);                                     \
+        chi = dp_fma(dp_ldg(ch.wj + (16 + 15 - r) * NT), cnorm2(Xm), chi);                                \
         zb[r] = Xk;                                                                                      \
         zb[15 - r] = Xm;                                                                                 \
     }
@@ -409,8 +409,8 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
                 if (tid != 0) {
 #define DP_FP(r)                                                                                         \
     {                                                                                                    \
-        const cx<T> Fk = cmul(__ldg(tp.phi + r * NT + tid), za[r]);                                      \
-        const cx<T> Fm = cmul(__ldg(tp.phi + (16 + 15 - r) * NT + tid), zb[15 - r]);                     \
+        const cx<T> Fk = cmul(dp_ldg(tp.phi + r * NT + tid), za[r]);                                      \
+        const cx<T> Fm = cmul(dp_ldg(tp.phi + (16 + 15 - r) * NT + tid), zb[15 - r]);                     \
         dp_retangle(Fk, Fm, cmul(wn, dp_w64<T, 2 * r, -1>()), za[r], zb[15 - r]);                        \
     }
                     DP_FP(0) DP_FP(1) DP_FP(2) DP_FP(3) DP_FP(4) DP_FP(5) DP_FP(6) DP_FP(7)
@@ -419,9 +419,9 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
                 } else {
 #define DP_FA(r, rp)                                                                                     \
     {                                                                                                    \
-        const cx<T> Fk = cmul(__ldg(tp.phi + r * NT), za[r]);                                            \
+        const cx<T> Fk = cmul(dp_ldg(tp.phi + r * NT), za[r]);                                            \
         const cx<T> Fm = (r == 0) ? cmul(tp.phi_nyq, sm.stash[DP_NLOW_MAX - 1])                          \
-                                  : cmul(__ldg(tp.phi + rp * NT), za[rp]);                               \
+                                  : cmul(dp_ldg(tp.phi + rp * NT), za[rp]);                               \
         cx<T> Ck, Cm;                                                                                    \
         dp_retangle(Fk, Fm, dp_w64<T, 2 * r, -1>(), Ck, Cm);                                             \
         za[r] = Ck;                                                                                      \
@@ -432,8 +432,8 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
 #undef DP_FA
 #define DP_FB(r)                                                                                         \
     {                                                                                                    \
-        const cx<T> Fk = cmul(__ldg(tp.phi + (16 + r) * NT), zb[r]);                                     \
-        const cx<T> Fm = cmul(__ldg(tp.phi + (16 + 15 - r) * NT), zb[15 - r]);                           \
+        const cx<T> Fk = cmul(dp_ldg(tp.phi + (16 + r) * NT), zb[r]);                                     \
+        const cx<T> Fm = cmul(dp_ldg(tp.phi + (16 + 15 - r) * NT), zb[15 - r]);                           \
         dp_retangle(Fk, Fm, dp_w64<T, 1 + 2 * r, -1>(), zb[r], zb[15 - r]);                              \
     }
                     DP_FB(0) DP_FB(1) DP_FB(2) DP_FB(3) DP_FB(4) DP_FB(5) DP_FB(6) DP_FB(7)
@@ -495,11 +495,11 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
                         cs = (T)c_;
                     }
                     const cx<T> e = cx<T>{cs, -sn};
-                    const cx<T> S = __ldg(tp.s_low + k);
+                    const cx<T> S = dp_ldg(tp.s_low + k);
                     const cx<T> mdl = cmul(e, S);
                     const cx<T> X = sm.stash[k];
                     const cx<T> R = cx<T>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
-                    part += (double)(__ldg(ch.wj_low + k) * cnorm2(R));
+                    part += (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
                 }
                 const double low = dp_block_sum<NT>(part, sm.red);
                 if (tid == 0) {

@@ -1,0 +1,161 @@
+// Windowed trace reductions, bit-exact with numpy float64:
+//   mean  -> np.mean(trace[a:b])            reference detprocess/core/algorithms.py:698
+//   trapz -> np.trapz(trace[a:b]) / fs      reference detprocess/core/algorithms.py:759
+//   max   -> np.amax(trace[a:b])            reference detprocess/core/algorithms.py:818
+//   min   -> np.amin(trace[a:b])            reference detprocess/core/algorithms.py:879
+//
+// numpy sums float64 with pairwise_sum_DOUBLE: recursive halving (left half rounded
+// down to a multiple of 8) until <= 128 elements, then 8 strided accumulators
+// combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail.  The host
+// plan (dp_reduce_plan.hpp) flattens that recursion into leaves + a combine tree;
+// here 8 lanes play the 8 accumulators of one leaf and the tree is evaluated level
+// by level, so every addition happens in numpy's order with numpy's operands.
+// HBM-bound: each window sample is read once, coalesced 64 B per leaf row.
+#pragma once
+#include "dp_platform.cuh"
+
+enum { DP_OP_MEAN = 0, DP_OP_TRAPZ = 1, DP_OP_MAX = 2, DP_OP_MIN = 3 };
+
+struct DpLeaf {
+    int off;   // first element (absolute sample index)
+    int len;   // number of summed elements
+    int node;  // node slot receiving the leaf sum
+    int trapz; // element i is (y[i+1] + y[i]) / 2
+};
+struct DpNode {
+    int left, right, out, pad;
+};
+struct DpRedFeat {
+    int op, lo, hi, root;  // root node slot (sum ops)
+    int out;               // column in the event's output row
+    int n;                 // divisor for mean
+    int pad0, pad1;
+};
+struct DpRedChan {
+    int leaf_begin, leaf_end;
+    int level_begin, level_end;  // range in level_off[] (level l spans nodes level_off[l]..level_off[l+1])
+    int feat_begin, feat_end;
+    int pad0, pad1;
+};
+struct DpReduceParams {
+    const double* traces;
+    long long row_stride;
+    int n_rows, n_chan;
+    const DpRedChan* chans;
+    const DpLeaf* leaves;
+    const DpNode* nodes;
+    const int* level_off;
+    const DpRedFeat* feats;
+    double* out;  // [n_events][n_out]
+    int n_out;
+    double fs;
+    int max_nodes;  // smem doubles
+};
+
+#ifndef DP_HOST_EMU
+DP_DEV double dp_add_rn(double a, double b) { return __dadd_rn(a, b); }
+#else
+DP_DEV double dp_add_rn(double a, double b) { return a + b; }
+#endif
+
+DP_DEV double dp_red_elem(const double* DP_RESTRICT x, int i, int trapz) {
+    const double a = __ldg(x + i);
+    if (!trapz) return a;
+    const double b = __ldg(x + i + 1);
+    return dp_add_rn(b, a) * 0.5;  // exact halving == numpy's / 2.0
+}
+
+template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* nodeval, double* red) {
+    const int tid = threadIdx.x;
+    const int lane8 = tid & 7;
+    const int grp = tid >> 3;
+    constexpr int NG = NT / 8;
+    for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
+        const int chan = row % prm.n_chan;
+        const int ev = row / prm.n_chan;
+        const DpRedChan ch = prm.chans[chan];
+        const double* DP_RESTRICT x = prm.traces + (long long)row * prm.row_stride;
+        // ---- leaves: 8 lanes = numpy's 8 accumulators -------------------------------
+        // (loop bounds are CTA-uniform so the shuffles below are never divergent)
+        for (int L0 = ch.leaf_begin; L0 < ch.leaf_end; L0 += NG) {
+            const int L = L0 + grp;
+            const bool valid = L < ch.leaf_end;
+            DpLeaf lf = DpLeaf{0, 0, 0, 0};
+            if (valid) lf = prm.leaves[L];
+            const bool small = lf.len < 8;
+            const int nfull = small ? 0 : lf.len - (lf.len & 7);
+            double r = 0.0;
+            if (nfull > 0) {
+                r = dp_red_elem(x, lf.off + lane8, lf.trapz);
+                for (int i = 8; i < nfull; i += 8) r = dp_add_rn(r, dp_red_elem(x, lf.off + i + lane8, lf.trapz));
+            }
+            r = dp_add_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+            r = dp_add_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+            r = dp_add_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+            double res = small ? 0.0 : r;
+            for (int i = nfull; i < lf.len; ++i) res = dp_add_rn(res, dp_red_elem(x, lf.off + i, lf.trapz));
+            if (valid && lane8 == 0) nodeval[lf.node] = res;
+        }
+        __syncthreads();
+        // ---- combine tree, one level per barrier --------------------------------------
+        for (int l = ch.level_begin; l < ch.level_end; ++l) {
+            const int b = prm.level_off[l], e = prm.level_off[l + 1];
+            for (int i = b + tid; i < e; i += NT) {
+                const DpNode nd = prm.nodes[i];
+                nodeval[nd.out] = dp_add_rn(nodeval[nd.left], nodeval[nd.right]);
+            }
+            __syncthreads();
+        }
+        // ---- features ------------------------------------------------------------------
+        for (int f = ch.feat_begin; f < ch.feat_end; ++f) {
+            const DpRedFeat ft = prm.feats[f];
+            double* o = prm.out + (long long)ev * prm.n_out + ft.out;
+            if (ft.op == DP_OP_MEAN) {
+                if (tid == 0) *o = nodeval[ft.root] / (double)ft.n;
+            } else if (ft.op == DP_OP_TRAPZ) {
+                if (tid == 0) *o = nodeval[ft.root] / prm.fs;
+            } else {
+                // max / min with numpy NaN propagation
+                const bool is_max = ft.op == DP_OP_MAX;
+                double m = is_max ? -INFINITY : INFINITY;
+                int has_nan = 0;
+                for (int i = ft.lo + tid; i < ft.hi; i += NT) {
+                    const double v = __ldg(x + i);
+                    if (v != v) has_nan = 1;
+                    m = is_max ? fmax(m, v) : fmin(m, v);
+                }
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                    const double mo = __shfl_xor_sync(0xffffffffu, m, o2);
+                    has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o2);
+                    m = is_max ? fmax(m, mo) : fmin(m, mo);
+                }
+                if ((tid & 31) == 0) {
+                    red[tid >> 5] = m;
+                    red[32 + (tid >> 5)] = (double)has_nan;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    double mm = red[0];
+                    double nn = red[32];
+                    for (int w = 1; w < NT / 32; ++w) {
+                        mm = is_max ? fmax(mm, red[w]) : fmin(mm, red[w]);
+                        nn += red[32 + w];
+                    }
+                    *o = (nn > 0.0) ? NAN : mm;
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();  // nodeval reuse by the next row
+    }
+}
+
+#ifndef DP_HOST_EMU
+template <int NT> __global__ void __launch_bounds__(NT) dp_reduce_kernel(const DpReduceParams prm) {
+    extern __shared__ __align__(16) unsigned char dp_red_smem[];
+    double* nodeval = reinterpret_cast<double*>(dp_red_smem);
+    double* red = nodeval + prm.max_nodes;
+    dp_reduce_rows<NT>(prm, nodeval, red);
+}
+#endif

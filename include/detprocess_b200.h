@@ -1,0 +1,147 @@
+/*
+ * detprocess_b200 -- C ABI of the B200-native optimal-filter feature-extraction path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int error codes, no
+ * exceptions, no torch types.  Device pointers are CUDA device pointers of the
+ * current device; `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  All hot calls are asynchronous on `stream` and allocate nothing.
+ *
+ * The reference (spice-herald/detprocess, pure Python) has no FFI; each entry point
+ * names the reference interface it replaces (paths relative to the reference tree).
+ * INTEGRATION.md shows the ctypes binding a maintainer would add on the
+ * reference side.
+ */
+#ifndef DETPROCESS_B200_H
+#define DETPROCESS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define DP_OK 0
+#define DP_ERR_INVALID 1   /* bad argument / configuration (reference raises ValueError) */
+#define DP_ERR_CUDA 2      /* CUDA runtime failure */
+#define DP_ERR_STATE 3     /* call order (e.g. plan not finalized) */
+#define DP_ERR_UNSUPPORTED 4
+
+/* arithmetic precision of the fused OF kernel */
+#define DP_PREC_F64 0      /* parity mode: 1e-9 rel vs the float64 reference path */
+#define DP_PREC_F32 1      /* fast mode:   1e-5 amp / 1e-4 chi2 */
+
+/* sample type of the trace buffer */
+#define DP_IN_F64 0
+#define DP_IN_F32 1
+#define DP_IN_I16 2
+
+/* window-reduction ops */
+#define DP_OP_BASELINE 0   /* np.mean(trace[a:b])        detprocess/core/algorithms.py:651-704 */
+#define DP_OP_INTEGRAL 1   /* np.trapz(trace[a:b]) / fs  detprocess/core/algorithms.py:709-765 */
+#define DP_OP_MAXIMUM 2    /* np.amax(trace[a:b])        detprocess/core/algorithms.py:771-824 */
+#define DP_OP_MINIMUM 3    /* np.amin(trace[a:b])        detprocess/core/algorithms.py:830-885 */
+
+/* doubles written per OF fit: amp, rolled delay index, chi2, lowchi2, timeres */
+#define DP_FIT_NOUT 5
+
+const char* dp_last_error(void);         /* thread-local message of the last failing call */
+int dp_version(void);
+int dp_device_count(int* count);
+
+/* ------------------------------------------------------------------ OF1x1 plan
+ * One plan == one qp.OFBase object of the reference, i.e. one
+ * (nb_samples, nb_pretrigger, csd_tag/coupling) key built once in
+ * ProcessingData.instantiate_OF_base (detprocess/process/processing_data.py:155-433):
+ *   dp_of_plan_create        <- qp.OFBase(sample_rate)                       :278
+ *   dp_of_plan_set_psd       <- OFBase.set_csd(chan, csd, coupling=...)      :321-326
+ *   dp_of_plan_add_template  <- OFBase.add_template(chan, template, tag,
+ *                               pretrigger_samples, integralnorm)            :369-376
+ *                               + OFBase.calc_phi(chan, tag)                 :379-381
+ *   dp_of_plan_add_fit       <- one YAML OF algorithm block: the delay-search
+ *                               window qp.OF1x1.calc(...) receives from
+ *                               FeatureExtractors.of1x1_nodelay/unconstrained/
+ *                               constrained (detprocess/core/algorithms.py:278-570)
+ * Channels are dense indices 0..n_chan-1; row r of a trace batch belongs to channel
+ * r % n_chan (layout [n_events][n_chan][nb_samples]).
+ */
+typedef struct dp_of_plan dp_of_plan;
+
+int dp_of_plan_create(dp_of_plan** plan, int nb_samples, double sample_rate, int n_chan, int precision);
+void dp_of_plan_destroy(dp_of_plan* plan);
+
+/* psd: two-sided PSD [nb_samples], fftfreq order, A^2/Hz.  coupling_ac != 0 sets psd[0] = inf. */
+int dp_of_plan_set_psd(dp_of_plan* plan, int chan, const double* psd, int coupling_ac);
+
+/* returns the template index (>= 0) within the channel in *templ_index */
+int dp_of_plan_add_template(dp_of_plan* plan, int chan, const double* templ, int pretrigger_samples, int integralnorm,
+                            int* templ_index);
+
+/* Candidate delays are rolled indices [window_lo, window_hi) (zero delay sits at the
+ * template's pretrigger_samples); outside != 0 searches the complement.  A no-delay
+ * fit is the window [pretrigger, pretrigger+1).  Returns the fit slot in *fit_index. */
+int dp_of_plan_add_fit(dp_of_plan* plan, int chan, int templ_index, int window_lo, int window_hi, int outside,
+                       int* fit_index);
+
+/* lowchi2_fcutoff of qp.OF1x1.calc (default 10000 Hz, algorithms.py:280) */
+int dp_of_plan_set_lowchi2_fcutoff(dp_of_plan* plan, double fcutoff_hz);
+
+/* builds the device tables on `device`; the plan is immutable afterwards */
+int dp_of_plan_finalize(dp_of_plan* plan, int device);
+
+/* introspection (what OFBase.phi()/norm and OF1x1.get_energy_resolution() return) */
+int dp_of_plan_n_out(const dp_of_plan* plan, int* n_out);            /* doubles per event */
+int dp_of_plan_fit_offset(const dp_of_plan* plan, int chan, int fit_index, int* offset);
+int dp_of_plan_chi0_offset(const dp_of_plan* plan, int chan, int* offset);
+int dp_of_plan_get_phi(const dp_of_plan* plan, int chan, int templ_index, double* phi_re_im /* [nb_samples][2] */);
+int dp_of_plan_get_norm(const dp_of_plan* plan, int chan, int templ_index, double* norm);
+int dp_of_plan_get_template_fft(const dp_of_plan* plan, int chan, int templ_index, double* s_re_im);
+
+/* ----------------------------------------------------------------- OF1x1 batch
+ * Replaces, for a whole batch of events, the per-event
+ *   OFBase.clear_signal / update_signal(calc_fft=True) / calc_signal_filt /
+ *   calc_signal_filt_td      (detprocess/process/processing_data.py:712-772)
+ * and every qp.OF1x1(...).calc + get_result_* + get_chisq_nopulse the enabled
+ * extractors would run (detprocess/core/algorithms.py:331-341, 410-421, 533-558).
+ *
+ * traces_dev : [n_events][n_chan][row_stride >= nb_samples] samples of `in_dtype`
+ * out_dev    : [n_events][n_out] float64; per channel: chi0 (= chi2 no pulse), then per
+ *              fit DP_FIT_NOUT doubles {amp, rolled index of best delay, chi2, lowchi2,
+ *              time resolution}.  t0 = (index - pretrigger) / sample_rate.
+ */
+int dp_of1x1_batch(dp_of_plan* plan, const void* traces_dev, int in_dtype, long long n_events, long long row_stride,
+                   double* out_dev, void* stream);
+
+/* Host-buffer convenience used by the plugin layer and the end-to-end benchmark:
+ * copies traces_host (pageable or pinned) to the device in chunks on two streams,
+ * runs the batch and copies the feature table back.  Synchronous. */
+int dp_of1x1_batch_host(dp_of_plan* plan, const void* traces_host, int in_dtype, long long n_events,
+                        long long row_stride, double* out_host);
+
+/* measured duration (ms) of the last dp_of1x1_batch launch on this plan, from CUDA
+ * events recorded on the launch stream; synchronises on the end event. */
+int dp_of_plan_last_kernel_ms(dp_of_plan* plan, float* ms);
+int dp_of_plan_launch_count(const dp_of_plan* plan, long long* n);
+
+/* --------------------------------------------------------- window reductions
+ * dp_reduce_plan_add <- one YAML block of base_algorithm baseline / integral /
+ * maximum / minimum with its resolved [window_min_index, window_max_index) slice
+ * (FeatureProcessing._get_window_indices, detprocess/process/features.py:1243-1344).
+ * Results are bit-identical to numpy float64 (pairwise summation order reproduced).
+ */
+typedef struct dp_reduce_plan dp_reduce_plan;
+int dp_reduce_plan_create(dp_reduce_plan** plan, int nb_samples, double sample_rate, int n_chan);
+void dp_reduce_plan_destroy(dp_reduce_plan* plan);
+/* returns the feature's index within its channel; its output column is
+ * dp_reduce_plan_column(plan, chan, feat_index) (channels first, then add order) */
+int dp_reduce_plan_add(dp_reduce_plan* plan, int chan, int op, int window_lo, int window_hi, int* feat_index);
+int dp_reduce_plan_column(const dp_reduce_plan* plan, int chan, int feat_index, int* column);
+int dp_reduce_plan_finalize(dp_reduce_plan* plan, int device);
+int dp_reduce_plan_n_out(const dp_reduce_plan* plan, int* n_out);
+/* traces_dev: float64 [n_events][n_chan][row_stride]; out_dev: float64 [n_events][n_out] */
+int dp_window_reduce_batch(dp_reduce_plan* plan, const double* traces_dev, long long n_events, long long row_stride,
+                           double* out_dev, void* stream);
+int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* plan, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DETPROCESS_B200_H */
