@@ -309,6 +309,11 @@ int dp_of_plan_add_fit(dp_of_plan* p, int chan, int templ_index, int window_lo, 
     auto& ch = p->chans[chan];
     if (templ_index < 0 || templ_index >= (int)ch.templ.size()) return fail(DP_ERR_INVALID, "template index out of range");
     if ((int)ch.fits.size() >= DP_MAX_SLOTS) return fail(DP_ERR_UNSUPPORTED, "too many fits for one channel");
+    {
+        int nt = 0;
+        for (const auto& f : ch.fits) nt += f.templ == templ_index;
+        if (nt >= DP_MAX_TSLOTS) return fail(DP_ERR_UNSUPPORTED, "too many fits for one template");
+    }
     window_lo = std::min(std::max(window_lo, 0), p->N);
     window_hi = std::min(std::max(window_hi, 0), p->N);
     const int ncand = outside ? p->N - std::max(0, window_hi - window_lo) : window_hi - window_lo;

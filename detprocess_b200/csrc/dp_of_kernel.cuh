@@ -25,7 +25,8 @@
 #include "dp_fft.cuh"
 
 #define DP_MAX_TEMPLATES 4
-#define DP_MAX_SLOTS 8
+#define DP_MAX_SLOTS 8   // fits per channel
+#define DP_MAX_TSLOTS 4  // fits per template
 #define DP_NLOW_MAX 512
 #define DP_SLOT_NOUT 5  // amp, ind, chi2, lowchi2, timeres
 
@@ -131,27 +132,35 @@ template <int NT> DP_DEV double dp_block_sum(double v, double* red) {
     return r;
 }
 
-// arg-max of key with smallest-index tie break; (key, idx, val) of the winner is
-// returned to every thread.  idx < 0 means "no candidate".
+// arg-max of |val| with smallest-index tie break.  idx < 0 means "no candidate".
 template <class T> struct DpBest {
-    T key;
     T val;
     int idx;
 };
+DP_DEV float dp_abs(float a) { return fabsf(a); }
+DP_DEV double dp_abs(double a) { return fabs(a); }
 template <class T> DP_DEV void dp_best_merge(DpBest<T>& a, const DpBest<T>& b) {
-    const bool take = (b.idx >= 0) && (a.idx < 0 || b.key > a.key || (b.key == a.key && b.idx < a.idx));
+    const T ka = dp_abs(a.val), kb = dp_abs(b.val);
+    const bool take = (b.idx >= 0) && (a.idx < 0 || kb > ka || (kb == ka && b.idx < a.idx));
     if (take) a = b;
 }
 template <class T> DP_DEV DpBest<T> dp_warp_best(DpBest<T> a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         DpBest<T> b;
-        b.key = __shfl_xor_sync(0xffffffffu, a.key, o);
         b.val = __shfl_xor_sync(0xffffffffu, a.val, o);
         b.idx = __shfl_xor_sync(0xffffffffu, a.idx, o);
         dp_best_merge(a, b);
     }
     return a;
+}
+
+DP_DEV void dp_prefetch_l2(const void* p) {
+#ifndef DP_HOST_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
 }
 
 // ------------------------------------------------------------------ trace loads
@@ -220,13 +229,12 @@ DP_DEV void dp_fwd_subfft(const void* row, int in_dtype, int p, double x0, doubl
 }
 
 // ------------------------------------------------------------- inverse sub-FFT
-// Consumes Z' in (za, zb); calls sink(j, value) for every element z'[j] of the
-// sub-sequence (j = m + 512*n1).  Starts with a barrier-free in-place store (own
-// positions) and ends without a barrier: the caller must __syncthreads() before the
-// next store into buf.
-template <class T, int R1, class Sink>
+// Consumes Z' in (za, zb); leaves z'[j], j = tid + i*NT + 512*n, in y[i*R1 + n].
+// Starts with a barrier-free in-place store (own positions) and ends without a
+// barrier: the caller must __syncthreads() before the next store into buf.
+template <class T, int R1>
 DP_DEV void dp_inv_subfft(cx<T>* buf, const cx<T>* DP_RESTRICT tw1, const cx<T>* DP_RESTRICT tw2, int bA, int bB,
-                          cx<T> (&za)[16], cx<T> (&zb)[16], Sink&& sink) {
+                          cx<T> (&za)[16], cx<T> (&zb)[16], cx<T> (&y)[32]) {
     using G = DpGeom<R1>;
     const int tid = threadIdx.x;
     dp_dft<16, +1, T>::run(za);
@@ -239,13 +247,12 @@ DP_DEV void dp_inv_subfft(cx<T>* buf, const cx<T>* DP_RESTRICT tw1, const cx<T>*
     __syncthreads();
     {
         const int base = (tid >> 4) * 512 + (tid & 15);
-        cx<T> v[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = buf[G::phys(base + k * 16)];
-        dp_twiddle<32, true, T>(v, dp_ldg(tw2 + (tid & 15)));
-        dp_dft<32, +1, T>::run(v);
+        for (int k = 0; k < 32; ++k) y[k] = buf[G::phys(base + k * 16)];
+        dp_twiddle<32, true, T>(y, dp_ldg(tw2 + (tid & 15)));
+        dp_dft<32, +1, T>::run(y);
 #pragma unroll
-        for (int n = 0; n < 32; ++n) buf[G::phys(base + n * 16)] = v[n];
+        for (int n = 0; n < 32; ++n) buf[G::phys(base + n * 16)] = y[n];
     }
     __syncthreads();
 #pragma unroll
@@ -257,9 +264,80 @@ DP_DEV void dp_inv_subfft(cx<T>* buf, const cx<T>* DP_RESTRICT tw1, const cx<T>*
         dp_twiddle<R1, true, T>(v, dp_ldg(tw1 + m));
         dp_dft<R1, +1, T>::run(v);
 #pragma unroll
-        for (int n = 0; n < R1; ++n) sink(m + n * 512, v[n]);
+        for (int n = 0; n < R1; ++n) y[i * R1 + n] = v[n];
     }
 }
+
+// ------------------------------------------------------- windowed arg-max scans
+// y[i*R1 + n] holds the complex sample j = tid + i*NT + 512*n of the sub-sequence,
+// i.e. the two real amplitude samples with rolled delay index
+//     r = RS*j + RO (+ RS/2 for the imaginary part),   RS = 2*P, RO = 2*p
+// (the roll by `pretrigger` is folded into phi on the host, so the output index IS
+// the rolled index).  Scan order is ascending r, so a strict '>' keeps the first
+// (smallest-index) maximum exactly like numpy's argmin on the chi-square.
+template <class T, int R1, int P> struct DpScan {
+    static constexpr int NT = 16 * R1, NB1 = 32 / R1, RS = 2 * P;
+    // every sample is a candidate
+    static DP_DEV void full(const cx<T> (&y)[32], int tid, int p, DpBest<T>& b) {
+        T vb = y[0].re;
+        int pb = 0;
+#pragma unroll
+        for (int n = 0; n < R1; ++n) {
+#pragma unroll
+            for (int i = 0; i < NB1; ++i) {
+                const int e = i * R1 + n;
+                const int off = RS * (i * NT + 512 * n);
+                if (e != 0) {
+                    if (dp_abs(y[e].re) > dp_abs(vb)) {
+                        vb = y[e].re;
+                        pb = off;
+                    }
+                }
+                if (dp_abs(y[e].im) > dp_abs(vb)) {
+                    vb = y[e].im;
+                    pb = off + 1;
+                }
+            }
+        }
+        DpBest<T> c{vb, RS * tid + 2 * p + pb};
+        dp_best_merge(b, c);
+    }
+    // candidates: r in [lo, lo+len) (outside: the complement)
+    static DP_DEV void window(const cx<T> (&y)[32], int tid, int p, int lo, unsigned len, bool outside, DpBest<T>& b) {
+        T kb = (T)-1, vb = (T)0;
+        int pb = -1;
+        const int rb = RS * tid + 2 * p;
+#pragma unroll
+        for (int n = 0; n < R1; ++n) {
+            // CTA-uniform skip: block n covers r in [RS*512*n, RS*512*(n+1))
+            const int blo = RS * 512 * n, bhi = RS * 512 * (n + 1);
+            const bool hit = outside ? !(lo <= blo && (long long)bhi <= (long long)lo + (long long)len)
+                                     : (lo < bhi && (long long)lo + (long long)len > (long long)blo);
+            if (hit) {
+#pragma unroll
+                for (int i = 0; i < NB1; ++i) {
+                    const int e = i * R1 + n;
+                    const int r0 = rb + RS * (i * NT + 512 * n);
+                    const int r1 = r0 + 1;
+                    const bool in0 = ((unsigned)(r0 - lo) < len) != outside;
+                    const bool in1 = ((unsigned)(r1 - lo) < len) != outside;
+                    if (in0 && dp_abs(y[e].re) > kb) {
+                        kb = dp_abs(y[e].re);
+                        vb = y[e].re;
+                        pb = r0;
+                    }
+                    if (in1 && dp_abs(y[e].im) > kb) {
+                        kb = dp_abs(y[e].im);
+                        vb = y[e].im;
+                        pb = r1;
+                    }
+                }
+            }
+        }
+        DpBest<T> c{vb, pb};
+        dp_best_merge(b, c);
+    }
+};
 
 // --------------------------------------------------------- point-wise helpers
 // Real-FFT untangle of the pair (k, M-k):  Zk = C[k], Zm = C[M-k], w = exp(-2 pi i k/N).
@@ -286,21 +364,25 @@ template <class T, int R1, int P> struct DpOfKernel {
     static constexpr int NT = G::NT;
     static constexpr int NE = 32 * P;  // table entries (and X values) per thread
     static constexpr int N = 2 * P * G::MS;
-    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (G::SMEM_ELEMS + DP_NLOW_MAX) + sizeof(double) * 40 +
-                                         sizeof(DpBest<T>) * 32 * DP_MAX_SLOTS + 64;
+    static constexpr int RED_DOUBLES = (DP_MAX_TSLOTS + 1) * 32 + 8;
+    static constexpr int BEST_ELEMS = DP_MAX_TSLOTS * 32 + DP_MAX_TSLOTS;
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (G::SMEM_ELEMS + DP_NLOW_MAX) + sizeof(double) * RED_DOUBLES +
+                                         sizeof(DpBest<T>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS + 64;
 
     struct Smem {
         cx<T>* buf;
         cx<T>* stash;
         double* red;
-        DpBest<T>* best;  // [DP_MAX_SLOTS][32]
+        DpBest<T>* best;  // [DP_MAX_TSLOTS][32] per-warp + [DP_MAX_TSLOTS] final
+        int* slot_id;     // [DP_MAX_TSLOTS]
     };
     static DP_DEV Smem carve(unsigned char* raw) {
         Smem s;
         s.buf = reinterpret_cast<cx<T>*>(raw);
         s.stash = s.buf + G::SMEM_ELEMS;
         s.red = reinterpret_cast<double*>(s.stash + DP_NLOW_MAX);
-        s.best = reinterpret_cast<DpBest<T>*>(s.red + 40);
+        s.best = reinterpret_cast<DpBest<T>*>(s.red + RED_DOUBLES);
+        s.slot_id = reinterpret_cast<int*>(s.best + BEST_ELEMS);
         return s;
     }
 
@@ -382,8 +464,17 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
             if (K12 < prm.nlow) sm.stash[K12] = za[0];
         }
 
-        // chi0 (block sum) -- also the barrier that publishes the stash
-        const double chi0 = dp_block_sum<NT>((double)chi, sm.red);
+        // L2 prefetch of the trace this CTA processes next: the load phase of the next
+        // event then overlaps with this event's compute instead of waiting on HBM.
+        {
+            const int nrow = row + gridDim.x;
+            if (nrow < prm.n_rows) {
+                const size_t esz = prm.in_dtype == 0 ? 8 : (prm.in_dtype == 1 ? 4 : 2);
+                const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * esz;
+                const int nlines = (int)((size_t)N * esz / 128);
+                for (int l = tid; l < nlines; l += NT) dp_prefetch_l2(nx + (size_t)l * 128);
+            }
+        }
 
         // multi-template: X must survive the in-place inverse of the previous template
         const bool spill_x = ch.n_templ > 1;
@@ -394,6 +485,7 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
                 scr[(16 + r) * NT + tid] = zb[r];
             }
         }
+        __syncthreads();  // publishes the lowchi2 stash
 
         for (int it = 0; it < ch.n_templ; ++it) {
             const DpTemplDev<T>& tp = ch.templ[it];
@@ -441,71 +533,92 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
                 }
             }
 
-            // ---- inverse + windowed arg-max ---------------------------------------------
-            DpBest<T> best[DP_MAX_SLOTS];
-#pragma unroll
-            for (int s = 0; s < DP_MAX_SLOTS; ++s) best[s] = DpBest<T>{(T)0, (T)0, -1};
-            const int pre = tp.pretrigger;
-            auto sink = [&](int j, cx<T> v) {
-                // c'[j] -> real samples n = 2j, 2j+1; rolled index r = (n + pre) mod N
-                const int r0 = (2 * j + pre) & (N - 1);
-                const int r1 = (2 * j + 1 + pre) & (N - 1);
-#pragma unroll
-                for (int s = 0; s < DP_MAX_SLOTS; ++s) {
-                    if (s < ch.n_slots && ch.slots[s].templ == it) {
-                        const DpSlot sl = ch.slots[s];
-                        const unsigned len = (unsigned)(sl.hi - sl.lo);
-                        const bool in0 = (((unsigned)(r0 - sl.lo) < len) != (sl.outside != 0));
-                        const bool in1 = (((unsigned)(r1 - sl.lo) < len) != (sl.outside != 0));
-                        if (in0) dp_best_merge(best[s], DpBest<T>{v.re * v.re, v.re, r0});
-                        if (in1) dp_best_merge(best[s], DpBest<T>{v.im * v.im, v.im, r1});
-                    }
-                }
-            };
-            if constexpr (P == 1) dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, sink);
+            // ---- inverse: amplitude-vs-delay samples into registers ------------------------
+            cx<T> y[32];
+            if constexpr (P == 1) dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
 
-            // ---- block arg-max per slot, lowchi2, outputs -------------------------------
-#pragma unroll
-            for (int s = 0; s < DP_MAX_SLOTS; ++s) {
-                if (s < ch.n_slots && ch.slots[s].templ == it) {
-                    DpBest<T> b = dp_warp_best(best[s]);
-                    if ((tid & 31) == 0) sm.best[s * 32 + (tid >> 5)] = b;
+            // ---- windowed arg-max: one pass over y per fit of this template -------------
+            int nts = 0;
+            for (int s = 0; s < ch.n_slots; ++s) {
+                const DpSlot sl = ch.slots[s];
+                if (sl.templ != it) continue;
+                DpBest<T> b{(T)0, -1};
+                if (sl.lo == 0 && sl.hi == N && !sl.outside)
+                    DpScan<T, R1, P>::full(y, tid, 0, b);
+                else
+                    DpScan<T, R1, P>::window(y, tid, 0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, b);
+                b = dp_warp_best(b);
+                if ((tid & 31) == 0) sm.best[nts * 32 + (tid >> 5)] = b;
+                if (tid == 0) sm.slot_id[nts] = s;
+                ++nts;
+            }
+            __syncthreads();
+            // warp q merges fit q
+            {
+                constexpr int NW = (NT + 31) / 32;
+                const int l = tid & 31;
+                for (int q = tid >> 5; q < nts; q += NW) {
+                    DpBest<T> b{(T)0, -1};
+                    if (l < NW) b = sm.best[q * 32 + l];
+                    b = dp_warp_best(b);
+                    if (l == 0) sm.best[DP_MAX_TSLOTS * 32 + q] = b;
                 }
             }
             __syncthreads();
-            for (int s = 0; s < ch.n_slots; ++s) {
-                if (ch.slots[s].templ != it) continue;
-                DpBest<T> b = sm.best[s * 32];
-                for (int w = 1; w < (NT + 31) / 32; ++w) dp_best_merge(b, sm.best[s * 32 + w]);
-                // low-frequency chi2 at (amp, delay)
-                const int d = b.idx - pre;
-                double part = 0.0;
-                for (int k = tid; k < prm.nlow; k += NT) {
-                    const int ph = (int)(((long long)k * (long long)d) % N + N) % N;  // exp(-2 pi i k d / N)
-                    T sn, cs;
-                    if constexpr (sizeof(T) == 8) {
-                        double s_, c_;
-                        sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
-                        sn = (T)s_;
-                        cs = (T)c_;
-                    } else {
-                        float s_, c_;
-                        sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
-                        sn = (T)s_;
-                        cs = (T)c_;
+            // ---- low-frequency chi2 at each fit's (amp, delay); chi0 rides along -----------
+            {
+                double part[DP_MAX_TSLOTS + 1];
+#pragma unroll
+                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                    part[q] = 0.0;
+                    if (q < nts && tid < prm.nlow) {
+                        const DpBest<T> b = sm.best[DP_MAX_TSLOTS * 32 + q];
+                        const int k = tid;
+                        const int d = b.idx - tp.pretrigger;
+                        const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
+                        T sn, cs;
+                        if constexpr (sizeof(T) == 8) {
+                            double s_, c_;
+                            sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
+                            sn = (T)s_;
+                            cs = (T)c_;
+                        } else {
+                            float s_, c_;
+                            sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
+                            sn = (T)s_;
+                            cs = (T)c_;
+                        }
+                        const cx<T> mdl = cmul(cx<T>{cs, -sn}, dp_ldg(tp.s_low + k));
+                        const cx<T> X = sm.stash[k];
+                        const cx<T> R = cx<T>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
+                        part[q] = (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
                     }
-                    const cx<T> e = cx<T>{cs, -sn};
-                    const cx<T> S = dp_ldg(tp.s_low + k);
-                    const cx<T> mdl = cmul(e, S);
-                    const cx<T> X = sm.stash[k];
-                    const cx<T> R = cx<T>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
-                    part += (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
                 }
-                const double low = dp_block_sum<NT>(part, sm.red);
-                if (tid == 0) {
-                    double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
-                    o[0] = chi0;
-                    double* os = o + 1 + s * DP_SLOT_NOUT;
+                part[DP_MAX_TSLOTS] = (it == 0) ? (double)chi : 0.0;
+#pragma unroll
+                for (int q = 0; q <= DP_MAX_TSLOTS; ++q) {
+                    if (q < nts || (q == DP_MAX_TSLOTS && it == 0)) {
+                        const double v = dp_warp_sum(part[q]);
+                        if ((tid & 31) == 0) sm.red[q * 32 + (tid >> 5)] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                constexpr int NW = (NT + 31) / 32;
+                double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
+                if (it == 0) {
+                    double c0 = 0.0;
+                    for (int w = 0; w < NW; ++w) c0 += sm.red[DP_MAX_TSLOTS * 32 + w];
+                    sm.red[(DP_MAX_TSLOTS + 1) * 32] = c0;
+                    o[0] = c0;
+                }
+                const double chi0 = sm.red[(DP_MAX_TSLOTS + 1) * 32];
+                for (int q = 0; q < nts; ++q) {
+                    double low = 0.0;
+                    for (int w = 0; w < NW; ++w) low += sm.red[q * 32 + w];
+                    const DpBest<T> b = sm.best[DP_MAX_TSLOTS * 32 + q];
+                    double* os = o + 1 + sm.slot_id[q] * DP_SLOT_NOUT;
                     const double amp = (double)b.val;
                     os[0] = amp;
                     os[1] = (double)b.idx;
@@ -514,9 +627,8 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
                     os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
                 }
             }
-            __syncthreads();  // buf / best / stash reuse
+            __syncthreads();  // buf / best / red reuse
         }
-        if (ch.n_slots == 0 && tid == 0) prm.out[(long long)ev * prm.n_out + ch.out_base] = chi0;
     }
 }
 

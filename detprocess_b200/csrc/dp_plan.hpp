@@ -209,7 +209,9 @@ DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Cha
             std::vector<cplx> pe(M + 1);
             for (int k = 0; k <= M; ++k) {
                 const cplx a = tp.phi[k], b = std::conj(tp.phi[(N - k) % N]);
-                pe[k] = 0.5 * (a + b) / ((double)N * tp.norm * 2.0 * scale);
+                // the roll by `pretrigger` (zero delay at index pretrigger) is a phase ramp
+                const cplx roll = root(((long long)k * (long long)tp.pretrigger) % N, N);
+                pe[k] = 0.5 * (a + b) * roll / ((double)N * tp.norm * 2.0 * scale);
             }
             pe[0] = cplx(pe[0].real(), 0.0);
             pe[M] = cplx(pe[M].real(), 0.0);
