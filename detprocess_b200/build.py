@@ -16,9 +16,14 @@ CSRC = os.path.join(PKG, 'csrc')
 OUT_DIR = os.path.join(PKG, '_C')
 LIB = os.path.join(OUT_DIR, 'libdetprocess_b200.so')
 
-SOURCES = ['dp_capi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3', '-lineinfo',
-              '--fmad=true', '-Xcompiler', '-fPIC,-O2', '-shared']
+              '--fmad=true', '-Xcompiler', '-fPIC,-O2', '-Xptxas', '-v']
+
+# (object name, source, extra defines): the OF kernel is instantiated per
+# (precision, input type) in separate translation units so they compile in parallel
+UNITS = [('dp_capi', 'dp_capi.cu', [])] + [
+    (f'dp_of_inst_p{p}_{i}', 'dp_of_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_IN={i}'])
+    for p in (1, 0) for i in (0, 1, 2)]
 
 
 def _deps():
@@ -40,18 +45,39 @@ def needs_build():
 def build(force=False, verbose=True):
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libdetprocess_b200.so')
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + ['-Xptxas', '-v', '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    obj_dir = os.path.join(OUT_DIR, 'obj')
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_unit(unit):
+        name, src, defs = unit
+        obj = os.path.join(obj_dir, name + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + defs + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return name, obj, ' '.join(cmd), res.returncode, res.stdout
+
     if verbose:
-        print('[detprocess_b200.build]', ' '.join(cmd), flush=True)
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        print(f'[detprocess_b200.build] nvcc sm_100a: {len(UNITS)} translation units', flush=True)
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_unit, UNITS))
+    log = []
+    ok = True
+    for name, obj, cmd, rc, out in results:
+        log.append(f'### {cmd}\n{out}')
+        ok &= rc == 0
+    link = [nvcc, '-shared', '-o', LIB] + [r[1] for r in results]
+    if ok:
+        res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log.append(f'### {" ".join(link)}\n{res.stdout}')
+        ok = res.returncode == 0
     with open(os.path.join(OUT_DIR, 'build.log'), 'w') as f:
-        f.write(res.stdout)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout)
+        f.write('\n'.join(log))
+    if not ok:
+        sys.stderr.write('\n'.join(log)[-8000:])
         raise RuntimeError('nvcc failed building libdetprocess_b200.so')
     return LIB
 

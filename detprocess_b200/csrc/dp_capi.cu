@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/detprocess_b200.h"
+#include "dp_of_launch.hpp"
 #include "dp_plan.hpp"
 #include "dp_reduce_plan.hpp"
 
@@ -84,42 +85,27 @@ struct dp_of_plan {
 
 namespace {
 
-template <class T, int R1, int P> int of_setup_kernel(dp_of_plan* p) {
-    using K = DpOfKernel<T, R1, P>;
-    auto kern = dp_of_kernel<T, R1, P>;
-    p->smem = K::SMEM_BYTES;
-    DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES));
-    int occ = 0;
-    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::NT, K::SMEM_BYTES));
-    if (occ < 1) return fail(DP_ERR_CUDA, "OF kernel does not fit on an SM");
-    int sms = 0;
-    DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
-    p->grid_max = sms * occ;
-    return DP_OK;
-}
-
-template <class T, int R1, int P> int of_launch_kernel(dp_of_plan* p, const DpOfParams<T>& prm, int grid, cudaStream_t st) {
-    dp_of_kernel<T, R1, P><<<grid, DpGeom<R1>::NT, p->smem, st>>>(prm);
-    DP_CUDA(cudaGetLastError());
-    return DP_OK;
-}
-
-#define DP_DISPATCH_R1(T, P, r1, FN, ...)                                   \
-    switch (r1) {                                                           \
-        case 2: return FN<T, 2, P>(__VA_ARGS__);                            \
-        case 4: return FN<T, 4, P>(__VA_ARGS__);                            \
-        case 8: return FN<T, 8, P>(__VA_ARGS__);                            \
-        case 16: return FN<T, 16, P>(__VA_ARGS__);                          \
-        case 32: return FN<T, 32, P>(__VA_ARGS__);                          \
-        default: return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");\
-    }
-
 template <class T> int of_setup(dp_of_plan* p) {
     if (p->geom.P != 1) return fail(DP_ERR_UNSUPPORTED, "trace length needs the split (P=2) path, not built yet");
-    DP_DISPATCH_R1(T, 1, p->geom.R1, of_setup_kernel, p)
+    const int prec = sizeof(T) == 8 ? 0 : 1;
+    for (int in = 0; in < 3; ++in) {
+        size_t smem = 0;
+        int grid_max = 0, occ = 0;
+        const int rc = dp_of_setup_table[prec][in](p->geom.R1, p->device, &smem, &grid_max, &occ);
+        if (rc == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length for this precision");
+        if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel setup: ") + cudaGetErrorString((cudaError_t)rc));
+        if (occ < 1) return fail(DP_ERR_CUDA, "OF kernel does not fit on an SM");
+        p->smem = smem;
+        p->grid_max = in == 0 ? grid_max : std::min(p->grid_max, grid_max);
+    }
+    return DP_OK;
 }
 template <class T> int of_launch(dp_of_plan* p, const DpOfParams<T>& prm, int grid, cudaStream_t st) {
-    DP_DISPATCH_R1(T, 1, p->geom.R1, of_launch_kernel, p, prm, grid, st)
+    const int prec = sizeof(T) == 8 ? 0 : 1;
+    const int rc = dp_of_launch_table[prec][prm.in_dtype](p->geom.R1, &prm, grid, p->smem, st);
+    if (rc == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length for this precision");
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return DP_OK;
 }
 
 template <class T> int of_finalize(dp_of_plan* p) {

@@ -164,42 +164,46 @@ DP_DEV void dp_prefetch_l2(const void* p) {
 }
 
 // ------------------------------------------------------------------ trace loads
-// element j of the packed complex sequence: (x[2j], x[2j+1]) - offset, scaled
-template <class T> DP_DEV cx<T> dp_load_pair(const void* row, int in_dtype, long long j, double x0, double sc) {
-    if (in_dtype == 0) {
-        const double2 d = __ldg(reinterpret_cast<const double2*>(row) + j);
-        return cx<T>{(T)((d.x - x0) * sc), (T)((d.y - x0) * sc)};
-    } else if (in_dtype == 1) {
-        const float2 d = __ldg(reinterpret_cast<const float2*>(row) + j);
-        return cx<T>{(T)(((double)d.x - x0) * sc), (T)(((double)d.y - x0) * sc)};
-    } else {
-        const short2* p = reinterpret_cast<const short2*>(row) + j;
-        const short2 d = __ldg(p);
-        return cx<T>{(T)(((double)d.x - x0) * sc), (T)(((double)d.y - x0) * sc)};
-    }
+// Element j of the packed complex sequence is the sample pair (x[2j], x[2j+1]).  The
+// input type is a template parameter so that the R1 loads of a butterfly are issued
+// back to back (a runtime switch made ptxas serialise them: one load in flight).
+template <int IN> struct DpRaw;
+template <> struct DpRaw<0> { using type = double2; using scalar = double; };
+template <> struct DpRaw<1> { using type = float2; using scalar = float; };
+template <> struct DpRaw<2> { using type = short2; using scalar = short; };
+
+template <int IN> DP_DEV typename DpRaw<IN>::type dp_load_raw(const void* row, long long j) {
+    return __ldg(reinterpret_cast<const typename DpRaw<IN>::type*>(row) + j);
 }
-DP_DEV double dp_load_first(const void* row, int in_dtype) {
-    if (in_dtype == 0) return __ldg(reinterpret_cast<const double*>(row));
-    if (in_dtype == 1) return (double)__ldg(reinterpret_cast<const float*>(row));
-    return (double)__ldg(reinterpret_cast<const short*>(row));
+template <class T, int IN> DP_DEV cx<T> dp_convert_raw(typename DpRaw<IN>::type d, double x0, double sc) {
+    return cx<T>{(T)(((double)d.x - x0) * sc), (T)(((double)d.y - x0) * sc)};
+}
+template <int IN> DP_DEV double dp_load_first(const void* row) {
+    return (double)__ldg(reinterpret_cast<const typename DpRaw<IN>::scalar*>(row));
 }
 
 // ------------------------------------------------------------- forward sub-FFT
 // Loads sub-sequence z[j] = c[P*j + p] from global, runs passes 1..3 and leaves
 // Z[K12 + KQ*r] in za[r], Z[K12' + KQ*r] in zb[r].
-template <class T, int R1, int P>
-DP_DEV void dp_fwd_subfft(const void* row, int in_dtype, int p, double x0, double sc, cx<T>* buf,
-                          const cx<T>* DP_RESTRICT tw1, const cx<T>* DP_RESTRICT tw2, int bA, int bB,
-                          cx<T> (&za)[16], cx<T> (&zb)[16]) {
+template <class T, int R1, int P, int IN>
+DP_DEV void dp_fwd_subfft(const void* row, int p, double x0, double sc, cx<T>* buf, const cx<T>* DP_RESTRICT tw1,
+                          const cx<T>* DP_RESTRICT tw2, int bA, int bB, cx<T> (&za)[16], cx<T> (&zb)[16]) {
     using G = DpGeom<R1>;
     const int tid = threadIdx.x;
-    // pass 1: radix R1 over n1 (stride 512)
+    // pass 1: radix R1 over n1 (stride 512); loads issued in batches of <= 16 (64 registers of raw f64)
 #pragma unroll
     for (int i = 0; i < G::NB1; ++i) {
         const int m = tid + i * G::NT;
         cx<T> v[R1];
+        constexpr int BATCH = R1 < 16 ? R1 : 16;
 #pragma unroll
-        for (int n = 0; n < R1; ++n) v[n] = dp_load_pair<T>(row, in_dtype, (long long)P * (m + n * 512) + p, x0, sc);
+        for (int n0 = 0; n0 < R1; n0 += BATCH) {
+            typename DpRaw<IN>::type raw[BATCH];
+#pragma unroll
+            for (int n = 0; n < BATCH; ++n) raw[n] = dp_load_raw<IN>(row, (long long)P * (m + (n0 + n) * 512) + p);
+#pragma unroll
+            for (int n = 0; n < BATCH; ++n) v[n0 + n] = dp_convert_raw<T, IN>(raw[n], x0, sc);
+        }
         dp_dft<R1, -1, T>::run(v);
         dp_twiddle<R1, false, T>(v, dp_ldg(tw1 + m));
 #pragma unroll
@@ -359,19 +363,51 @@ template <class T> DP_DEV void dp_retangle(cx<T> Fk, cx<T> Fm, cx<T> w, cx<T>& C
 }
 
 // ======================================================================== kernel
-template <class T, int R1, int P> struct DpOfKernel {
+// Self-paired butterflies.  Thread 0 owns K12 = 0 (k = KQ*r: pairs r <-> 16-r, r = 0 is
+// DC/Nyquist, r = 8 is k = M/2) and K12 = KQ/2 (k = KQ/2 + KQ*r: pairs r <-> 15-r).
+// Their 17 pairs are processed by lanes 0..16 of warp 0 through a 32-element shared
+// scratch, so warp 0 does not execute a second unrolled copy of the point-wise code.
+template <class T> struct DpSelfPair {
+    int ek, em;   // element slots (0..15 = A, 16..31 = B) of k and its mirror
+    cx<T> w;      // exp(-2 pi i k / N) of the pair
+    bool dc;      // the (DC, Nyquist) pair
+};
+template <class T> DP_DEV DpSelfPair<T> dp_self_pair(int lane) {
+    DpSelfPair<T> sp;
+    double s_, c_;
+    if (lane < 9) {
+        const int r = lane;
+        sp.ek = r;
+        sp.em = (16 - r) & 15;
+        sincospi(-2.0 * (double)r / 32.0, &s_, &c_);
+    } else {
+        const int r = lane - 9;
+        sp.ek = 16 + r;
+        sp.em = 16 + 15 - r;
+        sincospi(-2.0 * (double)(1 + 2 * r) / 64.0, &s_, &c_);
+    }
+    sp.w = cx<T>{(T)c_, (T)s_};
+    sp.dc = lane == 0;
+    return sp;
+}
+
+template <class T, int R1, int P, int IN> struct DpOfKernel {
     using G = DpGeom<R1>;
     static constexpr int NT = G::NT;
     static constexpr int NE = 32 * P;  // table entries (and X values) per thread
     static constexpr int N = 2 * P * G::MS;
     static constexpr int RED_DOUBLES = (DP_MAX_TSLOTS + 1) * 32 + 8;
     static constexpr int BEST_ELEMS = DP_MAX_TSLOTS * 32 + DP_MAX_TSLOTS;
-    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (G::SMEM_ELEMS + DP_NLOW_MAX) + sizeof(double) * RED_DOUBLES +
-                                         sizeof(DpBest<T>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS + 64;
+    static constexpr int SP_ELEMS = 33 + 32;  // self-pair X (+ Nyquist) and Z'
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (G::SMEM_ELEMS + DP_NLOW_MAX + SP_ELEMS + 1) +
+                                         sizeof(double) * RED_DOUBLES + sizeof(DpBest<T>) * BEST_ELEMS +
+                                         sizeof(int) * DP_MAX_TSLOTS + 64;
 
     struct Smem {
         cx<T>* buf;
         cx<T>* stash;
+        cx<T>* spx;  // [33] X of thread 0's butterflies (A: 0..15, B: 16..31), [32] = X at Nyquist
+        cx<T>* spz;  // [32] Z' of the same
         double* red;
         DpBest<T>* best;  // [DP_MAX_TSLOTS][32] per-warp + [DP_MAX_TSLOTS] final
         int* slot_id;     // [DP_MAX_TSLOTS]
@@ -380,7 +416,9 @@ template <class T, int R1, int P> struct DpOfKernel {
         Smem s;
         s.buf = reinterpret_cast<cx<T>*>(raw);
         s.stash = s.buf + G::SMEM_ELEMS;
-        s.red = reinterpret_cast<double*>(s.stash + DP_NLOW_MAX);
+        s.spx = s.stash + DP_NLOW_MAX;
+        s.spz = s.spx + 33;
+        s.red = reinterpret_cast<double*>(s.spz + 33);
         s.best = reinterpret_cast<DpBest<T>*>(s.red + RED_DOUBLES);
         s.slot_id = reinterpret_cast<int*>(s.best + BEST_ELEMS);
         return s;
@@ -390,78 +428,85 @@ template <class T, int R1, int P> struct DpOfKernel {
 };
 
 // The body is long; keep it out of the class for readability.
-template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const DpOfParams<T>& prm, unsigned char* smem_raw) {
-    static_assert(P == 1 || P == 2, "P");
+template <class T, int R1, int P, int IN>
+DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned char* smem_raw) {
+    static_assert(P == 1, "P = 2 (split) path is built separately");
     const Smem sm = carve(smem_raw);
     const int tid = threadIdx.x;
     int K12, bA, bB;
     G::map(tid, K12, bA, bB);
     const cx<T> wn = dp_ldg(prm.twn + tid);  // exp(-2 pi i K12 / N)
     cx<T>* scr = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
+    constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
+    const DpSelfPair<T> sp = dp_self_pair<T>(tid & 31);
 
     for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
         const int chan = row % prm.n_chan;
         const int ev = row / prm.n_chan;
         const DpChanDev<T>& ch = prm.chans[chan];
-        const void* xrow;
-        {
-            const size_t esz = prm.in_dtype == 0 ? 8 : (prm.in_dtype == 1 ? 4 : 2);
-            xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * esz;
-        }
-        const double x0 = prm.subtract_first ? dp_load_first(xrow, prm.in_dtype) : 0.0;
+        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
+        const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
         const double sc = prm.scale;
 
         cx<T> za[16], zb[16];
         T chi = (T)0;
 
-        if constexpr (P == 1) {
-            dp_fwd_subfft<T, R1, 1>(xrow, prm.in_dtype, 0, x0, sc, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
-            // ---- untangle: (za, zb) <- 2*X ---------------------------------------------
-            if (tid != 0) {
-                // A[r] (k = K12 + KQ r) pairs with B[15-r] (k' = M - k);  w = wn * W_32^r
+        dp_fwd_subfft<T, R1, 1, IN>(xrow, 0, x0, sc, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+
+        // ---- self-paired butterflies of thread 0, cooperatively in warp 0 ------------------
+        if (tid < 32) {
+            if (tid == 0) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    sm.spx[r] = za[r];
+                    sm.spx[16 + r] = zb[r];
+                }
+            }
+            __syncwarp();
+            if (tid < 17) {
+                cx<T> Xk, Xm;
+                dp_untangle(sm.spx[sp.ek], sm.spx[sp.em], sp.w, Xk, Xm);
+                chi = dp_fma(dp_ldg(ch.wj + sp.ek * NT), cnorm2(Xk), chi);
+                if (sp.dc)
+                    chi = dp_fma(ch.wj_nyq, cnorm2(Xm), chi);
+                else if (sp.ek != sp.em)
+                    chi = dp_fma(dp_ldg(ch.wj + sp.em * NT), cnorm2(Xm), chi);
+                sm.spx[sp.ek] = Xk;
+                if (sp.ek != sp.em) sm.spx[sp.em] = Xm;
+                if (sp.dc) {
+                    sm.spx[32] = Xm;    // X at Nyquist
+                    sm.stash[0] = Xk;   // X at DC, first lowchi2 bin
+                }
+            }
+            __syncwarp();
+        }
+        // ---- untangle: (za, zb) <- 2*X   (thread 0 computes throw-away values) -------------
+        {
+            T chin = (T)0;
+            // A[r] (k = K12 + KQ r) pairs with B[15-r] (k' = M - k);  w = wn * W_32^r
 #define DP_XP(r)                                                                                         \
     {                                                                                                    \
         cx<T> Xk, Xm;                                                                                    \
         dp_untangle(za[r], zb[15 - r], cmul(wn, dp_w64<T, 2 * r, -1>()), Xk, Xm);                        \
-        chi = dp_fma(dp_ldg(ch.wj + r * NT + tid), cnorm2(Xk), chi);                                      \
-        chi = dp_fma(dp_ldg(ch.wj + (16 + 15 - r) * NT + tid), cnorm2(Xm), chi);                          \
+        chin = dp_fma(dp_ldg(ch.wj + r * NT + tid), cnorm2(Xk), chin);                                   \
+        chin = dp_fma(dp_ldg(ch.wj + (16 + 15 - r) * NT + tid), cnorm2(Xm), chin);                       \
         za[r] = Xk;                                                                                      \
         zb[15 - r] = Xm;                                                                                 \
     }
-                DP_XP(0) DP_XP(1) DP_XP(2) DP_XP(3) DP_XP(4) DP_XP(5) DP_XP(6) DP_XP(7)
-                DP_XP(8) DP_XP(9) DP_XP(10) DP_XP(11) DP_XP(12) DP_XP(13) DP_XP(14) DP_XP(15)
+            DP_XP(0) DP_XP(1) DP_XP(2) DP_XP(3) DP_XP(4) DP_XP(5) DP_XP(6) DP_XP(7)
+            DP_XP(8) DP_XP(9) DP_XP(10) DP_XP(11) DP_XP(12) DP_XP(13) DP_XP(14) DP_XP(15)
 #undef DP_XP
+            if (tid != 0) {
+                chi += chin;
+                // low-frequency bins for lowchi2: k = K12 < nlow lives in A[0]
+                if (K12 < prm.nlow) sm.stash[K12] = za[0];
             } else {
-                // thread 0: A = K12 0 (k = KQ r, pairs r <-> 16-r; r = 0 is DC/Nyquist, r = 8 is k = M/2)
-                //           B = K12 KQ/2 (k = KQ/2 + KQ r, pairs r <-> 15-r)
-#define DP_XA(r, rp)                                                                                     \
-    {                                                                                                    \
-        cx<T> Xk, Xm;                                                                                    \
-        dp_untangle(za[r], za[rp], dp_w64<T, 2 * r, -1>(), Xk, Xm);                                      \
-        chi = dp_fma(dp_ldg(ch.wj + r * NT), cnorm2(Xk), chi);                                            \
-        if (r == 0) chi = dp_fma(ch.wj_nyq, cnorm2(Xm), chi);                                            \
-        else if (r != rp) chi = dp_fma(dp_ldg(ch.wj + rp * NT), cnorm2(Xm), chi);                         \
-        za[r] = Xk;                                                                                      \
-        if (r != rp) za[rp] = Xm;                                                                        \
-        if (r == 0) sm.stash[DP_NLOW_MAX - 1] = Xm; /* Nyquist X kept for the filter step */             \
-    }
-                DP_XA(0, 0) DP_XA(1, 15) DP_XA(2, 14) DP_XA(3, 13) DP_XA(4, 12) DP_XA(5, 11) DP_XA(6, 10)
-                DP_XA(7, 9) DP_XA(8, 8)
-#undef DP_XA
-#define DP_XB(r)                                                                                         \
-    {                                                                                                    \
-        cx<T> Xk, Xm;                                                                                    \
-        dp_untangle(zb[r], zb[15 - r], dp_w64<T, 1 + 2 * r, -1>(), Xk, Xm);                              \
-        chi = dp_fma(dp_ldg(ch.wj + (16 + r) * NT), cnorm2(Xk), chi);                                     \
-        chi = dp_fma(dp_ldg(ch.wj + (16 + 15 - r) * NT), cnorm2(Xm), chi);                                \
-        zb[r] = Xk;                                                                                      \
-        zb[15 - r] = Xm;                                                                                 \
-    }
-                DP_XB(0) DP_XB(1) DP_XB(2) DP_XB(3) DP_XB(4) DP_XB(5) DP_XB(6) DP_XB(7)
-#undef DP_XB
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    za[r] = sm.spx[r];
+                    zb[r] = sm.spx[16 + r];
+                }
             }
-            // low-frequency bins for lowchi2: k = K12 < nlow lives in A[0]
-            if (K12 < prm.nlow) sm.stash[K12] = za[0];
         }
 
         // L2 prefetch of the trace this CTA processes next: the load phase of the next
@@ -469,9 +514,8 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
         {
             const int nrow = row + gridDim.x;
             if (nrow < prm.n_rows) {
-                const size_t esz = prm.in_dtype == 0 ? 8 : (prm.in_dtype == 1 ? 4 : 2);
-                const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * esz;
-                const int nlines = (int)((size_t)N * esz / 128);
+                const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * ESZ;
+                constexpr int nlines = (int)((size_t)N * ESZ / 128);
                 for (int l = tid; l < nlines; l += NT) dp_prefetch_l2(nx + (size_t)l * 128);
             }
         }
@@ -497,45 +541,38 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
                 }
             }
             // ---- filter + inverse untangle: (za, zb) <- Z' -----------------------------
-            if constexpr (P == 1) {
-                if (tid != 0) {
+            if (tid < 17) {
+                const cx<T> Fk = cmul(dp_ldg(tp.phi + sp.ek * NT), sm.spx[sp.ek]);
+                const cx<T> Fm = sp.dc ? cmul(tp.phi_nyq, sm.spx[32]) : cmul(dp_ldg(tp.phi + sp.em * NT), sm.spx[sp.em]);
+                cx<T> Ck, Cm;
+                dp_retangle(Fk, Fm, sp.w, Ck, Cm);
+                sm.spz[sp.ek] = Ck;
+                if (sp.ek != sp.em) sm.spz[sp.em] = Cm;
+            }
 #define DP_FP(r)                                                                                         \
     {                                                                                                    \
-        const cx<T> Fk = cmul(dp_ldg(tp.phi + r * NT + tid), za[r]);                                      \
-        const cx<T> Fm = cmul(dp_ldg(tp.phi + (16 + 15 - r) * NT + tid), zb[15 - r]);                     \
+        const cx<T> Fk = cmul(dp_ldg(tp.phi + r * NT + tid), za[r]);                                     \
+        const cx<T> Fm = cmul(dp_ldg(tp.phi + (16 + 15 - r) * NT + tid), zb[15 - r]);                    \
         dp_retangle(Fk, Fm, cmul(wn, dp_w64<T, 2 * r, -1>()), za[r], zb[15 - r]);                        \
     }
-                    DP_FP(0) DP_FP(1) DP_FP(2) DP_FP(3) DP_FP(4) DP_FP(5) DP_FP(6) DP_FP(7)
-                    DP_FP(8) DP_FP(9) DP_FP(10) DP_FP(11) DP_FP(12) DP_FP(13) DP_FP(14) DP_FP(15)
+            DP_FP(0) DP_FP(1) DP_FP(2) DP_FP(3) DP_FP(4) DP_FP(5) DP_FP(6) DP_FP(7)
+            DP_FP(8) DP_FP(9) DP_FP(10) DP_FP(11) DP_FP(12) DP_FP(13) DP_FP(14) DP_FP(15)
 #undef DP_FP
-                } else {
-#define DP_FA(r, rp)                                                                                     \
-    {                                                                                                    \
-        const cx<T> Fk = cmul(dp_ldg(tp.phi + r * NT), za[r]);                                            \
-        const cx<T> Fm = (r == 0) ? cmul(tp.phi_nyq, sm.stash[DP_NLOW_MAX - 1])                          \
-                                  : cmul(dp_ldg(tp.phi + rp * NT), za[rp]);                               \
-        cx<T> Ck, Cm;                                                                                    \
-        dp_retangle(Fk, Fm, dp_w64<T, 2 * r, -1>(), Ck, Cm);                                             \
-        za[r] = Ck;                                                                                      \
-        if (r != rp) za[rp] = Cm;                                                                        \
-    }
-                    DP_FA(0, 0) DP_FA(1, 15) DP_FA(2, 14) DP_FA(3, 13) DP_FA(4, 12) DP_FA(5, 11) DP_FA(6, 10)
-                    DP_FA(7, 9) DP_FA(8, 8)
-#undef DP_FA
-#define DP_FB(r)                                                                                         \
-    {                                                                                                    \
-        const cx<T> Fk = cmul(dp_ldg(tp.phi + (16 + r) * NT), zb[r]);                                     \
-        const cx<T> Fm = cmul(dp_ldg(tp.phi + (16 + 15 - r) * NT), zb[15 - r]);                           \
-        dp_retangle(Fk, Fm, dp_w64<T, 1 + 2 * r, -1>(), zb[r], zb[15 - r]);                              \
-    }
-                    DP_FB(0) DP_FB(1) DP_FB(2) DP_FB(3) DP_FB(4) DP_FB(5) DP_FB(6) DP_FB(7)
-#undef DP_FB
+            if (tid < 32) {
+                __syncwarp();
+                if (tid == 0) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        za[r] = sm.spz[r];
+                        zb[r] = sm.spz[16 + r];
+                    }
                 }
+                __syncwarp();
             }
 
             // ---- inverse: amplitude-vs-delay samples into registers ------------------------
             cx<T> y[32];
-            if constexpr (P == 1) dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
+            dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
 
             // ---- windowed arg-max: one pass over y per fit of this template -------------
             int nts = 0;
@@ -633,9 +670,9 @@ template <class T, int R1, int P> DP_DEV void DpOfKernel<T, R1, P>::run(const Dp
 }
 
 #ifndef DP_HOST_EMU
-template <class T, int R1, int P>
+template <class T, int R1, int P, int IN>
 __global__ void __launch_bounds__(DpGeom<R1>::NT, 1) dp_of_kernel(const DpOfParams<T> prm) {
     extern __shared__ __align__(16) unsigned char dp_smem_raw[];
-    DpOfKernel<T, R1, P>::run(prm, dp_smem_raw);
+    DpOfKernel<T, R1, P, IN>::run(prm, dp_smem_raw);
 }
 #endif

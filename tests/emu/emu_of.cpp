@@ -34,7 +34,7 @@ template <class V> static void rd(std::ifstream& f, V* p, size_t n) { f.read(rei
 template <class T, int R1, int P>
 static void run_all(const dpplan::Geometry& g, dpplan::DeviceTables<T>& dt, const std::vector<dpplan::Channel>& chans,
                     const std::vector<double>& traces, int n_events, int subtract_first, std::vector<double>& out, int n_out) {
-    using K = DpOfKernel<T, R1, P>;
+    using K = DpOfKernel<T, R1, P, 0>;
     std::vector<DpChanDev<T>> cd(chans.size());
     int base = 0;
     for (size_t c = 0; c < chans.size(); ++c) {
