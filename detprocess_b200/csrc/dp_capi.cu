@@ -86,12 +86,11 @@ struct dp_of_plan {
 namespace {
 
 template <class T> int of_setup(dp_of_plan* p) {
-    if (p->geom.P != 1) return fail(DP_ERR_UNSUPPORTED, "trace length needs the split (P=2) path, not built yet");
     const int prec = sizeof(T) == 8 ? 0 : 1;
     for (int in = 0; in < 3; ++in) {
         size_t smem = 0;
         int grid_max = 0, occ = 0;
-        const int rc = dp_of_setup_table[prec][in](p->geom.R1, p->device, &smem, &grid_max, &occ);
+        const int rc = dp_of_setup_table[prec][in](p->geom.R1, p->geom.P, p->device, &smem, &grid_max, &occ);
         if (rc == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length for this precision");
         if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel setup: ") + cudaGetErrorString((cudaError_t)rc));
         if (occ < 1) return fail(DP_ERR_CUDA, "OF kernel does not fit on an SM");
@@ -102,7 +101,7 @@ template <class T> int of_setup(dp_of_plan* p) {
 }
 template <class T> int of_launch(dp_of_plan* p, const DpOfParams<T>& prm, int grid, cudaStream_t st) {
     const int prec = sizeof(T) == 8 ? 0 : 1;
-    const int rc = dp_of_launch_table[prec][prm.in_dtype](p->geom.R1, &prm, grid, p->smem, st);
+    const int rc = dp_of_launch_table[prec][prm.in_dtype](p->geom.R1, p->geom.P, &prm, grid, p->smem, st);
     if (rc == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length for this precision");
     if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     return DP_OK;
@@ -137,7 +136,8 @@ template <class T> int of_finalize(dp_of_plan* p) {
         dc.wj = w;
         if ((rc = upload(p->owned, dt.chans[c].wj_low, &w))) return rc;
         dc.wj_low = w;
-        dc.wj_nyq = dt.chans[c].wj_nyq;
+        if ((rc = upload(p->owned, dt.chans[c].wj_self, &w))) return rc;
+        dc.wj_self = w;
         dc.n_templ = (int)p->chans[c].templ.size();
         dc.n_slots = (int)p->chans[c].fits.size();
         dc.out_base = base;
@@ -150,7 +150,8 @@ template <class T> int of_finalize(dp_of_plan* p) {
             dc.templ[i].phi = ph;
             if ((rc = upload(p->owned, h.s_low, &ph))) return rc;
             dc.templ[i].s_low = ph;
-            dc.templ[i].phi_nyq = h.phi_nyq;
+            if ((rc = upload(p->owned, h.phi_self, &ph))) return rc;
+            dc.templ[i].phi_self = ph;
             dc.templ[i].norm = h.norm;
             dc.templ[i].tsum = h.tsum;
             dc.templ[i].pretrigger = h.pretrigger;
@@ -165,7 +166,7 @@ template <class T> int of_finalize(dp_of_plan* p) {
     if ((rc = upload(p->owned, cd, &dcd))) return rc;
     p->d_chans = dcd;
     if ((rc = of_setup<T>(p))) return rc;
-    p->scratch_per_cta = 64LL * p->geom.NT;
+    p->scratch_per_cta = 96LL * p->geom.NT;
     DP_CUDA(cudaMalloc(&p->scratch, sizeof(cx<T>) * (size_t)p->scratch_per_cta * (size_t)p->grid_max));
     p->owned.push_back(p->scratch);
     return DP_OK;

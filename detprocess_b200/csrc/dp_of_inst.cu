@@ -1,6 +1,10 @@
 // One translation unit per (precision, input type): compiled several times by
 // detprocess_b200/build.py with -DDP_INST_PREC={0,1} -DDP_INST_IN={0,1,2} so the
 // kernel instantiations build in parallel.
+//
+// Geometries built: nb_samples = 1024 * R1 * P.
+//   P = 1: R1 = 2..32 (fp32), 2..16 (fp64: M' = 16384 complex f64 exceeds one CTA's smem)
+//   P = 2: the largest sub-FFT only (fp32: 65536 samples, fp64: 32768 samples)
 #include <cuda_runtime.h>
 
 #include "dp_of_kernel.cuh"
@@ -8,16 +12,18 @@
 
 #if DP_INST_PREC == 0
 using InstT = double;
+constexpr int kR1Max = 16;
 #else
 using InstT = float;
+constexpr int kR1Max = 32;
 #endif
 constexpr int kIN = DP_INST_IN;
 
 namespace {
 
-template <int R1> int setup_one(int device, size_t* smem, int* grid_max, int* occ_out) {
-    using K = DpOfKernel<InstT, R1, 1, kIN>;
-    auto kern = dp_of_kernel<InstT, R1, 1, kIN>;
+template <int R1, int P> int setup_one(int device, size_t* smem, int* grid_max, int* occ_out) {
+    using K = DpOfKernel<InstT, R1, P, kIN>;
+    auto kern = dp_of_kernel<InstT, R1, P, kIN>;
     *smem = K::SMEM_BYTES;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -32,8 +38,8 @@ template <int R1> int setup_one(int device, size_t* smem, int* grid_max, int* oc
     return 0;
 }
 
-template <int R1> int launch_one(const DpOfParams<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
-    dp_of_kernel<InstT, R1, 1, kIN><<<grid, DpGeom<R1>::NT, smem, st>>>(prm);
+template <int R1, int P> int launch_one(const DpOfParams<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
+    dp_of_kernel<InstT, R1, P, kIN><<<grid, DpGeom<R1>::NT, smem, st>>>(prm);
     return (int)cudaGetLastError();
 }
 
@@ -42,33 +48,30 @@ template <int R1> int launch_one(const DpOfParams<InstT>& prm, int grid, size_t 
 #define DP_CAT2(a, b, c) a##b##_##c
 #define DP_CAT(a, b, c) DP_CAT2(a, b, c)
 
-// f64 traces do not fit one CTA's shared memory beyond M' = 8192 (R1 = 16)
-#if DP_INST_PREC == 0
-#define DP_R1_32(FN, ...) return -1;
-#else
-#define DP_R1_32(FN, ...) return FN<32>(__VA_ARGS__);
-#endif
-
-int DP_CAT(dp_of_setup_p, DP_INST_PREC, DP_INST_IN)(int R1, int device, size_t* smem, int* grid_max, int* occ) {
+int DP_CAT(dp_of_setup_p, DP_INST_PREC, DP_INST_IN)(int R1, int P, int device, size_t* smem, int* grid_max, int* occ) {
+    if (P == 2) return R1 == kR1Max ? setup_one<kR1Max, 2>(device, smem, grid_max, occ) : -1;
+    if (P != 1 || R1 > kR1Max) return -1;
     switch (R1) {
-        case 2: return setup_one<2>(device, smem, grid_max, occ);
-        case 4: return setup_one<4>(device, smem, grid_max, occ);
-        case 8: return setup_one<8>(device, smem, grid_max, occ);
-        case 16: return setup_one<16>(device, smem, grid_max, occ);
-        case 32: DP_R1_32(setup_one, device, smem, grid_max, occ)
+        case 2: return setup_one<2, 1>(device, smem, grid_max, occ);
+        case 4: return setup_one<4, 1>(device, smem, grid_max, occ);
+        case 8: return setup_one<8, 1>(device, smem, grid_max, occ);
+        case 16: return setup_one<16, 1>(device, smem, grid_max, occ);
+        case 32: return setup_one<(kR1Max >= 32 ? 32 : 16), 1>(device, smem, grid_max, occ);
         default: return -1;
     }
 }
 
-int DP_CAT(dp_of_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
+int DP_CAT(dp_of_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, int P, const void* prm_v, int grid, size_t smem, void* st_v) {
     const DpOfParams<InstT>& prm = *reinterpret_cast<const DpOfParams<InstT>*>(prm_v);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
+    if (P == 2) return R1 == kR1Max ? launch_one<kR1Max, 2>(prm, grid, smem, st) : -1;
+    if (P != 1 || R1 > kR1Max) return -1;
     switch (R1) {
-        case 2: return launch_one<2>(prm, grid, smem, st);
-        case 4: return launch_one<4>(prm, grid, smem, st);
-        case 8: return launch_one<8>(prm, grid, smem, st);
-        case 16: return launch_one<16>(prm, grid, smem, st);
-        case 32: DP_R1_32(launch_one, prm, grid, smem, st)
+        case 2: return launch_one<2, 1>(prm, grid, smem, st);
+        case 4: return launch_one<4, 1>(prm, grid, smem, st);
+        case 8: return launch_one<8, 1>(prm, grid, smem, st);
+        case 16: return launch_one<16, 1>(prm, grid, smem, st);
+        case 32: return launch_one<(kR1Max >= 32 ? 32 : 16), 1>(prm, grid, smem, st);
         default: return -1;
     }
 }

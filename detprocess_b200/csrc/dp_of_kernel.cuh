@@ -27,7 +27,7 @@
 #define DP_MAX_TEMPLATES 4
 #define DP_MAX_SLOTS 8   // fits per channel
 #define DP_MAX_TSLOTS 4  // fits per template
-#define DP_NLOW_MAX 512
+#define DP_NLOW_MAX 1024
 #define DP_SLOT_NOUT 5  // amp, ind, chi2, lowchi2, timeres
 
 struct DpSlot {
@@ -37,8 +37,8 @@ struct DpSlot {
 };
 
 template <class T> struct DpTemplDev {
-    const cx<T>* phi;    // [32*P][NT] thread-order filter
-    cx<T> phi_nyq;       // filter at k = N/2
+    const cx<T>* phi;       // [32*P][NT] thread-order filter
+    const cx<T>* phi_self;  // [17][2*P] filter at the bins of the self-paired butterflies
     const cx<T>* s_low;  // [nlow] scaled template spectrum, natural order
     double norm;         // QETpy OF norm
     double tsum;         // sum((2 pi f)^2 |s|^2 / J) * df
@@ -47,9 +47,9 @@ template <class T> struct DpTemplDev {
 };
 
 template <class T> struct DpChanDev {
-    const T* wj;      // [32*P][NT] thread-order chi0 weights
-    const T* wj_low;  // [nlow] natural order
-    T wj_nyq;
+    const T* wj;       // [32*P][NT] thread-order chi0 weights
+    const T* wj_self;  // [17][2*P] weights at the bins of the self-paired butterflies (0 for duplicates)
+    const T* wj_low;   // [nlow] natural order
     int n_templ;
     int n_slots;
     int out_base;  // offset (doubles) of this channel's block in an event's output row
@@ -363,74 +363,214 @@ template <class T> DP_DEV void dp_retangle(cx<T> Fk, cx<T> Fm, cx<T> w, cx<T>& C
 }
 
 // ======================================================================== kernel
-// Self-paired butterflies.  Thread 0 owns K12 = 0 (k = KQ*r: pairs r <-> 16-r, r = 0 is
-// DC/Nyquist, r = 8 is k = M/2) and K12 = KQ/2 (k = KQ/2 + KQ*r: pairs r <-> 15-r).
-// Their 17 pairs are processed by lanes 0..16 of warp 0 through a 32-element shared
-// scratch, so warp 0 does not execute a second unrolled copy of the point-wise code.
-template <class T> struct DpSelfPair {
-    int ek, em;   // element slots (0..15 = A, 16..31 = B) of k and its mirror
-    cx<T> w;      // exp(-2 pi i k / N) of the pair
-    bool dc;      // the (DC, Nyquist) pair
+// Self-paired butterflies.  Thread 0 owns K12 = 0 (k' = KQ*r: r pairs with 16-r; r = 0
+// holds DC/Nyquist, r = 8 is its own mirror) and K12 = KQ/2 (k' = KQ/2 + KQ*r: r pairs
+// with 15-r).  Their 17 pairs are processed by lanes 0..16 of warp 0 through a small
+// shared scratch, so warp 0 does not run a second unrolled copy of the point-wise code;
+// bins and duplicate handling live in the host-built phi_self / wj_self tables.
+template <class T> struct DpSelfLane {
+    int ek, em;  // element slots (0..15 = A, 16..31 = B) of k' and of its mirror
+    cx<T> w;     // exp(-2 pi i k' / N)
+    cx<T> u;     // exp(-2 pi i k' / M)   (P = 2 only)
 };
-template <class T> DP_DEV DpSelfPair<T> dp_self_pair(int lane) {
-    DpSelfPair<T> sp;
+template <class T, int P> DP_DEV DpSelfLane<T> dp_self_lane(int lane) {
+    DpSelfLane<T> sp;
     double s_, c_;
+    int num;  // k' / (KQ/2)
     if (lane < 9) {
-        const int r = lane;
-        sp.ek = r;
-        sp.em = (16 - r) & 15;
-        sincospi(-2.0 * (double)r / 32.0, &s_, &c_);
+        sp.ek = lane;
+        sp.em = (16 - lane) & 15;
+        num = 2 * lane;
     } else {
-        const int r = lane - 9;
+        const int r = (lane - 9) & 7;
         sp.ek = 16 + r;
         sp.em = 16 + 15 - r;
-        sincospi(-2.0 * (double)(1 + 2 * r) / 64.0, &s_, &c_);
+        num = 1 + 2 * r;
     }
+    // KQ/2 / N = 1/(64*P),  KQ/2 / M = 1/(32*P)
+    sincospi(-2.0 * (double)num / (64.0 * P), &s_, &c_);
     sp.w = cx<T>{(T)c_, (T)s_};
-    sp.dc = lane == 0;
+    sincospi(-2.0 * (double)num / (32.0 * P), &s_, &c_);
+    sp.u = cx<T>{(T)c_, (T)s_};
     return sp;
+}
+
+// P = 2 quad: Z_p at k' (k) and at k'' = M' - k' (m);  u = exp(-2 pi i k'/M), w1 = exp(-2 pi i k'/N).
+// X[0..3] = 2*X at bins k', M-k', k'+M', M'-k'.
+template <class T>
+DP_DEV void dp_quad_x(cx<T> Z0k, cx<T> Z1k, cx<T> Z0m, cx<T> Z1m, cx<T> u, cx<T> w1, cx<T> (&X)[4]) {
+    const cx<T> t = cmul(u, Z1k), q = cmulc(Z1m, u);
+    dp_untangle(cadd(Z0k, t), cadd(Z0m, q), w1, X[0], X[1]);
+    dp_untangle(csub(Z0k, t), csub(Z0m, q), cmulni(w1), X[2], X[3]);
+}
+template <class T>
+DP_DEV void dp_quad_z(const cx<T> (&F)[4], cx<T> u, cx<T> w1, cx<T>& Z0k, cx<T>& Z1k, cx<T>& Z0m, cx<T>& Z1m) {
+    cx<T> Ck, Cmp, Ckp, Cm;
+    dp_retangle(F[0], F[1], w1, Ck, Cmp);
+    dp_retangle(F[2], F[3], cmulni(w1), Ckp, Cm);
+    Z0k = cadd(Ck, Ckp);
+    Z1k = cmulc(csub(Ck, Ckp), u);
+    Z0m = cadd(Cm, Cmp);
+    const cx<T> d = csub(Cmp, Cm);  // (Cm - Cmp) * (-u)
+    Z1m = cmul(d, u);
 }
 
 template <class T, int R1, int P, int IN> struct DpOfKernel {
     using G = DpGeom<R1>;
     static constexpr int NT = G::NT;
-    static constexpr int NE = 32 * P;  // table entries (and X values) per thread
+    static constexpr int NW = (NT + 31) / 32;
+    static constexpr int NE = 32 * P;  // table entries per thread
     static constexpr int N = 2 * P * G::MS;
-    static constexpr int RED_DOUBLES = (DP_MAX_TSLOTS + 1) * 32 + 8;
-    static constexpr int BEST_ELEMS = DP_MAX_TSLOTS * 32 + DP_MAX_TSLOTS;
-    static constexpr int SP_ELEMS = 33 + 32;  // self-pair X (+ Nyquist) and Z'
-    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (G::SMEM_ELEMS + DP_NLOW_MAX + SP_ELEMS + 1) +
-                                         sizeof(double) * RED_DOUBLES + sizeof(DpBest<T>) * BEST_ELEMS +
-                                         sizeof(int) * DP_MAX_TSLOTS + 64;
+    static constexpr int RED_DOUBLES = (DP_MAX_TSLOTS + 1) * 32;
+    static constexpr int BEST_ELEMS = DP_MAX_TSLOTS * 32;
+    static constexpr int SP_ELEMS = 64;  // thread 0's butterflies: [0..31] sub-sequence 1 (or the only one), [32..63] sub-sequence 0
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (G::SMEM_ELEMS + DP_NLOW_MAX + SP_ELEMS) +
+                                         2 * (sizeof(double) * RED_DOUBLES + sizeof(DpBest<T>) * BEST_ELEMS +
+                                              sizeof(int) * DP_MAX_TSLOTS) + 64;
 
     struct Smem {
         cx<T>* buf;
         cx<T>* stash;
-        cx<T>* spx;  // [33] X of thread 0's butterflies (A: 0..15, B: 16..31), [32] = X at Nyquist
-        cx<T>* spz;  // [32] Z' of the same
-        double* red;
-        DpBest<T>* best;  // [DP_MAX_TSLOTS][32] per-warp + [DP_MAX_TSLOTS] final
-        int* slot_id;     // [DP_MAX_TSLOTS]
+        cx<T>* sp;
+        // double-buffered epilogue arrays (buffer = parity of the template iteration)
+        double* red0;      // [2][DP_MAX_TSLOTS + 1][32] per-warp partial sums
+        DpBest<T>* best0;  // [2][DP_MAX_TSLOTS][32] per-warp arg-max
+        int* slot0;        // [2][DP_MAX_TSLOTS]
+        DP_DEV double* red(int par) const { return red0 + par * RED_DOUBLES; }
+        DP_DEV DpBest<T>* best(int par) const { return best0 + par * BEST_ELEMS; }
+        DP_DEV int* slot_id(int par) const { return slot0 + par * DP_MAX_TSLOTS; }
     };
     static DP_DEV Smem carve(unsigned char* raw) {
         Smem s;
         s.buf = reinterpret_cast<cx<T>*>(raw);
         s.stash = s.buf + G::SMEM_ELEMS;
-        s.spx = s.stash + DP_NLOW_MAX;
-        s.spz = s.spx + 33;
-        s.red = reinterpret_cast<double*>(s.spz + 33);
-        s.best = reinterpret_cast<DpBest<T>*>(s.red + RED_DOUBLES);
-        s.slot_id = reinterpret_cast<int*>(s.best + BEST_ELEMS);
+        s.sp = s.stash + DP_NLOW_MAX;
+        s.red0 = reinterpret_cast<double*>(s.sp + SP_ELEMS);
+        s.best0 = reinterpret_cast<DpBest<T>*>(s.red0 + 2 * RED_DOUBLES);
+        s.slot0 = reinterpret_cast<int*>(s.best0 + 2 * BEST_ELEMS);
         return s;
     }
 
-    static DP_DEV void run(const DpOfParams<T>& prm, unsigned char* smem_raw);
+    // ---- windowed arg-max of one inverse sub-FFT: one pass over y per fit of template `it`
+    // Per-warp winners go to best[q][warp]; `merge` folds them into the previous round
+    // (P = 2: the two sub-sequences are scanned one after the other).
+    static DP_DEV int scan_slots(const cx<T> (&y)[32], const DpChanDev<T>& ch, int it, int p, bool merge,
+                                 DpBest<T>* best, int* slot_id) {
+        const int tid = threadIdx.x;
+        int nts = 0;
+        for (int s = 0; s < ch.n_slots; ++s) {
+            const DpSlot sl = ch.slots[s];
+            if (sl.templ != it) continue;
+            DpBest<T> b{(T)0, -1};
+            if (sl.lo == 0 && sl.hi == N && !sl.outside)
+                DpScan<T, R1, P>::full(y, tid, p, b);
+            else
+                DpScan<T, R1, P>::window(y, tid, p, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, b);
+            b = dp_warp_best(b);
+            if ((tid & 31) == 0) {
+                if (merge) dp_best_merge(b, best[nts * 32 + (tid >> 5)]);
+                best[nts * 32 + (tid >> 5)] = b;
+            }
+            if (tid == 0) slot_id[nts] = s;
+            ++nts;
+        }
+        return nts;
+    }
+
+    // ---- low-frequency chi2 at each fit's (amp, delay), chi0, outputs.  Two barriers; the
+    // small smem arrays are double buffered so no trailing barrier is needed.
+    static DP_DEV void epilogue(const DpOfParams<T>& prm, const Smem& sm, const DpChanDev<T>& ch,
+                                const DpTemplDev<T>& tp, int it, int nts, int par, int ev, T chi, double& chi0_keep) {
+        const int tid = threadIdx.x;
+        DpBest<T>* best = sm.best(par);
+        double* red = sm.red(par);
+        __syncthreads();  // per-warp winners + (first template) the lowchi2 stash are visible
+        double part[DP_MAX_TSLOTS + 1];
+#pragma unroll
+        for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+            part[q] = 0.0;
+            if (q < nts && tid < prm.nlow) {
+                DpBest<T> b = best[q * 32];
+                for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
+                const int d = b.idx - tp.pretrigger;
+                for (int k = tid; k < prm.nlow; k += NT) {
+                    const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
+                    T sn, cs;
+                    if constexpr (sizeof(T) == 8) {
+                        double s_, c_;
+                        sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
+                        sn = (T)s_;
+                        cs = (T)c_;
+                    } else {
+                        float s_, c_;
+                        sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
+                        sn = (T)s_;
+                        cs = (T)c_;
+                    }
+                    const cx<T> mdl = cmul(cx<T>{cs, -sn}, dp_ldg(tp.s_low + k));
+                    const cx<T> X = sm.stash[k];
+                    const cx<T> R = cx<T>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
+                    part[q] += (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
+                }
+            }
+        }
+        part[DP_MAX_TSLOTS] = (it == 0) ? (double)chi : 0.0;
+#pragma unroll
+        for (int q = 0; q <= DP_MAX_TSLOTS; ++q) {
+            if (q < nts || (q == DP_MAX_TSLOTS && it == 0)) {
+                const double v = dp_warp_sum(part[q]);
+                if ((tid & 31) == 0) red[q * 32 + (tid >> 5)] = v;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
+            if (it == 0) {
+                double c0 = 0.0;
+                for (int w = 0; w < NW; ++w) c0 += red[DP_MAX_TSLOTS * 32 + w];
+                chi0_keep = c0;
+                o[0] = c0;
+            }
+            const double chi0 = chi0_keep;
+            for (int q = 0; q < nts; ++q) {
+                double low = 0.0;
+                for (int w = 0; w < NW; ++w) low += red[q * 32 + w];
+                DpBest<T> b = best[q * 32];
+                for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
+                double* os = o + 1 + sm.slot_id(par)[q] * DP_SLOT_NOUT;
+                const double amp = (double)b.val;
+                os[0] = amp;
+                os[1] = (double)b.idx;
+                os[2] = chi0 - amp * amp * tp.norm;
+                os[3] = low;
+                os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
+            }
+        }
+    }
+
+    static DP_DEV void prefetch_next(const DpOfParams<T>& prm, int row) {
+        constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
+        const int nrow = row + gridDim.x;
+        if (nrow < prm.n_rows) {
+            const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * ESZ;
+            constexpr int nlines = (int)((size_t)N * ESZ / 128);
+            for (int l = threadIdx.x; l < nlines; l += NT) dp_prefetch_l2(nx + (size_t)l * 128);
+        }
+    }
+
+    static DP_DEV void run(const DpOfParams<T>& prm, unsigned char* smem_raw) {
+        if constexpr (P == 1)
+            run_p1(prm, smem_raw);
+        else
+            run_p2(prm, smem_raw);
+    }
+    static DP_DEV void run_p1(const DpOfParams<T>& prm, unsigned char* smem_raw);
+    static DP_DEV void run_p2(const DpOfParams<T>& prm, unsigned char* smem_raw);
 };
 
-// The body is long; keep it out of the class for readability.
+// ------------------------------------------------------------------------- P = 1
 template <class T, int R1, int P, int IN>
-DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned char* smem_raw) {
-    static_assert(P == 1, "P = 2 (split) path is built separately");
+DP_DEV void DpOfKernel<T, R1, P, IN>::run_p1(const DpOfParams<T>& prm, unsigned char* smem_raw) {
     const Smem sm = carve(smem_raw);
     const int tid = threadIdx.x;
     int K12, bA, bB;
@@ -438,7 +578,9 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned cha
     const cx<T> wn = dp_ldg(prm.twn + tid);  // exp(-2 pi i K12 / N)
     cx<T>* scr = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
     constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
-    const DpSelfPair<T> sp = dp_self_pair<T>(tid & 31);
+    const DpSelfLane<T> sp = dp_self_lane<T, 1>(tid & 31);
+    int par = 0;
+    double chi0_keep = 0.0;
 
     for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
         const int chan = row % prm.n_chan;
@@ -446,37 +588,28 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned cha
         const DpChanDev<T>& ch = prm.chans[chan];
         const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
         const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
-        const double sc = prm.scale;
 
         cx<T> za[16], zb[16];
         T chi = (T)0;
-
-        dp_fwd_subfft<T, R1, 1, IN>(xrow, 0, x0, sc, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+        dp_fwd_subfft<T, R1, 1, IN>(xrow, 0, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
 
         // ---- self-paired butterflies of thread 0, cooperatively in warp 0 ------------------
+        cx<T> sXk = cx<T>{(T)0, (T)0}, sXm = sXk;  // lanes 0..16 of warp 0: 2*X of their pair
         if (tid < 32) {
             if (tid == 0) {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    sm.spx[r] = za[r];
-                    sm.spx[16 + r] = zb[r];
+                    sm.sp[r] = za[r];
+                    sm.sp[16 + r] = zb[r];
                 }
             }
             __syncwarp();
             if (tid < 17) {
-                cx<T> Xk, Xm;
-                dp_untangle(sm.spx[sp.ek], sm.spx[sp.em], sp.w, Xk, Xm);
-                chi = dp_fma(dp_ldg(ch.wj + sp.ek * NT), cnorm2(Xk), chi);
-                if (sp.dc)
-                    chi = dp_fma(ch.wj_nyq, cnorm2(Xm), chi);
-                else if (sp.ek != sp.em)
-                    chi = dp_fma(dp_ldg(ch.wj + sp.em * NT), cnorm2(Xm), chi);
-                sm.spx[sp.ek] = Xk;
-                if (sp.ek != sp.em) sm.spx[sp.em] = Xm;
-                if (sp.dc) {
-                    sm.spx[32] = Xm;    // X at Nyquist
-                    sm.stash[0] = Xk;   // X at DC, first lowchi2 bin
-                }
+                dp_untangle(sm.sp[sp.ek], sm.sp[sp.em], sp.w, sXk, sXm);
+                chi = dp_fma(dp_ldg(ch.wj_self + 2 * tid), cnorm2(sXk), chi);
+                chi = dp_fma(dp_ldg(ch.wj_self + 2 * tid + 1), cnorm2(sXm), chi);
+                if (tid == 0) sm.stash[0] = sXk;                          // X at DC, first lowchi2 bin
+                if (tid == 9 && G::KQ / 2 < prm.nlow) sm.stash[G::KQ / 2] = sXk;  // k = KQ/2
             }
             __syncwarp();
         }
@@ -498,27 +631,12 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned cha
 #undef DP_XP
             if (tid != 0) {
                 chi += chin;
-                // low-frequency bins for lowchi2: k = K12 < nlow lives in A[0]
+                // low-frequency bins for lowchi2: k = K12 lives in A[0], k = KQ - K12 in B[0]
                 if (K12 < prm.nlow) sm.stash[K12] = za[0];
-            } else {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    za[r] = sm.spx[r];
-                    zb[r] = sm.spx[16 + r];
-                }
+                if (G::KQ - K12 < prm.nlow) sm.stash[G::KQ - K12] = zb[0];
             }
         }
-
-        // L2 prefetch of the trace this CTA processes next: the load phase of the next
-        // event then overlaps with this event's compute instead of waiting on HBM.
-        {
-            const int nrow = row + gridDim.x;
-            if (nrow < prm.n_rows) {
-                const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * ESZ;
-                constexpr int nlines = (int)((size_t)N * ESZ / 128);
-                for (int l = tid; l < nlines; l += NT) dp_prefetch_l2(nx + (size_t)l * 128);
-            }
-        }
+        prefetch_next(prm, row);
 
         // multi-template: X must survive the in-place inverse of the previous template
         const bool spill_x = ch.n_templ > 1;
@@ -529,7 +647,6 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned cha
                 scr[(16 + r) * NT + tid] = zb[r];
             }
         }
-        __syncthreads();  // publishes the lowchi2 stash
 
         for (int it = 0; it < ch.n_templ; ++it) {
             const DpTemplDev<T>& tp = ch.templ[it];
@@ -542,12 +659,12 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned cha
             }
             // ---- filter + inverse untangle: (za, zb) <- Z' -----------------------------
             if (tid < 17) {
-                const cx<T> Fk = cmul(dp_ldg(tp.phi + sp.ek * NT), sm.spx[sp.ek]);
-                const cx<T> Fm = sp.dc ? cmul(tp.phi_nyq, sm.spx[32]) : cmul(dp_ldg(tp.phi + sp.em * NT), sm.spx[sp.em]);
+                const cx<T> Fk = cmul(dp_ldg(tp.phi_self + 2 * tid), sXk);
+                const cx<T> Fm = cmul(dp_ldg(tp.phi_self + 2 * tid + 1), sXm);
                 cx<T> Ck, Cm;
                 dp_retangle(Fk, Fm, sp.w, Ck, Cm);
-                sm.spz[sp.ek] = Ck;
-                if (sp.ek != sp.em) sm.spz[sp.em] = Cm;
+                sm.sp[sp.ek] = Ck;
+                if (sp.ek != sp.em) sm.sp[sp.em] = Cm;
             }
 #define DP_FP(r)                                                                                         \
     {                                                                                                    \
@@ -563,108 +680,179 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run(const DpOfParams<T>& prm, unsigned cha
                 if (tid == 0) {
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
-                        za[r] = sm.spz[r];
-                        zb[r] = sm.spz[16 + r];
+                        za[r] = sm.sp[r];
+                        zb[r] = sm.sp[16 + r];
                     }
                 }
                 __syncwarp();
             }
-
-            // ---- inverse: amplitude-vs-delay samples into registers ------------------------
+            // ---- inverse, windowed arg-max, outputs -----------------------------------------
             cx<T> y[32];
             dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
+            const int nts = scan_slots(y, ch, it, 0, false, sm.best(par), sm.slot_id(par));
+            epilogue(prm, sm, ch, tp, it, nts, par, ev, chi, chi0_keep);
+            par ^= 1;
+        }
+    }
+}
 
-            // ---- windowed arg-max: one pass over y per fit of this template -------------
-            int nts = 0;
-            for (int s = 0; s < ch.n_slots; ++s) {
-                const DpSlot sl = ch.slots[s];
-                if (sl.templ != it) continue;
-                DpBest<T> b{(T)0, -1};
-                if (sl.lo == 0 && sl.hi == N && !sl.outside)
-                    DpScan<T, R1, P>::full(y, tid, 0, b);
-                else
-                    DpScan<T, R1, P>::window(y, tid, 0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, b);
-                b = dp_warp_best(b);
-                if ((tid & 31) == 0) sm.best[nts * 32 + (tid >> 5)] = b;
-                if (tid == 0) sm.slot_id[nts] = s;
-                ++nts;
-            }
-            __syncthreads();
-            // warp q merges fit q
-            {
-                constexpr int NW = (NT + 31) / 32;
-                const int l = tid & 31;
-                for (int q = tid >> 5; q < nts; q += NW) {
-                    DpBest<T> b{(T)0, -1};
-                    if (l < NW) b = sm.best[q * 32 + l];
-                    b = dp_warp_best(b);
-                    if (l == 0) sm.best[DP_MAX_TSLOTS * 32 + q] = b;
-                }
-            }
-            __syncthreads();
-            // ---- low-frequency chi2 at each fit's (amp, delay); chi0 rides along -----------
-            {
-                double part[DP_MAX_TSLOTS + 1];
+// ------------------------------------------------------------------------- P = 2
+// N = 4*M': the packed complex sequence c[m] is split once more, z_p[m'] = c[2m'+p].  Z_0
+// is parked in a thread-private global scratch column (L2 resident) while Z_1 is
+// transformed; the outer radix-2, the real-FFT untangle, the filter and their inverses
+// are one thread-local "quad" step.
+template <class T, int R1, int P, int IN>
+DP_DEV void DpOfKernel<T, R1, P, IN>::run_p2(const DpOfParams<T>& prm, unsigned char* smem_raw) {
+    const Smem sm = carve(smem_raw);
+    const int tid = threadIdx.x;
+    int K12, bA, bB;
+    G::map(tid, K12, bA, bB);
+    const cx<T> wn = dp_ldg(prm.twn + tid);  // exp(-2 pi i K12 / N)
+    const cx<T> wp = dp_ldg(prm.twp + tid);  // exp(-2 pi i K12 / M)
+    cx<T>* scr0 = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;  // Z_0   [32][NT]
+    cx<T>* scr1 = scr0 + 32 * NT;                                             // Z_1   [32][NT] (multi-template)
+    cx<T>* scrz = scr1 + 32 * NT;                                             // Z'_0  [32][NT]
+    constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
+    const DpSelfLane<T> sp = dp_self_lane<T, 2>(tid & 31);
+    int par = 0;
+    double chi0_keep = 0.0;
+
+    for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
+        const int chan = row % prm.n_chan;
+        const int ev = row / prm.n_chan;
+        const DpChanDev<T>& ch = prm.chans[chan];
+        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
+        const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+
+        cx<T> za[16], zb[16];
+        T chi = (T)0;
+        // ---- forward: sub-sequence 0 -> scratch, sub-sequence 1 -> registers --------------
+        dp_fwd_subfft<T, R1, 2, IN>(xrow, 0, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
 #pragma unroll
-                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
-                    part[q] = 0.0;
-                    if (q < nts && tid < prm.nlow) {
-                        const DpBest<T> b = sm.best[DP_MAX_TSLOTS * 32 + q];
-                        const int k = tid;
-                        const int d = b.idx - tp.pretrigger;
-                        const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
-                        T sn, cs;
-                        if constexpr (sizeof(T) == 8) {
-                            double s_, c_;
-                            sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
-                            sn = (T)s_;
-                            cs = (T)c_;
-                        } else {
-                            float s_, c_;
-                            sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
-                            sn = (T)s_;
-                            cs = (T)c_;
-                        }
-                        const cx<T> mdl = cmul(cx<T>{cs, -sn}, dp_ldg(tp.s_low + k));
-                        const cx<T> X = sm.stash[k];
-                        const cx<T> R = cx<T>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
-                        part[q] = (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
-                    }
-                }
-                part[DP_MAX_TSLOTS] = (it == 0) ? (double)chi : 0.0;
+        for (int r = 0; r < 16; ++r) {
+            scr0[r * NT + tid] = za[r];
+            scr0[(16 + r) * NT + tid] = zb[r];
+        }
+        if (tid == 0) {
 #pragma unroll
-                for (int q = 0; q <= DP_MAX_TSLOTS; ++q) {
-                    if (q < nts || (q == DP_MAX_TSLOTS && it == 0)) {
-                        const double v = dp_warp_sum(part[q]);
-                        if ((tid & 31) == 0) sm.red[q * 32 + (tid >> 5)] = v;
-                    }
-                }
+            for (int r = 0; r < 16; ++r) {
+                sm.sp[32 + r] = za[r];
+                sm.sp[32 + 16 + r] = zb[r];
             }
-            __syncthreads();
+        }
+        __syncthreads();  // pass-3 reads of buf are done before the next pass-1 stores
+        dp_fwd_subfft<T, R1, 2, IN>(xrow, 1, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+        prefetch_next(prm, row);
+        const bool multi = ch.n_templ > 1;
+        if (multi) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                scr1[r * NT + tid] = za[r];
+                scr1[(16 + r) * NT + tid] = zb[r];
+            }
+        }
+        // self-paired butterflies: Z of thread 0 into shared scratch, X of each lane's quad in registers
+        cx<T> sX[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sX[j] = cx<T>{(T)0, (T)0};
+        if (tid < 32) {
             if (tid == 0) {
-                constexpr int NW = (NT + 31) / 32;
-                double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
-                if (it == 0) {
-                    double c0 = 0.0;
-                    for (int w = 0; w < NW; ++w) c0 += sm.red[DP_MAX_TSLOTS * 32 + w];
-                    sm.red[(DP_MAX_TSLOTS + 1) * 32] = c0;
-                    o[0] = c0;
-                }
-                const double chi0 = sm.red[(DP_MAX_TSLOTS + 1) * 32];
-                for (int q = 0; q < nts; ++q) {
-                    double low = 0.0;
-                    for (int w = 0; w < NW; ++w) low += sm.red[q * 32 + w];
-                    const DpBest<T> b = sm.best[DP_MAX_TSLOTS * 32 + q];
-                    double* os = o + 1 + sm.slot_id[q] * DP_SLOT_NOUT;
-                    const double amp = (double)b.val;
-                    os[0] = amp;
-                    os[1] = (double)b.idx;
-                    os[2] = chi0 - amp * amp * tp.norm;
-                    os[3] = low;
-                    os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    sm.sp[r] = za[r];
+                    sm.sp[16 + r] = zb[r];
                 }
             }
-            __syncthreads();  // buf / best / red reuse
+            __syncwarp();
+            if (tid < 17) {
+                dp_quad_x(sm.sp[32 + sp.ek], sm.sp[sp.ek], sm.sp[32 + sp.em], sm.sp[sp.em], sp.u, sp.w, sX);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) chi = dp_fma(dp_ldg(ch.wj_self + 4 * tid + j), cnorm2(sX[j]), chi);
+                if (tid == 0) sm.stash[0] = sX[0];
+                if (tid == 9 && G::KQ / 2 < prm.nlow) sm.stash[G::KQ / 2] = sX[0];
+            }
+            __syncwarp();
+        }
+
+        for (int it = 0; it < ch.n_templ; ++it) {
+            const DpTemplDev<T>& tp = ch.templ[it];
+            if (it > 0) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    za[r] = scr1[r * NT + tid];
+                    zb[r] = scr1[(16 + r) * NT + tid];
+                }
+            }
+            // ---- quads: outer radix-2 + untangle + filter + retangle + inverse radix-2 ------
+            if (tid < 17) {
+                cx<T> F[4], Z0k, Z1k, Z0m, Z1m;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) F[j] = cmul(dp_ldg(tp.phi_self + 4 * tid + j), sX[j]);
+                dp_quad_z(F, sp.u, sp.w, Z0k, Z1k, Z0m, Z1m);
+                sm.sp[32 + sp.ek] = Z0k;
+                sm.sp[sp.ek] = Z1k;
+                if (sp.ek != sp.em) {
+                    sm.sp[32 + sp.em] = Z0m;
+                    sm.sp[sp.em] = Z1m;
+                }
+            }
+            {
+                T chin = (T)0;
+                const bool first = it == 0;
+#define DP_QD(r)                                                                                         \
+    {                                                                                                    \
+        const cx<T> u = cmul(wp, dp_w64<T, 2 * r, -1>());                                                \
+        const cx<T> w1 = cmul(wn, dp_w64<T, r, -1>());                                                   \
+        cx<T> X[4], F[4], Z0k, Z0m;                                                                      \
+        dp_quad_x(scr0[r * NT + tid], za[r], scr0[(16 + 15 - r) * NT + tid], zb[15 - r], u, w1, X);      \
+        if (first) {                                                                                     \
+            chin = dp_fma(dp_ldg(ch.wj + (4 * r + 0) * NT + tid), cnorm2(X[0]), chin);                   \
+            chin = dp_fma(dp_ldg(ch.wj + (4 * r + 1) * NT + tid), cnorm2(X[1]), chin);                   \
+            chin = dp_fma(dp_ldg(ch.wj + (4 * r + 2) * NT + tid), cnorm2(X[2]), chin);                   \
+            chin = dp_fma(dp_ldg(ch.wj + (4 * r + 3) * NT + tid), cnorm2(X[3]), chin);                   \
+            if (r == 0 && tid != 0 && K12 < prm.nlow) sm.stash[K12] = X[0];                              \
+            if (r == 15 && tid != 0 && G::KQ - K12 < prm.nlow) sm.stash[G::KQ - K12] = X[3];             \
+        }                                                                                                \
+        F[0] = cmul(dp_ldg(tp.phi + (4 * r + 0) * NT + tid), X[0]);                                      \
+        F[1] = cmul(dp_ldg(tp.phi + (4 * r + 1) * NT + tid), X[1]);                                      \
+        F[2] = cmul(dp_ldg(tp.phi + (4 * r + 2) * NT + tid), X[2]);                                      \
+        F[3] = cmul(dp_ldg(tp.phi + (4 * r + 3) * NT + tid), X[3]);                                      \
+        dp_quad_z(F, u, w1, Z0k, za[r], Z0m, zb[15 - r]);                                                \
+        scrz[r * NT + tid] = Z0k;                                                                        \
+        scrz[(16 + 15 - r) * NT + tid] = Z0m;                                                            \
+    }
+                DP_QD(0) DP_QD(1) DP_QD(2) DP_QD(3) DP_QD(4) DP_QD(5) DP_QD(6) DP_QD(7)
+                DP_QD(8) DP_QD(9) DP_QD(10) DP_QD(11) DP_QD(12) DP_QD(13) DP_QD(14) DP_QD(15)
+#undef DP_QD
+                if (first && tid != 0) chi += chin;
+            }
+            if (tid < 32) {
+                __syncwarp();
+                if (tid == 0) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        za[r] = sm.sp[r];
+                        zb[r] = sm.sp[16 + r];
+                        scrz[r * NT] = sm.sp[32 + r];
+                        scrz[(16 + r) * NT] = sm.sp[32 + 16 + r];
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- inverse of sub-sequence 1, then 0; arg-max over both ------------------------
+            cx<T> y[32];
+            dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
+            scan_slots(y, ch, it, 1, false, sm.best(par), sm.slot_id(par));
+            __syncthreads();  // pass-1' reads of buf are done before the next pass-3' stores
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                za[r] = scrz[r * NT + tid];
+                zb[r] = scrz[(16 + r) * NT + tid];
+            }
+            dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
+            const int nts = scan_slots(y, ch, it, 0, true, sm.best(par), sm.slot_id(par));
+            epilogue(prm, sm, ch, tp, it, nts, par, ev, chi, chi0_keep);
+            par ^= 1;
         }
     }
 }

@@ -4,8 +4,8 @@
 #include <cstddef>
 
 #define DP_DECL_INST(p, in)                                                                      \
-    int dp_of_setup_p##p##_##in(int R1, int device, size_t* smem, int* grid_max, int* occ);      \
-    int dp_of_launch_p##p##_##in(int R1, const void* prm, int grid, size_t smem, void* stream);
+    int dp_of_setup_p##p##_##in(int R1, int P, int device, size_t* smem, int* grid_max, int* occ);      \
+    int dp_of_launch_p##p##_##in(int R1, int P, const void* prm, int grid, size_t smem, void* stream);
 DP_DECL_INST(0, 0)
 DP_DECL_INST(0, 1)
 DP_DECL_INST(0, 2)
@@ -14,8 +14,8 @@ DP_DECL_INST(1, 1)
 DP_DECL_INST(1, 2)
 #undef DP_DECL_INST
 
-typedef int (*dp_of_setup_fn)(int, int, size_t*, int*, int*);
-typedef int (*dp_of_launch_fn)(int, const void*, int, size_t, void*);
+typedef int (*dp_of_setup_fn)(int, int, int, size_t*, int*, int*);
+typedef int (*dp_of_launch_fn)(int, int, const void*, int, size_t, void*);
 static const dp_of_setup_fn dp_of_setup_table[2][3] = {{dp_of_setup_p0_0, dp_of_setup_p0_1, dp_of_setup_p0_2},
                                                        {dp_of_setup_p1_0, dp_of_setup_p1_1, dp_of_setup_p1_2}};
 static const dp_of_launch_fn dp_of_launch_table[2][3] = {{dp_of_launch_p0_0, dp_of_launch_p0_1, dp_of_launch_p0_2},

@@ -87,35 +87,66 @@ inline Geometry pick_geometry(int N, bool f64) {
     return g;
 }
 
-// k index held by thread t, element e (thread-order tables); P = 1: e in [0,32)
+// spectrum bin held by thread t, table entry e (thread-order tables).
+//   P = 1: e in [0,32): e < 16 -> A[e] (k = K12 + KQ e), else B[e-16] (k = K12' + KQ (e-16))
+//   P = 2: e = 4 r + j: quad r of the pair (A[r], B[15-r]) with k' = K12 + KQ r,
+//          j = 0: k', 1: M - k', 2: k' + M', 3: M' - k'
+// Entries of thread 0 are placeholders (its butterflies are self-paired, see self_bins).
 inline int k_of(const Geometry& g, int t, int e) {
-    const int R1 = g.R1, KQ = 32 * R1;
+    const int R1 = g.R1, KQ = 32 * R1, MS = g.MS, M = g.N / 2;
     const int k1 = t >> 4, k2 = t & 15;
     const int K12 = k1 + R1 * k2;
-    int K12p;
-    if (t == 0)
-        K12p = KQ / 2;
-    else
-        K12p = KQ - K12;
+    const int K12p = (t == 0) ? KQ / 2 : KQ - K12;
     if (g.P == 1) {
         if (e < 16) return K12 + KQ * e;
         return K12p + KQ * (e - 16);
     }
-    throw std::invalid_argument("k_of: P=2 handled by k_of_p2");
+    const int r = e >> 2, j = e & 3;
+    const int kp = K12 + KQ * r;
+    switch (j) {
+        case 0: return kp;
+        case 1: return (M - kp) % M;
+        case 2: return kp + MS;
+        default: return (MS - kp + M) % M;
+    }
+}
+
+// bins of self-pair lane l (0..16), 2*P entries: P = 1: (k, M-k); P = 2: (k', M-k', k'+M', M'-k').
+// The DC pair's mirror is the Nyquist bin M.  dup[j] marks bins already listed by the lane
+// (self-mirrored quads) whose chi0 weight must be zero.
+inline void self_bins(const Geometry& g, int l, int* bins, bool* dup) {
+    const int KQ = 32 * g.R1, MS = g.MS, M = g.N / 2;
+    int kp;
+    if (l < 9)
+        kp = KQ * l;
+    else
+        kp = KQ / 2 + KQ * (l - 9);
+    if (g.P == 1) {
+        bins[0] = kp;
+        bins[1] = (kp == 0) ? M : M - kp;
+    } else {
+        bins[0] = kp;
+        bins[1] = (kp == 0) ? M : M - kp;
+        bins[2] = kp + MS;
+        bins[3] = MS - kp;
+    }
+    for (int j = 0; j < 2 * g.P; ++j) {
+        dup[j] = false;
+        for (int i = 0; i < j; ++i)
+            if (bins[i] == bins[j]) dup[j] = true;
+    }
 }
 
 template <class T> struct DeviceTables {
     // flat host images; the C-ABI layer copies them to the device
     std::vector<cx<T>> tw1, tw2, twn, twp;
     struct Templ {
-        std::vector<cx<T>> phi, s_low;
-        cx<T> phi_nyq;
+        std::vector<cx<T>> phi, phi_self, s_low;
         double norm, tsum;
         int pretrigger;
     };
     struct Chan {
-        std::vector<T> wj, wj_low;
-        T wj_nyq;
+        std::vector<T> wj, wj_self, wj_low;
         std::vector<Templ> templ;
     };
     std::vector<Chan> chans;
@@ -160,15 +191,14 @@ inline int count_low_bins(int N, double fs, double fcut) {
 
 template <class T>
 DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Channel>& chans, double fcut, double scale) {
-    if (g.P != 1) throw std::invalid_argument("P=2 tables are built by build_tables_p2");
     DeviceTables<T> dt;
     const int N = g.N, M = N / 2, NT = g.NT, MS = g.MS;
     const double df = fs / N;
     dt.scale = scale;
     dt.nlow = count_low_bins(N, fs, fcut);
-    if (dt.nlow > NT || dt.nlow > DP_NLOW_MAX - 1)
+    if (dt.nlow > 2 * NT || dt.nlow > DP_NLOW_MAX)
         throw std::invalid_argument("lowchi2_fcutoff too high for the fused kernel (needs <= " +
-                                    std::to_string(std::min(NT, DP_NLOW_MAX - 1)) + " bins)");
+                                    std::to_string(std::min(2 * NT, DP_NLOW_MAX)) + " bins)");
     auto cxT = [](cplx z) { return cx<T>{(T)z.real(), (T)z.imag()}; };
     auto root = [](long long num, long long den) {  // exp(-2 pi i num/den)
         const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)num / (long double)den;
@@ -199,7 +229,13 @@ DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Cha
         dc.wj.resize((size_t)NE * NT);
         for (int e = 0; e < NE; ++e)
             for (int t = 0; t < NT; ++t) dc.wj[(size_t)e * NT + t] = (T)wJ[k_of(g, t, e)];
-        dc.wj_nyq = (T)wJ[M];
+        dc.wj_self.resize(17 * 2 * g.P);
+        for (int l = 0; l < 17; ++l) {
+            int bins[4];
+            bool dup[4];
+            self_bins(g, l, bins, dup);
+            for (int j = 0; j < 2 * g.P; ++j) dc.wj_self[l * 2 * g.P + j] = dup[j] ? (T)0 : (T)wJ[bins[j]];
+        }
         dc.wj_low.resize(dt.nlow);
         for (int k = 0; k < dt.nlow; ++k) dc.wj_low[k] = (T)wJ[k];
         for (const auto& tp : ch.templ) {
@@ -218,7 +254,13 @@ DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Cha
             d.phi.resize((size_t)NE * NT);
             for (int e = 0; e < NE; ++e)
                 for (int t = 0; t < NT; ++t) d.phi[(size_t)e * NT + t] = cxT(pe[k_of(g, t, e)]);
-            d.phi_nyq = cxT(pe[M]);
+            d.phi_self.resize(17 * 2 * g.P);
+            for (int l = 0; l < 17; ++l) {
+                int bins[4];
+                bool dup[4];
+                self_bins(g, l, bins, dup);
+                for (int j = 0; j < 2 * g.P; ++j) d.phi_self[l * 2 * g.P + j] = cxT(pe[bins[j]]);
+            }
             d.s_low.resize(dt.nlow);
             for (int k = 0; k < dt.nlow; ++k) d.s_low[k] = cxT(tp.s[k] * ((double)N * df) * 2.0 * scale);
             d.norm = tp.norm;

@@ -41,7 +41,7 @@ static void run_all(const dpplan::Geometry& g, dpplan::DeviceTables<T>& dt, cons
         auto& d = cd[c];
         d.wj = dt.chans[c].wj.data();
         d.wj_low = dt.chans[c].wj_low.data();
-        d.wj_nyq = dt.chans[c].wj_nyq;
+        d.wj_self = dt.chans[c].wj_self.data();
         d.n_templ = (int)chans[c].templ.size();
         d.n_slots = (int)chans[c].fits.size();
         d.out_base = base;
@@ -50,7 +50,7 @@ static void run_all(const dpplan::Geometry& g, dpplan::DeviceTables<T>& dt, cons
             auto& t = d.templ[i];
             auto& h = dt.chans[c].templ[i];
             t.phi = h.phi.data();
-            t.phi_nyq = h.phi_nyq;
+            t.phi_self = h.phi_self.data();
             t.s_low = h.s_low.data();
             t.norm = h.norm;
             t.tsum = h.tsum;
@@ -59,7 +59,7 @@ static void run_all(const dpplan::Geometry& g, dpplan::DeviceTables<T>& dt, cons
         for (int i = 0; i < d.n_slots; ++i) d.slots[i] = DpSlot{chans[c].fits[i].templ, chans[c].fits[i].lo, chans[c].fits[i].hi, chans[c].fits[i].outside};
     }
     const int grid = 2;
-    std::vector<cx<T>> scratch((size_t)grid * 64 * g.NT);
+    std::vector<cx<T>> scratch((size_t)grid * 96 * g.NT);
     DpOfParams<T> prm{};
     prm.traces = traces.data();
     prm.row_stride = g.N;
@@ -71,7 +71,7 @@ static void run_all(const dpplan::Geometry& g, dpplan::DeviceTables<T>& dt, cons
     prm.twn = dt.twn.data();
     prm.twp = dt.twp.data();
     prm.scratch = scratch.data();
-    prm.scratch_per_cta = 64 * g.NT;
+    prm.scratch_per_cta = 96 * g.NT;
     prm.out = out.data();
     prm.n_out = n_out;
     prm.nlow = dt.nlow;
@@ -86,7 +86,7 @@ static void run_all(const dpplan::Geometry& g, dpplan::DeviceTables<T>& dt, cons
     }
 }
 
-template <class T> static int main_t(const char* in, const char* outp) {
+template <class T> static int main_t(const char* in, const char* outp, bool force_p2) {
     std::ifstream f(in, std::ios::binary);
     int32_t hdr[6];
     rd(f, hdr, 6);
@@ -122,10 +122,16 @@ template <class T> static int main_t(const char* in, const char* outp) {
 
     const bool f64 = sizeof(T) == 8;
     dpplan::Geometry g = dpplan::pick_geometry(N, f64);
+    if (force_p2 && g.P == 1 && g.R1 >= 4) {
+        g.P = 2;
+        g.MS /= 2;
+        g.R1 /= 2;
+        g.NT /= 2;
+    }
     const int n_out = 1 + DP_SLOT_NOUT * n_fits;
     std::vector<double> out((size_t)n_events * n_out, -1.0);
+    auto dt = dpplan::build_tables<T>(g, fs, chans, fcut, scale);
     if (g.P == 1) {
-        auto dt = dpplan::build_tables<T>(g, fs, chans, fcut, scale);
         switch (g.R1) {
 #define CASE(r) case r: run_all<T, r, 1>(g, dt, chans, traces, n_events, subtract_first, out, n_out); break;
             CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
@@ -133,8 +139,13 @@ template <class T> static int main_t(const char* in, const char* outp) {
             default: std::fprintf(stderr, "bad R1\n"); return 3;
         }
     } else {
-        std::fprintf(stderr, "P=2 not built in this emulator yet\n");
-        return 4;
+        // the emulator also runs small split geometries the library does not build (P = 2, any R1)
+        switch (g.R1) {
+#define CASE(r) case r: run_all<T, r, 2>(g, dt, chans, traces, n_events, subtract_first, out, n_out); break;
+            CASE(2) CASE(4) CASE(8) CASE(16) CASE(32)
+#undef CASE
+            default: std::fprintf(stderr, "bad R1\n"); return 3;
+        }
     }
     std::ofstream o(outp, std::ios::binary);
     o.write(reinterpret_cast<const char*>(out.data()), sizeof(double) * out.size());
@@ -144,8 +155,9 @@ template <class T> static int main_t(const char* in, const char* outp) {
 int main(int argc, char** argv) {
     if (argc < 4) { std::fprintf(stderr, "usage: emu_of in out f32|f64\n"); return 1; }
     try {
-        if (std::string(argv[3]) == "f32") return main_t<float>(argv[1], argv[2]);
-        return main_t<double>(argv[1], argv[2]);
+        const bool p2 = argc > 4 && std::string(argv[4]) == "p2";
+        if (std::string(argv[3]) == "f32") return main_t<float>(argv[1], argv[2], p2);
+        return main_t<double>(argv[1], argv[2], p2);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 5;

@@ -22,7 +22,7 @@ def build(tsan=False):
 
 
 def run(traces, psd, templates, fits, fs, fcut=10000.0, precision='f64', ac=True,
-        subtract_first=False, scale=1.0, tsan=False):
+        subtract_first=False, scale=1.0, tsan=False, force_p2=False):
     """templates: list of (template, pretrigger, integralnorm); fits: list of (templ, lo, hi, outside)."""
     exe = build(tsan)
     traces = np.ascontiguousarray(traces, dtype=np.float64)
@@ -39,6 +39,6 @@ def run(traces, psd, templates, fits, fs, fcut=10000.0, precision='f64', ac=True
             for ft in fits:
                 f.write(struct.pack('<4i', *ft))
             f.write(traces.tobytes())
-        subprocess.check_call([exe, fin, fout, precision])
+        subprocess.check_call([exe, fin, fout, precision] + (['p2'] if force_p2 else []))
         out = np.fromfile(fout, dtype=np.float64).reshape(nev, 1 + 5 * len(fits))
     return out

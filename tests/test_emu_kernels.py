@@ -1,0 +1,87 @@
+"""
+The kernel SOURCE (detprocess_b200/csrc/*.cuh) compiled with g++ against a host-thread
+CTA emulator (tests/emu): index maths, barrier placement, table layouts and the numpy
+pairwise-summation order are checked here without a GPU.  The emulator is test
+infrastructure only -- the product has no CPU path.
+"""
+import os
+import struct
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'emu'))
+import run_emu  # noqa: E402
+
+from detprocess_b200.synth import SynthSetup, make_traces  # noqa: E402
+from oracle.of1x1 import of1x1_batch  # noqa: E402
+from oracle import reductions as R  # noqa: E402
+
+
+def _check(out, o, fits_off, tol_amp, tol_chi2, tol_low):
+    for iw, off in enumerate(fits_off):
+        b = out[:, off:off + 5]
+        assert np.array_equal(b[:, 1].astype(np.int64), o['ind'][iw])
+        assert np.max(np.abs(b[:, 0] / o['amp'][iw] - 1)) < tol_amp
+        assert np.max(np.abs(b[:, 2] / o['chi2'][iw] - 1)) < tol_chi2
+        assert np.max(np.abs(b[:, 3] / o['lowchi2'][iw] - 1)) < tol_low
+        assert np.max(np.abs(b[:, 4] / o['timeres'][iw] - 1)) < 4 * tol_amp
+
+
+@pytest.mark.parametrize('nb_samples,precision,force_p2', [
+    (2048, 'f64', False), (4096, 'f32', False), (8192, 'f64', False),
+    (4096, 'f64', True), (8192, 'f32', True)])
+def test_of_kernel_emulated(nb_samples, precision, force_p2):
+    S = SynthSetup(nb_samples)
+    pre = S.nb_pretrigger
+    tr = make_traces(3, S.template, S.psd, S.fs, np.random.default_rng(5),
+                     offset=(1e-6 if precision == 'f64' else 0.0), amp_max=2e-7)
+    w_def = [(None, None, False), (pre - 500, pre + 500, False), (pre, pre + 1, False)]
+    w_gl = [(pre - 100, pre + 300, True)]
+    fits = [(0, 0 if w[0] is None else w[0], nb_samples if w[1] is None else w[1], int(w[2])) for w in w_def]
+    fits += [(1, w[0], w[1], int(w[2])) for w in w_gl]
+    out = run_emu.run(tr, S.psd, [(S.template, pre, False), (S.template_glitch, pre, False)], fits, S.fs,
+                      precision=precision, subtract_first=(precision == 'f32'),
+                      scale=(2.0 ** 26 if precision == 'f32' else 1.0), force_p2=force_p2)
+    o1 = of1x1_batch(tr, S.template, S.psd, S.fs, pre, windows=w_def)
+    o2 = of1x1_batch(tr, S.template_glitch, S.psd, S.fs, pre, windows=w_gl)
+    tol = (1e-11, 1e-11, 1e-11) if precision == 'f64' else (1e-5, 1e-4, 1e-4)
+    assert np.max(np.abs(out[:, 0] / o1['chi0'] - 1)) < tol[1]
+    _check(out, o1, [1, 6, 11], *tol)
+    _check(out, o2, [16], *tol)
+
+
+def test_reduce_kernel_emulated_bit_exact():
+    exe = os.path.join(HERE, 'emu', '_build', 'emu_reduce')
+    src = os.path.join(HERE, 'emu', 'emu_reduce.cpp')
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(['g++', '-std=c++20', '-O1', '-pthread', '-o', exe, src])
+    rng = np.random.default_rng(3)
+    n, nev, fs = 8192, 3, 1.25e6
+    tr = rng.standard_normal((nev, n)) * 1e-8 + 3e-7
+    tr[1, 500] = np.nan
+    feats = [(0, 0, 3000), (1, 3500, 4750), (2, 0, n - 1), (3, 0, n - 1), (0, 100, 105), (1, 7, 8), (0, 3, 3 + 129),
+             (1, 1, 1 + 1025), (0, 0, n), (2, 501, 600), (0, 17, 17 + 8), (1, 40, 40 + 10), (0, 9, 9)]
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, 'i.bin'), os.path.join(td, 'o.bin')
+        with open(fin, 'wb') as f:
+            f.write(struct.pack('<3i', n, nev, len(feats)))
+            f.write(struct.pack('<d', fs))
+            for ft in feats:
+                f.write(struct.pack('<3i', *ft))
+            f.write(tr.tobytes())
+        subprocess.check_call([exe, fin, fout])
+        out = np.fromfile(fout).reshape(nev, len(feats))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for i, (op, a, b) in enumerate(feats):
+            ref = [R.baseline_batch, lambda t, a, b: R.integral_batch(t, fs, a, b), R.maximum_batch,
+                   R.minimum_batch][op](tr, a, b)
+            nan = np.isnan(ref)
+            assert np.array_equal(np.isnan(out[:, i]), nan)
+            assert np.array_equal(out[:, i][~nan].view(np.uint64), ref[~nan].view(np.uint64)), (op, a, b)

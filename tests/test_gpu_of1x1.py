@@ -67,8 +67,9 @@ def _compare(plan, fit, out, o, iw, tol, amp_floor):
     assert np.max(np.abs(tres / o['timeres'][iw] - 1)[sel & big]) < max(tol['tres'], tol['amp'] * 2)
 
 
-@pytest.mark.parametrize('precision,nb_samples', [('f64', 2048), ('f64', 4096), ('f64', 16384),
-                                                  ('f32', 2048), ('f32', 8192), ('f32', 16384), ('f32', 32768)])
+@pytest.mark.parametrize('precision,nb_samples', [('f64', 2048), ('f64', 4096), ('f64', 16384), ('f64', 32768),
+                                                  ('f32', 2048), ('f32', 8192), ('f32', 16384), ('f32', 32768),
+                                                  ('f32', 65536)])
 def test_of1x1_parity_single_template(precision, nb_samples):
     S = SynthSetup(nb_samples)
     nev = 300
@@ -82,7 +83,7 @@ def test_of1x1_parity_single_template(precision, nb_samples):
         _compare(plan, fit, out, o, iw, tol, amp_floor=5 * o['ampres'])
 
 
-@pytest.mark.parametrize('precision,nb_samples', [('f64', 16384), ('f32', 32768)])
+@pytest.mark.parametrize('precision,nb_samples', [('f64', 16384), ('f64', 32768), ('f32', 32768), ('f32', 65536)])
 def test_of1x1_parity_glitch_template_variant(precision, nb_samples):
     """C2 shape: constrained fit with the default and the glitch template on the same events."""
     S = SynthSetup(nb_samples)

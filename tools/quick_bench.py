@@ -62,6 +62,9 @@ if __name__ == '__main__':
     time_of(32768, 'f32', 8192, windows='c2')
     time_of(32768, 'f32', 8192, two_templ=True, windows='c2')
     time_of(16384, 'f32', 16384)
+    time_of(32768, 'f64', 8192)
+    time_of(32768, 'f64', 8192, two_templ=True, windows='c2')
+    time_of(65536, 'f32', 4096)
     time_of(16384, 'f64', 8192)
     time_of(8192, 'f64', 8192)
     time_reduce(32768, 8192)
