@@ -1,0 +1,160 @@
+"""
+``FeatureExtractors``: drop-in for the in-scope static methods of the reference's
+``detprocess/core/algorithms.py`` (same names, argument meaning, returned keys and
+``-999999.0`` sentinels):
+
+    of1x1_nodelay :278   of1x1_unconstrained :355   of1x1_constrained :436
+    baseline :651        integral :709              maximum :771        minimum :830
+
+OF methods take ``(channel, of_base, ...)`` where ``of_base`` is an ``OFBaseBatch`` holding a
+batch of B events on the device; trace methods take ``(trace, ...)`` where ``trace`` is
+``[N]`` or ``[B, N]`` (ndarray, CPU tensor or CUDA tensor).  For a batch every returned
+value is an array of length B; for a single trace it is a scalar, as in the reference.
+All arithmetic runs in the CUDA library; there is no CPU path.
+
+The class deliberately exposes no other public attribute: the reference's pipeline
+treats every non-underscore name as an algorithm (``process/features.py:1112-1116``).
+"""
+import numpy as np
+
+from .plans import ReducePlan
+
+__all__ = ['FeatureExtractors']
+
+_SENTINEL = -999999.0
+# Whether window_max_index itself is a candidate delay of the constrained fit.  The
+# reference forwards the index to QETpy, which slices [min:max) (see oracle/of1x1.py).
+_OF_WINDOW_MAX_INCLUSIVE = False
+_reduce_cache = {}
+
+
+def _scalarize(of_base, d):
+    if getattr(of_base, 'single', False):
+        return {k: (v[0] if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+    return d
+
+
+def _of_window(of_base, channel, template_tag, window_min_from_trig_usec, window_max_from_trig_usec,
+               window_min_index, window_max_index):
+    """usec form wins over the index form (QETpy OF1x1.calc); returns rolled [lo, hi)."""
+    n = of_base.nb_samples()
+    fs = of_base.sample_rate()
+    pre = of_base.pretrigger_samples(channel, template_tag)
+    lo = hi = None
+    if window_min_from_trig_usec is not None:
+        lo = int(np.floor(pre + window_min_from_trig_usec * fs * 1e-6))
+    elif window_min_index is not None:
+        lo = int(window_min_index)
+    if window_max_from_trig_usec is not None:
+        hi = int(np.ceil(pre + window_max_from_trig_usec * fs * 1e-6))
+    elif window_max_index is not None:
+        hi = int(window_max_index)
+    lo = 0 if lo is None else min(max(lo, 0), n)
+    hi = n if hi is None else min(max(hi + (1 if _OF_WINDOW_MAX_INCLUSIVE else 0), 0), n)
+    return lo, hi
+
+
+def _reduce(trace, op, window_min_index, window_max_index, fs):
+    """One windowed reduction on the device; returns ndarray [B] (or scalar for a 1-D trace)."""
+    import torch
+    single = trace.ndim == 1
+    if isinstance(trace, np.ndarray):
+        trace = torch.from_numpy(np.ascontiguousarray(trace, dtype=np.float64))
+    if trace.ndim == 1:
+        trace = trace[None, :]
+    n = trace.shape[-1]
+    key = (n, float(fs), op, window_min_index, window_max_index)
+    plan = _reduce_cache.get(key)
+    if plan is None:
+        plan = ReducePlan(n, fs, 1)
+        plan.add(0, op, window_min_index, window_max_index)
+        plan.finalize()
+        if len(_reduce_cache) > 256:
+            _reduce_cache.clear()
+        _reduce_cache[key] = plan
+    x = trace.to(device=plan.device, dtype=torch.float64)
+    out = plan.run(x).cpu().numpy()[:, 0]
+    return out[0] if single else out
+
+
+def _empty(trace):
+    if trace is None:
+        return True
+    size = trace.size if isinstance(trace, np.ndarray) else trace.numel()
+    return size == 0
+
+
+class FeatureExtractors:
+
+    @staticmethod
+    def of1x1_nodelay(channel, of_base, template_tag=None, lowchi2_fcutoff=10000,
+                      feature_base_name='of1x1_nodelay', **kwargs):
+        if template_tag is None:
+            raise ValueError('ERROR: Template tag required for OF 1x1')
+        names = ('amp', 'chi2', 'lowchi2')
+        if not of_base.is_signal_stored(channel):
+            return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
+        of_base.set_lowchi2_fcutoff(lowchi2_fcutoff)
+        pre = of_base.pretrigger_samples(channel, template_tag)
+        r = of_base.results(of_base.request_fit(channel, template_tag, pre, pre + 1))
+        return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
+
+    @staticmethod
+    def of1x1_unconstrained(channel, of_base, template_tag='default', interpolate=False,
+                            lowchi2_fcutoff=10000, feature_base_name='of1x1_unconstrained', **kwargs):
+        names = ('amp', 't0', 'chi2', 'lowchi2')
+        if not of_base.is_signal_stored(channel):
+            return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
+        if interpolate:
+            raise NotImplementedError('interpolate=True (parabolic t0 refinement) is not built')
+        of_base.set_lowchi2_fcutoff(lowchi2_fcutoff)
+        r = of_base.results(of_base.request_fit(channel, template_tag, None, None))
+        return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
+
+    @staticmethod
+    def of1x1_constrained(channel, of_base, template_tag='default',
+                          window_min_from_trig_usec=None, window_max_from_trig_usec=None,
+                          window_min_index=None, window_max_index=None, lgc_outside_window=False,
+                          interpolate=False, lowchi2_fcutoff=10000,
+                          feature_base_name='of1x1_constrained', **kwargs):
+        names = ('amp', 't0', 'chi2', 'lowchi2', 'chi2nopulse', 'ampres', 'timeres')
+        if not of_base.is_signal_stored(channel):
+            return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
+        if interpolate:
+            raise NotImplementedError('interpolate=True (parabolic t0 refinement) is not built')
+        of_base.set_lowchi2_fcutoff(lowchi2_fcutoff)
+        lo, hi = _of_window(of_base, channel, template_tag, window_min_from_trig_usec,
+                            window_max_from_trig_usec, window_min_index, window_max_index)
+        r = of_base.results(of_base.request_fit(channel, template_tag, lo, hi, lgc_outside_window))
+        return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
+
+    @staticmethod
+    def baseline(trace, window_min_index=None, window_max_index=None,
+                 feature_base_name='baseline', **kwargs):
+        if _empty(trace):
+            return {feature_base_name: _SENTINEL}
+        return {feature_base_name: _reduce(trace, 'baseline', window_min_index, window_max_index,
+                                           kwargs.get('fs', 1.0))}
+
+    @staticmethod
+    def integral(trace, fs, window_min_index=None, window_max_index=None,
+                 feature_base_name='integral', **kwargs):
+        if _empty(trace):
+            return {feature_base_name: _SENTINEL}
+        return {feature_base_name: _reduce(trace, 'integral', window_min_index, window_max_index, fs)}
+
+    @staticmethod
+    def maximum(trace, window_min_index=None, window_max_index=None,
+                feature_base_name='maximum', **kwargs):
+        if _empty(trace):
+            return {feature_base_name: _SENTINEL}
+        return {feature_base_name: _reduce(trace, 'maximum', window_min_index, window_max_index,
+                                           kwargs.get('fs', 1.0))}
+
+    @staticmethod
+    def minimum(trace, window_min_index=None, window_max_index=None,
+                feature_base_name='minimum', **kwargs):
+        if _empty(trace):
+            return {feature_base_name: _SENTINEL}
+        return {feature_base_name: _reduce(trace, 'minimum', window_min_index, window_max_index,
+                                           kwargs.get('fs', 1.0))}

@@ -1,0 +1,216 @@
+"""
+``OFBaseBatch``: the object passed as ``of_base`` to the ``FeatureExtractors`` OF methods.
+
+It exposes the ``qp.OFBase`` calls detprocess makes (reference
+``process/processing_data.py:278-381, 731-772``): ``set_csd``, ``add_template``,
+``calc_phi``, ``phi``, ``csd``, ``clear_signal``, ``update_signal``, ``is_signal_stored``,
+``calc_signal_filt``, ``calc_signal_filt_td`` -- but inverts the ownership: instead of
+one trace mutated per event it holds a ``[B, N]`` batch per channel on the device, runs
+the fused CUDA kernel once for every requested fit and lets the extractors index into
+the result columns.  The kernel launch is lazy: the first extractor call after
+``update_signal`` (or after a new fit was requested) triggers it.
+"""
+import numpy as np
+
+from .plans import OFPlan
+
+__all__ = ['OFBaseBatch']
+
+
+class OFBaseBatch:
+    def __init__(self, sample_rate, verbose=False, precision='f64', device=None):
+        self._fs = float(sample_rate)
+        self._verbose = verbose
+        self._precision = precision
+        self._device = device
+        self._nbins = None
+        self._chans = []       # channel names, dense order
+        self._psd = {}         # chan -> (psd, coupling)
+        self._templates = {}   # chan -> {tag: (template, pretrigger, integralnorm)}
+        self._fits = {}        # (chan, tag, lo, hi, outside) -> None
+        self._fcut = 10000.0
+        self._plan = None
+        self._plan_key = None
+        self._handles = {}
+        self._signals = {}     # chan -> tensor [B, N]
+        self._out = None       # host ndarray [B, n_out]
+
+    # ---- reference-shaped setup -------------------------------------------------
+    def sample_rate(self):
+        return self._fs
+
+    def nb_samples(self):
+        return self._nbins
+
+    def fft_freqs(self):
+        return np.fft.fftfreq(self._nbins, d=1.0 / self._fs)
+
+    def _check_n(self, n):
+        if self._nbins is None:
+            self._nbins = int(n)
+        elif self._nbins != int(n):
+            raise ValueError('ERROR: inconsistent number of samples')
+
+    def set_csd(self, channel, csd, coupling='AC', ignored_frequency_peaks=None, ignore_harmonics=False):
+        psd = np.array(np.real(np.asarray(csd)), dtype=np.float64).reshape(-1)
+        self._check_n(psd.shape[-1])
+        if ignored_frequency_peaks is not None:
+            # bins on an ignored peak carry no weight: J = inf  (handled on the host: 1/J = 0)
+            f = np.abs(self.fft_freqs())
+            df = self._fs / self._nbins
+            for pk in np.atleast_1d(np.asarray(ignored_frequency_peaks, dtype=float)):
+                lines = np.arange(pk, self._fs / 2, pk) if ignore_harmonics else [pk]
+                for fpk in lines:
+                    psd[np.abs(f - fpk) <= df / 2] = np.inf
+        if channel not in self._chans:
+            self._chans.append(channel)
+        self._psd[channel] = (psd, coupling)
+        self._plan = None
+
+    def csd(self, channel):
+        return self._psd[channel][0] if channel in self._psd else None
+
+    def add_template(self, channel, template, template_tag='default', pretrigger_samples=None,
+                     integralnorm=False, overwrite=False, **kwargs):
+        template = np.asarray(template, dtype=np.float64).reshape(-1)
+        self._check_n(template.shape[-1])
+        tags = self._templates.setdefault(channel, {})
+        if template_tag in tags and not overwrite:
+            raise ValueError(f'ERROR: template "{template_tag}" already exists (use overwrite=True)')
+        if pretrigger_samples is None:
+            pretrigger_samples = self._nbins // 2
+        tags[template_tag] = (template, int(pretrigger_samples), bool(integralnorm))
+        if channel not in self._chans:
+            self._chans.append(channel)
+        self._plan = None
+
+    def template(self, channel, template_tag='default'):
+        t = self._templates.get(channel, {}).get(template_tag)
+        return None if t is None else t[0]
+
+    def template_tags(self, channel):
+        return list(self._templates.get(channel, {}).keys())
+
+    def pretrigger_samples(self, channel, template_tag='default'):
+        return self._templates[channel][template_tag][1]
+
+    def calc_phi(self, channel, template_tag='default'):
+        self._ensure_plan()
+
+    def phi(self, channel, template_tag='default'):
+        if channel not in self._templates or template_tag not in self._templates[channel]:
+            return None
+        if channel not in self._psd:
+            return None
+        self._ensure_plan(finalize=False)
+        c, t = self._handles[('templ', channel, template_tag)]
+        return self._plan.phi(c, t)
+
+    def norm(self, channel, template_tag='default'):
+        self._ensure_plan(finalize=False)
+        c, t = self._handles[('templ', channel, template_tag)]
+        return self._plan.norm(c, t)
+
+    def set_lowchi2_fcutoff(self, fcutoff):
+        if float(fcutoff) != self._fcut:
+            self._fcut = float(fcutoff)
+            self._plan = None
+
+    # ---- fits (one per YAML OF algorithm block) ---------------------------------
+    def request_fit(self, channel, template_tag, lo, hi, outside=False):
+        key = (channel, template_tag, None if lo is None else int(lo), None if hi is None else int(hi), bool(outside))
+        if key not in self._fits:
+            if channel not in self._templates or template_tag not in self._templates[channel]:
+                raise ValueError(f'ERROR: no template "{template_tag}" for channel {channel}')
+            self._fits[key] = None
+            self._plan = None
+        return key
+
+    # ---- plan -------------------------------------------------------------------
+    def _ensure_plan(self, finalize=True):
+        if self._plan is not None and (self._plan.finalized or not finalize):
+            return
+        if self._plan is None:
+            chans = [c for c in self._chans if c in self._psd and c in self._templates]
+            if not chans:
+                raise ValueError('ERROR: no channel has both a csd and a template')
+            plan = OFPlan(self._nbins, self._fs, len(chans), self._precision)
+            plan.set_lowchi2_fcutoff(self._fcut)
+            handles = {}
+            for ci, chan in enumerate(chans):
+                psd, coupling = self._psd[chan]
+                plan.set_psd(ci, psd, coupling)
+                for tag, (tmpl, pre, inorm) in self._templates[chan].items():
+                    handles[('templ', chan, tag)] = (ci, plan.add_template(ci, tmpl, pre, inorm))
+            for key in self._fits:
+                chan, tag, lo, hi, outside = key
+                ci, ti = handles[('templ', chan, tag)]
+                handles[('fit',) + key] = (ci, plan.add_fit(ci, ti, lo, hi, outside))
+            self._plan, self._handles, self._plan_chans = plan, handles, chans
+            self._out = None
+        if finalize and not self._plan.finalized:
+            self._plan.finalize(self._device)
+
+    # ---- per batch --------------------------------------------------------------
+    def clear_signal(self):
+        self._signals = {}
+        self._out = None
+
+    def is_signal_stored(self, channel):
+        return channel in self._signals
+
+    def update_signal(self, channel, signal, calc_fft=True, **kwargs):
+        """signal: [N] or [B, N]; ndarray, CPU tensor or CUDA tensor (f64 / f32 / i16)."""
+        import torch
+        if isinstance(signal, np.ndarray):
+            signal = torch.from_numpy(np.ascontiguousarray(signal))
+        self._single = signal.ndim == 1
+        if signal.ndim == 1:
+            signal = signal[None, :]
+        if signal.shape[-1] != self._nbins:
+            raise ValueError('ERROR: signal length != template/psd length')
+        self._signals[channel] = signal
+        self._out = None
+
+    def signal(self, channel):
+        return self._signals.get(channel)
+
+    def calc_signal_filt(self, channel, template_tag=None):
+        return None   # fused into the kernel (phi * v / norm)
+
+    def calc_signal_filt_td(self, channel, template_tag=None):
+        return None   # fused into the kernel (inverse FFT)
+
+    def _run(self):
+        import torch
+        self._ensure_plan()
+        chans = self._plan_chans
+        missing = [c for c in chans if c not in self._signals]
+        if missing:
+            raise ValueError(f'ERROR: no signal stored for channel(s) {missing}')
+        dev = self._plan.device
+        cols = [self._signals[c].to(dev, non_blocking=True) for c in chans]
+        x = cols[0] if len(cols) == 1 else torch.stack(cols, dim=1)
+        self._out = self._plan.run(x.contiguous()).cpu().numpy()
+
+    def results(self, fit_key):
+        """dict of arrays for one fit: amp, ind, t0, chi2, lowchi2, timeres, chi2nopulse, ampres"""
+        if fit_key not in self._fits:
+            raise ValueError('ERROR: unknown fit (call request_fit first)')
+        if self._plan is None or self._out is None:
+            self._run()
+        chan, tag = fit_key[0], fit_key[1]
+        ci, fi = self._handles[('fit',) + fit_key]
+        off = self._plan.fit_offset(ci, fi)
+        o = self._out
+        pre = self._templates[chan][tag][1]
+        ind = o[:, off + 1].astype(np.int64)
+        res = {'amp': o[:, off], 'ind': ind, 't0': (ind - pre) / self._fs, 'chi2': o[:, off + 2],
+               'lowchi2': o[:, off + 3], 'timeres': o[:, off + 4],
+               'chi2nopulse': o[:, self._plan.chi0_offset(ci)],
+               'ampres': 1.0 / np.sqrt(self.norm(chan, tag))}
+        return res
+
+    @property
+    def single(self):
+        return getattr(self, '_single', False)

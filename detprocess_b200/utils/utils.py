@@ -1,0 +1,105 @@
+"""
+Host-side helpers with the semantics of the reference's ``detprocess/utils/utils.py``
+(channel-name algebra :70-184, window indices :189-301) and pytesio's
+``convert_length_msec_to_samples`` (used by ``process/config.py:10``).
+"""
+
+ALLOWED_SEPARATORS = [',', '|', '+', '-']
+
+
+def unique_list(seq):
+    seen = set()
+    out = []
+    for x in seq:
+        if x not in seen:
+            seen.add(x)
+            out.append(x)
+    return out
+
+
+def convert_length_msec_to_samples(length_msec, sample_rate):
+    """20 ms @ 1.25 MHz -> 25000 (matches the reference's saved YamlConfig output)."""
+    return int(round(float(length_msec) * 1e-3 * float(sample_rate)))
+
+
+def split_channel_name(channel_name, available_channels=None, separator=None, label=None):
+    """
+    Split "a,b" / "a+b" / "a-b" / "a|b" into individual channels.
+    Returns (channel_list, separator) like the reference (separator None when the name
+    is a single channel).  Same checks: unknown separators and unknown channels raise
+    ValueError; "-" needs ``available_channels``.
+    """
+    channel_name = channel_name.replace(' ', '')
+    if separator is not None and separator not in ALLOWED_SEPARATORS:
+        raise ValueError(f'ERROR: separator "{separator}" not recognized. '
+                         f'Allowed separator {ALLOWED_SEPARATORS} ')
+    if not any(sep in channel_name for sep in ALLOWED_SEPARATORS):
+        return [channel_name], None
+
+    if available_channels is None:
+        if separator is None:
+            raise ValueError('ERROR: separator required when "available_channels" not provided! ')
+        if separator == '-':
+            raise ValueError('ERROR: "available_channels" required when using separator "-"')
+        if separator == '+' and (',' in channel_name or '|' in channel_name):
+            raise ValueError(f'ERROR: Channels cannot be split with {separator} before channels '
+                             f'split with "," and "|"')
+        return channel_name.split(separator), separator
+
+    if channel_name in available_channels or channel_name == 'all':
+        return [channel_name], None
+
+    # strip known channel names; what is left must be separators only
+    remainder = channel_name
+    found = []
+    for chan in available_channels:
+        if chan in remainder:
+            remainder = remainder.replace(chan, '')
+            found.append(chan)
+    seps = list(set(remainder))
+    bad = [s for s in seps if s not in ALLOWED_SEPARATORS]
+    if bad:
+        raise ValueError(f'ERROR: Unidentified channel "{channel_name}" in yaml file! '
+                         f'Perhaps not in raw data? Available channels = {available_channels}')
+
+    if separator is None:
+        if len(seps) == 1:
+            sep = seps[0]
+            if sep != '-':
+                found = channel_name.split(sep)
+            return found, sep
+        return found, seps
+
+    if separator not in channel_name:
+        return [channel_name], None
+    if separator != '-':
+        return channel_name.split(separator), separator
+    if any(s in channel_name for s in ('|', '+', ',')):
+        raise ValueError('Multiple separators available, split first with other separators before "-"')
+    return list(found), separator
+
+
+def get_window_indices(nb_samples, nb_pretrigger_samples, fs,
+                       window_min_from_start_usec=None, window_min_to_end_usec=None,
+                       window_min_from_trig_usec=None, window_max_from_start_usec=None,
+                       window_max_to_end_usec=None, window_max_from_trig_usec=None, **kwargs):
+    """
+    usec -> sample indices exactly as FeatureProcessing._get_window_indices
+    (reference process/features.py:1243-1344): priority from_start > to_end > from_trig,
+    int() truncation, clamp to [0, N-1], ValueError if max < min.
+    """
+    def resolve(from_start, to_end, from_trig, default):
+        idx = default
+        if from_start is not None:
+            idx = int(from_start * fs * 1e-6)
+        elif to_end is not None:
+            idx = nb_samples - abs(int(to_end * fs * 1e-6)) - 1
+        elif from_trig is not None:
+            idx = nb_pretrigger_samples + int(from_trig * fs * 1e-6)
+        return min(max(idx, 0), nb_samples - 1)
+
+    lo = resolve(window_min_from_start_usec, window_min_to_end_usec, window_min_from_trig_usec, 0)
+    hi = resolve(window_max_from_start_usec, window_max_to_end_usec, window_max_from_trig_usec, nb_samples - 1)
+    if hi < lo:
+        raise ValueError('ERROR window calculation: max index smaller than min!Check configuration!')
+    return lo, hi

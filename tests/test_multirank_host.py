@@ -1,0 +1,60 @@
+"""World-size-2 gloo test (CPU) of the N>1 host path: contiguous event shards per rank, no
+data-path collective, one gather of the small feature tables."""
+import os
+import socket
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from detprocess_b200.process.features import shard_range, gather_frames, dist_info
+
+
+def test_shard_range_partitions_events():
+    for n in (0, 1, 7, 100, 1_000_003):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n_events, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    assert dist_info() == (rank, world)
+    lo, hi = shard_range(n_events, rank, world)
+    # stand-in for the per-rank feature table: a deterministic function of the event number
+    ev = np.arange(lo, hi)
+    df = pd.DataFrame({'event_number': ev, 'amp_x': np.sin(ev) * 1e-7, 'rank': rank})
+    full = gather_frames(df)
+    if rank == 0:
+        q.put(full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_events', [101, 1])
+def test_two_rank_gather_equals_single(n_events):
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_events, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ev = np.arange(n_events)
+    assert np.array_equal(full['event_number'].to_numpy(), ev)          # rank order == event order
+    assert np.array_equal(full['amp_x'].to_numpy(), np.sin(ev) * 1e-7)  # sharded == single
+    assert sorted(set(full['rank'])) == ([0, 1] if n_events > 1 else [1])
