@@ -64,6 +64,13 @@ SIGNATURES = {
     'dp_reduce_plan_n_out': (_i, [_vp, _ip]),
     'dp_window_reduce_batch': (_i, [_vp, _vp, _ll, _ll, _vp, _vp]),
     'dp_reduce_plan_last_kernel_ms': (_i, [_vp, _fp]),
+    'dp_psd_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i]),
+    'dp_psd_plan_destroy': (None, [_vp]),
+    'dp_psd_plan_set_scale': (_i, [_vp, _d]),
+    'dp_psd_reset': (_i, [_vp, _vp]),
+    'dp_psd_accumulate': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _vp]),
+    'dp_psd_get_sums': (_i, [_vp, _vp, _vp, _vp]),
+    'dp_psd_plan_last_kernel_ms': (_i, [_vp, _fp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -1,0 +1,98 @@
+"""
+Noise PSD estimation on the GPU -- the ``Noise.calc_psd`` hot path of the reference
+(detprocess/core/noise.py:216-370), config C5 of BASELINE.json.
+
+The reference holds every trace in RAM and calls ``qp.calc_psd(traces[cut], fs,
+folded_over=False)`` (noise.py:344).  Here traces stream through ``PSDPlan.accumulate`` in
+batches (each trace is read from HBM exactly once); every rank accumulates
+``sum |fft(x)_k|^2`` for its shard, the ``[N/2+1]`` sums and the accepted-trace counts are
+all-reduced (NCCL over NVLink when ``torch.distributed`` is initialised with the nccl
+backend) and the two-sided PSD is formed on every rank.
+
+The noise autocut (``qp.autocuts_noise``, noise.py:331) is QETpy code that is not part of
+the reference tree; its result enters here as the boolean ``cut`` mask.
+"""
+import numpy as np
+
+from .plans import PSDPlan
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def two_sided_from_sums(sums, count, nb_samples, fs):
+    """psd[k] = sums[|k|] / (count * N * fs) in fftfreq order (numpy or torch input)."""
+    half = sums / (float(count) * nb_samples * fs)
+    if isinstance(half, np.ndarray):
+        return np.concatenate([half, half[1:nb_samples - nb_samples // 2][::-1]])
+    torch = _torch()
+    return torch.cat([half, torch.flip(half[1:nb_samples - nb_samples // 2], dims=[0])])
+
+
+class NoisePSD:
+    """Streaming, multi-GPU ``calc_psd``.
+
+    >>> est = NoisePSD(nb_samples=65536, fs=1.25e6)
+    >>> for batch, cut in shard:            # CUDA float64 [n, N], optional bool [n]
+    ...     est.update(batch, cut)
+    >>> freqs, psd = est.finalize()          # all-reduce across ranks, two-sided, A^2/Hz
+    """
+
+    def __init__(self, nb_samples, fs, precision='f64', device=None, typical_rms=None):
+        self.nb_samples = int(nb_samples)
+        self.fs = float(fs)
+        self.plan = PSDPlan(nb_samples, fs, precision=precision, device=device)
+        if typical_rms is not None:
+            self.plan.set_scale(typical_rms)
+        self._median_sum = None
+        self._n_median = 0
+
+    def update(self, traces, cut=None, with_offset=False):
+        """Accumulate one batch.  ``with_offset`` also accumulates the per-trace medians that
+        ``Noise.calc_psd`` averages into the channel offset (noise.py:349)."""
+        self.plan.accumulate(traces, cut)
+        if with_offset:
+            torch = _torch()
+            sel = traces if cut is None else traces[cut.to(torch.bool)]
+            if sel.shape[0]:
+                # np.median of an even-length trace is the mean of the two middle samples
+                n = sel.shape[1]
+                srt = torch.sort(sel, dim=1).values
+                med = srt[:, n // 2] if n % 2 else 0.5 * (srt[:, n // 2 - 1] + srt[:, n // 2])
+                s = med.sum().reshape(1)
+                self._median_sum = s if self._median_sum is None else self._median_sum + s
+                self._n_median += sel.shape[0]
+
+    def local_sums(self):
+        return self.plan.sums()
+
+    def finalize(self, group=None):
+        """All-reduce the per-rank sums/counts and return (freqs, psd) as numpy float64 [N]."""
+        torch = _torch()
+        sums, count = self.plan.sums()
+        off = self._median_sum
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
+            torch.distributed.all_reduce(count, op=torch.distributed.ReduceOp.SUM, group=group)
+            if off is not None:
+                pack = torch.cat([off, torch.tensor([float(self._n_median)], dtype=off.dtype, device=off.device)])
+                torch.distributed.all_reduce(pack, op=torch.distributed.ReduceOp.SUM, group=group)
+                off, self._n_median = pack[:1], float(pack[1].item())
+        n = int(count.item())
+        if n == 0:
+            raise ValueError('ERROR: No events selected after noise autocut! Unable to calculate PSD')
+        psd = two_sided_from_sums(sums, n, self.nb_samples, self.fs).cpu().numpy()
+        freqs = np.fft.fftfreq(self.nb_samples, 1.0 / self.fs)
+        self.count = n
+        self.offset = None if off is None else float(off.item()) / self._n_median
+        return freqs, psd
+
+
+def calc_psd(traces, fs, cut=None, precision='f64', batch=4096):
+    """One-call form on a CUDA tensor [n, N] (what ``qp.calc_psd(traces[cut], fs, folded_over=False)`` returns)."""
+    est = NoisePSD(traces.shape[-1], fs, precision=precision, device=traces.device)
+    for i in range(0, traces.shape[0], batch):
+        est.update(traces[i:i + batch], None if cut is None else cut[i:i + batch])
+    return est.finalize()

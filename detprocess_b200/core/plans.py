@@ -284,3 +284,72 @@ class ReducePlan:
         ms = C.c_float()
         check(lib.dp_reduce_plan_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+class PSDPlan:
+    """Per-GPU accumulation of sum_traces |fft(x)_k|^2, k = 0..N/2 (``dp_psd_plan``).
+
+    ``accumulate`` may be called any number of times (C5 streams 262 GB through it);
+    ``sums`` returns the per-GPU sums and accepted-trace count as CUDA tensors so the host
+    layer can all-reduce them over NCCL before forming the PSD.
+    """
+
+    def __init__(self, nb_samples, sample_rate, precision='f64', device=None):
+        torch = _torch()
+        if precision not in _PREC:
+            raise ValueError(f'unknown precision "{precision}"')
+        if not torch.cuda.is_available():
+            raise _lib.DetprocessB200Error('no CUDA device: detprocess_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        self.device = device
+        self.nb_samples = int(nb_samples)
+        self.sample_rate = float(sample_rate)
+        self.precision = 'f32' if _PREC[precision] == _lib.DP_PREC_F32 else 'f64'
+        self._h = C.c_void_p()
+        check(lib.dp_psd_plan_create(C.byref(self._h), self.nb_samples, self.sample_rate, _PREC[precision],
+                                     device.index or 0))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            lib.dp_psd_plan_destroy(h)
+            self._h = C.c_void_p()
+
+    def set_scale(self, typical_rms):
+        check(lib.dp_psd_plan_set_scale(self._h, float(typical_rms)))
+
+    def reset(self):
+        check(lib.dp_psd_reset(self._h, _stream_ptr(self.device)))
+
+    def accumulate(self, traces, mask=None):
+        """traces: CUDA float64 [n, N]; mask: optional CUDA bool/uint8 [n] (True = keep)."""
+        torch = _torch()
+        if not traces.is_cuda or traces.dtype != torch.float64:
+            raise ValueError('accumulate() takes float64 CUDA tensors')
+        if traces.ndim != 2 or traces.shape[1] != self.nb_samples:
+            raise ValueError('traces must be [n_traces, nb_samples]')
+        traces = traces.contiguous()
+        mptr = C.c_void_p(0)
+        if mask is not None:
+            mask = mask.to(device=traces.device, dtype=torch.uint8).contiguous()
+            if mask.shape != (traces.shape[0],):
+                raise ValueError('mask must be [n_traces]')
+            mptr = C.c_void_p(mask.data_ptr())
+        check(lib.dp_psd_accumulate(self._h, C.c_void_p(traces.data_ptr()), _lib.DP_IN_F64, traces.shape[0],
+                                    self.nb_samples, mptr, _stream_ptr(traces.device)))
+
+    def sums(self):
+        """(sums [N/2+1] float64, count [1] int64) CUDA tensors of everything accumulated so far."""
+        torch = _torch()
+        sums = torch.empty(self.nb_samples // 2 + 1, dtype=torch.float64, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        check(lib.dp_psd_get_sums(self._h, C.c_void_p(sums.data_ptr()), C.c_void_p(count.data_ptr()),
+                                  _stream_ptr(self.device)))
+        return sums, count
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(lib.dp_psd_plan_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value

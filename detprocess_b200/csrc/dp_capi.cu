@@ -13,6 +13,7 @@
 #include "../../include/detprocess_b200.h"
 #include "dp_of_launch.hpp"
 #include "dp_plan.hpp"
+#include "dp_psd_kernel.cuh"
 #include "dp_reduce_plan.hpp"
 
 namespace {
@@ -605,6 +606,209 @@ int dp_window_reduce_batch(dp_reduce_plan* p, const double* traces_dev, long lon
 }
 int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* p, float* ms) {
     if (!p || !p->finalized || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
+    DP_CUDA(cudaEventSynchronize(p->ev1));
+    DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return DP_OK;
+}
+
+}  // extern "C"
+
+// ========================================================================== PSD plan
+struct dp_psd_plan {
+    int N = 0;
+    double fs = 0;
+    int precision = DP_PREC_F64;
+    int device = 0;
+    dpplan::Geometry geom;
+    std::vector<void*> owned;
+    const void *tw1 = nullptr, *tw2 = nullptr, *twn = nullptr, *twp = nullptr;
+    void* scratch = nullptr;
+    long long scratch_per_cta = 0;
+    double* partial = nullptr;
+    long long partial_per_cta = 0;
+    unsigned long long* count = nullptr;
+    unsigned long long* count_out = nullptr;
+    const int* loc = nullptr;
+    int grid_max = 0;
+    size_t smem = 0;
+    double scale = 1.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+
+template <class T> int psd_finalize(dp_psd_plan* p) {
+    // twiddle bases are shared with the OF kernel: build them through an empty table set
+    std::vector<dpplan::Channel> none;
+    dpplan::DeviceTables<T> dt;
+    try {
+        dt = dpplan::build_tables<T>(p->geom, p->fs, none, 0.0, 1.0);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_INVALID, e.what());
+    }
+    int rc;
+    const cx<T>* d;
+    if ((rc = upload(p->owned, dt.tw1, &d))) return rc;
+    p->tw1 = d;
+    if ((rc = upload(p->owned, dt.tw2, &d))) return rc;
+    p->tw2 = d;
+    if ((rc = upload(p->owned, dt.twn, &d))) return rc;
+    p->twn = d;
+    if ((rc = upload(p->owned, dt.twp, &d))) return rc;
+    p->twp = d;
+    const int prec = sizeof(T) == 8 ? 0 : 1;
+    const int src = prec == 0 ? dp_psd_setup_p0_0(p->geom.R1, p->geom.P, p->device, &p->smem, &p->grid_max)
+                              : dp_psd_setup_p1_0(p->geom.R1, p->geom.P, p->device, &p->smem, &p->grid_max);
+    if (src == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length for this precision");
+    if (src != 0) return fail(DP_ERR_CUDA, "PSD kernel setup failed");
+    const int NT = p->geom.NT, P = p->geom.P, M = p->N / 2;
+    p->scratch_per_cta = 32LL * NT;
+    DP_CUDA(cudaMalloc(&p->scratch, sizeof(cx<T>) * (size_t)p->scratch_per_cta * (size_t)p->grid_max));
+    p->owned.push_back(p->scratch);
+    p->partial_per_cta = 32LL * P * NT + 17 * 2 * P;
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->partial), sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
+    p->owned.push_back(p->partial);
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->count), sizeof(unsigned long long) * (size_t)(p->grid_max + 1)));
+    p->owned.push_back(p->count);
+    p->count_out = p->count + p->grid_max;
+    // natural bin k -> slot in one CTA's partial array (thread 0's placeholders are skipped)
+    std::vector<int> loc(M + 1, -1);
+    for (int t = 1; t < NT; ++t)
+        for (int e = 0; e < 32 * P; ++e) loc[dpplan::k_of(p->geom, t, e)] = e * NT + t;
+    for (int l = 0; l < 17; ++l) {
+        int bins[4];
+        bool dup[4];
+        dpplan::self_bins(p->geom, l, bins, dup);
+        for (int j = 0; j < 2 * P; ++j)
+            if (!dup[j]) loc[bins[j]] = 32 * P * NT + l * 2 * P + j;
+    }
+    for (int k = 0; k <= M; ++k)
+        if (loc[k] < 0) return fail(DP_ERR_STATE, "internal: PSD bin map incomplete");
+    if ((rc = upload(p->owned, loc, &p->loc))) return rc;
+    return DP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_psd_plan_create(dp_psd_plan** plan, int nb_samples, double sample_rate, int precision, int device) {
+    if (!plan) return fail(DP_ERR_INVALID, "null plan pointer");
+    if (!(sample_rate > 0)) return fail(DP_ERR_INVALID, "sample_rate must be > 0");
+    if (precision != DP_PREC_F64 && precision != DP_PREC_F32) return fail(DP_ERR_INVALID, "unknown precision");
+    auto p = std::make_unique<dp_psd_plan>();
+    try {
+        p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_UNSUPPORTED, e.what());
+    }
+    p->N = nb_samples;
+    p->fs = sample_rate;
+    p->precision = precision;
+    p->device = device;
+    DP_CUDA(cudaSetDevice(device));
+    int rc = precision == DP_PREC_F32 ? psd_finalize<float>(p.get()) : psd_finalize<double>(p.get());
+    if (rc) {
+        for (void* d : p->owned) cudaFree(d);
+        return rc;
+    }
+    DP_CUDA(cudaEventCreate(&p->ev0));
+    DP_CUDA(cudaEventCreate(&p->ev1));
+    DP_CUDA(cudaMemset(p->partial, 0, sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
+    DP_CUDA(cudaMemset(p->count, 0, sizeof(unsigned long long) * (size_t)(p->grid_max + 1)));
+    *plan = p.release();
+    return DP_OK;
+}
+void dp_psd_plan_destroy(dp_psd_plan* p) {
+    if (!p) return;
+    for (void* d : p->owned) cudaFree(d);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+int dp_psd_plan_set_scale(dp_psd_plan* p, double typical_rms) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (!(typical_rms > 0)) return fail(DP_ERR_INVALID, "typical_rms must be > 0");
+    p->scale = p->precision == DP_PREC_F32 ? std::exp2(-std::round(std::log2(typical_rms))) : 1.0;
+    return DP_OK;
+}
+int dp_psd_reset(dp_psd_plan* p, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DP_CUDA(cudaMemsetAsync(p->partial, 0, sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max, st));
+    DP_CUDA(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long) * (size_t)(p->grid_max + 1), st));
+    return DP_OK;
+}
+int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long long n_traces, long long row_stride,
+                      const unsigned char* mask_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (n_traces < 0) return fail(DP_ERR_INVALID, "negative n_traces");
+    if (n_traces == 0) return DP_OK;
+    if (!traces_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if (in_dtype != DP_IN_F64) return fail(DP_ERR_UNSUPPORTED, "PSD accumulation takes float64 traces");
+    if (row_stride < p->N || (row_stride & 1)) return fail(DP_ERR_INVALID, "row_stride must be even and >= nb_samples");
+    if (n_traces > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = (int)std::min<long long>(n_traces, p->grid_max);
+    auto fill = [&](auto& prm) {
+        std::memset(&prm, 0, sizeof(prm));
+        prm.traces = traces_dev;
+        prm.row_stride = row_stride;
+        prm.n_rows = (int)n_traces;
+        prm.mask = mask_dev;
+        prm.scratch_per_cta = p->scratch_per_cta;
+        prm.partial = p->partial;
+        prm.partial_per_cta = p->partial_per_cta;
+        prm.count = p->count;
+        prm.scale = p->scale;
+        prm.subtract_first = p->precision == DP_PREC_F32 ? 1 : 0;
+    };
+    DP_CUDA(cudaEventRecord(p->ev0, st));
+    int rc;
+    if (p->precision == DP_PREC_F32) {
+        DpPsdParams<float> prm;
+        fill(prm);
+        prm.tw1 = (const cx<float>*)p->tw1; prm.tw2 = (const cx<float>*)p->tw2;
+        prm.twn = (const cx<float>*)p->twn; prm.twp = (const cx<float>*)p->twp;
+        prm.scratch = (cx<float>*)p->scratch;
+        rc = dp_psd_launch_p1_0(p->geom.R1, p->geom.P, &prm, grid, p->smem, st);
+    } else {
+        DpPsdParams<double> prm;
+        fill(prm);
+        prm.tw1 = (const cx<double>*)p->tw1; prm.tw2 = (const cx<double>*)p->tw2;
+        prm.twn = (const cx<double>*)p->twn; prm.twp = (const cx<double>*)p->twp;
+        prm.scratch = (cx<double>*)p->scratch;
+        rc = dp_psd_launch_p0_0(p->geom.R1, p->geom.P, &prm, grid, p->smem, st);
+    }
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("PSD kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    DP_CUDA(cudaEventRecord(p->ev1, st));
+    p->timed = true;
+    return DP_OK;
+}
+int dp_psd_get_sums(dp_psd_plan* p, double* sums_dev, unsigned long long* count_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (!sums_dev || !count_dev) return fail(DP_ERR_INVALID, "null buffer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nbins = p->N / 2 + 1;
+    DP_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * (size_t)nbins, st));
+    DP_CUDA(cudaMemsetAsync(p->count_out, 0, sizeof(unsigned long long), st));
+    DpPsdReduceParams prm;
+    prm.partial = p->partial;
+    prm.partial_per_cta = p->partial_per_cta;
+    prm.grid = p->grid_max;
+    prm.loc = p->loc;
+    prm.nbins = nbins;
+    prm.sum_out = sums_dev;
+    prm.count = p->count;
+    prm.count_out = p->count_out;
+    const int rc = dp_psd_reduce_launch(&prm, st);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("PSD reduce launch: ") + cudaGetErrorString((cudaError_t)rc));
+    DP_CUDA(cudaMemcpyAsync(count_dev, p->count_out, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    return DP_OK;
+}
+int dp_psd_plan_last_kernel_ms(dp_psd_plan* p, float* ms) {
+    if (!p || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
     DP_CUDA(cudaEventSynchronize(p->ev1));
     DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
     return DP_OK;

@@ -73,6 +73,12 @@ template <class T, int J64, int SIGN> DP_HD cx<T> dp_w64() {
     return cx<T>{(T)c, (T)(SIGN * s)};
 }
 
+// exp(-2*pi*i*j/64) for a loop index that the compiler unrolls (j known at compile time
+// after unrolling; falls back to a 64-entry select chain otherwise)
+template <class T> DP_HD cx<T> dp_w64_rt(int j) {
+    return cx<T>{(T)dp_cos64(j), (T)(-dp_sin64(j))};
+}
+
 // ----------------------------------------------------- radix-2 DIT, natural order
 // out[k] = sum_n in[n] * exp(SIGN*2*pi*i*n*k/R); in and out natural order.
 // Butterfly (e + w*o, e - w*o) in the 6-FMA form: x = e + w*o; x' = 2e - x.

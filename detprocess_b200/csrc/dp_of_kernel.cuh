@@ -727,21 +727,27 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run_p2(const DpOfParams<T>& prm, unsigned 
         cx<T> za[16], zb[16];
         T chi = (T)0;
         // ---- forward: sub-sequence 0 -> scratch, sub-sequence 1 -> registers --------------
-        dp_fwd_subfft<T, R1, 2, IN>(xrow, 0, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+        // (a real loop: ONE copy of the sub-FFT code; instruction fetch is what limits
+        //  the 8-warp fp64 CTA, see profiles/)
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            dp_fwd_subfft<T, R1, 2, IN>(xrow, p, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+            if (p == 0) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            scr0[r * NT + tid] = za[r];
-            scr0[(16 + r) * NT + tid] = zb[r];
-        }
-        if (tid == 0) {
+                for (int r = 0; r < 16; ++r) {
+                    scr0[r * NT + tid] = za[r];
+                    scr0[(16 + r) * NT + tid] = zb[r];
+                }
+                if (tid == 0) {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                sm.sp[32 + r] = za[r];
-                sm.sp[32 + 16 + r] = zb[r];
+                    for (int r = 0; r < 16; ++r) {
+                        sm.sp[32 + r] = za[r];
+                        sm.sp[32 + 16 + r] = zb[r];
+                    }
+                }
+                __syncthreads();  // pass-3 reads of buf are done before the next pass-1 stores
             }
         }
-        __syncthreads();  // pass-3 reads of buf are done before the next pass-1 stores
-        dp_fwd_subfft<T, R1, 2, IN>(xrow, 1, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
         prefetch_next(prm, row);
         const bool multi = ch.n_templ > 1;
         if (multi) {
@@ -839,18 +845,22 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run_p2(const DpOfParams<T>& prm, unsigned 
                 }
                 __syncwarp();
             }
-            // ---- inverse of sub-sequence 1, then 0; arg-max over both ------------------------
-            cx<T> y[32];
-            dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
-            scan_slots(y, ch, it, 1, false, sm.best(par), sm.slot_id(par));
-            __syncthreads();  // pass-1' reads of buf are done before the next pass-3' stores
+            // ---- inverse of sub-sequence 1, then 0; arg-max over both (one code copy) ---------
+            int nts = 0;
+#pragma unroll 1
+            for (int p = 1; p >= 0; --p) {
+                if (p == 0) {
+                    __syncthreads();  // pass-1' reads of buf are done before the next pass-3' stores
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                za[r] = scrz[r * NT + tid];
-                zb[r] = scrz[(16 + r) * NT + tid];
+                    for (int r = 0; r < 16; ++r) {
+                        za[r] = scrz[r * NT + tid];
+                        zb[r] = scrz[(16 + r) * NT + tid];
+                    }
+                }
+                cx<T> y[32];
+                dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
+                nts = scan_slots(y, ch, it, p, p == 0, sm.best(par), sm.slot_id(par));
             }
-            dp_inv_subfft<T, R1>(sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb, y);
-            const int nts = scan_slots(y, ch, it, 0, true, sm.best(par), sm.slot_id(par));
             epilogue(prm, sm, ch, tp, it, nts, par, ev, chi, chi0_keep);
             par ^= 1;
         }

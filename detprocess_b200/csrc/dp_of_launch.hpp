@@ -20,3 +20,10 @@ static const dp_of_setup_fn dp_of_setup_table[2][3] = {{dp_of_setup_p0_0, dp_of_
                                                        {dp_of_setup_p1_0, dp_of_setup_p1_1, dp_of_setup_p1_2}};
 static const dp_of_launch_fn dp_of_launch_table[2][3] = {{dp_of_launch_p0_0, dp_of_launch_p0_1, dp_of_launch_p0_2},
                                                          {dp_of_launch_p1_0, dp_of_launch_p1_1, dp_of_launch_p1_2}};
+
+// PSD accumulation kernels (float64 traces)
+int dp_psd_setup_p0_0(int R1, int P, int device, size_t* smem, int* grid_max);
+int dp_psd_setup_p1_0(int R1, int P, int device, size_t* smem, int* grid_max);
+int dp_psd_launch_p0_0(int R1, int P, const void* prm, int grid, size_t smem, void* stream);
+int dp_psd_launch_p1_0(int R1, int P, const void* prm, int grid, size_t smem, void* stream);
+int dp_psd_reduce_launch(const void* prm, void* stream);

@@ -141,6 +141,25 @@ int dp_window_reduce_batch(dp_reduce_plan* plan, const double* traces_dev, long 
                            double* out_dev, void* stream);
 int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* plan, float* ms);
 
+/* ------------------------------------------------------------------ noise PSD
+ * Replaces qp.calc_psd(traces[cut], fs, folded_over=False) as called by Noise.calc_psd
+ * (detprocess/core/noise.py:344): the plan accumulates sum_traces |fft(x)_k|^2 for
+ * k = 0..N/2 over any number of dp_psd_accumulate calls (mask_dev selects the traces that
+ * passed the cut, noise.py:331; NULL = all).  dp_psd_get_sums returns the per-GPU sums and
+ * the number of accepted traces; the host layer all-reduces both over NCCL and forms
+ * psd[k] = sum[k] / (count * N * fs), mirrored to the two-sided layout.
+ */
+typedef struct dp_psd_plan dp_psd_plan;
+int dp_psd_plan_create(dp_psd_plan** plan, int nb_samples, double sample_rate, int precision, int device);
+void dp_psd_plan_destroy(dp_psd_plan* plan);
+int dp_psd_plan_set_scale(dp_psd_plan* plan, double typical_rms);   /* fp32 mode: sample scale hint */
+int dp_psd_reset(dp_psd_plan* plan, void* stream);
+int dp_psd_accumulate(dp_psd_plan* plan, const void* traces_dev, int in_dtype, long long n_traces,
+                      long long row_stride, const unsigned char* mask_dev, void* stream);
+int dp_psd_get_sums(dp_psd_plan* plan, double* sums_dev /* [N/2+1] */, unsigned long long* count_dev /* [1] */,
+                    void* stream);
+int dp_psd_plan_last_kernel_ms(dp_psd_plan* plan, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

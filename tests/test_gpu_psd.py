@@ -1,0 +1,55 @@
+"""GPU parity of the noise PSD accumulation (C5 row a13) against oracle/psd.py, through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+from oracle import psd as P  # noqa: E402
+
+
+def _traces(n_tr, n, seed, offset=0.0):
+    rng = np.random.default_rng(seed)
+    # coloured: white + random walk component + a line
+    w = rng.standard_normal((n_tr, n)) * 2e-11
+    t = np.arange(n)
+    line = 5e-11 * np.sin(2 * np.pi * 60.0 * t / n + rng.uniform(0, 6.28, (n_tr, 1)))
+    return w + line + offset
+
+
+@pytest.mark.parametrize('n,prec,tol', [(32768, 'f64', 1e-11), (16384, 'f64', 1e-11), (4096, 'f64', 1e-11),
+                                        (65536, 'f32', 2e-5), (32768, 'f32', 2e-5)])
+def test_psd_matches_oracle(n, prec, tol):
+    from detprocess_b200.core.noise import NoisePSD
+    fs = 1.25e6
+    tr = _traces(300, n, 7, offset=(3e-9 if prec == 'f64' else 3e-9))
+    cut = np.random.default_rng(8).random(300) < 0.8
+    dev = torch.device('cuda', 0)
+    est = NoisePSD(n, fs, precision=prec, device=dev, typical_rms=2e-11)
+    x = torch.from_numpy(tr).to(dev)
+    c = torch.from_numpy(cut).to(dev)
+    est.update(x[:128], c[:128])
+    est.update(x[128:], c[128:])
+    freqs, psd = est.finalize()
+    f0, p0 = P.calc_psd(tr, fs, cut)
+    assert est.count == int(cut.sum())
+    assert np.array_equal(freqs, f0)
+    rel = np.abs(psd / p0 - 1)
+    assert rel.max() < tol, (rel.max(), int(rel.argmax()))
+
+
+def test_psd_offset_and_reset():
+    from detprocess_b200.core.noise import NoisePSD
+    n, fs = 4096, 1.25e6
+    tr = _traces(50, n, 9, offset=1e-9)
+    dev = torch.device('cuda', 0)
+    est = NoisePSD(n, fs, device=dev)
+    est.update(torch.from_numpy(tr).to(dev), None, with_offset=True)
+    _, psd = est.finalize()
+    assert np.isclose(est.offset, P.offset(tr), rtol=1e-12)
+    est.plan.reset()
+    est.update(torch.from_numpy(tr[:10]).to(dev))
+    _, psd2 = est.finalize()
+    _, p0 = P.calc_psd(tr[:10], fs)
+    assert np.abs(psd2 / p0 - 1).max() < 1e-11
