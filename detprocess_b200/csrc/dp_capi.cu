@@ -5,14 +5,17 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/detprocess_b200.h"
+#include "dp_of2_launch.hpp"
 #include "dp_of_launch.hpp"
 #include "dp_plan.hpp"
+#include "dp_plan2.hpp"
 #include "dp_psd_kernel.cuh"
 #include "dp_reduce_plan.hpp"
 
@@ -59,10 +62,11 @@ struct dp_of_plan {
     bool finalized = false;
     int device = 0;
     dpplan::Geometry geom;
+    int v2_r1 = 0;  // != 0: the v2 kernels (dp_of2_kernel.cuh) serve this plan, M = v2_r1 * 4096
     // device state
     std::vector<void*> owned;
     const void* d_chans = nullptr;
-    const void *tw1 = nullptr, *tw2 = nullptr, *twn = nullptr, *twp = nullptr;
+    const void *tw1 = nullptr, *tw2 = nullptr, *twn = nullptr, *twp = nullptr, *tw3 = nullptr, *groups = nullptr;
     void* scratch = nullptr;
     long long scratch_per_cta = 0;
     int grid_max = 0;
@@ -205,6 +209,148 @@ int of_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_even
     return DP_OK;
 }
 
+// ------------------------------------------------------------------ v2 kernels
+template <class T> int of2_finalize(dp_of_plan* p) {
+    using S = typename Dp2Traits<T>::S;
+    dpplan2::Tables2<T> dt;
+    try {
+        switch (p->v2_r1) {
+            case 2: dt = dpplan2::build_tables2<T, 2>(p->fs, p->chans, p->fcut, p->scale); break;
+            case 4: dt = dpplan2::build_tables2<T, 4>(p->fs, p->chans, p->fcut, p->scale); break;
+            default: dt = dpplan2::build_tables2<T, 8>(p->fs, p->chans, p->fcut, p->scale); break;
+        }
+    } catch (const std::invalid_argument& e) {
+        return fail(DP_ERR_INVALID, e.what());
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_STATE, e.what());
+    }
+    p->nlow = dt.nlow;
+    int rc;
+    const cx<T>* d;
+    if ((rc = upload(p->owned, dt.tw1, &d))) return rc;
+    p->tw1 = d;
+    if ((rc = upload(p->owned, dt.tw2, &d))) return rc;
+    p->tw2 = d;
+    if ((rc = upload(p->owned, dt.tw3, &d))) return rc;
+    p->tw3 = d;
+    const cx<S>* ds;
+    if ((rc = upload(p->owned, dt.twn, &ds))) return rc;
+    p->twn = ds;
+    const int2* dg;
+    if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
+    p->groups = dg;
+    std::vector<Dp2ChanDev<T>> cd(p->n_chan);
+    p->chan_out_base.assign(p->n_chan, 0);
+    int base = 0, max_templ = 1;
+    for (int c = 0; c < p->n_chan; ++c) {
+        Dp2ChanDev<T>& dc = cd[c];
+        std::memset(&dc, 0, sizeof(dc));
+        const T* w;
+        const S* ws;
+        if ((rc = upload(p->owned, dt.chans[c].wj, &w))) return rc;
+        dc.wj = w;
+        if ((rc = upload(p->owned, dt.chans[c].wj_low, &ws))) return rc;
+        dc.wj_low = ws;
+        if ((rc = upload(p->owned, dt.chans[c].wj_self, &ws))) return rc;
+        dc.wj_self = ws;
+        dc.n_templ = (int)p->chans[c].templ.size();
+        dc.n_slots = (int)p->chans[c].fits.size();
+        dc.out_base = base;
+        p->chan_out_base[c] = base;
+        base += 1 + DP_SLOT_NOUT * dc.n_slots;
+        max_templ = std::max(max_templ, dc.n_templ);
+        for (int i = 0; i < dc.n_templ; ++i) {
+            auto& h = dt.chans[c].templ[i];
+            const cx<T>* ph;
+            const cx<S>* phs;
+            if ((rc = upload(p->owned, h.phi, &ph))) return rc;
+            dc.templ[i].phi = ph;
+            if ((rc = upload(p->owned, h.s_low, &phs))) return rc;
+            dc.templ[i].s_low = phs;
+            if ((rc = upload(p->owned, h.phi_self, &phs))) return rc;
+            dc.templ[i].phi_self = phs;
+            dc.templ[i].norm = h.norm;
+            dc.templ[i].tsum = h.tsum;
+            dc.templ[i].pretrigger = h.pretrigger;
+        }
+        for (int i = 0; i < dc.n_slots; ++i) {
+            const auto& f = p->chans[c].fits[i];
+            dc.slots[i] = DpSlot{f.templ, f.lo, f.hi, f.outside};
+        }
+    }
+    p->n_out = base;
+    const Dp2ChanDev<T>* dcd;
+    if ((rc = upload(p->owned, cd, &dcd))) return rc;
+    p->d_chans = dcd;
+    const int prec = sizeof(S) == 8 ? 0 : 1;
+    for (int in = 0; in < 3; ++in) {
+        size_t smem = 0;
+        int grid_max = 0, occ = 0, threads = 0;
+        const int src = dp_of2_setup_table[prec][in](p->v2_r1, p->device, &smem, &grid_max, &occ, &threads);
+        if (src == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");
+        if (src != 0) return fail(DP_ERR_CUDA, std::string("OF kernel setup: ") + cudaGetErrorString((cudaError_t)src));
+        if (occ < 1) return fail(DP_ERR_CUDA, "OF kernel does not fit on an SM");
+        p->smem = smem;
+        p->grid_max = in == 0 ? grid_max : std::min(p->grid_max, grid_max);
+    }
+    long long per_cta = 0;
+    switch (p->v2_r1) {
+        case 2: per_cta = Dp2OfKernel<T, 2, 0>::scratch_v(max_templ); break;
+        case 4: per_cta = Dp2OfKernel<T, 4, 0>::scratch_v(max_templ); break;
+        default: per_cta = Dp2OfKernel<T, 8, 0>::scratch_v(max_templ); break;
+    }
+    p->scratch_per_cta = per_cta;
+    DP_CUDA(cudaMalloc(&p->scratch, sizeof(cx<T>) * (size_t)per_cta * (size_t)p->grid_max));
+    p->owned.push_back(p->scratch);
+    return DP_OK;
+}
+
+template <class T>
+int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride, double* out_dev,
+            cudaStream_t st, bool timed) {
+    using S = typename Dp2Traits<T>::S;
+    Dp2Params<T> prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.traces = traces_dev;
+    prm.row_stride = row_stride;
+    prm.n_rows = (int)(n_events * p->n_chan);
+    prm.n_chan = p->n_chan;
+    prm.chans = reinterpret_cast<const Dp2ChanDev<T>*>(p->d_chans);
+    prm.tw1 = reinterpret_cast<const cx<T>*>(p->tw1);
+    prm.tw2 = reinterpret_cast<const cx<T>*>(p->tw2);
+    prm.tw3 = reinterpret_cast<const cx<T>*>(p->tw3);
+    prm.twn = reinterpret_cast<const cx<S>*>(p->twn);
+    prm.groups = reinterpret_cast<const int2*>(p->groups);
+    prm.scratch = reinterpret_cast<cx<T>*>(p->scratch);
+    prm.scratch_per_cta = p->scratch_per_cta;
+    prm.out = out_dev;
+    prm.n_out = p->n_out;
+    prm.nlow = p->nlow;
+    prm.scale = p->scale;
+    prm.subtract_first = p->subtract_first;
+    const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
+    if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
+    const int prec = sizeof(S) == 8 ? 0 : 1;
+    const int rc = dp_of2_launch_table[prec][in_dtype](p->v2_r1, &prm, grid, p->smem, st);
+    if (rc == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    if (timed) DP_CUDA(cudaEventRecord(p->ev1, st));
+    p->timed = timed;
+    p->launches += 1;
+    return DP_OK;
+}
+
+// precision / kernel-generation dispatch of one batch launch
+int of_dispatch(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride, double* out_dev,
+                cudaStream_t st, bool timed) {
+    if (p->v2_r1) {
+        if (p->precision == DP_PREC_F32) return of2_run<f2>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
+        return of2_run<double>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
+    }
+    if (p->precision == DP_PREC_F32) return of_run<float>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
+    return of_run<double>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
+}
+
 int of_check(const dp_of_plan* p, int chan) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
     if (chan < 0 || chan >= p->n_chan) return fail(DP_ERR_INVALID, "channel index out of range");
@@ -228,10 +374,16 @@ int dp_of_plan_create(dp_of_plan** plan, int nb_samples, double sample_rate, int
     if (!(sample_rate > 0)) return fail(DP_ERR_INVALID, "sample_rate must be > 0");
     if (precision != DP_PREC_F64 && precision != DP_PREC_F32) return fail(DP_ERR_INVALID, "unknown precision");
     auto p = std::make_unique<dp_of_plan>();
-    try {
-        p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
-    } catch (const std::exception& e) {
-        return fail(DP_ERR_UNSUPPORTED, e.what());
+    // nb_samples 16384 / 32768 / 65536 run on the v2 kernels (DP_OF_KERNEL=v1 selects the first
+    // generation where it supports the length; kept for A/B measurements)
+    const char* gen = std::getenv("DP_OF_KERNEL");
+    p->v2_r1 = (gen && std::string(gen) == "v1") ? 0 : dpplan2::r1_of(nb_samples);
+    if (!p->v2_r1) {
+        try {
+            p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
+        } catch (const std::exception& e) {
+            return fail(DP_ERR_UNSUPPORTED, e.what());
+        }
     }
     p->N = nb_samples;
     p->fs = sample_rate;
@@ -345,7 +497,11 @@ int dp_of_plan_finalize(dp_of_plan* p, int device) {
         p->scale = 1.0;
         p->subtract_first = 0;
     }
-    int rc = (p->precision == DP_PREC_F32) ? of_finalize<float>(p) : of_finalize<double>(p);
+    int rc;
+    if (p->v2_r1)
+        rc = (p->precision == DP_PREC_F32) ? of2_finalize<f2>(p) : of2_finalize<double>(p);
+    else
+        rc = (p->precision == DP_PREC_F32) ? of_finalize<float>(p) : of_finalize<double>(p);
     if (rc) return rc;
     DP_CUDA(cudaEventCreate(&p->ev0));
     DP_CUDA(cudaEventCreate(&p->ev1));
@@ -415,8 +571,7 @@ int dp_of1x1_batch(dp_of_plan* p, const void* traces_dev, int in_dtype, long lon
     if ((reinterpret_cast<uintptr_t>(traces_dev) % (2 * esz)) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
     if (n_events * p->n_chan > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (p->precision == DP_PREC_F32) return of_run<float>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, true);
-    return of_run<double>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, true);
+    return of_dispatch(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, true);
 }
 
 int dp_of_plan_last_kernel_ms(dp_of_plan* p, float* ms) {
@@ -464,9 +619,7 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
         const long long ne = std::min(chunk, n_events - e0);
         cudaStream_t st = p->streams[k];
         DP_CUDA(cudaMemcpyAsync(p->stage_dev[k], src + (size_t)e0 * ev_bytes, ev_bytes * (size_t)ne, cudaMemcpyHostToDevice, st));
-        int rc = (p->precision == DP_PREC_F32)
-                     ? of_run<float>(p, p->stage_dev[k], in_dtype, ne, row_stride, p->stage_out[k], st, false)
-                     : of_run<double>(p, p->stage_dev[k], in_dtype, ne, row_stride, p->stage_out[k], st, false);
+        int rc = of_dispatch(p, p->stage_dev[k], in_dtype, ne, row_stride, p->stage_out[k], st, false);
         if (rc) return rc;
         DP_CUDA(cudaMemcpyAsync(out_host + (size_t)e0 * p->n_out, p->stage_out[k], sizeof(double) * (size_t)p->n_out * (size_t)ne,
                                 cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,64 @@
+// One translation unit per (precision, input type) of the v2 fused OF kernel
+// (nb_samples 16384 / 32768 / 65536), so they compile in parallel.  Build with
+//   -DDP_INST_PREC=0|1 (double | packed float)  -DDP_INST_IN=0|1|2 (f64 | f32 | i16)
+#ifndef DP_INST_PREC
+#error "DP_INST_PREC must be defined"
+#endif
+#ifndef DP_INST_IN
+#error "DP_INST_IN must be defined"
+#endif
+#include <cuda_runtime.h>
+
+#include "dp_of2_kernel.cuh"
+#include "dp_of2_launch.hpp"
+
+#if DP_INST_PREC == 0
+using InstT = double;
+#else
+using InstT = f2;
+#endif
+
+#define DP_CAT_(a, b, c) a##b##_##c
+#define DP_CAT(a, b, c) DP_CAT_(a, b, c)
+
+namespace {
+template <int R1> int setup_one(int device, size_t* smem, int* grid_max, int* occ_out, int* threads) {
+    using K = Dp2OfKernel<InstT, R1, DP_INST_IN>;
+    auto kern = dp_of2_kernel<InstT, R1, DP_INST_IN>;
+    *smem = K::SMEM_BYTES;
+    *threads = K::NT;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::NT, K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return (int)e;
+    *occ_out = occ;
+    *grid_max = sms * occ;
+    return 0;
+}
+template <int R1> int launch_one(const Dp2Params<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
+    dp_of2_kernel<InstT, R1, DP_INST_IN><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+    return (int)cudaGetLastError();
+}
+}  // namespace
+
+int DP_CAT(dp_of2_setup_p, DP_INST_PREC, DP_INST_IN)(int R1, int device, size_t* smem, int* grid_max, int* occ, int* threads) {
+    switch (R1) {
+        case 2: return setup_one<2>(device, smem, grid_max, occ, threads);
+        case 4: return setup_one<4>(device, smem, grid_max, occ, threads);
+        case 8: return setup_one<8>(device, smem, grid_max, occ, threads);
+        default: return -1;
+    }
+}
+int DP_CAT(dp_of2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
+    const Dp2Params<InstT>& prm = *reinterpret_cast<const Dp2Params<InstT>*>(prm_v);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
+    switch (R1) {
+        case 2: return launch_one<2>(prm, grid, smem, st);
+        case 4: return launch_one<4>(prm, grid, smem, st);
+        case 8: return launch_one<8>(prm, grid, smem, st);
+        default: return -1;
+    }
+}

@@ -1,0 +1,885 @@
+// v2 fused OF1x1 kernel for nb_samples = 16384 / 32768 / 65536 (the lengths BASELINE.json
+// names): same maths as dp_of_kernel.cuh, re-laid out for the measured B200 pipes
+// (tools/ubench/pipes.cu; profiles/README.md):
+//   * fp32 mode computes on cx<f2>: every butterfly, twiddle and filter multiply is an
+//     FFMA2 / FADD2 / FMUL2 on TWO complex points (adjacent elements in passes 1-3, the
+//     (k, M-k) mirror groups in pass 4), halving the issue slots per event;
+//   * fp64 mode uses the same code on cx<double> (DFMA issues at the FFMA2 rate on B200);
+//   * all passes have radix <= 16 (16 register-resident points per thread, no spills),
+//     512 threads per CTA;
+//   * the complex FFT of M = N/2 = R1*4096 points is one radix-R1 pass followed by R1
+//     independent 4096-point blocks (16 x 16 x 16).  Shared memory holds NB blocks at a time
+//     (128 KB); when NB < R1 the blocks are processed in mirror-closed PHASES, each phase
+//     re-reading the (L2-resident) trace, untangling its own (k, M-k) pairs, and only the
+//     inverse needs one L2 round trip of the parked block results.
+//
+// Replaces, per event: qp.OFBase.update_signal / calc_signal_filt / calc_signal_filt_td
+// (reference detprocess/process/processing_data.py:763-772) and qp.OF1x1.calc /
+// get_result_* (reference detprocess/core/algorithms.py:331-341, 410-421, 533-558).
+//
+// Index conventions.  Packed complex sequence c[n] = x[2n] + i x[2n+1], n = n1*4096 + m,
+// m = n2*256 + n3*16 + n4.  Decimation in frequency, in place: after pass j digit n_j holds
+// k_j and the spectrum bin is k = k1 + R1*(k2 + 16 k3 + 256 k4).  A "group" is the 16
+// elements (k4 = 0..15) of one (block, k2, k3); the mirror M - k of a group element lies in
+// the mirror group with k4 -> 15 - k4 (except the two self-paired groups of block 0).
+#pragma once
+#include "dp_f2.cuh"
+#include "dp_of_kernel.cuh"
+
+template <class T> struct Dp2Traits;
+template <> struct Dp2Traits<double> {
+    using S = double;
+    static constexpr int VL = 1;
+};
+template <> struct Dp2Traits<f2> {
+    using S = float;
+    static constexpr int VL = 2;
+};
+
+// read-only 16-byte load of a packed pair of complex points
+DP_DEV cx<f2> dp_ldg(const cx<f2>* p) {
+#ifdef DP_HOST_EMU
+    return *p;
+#else
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return cx<f2>{f2(v.x, v.y), f2(v.z, v.w)};
+#endif
+}
+DP_DEV f2 dp_ldg(const f2* p) {
+#ifdef DP_HOST_EMU
+    return *p;
+#else
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return f2(v.x, v.y);
+#endif
+}
+
+// ------------------------------------------------------------------- geometry
+template <class T, int R1_> struct Dp2Geom {
+    using S = typename Dp2Traits<T>::S;
+    static constexpr int R1 = R1_;
+    static constexpr int VL = Dp2Traits<T>::VL;  // complex points per register vector V = cx<T>
+    static constexpr int M = 4096 * R1, N = 2 * M;
+    static constexpr int NBMAX = (VL == 2) ? 4 : 2;       // blocks that fit in 128 KB of shared memory
+    static constexpr int NB = R1 < NBMAX ? R1 : NBMAX;    // blocks per phase
+    static constexpr int NPH = R1 / NB;                   // phases
+    static constexpr int VPB = 4096 / VL;                 // V's per block
+    static constexpr int NV = NB * VPB;                   // V's per phase (<= 8192)
+    static constexpr int NT = NV / 16;                    // threads per CTA
+    static constexpr int GV = 16 / VL;                    // V's per group
+    static constexpr int CV = 256 / VL;                   // V's per 256 elements
+    static constexpr int NC = VPB / NT;                   // pass-1 columns per thread
+    static constexpr int GC = (16 / R1 < NC) ? 16 / R1 : NC;  // pass-1' columns handled together (<= 16 V live)
+    static constexpr int SMEM_V = NV + NV / GV;           // one pad V per group: conflict-free LDS.128 everywhere
+    static constexpr int KQ = M / 16;                     // bin stride between group elements (k4)
+    static DP_HD int phys(int v) { return v + v / GV; }
+    // spectrum-block index k1 of local block b in phase p
+    static DP_HD constexpr int k1_of(int p, int b) {
+        if (NPH == 1) return b;
+        if (NPH == 2) return p + 2 * b;
+        // NPH == 4 (R1 = 8, NB = 2): {0,4} {2,6} {1,7} {3,5}
+        const int a = (p == 0) ? 0 : (p == 1) ? 2 : (p == 2) ? 1 : 3;
+        return b == 0 ? a : (a == 0 ? R1 / 2 : R1 - a);
+    }
+    // local index of the mirror block (R1 - k1) % R1
+    static DP_HD constexpr int mirror_b(int p, int b) {
+        const int km = (R1 - k1_of(p, b)) % R1;
+        for (int c = 0; c < NB; ++c)
+            if (k1_of(p, c) == km) return c;
+        return -1;
+    }
+    // bin of element r of group G (phase-local group id b*256 + k2*16 + k3)
+    static DP_HD int bin_of(int p, int G, int r) {
+        const int b = G >> 8, k2 = (G >> 4) & 15, k3 = G & 15;
+        return k1_of(p, b) + R1 * (k2 + 16 * k3 + 256 * r);
+    }
+    // i-th (g, g') pair of phase p.  Pair 0 of phase 0 is the special one: both groups
+    // ((0,0,0) and (0,0,8) of block 0) are self-paired.
+    static DP_HD void pair_of(int p, int i, int& GA, int& GB) {
+        for (int b = 0; b < NB; ++b) {
+            const int mb = mirror_b(p, b);
+            if (mb < b) continue;
+            const int k1 = k1_of(p, b);
+            if (mb > b) {
+                if (i < 256) {
+                    const int k2 = i >> 4, k3 = i & 15;
+                    GA = b * 256 + k2 * 16 + k3;
+                    GB = mb * 256 + (15 - k2) * 16 + (15 - k3);
+                    return;
+                }
+                i -= 256;
+            } else {
+                if (i < 128) {
+                    int k2, k3, k2m, k3m;
+                    if (k1 != 0) {
+                        k2 = i >> 4, k3 = i & 15, k2m = 15 - k2, k3m = 15 - k3;
+                    } else if (i == 0) {
+                        k2 = 0, k3 = 0, k2m = 0, k3m = 8;
+                    } else if (i < 8) {
+                        k2 = 0, k3 = i, k2m = 0, k3m = 16 - i;
+                    } else if (i < 16) {
+                        k2 = 8, k3 = i - 8, k2m = 8, k3m = 15 - k3;
+                    } else {
+                        k2 = i >> 4, k3 = i & 15, k2m = 16 - k2, k3m = 15 - k3;
+                    }
+                    GA = b * 256 + k2 * 16 + k3;
+                    GB = b * 256 + k2m * 16 + k3m;
+                    return;
+                }
+                i -= 128;
+            }
+        }
+        GA = GB = -1;
+    }
+    // groups of thread t in phase p: VL == 2: (GA, GB) of pair t; VL == 1: own group and the
+    // partner's (thread t ^ 1)
+    static DP_HD void groups_of(int p, int t, int& Gown, int& Gother) {
+        if (VL == 2) {
+            pair_of(p, t, Gown, Gother);
+        } else {
+            int GA, GB;
+            pair_of(p, t >> 1, GA, GB);
+            Gown = (t & 1) ? GB : GA;
+            Gother = (t & 1) ? GA : GB;
+        }
+    }
+};
+
+// --------------------------------------------------------------- device tables
+template <class T> struct Dp2TemplDev {
+    using S = typename Dp2Traits<T>::S;
+    const cx<T>* phi;       // [NPH][16][NT] thread-order filter (VL == 2: lanes = (group A, group B) bins)
+    const cx<S>* phi_self;  // [17][2] filter at the bins of the self-paired groups
+    const cx<S>* s_low;     // [nlow] scaled template spectrum, natural order
+    double norm;
+    double tsum;
+    int pretrigger;
+    int pad_;
+};
+
+template <class T> struct Dp2ChanDev {
+    using S = typename Dp2Traits<T>::S;
+    const T* wj;       // [NPH][16][NT] thread-order chi0 weights
+    const S* wj_self;  // [17][2]
+    const S* wj_low;   // [nlow]
+    int n_templ;
+    int n_slots;
+    int out_base;
+    Dp2TemplDev<T> templ[DP_MAX_TEMPLATES];
+    DpSlot slots[DP_MAX_SLOTS];
+};
+
+template <class T> struct Dp2Params {
+    using S = typename Dp2Traits<T>::S;
+    const void* traces;
+    long long row_stride;  // elements
+    int n_rows;
+    int n_chan;
+    const Dp2ChanDev<T>* chans;
+    const cx<T>* tw1;      // [VPB]  exp(-2 pi i m / M), lanes m = VL*c + lane
+    const cx<T>* tw2;      // [CV]   exp(-2 pi i r / 4096)
+    const cx<T>* tw3;      // [GV]   exp(-2 pi i n4 / 256)
+    const cx<S>* twn;      // [NPH][NT] exp(-2 pi i k(own group, 0) / N)
+    const int2* groups;    // [NPH][NT] (own / A group, other / B group)
+    cx<T>* scratch;        // [grid][scratch_per_cta]
+    long long scratch_per_cta;
+    double* out;
+    int n_out;
+    int nlow;
+    double scale;
+    int subtract_first;
+};
+
+// --------------------------------------------------------------------- helpers
+template <class T> DP_DEV cx<T> dp2_csq(cx<T> a) { return cx<T>{dp_fma(a.re, a.re, -(a.im * a.im)), (a.re + a.re) * a.im}; }
+
+// powers w^0..w^(R-1) (only the used ones survive dead-code elimination)
+template <int R, class T> DP_DEV void dp2_powers(cx<T> w, cx<T> (&pw)[R]) {
+    pw[0] = cx<T>{(T)1.0f, (T)0.0f};
+    if constexpr (R > 1) pw[1] = w;
+    if constexpr (R > 2) pw[2] = dp2_csq(w);
+    if constexpr (R > 3) pw[3] = cmul(pw[2], w);
+    if constexpr (R > 4) pw[4] = dp2_csq(pw[2]);
+    if constexpr (R > 5) pw[5] = cmul(pw[4], w);
+    if constexpr (R > 6) pw[6] = cmul(pw[4], pw[2]);
+    if constexpr (R > 7) pw[7] = cmul(pw[4], pw[3]);
+}
+
+// lanes of a packed complex pair
+DP_DEV cx<float> dp2_lane0(cx<f2> z) { return cx<float>{z.re.x, z.im.x}; }
+DP_DEV cx<float> dp2_lane1(cx<f2> z) { return cx<float>{z.re.y, z.im.y}; }
+DP_DEV void dp2_set0(cx<f2>& z, cx<float> v) { z.re.x = v.re, z.im.x = v.im; }
+DP_DEV void dp2_set1(cx<f2>& z, cx<float> v) { z.re.y = v.re, z.im.y = v.im; }
+
+// ---- trace loads: V (n1, c) = complex points n = n1*4096 + VL*c + lane = samples 2n, 2n+1
+template <int IN, int VL> struct Dp2Raw {
+    typename DpRaw<IN>::type q[VL];
+};
+template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw(const void* row, int n1, int c) {
+    Dp2Raw<IN, VL> r;
+    const long long j0 = (long long)n1 * 4096 + (long long)VL * c;
+#pragma unroll
+    for (int l = 0; l < VL; ++l) r.q[l] = dp_load_raw<IN>(row, j0 + l);
+    return r;
+}
+template <int IN> DP_DEV cx<double> dp2_convert(const Dp2Raw<IN, 1>& r, double x0, double sc) {
+    return cx<double>{((double)r.q[0].x - x0) * sc, ((double)r.q[0].y - x0) * sc};
+}
+template <int IN> DP_DEV cx<f2> dp2_convert(const Dp2Raw<IN, 2>& r, double x0, double sc) {
+    return cx<f2>{f2((float)(((double)r.q[0].x - x0) * sc), (float)(((double)r.q[1].x - x0) * sc)),
+                  f2((float)(((double)r.q[0].y - x0) * sc), (float)(((double)r.q[1].y - x0) * sc))};
+}
+
+// tie-aware running best (|val| larger, or equal and smaller index)
+template <class S> DP_DEV void dp2_consider(DpBest<S>& b, S kabs, S v, int idx) {
+    const S kb = dp_abs(b.val);
+    if (b.idx < 0 || kabs > kb || (kabs == kb && idx < b.idx)) {
+        b.val = v;
+        b.idx = idx;
+    }
+}
+
+// ======================================================================== core
+template <class T, int R1, int IN> struct Dp2Core {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    using V = cx<T>;
+    static constexpr int NT = G::NT, VL = G::VL, NB = G::NB, NPH = G::NPH, VPB = G::VPB, GV = G::GV, CV = G::CV, NC = G::NC;
+
+    // ---- pass 1 of phase PH: global -> radix-R1 over n1 (only the phase's blocks) -> twiddle -> smem
+    template <int PH> static DP_DEV void pass1(const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1) {
+        const int tid = threadIdx.x;
+        // columns loaded back to back: <= 64 registers of raw float64 samples in flight
+        constexpr int CBW = ((VL == 2) ? 8 : 16) / R1;
+        constexpr int CB = CBW < 1 ? 1 : (CBW > NC ? NC : CBW);
+#pragma unroll
+        for (int i0 = 0; i0 < NC; i0 += CB) {
+            Dp2Raw<IN, VL> raw[CB][R1];
+#pragma unroll
+            for (int i = 0; i < CB; ++i)
+#pragma unroll
+                for (int n = 0; n < R1; ++n) raw[i][n] = dp2_load_raw<IN, VL>(row, n, tid + (i0 + i) * NT);
+#pragma unroll
+            for (int i = 0; i < CB; ++i) {
+                const int c = tid + (i0 + i) * NT;
+                V v[R1];
+#pragma unroll
+                for (int n = 0; n < R1; ++n) v[n] = dp2_convert<IN>(raw[i][n], x0, sc);
+                dp_dft<R1, -1, T>::run(v);
+                V pw[R1];
+                dp2_powers<R1, T>(dp_ldg(tw1 + c), pw);
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const int k1 = G::k1_of(PH, b);
+                    buf[G::phys(b * VPB + c)] = (k1 == 0) ? v[k1] : cmul(v[k1], pw[k1]);
+                }
+            }
+        }
+    }
+    static DP_DEV void pass1_any(int p, const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1) {
+        if constexpr (NPH == 1) {
+            pass1<0>(row, x0, sc, buf, tw1);
+        } else if constexpr (NPH == 2) {
+            if (p == 0)
+                pass1<0>(row, x0, sc, buf, tw1);
+            else
+                pass1<1>(row, x0, sc, buf, tw1);
+        } else {
+            switch (p) {
+                case 0: pass1<0>(row, x0, sc, buf, tw1); break;
+                case 1: pass1<1>(row, x0, sc, buf, tw1); break;
+                case 2: pass1<2>(row, x0, sc, buf, tw1); break;
+                default: pass1<3>(row, x0, sc, buf, tw1); break;
+            }
+        }
+    }
+
+    // ---- passes 2..4 (caller has synchronised after pass 1); result: pass-4 outputs of the
+    // thread's group(s) in z[16] (VL == 2: lane 0 = group GA, lane 1 = group GB)
+    static DP_DEV void fwd_234(V* buf, const V* DP_RESTRICT tw2, const V* DP_RESTRICT tw3, int GA, int GB, V (&z)[16]) {
+        const int tid = threadIdx.x;
+        {
+            const int b = tid / CV, cc = tid % CV, base = b * VPB + cc;
+#pragma unroll
+            for (int n = 0; n < 16; ++n) z[n] = buf[G::phys(base + n * CV)];
+            dp_dft<16, -1, T>::run(z);
+            dp_twiddle<16, false, T>(z, dp_ldg(tw2 + cc));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) buf[G::phys(base + k * CV)] = z[k];
+        }
+        __syncthreads();
+        {
+            const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV, base = b * VPB + k2 * CV + q;
+#pragma unroll
+            for (int n = 0; n < 16; ++n) z[n] = buf[G::phys(base + n * GV)];
+            dp_dft<16, -1, T>::run(z);
+            dp_twiddle<16, false, T>(z, dp_ldg(tw3 + q));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) buf[G::phys(base + k * GV)] = z[k];
+        }
+        __syncthreads();
+        load_groups(buf, GA, GB, z);
+        dp_dft<16, -1, T>::run(z);
+    }
+
+    // group element r of GA (and GB) -> z[r] (lanes)
+    static DP_DEV void load_groups(const V* buf, int GA, int GB, V (&z)[16]) {
+        if constexpr (VL == 1) {
+            (void)GB;
+#pragma unroll
+            for (int n = 0; n < 16; ++n) z[n] = buf[G::phys(GA * 16 + n)];
+        } else {
+            // canonical layout packs adjacent elements (2j, 2j+1); pass 4 wants (A[r], B[r]) lanes
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const V a = buf[G::phys(GA * 8 + j)], b = buf[G::phys(GB * 8 + j)];
+                z[2 * j] = V{f2(a.re.x, b.re.x), f2(a.im.x, b.im.x)};
+                z[2 * j + 1] = V{f2(a.re.y, b.re.y), f2(a.im.y, b.im.y)};
+            }
+        }
+    }
+    static DP_DEV void store_groups(V* buf, int GA, int GB, const V (&z)[16]) {
+        if constexpr (VL == 1) {
+            (void)GB;
+#pragma unroll
+            for (int n = 0; n < 16; ++n) buf[G::phys(GA * 16 + n)] = z[n];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                buf[G::phys(GA * 8 + j)] = V{f2(z[2 * j].re.x, z[2 * j + 1].re.x), f2(z[2 * j].im.x, z[2 * j + 1].im.x)};
+                buf[G::phys(GB * 8 + j)] = V{f2(z[2 * j].re.y, z[2 * j + 1].re.y), f2(z[2 * j].im.y, z[2 * j + 1].im.y)};
+            }
+        }
+    }
+
+    // ---- inverse passes 4', 3', 2': consumes group values z; leaves the pass-2' outputs of
+    // column (b, cc) in z[n2] (V index b*VPB + n2*CV + cc).  No trailing barrier.
+    static DP_DEV void inv_432(V* buf, const V* DP_RESTRICT tw2, const V* DP_RESTRICT tw3, int GA, int GB, V (&z)[16]) {
+        const int tid = threadIdx.x;
+        dp_dft<16, +1, T>::run(z);
+        store_groups(buf, GA, GB, z);
+        __syncthreads();
+        {
+            const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV, base = b * VPB + k2 * CV + q;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) z[k] = buf[G::phys(base + k * GV)];
+            dp_twiddle<16, true, T>(z, dp_ldg(tw3 + q));
+            dp_dft<16, +1, T>::run(z);
+#pragma unroll
+            for (int n = 0; n < 16; ++n) buf[G::phys(base + n * GV)] = z[n];
+        }
+        __syncthreads();
+        {
+            const int b = tid / CV, cc = tid % CV, base = b * VPB + cc;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) z[k] = buf[G::phys(base + k * CV)];
+            dp_twiddle<16, true, T>(z, dp_ldg(tw2 + cc));
+            dp_dft<16, +1, T>::run(z);
+        }
+    }
+    // pass-2' outputs -> smem (own positions, in place)
+    static DP_DEV void store_pass2(V* buf, const V (&z)[16]) {
+        const int tid = threadIdx.x;
+        const int b = tid / CV, cc = tid % CV, base = b * VPB + cc;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) buf[G::phys(base + n * CV)] = z[n];
+    }
+    // pass-2' outputs of a non-final phase -> parked block results in scratch [p*NB + b][VPB]
+    static DP_DEV void park_pass2(V* scr, int p, const V (&z)[16]) {
+        const int tid = threadIdx.x;
+        const int b = tid / CV, cc = tid % CV;
+        V* dst = scr + (long long)(p * NB + b) * VPB + cc;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) dst[n * CV] = z[n];
+    }
+    // ---- pass 1' for columns [i0, i0 + GC): y[i*R1 + n1] = c'[n1*4096 + VL*(tid + (i0+i)*NT) + lane]
+    static DP_DEV void inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1]) {
+        const int tid = threadIdx.x;
+        constexpr int LP = NPH - 1;
+#pragma unroll
+        for (int i = 0; i < G::GC; ++i) {
+            const int c = tid + (i0 + i) * NT;
+            V u[R1];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) u[G::k1_of(LP, b)] = buf[G::phys(b * VPB + c)];
+#pragma unroll
+            for (int p = 0; p < LP; ++p)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) u[G::k1_of(p, b)] = scr[(long long)(p * NB + b) * VPB + c];
+            V w = dp_ldg(tw1 + c);
+            w.im = -w.im;
+            V pw[R1];
+            dp2_powers<R1, T>(w, pw);
+#pragma unroll
+            for (int k = 1; k < R1; ++k) u[k] = cmul(u[k], pw[k]);
+            dp_dft<R1, +1, T>::run(u);
+#pragma unroll
+            for (int n = 0; n < R1; ++n) y[i * R1 + n] = u[n];
+        }
+    }
+};
+
+// ------------------------------------------------------- windowed arg-max scans
+// y[i*R1 + n1], i < GC: amplitude samples with rolled delay index
+//     r = 2*(n1*4096 + VL*(tid + (i0+i)*NT) + lane) + (0: real part, 1: imaginary part).
+// Scanned in ascending r with a strict '>' (first maximum, like numpy argmin on chi2).
+template <class T, int R1> struct Dp2Scan {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    static constexpr int VL = G::VL, NT = G::NT, GC = G::GC;
+
+    template <int L> static DP_DEV S re_of(const cx<T>& v) {
+        if constexpr (VL == 1) return v.re; else return L == 0 ? v.re.x : v.re.y;
+    }
+    template <int L> static DP_DEV S im_of(const cx<T>& v) {
+        if constexpr (VL == 1) return v.im; else return L == 0 ? v.im.x : v.im.y;
+    }
+    static DP_DEV void full(const cx<T> (&y)[GC * R1], int tid, int i0, DpBest<S>& out) {
+        S vb = (S)0, kb = (S)-1;
+        int pb = 0;
+#pragma unroll
+        for (int n = 0; n < R1; ++n)
+#pragma unroll
+            for (int i = 0; i < GC; ++i) {
+                const int off = 2 * (n * 4096 + VL * (i0 + i) * NT);
+                const cx<T>& v = y[i * R1 + n];
+                if (dp_abs(re_of<0>(v)) > kb) kb = dp_abs(re_of<0>(v)), vb = re_of<0>(v), pb = off;
+                if (dp_abs(im_of<0>(v)) > kb) kb = dp_abs(im_of<0>(v)), vb = im_of<0>(v), pb = off + 1;
+                if constexpr (VL == 2) {
+                    if (dp_abs(re_of<1>(v)) > kb) kb = dp_abs(re_of<1>(v)), vb = re_of<1>(v), pb = off + 2;
+                    if (dp_abs(im_of<1>(v)) > kb) kb = dp_abs(im_of<1>(v)), vb = im_of<1>(v), pb = off + 3;
+                }
+            }
+        DpBest<S> c{vb, 2 * VL * tid + pb};
+        dp_best_merge(out, c);
+    }
+    static DP_DEV void window(const cx<T> (&y)[GC * R1], int tid, int i0, int lo, unsigned len, bool outside, DpBest<S>& out) {
+        S kb = (S)-1, vb = (S)0;
+        int pb = -1;
+        const int rb = 2 * VL * tid;
+#pragma unroll
+        for (int n = 0; n < R1; ++n) {
+            // CTA-uniform skip: row n1 = n of this column set covers r in [blo, bhi)
+            const int blo = 2 * (n * 4096 + VL * i0 * NT), bhi = 2 * (n * 4096 + VL * (i0 + GC) * NT);
+            const bool hit = outside ? !(lo <= blo && (long long)bhi <= (long long)lo + (long long)len)
+                                     : (lo < bhi && (long long)lo + (long long)len > (long long)blo);
+            if (hit) {
+#pragma unroll
+                for (int i = 0; i < GC; ++i) {
+                    const int r0 = rb + 2 * (n * 4096 + VL * (i0 + i) * NT);
+                    const cx<T>& v = y[i * R1 + n];
+#define DP2_CAND(val, rr)                                                  \
+    {                                                                      \
+        const S a_ = (val);                                                \
+        const int r_ = (rr);                                               \
+        const bool in_ = ((unsigned)(r_ - lo) < len) != outside;           \
+        if (in_ && dp_abs(a_) > kb) kb = dp_abs(a_), vb = a_, pb = r_;     \
+    }
+                    DP2_CAND(re_of<0>(v), r0)
+                    DP2_CAND(im_of<0>(v), r0 + 1)
+                    if constexpr (VL == 2) {
+                        DP2_CAND(re_of<1>(v), r0 + 2)
+                        DP2_CAND(im_of<1>(v), r0 + 3)
+                    }
+#undef DP2_CAND
+                }
+            }
+        }
+        DpBest<S> c{vb, pb};
+        dp_best_merge(out, c);
+    }
+};
+
+// ====================================================================== kernel
+template <class T, int R1, int IN> struct Dp2OfKernel {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    using V = cx<T>;
+    using Core = Dp2Core<T, R1, IN>;
+    static constexpr int NT = G::NT, VL = G::VL, NB = G::NB, NPH = G::NPH, VPB = G::VPB, GC = G::GC, NC = G::NC;
+    static constexpr int NW = NT / 32;
+    static constexpr int N = G::N;
+    static constexpr int RED_DOUBLES = (DP_MAX_TSLOTS + 1) * 32;
+    static constexpr int BEST_ELEMS = DP_MAX_TSLOTS * 32;
+    static constexpr int SP_ELEMS = 32;
+    static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (DP_NLOW_MAX + SP_ELEMS) +
+                                         2 * (sizeof(double) * RED_DOUBLES + sizeof(DpBest<S>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS) + 64;
+    // scratch per CTA (V units): X spill [16][NT] (multi-template) + per template the parked
+    // block results of the non-final phases [(NPH-1)*NB][VPB]
+    static constexpr long long SCR_X = (long long)16 * NT;
+    static constexpr long long SCR_PARK = (long long)(NPH - 1) * NB * VPB;
+    static DP_HD long long scratch_v(int n_templ) { return SCR_X + SCR_PARK * n_templ; }
+
+    struct Smem {
+        V* buf;
+        cx<S>* stash;
+        cx<S>* sp;
+        double* red0;
+        DpBest<S>* best0;
+        int* slot0;
+        DP_DEV double* red(int par) const { return red0 + par * RED_DOUBLES; }
+        DP_DEV DpBest<S>* best(int par) const { return best0 + par * BEST_ELEMS; }
+        DP_DEV int* slot_id(int par) const { return slot0 + par * DP_MAX_TSLOTS; }
+    };
+    static DP_DEV Smem carve(unsigned char* raw) {
+        Smem s;
+        s.buf = reinterpret_cast<V*>(raw);
+        s.stash = reinterpret_cast<cx<S>*>(s.buf + G::SMEM_V);
+        s.sp = s.stash + DP_NLOW_MAX;
+        s.red0 = reinterpret_cast<double*>(s.sp + SP_ELEMS);
+        s.best0 = reinterpret_cast<DpBest<S>*>(s.red0 + 2 * RED_DOUBLES);
+        s.slot0 = reinterpret_cast<int*>(s.best0 + 2 * BEST_ELEMS);
+        return s;
+    }
+
+    static DP_DEV void prefetch_next(const Dp2Params<T>& prm, int row) {
+        constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
+        const int nrow = row + gridDim.x;
+        if (nrow < prm.n_rows) {
+            const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * ESZ;
+            constexpr int nlines = (int)((size_t)N * ESZ / 128);
+            for (int l = threadIdx.x; l < nlines; l += NT) dp_prefetch_l2(nx + (size_t)l * 128);
+        }
+    }
+
+    // ---- point-wise stage, forward half: z (pass-4 outputs) -> 2*X at the thread's bins.
+    // VL == 2: z[r] lanes = X at (bin of A[r], bin of B[r]).
+    // VL == 1: z[0..7] = X at own[r]; zm[0..7] = X at M - bin(own[r]) (the partner's element 15 - r).
+    // Returns the thread's chi0 partial sum (scalar type S).
+    static DP_DEV S untangle_all(const Smem& sm, V (&z)[16], V (&zm)[VL == 1 ? 8 : 1], const T* DP_RESTRICT wj, cx<S> wn, int Gown,
+                                 bool special) {
+        const int tid = threadIdx.x;
+        S chi = (S)0;
+        if constexpr (VL == 2) {
+            (void)zm;
+            (void)Gown;
+            (void)sm;
+#define DP2_XP(r)                                                                         \
+    {                                                                                     \
+        cx<S> Xk, Xm;                                                                     \
+        dp_untangle(dp2_lane0(z[r]), dp2_lane1(z[15 - r]), cmul(wn, dp_w64<S, 2 * r, -1>()), Xk, Xm); \
+        dp2_set0(z[r], Xk);                                                               \
+        dp2_set1(z[15 - r], Xm);                                                          \
+    }
+            DP2_XP(0) DP2_XP(1) DP2_XP(2) DP2_XP(3) DP2_XP(4) DP2_XP(5) DP2_XP(6) DP2_XP(7)
+            DP2_XP(8) DP2_XP(9) DP2_XP(10) DP2_XP(11) DP2_XP(12) DP2_XP(13) DP2_XP(14) DP2_XP(15)
+#undef DP2_XP
+            f2 acc = f2(0.0f);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc = dp_fma(dp_ldg(wj + r * NT + tid), cnorm2(z[r]), acc);
+            chi = acc.x + acc.y;
+        } else {
+            // exchange the upper halves with the partner thread (tid ^ 1) through the (now idle)
+            // group rows of the shared buffer: own elements 8..15 out, partner's 8..15 in
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sm.buf[G::phys(Gown * 16 + 8 + j)] = z[8 + j];
+            __syncwarp();
+            int Gp = __shfl_xor_sync(0xffffffffu, Gown, 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) zm[j] = sm.buf[G::phys(Gp * 16 + 15 - j)];  // partner element 15 - j
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                cx<S> Xk, Xm;
+                dp_untangle(z[r], zm[r], cmul(wn, dp_w64_rt<S>(2 * r)), Xk, Xm);
+                chi = dp_fma(dp_ldg(wj + (2 * r) * NT + tid), cnorm2(Xk), chi);
+                chi = dp_fma(dp_ldg(wj + (2 * r + 1) * NT + tid), cnorm2(Xm), chi);
+                z[r] = Xk;
+                zm[r] = Xm;
+            }
+        }
+        return special ? (S)0 : chi;
+    }
+
+    // filter multiply + inverse untangle, in place: (z, zm) X -> Z' (group values for pass 4')
+    static DP_DEV void filter_all(const Smem& sm, V (&z)[16], V (&zm)[VL == 1 ? 8 : 1], const V* DP_RESTRICT phi, cx<S> wn, int Gown) {
+        const int tid = threadIdx.x;
+        if constexpr (VL == 2) {
+            (void)zm;
+            (void)Gown;
+            (void)sm;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) z[r] = cmul(dp_ldg(phi + r * NT + tid), z[r]);
+#define DP2_FP(r)                                                                          \
+    {                                                                                      \
+        cx<S> Ck, Cm;                                                                      \
+        dp_retangle(dp2_lane0(z[r]), dp2_lane1(z[15 - r]), cmul(wn, dp_w64<S, 2 * r, -1>()), Ck, Cm); \
+        dp2_set0(z[r], Ck);                                                                \
+        dp2_set1(z[15 - r], Cm);                                                           \
+    }
+            DP2_FP(0) DP2_FP(1) DP2_FP(2) DP2_FP(3) DP2_FP(4) DP2_FP(5) DP2_FP(6) DP2_FP(7)
+            DP2_FP(8) DP2_FP(9) DP2_FP(10) DP2_FP(11) DP2_FP(12) DP2_FP(13) DP2_FP(14) DP2_FP(15)
+#undef DP2_FP
+        } else {
+            const int Gp = __shfl_xor_sync(0xffffffffu, Gown, 1);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const cx<S> Fk = cmul(dp_ldg(phi + (2 * r) * NT + tid), z[r]);
+                const cx<S> Fm = cmul(dp_ldg(phi + (2 * r + 1) * NT + tid), zm[r]);
+                cx<S> Ck, Cm;
+                dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
+                z[r] = Ck;
+                sm.buf[G::phys(Gp * 16 + 15 - r)] = Cm;  // partner's element 15 - r
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[8 + j] = sm.buf[G::phys(Gown * 16 + 8 + j)];
+        }
+    }
+
+    static DP_DEV void run(const Dp2Params<T>& prm, unsigned char* smem_raw);
+};
+
+template <class T, int R1, int IN>
+DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* smem_raw) {
+    const Smem sm = carve(smem_raw);
+    const int tid = threadIdx.x;
+    constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
+    V* scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;  // [16][NT] X of the current phase (multi-template)
+    V* scr_park = scr_x + SCR_X;                                           // [n_templ][(NPH-1)*NB][VPB] parked block results
+    const DpSelfLane<S> sp = dp_self_lane<S, 1>(tid & 31);
+    // special threads: the self-paired groups (0,0,0) and (0,0,8) of block 0 (phase 0)
+    constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
+    int par = 0;
+    double chi0_keep = 0.0;
+
+    for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
+        const int chan = row % prm.n_chan;
+        const int ev = row / prm.n_chan;
+        const Dp2ChanDev<T>& ch = prm.chans[chan];
+        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
+        const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+        const bool multi = ch.n_templ > 1;
+        S chi = (S)0;
+        cx<S> sXk = cx<S>{(S)0, (S)0}, sXm = sXk;  // lanes 0..16 of warp 0: 2*X of their self pair
+
+#pragma unroll 1
+        for (int p = 0; p < NPH; ++p) {
+            // ---------------- forward of phase p: X at the phase's bins, in registers ----------
+            V z[16];
+            V zm[VL == 1 ? 8 : 1];
+            const int2 gg = prm.groups[p * NT + tid];
+            const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
+            const bool special = (p == 0) && (tid < NSPECIAL);
+            Core::pass1_any(p, xrow, x0, prm.scale, sm.buf, prm.tw1);
+            __syncthreads();
+            Core::fwd_234(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+            if (p == 0 && tid < 32) {
+                // self-paired groups -> 17 lanes of warp 0
+                if constexpr (VL == 2) {
+                    if (tid == 0) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            sm.sp[r] = dp2_lane0(z[r]);
+                            sm.sp[16 + r] = dp2_lane1(z[r]);
+                        }
+                    }
+                } else {
+                    if (tid < 2) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) sm.sp[16 * tid + r] = z[r];
+                    }
+                }
+                __syncwarp();
+                if (tid < 17) {
+                    dp_untangle(sm.sp[sp.ek], sm.sp[sp.em], sp.w, sXk, sXm);
+                    chi = dp_fma(dp_ldg(ch.wj_self + 2 * tid), cnorm2(sXk), chi);
+                    chi = dp_fma(dp_ldg(ch.wj_self + 2 * tid + 1), cnorm2(sXm), chi);
+                    if (tid == 0) sm.stash[0] = sXk;
+                    if (tid == 9 && G::KQ / 2 < prm.nlow) sm.stash[G::KQ / 2] = sXk;
+                }
+                __syncwarp();
+            }
+            chi += untangle_all(sm, z, zm, ch.wj + (long long)p * 16 * NT, wn, gg.x, special);
+            if (!special) {
+                // low-frequency bins for lowchi2: element 0 of each group (k4 = 0)
+                const int kA = G::bin_of(p, gg.x, 0);
+                if constexpr (VL == 2) {
+                    const int kB = G::bin_of(p, gg.y, 0);
+                    if (kA < prm.nlow) sm.stash[kA] = dp2_lane0(z[0]);
+                    if (kB < prm.nlow) sm.stash[kB] = dp2_lane1(z[0]);
+                } else {
+                    if (kA < prm.nlow) sm.stash[kA] = z[0];
+                }
+            }
+            if (p == NPH - 1) prefetch_next(prm, row);
+            if (multi) {
+                // X must survive the in-place inverse of the previous template (thread-private column)
+                V* dst = scr_x + tid;
+                if constexpr (VL == 2) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) dst[r * NT] = z[r];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        dst[(2 * r) * NT] = z[r];
+                        dst[(2 * r + 1) * NT] = zm[r];
+                    }
+                }
+            }
+
+            // ---------------- per template: filter, inverse passes 4' 3' 2' ---------------------
+            for (int it = 0; it < ch.n_templ; ++it) {
+                const Dp2TemplDev<T>& tp = ch.templ[it];
+                V* park = scr_park + (long long)it * SCR_PARK;
+                if (it > 0) {
+                    const V* src = scr_x + tid;
+                    if constexpr (VL == 2) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) z[r] = src[r * NT];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            z[r] = src[(2 * r) * NT];
+                            zm[r] = src[(2 * r + 1) * NT];
+                        }
+                    }
+                }
+                if (p == 0 && tid < 17) {
+                    const cx<S> Fk = cmul(dp_ldg(tp.phi_self + 2 * tid), sXk);
+                    const cx<S> Fm = cmul(dp_ldg(tp.phi_self + 2 * tid + 1), sXm);
+                    cx<S> Ck, Cm;
+                    dp_retangle(Fk, Fm, sp.w, Ck, Cm);
+                    sm.sp[sp.ek] = Ck;
+                    if (sp.ek != sp.em) sm.sp[sp.em] = Cm;
+                }
+                filter_all(sm, z, zm, tp.phi + (long long)p * 16 * NT, wn, gg.x);
+                if (p == 0 && tid < 32) {
+                    __syncwarp();
+                    if constexpr (VL == 2) {
+                        if (tid == 0) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) z[r] = V{f2(sm.sp[r].re, sm.sp[16 + r].re), f2(sm.sp[r].im, sm.sp[16 + r].im)};
+                        }
+                    } else {
+                        if (tid < 2) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) z[r] = sm.sp[16 * tid + r];
+                        }
+                    }
+                    __syncwarp();
+                }
+                Core::inv_432(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                if (p < NPH - 1) {
+                    Core::park_pass2(park, p, z);
+                    __syncthreads();  // pass-2' reads of buf precede the next group / pass-1 stores
+                    continue;
+                }
+                // ------------ last phase: pass 1' over all blocks, arg-max, outputs --------------
+                Core::store_pass2(sm.buf, z);
+                __syncthreads();  // also orders the parked block results (global memory) within the CTA
+                int slot_of[DP_MAX_TSLOTS];
+                int nts = 0;
+#pragma unroll
+                for (int q = 0; q < DP_MAX_TSLOTS; ++q) slot_of[q] = -1;
+                for (int s = 0; s < ch.n_slots; ++s) {
+                    if (ch.slots[s].templ == it) {
+#pragma unroll
+                        for (int q = 0; q < DP_MAX_TSLOTS; ++q)
+                            if (q == nts) slot_of[q] = s;
+                        ++nts;
+                    }
+                }
+                DpBest<S> tb[DP_MAX_TSLOTS];
+#pragma unroll
+                for (int q = 0; q < DP_MAX_TSLOTS; ++q) tb[q] = DpBest<S>{(S)0, -1};
+#pragma unroll 1
+                for (int i0 = 0; i0 < NC; i0 += GC) {
+                    V y[GC * R1];
+                    Core::inv_pass1(sm.buf, park, prm.tw1, i0, y);
+#pragma unroll
+                    for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                        if (q < nts) {
+                            const DpSlot sl = ch.slots[slot_of[q]];
+                            if (sl.lo == 0 && sl.hi == N && !sl.outside)
+                                Dp2Scan<T, R1>::full(y, tid, i0, tb[q]);
+                            else
+                                Dp2Scan<T, R1>::window(y, tid, i0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, tb[q]);
+                        }
+                    }
+                }
+                DpBest<S>* best = sm.best(par);
+                double* red = sm.red(par);
+#pragma unroll
+                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                    if (q < nts) {
+                        const DpBest<S> b = dp_warp_best(tb[q]);
+                        if ((tid & 31) == 0) best[q * 32 + (tid >> 5)] = b;
+                        if (tid == 0) sm.slot_id(par)[q] = slot_of[q];
+                    }
+                }
+                __syncthreads();  // winners + the lowchi2 stash are visible; pass-1' reads of buf are done
+                // ---- low-frequency chi2 at each fit's (amp, delay); chi0; outputs ----------------
+                double part[DP_MAX_TSLOTS + 1];
+#pragma unroll
+                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                    part[q] = 0.0;
+                    if (q < nts && tid < prm.nlow) {
+                        DpBest<S> b = best[q * 32];
+                        for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
+                        const int d = b.idx - tp.pretrigger;
+                        for (int k = tid; k < prm.nlow; k += NT) {
+                            const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
+                            S sn, cs;
+                            if constexpr (sizeof(S) == 8) {
+                                double s_, c_;
+                                sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
+                                sn = (S)s_;
+                                cs = (S)c_;
+                            } else {
+                                float s_, c_;
+                                sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
+                                sn = (S)s_;
+                                cs = (S)c_;
+                            }
+                            const cx<S> mdl = cmul(cx<S>{cs, -sn}, dp_ldg(tp.s_low + k));
+                            const cx<S> X = sm.stash[k];
+                            const cx<S> R = cx<S>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
+                            part[q] += (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
+                        }
+                    }
+                }
+                part[DP_MAX_TSLOTS] = (it == 0) ? (double)chi : 0.0;
+#pragma unroll
+                for (int q = 0; q <= DP_MAX_TSLOTS; ++q) {
+                    if (q < nts || (q == DP_MAX_TSLOTS && it == 0)) {
+                        const double v = dp_warp_sum(part[q]);
+                        if ((tid & 31) == 0) red[q * 32 + (tid >> 5)] = v;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
+                    if (it == 0) {
+                        double c0 = 0.0;
+                        for (int w = 0; w < NW; ++w) c0 += red[DP_MAX_TSLOTS * 32 + w];
+                        chi0_keep = c0;
+                        o[0] = c0;
+                    }
+                    const double chi0 = chi0_keep;
+                    for (int q = 0; q < nts; ++q) {
+                        double low = 0.0;
+                        for (int w = 0; w < NW; ++w) low += red[q * 32 + w];
+                        DpBest<S> b = best[q * 32];
+                        for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
+                        double* os = o + 1 + sm.slot_id(par)[q] * DP_SLOT_NOUT;
+                        const double amp = (double)b.val;
+                        os[0] = amp;
+                        os[1] = (double)b.idx;
+                        os[2] = chi0 - amp * amp * tp.norm;
+                        os[3] = low;
+                        os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
+                    }
+                }
+                par ^= 1;
+            }
+        }
+    }
+}
+
+#ifndef DP_HOST_EMU
+template <class T, int R1, int IN>
+__global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, 1) dp_of2_kernel(const Dp2Params<T> prm) {
+    extern __shared__ __align__(16) unsigned char dp_smem_raw[];
+    Dp2OfKernel<T, R1, IN>::run(prm, dp_smem_raw);
+}
+#endif

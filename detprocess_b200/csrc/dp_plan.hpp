@@ -189,6 +189,42 @@ inline int count_low_bins(int N, double fs, double fcut) {
     return n;
 }
 
+
+// exp(-2 pi i num/den), evaluated directly in long double
+inline cplx unit_root(long long num, long long den) {
+    const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)num / (long double)den;
+    return cplx((double)cosl(ang), (double)sinl(ang));
+}
+
+// chi0 weights on 2*sc*fft(x), one-sided bins k = 0..M:  wJ[k] = (1/J[k] + 1/J[N-k]) / (N^2 df) / (4 sc^2)
+inline std::vector<double> chi0_weights(const std::vector<double>& J, double fs, double scale) {
+    const int N = (int)J.size(), M = N / 2;
+    const double df = fs / N;
+    std::vector<double> wJ(M + 1);
+    for (int k = 0; k <= M; ++k) {
+        double w = 1.0 / J[k];
+        if (k != 0 && k != M) w += 1.0 / J[N - k];
+        wJ[k] = w / ((double)N * (double)N * df) / (4.0 * scale * scale);
+    }
+    return wJ;
+}
+
+// hermitian-symmetrised filter on the one-sided bins, all scalings folded in:
+//   amps_td[n] = sum_k phi_k fft(x)_k e^{+2 pi i k n/N} / (N norm),  kernel feeds 2*sc*fft(x);
+// the roll by `pretrigger` (zero delay at index pretrigger) is a phase ramp
+inline std::vector<cplx> filter_onesided(const Template& tp, double scale) {
+    const int N = (int)tp.phi.size(), M = N / 2;
+    std::vector<cplx> pe(M + 1);
+    for (int k = 0; k <= M; ++k) {
+        const cplx a = tp.phi[k], b = std::conj(tp.phi[(N - k) % N]);
+        const cplx roll = unit_root(((long long)k * (long long)tp.pretrigger) % N, N);
+        pe[k] = 0.5 * (a + b) * roll / ((double)N * tp.norm * 2.0 * scale);
+    }
+    pe[0] = cplx(pe[0].real(), 0.0);
+    pe[M] = cplx(pe[M].real(), 0.0);
+    return pe;
+}
+
 template <class T>
 DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Channel>& chans, double fcut, double scale) {
     DeviceTables<T> dt;
@@ -200,10 +236,7 @@ DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Cha
         throw std::invalid_argument("lowchi2_fcutoff too high for the fused kernel (needs <= " +
                                     std::to_string(std::min(2 * NT, DP_NLOW_MAX)) + " bins)");
     auto cxT = [](cplx z) { return cx<T>{(T)z.real(), (T)z.imag()}; };
-    auto root = [](long long num, long long den) {  // exp(-2 pi i num/den)
-        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)num / (long double)den;
-        return cplx((double)cosl(ang), (double)sinl(ang));
-    };
+    auto root = [](long long num, long long den) { return unit_root(num, den); };
     dt.tw1.resize(512);
     for (int m = 0; m < 512; ++m) dt.tw1[m] = cxT(root(m, MS));
     dt.tw2.resize(16);
@@ -219,13 +252,7 @@ DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Cha
     for (const auto& ch : chans) {
         typename DeviceTables<T>::Chan dc;
         if ((int)ch.J.size() != N) throw std::invalid_argument("psd not set for a channel");
-        // chi0 weights on 2*sc*fft(x):  wJ[k] = (1/J[k] + 1/J[N-k]) / (N^2 df) / (4 sc^2)
-        std::vector<double> wJ(M + 1);
-        for (int k = 0; k <= M; ++k) {
-            double w = 1.0 / ch.J[k];
-            if (k != 0 && k != M) w += 1.0 / ch.J[N - k];
-            wJ[k] = w / ((double)N * (double)N * df) / (4.0 * scale * scale);
-        }
+        const std::vector<double> wJ = chi0_weights(ch.J, fs, scale);
         dc.wj.resize((size_t)NE * NT);
         for (int e = 0; e < NE; ++e)
             for (int t = 0; t < NT; ++t) dc.wj[(size_t)e * NT + t] = (T)wJ[k_of(g, t, e)];
@@ -240,17 +267,7 @@ DeviceTables<T> build_tables(const Geometry& g, double fs, const std::vector<Cha
         for (int k = 0; k < dt.nlow; ++k) dc.wj_low[k] = (T)wJ[k];
         for (const auto& tp : ch.templ) {
             typename DeviceTables<T>::Templ d;
-            // hermitian-symmetrised filter, all scalings folded in:
-            //   amps_td[n] = sum_k phi_k fft(x)_k e^{+2 pi i k n/N} / (N norm),  kernel feeds 2*sc*fft(x)
-            std::vector<cplx> pe(M + 1);
-            for (int k = 0; k <= M; ++k) {
-                const cplx a = tp.phi[k], b = std::conj(tp.phi[(N - k) % N]);
-                // the roll by `pretrigger` (zero delay at index pretrigger) is a phase ramp
-                const cplx roll = root(((long long)k * (long long)tp.pretrigger) % N, N);
-                pe[k] = 0.5 * (a + b) * roll / ((double)N * tp.norm * 2.0 * scale);
-            }
-            pe[0] = cplx(pe[0].real(), 0.0);
-            pe[M] = cplx(pe[M].real(), 0.0);
+            const std::vector<cplx> pe = filter_onesided(tp, scale);
             d.phi.resize((size_t)NE * NT);
             for (int e = 0; e < NE; ++e)
                 for (int t = 0; t < NT; ++t) d.phi[(size_t)e * NT + t] = cxT(pe[k_of(g, t, e)]);

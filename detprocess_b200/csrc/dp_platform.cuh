@@ -24,6 +24,7 @@
 struct float2 { float x, y; };
 struct double2 { double x, y; };
 struct short2 { short x, y; };
+struct int2 { int x, y; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline double2 make_double2(double a, double b) { return double2{a, b}; }
 struct dp_dim3 { unsigned x = 1, y = 1, z = 1; };

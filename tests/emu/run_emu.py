@@ -6,12 +6,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EXE = os.path.join(HERE, '_build', 'emu_of')
 
 
-def build(tsan=False):
+def build(tsan=False, v2=False):
     os.makedirs(os.path.join(HERE, '_build'), exist_ok=True)
-    exe = EXE + ('_tsan' if tsan else '')
-    src = os.path.join(HERE, 'emu_of.cpp')
+    exe = EXE + ('2' if v2 else '') + ('_tsan' if tsan else '')
+    src = os.path.join(HERE, 'emu_of2.cpp' if v2 else 'emu_of.cpp')
     deps = [src] + [os.path.join(HERE, '../../detprocess_b200/csrc', f) for f in
-                    ('dp_of_kernel.cuh', 'dp_fft.cuh', 'dp_platform.cuh', 'dp_plan.hpp')]
+                    ('dp_of_kernel.cuh', 'dp_fft.cuh', 'dp_platform.cuh', 'dp_plan.hpp', 'dp_of2_kernel.cuh',
+                     'dp_plan2.hpp', 'dp_f2.cuh')]
     if os.path.exists(exe) and all(os.path.getmtime(exe) > os.path.getmtime(d) for d in deps):
         return exe
     cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-o', exe, src]
@@ -22,9 +23,9 @@ def build(tsan=False):
 
 
 def run(traces, psd, templates, fits, fs, fcut=10000.0, precision='f64', ac=True,
-        subtract_first=False, scale=1.0, tsan=False, force_p2=False):
+        subtract_first=False, scale=1.0, tsan=False, force_p2=False, v2=False):
     """templates: list of (template, pretrigger, integralnorm); fits: list of (templ, lo, hi, outside)."""
-    exe = build(tsan)
+    exe = build(tsan, v2)
     traces = np.ascontiguousarray(traces, dtype=np.float64)
     nev, n = traces.shape
     with tempfile.TemporaryDirectory() as td:

@@ -55,6 +55,35 @@ def test_of_kernel_emulated(nb_samples, precision, force_p2):
     _check(out, o2, [16], *tol)
 
 
+@pytest.mark.parametrize('nb_samples,precision', [
+    (16384, 'f64'), (16384, 'f32'), (32768, 'f32'), (32768, 'f64'), (65536, 'f32'), (65536, 'f64')])
+def test_of_v2_kernel_emulated(nb_samples, precision):
+    """v2 kernels (dp_of2_kernel.cuh): packed-fp32 / fp64, 1, 2 and 4 phases, two templates,
+    unconstrained + constrained + nodelay + outside-window fits."""
+    S = SynthSetup(nb_samples)
+    pre = S.nb_pretrigger
+    tr = make_traces(3, S.template, S.psd, S.fs, np.random.default_rng(5),
+                     offset=(1e-6 if precision == 'f64' else 0.0), amp_max=2e-7)
+    tr[2] = 0.0     # all-zero trace: every delay ties, numpy argmin takes the first candidate
+    w_def = [(None, None, False), (pre - 500, pre + 500, False), (pre, pre + 1, False)]
+    w_gl = [(pre - 100, pre + 300, True)]
+    fits = [(0, 0 if w[0] is None else w[0], nb_samples if w[1] is None else w[1], int(w[2])) for w in w_def]
+    fits += [(1, w[0], w[1], int(w[2])) for w in w_gl]
+    out = run_emu.run(tr, S.psd, [(S.template, pre, False), (S.template_glitch, pre, False)], fits, S.fs,
+                      precision=precision, subtract_first=(precision == 'f32'),
+                      scale=(2.0 ** 26 if precision == 'f32' else 1.0), v2=True)
+    o1 = of1x1_batch(tr[:2], S.template, S.psd, S.fs, pre, windows=w_def)
+    o2 = of1x1_batch(tr[:2], S.template_glitch, S.psd, S.fs, pre, windows=w_gl)
+    # tie-breaking on the all-zero trace: first candidate index of each window
+    assert list(out[2, [2, 7, 12, 17]].astype(int)) == [0, pre - 500, pre, 0]
+    assert np.all(out[2, [1, 6, 11, 16]] == 0.0)
+    tol = (1e-11, 1e-11, 1e-11) if precision == 'f64' else (1e-5, 1e-4, 1e-4)
+    out = out[:2]
+    assert np.max(np.abs(out[:, 0] / o1['chi0'] - 1)) < tol[1]
+    _check(out, o1, [1, 6, 11], *tol)
+    _check(out, o2, [16], *tol)
+
+
 def test_reduce_kernel_emulated_bit_exact():
     exe = os.path.join(HERE, 'emu', '_build', 'emu_reduce')
     src = os.path.join(HERE, 'emu', 'emu_reduce.cpp')

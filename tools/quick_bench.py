@@ -57,14 +57,19 @@ def time_reduce(N, B):
 
 
 if __name__ == '__main__':
-    print(torch.cuda.get_device_name(0))
+    import os
+    print(torch.cuda.get_device_name(0), 'DP_OF_KERNEL=' + os.environ.get('DP_OF_KERNEL', 'v2'))
+    only = sys.argv[1] if len(sys.argv) > 1 else 'all'
     time_of(32768, 'f32', 8192)
     time_of(32768, 'f32', 8192, windows='c2')
     time_of(32768, 'f32', 8192, two_templ=True, windows='c2')
-    time_of(16384, 'f32', 16384)
     time_of(32768, 'f64', 8192)
     time_of(32768, 'f64', 8192, two_templ=True, windows='c2')
-    time_of(65536, 'f32', 4096)
-    time_of(16384, 'f64', 8192)
-    time_of(8192, 'f64', 8192)
-    time_reduce(32768, 8192)
+    if only == 'all':
+        time_of(16384, 'f32', 16384)
+        time_of(16384, 'f64', 8192)
+        time_of(65536, 'f32', 4096)
+        if os.environ.get('DP_OF_KERNEL', 'v2') != 'v1':
+            time_of(65536, 'f64', 4096)
+        time_of(8192, 'f64', 8192)
+        time_reduce(32768, 8192)
