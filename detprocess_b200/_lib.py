@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_C', 'libdetprocess_b200.so')
+LIB_PATH = os.path.join(_HERE, '_C', os.environ.get('DP_LIB_NAME', 'libdetprocess_b200.so'))
 
 DP_OK = 0
 DP_PREC_F64, DP_PREC_F32 = 0, 1

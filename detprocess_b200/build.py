@@ -14,7 +14,9 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 OUT_DIR = os.path.join(PKG, '_C')
-LIB = os.path.join(OUT_DIR, 'libdetprocess_b200.so')
+# development A/B builds: DP_LIB_NAME=<name>.so DP_BUILD_DEFS='-DX=1 ...' python -m detprocess_b200.build --force
+LIB = os.path.join(OUT_DIR, os.environ.get('DP_LIB_NAME', 'libdetprocess_b200.so'))
+EXTRA_DEFS = os.environ.get('DP_BUILD_DEFS', '').split()
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3', '-lineinfo',
               '--fmad=true', '-Xcompiler', '-fPIC,-O2', '-Xptxas', '-v']
@@ -52,13 +54,13 @@ def build(force=False, verbose=True):
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libdetprocess_b200.so')
     os.makedirs(OUT_DIR, exist_ok=True)
-    obj_dir = os.path.join(OUT_DIR, 'obj')
+    obj_dir = os.path.join(OUT_DIR, 'obj' + ('_' + os.path.basename(LIB) if EXTRA_DEFS else ''))
     os.makedirs(obj_dir, exist_ok=True)
 
     def compile_unit(unit):
         name, src, defs = unit
         obj = os.path.join(obj_dir, name + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + defs + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_DEFS + defs + ['-c', '-o', obj, os.path.join(CSRC, src)]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return name, obj, ' '.join(cmd), res.returncode, res.stdout
 
@@ -76,7 +78,7 @@ def build(force=False, verbose=True):
         res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         log.append(f'### {" ".join(link)}\n{res.stdout}')
         ok = res.returncode == 0
-    with open(os.path.join(OUT_DIR, 'build.log'), 'w') as f:
+    with open(os.path.join(OUT_DIR, 'build.log' if not EXTRA_DEFS else 'build_' + os.path.basename(LIB) + '.log'), 'w') as f:
         f.write('\n'.join(log))
     if not ok:
         sys.stderr.write('\n'.join(log)[-8000:])

@@ -63,6 +63,7 @@ struct dp_of_plan {
     int device = 0;
     dpplan::Geometry geom;
     int v2_r1 = 0;  // != 0: the v2 kernels (dp_of2_kernel.cuh) serve this plan, M = v2_r1 * 4096
+    int v2_multi = 0;  // some channel has more than one template
     // device state
     std::vector<void*> owned;
     const void* d_chans = nullptr;
@@ -300,6 +301,7 @@ template <class T> int of2_finalize(dp_of_plan* p) {
         default: per_cta = Dp2OfKernel<T, 8, 0>::scratch_v(max_templ); break;
     }
     p->scratch_per_cta = per_cta;
+    p->v2_multi = max_templ > 1 ? 1 : 0;
     DP_CUDA(cudaMalloc(&p->scratch, sizeof(cx<T>) * (size_t)per_cta * (size_t)p->grid_max));
     p->owned.push_back(p->scratch);
     return DP_OK;
@@ -331,7 +333,7 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
     const int prec = sizeof(S) == 8 ? 0 : 1;
-    const int rc = dp_of2_launch_table[prec][in_dtype](p->v2_r1, &prm, grid, p->smem, st);
+    const int rc = dp_of2_launch_table[prec][in_dtype](p->v2_r1, p->v2_multi, &prm, grid, p->smem, st);
     if (rc == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");
     if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     if (timed) DP_CUDA(cudaEventRecord(p->ev1, st));

@@ -24,13 +24,16 @@ using InstT = f2;
 namespace {
 template <int R1> int setup_one(int device, size_t* smem, int* grid_max, int* occ_out, int* threads) {
     using K = Dp2OfKernel<InstT, R1, DP_INST_IN>;
-    auto kern = dp_of2_kernel<InstT, R1, DP_INST_IN>;
+    auto kern = dp_of2_kernel<InstT, R1, DP_INST_IN, false>;
+    auto kern_m = dp_of2_kernel<InstT, R1, DP_INST_IN, true>;
     *smem = K::SMEM_BYTES;
     *threads = K::NT;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
     int occ = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::NT, K::SMEM_BYTES);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_m, K::NT, K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return (int)e;
@@ -38,8 +41,11 @@ template <int R1> int setup_one(int device, size_t* smem, int* grid_max, int* oc
     *grid_max = sms * occ;
     return 0;
 }
-template <int R1> int launch_one(const Dp2Params<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
-    dp_of2_kernel<InstT, R1, DP_INST_IN><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+template <int R1> int launch_one(const Dp2Params<InstT>& prm, int multi, int grid, size_t smem, cudaStream_t st) {
+    if (multi)
+        dp_of2_kernel<InstT, R1, DP_INST_IN, true><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+    else
+        dp_of2_kernel<InstT, R1, DP_INST_IN, false><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
     return (int)cudaGetLastError();
 }
 }  // namespace
@@ -52,13 +58,13 @@ int DP_CAT(dp_of2_setup_p, DP_INST_PREC, DP_INST_IN)(int R1, int device, size_t*
         default: return -1;
     }
 }
-int DP_CAT(dp_of2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
+int DP_CAT(dp_of2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, int multi, const void* prm_v, int grid, size_t smem, void* st_v) {
     const Dp2Params<InstT>& prm = *reinterpret_cast<const Dp2Params<InstT>*>(prm_v);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
     switch (R1) {
-        case 2: return launch_one<2>(prm, grid, smem, st);
-        case 4: return launch_one<4>(prm, grid, smem, st);
-        case 8: return launch_one<8>(prm, grid, smem, st);
+        case 2: return launch_one<2>(prm, multi, grid, smem, st);
+        case 4: return launch_one<4>(prm, multi, grid, smem, st);
+        case 8: return launch_one<8>(prm, multi, grid, smem, st);
         default: return -1;
     }
 }

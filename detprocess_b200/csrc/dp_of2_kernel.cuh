@@ -26,6 +26,10 @@
 #include "dp_f2.cuh"
 #include "dp_of_kernel.cuh"
 
+#ifndef DP2_TBL_BATCH
+#define DP2_TBL_BATCH 8
+#endif
+
 template <class T> struct Dp2Traits;
 template <> struct Dp2Traits<double> {
     using S = double;
@@ -60,7 +64,13 @@ template <class T, int R1_> struct Dp2Geom {
     static constexpr int R1 = R1_;
     static constexpr int VL = Dp2Traits<T>::VL;  // complex points per register vector V = cx<T>
     static constexpr int M = 4096 * R1, N = 2 * M;
-    static constexpr int NBMAX = (VL == 2) ? 4 : 2;       // blocks that fit in 128 KB of shared memory
+#ifndef DP2_NBMAX_F32
+#define DP2_NBMAX_F32 4
+#endif
+    // blocks per phase: fp64 2 (128 KB of shared memory, 512 threads, one CTA per SM);
+    // packed fp32 2 (64 KB, 256 threads, TWO independent CTAs per SM whose load / butterfly /
+    // store phases overlap) -- 4 would be one 512-thread CTA per SM
+    static constexpr int NBMAX = (VL == 2) ? DP2_NBMAX_F32 : 2;
     static constexpr int NB = R1 < NBMAX ? R1 : NBMAX;    // blocks per phase
     static constexpr int NPH = R1 / NB;                   // phases
     static constexpr int VPB = 4096 / VL;                 // V's per block
@@ -191,6 +201,14 @@ template <class T> struct Dp2Params {
 };
 
 // --------------------------------------------------------------------- helpers
+// compiler-level fence: keeps ptxas from hoisting the next batch of table loads above the
+// work in front of it (the hoisted loads otherwise push the 16 register-resident points
+// into local memory; there is no L1 left to catch those spills)
+DP_DEV void dp2_sched_fence() {
+#ifndef DP_HOST_EMU
+    asm volatile("" ::: "memory");
+#endif
+}
 template <class T> DP_DEV cx<T> dp2_csq(cx<T> a) { return cx<T>{dp_fma(a.re, a.re, -(a.im * a.im)), (a.re + a.re) * a.im}; }
 
 // powers w^0..w^(R-1) (only the used ones survive dead-code elimination)
@@ -245,6 +263,8 @@ template <class T, int R1, int IN> struct Dp2Core {
     using S = typename G::S;
     using V = cx<T>;
     static constexpr int NT = G::NT, VL = G::VL, NB = G::NB, NPH = G::NPH, VPB = G::VPB, GV = G::GV, CV = G::CV, NC = G::NC;
+    // physical (padded) strides in V units: one group, 256 elements, one block
+    static constexpr int PG = GV + 1, PC = CV + CV / GV, PB = VPB + VPB / GV;
 
     // ---- pass 1 of phase PH: global -> radix-R1 over n1 (only the phase's blocks) -> twiddle -> smem
     template <int PH> static DP_DEV void pass1(const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1) {
@@ -271,7 +291,7 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     const int k1 = G::k1_of(PH, b);
-                    buf[G::phys(b * VPB + c)] = (k1 == 0) ? v[k1] : cmul(v[k1], pw[k1]);
+                    buf[G::phys(c) + b * PB] = (k1 == 0) ? v[k1] : cmul(v[k1], pw[k1]);
                 }
             }
         }
@@ -299,23 +319,25 @@ template <class T, int R1, int IN> struct Dp2Core {
     static DP_DEV void fwd_234(V* buf, const V* DP_RESTRICT tw2, const V* DP_RESTRICT tw3, int GA, int GB, V (&z)[16]) {
         const int tid = threadIdx.x;
         {
-            const int b = tid / CV, cc = tid % CV, base = b * VPB + cc;
+            const int b = tid / CV, cc = tid % CV;
+            V* pb = buf + G::phys(b * VPB + cc);
 #pragma unroll
-            for (int n = 0; n < 16; ++n) z[n] = buf[G::phys(base + n * CV)];
+            for (int n = 0; n < 16; ++n) z[n] = pb[n * PC];
             dp_dft<16, -1, T>::run(z);
             dp_twiddle<16, false, T>(z, dp_ldg(tw2 + cc));
 #pragma unroll
-            for (int k = 0; k < 16; ++k) buf[G::phys(base + k * CV)] = z[k];
+            for (int k = 0; k < 16; ++k) pb[k * PC] = z[k];
         }
         __syncthreads();
         {
-            const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV, base = b * VPB + k2 * CV + q;
+            const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV;
+            V* pb = buf + G::phys(b * VPB + k2 * CV + q);
 #pragma unroll
-            for (int n = 0; n < 16; ++n) z[n] = buf[G::phys(base + n * GV)];
+            for (int n = 0; n < 16; ++n) z[n] = pb[n * PG];
             dp_dft<16, -1, T>::run(z);
             dp_twiddle<16, false, T>(z, dp_ldg(tw3 + q));
 #pragma unroll
-            for (int k = 0; k < 16; ++k) buf[G::phys(base + k * GV)] = z[k];
+            for (int k = 0; k < 16; ++k) pb[k * PG] = z[k];
         }
         __syncthreads();
         load_groups(buf, GA, GB, z);
@@ -327,12 +349,14 @@ template <class T, int R1, int IN> struct Dp2Core {
         if constexpr (VL == 1) {
             (void)GB;
 #pragma unroll
-            for (int n = 0; n < 16; ++n) z[n] = buf[G::phys(GA * 16 + n)];
+            for (int n = 0; n < 16; ++n) z[n] = buf[GA * PG + n];
         } else {
             // canonical layout packs adjacent elements (2j, 2j+1); pass 4 wants (A[r], B[r]) lanes
+            const V* pa = buf + GA * PG;
+            const V* pb = buf + GB * PG;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const V a = buf[G::phys(GA * 8 + j)], b = buf[G::phys(GB * 8 + j)];
+                const V a = pa[j], b = pb[j];
                 z[2 * j] = V{f2(a.re.x, b.re.x), f2(a.im.x, b.im.x)};
                 z[2 * j + 1] = V{f2(a.re.y, b.re.y), f2(a.im.y, b.im.y)};
             }
@@ -342,12 +366,14 @@ template <class T, int R1, int IN> struct Dp2Core {
         if constexpr (VL == 1) {
             (void)GB;
 #pragma unroll
-            for (int n = 0; n < 16; ++n) buf[G::phys(GA * 16 + n)] = z[n];
+            for (int n = 0; n < 16; ++n) buf[GA * PG + n] = z[n];
         } else {
+            V* pa = buf + GA * PG;
+            V* pb = buf + GB * PG;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                buf[G::phys(GA * 8 + j)] = V{f2(z[2 * j].re.x, z[2 * j + 1].re.x), f2(z[2 * j].im.x, z[2 * j + 1].im.x)};
-                buf[G::phys(GB * 8 + j)] = V{f2(z[2 * j].re.y, z[2 * j + 1].re.y), f2(z[2 * j].im.y, z[2 * j + 1].im.y)};
+                pa[j] = V{f2(z[2 * j].re.x, z[2 * j + 1].re.x), f2(z[2 * j].im.x, z[2 * j + 1].im.x)};
+                pb[j] = V{f2(z[2 * j].re.y, z[2 * j + 1].re.y), f2(z[2 * j].im.y, z[2 * j + 1].im.y)};
             }
         }
     }
@@ -360,19 +386,21 @@ template <class T, int R1, int IN> struct Dp2Core {
         store_groups(buf, GA, GB, z);
         __syncthreads();
         {
-            const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV, base = b * VPB + k2 * CV + q;
+            const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV;
+            V* pb = buf + G::phys(b * VPB + k2 * CV + q);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) z[k] = buf[G::phys(base + k * GV)];
+            for (int k = 0; k < 16; ++k) z[k] = pb[k * PG];
             dp_twiddle<16, true, T>(z, dp_ldg(tw3 + q));
             dp_dft<16, +1, T>::run(z);
 #pragma unroll
-            for (int n = 0; n < 16; ++n) buf[G::phys(base + n * GV)] = z[n];
+            for (int n = 0; n < 16; ++n) pb[n * PG] = z[n];
         }
         __syncthreads();
         {
-            const int b = tid / CV, cc = tid % CV, base = b * VPB + cc;
+            const int b = tid / CV, cc = tid % CV;
+            const V* pb = buf + G::phys(b * VPB + cc);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) z[k] = buf[G::phys(base + k * CV)];
+            for (int k = 0; k < 16; ++k) z[k] = pb[k * PC];
             dp_twiddle<16, true, T>(z, dp_ldg(tw2 + cc));
             dp_dft<16, +1, T>::run(z);
         }
@@ -380,9 +408,10 @@ template <class T, int R1, int IN> struct Dp2Core {
     // pass-2' outputs -> smem (own positions, in place)
     static DP_DEV void store_pass2(V* buf, const V (&z)[16]) {
         const int tid = threadIdx.x;
-        const int b = tid / CV, cc = tid % CV, base = b * VPB + cc;
+        const int b = tid / CV, cc = tid % CV;
+        V* pb = buf + G::phys(b * VPB + cc);
 #pragma unroll
-        for (int n = 0; n < 16; ++n) buf[G::phys(base + n * CV)] = z[n];
+        for (int n = 0; n < 16; ++n) pb[n * PC] = z[n];
     }
     // pass-2' outputs of a non-final phase -> parked block results in scratch [p*NB + b][VPB]
     static DP_DEV void park_pass2(V* scr, int p, const V (&z)[16]) {
@@ -401,7 +430,7 @@ template <class T, int R1, int IN> struct Dp2Core {
             const int c = tid + (i0 + i) * NT;
             V u[R1];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) u[G::k1_of(LP, b)] = buf[G::phys(b * VPB + c)];
+            for (int b = 0; b < NB; ++b) u[G::k1_of(LP, b)] = buf[G::phys(c) + b * PB];
 #pragma unroll
             for (int p = 0; p < LP; ++p)
 #pragma unroll
@@ -501,9 +530,11 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
     static constexpr int N = G::N;
     static constexpr int RED_DOUBLES = (DP_MAX_TSLOTS + 1) * 32;
     static constexpr int BEST_ELEMS = DP_MAX_TSLOTS * 32;
-    static constexpr int SP_ELEMS = 32;
+    static constexpr int SP_ELEMS = 32 + 34 + 2;  // self-paired group values, X of the 17 self pairs, chi0 (as one cx slot)
+    static constexpr int CH_WORDS = (int)(sizeof(Dp2ChanDev<T>) / 4);  // channel descriptor, 32-bit words
     static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (DP_NLOW_MAX + SP_ELEMS) +
-                                         2 * (sizeof(double) * RED_DOUBLES + sizeof(DpBest<S>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS) + 64;
+                                         2 * (sizeof(double) * RED_DOUBLES + sizeof(DpBest<S>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS) +
+                                         2 * sizeof(int) * CH_WORDS + 64;
     // scratch per CTA (V units): X spill [16][NT] (multi-template) + per template the parked
     // block results of the non-final phases [(NPH-1)*NB][VPB]
     static constexpr long long SCR_X = (long long)16 * NT;
@@ -517,6 +548,8 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         double* red0;
         DpBest<S>* best0;
         int* slot0;
+        int* chs0;  // [2][CH_WORDS] this event's channel descriptor (table pointers are read from
+                    // shared memory, not through a dependent global load)
         DP_DEV double* red(int par) const { return red0 + par * RED_DOUBLES; }
         DP_DEV DpBest<S>* best(int par) const { return best0 + par * BEST_ELEMS; }
         DP_DEV int* slot_id(int par) const { return slot0 + par * DP_MAX_TSLOTS; }
@@ -529,14 +562,25 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         s.red0 = reinterpret_cast<double*>(s.sp + SP_ELEMS);
         s.best0 = reinterpret_cast<DpBest<S>*>(s.red0 + 2 * RED_DOUBLES);
         s.slot0 = reinterpret_cast<int*>(s.best0 + 2 * BEST_ELEMS);
+        s.chs0 = s.slot0 + 2 * DP_MAX_TSLOTS + ((2 * DP_MAX_TSLOTS) & 3 ? 4 - ((2 * DP_MAX_TSLOTS) & 3) : 0);
         return s;
     }
 
+    // next trace of this CTA -> L2, one bulk-prefetch instruction (TMA path, no LSU traffic) issued
+    // by one thread at the start of the event; falls back to per-line prefetches when the row is
+    // not 16-byte aligned
     static DP_DEV void prefetch_next(const Dp2Params<T>& prm, int row) {
         constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
         const int nrow = row + gridDim.x;
         if (nrow < prm.n_rows) {
             const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * ESZ;
+#ifndef DP_HOST_EMU
+            if ((reinterpret_cast<unsigned long long>(nx) & 15ull) == 0) {
+                if (threadIdx.x == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)((size_t)N * ESZ)) : "memory");
+                return;
+            }
+#endif
             constexpr int nlines = (int)((size_t)N * ESZ / 128);
             for (int l = threadIdx.x; l < nlines; l += NT) dp_prefetch_l2(nx + (size_t)l * 128);
         }
@@ -566,17 +610,24 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
 #undef DP2_XP
             f2 acc = f2(0.0f);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) acc = dp_fma(dp_ldg(wj + r * NT + tid), cnorm2(z[r]), acc);
+            for (int h = 0; h < 16; h += DP2_TBL_BATCH) {
+                dp2_sched_fence();
+                f2 w[DP2_TBL_BATCH];
+#pragma unroll
+                for (int j = 0; j < DP2_TBL_BATCH; ++j) w[j] = dp_ldg(wj + (h + j) * NT + tid);
+#pragma unroll
+                for (int j = 0; j < DP2_TBL_BATCH; ++j) acc = dp_fma(w[j], cnorm2(z[h + j]), acc);
+            }
             chi = acc.x + acc.y;
         } else {
             // exchange the upper halves with the partner thread (tid ^ 1) through the (now idle)
             // group rows of the shared buffer: own elements 8..15 out, partner's 8..15 in
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sm.buf[G::phys(Gown * 16 + 8 + j)] = z[8 + j];
+            for (int j = 0; j < 8; ++j) sm.buf[Gown * 17 + 8 + j] = z[8 + j];
             __syncwarp();
             int Gp = __shfl_xor_sync(0xffffffffu, Gown, 1);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) zm[j] = sm.buf[G::phys(Gp * 16 + 15 - j)];  // partner element 15 - j
+            for (int j = 0; j < 8; ++j) zm[j] = sm.buf[Gp * 17 + 15 - j];  // partner element 15 - j
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 cx<S> Xk, Xm;
@@ -598,7 +649,14 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
             (void)Gown;
             (void)sm;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) z[r] = cmul(dp_ldg(phi + r * NT + tid), z[r]);
+            for (int h = 0; h < 16; h += DP2_TBL_BATCH) {
+                dp2_sched_fence();
+                V ph[DP2_TBL_BATCH];
+#pragma unroll
+                for (int j = 0; j < DP2_TBL_BATCH; ++j) ph[j] = dp_ldg(phi + (h + j) * NT + tid);
+#pragma unroll
+                for (int j = 0; j < DP2_TBL_BATCH; ++j) z[h + j] = cmul(ph[j], z[h + j]);
+            }
 #define DP2_FP(r)                                                                          \
     {                                                                                      \
         cx<S> Ck, Cm;                                                                      \
@@ -618,39 +676,47 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
                 cx<S> Ck, Cm;
                 dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
                 z[r] = Ck;
-                sm.buf[G::phys(Gp * 16 + 15 - r)] = Cm;  // partner's element 15 - r
+                sm.buf[Gp * 17 + 15 - r] = Cm;  // partner's element 15 - r
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) z[8 + j] = sm.buf[G::phys(Gown * 16 + 8 + j)];
+            for (int j = 0; j < 8; ++j) z[8 + j] = sm.buf[Gown * 17 + 8 + j];
         }
     }
 
-    static DP_DEV void run(const Dp2Params<T>& prm, unsigned char* smem_raw);
+    // MULTI: some channel has more than one template (X goes through the thread-private scratch
+    // column so that nothing is live across the template loop)
+    template <bool MULTI> static DP_DEV void run(const Dp2Params<T>& prm, unsigned char* smem_raw);
 };
 
 template <class T, int R1, int IN>
+template <bool MULTI>
 DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* smem_raw) {
     const Smem sm = carve(smem_raw);
     const int tid = threadIdx.x;
     constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
     V* scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;  // [16][NT] X of the current phase (multi-template)
     V* scr_park = scr_x + SCR_X;                                           // [n_templ][(NPH-1)*NB][VPB] parked block results
-    const DpSelfLane<S> sp = dp_self_lane<S, 1>(tid & 31);
     // special threads: the self-paired groups (0,0,0) and (0,0,8) of block 0 (phase 0)
     constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
     int par = 0;
-    double chi0_keep = 0.0;
+    int evpar = 0;
+    cx<S>* const sx = sm.sp + 32;                                        // [17][2] X of the self pairs
+    double* const chi0_keep = reinterpret_cast<double*>(sm.sp + 32 + 34);  // chi0 of the current event (thread 0)
 
     for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
         const int chan = row % prm.n_chan;
         const int ev = row / prm.n_chan;
-        const Dp2ChanDev<T>& ch = prm.chans[chan];
+        // channel descriptor -> shared memory (double buffered: thread 0 may still be writing the
+        // previous event's outputs); visible after the first barrier of the event
+        int* chs = sm.chs0 + evpar * CH_WORDS;
+        evpar ^= 1;
+        if (tid < CH_WORDS) chs[tid] = reinterpret_cast<const int*>(prm.chans + chan)[tid];
+        const Dp2ChanDev<T>& ch = *reinterpret_cast<const Dp2ChanDev<T>*>(chs);
         const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
         const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
-        const bool multi = ch.n_templ > 1;
+        prefetch_next(prm, row);
         S chi = (S)0;
-        cx<S> sXk = cx<S>{(S)0, (S)0}, sXm = sXk;  // lanes 0..16 of warp 0: 2*X of their self pair
 
 #pragma unroll 1
         for (int p = 0; p < NPH; ++p) {
@@ -681,7 +747,11 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 }
                 __syncwarp();
                 if (tid < 17) {
+                    const DpSelfLane<S> sp = dp_self_lane<S, 1>(tid);
+                    cx<S> sXk, sXm;
                     dp_untangle(sm.sp[sp.ek], sm.sp[sp.em], sp.w, sXk, sXm);
+                    sx[2 * tid] = sXk;
+                    sx[2 * tid + 1] = sXm;
                     chi = dp_fma(dp_ldg(ch.wj_self + 2 * tid), cnorm2(sXk), chi);
                     chi = dp_fma(dp_ldg(ch.wj_self + 2 * tid + 1), cnorm2(sXm), chi);
                     if (tid == 0) sm.stash[0] = sXk;
@@ -701,8 +771,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     if (kA < prm.nlow) sm.stash[kA] = z[0];
                 }
             }
-            if (p == NPH - 1) prefetch_next(prm, row);
-            if (multi) {
+            if constexpr (MULTI) {
                 // X must survive the in-place inverse of the previous template (thread-private column)
                 V* dst = scr_x + tid;
                 if constexpr (VL == 2) {
@@ -718,10 +787,12 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             }
 
             // ---------------- per template: filter, inverse passes 4' 3' 2' ---------------------
-            for (int it = 0; it < ch.n_templ; ++it) {
+            const int n_templ = MULTI ? ch.n_templ : 1;
+#pragma unroll 1
+            for (int it = 0; it < n_templ; ++it) {
                 const Dp2TemplDev<T>& tp = ch.templ[it];
                 V* park = scr_park + (long long)it * SCR_PARK;
-                if (it > 0) {
+                if constexpr (MULTI) {
                     const V* src = scr_x + tid;
                     if constexpr (VL == 2) {
 #pragma unroll
@@ -735,8 +806,9 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     }
                 }
                 if (p == 0 && tid < 17) {
-                    const cx<S> Fk = cmul(dp_ldg(tp.phi_self + 2 * tid), sXk);
-                    const cx<S> Fm = cmul(dp_ldg(tp.phi_self + 2 * tid + 1), sXm);
+                    const DpSelfLane<S> sp = dp_self_lane<S, 1>(tid);
+                    const cx<S> Fk = cmul(dp_ldg(tp.phi_self + 2 * tid), sx[2 * tid]);
+                    const cx<S> Fm = cmul(dp_ldg(tp.phi_self + 2 * tid + 1), sx[2 * tid + 1]);
                     cx<S> Ck, Cm;
                     dp_retangle(Fk, Fm, sp.w, Ck, Cm);
                     sm.sp[sp.ek] = Ck;
@@ -852,10 +924,10 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     if (it == 0) {
                         double c0 = 0.0;
                         for (int w = 0; w < NW; ++w) c0 += red[DP_MAX_TSLOTS * 32 + w];
-                        chi0_keep = c0;
+                        *chi0_keep = c0;
                         o[0] = c0;
                     }
-                    const double chi0 = chi0_keep;
+                    const double chi0 = *chi0_keep;
                     for (int q = 0; q < nts; ++q) {
                         double low = 0.0;
                         for (int w = 0; w < NW; ++w) low += red[q * 32 + w];
@@ -877,9 +949,9 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
 }
 
 #ifndef DP_HOST_EMU
-template <class T, int R1, int IN>
-__global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, 1) dp_of2_kernel(const Dp2Params<T> prm) {
+template <class T, int R1, int IN, bool MULTI>
+__global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, Dp2Geom<T, R1>::NT <= 256 ? 2 : 1) dp_of2_kernel(const Dp2Params<T> prm) {
     extern __shared__ __align__(16) unsigned char dp_smem_raw[];
-    Dp2OfKernel<T, R1, IN>::run(prm, dp_smem_raw);
+    Dp2OfKernel<T, R1, IN>::template run<MULTI>(prm, dp_smem_raw);
 }
 #endif

@@ -87,7 +87,10 @@ static void run_all(double fs, double fcut, double scale, const std::vector<dppl
         std::vector<unsigned char> smem(K::SMEM_BYTES + 64);
         unsigned char* sp = smem.data();
         sp += (64 - (reinterpret_cast<uintptr_t>(sp) & 63)) & 63;
-        run_cta(G::NT, b, grid, [&] { K::run(prm, sp); });
+        if (max_templ > 1)
+            run_cta(G::NT, b, grid, [&] { K::template run<true>(prm, sp); });
+        else
+            run_cta(G::NT, b, grid, [&] { K::template run<false>(prm, sp); });
     }
 }
 
