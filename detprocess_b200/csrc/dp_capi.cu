@@ -16,6 +16,7 @@
 #include "dp_of_launch.hpp"
 #include "dp_plan.hpp"
 #include "dp_plan2.hpp"
+#include "dp_psd2_kernel.cuh"
 #include "dp_psd_kernel.cuh"
 #include "dp_reduce_plan.hpp"
 
@@ -770,6 +771,8 @@ int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* p, float* ms) {
 
 // ========================================================================== PSD plan
 struct dp_psd_plan {
+    int v2_r1 = 0;  // != 0: v2 FFT core (dp_psd2_kernel.cuh)
+    const void *tw3 = nullptr, *groups = nullptr;
     int N = 0;
     double fs = 0;
     int precision = DP_PREC_F64;
@@ -844,6 +847,75 @@ template <class T> int psd_finalize(dp_psd_plan* p) {
     return DP_OK;
 }
 
+template <class T, int R1> int psd2_tables(dp_psd_plan* p) {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    std::vector<dpplan::Channel> none;
+    dpplan2::Tables2<T> dt;
+    try {
+        dt = dpplan2::build_tables2<T, R1>(p->fs, none, 0.0, 1.0);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_STATE, e.what());
+    }
+    int rc;
+    const cx<T>* d;
+    if ((rc = upload(p->owned, dt.tw1, &d))) return rc;
+    p->tw1 = d;
+    if ((rc = upload(p->owned, dt.tw2, &d))) return rc;
+    p->tw2 = d;
+    if ((rc = upload(p->owned, dt.tw3, &d))) return rc;
+    p->tw3 = d;
+    const cx<S>* ds;
+    if ((rc = upload(p->owned, dt.twn, &ds))) return rc;
+    p->twn = ds;
+    const int2* dg;
+    if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
+    p->groups = dg;
+    // natural bin k -> slot in one CTA's partial array
+    std::vector<int> loc(G::M + 1, -1);
+    const int nspecial = G::VL == 2 ? 1 : 2;
+    for (int ph = 0; ph < G::NPH; ++ph)
+        for (int t = 0; t < G::NT; ++t) {
+            if (ph == 0 && t < nspecial) continue;
+            for (int e = 0; e < 16; ++e) {
+                int b[2];
+                dpplan2::entry_bins<G>(ph, t, e, b);
+                for (int l = 0; l < G::VL; ++l) loc[b[l]] = ((ph * 16 + e) * G::NT + t) * G::VL + l;
+            }
+        }
+    for (int l = 0; l < 17; ++l) {
+        int b[2];
+        bool dup[2];
+        dpplan2::self_bins<G>(l, b, dup);
+        for (int j = 0; j < 2; ++j)
+            if (!dup[j]) loc[b[j]] = G::NPH * 16 * G::NT * G::VL + 2 * l + j;
+    }
+    for (int k = 0; k <= G::M; ++k)
+        if (loc[k] < 0) return fail(DP_ERR_STATE, "internal: PSD bin map incomplete");
+    if ((rc = upload(p->owned, loc, &p->loc))) return rc;
+    return DP_OK;
+}
+
+template <class T> int psd2_finalize(dp_psd_plan* p) {
+    int rc;
+    switch (p->v2_r1) {
+        case 2: rc = psd2_tables<T, 2>(p); break;
+        case 4: rc = psd2_tables<T, 4>(p); break;
+        default: rc = psd2_tables<T, 8>(p); break;
+    }
+    if (rc) return rc;
+    const int src = sizeof(typename Dp2Traits<T>::S) == 8
+                        ? dp_psd2_setup_p0_0(p->v2_r1, p->device, &p->smem, &p->grid_max, &p->partial_per_cta)
+                        : dp_psd2_setup_p1_0(p->v2_r1, p->device, &p->smem, &p->grid_max, &p->partial_per_cta);
+    if (src != 0) return fail(DP_ERR_CUDA, "PSD kernel setup failed");
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->partial), sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
+    p->owned.push_back(p->partial);
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->count), sizeof(unsigned long long) * (size_t)(p->grid_max + 1)));
+    p->owned.push_back(p->count);
+    p->count_out = p->count + p->grid_max;
+    return DP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -853,17 +925,25 @@ int dp_psd_plan_create(dp_psd_plan** plan, int nb_samples, double sample_rate, i
     if (!(sample_rate > 0)) return fail(DP_ERR_INVALID, "sample_rate must be > 0");
     if (precision != DP_PREC_F64 && precision != DP_PREC_F32) return fail(DP_ERR_INVALID, "unknown precision");
     auto p = std::make_unique<dp_psd_plan>();
-    try {
-        p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
-    } catch (const std::exception& e) {
-        return fail(DP_ERR_UNSUPPORTED, e.what());
+    const char* gen = std::getenv("DP_OF_KERNEL");
+    p->v2_r1 = (gen && std::string(gen) == "v1") ? 0 : dpplan2::r1_of(nb_samples);
+    if (!p->v2_r1) {
+        try {
+            p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
+        } catch (const std::exception& e) {
+            return fail(DP_ERR_UNSUPPORTED, e.what());
+        }
     }
     p->N = nb_samples;
     p->fs = sample_rate;
     p->precision = precision;
     p->device = device;
     DP_CUDA(cudaSetDevice(device));
-    int rc = precision == DP_PREC_F32 ? psd_finalize<float>(p.get()) : psd_finalize<double>(p.get());
+    int rc;
+    if (p->v2_r1)
+        rc = precision == DP_PREC_F32 ? psd2_finalize<f2>(p.get()) : psd2_finalize<double>(p.get());
+    else
+        rc = precision == DP_PREC_F32 ? psd_finalize<float>(p.get()) : psd_finalize<double>(p.get());
     if (rc) {
         for (void* d : p->owned) cudaFree(d);
         return rc;
@@ -921,7 +1001,34 @@ int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long
     };
     DP_CUDA(cudaEventRecord(p->ev0, st));
     int rc;
-    if (p->precision == DP_PREC_F32) {
+    if (p->v2_r1) {
+        auto fill2 = [&](auto& prm) {
+            std::memset(&prm, 0, sizeof(prm));
+            prm.traces = traces_dev;
+            prm.row_stride = row_stride;
+            prm.n_rows = (int)n_traces;
+            prm.mask = mask_dev;
+            prm.groups = reinterpret_cast<const int2*>(p->groups);
+            prm.partial = p->partial;
+            prm.partial_per_cta = p->partial_per_cta;
+            prm.count = p->count;
+            prm.scale = p->scale;
+            prm.subtract_first = p->precision == DP_PREC_F32 ? 1 : 0;
+        };
+        if (p->precision == DP_PREC_F32) {
+            DpPsd2Params<f2> prm;
+            fill2(prm);
+            prm.tw1 = (const cx<f2>*)p->tw1; prm.tw2 = (const cx<f2>*)p->tw2; prm.tw3 = (const cx<f2>*)p->tw3;
+            prm.twn = (const cx<float>*)p->twn;
+            rc = dp_psd2_launch_p1_0(p->v2_r1, &prm, grid, p->smem, st);
+        } else {
+            DpPsd2Params<double> prm;
+            fill2(prm);
+            prm.tw1 = (const cx<double>*)p->tw1; prm.tw2 = (const cx<double>*)p->tw2; prm.tw3 = (const cx<double>*)p->tw3;
+            prm.twn = (const cx<double>*)p->twn;
+            rc = dp_psd2_launch_p0_0(p->v2_r1, &prm, grid, p->smem, st);
+        }
+    } else if (p->precision == DP_PREC_F32) {
         DpPsdParams<float> prm;
         fill(prm);
         prm.tw1 = (const cx<float>*)p->tw1; prm.tw2 = (const cx<float>*)p->tw2;

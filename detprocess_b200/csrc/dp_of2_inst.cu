@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "dp_of2_kernel.cuh"
+#include "dp_psd2_kernel.cuh"
 #include "dp_of2_launch.hpp"
 
 #if DP_INST_PREC == 0
@@ -68,3 +69,49 @@ int DP_CAT(dp_of2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, int multi, const v
         default: return -1;
     }
 }
+
+// ------------------------------------------------------------------------ PSD kernels
+// built for float64 traces only (IN = 0)
+#if DP_INST_IN == 0
+namespace {
+template <int R1> int psd_setup_one(int device, size_t* smem, int* grid_max, long long* partial_per_cta) {
+    using K = DpPsd2Kernel<InstT, R1, 0>;
+    auto kern = dp_psd2_kernel<InstT, R1, 0>;
+    *smem = K::SMEM_BYTES;
+    *partial_per_cta = K::PARTIAL;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::NT, K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) return -2;
+    *grid_max = sms * occ;
+    return 0;
+}
+template <int R1> int psd_launch_one(const DpPsd2Params<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
+    dp_psd2_kernel<InstT, R1, 0><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+    return (int)cudaGetLastError();
+}
+}  // namespace
+
+int DP_CAT(dp_psd2_setup_p, DP_INST_PREC, 0)(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta) {
+    switch (R1) {
+        case 2: return psd_setup_one<2>(device, smem, grid_max, partial_per_cta);
+        case 4: return psd_setup_one<4>(device, smem, grid_max, partial_per_cta);
+        case 8: return psd_setup_one<8>(device, smem, grid_max, partial_per_cta);
+        default: return -1;
+    }
+}
+int DP_CAT(dp_psd2_launch_p, DP_INST_PREC, 0)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
+    const DpPsd2Params<InstT>& prm = *reinterpret_cast<const DpPsd2Params<InstT>*>(prm_v);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
+    switch (R1) {
+        case 2: return psd_launch_one<2>(prm, grid, smem, st);
+        case 4: return psd_launch_one<4>(prm, grid, smem, st);
+        case 8: return psd_launch_one<8>(prm, grid, smem, st);
+        default: return -1;
+    }
+}
+#endif

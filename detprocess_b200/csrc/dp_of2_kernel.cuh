@@ -590,14 +590,15 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
     // VL == 2: z[r] lanes = X at (bin of A[r], bin of B[r]).
     // VL == 1: z[0..7] = X at own[r]; zm[0..7] = X at M - bin(own[r]) (the partner's element 15 - r).
     // Returns the thread's chi0 partial sum (scalar type S).
-    static DP_DEV S untangle_all(const Smem& sm, V (&z)[16], V (&zm)[VL == 1 ? 8 : 1], const T* DP_RESTRICT wj, cx<S> wn, int Gown,
+    template <bool WITH_CHI = true>
+    static DP_DEV S untangle_all(V* buf, V (&z)[16], V (&zm)[VL == 1 ? 8 : 1], const T* DP_RESTRICT wj, cx<S> wn, int Gown,
                                  bool special) {
         const int tid = threadIdx.x;
         S chi = (S)0;
         if constexpr (VL == 2) {
             (void)zm;
             (void)Gown;
-            (void)sm;
+            (void)buf;
 #define DP2_XP(r)                                                                         \
     {                                                                                     \
         cx<S> Xk, Xm;                                                                     \
@@ -609,6 +610,7 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
             DP2_XP(8) DP2_XP(9) DP2_XP(10) DP2_XP(11) DP2_XP(12) DP2_XP(13) DP2_XP(14) DP2_XP(15)
 #undef DP2_XP
             f2 acc = f2(0.0f);
+            if constexpr (WITH_CHI) {
 #pragma unroll
             for (int h = 0; h < 16; h += DP2_TBL_BATCH) {
                 dp2_sched_fence();
@@ -618,22 +620,25 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
 #pragma unroll
                 for (int j = 0; j < DP2_TBL_BATCH; ++j) acc = dp_fma(w[j], cnorm2(z[h + j]), acc);
             }
+            }
             chi = acc.x + acc.y;
         } else {
             // exchange the upper halves with the partner thread (tid ^ 1) through the (now idle)
             // group rows of the shared buffer: own elements 8..15 out, partner's 8..15 in
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sm.buf[Gown * 17 + 8 + j] = z[8 + j];
+            for (int j = 0; j < 8; ++j) buf[Gown * 17 + 8 + j] = z[8 + j];
             __syncwarp();
             int Gp = __shfl_xor_sync(0xffffffffu, Gown, 1);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) zm[j] = sm.buf[Gp * 17 + 15 - j];  // partner element 15 - j
+            for (int j = 0; j < 8; ++j) zm[j] = buf[Gp * 17 + 15 - j];  // partner element 15 - j
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 cx<S> Xk, Xm;
                 dp_untangle(z[r], zm[r], cmul(wn, dp_w64_rt<S>(2 * r)), Xk, Xm);
-                chi = dp_fma(dp_ldg(wj + (2 * r) * NT + tid), cnorm2(Xk), chi);
-                chi = dp_fma(dp_ldg(wj + (2 * r + 1) * NT + tid), cnorm2(Xm), chi);
+                if constexpr (WITH_CHI) {
+                    chi = dp_fma(dp_ldg(wj + (2 * r) * NT + tid), cnorm2(Xk), chi);
+                    chi = dp_fma(dp_ldg(wj + (2 * r + 1) * NT + tid), cnorm2(Xm), chi);
+                }
                 z[r] = Xk;
                 zm[r] = Xm;
             }
@@ -759,7 +764,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 }
                 __syncwarp();
             }
-            chi += untangle_all(sm, z, zm, ch.wj + (long long)p * 16 * NT, wn, gg.x, special);
+            chi += untangle_all(sm.buf, z, zm, ch.wj + (long long)p * 16 * NT, wn, gg.x, special);
             if (!special) {
                 // low-frequency bins for lowchi2: element 0 of each group (k4 = 0)
                 const int kA = G::bin_of(p, gg.x, 0);

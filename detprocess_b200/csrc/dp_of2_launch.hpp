@@ -15,3 +15,9 @@ static const dp_of2_setup_fn dp_of2_setup_table[2][3] = {{dp_of2_setup_p0_0, dp_
                                                          {dp_of2_setup_p1_0, dp_of2_setup_p1_1, dp_of2_setup_p1_2}};
 static const dp_of2_launch_fn dp_of2_launch_table[2][3] = {{dp_of2_launch_p0_0, dp_of2_launch_p0_1, dp_of2_launch_p0_2},
                                                            {dp_of2_launch_p1_0, dp_of2_launch_p1_1, dp_of2_launch_p1_2}};
+
+// PSD accumulation on the v2 core (float64 traces)
+int dp_psd2_setup_p0_0(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta);
+int dp_psd2_setup_p1_0(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta);
+int dp_psd2_launch_p0_0(int R1, const void* prm, int grid, size_t smem, void* stream);
+int dp_psd2_launch_p1_0(int R1, const void* prm, int grid, size_t smem, void* stream);

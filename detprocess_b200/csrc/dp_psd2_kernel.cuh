@@ -1,0 +1,131 @@
+// Noise PSD accumulation on the v2 FFT core (nb_samples 16384 / 32768 / 65536): per trace the
+// forward half of the fused OF kernel (dp_of2_kernel.cuh) and |X[k]|^2 added into a per-CTA
+// partial-sum array kept in thread order (coalesced read-modify-write of thread-private
+// slots, no atomics, L2 resident).  dp_psd_reduce_kernel (dp_of_inst.cu) folds the CTAs and
+// maps thread order -> natural k; the per-GPU sums are all-reduced over NCCL by the host layer.
+//
+// Replaces qp.calc_psd(traces[cut], fs, folded_over=False) as called from Noise.calc_psd
+// (reference detprocess/core/noise.py:344).
+#pragma once
+#include "dp_of2_kernel.cuh"
+
+template <class T> struct DpPsd2Params {
+    using S = typename Dp2Traits<T>::S;
+    const void* traces;
+    long long row_stride;
+    int n_rows;
+    const unsigned char* mask;  // [n_rows] 1 = use the trace (nullptr: all)
+    const cx<T>* tw1;
+    const cx<T>* tw2;
+    const cx<T>* tw3;
+    const cx<S>* twn;
+    const int2* groups;
+    double* partial;            // [grid][partial_per_cta]: [NPH][16][NT][VL] thread order, then [17][2] self lanes
+    long long partial_per_cta;
+    unsigned long long* count;  // [grid] accepted traces per CTA
+    double scale;
+    int subtract_first;
+};
+
+template <class T, int R1, int IN> struct DpPsd2Kernel {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    using V = cx<T>;
+    using Core = Dp2Core<T, R1, IN>;
+    using OF = Dp2OfKernel<T, R1, IN>;
+    static constexpr int NT = G::NT, VL = G::VL, NPH = G::NPH, N = G::N;
+    static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * 32 + 64;
+    static constexpr long long PARTIAL = (long long)NPH * 16 * NT * VL + 17 * 2;
+
+    static DP_DEV void run(const DpPsd2Params<T>& prm, unsigned char* smem_raw) {
+        V* buf = reinterpret_cast<V*>(smem_raw);
+        cx<S>* sp = reinterpret_cast<cx<S>*>(buf + G::SMEM_V);
+        const int tid = threadIdx.x;
+        constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
+        constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
+        double* part = prm.partial + (long long)blockIdx.x * prm.partial_per_cta;
+        double* part_self = part + (long long)NPH * 16 * NT * VL;
+        const double inv_s2 = 1.0 / (4.0 * prm.scale * prm.scale);  // kernel values are 2*scale*X
+        unsigned long long n_acc = 0;
+
+        for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
+            if (prm.mask != nullptr && prm.mask[row] == 0) continue;  // CTA-uniform
+            ++n_acc;
+            const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
+            const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+#pragma unroll 1
+            for (int p = 0; p < NPH; ++p) {
+                V z[16];
+                V zm[VL == 1 ? 8 : 1];
+                const int2 gg = prm.groups[p * NT + tid];
+                const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
+                const bool special = (p == 0) && (tid < NSPECIAL);
+                Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
+                __syncthreads();
+                Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                if (p == 0 && tid < 32) {
+                    if constexpr (VL == 2) {
+                        if (tid == 0) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                sp[r] = dp2_lane0(z[r]);
+                                sp[16 + r] = dp2_lane1(z[r]);
+                            }
+                        }
+                    } else {
+                        if (tid < 2) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) sp[16 * tid + r] = z[r];
+                        }
+                    }
+                    __syncwarp();
+                    if (tid < 17) {
+                        const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
+                        cx<S> Xk, Xm;
+                        dp_untangle(sp[sl.ek], sp[sl.em], sl.w, Xk, Xm);
+                        double pk = (double)cnorm2(Xk) * inv_s2, pm = (double)cnorm2(Xm) * inv_s2;
+                        if (tid == 0 && prm.subtract_first) {
+                            // DC bin: put back the subtracted first sample, X[0] += N*x0 (in double)
+                            const double dc = (double)Xk.re / (2.0 * prm.scale) + (double)N * x0;
+                            pk = dc * dc;
+                        }
+                        part_self[2 * tid] += pk;
+                        part_self[2 * tid + 1] += pm;
+                    }
+                    __syncwarp();
+                }
+                OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+                if (!special) {
+                    if constexpr (VL == 2) {
+                        double2* dst = reinterpret_cast<double2*>(part) + (long long)p * 16 * NT + tid;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const f2 pw = cnorm2(z[r]);
+                            double2 a = dst[r * NT];
+                            a.x += (double)pw.x * inv_s2;
+                            a.y += (double)pw.y * inv_s2;
+                            dst[r * NT] = a;
+                        }
+                    } else {
+                        double* dst = part + (long long)p * 16 * NT + tid;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            dst[(2 * r) * NT] += cnorm2(z[r]) * inv_s2;
+                            dst[(2 * r + 1) * NT] += cnorm2(zm[r]) * inv_s2;
+                        }
+                    }
+                }
+                __syncthreads();  // group rows of buf are rewritten by the next pass 1
+            }
+        }
+        if (tid == 0) prm.count[blockIdx.x] += n_acc;
+    }
+};
+
+#ifndef DP_HOST_EMU
+template <class T, int R1, int IN>
+__global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, Dp2Geom<T, R1>::NT <= 256 ? 2 : 1) dp_psd2_kernel(const DpPsd2Params<T> prm) {
+    extern __shared__ __align__(16) unsigned char dp_smem_raw[];
+    DpPsd2Kernel<T, R1, IN>::run(prm, dp_smem_raw);
+}
+#endif

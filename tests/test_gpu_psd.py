@@ -18,8 +18,9 @@ def _traces(n_tr, n, seed, offset=0.0):
     return w + line + offset
 
 
-@pytest.mark.parametrize('n,prec,tol', [(32768, 'f64', 1e-11), (16384, 'f64', 1e-11), (4096, 'f64', 1e-11),
-                                        (65536, 'f32', 2e-5), (32768, 'f32', 2e-5)])
+@pytest.mark.parametrize('n,prec,tol', [(65536, 'f64', 1e-11), (32768, 'f64', 1e-11), (16384, 'f64', 1e-11),
+                                        (4096, 'f64', 1e-11), (65536, 'f32', 2e-5), (32768, 'f32', 2e-5),
+                                        (16384, 'f32', 2e-5), (8192, 'f32', 2e-5)])
 def test_psd_matches_oracle(n, prec, tol):
     from detprocess_b200.core.noise import NoisePSD
     fs = 1.25e6

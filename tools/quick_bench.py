@@ -56,6 +56,22 @@ def time_reduce(N, B):
     print(f'reduce N={N} B={B}: {m:.3f} ms {B/(m*1e-3)/1e6:.3f} Mev/s window-bytes {byt/(m*1e-3)/1e9:.0f} GB/s', flush=True)
 
 
+def time_psd(N, prec, B):
+    from detprocess_b200.core.plans import PSDPlan
+    plan = PSDPlan(N, 1.25e6, precision=prec)
+    plan.set_scale(1.0)
+    x = torch.randn((B, N), dtype=torch.float64, device='cuda')
+    for _ in range(2):
+        plan.accumulate(x)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        plan.accumulate(x)
+        ms.append(plan.last_kernel_ms())
+    m = float(np.median(ms))
+    print(f'PSD N={N} {prec} B={B}: {m:.3f} ms {B/(m*1e-3)/1e6:.3f} Mtraces/s {B*N*8/(m*1e-3)/1e9:.0f} GB/s ({B*N*8/(m*1e-3)/1e9/6551*100:.1f}% HBM)', flush=True)
+
+
 if __name__ == '__main__':
     import os
     print(torch.cuda.get_device_name(0), 'DP_OF_KERNEL=' + os.environ.get('DP_OF_KERNEL', 'v2'))
@@ -73,3 +89,6 @@ if __name__ == '__main__':
             time_of(65536, 'f64', 4096)
         time_of(8192, 'f64', 8192)
         time_reduce(32768, 8192)
+        time_psd(65536, 'f64', 4096)
+        time_psd(65536, 'f32', 4096)
+        time_psd(32768, 'f64', 8192)
