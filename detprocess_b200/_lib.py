@@ -71,6 +71,12 @@ SIGNATURES = {
     'dp_psd_accumulate': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _vp]),
     'dp_psd_get_sums': (_i, [_vp, _vp, _vp, _vp]),
     'dp_psd_plan_last_kernel_ms': (_i, [_vp, _fp]),
+    'dp_trigger_plan_create': (_i, [C.POINTER(_vp), _vp, _i, _d, _d, _i, _ll, _i]),
+    'dp_trigger_plan_destroy': (None, [_vp]),
+    'dp_trigger_plan_set_scale': (_i, [_vp, _d]),
+    'dp_trigger_plan_geometry': (_i, [_vp, _ip, _ip]),
+    'dp_trigger_run': (_i, [_vp, _vp, _ll, _d, _ll, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'dp_trigger_plan_last_kernel_ms': (_i, [_vp, _fp, _fp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

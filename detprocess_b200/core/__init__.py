@@ -2,3 +2,6 @@ from .plans import OFPlan, ReducePlan
 from .ofbase import OFBaseBatch
 from .algorithms import FeatureExtractors
 from .filterdata import FilterData
+from .plans import PSDPlan
+from .noise import NoisePSD
+from .oftrigger import OptimumFilterTrigger, TriggerPlan

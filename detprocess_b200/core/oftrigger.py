@@ -1,0 +1,192 @@
+"""
+Continuous-stream optimal-filter trigger on the GPU -- the hot path of
+``OptimumFilterTrigger`` (reference detprocess/core/oftrigger.py), BASELINE.json config C4.
+
+Same construction / call sequence as the reference for one trigger channel and one amplitude:
+
+    oftrigger = OptimumFilterTrigger(trigger_channel, fs, template, noisecsd, pretrigger_samples)
+    oftrigger.update_trace(trace)                      # CUDA float64 tensor [L] (or [1, L])
+    oftrigger.find_triggers_once(thresh=5, pileup_window_msec=1)
+    data = oftrigger.get_trigger_data()                # {trigger_name: {trigger_index: [...], ...}}
+
+The FIR filter (``oaconvolve(raw, phi_td, 'same')``, oftrigger.py:659-666), delta-chi2, edge
+padding, threshold and pile-up grouping all run in ``dp_trigger_run``; the filtered trace is
+never written to memory, so the threshold is needed at filter time: ``update_trace`` only
+registers the device buffer and ``find_triggers_once`` launches the fused kernels.
+
+phi is conj(s)/J under the OF conventions of ``oracle/of1x1.py`` (QETpy is not in the reference
+tree; parity unpinned).  Defaults ``w = norm``, ``iw = 1/norm`` make
+``filtered`` the OF amplitude and ``delta_chi2 = amp^2/sigma_amp^2``; pass ``iw`` / ``w`` to use
+the values of a QETpy ``OFBase`` instead.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .._lib import lib, check
+from .plans import _PREC, _stream_ptr
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def chi2_threshold_from_sigma(thresh, m_amplitudes=1):
+    """sigma -> chi2 threshold exactly as oftrigger.py:961-965 (host scalar)."""
+    from scipy import special, stats
+    if thresh < 25:
+        survival_fraction = stats.norm.sf(thresh) * 2
+        return float(special.gammainccinv(m_amplitudes / 2, survival_fraction) * 2)
+    return float(thresh) ** 2
+
+
+class TriggerPlan:
+    """``dp_trigger_plan``: FIR taps + weights -> fused filter / threshold / grouping launches."""
+
+    def __init__(self, phi_td, iw, w, precision='f64', max_samples=12_500_000, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.DetprocessB200Error('no CUDA device: detprocess_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        phi_td = np.ascontiguousarray(phi_td, dtype=np.float64)
+        self.nb_filter = phi_td.shape[0]
+        self.max_samples = int(max_samples)
+        self._h = C.c_void_p()
+        check(lib.dp_trigger_plan_create(C.byref(self._h), phi_td.ctypes.data, self.nb_filter, float(iw), float(w),
+                                         _PREC[precision], self.max_samples, self.device.index or 0))
+        f, h = C.c_int(), C.c_int()
+        check(lib.dp_trigger_plan_geometry(self._h, C.byref(f), C.byref(h)))
+        self.fft_size, self.hop = f.value, h.value
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            lib.dp_trigger_plan_destroy(h)
+            self._h = C.c_void_p()
+
+    def set_scale(self, typical_rms):
+        check(lib.dp_trigger_plan_set_scale(self._h, float(typical_rms)))
+
+    def run(self, trace, chi2_threshold, pileup_window_samples=0, index_shift=0, padding=True, max_triggers=65536):
+        """trace: CUDA float64 [L] (L even).  Returns (index int64 [n], amplitude [n], delta_chi2 [n]) CUDA tensors."""
+        torch = _torch()
+        if not trace.is_cuda or trace.dtype != torch.float64 or trace.ndim != 1:
+            raise ValueError('run() takes a 1-D float64 CUDA tensor')
+        trace = trace.contiguous()
+        idx = torch.empty(max_triggers, dtype=torch.int64, device=trace.device)
+        amp = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
+        dchi2 = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
+        n = torch.zeros(1, dtype=torch.int32, device=trace.device)
+        check(lib.dp_trigger_run(self._h, C.c_void_p(trace.data_ptr()), trace.shape[0], float(chi2_threshold),
+                                 int(pileup_window_samples), int(index_shift), int(bool(padding)),
+                                 C.c_void_p(idx.data_ptr()), C.c_void_p(amp.data_ptr()), C.c_void_p(dchi2.data_ptr()),
+                                 int(max_triggers), C.c_void_p(n.data_ptr()), _stream_ptr(trace.device)))
+        nt = int(n.item())
+        self.n_found = nt
+        nt = min(nt, max_triggers)
+        return idx[:nt], amp[:nt], dchi2[:nt]
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        check(lib.dp_trigger_plan_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class OptimumFilterTrigger:
+    """1x1 mirror of the reference class (oftrigger.py:255-499, 588-679, 884-1034)."""
+
+    def __init__(self, trigger_channel, fs, template, noisecsd, pretrigger_samples, trigger_name=None,
+                 coupling='AC', iw=None, w=None, precision='f64', max_samples=12_500_000, device=None):
+        template = np.asarray(template, dtype=np.float64).reshape(-1)
+        noisecsd = np.real(np.asarray(noisecsd)).reshape(-1)
+        if template.shape[0] != noisecsd.shape[0]:
+            raise ValueError('ERROR: template and noise csd must have the same number of samples')
+        self._trigger_channel = trigger_channel
+        self._trigger_name = trigger_channel if trigger_name is None else trigger_name
+        self._fs = float(fs)
+        self._template = template
+        self._nb_samples = template.shape[0]
+        self._pretrigger_samples = int(pretrigger_samples)
+        # oftrigger.py:456
+        self._trigger_index_shift = self._pretrigger_samples - self._nb_samples // 2
+        # OF pre-calculations (reference: qp.OFBase add_template / set_csd / calc_phi, oftrigger.py:468-485)
+        # one-time host setup, any trace length: s = fft(template)/N/df, phi = conj(s)/J, norm = Re sum(phi s) df
+        # (same conventions as csrc/dp_plan.hpp::finalize_template and oracle/of1x1.py)
+        df = self._fs / self._nb_samples
+        J = np.array(noisecsd, dtype=np.float64)
+        if np.any(~(J > 0)):
+            raise ValueError('psd must be strictly positive')
+        if coupling == 'AC':
+            J[0] = np.inf
+        s_fd = np.fft.fft(template) / self._nb_samples / df
+        self._phi_fd = np.conj(s_fd) / J
+        norm = float(np.real(np.sum(self._phi_fd * s_fd)) * df)
+        self._w_matrix = float(norm if w is None else w)
+        self._iw_matrix = float(1.0 / norm if iw is None else iw)
+        phi_fd = self._phi_fd.copy()
+        phi_fd[0] = 0                                   # oftrigger.py:492
+        self._phi_td = np.fft.ifft(phi_fd).real         # oftrigger.py:493
+        self._norm = float(np.dot(self._phi_td, template))   # oftrigger.py:496
+        self._resolution = float(np.sqrt(1.0 / self._w_matrix))
+        self._plan = TriggerPlan(self._phi_td, self._iw_matrix, self._w_matrix, precision=precision,
+                                 max_samples=max_samples, device=device)
+        self._trace = None
+        self._padding = True
+        self._trigger_data = None
+        self.chi2_threshold = None
+
+    def get_phi(self):
+        return self._phi_td
+
+    def get_resolution(self):
+        return self._resolution
+
+    def update_trace(self, trace=None, filtered_trace=None, padding=True):
+        """Register the continuous trace (CUDA float64 tensor or numpy array, [L] or [1, L])."""
+        torch = _torch()
+        if filtered_trace is not None:
+            raise NotImplementedError('pre-filtered traces are not supported by the fused trigger')
+        if trace is None:
+            raise ValueError('ERROR: "trace" or "filtered_trace required!')
+        if isinstance(trace, np.ndarray):
+            trace = torch.from_numpy(np.ascontiguousarray(trace, dtype=np.float64)).to(self._plan.device)
+        if trace.ndim == 2:
+            if trace.shape[0] != 1:
+                raise ValueError(f'ERROR: "trace" has shape {tuple(trace.shape)}, but we have 1 channels!')
+            trace = trace[0]
+        if trace.shape[0] % 2:
+            trace = trace[:-1]
+        self._trace = trace
+        self._padding = bool(padding)
+
+    def find_triggers_once(self, thresh, pileup_window_msec=None, pileup_window_samples=None, max_triggers=65536):
+        if self._trace is None:
+            raise ValueError('ERROR: Filter trace not available.  Use "update_trace" first!')
+        pileup_window = 0
+        if pileup_window_msec is not None:
+            pileup_window = int(pileup_window_msec * self._fs / 1000)      # oftrigger.py:941
+        elif pileup_window_samples is not None:
+            pileup_window = pileup_window_samples
+        self.chi2_threshold = chi2_threshold_from_sigma(thresh)
+        idx, amp, dchi2 = self._plan.run(self._trace, self.chi2_threshold, pileup_window, self._trigger_index_shift,
+                                         self._padding, max_triggers)
+        idx = idx.cpu().numpy()
+        amp = amp.cpu().numpy()
+        dchi2 = dchi2.cpu().numpy()
+        n = len(idx)
+        d = {'trigger_delta_chi2': list(dchi2), 'trigger_time': list(idx / self._fs), 'trigger_index': list(idx),
+             'trigger_pileup_window': [pileup_window] * n, 'trigger_threshold_sigma': [thresh] * n,
+             'trigger_type': [4] * n, 'trigger_amplitude_0': list(amp), 'trigger_amplitude': list(amp)}
+        if n > 0:
+            d['trigger_channel'] = [str(self._trigger_name)] * n
+        for key, val in list(d.items()):        # oftrigger.py:1029-1031
+            d[key + '_' + self._trigger_name] = val
+        self._trigger_data = {self._trigger_name: d}
+        return self._trigger_data
+
+    def get_trigger_data(self):
+        return self._trigger_data

@@ -19,6 +19,8 @@
 #include "dp_psd2_kernel.cuh"
 #include "dp_psd_kernel.cuh"
 #include "dp_reduce_plan.hpp"
+#include "dp_trig_kernel.cuh"
+#include "dp_trig_launch.hpp"
 
 namespace {
 
@@ -1073,6 +1075,274 @@ int dp_psd_plan_last_kernel_ms(dp_psd_plan* p, float* ms) {
     if (!p || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
     DP_CUDA(cudaEventSynchronize(p->ev1));
     DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return DP_OK;
+}
+
+}  // extern "C"
+
+// ====================================================================== trigger plan
+struct dp_trigger_plan {
+    int nb_filter = 0;      // Nt taps
+    int precision = DP_PREC_F64;
+    int device = 0;
+    int r1 = 0, F = 0;      // FFT size F = r1 * 8192
+    int hop = 0, lead = 0;  // outputs per chunk, samples loaded ahead of the chunk's first output
+    long long max_samples = 0;
+    int max_chunks = 0;
+    double iw = 1.0, w = 1.0, scale = 1.0;
+    std::vector<double> phi_td;
+    bool tables_ok = false;
+    std::vector<void*> owned;
+    const void *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twn = nullptr, *groups = nullptr;
+    void* phi = nullptr;       // re-uploaded when the scale changes
+    void* phi_self = nullptr;
+    size_t phi_bytes = 0, phi_self_bytes = 0;
+    void* scratch = nullptr;
+    long long scratch_per_cta = 0;
+    int* cand_idx = nullptr;
+    double* cand_amp = nullptr;
+    int* cand_count = nullptr;
+    long long* chunk_offset = nullptr;
+    int grid_max = 0;
+    size_t smem = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+
+// filter spectrum on the one-sided bins, with the output alignment, iW and all scalings folded in
+std::vector<dpplan::cplx> trig_filter_onesided(const dp_trigger_plan* p) {
+    const int F = p->F, M = F / 2, Nt = p->nb_filter;
+    std::vector<dpplan::cplx> a(F, dpplan::cplx(0, 0));
+    for (int j = 0; j < Nt; ++j) a[j] = dpplan::cplx(p->phi_td[j], 0.0);
+    dpplan::fft_pow2(a);
+    const int c = (Nt - 1) / 2;
+    const long long sh = (long long)p->lead + c;  // circular-convolution index of output r = 0
+    std::vector<dpplan::cplx> pe(M + 1);
+    for (int k = 0; k <= M; ++k) {
+        const dpplan::cplx ramp = std::conj(dpplan::unit_root(((long long)k * sh) % F, F));  // e^{+2 pi i k sh / F}
+        pe[k] = a[k] * ramp * (p->iw / ((double)F * 2.0 * p->scale));
+    }
+    pe[0] = dpplan::cplx(pe[0].real(), 0.0);
+    pe[M] = dpplan::cplx(pe[M].real(), 0.0);
+    return pe;
+}
+
+template <class T, int R1> int trig_tables(dp_trigger_plan* p, bool filter_only) {
+    using S = typename Dp2Traits<T>::S;
+    int rc;
+    if (!filter_only) {
+        std::vector<dpplan::Channel> none;
+        dpplan2::Tables2<T> dt;
+        try {
+            dt = dpplan2::build_tables2<T, R1>(1.0, none, 0.0, 1.0);
+        } catch (const std::exception& e) {
+            return fail(DP_ERR_STATE, e.what());
+        }
+        const cx<T>* d;
+        if ((rc = upload(p->owned, dt.tw1, &d))) return rc;
+        p->tw1 = d;
+        if ((rc = upload(p->owned, dt.tw2, &d))) return rc;
+        p->tw2 = d;
+        if ((rc = upload(p->owned, dt.tw3, &d))) return rc;
+        p->tw3 = d;
+        const cx<S>* ds;
+        if ((rc = upload(p->owned, dt.twn, &ds))) return rc;
+        p->twn = ds;
+        const int2* dg;
+        if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
+        p->groups = dg;
+    }
+    std::vector<cx<T>> phi;
+    std::vector<cx<S>> phi_self;
+    dpplan2::pack_onesided<T, R1>(trig_filter_onesided(p), phi, phi_self);
+    if (!p->phi) {
+        p->phi_bytes = sizeof(cx<T>) * phi.size();
+        p->phi_self_bytes = sizeof(cx<S>) * phi_self.size();
+        DP_CUDA(cudaMalloc(&p->phi, p->phi_bytes));
+        p->owned.push_back(p->phi);
+        DP_CUDA(cudaMalloc(&p->phi_self, p->phi_self_bytes));
+        p->owned.push_back(p->phi_self);
+    }
+    DP_CUDA(cudaMemcpy(p->phi, phi.data(), p->phi_bytes, cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemcpy(p->phi_self, phi_self.data(), p->phi_self_bytes, cudaMemcpyHostToDevice));
+    return DP_OK;
+}
+template <class T> int trig_tables_r1(dp_trigger_plan* p, bool filter_only) {
+    switch (p->r1) {
+        case 2: return trig_tables<T, 2>(p, filter_only);
+        case 4: return trig_tables<T, 4>(p, filter_only);
+        default: return trig_tables<T, 8>(p, filter_only);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_trigger_plan_create(dp_trigger_plan** plan, const double* phi_td, int nb_filter, double iw, double w, int precision,
+                           long long max_samples, int device) {
+    if (!plan || !phi_td) return fail(DP_ERR_INVALID, "null pointer");
+    if (nb_filter < 2 || nb_filter > 32768) return fail(DP_ERR_UNSUPPORTED, "filter length must be in [2, 32768] samples");
+    if (precision != DP_PREC_F64 && precision != DP_PREC_F32) return fail(DP_ERR_INVALID, "unknown precision");
+    if (max_samples < 2 * (long long)nb_filter) return fail(DP_ERR_INVALID, "max_samples must be >= 2 * filter length");
+    if (!(w > 0) || !(iw > 0)) return fail(DP_ERR_INVALID, "weights must be > 0");
+    auto p = std::make_unique<dp_trigger_plan>();
+    p->nb_filter = nb_filter;
+    p->precision = precision;
+    p->device = device;
+    p->iw = iw;
+    p->w = w;
+    p->phi_td.assign(phi_td, phi_td + nb_filter);
+    p->F = nb_filter <= 8192 ? 16384 : (nb_filter <= 16384 ? 32768 : 65536);
+    p->r1 = p->F / 8192;
+    const int c = (nb_filter - 1) / 2, d = nb_filter - 1 - c;
+    p->lead = d + (d & 1);
+    p->hop = (p->F - p->lead - c) & ~1;
+    p->max_samples = max_samples;
+    p->max_chunks = (int)((max_samples + p->hop - 1) / p->hop);
+    DP_CUDA(cudaSetDevice(device));
+    int rc = precision == DP_PREC_F32 ? trig_tables_r1<f2>(p.get(), false) : trig_tables_r1<double>(p.get(), false);
+    if (!rc) {
+        const int src = precision == DP_PREC_F32 ? dp_trig_setup_p1(p->r1, device, &p->smem, &p->grid_max, &p->scratch_per_cta)
+                                                 : dp_trig_setup_p0(p->r1, device, &p->smem, &p->grid_max, &p->scratch_per_cta);
+        if (src != 0) rc = fail(DP_ERR_CUDA, "trigger kernel setup failed");
+    }
+    auto alloc = [&](void** ptr, size_t bytes) {
+        if (rc) return;
+        if (cudaMalloc(ptr, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+            rc = fail(DP_ERR_CUDA, "cudaMalloc failed (trigger plan)");
+            return;
+        }
+        p->owned.push_back(*ptr);
+    };
+    alloc(&p->scratch, 16 * (size_t)std::max<long long>(p->scratch_per_cta, 1) * (size_t)std::max(p->grid_max, 1));
+    alloc(reinterpret_cast<void**>(&p->cand_idx), sizeof(int) * (size_t)p->max_chunks * (size_t)p->hop);
+    alloc(reinterpret_cast<void**>(&p->cand_amp), sizeof(double) * (size_t)p->max_chunks * (size_t)p->hop);
+    alloc(reinterpret_cast<void**>(&p->cand_count), sizeof(int) * (size_t)p->max_chunks);
+    alloc(reinterpret_cast<void**>(&p->chunk_offset), sizeof(long long) * (size_t)(p->max_chunks + 1));
+    if (rc) {
+        for (void* dptr : p->owned) cudaFree(dptr);
+        return rc;
+    }
+    DP_CUDA(cudaEventCreate(&p->ev0));
+    DP_CUDA(cudaEventCreate(&p->ev1));
+    DP_CUDA(cudaEventCreate(&p->ev2));
+    *plan = p.release();
+    return DP_OK;
+}
+
+void dp_trigger_plan_destroy(dp_trigger_plan* p) {
+    if (!p) return;
+    for (void* d : p->owned) cudaFree(d);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->ev2) cudaEventDestroy(p->ev2);
+    delete p;
+}
+
+int dp_trigger_plan_set_scale(dp_trigger_plan* p, double typical_rms) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (!(typical_rms > 0)) return fail(DP_ERR_INVALID, "typical_rms must be > 0");
+    if (p->precision != DP_PREC_F32) return DP_OK;
+    p->scale = std::exp2(-std::round(std::log2(typical_rms)));
+    DP_CUDA(cudaSetDevice(p->device));
+    return trig_tables_r1<f2>(p, true);
+}
+
+int dp_trigger_plan_geometry(const dp_trigger_plan* p, int* fft_size, int* hop) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (fft_size) *fft_size = p->F;
+    if (hop) *hop = p->hop;
+    return DP_OK;
+}
+
+int dp_trigger_run(dp_trigger_plan* p, const double* trace_dev, long long n_samples, double chi2_threshold,
+                   long long pileup_window_samples, long long index_shift, int padding, long long* trig_index_dev,
+                   double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (!trace_dev || !trig_index_dev || !trig_amp_dev || !trig_dchi2_dev || !n_triggers_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if (n_samples < 2 || n_samples > p->max_samples) return fail(DP_ERR_INVALID, "n_samples out of the plan's range");
+    if (n_samples & 1) return fail(DP_ERR_INVALID, "n_samples must be even");
+    if ((reinterpret_cast<uintptr_t>(trace_dev) & 15) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
+    if (max_triggers < 0 || pileup_window_samples < 0) return fail(DP_ERR_INVALID, "negative argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int n_chunks = (int)((n_samples + p->hop - 1) / p->hop);
+    const int Nt = p->nb_filter;
+    long long vlo = 0, vhi = n_samples;
+    if (padding) {  // oftrigger.py:676-679
+        vlo = Nt;
+        vhi = n_samples - Nt + ((Nt + 1) % 2);
+    }
+    auto fill = [&](auto& prm) {
+        std::memset(&prm, 0, sizeof(prm));
+        prm.trace = trace_dev;
+        prm.n_samples = n_samples;
+        prm.n_chunks = n_chunks;
+        prm.hop = p->hop;
+        prm.lead = p->lead;
+        prm.valid_lo = vlo;
+        prm.valid_hi = vhi;
+        prm.groups = reinterpret_cast<const int2*>(p->groups);
+        prm.scratch_per_cta = p->scratch_per_cta;
+        prm.w = p->w;
+        prm.thr = chi2_threshold;
+        prm.scale = p->scale;
+        prm.subtract_first = p->precision == DP_PREC_F32 ? 1 : 0;
+        prm.cand_idx = p->cand_idx;
+        prm.cand_amp = p->cand_amp;
+        prm.cand_count = p->cand_count;
+    };
+    const int grid = std::min(n_chunks, p->grid_max);
+    DP_CUDA(cudaEventRecord(p->ev0, st));
+    int rc;
+    if (p->precision == DP_PREC_F32) {
+        DpTrigParams<f2> prm;
+        fill(prm);
+        prm.tw1 = (const cx<f2>*)p->tw1; prm.tw2 = (const cx<f2>*)p->tw2; prm.tw3 = (const cx<f2>*)p->tw3;
+        prm.twn = (const cx<float>*)p->twn;
+        prm.phi = (const cx<f2>*)p->phi; prm.phi_self = (const cx<float>*)p->phi_self;
+        prm.scratch = (cx<f2>*)p->scratch;
+        rc = dp_trig_launch_p1(p->r1, &prm, grid, p->smem, st);
+    } else {
+        DpTrigParams<double> prm;
+        fill(prm);
+        prm.tw1 = (const cx<double>*)p->tw1; prm.tw2 = (const cx<double>*)p->tw2; prm.tw3 = (const cx<double>*)p->tw3;
+        prm.twn = (const cx<double>*)p->twn;
+        prm.phi = (const cx<double>*)p->phi; prm.phi_self = (const cx<double>*)p->phi_self;
+        prm.scratch = (cx<double>*)p->scratch;
+        rc = dp_trig_launch_p0(p->r1, &prm, grid, p->smem, st);
+    }
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger filter launch: ") + cudaGetErrorString((cudaError_t)rc));
+    DP_CUDA(cudaEventRecord(p->ev1, st));
+    DpTrigGroupParams gp;
+    gp.cand_idx = p->cand_idx;
+    gp.cand_amp = p->cand_amp;
+    gp.cand_count = p->cand_count;
+    gp.n_chunks = n_chunks;
+    gp.hop = p->hop;
+    gp.pileup_window = pileup_window_samples;
+    gp.index_shift = index_shift;
+    gp.w = p->w;
+    gp.trig_index = trig_index_dev;
+    gp.trig_amp = trig_amp_dev;
+    gp.trig_dchi2 = trig_dchi2_dev;
+    gp.max_triggers = max_triggers;
+    gp.n_triggers = n_triggers_dev;
+    gp.chunk_offset = p->chunk_offset;
+    rc = dp_trig_group_launch(&gp, st);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger group launch: ") + cudaGetErrorString((cudaError_t)rc));
+    DP_CUDA(cudaEventRecord(p->ev2, st));
+    p->timed = true;
+    return DP_OK;
+}
+
+int dp_trigger_plan_last_kernel_ms(dp_trigger_plan* p, float* filter_ms, float* group_ms) {
+    if (!p || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
+    DP_CUDA(cudaEventSynchronize(p->ev2));
+    if (filter_ms) DP_CUDA(cudaEventElapsedTime(filter_ms, p->ev0, p->ev1));
+    if (group_ms) DP_CUDA(cudaEventElapsedTime(group_ms, p->ev1, p->ev2));
     return DP_OK;
 }
 

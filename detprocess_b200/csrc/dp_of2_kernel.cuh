@@ -240,6 +240,22 @@ template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw(const void* row, in
     for (int l = 0; l < VL; ++l) r.q[l] = dp_load_raw<IN>(row, j0 + l);
     return r;
 }
+// same, for a chunk of a continuous stream that may stick out of [0, n_pairs): `row` is the
+// stream base, jbase the (possibly negative) pair index of the chunk start; out-of-range
+// pairs read as zero (zero-padded linear convolution, like scipy's oaconvolve)
+template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, long long jmax, int n1, int c) {
+    Dp2Raw<IN, VL> r;
+    const long long j0 = jbase + (long long)n1 * 4096 + (long long)VL * c;
+#pragma unroll
+    for (int l = 0; l < VL; ++l) {
+        const long long j = j0 + l;
+        typename DpRaw<IN>::type zero;
+        zero.x = 0;
+        zero.y = 0;
+        r.q[l] = (j < 0 || j > jmax) ? zero : dp_load_raw<IN>(row, j);
+    }
+    return r;
+}
 template <int IN> DP_DEV cx<double> dp2_convert(const Dp2Raw<IN, 1>& r, double x0, double sc) {
     return cx<double>{((double)r.q[0].x - x0) * sc, ((double)r.q[0].y - x0) * sc};
 }
@@ -267,7 +283,10 @@ template <class T, int R1, int IN> struct Dp2Core {
     static constexpr int PG = GV + 1, PC = CV + CV / GV, PB = VPB + VPB / GV;
 
     // ---- pass 1 of phase PH: global -> radix-R1 over n1 (only the phase's blocks) -> twiddle -> smem
-    template <int PH> static DP_DEV void pass1(const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1) {
+    // CLAMP: `row` is a stream base and (jbase, jmax) place / bound the chunk (dp2_load_raw_clamped)
+    template <int PH, bool CLAMP = false>
+    static DP_DEV void pass1(const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1, long long jbase = 0,
+                             long long jmax = 0) {
         const int tid = threadIdx.x;
         // columns loaded back to back: <= 64 registers of raw float64 samples in flight
         constexpr int CBW = ((VL == 2) ? 8 : 16) / R1;
@@ -278,7 +297,9 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
             for (int i = 0; i < CB; ++i)
 #pragma unroll
-                for (int n = 0; n < R1; ++n) raw[i][n] = dp2_load_raw<IN, VL>(row, n, tid + (i0 + i) * NT);
+                for (int n = 0; n < R1; ++n)
+                    raw[i][n] = CLAMP ? dp2_load_raw_clamped<IN, VL>(row, jbase, jmax, n, tid + (i0 + i) * NT)
+                                      : dp2_load_raw<IN, VL>(row, n, tid + (i0 + i) * NT);
 #pragma unroll
             for (int i = 0; i < CB; ++i) {
                 const int c = tid + (i0 + i) * NT;
@@ -296,20 +317,22 @@ template <class T, int R1, int IN> struct Dp2Core {
             }
         }
     }
-    static DP_DEV void pass1_any(int p, const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1) {
+    template <bool CLAMP = false>
+    static DP_DEV void pass1_any(int p, const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1, long long jbase = 0,
+                                 long long jmax = 0) {
         if constexpr (NPH == 1) {
-            pass1<0>(row, x0, sc, buf, tw1);
+            pass1<0, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax);
         } else if constexpr (NPH == 2) {
             if (p == 0)
-                pass1<0>(row, x0, sc, buf, tw1);
+                pass1<0, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax);
             else
-                pass1<1>(row, x0, sc, buf, tw1);
+                pass1<1, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax);
         } else {
             switch (p) {
-                case 0: pass1<0>(row, x0, sc, buf, tw1); break;
-                case 1: pass1<1>(row, x0, sc, buf, tw1); break;
-                case 2: pass1<2>(row, x0, sc, buf, tw1); break;
-                default: pass1<3>(row, x0, sc, buf, tw1); break;
+                case 0: pass1<0, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax); break;
+                case 1: pass1<1, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax); break;
+                case 2: pass1<2, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax); break;
+                default: pass1<3, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax); break;
             }
         }
     }
@@ -647,12 +670,12 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
     }
 
     // filter multiply + inverse untangle, in place: (z, zm) X -> Z' (group values for pass 4')
-    static DP_DEV void filter_all(const Smem& sm, V (&z)[16], V (&zm)[VL == 1 ? 8 : 1], const V* DP_RESTRICT phi, cx<S> wn, int Gown) {
+    static DP_DEV void filter_all(V* buf, V (&z)[16], V (&zm)[VL == 1 ? 8 : 1], const V* DP_RESTRICT phi, cx<S> wn, int Gown) {
         const int tid = threadIdx.x;
         if constexpr (VL == 2) {
             (void)zm;
             (void)Gown;
-            (void)sm;
+            (void)buf;
 #pragma unroll
             for (int h = 0; h < 16; h += DP2_TBL_BATCH) {
                 dp2_sched_fence();
@@ -681,11 +704,11 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
                 cx<S> Ck, Cm;
                 dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
                 z[r] = Ck;
-                sm.buf[Gp * 17 + 15 - r] = Cm;  // partner's element 15 - r
+                buf[Gp * 17 + 15 - r] = Cm;  // partner's element 15 - r
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) z[8 + j] = sm.buf[Gown * 17 + 8 + j];
+            for (int j = 0; j < 8; ++j) z[8 + j] = buf[Gown * 17 + 8 + j];
         }
     }
 
@@ -819,7 +842,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     sm.sp[sp.ek] = Ck;
                     if (sp.ek != sp.em) sm.sp[sp.em] = Cm;
                 }
-                filter_all(sm, z, zm, tp.phi + (long long)p * 16 * NT, wn, gg.x);
+                filter_all(sm.buf, z, zm, tp.phi + (long long)p * 16 * NT, wn, gg.x);
                 if (p == 0 && tid < 32) {
                     __syncwarp();
                     if constexpr (VL == 2) {

@@ -104,6 +104,29 @@ template <class G> inline void verify_geometry() {
         if (seen[k] != 1) throw std::logic_error("v2 geometry: bin " + std::to_string(k) + " covered " + std::to_string(seen[k]) + " times");
 }
 
+// a one-sided filter pe[0..M] (applied to 2*sc*fft(x), see dpplan::filter_onesided) in thread order
+template <class T, int R1>
+void pack_onesided(const std::vector<cplx>& pe, std::vector<cx<T>>& phi, std::vector<cx<typename Dp2Traits<T>::S>>& phi_self) {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    phi.resize((size_t)G::NPH * 16 * G::NT);
+    for (int p = 0; p < G::NPH; ++p)
+        for (int e = 0; e < 16; ++e)
+            for (int t = 0; t < G::NT; ++t) {
+                int b[2];
+                entry_bins<G>(p, t, e, b);
+                const cplx z[2] = {pe[b[0]], pe[b[1]]};
+                phi[((size_t)p * 16 + e) * G::NT + t] = Pack<T>::c(z);
+            }
+    phi_self.resize(17 * 2);
+    for (int l = 0; l < 17; ++l) {
+        int b[2];
+        bool dd[2];
+        self_bins<G>(l, b, dd);
+        for (int j = 0; j < 2; ++j) phi_self[l * 2 + j] = cx<S>{(S)pe[b[j]].real(), (S)pe[b[j]].imag()};
+    }
+}
+
 template <class T, int R1>
 Tables2<T> build_tables2(double fs, const std::vector<dpplan::Channel>& chans, double fcut, double scale) {
     using G = Dp2Geom<T, R1>;

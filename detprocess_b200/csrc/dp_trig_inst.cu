@@ -1,0 +1,70 @@
+// Translation unit of the continuous-stream trigger kernels (dp_trig_kernel.cuh), one per
+// precision:  -DDP_INST_PREC=0|1 (double | packed float).  The stream is float64.
+#ifndef DP_INST_PREC
+#error "DP_INST_PREC must be defined"
+#endif
+#include <cuda_runtime.h>
+
+#if DP_INST_PREC == 0
+#define DP_TRIG_DEFINE_GROUP_KERNEL 1
+#endif
+#include "dp_trig_kernel.cuh"
+#include "dp_trig_launch.hpp"
+
+#if DP_INST_PREC == 0
+using InstT = double;
+#else
+using InstT = f2;
+#endif
+
+#define DP_CAT_(a, b) a##b
+#define DP_CAT(a, b) DP_CAT_(a, b)
+
+namespace {
+template <int R1> int setup_one(int device, size_t* smem, int* grid_max, long long* scratch_per_cta) {
+    using K = DpTrigKernel<InstT, R1, 0>;
+    auto kern = dp_trig_filter_kernel<InstT, R1, 0>;
+    *smem = K::SMEM_BYTES;
+    *scratch_per_cta = K::SCR_PARK;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::NT, K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) return -2;
+    *grid_max = sms * occ;
+    return 0;
+}
+template <int R1> int launch_one(const DpTrigParams<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
+    dp_trig_filter_kernel<InstT, R1, 0><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+    return (int)cudaGetLastError();
+}
+}  // namespace
+
+int DP_CAT(dp_trig_setup_p, DP_INST_PREC)(int R1, int device, size_t* smem, int* grid_max, long long* scratch_per_cta) {
+    switch (R1) {
+        case 2: return setup_one<2>(device, smem, grid_max, scratch_per_cta);
+        case 4: return setup_one<4>(device, smem, grid_max, scratch_per_cta);
+        case 8: return setup_one<8>(device, smem, grid_max, scratch_per_cta);
+        default: return -1;
+    }
+}
+int DP_CAT(dp_trig_launch_p, DP_INST_PREC)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
+    const DpTrigParams<InstT>& prm = *reinterpret_cast<const DpTrigParams<InstT>*>(prm_v);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
+    switch (R1) {
+        case 2: return launch_one<2>(prm, grid, smem, st);
+        case 4: return launch_one<4>(prm, grid, smem, st);
+        case 8: return launch_one<8>(prm, grid, smem, st);
+        default: return -1;
+    }
+}
+#if DP_INST_PREC == 0
+int dp_trig_group_launch(const void* prm_v, void* st_v) {
+    const DpTrigGroupParams& prm = *reinterpret_cast<const DpTrigGroupParams*>(prm_v);
+    dp_trig_group_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(st_v)>>>(prm);
+    return (int)cudaGetLastError();
+}
+#endif

@@ -1,0 +1,421 @@
+// Continuous-stream optimal-filter trigger (BASELINE.json config C4).
+//
+// Replaces OptimumFilterTrigger.update_trace + find_triggers_once for the 1x1 case
+// (reference detprocess/core/oftrigger.py:588-679, 884-1034):
+//     V        = oaconvolve(raw, phi_td, 'same')           (FIR filter, Nt taps)
+//     filtered = iW * V ;  delta_chi2 = filtered^2 * W     (:659-672)
+//     delta_chi2[:Nt] = 0 ; delta_chi2[-Nt + (Nt+1)%2:] = 0 (:676-679)
+//     mask = delta_chi2 > chi2_threshold ; groups of mask indices separated by gaps
+//     > pileup_window (:29-74) ; per group the first arg-max of delta_chi2 (:1001-1005).
+//
+// Kernel 1 (dp_trig_filter_kernel): overlap-save on the v2 FFT core.  Chunk q is the F-point
+// real FFT of samples [q*H - D, q*H - D + F) x the filter spectrum (alignment, iW and all
+// scalings folded into the table, so output index r IS stream index q*H + r) and the inverse
+// FFT, all in shared memory / registers: every stream sample is read from HBM once per chunk
+// it belongs to (F/H ~ 2 reads for Nt = F/2).  The filtered samples never leave the SM: the
+// threshold test runs on the registers that hold them, candidates are marked in a shared
+// bit mask and written -- ordered by stream index -- into the chunk's slice of the candidate
+// list.  Chunks without a candidate (the common case) stop after the mask.
+// Kernel 2 (dp_trig_group_kernel): one CTA walks the ordered candidate list, splits it where
+// the gap exceeds the pile-up window and emits the first arg-max of each group.
+#pragma once
+#include "dp_of2_kernel.cuh"
+
+template <class T> struct DpTrigParams {
+    using S = typename Dp2Traits<T>::S;
+    const void* trace;      // continuous stream (in_dtype samples)
+    long long n_samples;
+    int n_chunks;
+    int hop;                // H: outputs per chunk
+    int lead;               // D: chunk q loads samples [q*H - D, q*H - D + F)
+    long long valid_lo, valid_hi;  // only outputs i in [valid_lo, valid_hi) can trigger
+    const cx<T>* tw1;
+    const cx<T>* tw2;
+    const cx<T>* tw3;
+    const cx<S>* twn;
+    const int2* groups;
+    const cx<T>* phi;       // [NPH][16][NT] filter spectrum, thread order
+    const cx<S>* phi_self;  // [17][2]
+    cx<T>* scratch;         // [grid][(NPH-1)*NB*VPB] parked block results
+    long long scratch_per_cta;
+    double w;               // delta_chi2 = filtered^2 * w
+    double thr;             // chi2 threshold
+    double scale;
+    int subtract_first;
+    int* cand_idx;          // [n_chunks][hop] stream index relative to chunk start (r)
+    double* cand_amp;       // [n_chunks][hop] filtered amplitude
+    int* cand_count;        // [n_chunks]
+};
+
+template <class T, int R1, int IN> struct DpTrigKernel {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    using V = cx<T>;
+    using Core = Dp2Core<T, R1, IN>;
+    using OF = Dp2OfKernel<T, R1, IN>;
+    static constexpr int NT = G::NT, VL = G::VL, NB = G::NB, NPH = G::NPH, VPB = G::VPB, GC = G::GC, NC = G::NC, F = G::N;
+    static constexpr int NW = NT / 32;
+    static constexpr int MASK_WORDS = F / 32;
+    static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (32 + 34) + sizeof(unsigned) * (2 * MASK_WORDS + 64) + 64;
+    static constexpr long long SCR_PARK = (long long)(NPH - 1) * NB * VPB;
+
+    // visit the candidate samples of one pass-1' column set: fn(r, value)
+    template <class Fn> static DP_DEV void for_samples(const V (&y)[GC * R1], int tid, int i0, Fn&& fn) {
+#pragma unroll
+        for (int n = 0; n < R1; ++n)
+#pragma unroll
+            for (int i = 0; i < GC; ++i) {
+                const int r0 = 2 * (n * 4096 + VL * (tid + (i0 + i) * NT));
+                const V& v = y[i * R1 + n];
+                fn(r0, Dp2Scan<T, R1>::template re_of<0>(v));
+                fn(r0 + 1, Dp2Scan<T, R1>::template im_of<0>(v));
+                if constexpr (VL == 2) {
+                    fn(r0 + 2, Dp2Scan<T, R1>::template re_of<1>(v));
+                    fn(r0 + 3, Dp2Scan<T, R1>::template im_of<1>(v));
+                }
+            }
+    }
+
+    static DP_DEV void run(const DpTrigParams<T>& prm, unsigned char* smem_raw) {
+        V* buf = reinterpret_cast<V*>(smem_raw);
+        cx<S>* sp = reinterpret_cast<cx<S>*>(buf + G::SMEM_V);
+        cx<S>* sx = sp + 32;
+        unsigned* mask = reinterpret_cast<unsigned*>(sx + 34);   // [MASK_WORDS] candidate bits
+        unsigned* rank = mask + MASK_WORDS;                       // [MASK_WORDS] exclusive prefix of popc(mask)
+        unsigned* wsum = rank + MASK_WORDS;                       // [33] warp totals
+        const int tid = threadIdx.x;
+        constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
+        constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
+        V* park = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
+        const S wS = (S)prm.w, thrS = (S)prm.thr;
+        const long long jmax = prm.n_samples / 2 - 1;
+
+        for (int q = blockIdx.x; q < prm.n_chunks; q += gridDim.x) {
+            const long long s0 = (long long)q * prm.hop - prm.lead;  // first sample of the chunk (even)
+            const bool edge = s0 < 0 || s0 + F > prm.n_samples;
+            const void* xrow = reinterpret_cast<const unsigned char*>(prm.trace) + (size_t)(edge ? 0 : s0) * ESZ;
+            const long long jbase = s0 / 2;  // s0 is even, also when negative
+            // fp32 mode removes the chunk's first sample before the conversion (the filter has no DC
+            // gain); edge chunks are zero padded, so they keep their offset
+            const double x0 = (prm.subtract_first && !edge) ? dp_load_first<IN>(xrow) : 0.0;
+            for (int wd = tid; wd < MASK_WORDS; wd += NT) mask[wd] = 0u;
+
+#pragma unroll 1
+            for (int p = 0; p < NPH; ++p) {
+                V z[16];
+                V zm[VL == 1 ? 8 : 1];
+                const int2 gg = prm.groups[p * NT + tid];
+                const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
+                const bool special = (p == 0) && (tid < NSPECIAL);
+                if (edge)
+                    Core::template pass1_any<true>(p, prm.trace, x0, prm.scale, buf, prm.tw1, jbase, jmax);
+                else
+                    Core::template pass1_any<false>(p, xrow, x0, prm.scale, buf, prm.tw1);
+                __syncthreads();
+                Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                if (p == 0 && tid < 32) {
+                    if constexpr (VL == 2) {
+                        if (tid == 0) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                sp[r] = dp2_lane0(z[r]);
+                                sp[16 + r] = dp2_lane1(z[r]);
+                            }
+                        }
+                    } else {
+                        if (tid < 2) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) sp[16 * tid + r] = z[r];
+                        }
+                    }
+                    __syncwarp();
+                    if (tid < 17) {
+                        const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
+                        cx<S> Xk, Xm;
+                        dp_untangle(sp[sl.ek], sp[sl.em], sl.w, Xk, Xm);
+                        sx[2 * tid] = Xk;
+                        sx[2 * tid + 1] = Xm;
+                    }
+                    __syncwarp();
+                }
+                OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+                if (p == 0 && tid < 17) {
+                    const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
+                    const cx<S> Fk = cmul(dp_ldg(prm.phi_self + 2 * tid), sx[2 * tid]);
+                    const cx<S> Fm = cmul(dp_ldg(prm.phi_self + 2 * tid + 1), sx[2 * tid + 1]);
+                    cx<S> Ck, Cm;
+                    dp_retangle(Fk, Fm, sl.w, Ck, Cm);
+                    sp[sl.ek] = Ck;
+                    if (sl.ek != sl.em) sp[sl.em] = Cm;
+                }
+                OF::filter_all(buf, z, zm, prm.phi + (long long)p * 16 * NT, wn, gg.x);
+                if (p == 0 && tid < 32) {
+                    __syncwarp();
+                    if constexpr (VL == 2) {
+                        if (tid == 0) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) z[r] = V{f2(sp[r].re, sp[16 + r].re), f2(sp[r].im, sp[16 + r].im)};
+                        }
+                    } else {
+                        if (tid < 2) {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) z[r] = sp[16 * tid + r];
+                        }
+                    }
+                    __syncwarp();
+                }
+                Core::inv_432(buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                if (p < NPH - 1) {
+                    Core::park_pass2(park, p, z);
+                    __syncthreads();
+                } else {
+                    Core::store_pass2(buf, z);
+                    __syncthreads();
+                }
+            }
+            // ---- threshold on the filtered samples (registers) -> bit mask ----------------------
+            const long long ibase = (long long)q * prm.hop;
+            const long long lo = prm.valid_lo - ibase, hi = prm.valid_hi - ibase;  // candidate r range, clipped below
+            const int rlo = (int)(lo < 0 ? 0 : (lo > prm.hop ? prm.hop : lo));
+            const int rhi = (int)(hi < 0 ? 0 : (hi > prm.hop ? prm.hop : hi));
+#pragma unroll 1
+            for (int i0 = 0; i0 < NC; i0 += GC) {
+                V y[GC * R1];
+                Core::inv_pass1(buf, park, prm.tw1, i0, y);
+                for_samples(y, tid, i0, [&](int r, S a) {
+                    if (r >= rlo && r < rhi && a * a * wS > thrS) atomicOr(&mask[r >> 5], 1u << (r & 31));
+                });
+            }
+            __syncthreads();
+            // ---- exclusive prefix of the per-word candidate counts -------------------------------
+            constexpr int WPT = (MASK_WORDS + NT - 1) / NT;  // words per thread (contiguous)
+            unsigned cnt = 0;
+#pragma unroll
+            for (int j = 0; j < WPT; ++j) {
+                const int wd = tid * WPT + j;
+                if (wd < MASK_WORDS) cnt += __popc(mask[wd]);
+            }
+            unsigned inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((tid & 31) >= o) inc += t;
+            }
+            if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned v = tid < NW ? wsum[tid] : 0u;
+                unsigned iv = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, iv, o);
+                    if (tid >= o) iv += t;
+                }
+                wsum[tid] = iv - v;              // exclusive warp offsets
+                if (tid == 31) wsum[32] = iv;    // total
+            }
+            __syncthreads();
+            const unsigned total = wsum[32];
+            if (tid == 0) prm.cand_count[q] = (int)total;
+            if (total != 0) {  // CTA-uniform
+                unsigned run = wsum[tid >> 5] + inc - cnt;
+#pragma unroll
+                for (int j = 0; j < WPT; ++j) {
+                    const int wd = tid * WPT + j;
+                    if (wd < MASK_WORDS) {
+                        rank[wd] = run;
+                        run += __popc(mask[wd]);
+                    }
+                }
+                __syncthreads();
+                // second look at the filtered samples: candidates go to their ordered slot
+                int* ci = prm.cand_idx + (long long)q * prm.hop;
+                double* ca = prm.cand_amp + (long long)q * prm.hop;
+#pragma unroll 1
+                for (int i0 = 0; i0 < NC; i0 += GC) {
+                    V y[GC * R1];
+                    Core::inv_pass1(buf, park, prm.tw1, i0, y);
+                    for_samples(y, tid, i0, [&](int r, S a) {
+                        if (r >= rlo && r < rhi && a * a * wS > thrS) {
+                            const unsigned m = mask[r >> 5];
+                            const unsigned slot = rank[r >> 5] + __popc(m & ((1u << (r & 31)) - 1u));
+                            ci[slot] = r;
+                            ca[slot] = (double)a;
+                        }
+                    });
+                }
+            }
+            __syncthreads();  // mask / buf are rewritten by the next chunk
+        }
+    }
+};
+
+// --------------------------------------------------------------------- grouping
+struct DpTrigGroupParams {
+    const int* cand_idx;      // [n_chunks][hop]
+    const double* cand_amp;
+    const int* cand_count;    // [n_chunks]
+    int n_chunks;
+    int hop;
+    long long pileup_window;  // gap (samples) above which a new group starts
+    long long index_shift;    // added to the arg-max index (pretrigger - Nt/2, oftrigger.py:456)
+    double w;
+    long long* trig_index;    // [max_triggers]
+    double* trig_amp;
+    double* trig_dchi2;
+    int max_triggers;
+    int* n_triggers;          // [1] total number of groups found (may exceed max_triggers)
+    long long* chunk_offset;  // [n_chunks + 1] scratch: exclusive prefix of cand_count
+};
+
+#ifndef DP_HOST_EMU
+#ifdef DP_TRIG_DEFINE_GROUP_KERNEL  // exactly one translation unit (dp_trig_inst.cu, float64)
+// single CTA of 1024 threads; candidates are globally ordered by stream index
+__global__ void __launch_bounds__(1024, 1) dp_trig_group_kernel(const DpTrigGroupParams prm) {
+    constexpr int NTG = 1024;
+    __shared__ long long s_off[NTG + 1];
+    // slot 0 = group carried in from the previous tile, slots 1..1024 = groups that start in this tile
+    __shared__ unsigned long long s_best[NTG + 1];   // ordered bits of |amp| per group
+    __shared__ long long s_bidx[NTG + 1];            // smallest stream index attaining it
+    __shared__ double s_bamp[NTG + 1];
+    __shared__ int s_scan[NTG];
+    __shared__ long long s_carry_idx, s_prev_idx, s_total;
+    __shared__ unsigned long long s_carry_best;
+    __shared__ double s_carry_amp;
+    __shared__ int s_open, s_nout;
+    const int tid = threadIdx.x;
+    // 1) exclusive prefix of the chunk counts (sequential over tiles of 1024 chunks)
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < prm.n_chunks; c0 += NTG) {
+        const int c = c0 + tid;
+        const int v = c < prm.n_chunks ? prm.cand_count[c] : 0;
+        s_scan[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < NTG; o <<= 1) {
+            const int t = tid >= o ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += t;
+            __syncthreads();
+        }
+        if (c < prm.n_chunks) prm.chunk_offset[c] = s_total + s_scan[tid] - v;
+        __syncthreads();
+        if (tid == NTG - 1) s_total += s_scan[tid];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        prm.chunk_offset[prm.n_chunks] = s_total;
+        s_open = 0;
+        s_nout = 0;
+        s_prev_idx = 0;
+    }
+    __syncthreads();
+    const long long K = s_total;
+    // 2) tiles of 1024 candidates
+    int chunk_lo = 0;  // first chunk that can contain candidate g0 (monotone)
+    for (long long g0 = 0; g0 < K; g0 += NTG) {
+        const long long g = g0 + tid;
+        long long idx = 0;
+        double amp = 0.0;
+        bool have = g < K;
+        if (have) {
+            // chunk of candidate g: binary search in chunk_offset
+            int lo = chunk_lo, hi = prm.n_chunks - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (prm.chunk_offset[mid] <= g) lo = mid; else hi = mid - 1;
+            }
+            const long long pos = g - prm.chunk_offset[lo];
+            idx = (long long)lo * prm.hop + prm.cand_idx[(long long)lo * prm.hop + pos];
+            amp = prm.cand_amp[(long long)lo * prm.hop + pos];
+            if (tid == 0) chunk_lo = lo;
+        }
+        chunk_lo = __shfl_sync(0xffffffffu, chunk_lo, 0);  // warp 0 only matters; others keep a valid lower bound
+        s_off[tid + 1] = idx;
+        if (tid == 0) s_off[0] = s_prev_idx;
+        __syncthreads();
+        const bool head = have && ((g == 0) || (idx - s_off[tid] > prm.pileup_window));
+        // tile-local group id = number of heads at or before this candidate
+        s_scan[tid] = head ? 1 : 0;
+        __syncthreads();
+        for (int o = 1; o < NTG; o <<= 1) {
+            const int t = tid >= o ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += t;
+            __syncthreads();
+        }
+        const int gid = s_scan[tid];              // 0: continues the carried group
+        const int ngroups = s_scan[NTG - 1];      // heads in this tile
+        s_best[tid] = 0ull;
+        s_bidx[tid] = 0x7fffffffffffffffll;
+        if (tid == 0) {
+            s_best[NTG] = 0ull;
+            s_bidx[NTG] = 0x7fffffffffffffffll;
+        }
+        if (tid == 0 && s_open) {                 // slot 0 starts from the carried group
+            s_best[0] = s_carry_best;
+            s_bidx[0] = s_carry_idx;
+            s_bamp[0] = s_carry_amp;
+        }
+        __syncthreads();
+        const unsigned long long key = have ? (unsigned long long)__double_as_longlong(fabs(amp)) : 0ull;
+        // slot of a group: gid (slot 0 = carried group; tile groups 1..ngroups)
+        if (have) atomicMax(&s_best[gid], key);
+        __syncthreads();
+        // a member beat the carried maximum: the carried index no longer counts
+        if (tid == 0 && s_open && s_best[0] != s_carry_best) s_bidx[0] = 0x7fffffffffffffffll;
+        __syncthreads();
+        if (have && key == s_best[gid]) atomicMin(reinterpret_cast<unsigned long long*>(&s_bidx[gid]), (unsigned long long)idx);
+        __syncthreads();
+        if (have && key == s_best[gid] && idx == s_bidx[gid]) s_bamp[gid] = amp;
+        __syncthreads();
+        // closed groups: slot 0 (if open and a head exists in this tile) and tile groups 1..ngroups-1;
+        // the last group stays open.  With no head in the tile the carried group just grows.
+        const int first_slot = s_open ? 0 : 1;
+        const int n_closed = ngroups > 0 ? (ngroups - first_slot) : 0;  // slots first_slot .. ngroups-1
+        if (tid < n_closed) {
+            const int slot = first_slot + tid;
+            const int o = s_nout + tid;
+            if (o < prm.max_triggers) {
+                const double a = s_bamp[slot];
+                prm.trig_index[o] = s_bidx[slot] + prm.index_shift;
+                prm.trig_amp[o] = a;
+                prm.trig_dchi2[o] = a * a * prm.w;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_nout += n_closed;
+            const int last = ngroups > 0 ? ngroups : 0;
+            if (ngroups > 0 || s_open) {
+                s_carry_best = s_best[last];
+                s_carry_idx = s_bidx[last];
+                s_carry_amp = s_bamp[last];
+                s_open = 1;
+            }
+            const long long nk = K - g0 < NTG ? K - g0 : NTG;
+            s_prev_idx = s_off[nk];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (s_open) {
+            const int o = s_nout;
+            if (o < prm.max_triggers) {
+                prm.trig_index[o] = s_carry_idx + prm.index_shift;
+                prm.trig_amp[o] = s_carry_amp;
+                prm.trig_dchi2[o] = s_carry_amp * s_carry_amp * prm.w;
+            }
+            s_nout += 1;
+        }
+        *prm.n_triggers = s_nout;
+    }
+}
+#endif  // DP_TRIG_DEFINE_GROUP_KERNEL
+
+template <class T, int R1, int IN>
+__global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, Dp2Geom<T, R1>::NT <= 256 ? 2 : 1) dp_trig_filter_kernel(const DpTrigParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char dp_smem_raw[];
+    DpTrigKernel<T, R1, IN>::run(prm, dp_smem_raw);
+}
+#endif

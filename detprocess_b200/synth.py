@@ -8,7 +8,7 @@ HDF5 library in this environment, so every measurement runs on these arrays
 
 import numpy as np
 
-__all__ = ['make_template', 'make_psd', 'make_noise', 'make_traces', 'SynthSetup']
+__all__ = ['make_template', 'make_psd', 'make_noise', 'make_traces', 'make_continuous', 'SynthSetup']
 
 FS_DEFAULT = 1.25e6
 SEED_DEFAULT = 12345
@@ -69,6 +69,35 @@ def make_traces(nb_events, template, psd, fs=FS_DEFAULT, rng=None,
     if return_truth:
         return traces, amps, delays
     return traces
+
+
+def make_continuous(n_samples, template, psd, fs=FS_DEFAULT, rng=None, pulse_rate_hz=5.0, amp_range=(5e-8, 2e-7),
+                    nb_pretrigger=None, offset=0.0, return_truth=False):
+    """Continuous stream [n_samples]: coloured noise (drawn block-wise from ``psd``, blocks cross-faded so
+    the stream has no seams) + Poisson pulses of the template's shape (BASELINE.json config C4)."""
+    rng = np.random.default_rng(SEED_DEFAULT) if rng is None else rng
+    n = psd.shape[-1]
+    if nb_pretrigger is None:
+        nb_pretrigger = n // 2
+    nblk = n_samples // (n // 2) + 2
+    blocks = make_noise(nblk, psd, fs, rng)
+    w = np.sqrt(0.5 * (1 - np.cos(2 * np.pi * (np.arange(n) + 0.5) / n)))   # sqrt-Hann: w[i]^2 + w[i+n/2]^2 = 1
+    x = np.zeros(n_samples + 2 * n)
+    for b in range(nblk):
+        x[b * (n // 2): b * (n // 2) + n] += w * blocks[b]
+    x = x[n // 2: n // 2 + n_samples].copy()
+    n_pulses = rng.poisson(pulse_rate_hz * n_samples / fs)
+    t0 = np.sort(rng.integers(2 * n, max(2 * n + 1, n_samples - 2 * n), n_pulses))
+    amps = rng.uniform(amp_range[0], amp_range[1], n_pulses)
+    shape = template[nb_pretrigger:]
+    for t, a in zip(t0, amps):
+        m = min(len(shape), n_samples - t)
+        x[t:t + m] += a * shape[:m]
+    if offset:
+        x += offset
+    if return_truth:
+        return x, t0, amps
+    return x
 
 
 class SynthSetup:

@@ -160,6 +160,29 @@ int dp_psd_get_sums(dp_psd_plan* plan, double* sums_dev /* [N/2+1] */, unsigned 
                     void* stream);
 int dp_psd_plan_last_kernel_ms(dp_psd_plan* plan, float* ms);
 
+/* ------------------------------------------------------- continuous-stream OF trigger
+ * Replaces OptimumFilterTrigger.update_trace + find_triggers_once for one trigger channel and
+ * one amplitude (detprocess/core/oftrigger.py:588-679, 884-1034).  phi_td is the reference's
+ * `self._phi_td[0,0]` (real(ifft(phi_fd with the DC bin zeroed)), oftrigger.py:491-493), iw / w its
+ * 1x1 `_iw_matrix` / `_w_matrix`:  filtered = iw * oaconvolve(trace, phi_td, 'same'),
+ * delta_chi2 = filtered^2 * w.  dp_trigger_run filters the stream (overlap-save FFT chunks in shared
+ * memory), thresholds delta_chi2 > chi2_threshold (host computes it from sigma, oftrigger.py:961-965),
+ * merges indices closer than pileup_window_samples and returns, per group, the first arg-max:
+ * trig_index = argmax + index_shift (pretrigger - nb_samples/2, oftrigger.py:456,1005), the
+ * filtered amplitude and delta_chi2 there.  *n_triggers_dev receives the number of groups found
+ * (only the first max_triggers are stored).  padding != 0 zeroes the edges like the reference.
+ */
+typedef struct dp_trigger_plan dp_trigger_plan;
+int dp_trigger_plan_create(dp_trigger_plan** plan, const double* phi_td, int nb_filter, double iw, double w,
+                           int precision, long long max_samples, int device);
+void dp_trigger_plan_destroy(dp_trigger_plan* plan);
+int dp_trigger_plan_set_scale(dp_trigger_plan* plan, double typical_rms);   /* fp32 mode: sample scale hint */
+int dp_trigger_plan_geometry(const dp_trigger_plan* plan, int* fft_size, int* hop);
+int dp_trigger_run(dp_trigger_plan* plan, const double* trace_dev, long long n_samples, double chi2_threshold,
+                   long long pileup_window_samples, long long index_shift, int padding, long long* trig_index_dev,
+                   double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream);
+int dp_trigger_plan_last_kernel_ms(dp_trigger_plan* plan, float* filter_ms, float* group_ms);
+
 #ifdef __cplusplus
 }
 #endif
