@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=256, help='events per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fast-mode', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the C4 (trigger) / C5 (PSD) side measurements')
     return ap.parse_args()
 
 
@@ -229,6 +230,64 @@ def time_steps(plan, x, out, steps, warmup, dist, world):
     return ms, kms
 
 
+def extras(device, dist, world, hbm_peak):
+    """Side measurements of the other hot-path rows (not the headline metric): C5 noise PSD on
+    65536-sample traces (+ the all-reduce of the per-GPU sums when N > 1) and C4 continuous-stream
+    trigger on one 10 s stream.  Device-resident synthetic inputs, CUDA-event kernel times."""
+    import torch
+    from detprocess_b200.core.noise import NoisePSD
+    from detprocess_b200.core.oftrigger import OptimumFilterTrigger
+    from detprocess_b200.synth import make_template, make_psd
+    out = {}
+    # ---- C5
+    n, B = 65536, 4096
+    x = torch.randn((B, n), dtype=torch.float64, device=device) * 1e-10
+    for prec in ('f64', 'f32'):
+        est = NoisePSD(n, FS, precision=prec, device=device, typical_rms=1e-10)
+        for _ in range(2):
+            est.update(x)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(3):
+            est.update(x)
+            ms.append(est.plan.last_kernel_ms())
+        m = float(np.mean(ms))
+        t0 = time.perf_counter()
+        est.finalize()                      # all-reduce of [N/2+1] sums + count (NCCL when world > 1)
+        torch.cuda.synchronize()
+        out[f'c5_psd_{prec}'] = {'traces_per_s_per_gpu': B / (m * 1e-3), 'achieved_gbs': B * n * 8 / (m * 1e-3) / 1e9,
+                                 'roofline_frac': B * n * 8 / (m * 1e-3) / 1e9 / hbm_peak,
+                                 'finalize_ms_incl_allreduce': 1e3 * (time.perf_counter() - t0), 'nb_samples': n}
+        del est
+    del x
+    # ---- C4: one continuous 10 s stream @1.25 MHz, 32768-tap filter
+    nt, L = 32768, 12_500_000
+    g = torch.Generator(device=device)
+    g.manual_seed(777)
+    stream = torch.randn(L, generator=g, device=device, dtype=torch.float64) * 1.2e-8
+    tmpl = make_template(nt, FS)
+    psd = make_psd(nt, FS)
+    shape = torch.from_numpy(tmpl[nt // 2:]).to(device)
+    for t0 in range(300_000, L - 300_000, 250_000):             # 5 Hz pulses
+        stream[t0:t0 + shape.shape[0]] += 1.5e-7 * shape
+    for prec in ('f64', 'f32'):
+        trig = OptimumFilterTrigger('ch', FS, tmpl, psd, nt // 2, precision=prec, max_samples=L, device=device)
+        if prec == 'f32':
+            trig._plan.set_scale(1.2e-8)
+        trig.update_trace(stream)
+        for _ in range(2):
+            d = trig.find_triggers_once(5.0, pileup_window_msec=1.0)
+        torch.cuda.synchronize()
+        fms, gms = trig._plan.last_kernel_ms()
+        out[f'c4_trigger_{prec}'] = {'samples_per_s_per_gpu': L / ((fms + gms) * 1e-3), 'filter_ms': fms, 'group_ms': gms,
+                                     'stream_seconds': L / FS, 'n_triggers': len(d['ch']['trigger_index']),
+                                     'achieved_gbs': L * 8 / (fms * 1e-3) / 1e9,
+                                     'roofline_frac': L * 8 / (fms * 1e-3) / 1e9 / hbm_peak,
+                                     'fft_size': trig._plan.fft_size, 'hop': trig._plan.hop}
+        del trig
+    return out
+
+
 def gpu_main(a):
     import torch
     rank = int(os.environ.get('RANK', '0'))
@@ -301,6 +360,9 @@ def gpu_main(a):
         results[prec]['n_out'] = plan.n_out
         del plan, out
 
+    ex = None
+    if not a.no_extras:
+        ex = extras(device, dist, world, hbm_peak)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -317,8 +379,9 @@ def gpu_main(a):
                    'sharding': 'events sharded by rank, no data-path collective'},
         'roofline': {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': r['achieved_gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                     'kernel': 'dp_of_kernel<double,16,2,0>', 'kernel_ms': r['kernel_ms'],
-                     'note': 'FFT path is FP64-pipe/shared-memory bound, not HBM bound; see DESIGN.md'},
+                     'kernel': 'dp_of2_kernel<double,4,0,true>', 'kernel_ms': r['kernel_ms'],
+                     'algorithmic_bytes_per_event': BYTES_PER_EVENT,
+                     'note': 'FFT path is FP64-pipe / issue bound, not HBM bound (10 FLOP/B); see DESIGN.md 4.1'},
         'e2e': {k: r['e2e'][k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')},
         'gpu_launches': r['launches'] * world,
         'clocks': sampler.summary() if sampler else None,
@@ -327,8 +390,10 @@ def gpu_main(a):
         f = results['f32']
         line['fast_mode'] = {'dtype': 'f32', 'value': f['value'], 'unit': UNIT, 'ms_per_step': f['ms_per_step'],
                              'roofline_frac': f['achieved_gbs'] / hbm_peak, 'achieved_gbs': f['achieved_gbs'],
-                             'kernel': 'dp_of_kernel<float,32,1,0>', 'e2e': f['e2e']['value'],
+                             'kernel': 'dp_of2_kernel<f2,4,0,true>', 'e2e': f['e2e']['value'],
                              'tolerance': 'amp 1e-5, chi2 1e-4 rel vs float64 oracle'}
+    if ex is not None:
+        line['other_rows'] = ex
     if cb is not None:
         line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line), flush=True)

@@ -31,6 +31,16 @@ def two_sided_from_sums(sums, count, nb_samples, fs):
     return torch.cat([half, torch.flip(half[1:nb_samples - nb_samples // 2], dims=[0])])
 
 
+def allreduce_sums(sums, count, group=None):
+    """Sum the per-rank periodogram sums [N/2+1] and accepted-trace counts over all ranks (NCCL over
+    NVLink for CUDA tensors, gloo for the CPU tests).  No-op without an initialised process group."""
+    torch = _torch()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
+        torch.distributed.all_reduce(count, op=torch.distributed.ReduceOp.SUM, group=group)
+    return sums, count
+
+
 class NoisePSD:
     """Streaming, multi-GPU ``calc_psd``.
 
@@ -73,9 +83,8 @@ class NoisePSD:
         torch = _torch()
         sums, count = self.plan.sums()
         off = self._median_sum
+        sums, count = allreduce_sums(sums, count, group)
         if torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
-            torch.distributed.all_reduce(count, op=torch.distributed.ReduceOp.SUM, group=group)
             if off is not None:
                 pack = torch.cat([off, torch.tensor([float(self._n_median)], dtype=off.dtype, device=off.device)])
                 torch.distributed.all_reduce(pack, op=torch.distributed.ReduceOp.SUM, group=group)

@@ -58,3 +58,41 @@ def test_two_rank_gather_equals_single(n_events):
     assert np.array_equal(full['event_number'].to_numpy(), ev)          # rank order == event order
     assert np.array_equal(full['amp_x'].to_numpy(), np.sin(ev) * 1e-7)  # sharded == single
     assert sorted(set(full['rank'])) == ([0, 1] if n_events > 1 else [1])
+
+
+def _psd_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from detprocess_b200.core.noise import allreduce_sums, two_sided_from_sums
+    from oracle import psd as P
+    n, fs, n_tr = 1024, 1.25e6, 90
+    tr = np.random.default_rng(21).standard_normal((n_tr, n)) * 1e-10
+    cut = np.random.default_rng(22).random(n_tr) < 0.8
+    lo, hi = shard_range(n_tr, rank, world)
+    s, c = P.periodogram_sums(tr[lo:hi], cut[lo:hi])       # what one GPU accumulates for its shard
+    sums, count = allreduce_sums(torch.from_numpy(s.copy()), torch.tensor([c], dtype=torch.int64))
+    psd = two_sided_from_sums(sums, int(count.item()), n, fs).numpy()
+    if rank == 0:
+        q.put((psd, int(count.item()), P.calc_psd(tr, fs, cut)[1], int(cut.sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_psd_allreduce_equals_single():
+    """C5 host path: per-rank periodogram sums + counts all-reduced == PSD of the whole set."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_psd_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    psd, count, ref, nref = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert count == nref
+    assert np.allclose(psd, ref, rtol=1e-12, atol=0)
