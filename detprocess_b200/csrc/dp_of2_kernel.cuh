@@ -223,6 +223,78 @@ template <int R, class T> DP_DEV void dp2_powers(cx<T> w, cx<T> (&pw)[R]) {
     if constexpr (R > 7) pw[7] = cmul(pw[4], pw[3]);
 }
 
+// ---- L2-resident scratch (X spill of multi-template plans, parked block results of multi-phase
+// transforms): written and re-read within one event by the same CTA.  The streaming traces would
+// otherwise evict it between the write and the read (ncu: every scratch byte went to DRAM and
+// back); an evict_last cache policy on these 16-byte accesses keeps it in L2.
+DP_DEV unsigned long long dp2_policy_keep() {
+#ifdef DP_HOST_EMU
+    return 0ull;
+#else
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+#endif
+}
+template <class V> DP_DEV void dp2_st_keep(V* ptr, const V& v, unsigned long long pol) {
+    static_assert(sizeof(V) == 16, "scratch vectors are 16 bytes");
+#ifdef DP_HOST_EMU
+    (void)pol;
+    *ptr = v;
+#else
+    const uint4 u = *reinterpret_cast<const uint4*>(&v);
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w), "l"(pol)
+                 : "memory");
+#endif
+}
+template <class V> DP_DEV V dp2_ld_keep(const V* ptr, unsigned long long pol) {
+    static_assert(sizeof(V) == 16, "scratch vectors are 16 bytes");
+#ifdef DP_HOST_EMU
+    (void)pol;
+    return *ptr;
+#else
+    uint4 u;
+    asm volatile("ld.global.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(ptr), "l"(pol)
+                 : "memory");
+    V v;
+    *reinterpret_cast<uint4*>(&v) = u;
+    return v;
+#endif
+}
+
+// streaming policy for the LAST read of a trace (evict_first) / earlier reads (evict_normal)
+DP_DEV unsigned long long dp2_policy_stream(bool last_read) {
+#ifdef DP_HOST_EMU
+    (void)last_read;
+    return 0ull;
+#else
+    unsigned long long a, b;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(a));
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(b));
+    return last_read ? a : b;
+#endif
+}
+template <int IN> DP_DEV typename DpRaw<IN>::type dp2_load_pair(const void* row, long long j, unsigned long long pol) {
+#ifdef DP_HOST_EMU
+    (void)pol;
+    return dp_load_raw<IN>(row, j);
+#else
+    typename DpRaw<IN>::type v;
+    const typename DpRaw<IN>::type* ptr = reinterpret_cast<const typename DpRaw<IN>::type*>(row) + j;
+    if constexpr (IN == 0) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
+    } else if constexpr (IN == 1) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(ptr), "l"(pol));
+    } else {
+        unsigned u;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(u) : "l"(ptr), "l"(pol));
+        v.x = (short)(u & 0xffffu);
+        v.y = (short)(u >> 16);
+    }
+    return v;
+#endif
+}
+
 // lanes of a packed complex pair
 DP_DEV cx<float> dp2_lane0(cx<f2> z) { return cx<float>{z.re.x, z.im.x}; }
 DP_DEV cx<float> dp2_lane1(cx<f2> z) { return cx<float>{z.re.y, z.im.y}; }
@@ -233,17 +305,18 @@ DP_DEV void dp2_set1(cx<f2>& z, cx<float> v) { z.re.y = v.re, z.im.y = v.im; }
 template <int IN, int VL> struct Dp2Raw {
     typename DpRaw<IN>::type q[VL];
 };
-template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw(const void* row, int n1, int c) {
+template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw(const void* row, int n1, int c, unsigned long long pol) {
     Dp2Raw<IN, VL> r;
     const long long j0 = (long long)n1 * 4096 + (long long)VL * c;
 #pragma unroll
-    for (int l = 0; l < VL; ++l) r.q[l] = dp_load_raw<IN>(row, j0 + l);
+    for (int l = 0; l < VL; ++l) r.q[l] = dp2_load_pair<IN>(row, j0 + l, pol);
     return r;
 }
 // same, for a chunk of a continuous stream that may stick out of [0, n_pairs): `row` is the
 // stream base, jbase the (possibly negative) pair index of the chunk start; out-of-range
 // pairs read as zero (zero-padded linear convolution, like scipy's oaconvolve)
-template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, long long jmax, int n1, int c) {
+template <int IN, int VL>
+DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, long long jmax, int n1, int c, unsigned long long pol) {
     Dp2Raw<IN, VL> r;
     const long long j0 = jbase + (long long)n1 * 4096 + (long long)VL * c;
 #pragma unroll
@@ -252,7 +325,7 @@ template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void*
         typename DpRaw<IN>::type zero;
         zero.x = 0;
         zero.y = 0;
-        r.q[l] = (j < 0 || j > jmax) ? zero : dp_load_raw<IN>(row, j);
+        r.q[l] = (j < 0 || j > jmax) ? zero : dp2_load_pair<IN>(row, j, pol);
     }
     return r;
 }
@@ -288,6 +361,7 @@ template <class T, int R1, int IN> struct Dp2Core {
     static DP_DEV void pass1(const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1, long long jbase = 0,
                              long long jmax = 0) {
         const int tid = threadIdx.x;
+        const unsigned long long pol = dp2_policy_stream(PH == NPH - 1);  // the last phase's read is the trace's last use
         // columns loaded back to back: <= 64 registers of raw float64 samples in flight
         constexpr int CBW = ((VL == 2) ? 8 : 16) / R1;
         constexpr int CB = CBW < 1 ? 1 : (CBW > NC ? NC : CBW);
@@ -298,8 +372,8 @@ template <class T, int R1, int IN> struct Dp2Core {
             for (int i = 0; i < CB; ++i)
 #pragma unroll
                 for (int n = 0; n < R1; ++n)
-                    raw[i][n] = CLAMP ? dp2_load_raw_clamped<IN, VL>(row, jbase, jmax, n, tid + (i0 + i) * NT)
-                                      : dp2_load_raw<IN, VL>(row, n, tid + (i0 + i) * NT);
+                    raw[i][n] = CLAMP ? dp2_load_raw_clamped<IN, VL>(row, jbase, jmax, n, tid + (i0 + i) * NT, pol)
+                                      : dp2_load_raw<IN, VL>(row, n, tid + (i0 + i) * NT, pol);
 #pragma unroll
             for (int i = 0; i < CB; ++i) {
                 const int c = tid + (i0 + i) * NT;
@@ -441,23 +515,34 @@ template <class T, int R1, int IN> struct Dp2Core {
         const int tid = threadIdx.x;
         const int b = tid / CV, cc = tid % CV;
         V* dst = scr + (long long)(p * NB + b) * VPB + cc;
+        const unsigned long long pol = dp2_policy_keep();
 #pragma unroll
-        for (int n = 0; n < 16; ++n) dst[n * CV] = z[n];
+        for (int n = 0; n < 16; ++n) dp2_st_keep(dst + n * CV, z[n], pol);
     }
-    // ---- pass 1' for columns [i0, i0 + GC): y[i*R1 + n1] = c'[n1*4096 + VL*(tid + (i0+i)*NT) + lane]
-    static DP_DEV void inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1]) {
+    // ---- pass 1' for columns [i0, i0 + GC): y[i*R1 + n1] = c'[n1*4096 + VL*(tid + (i0+i)*NT) + lane].
+    // Only columns that hold a complex point n in [nlo, nhi] are computed (constrained delay windows
+    // touch ~1/8 of the columns); the others keep stale registers, which no window scan selects.
+    static DP_DEV void inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1], int nlo = 0,
+                                 int nhi = 0x7fffffff) {
         const int tid = threadIdx.x;
         constexpr int LP = NPH - 1;
 #pragma unroll
         for (int i = 0; i < G::GC; ++i) {
             const int c = tid + (i0 + i) * NT;
+            bool need = false;
+#pragma unroll
+            for (int n = 0; n < R1; ++n) {
+                const int a = n * 4096 + VL * c;
+                need = need || (a + VL - 1 >= nlo && a <= nhi);
+            }
+            if (!need) continue;
             V u[R1];
 #pragma unroll
             for (int b = 0; b < NB; ++b) u[G::k1_of(LP, b)] = buf[G::phys(c) + b * PB];
 #pragma unroll
             for (int p = 0; p < LP; ++p)
 #pragma unroll
-                for (int b = 0; b < NB; ++b) u[G::k1_of(p, b)] = scr[(long long)(p * NB + b) * VPB + c];
+                for (int b = 0; b < NB; ++b) u[G::k1_of(p, b)] = dp2_ld_keep(scr + (long long)(p * NB + b) * VPB + c, dp2_policy_keep());
             V w = dp_ldg(tw1 + c);
             w.im = -w.im;
             V pw[R1];
@@ -743,7 +828,6 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
         const Dp2ChanDev<T>& ch = *reinterpret_cast<const Dp2ChanDev<T>*>(chs);
         const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
         const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
-        prefetch_next(prm, row);
         S chi = (S)0;
 
 #pragma unroll 1
@@ -799,17 +883,21 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     if (kA < prm.nlow) sm.stash[kA] = z[0];
                 }
             }
+            // next trace -> L2 once this event's last read of its own trace is done (a whole event of
+            // lead time let the scratch / table traffic of 148 SMs evict the line before its use)
+            if (p == NPH - 1) prefetch_next(prm, row);
             if constexpr (MULTI) {
                 // X must survive the in-place inverse of the previous template (thread-private column)
                 V* dst = scr_x + tid;
+                const unsigned long long pol = dp2_policy_keep();
                 if constexpr (VL == 2) {
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) dst[r * NT] = z[r];
+                    for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
                 } else {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        dst[(2 * r) * NT] = z[r];
-                        dst[(2 * r + 1) * NT] = zm[r];
+                        dp2_st_keep(dst + (2 * r) * NT, z[r], pol);
+                        dp2_st_keep(dst + (2 * r + 1) * NT, zm[r], pol);
                     }
                 }
             }
@@ -822,14 +910,15 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 V* park = scr_park + (long long)it * SCR_PARK;
                 if constexpr (MULTI) {
                     const V* src = scr_x + tid;
+                    const unsigned long long pol = dp2_policy_keep();
                     if constexpr (VL == 2) {
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) z[r] = src[r * NT];
+                        for (int r = 0; r < 16; ++r) z[r] = dp2_ld_keep(src + r * NT, pol);
                     } else {
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            z[r] = src[(2 * r) * NT];
-                            zm[r] = src[(2 * r + 1) * NT];
+                            z[r] = dp2_ld_keep(src + (2 * r) * NT, pol);
+                            zm[r] = dp2_ld_keep(src + (2 * r + 1) * NT, pol);
                         }
                     }
                 }
@@ -882,10 +971,24 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 DpBest<S> tb[DP_MAX_TSLOTS];
 #pragma unroll
                 for (int q = 0; q < DP_MAX_TSLOTS; ++q) tb[q] = DpBest<S>{(S)0, -1};
+                // complex points n = r/2 that some fit of this template can select
+                int nlo = 0x7fffffff, nhi = -1;
+#pragma unroll
+                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                    if (q < nts) {
+                        const DpSlot sl = ch.slots[slot_of[q]];
+                        const bool everything = sl.outside || (sl.lo == 0 && sl.hi == N);
+                        const int a = everything ? 0 : (sl.lo >> 1), b = everything ? 0x7fffffff : ((sl.hi - 1) >> 1);
+                        nlo = a < nlo ? a : nlo;
+                        nhi = b > nhi ? b : nhi;
+                    }
+                }
 #pragma unroll 1
                 for (int i0 = 0; i0 < NC; i0 += GC) {
                     V y[GC * R1];
-                    Core::inv_pass1(sm.buf, park, prm.tw1, i0, y);
+#pragma unroll
+                    for (int j = 0; j < GC * R1; ++j) y[j] = V{(T)0.0f, (T)0.0f};
+                    Core::inv_pass1(sm.buf, park, prm.tw1, i0, y, nlo, nhi);
 #pragma unroll
                     for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
                         if (q < nts) {
