@@ -696,7 +696,7 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
 
     // ---- point-wise stage, forward half: z (pass-4 outputs) -> 2*X at the thread's bins.
     // VL == 2: z[r] lanes = X at (bin of A[r], bin of B[r]).
-    // VL == 1: z[0..7] = X at own[r]; zm[0..7] = X at M - bin(own[r]) (the partner's element 15 - r).
+    // (packed fp32 only; fp64 goes pair by pair through pw_untangle / pw_filter_pair below)
     // Returns the thread's chi0 partial sum (scalar type S).
     template <bool WITH_CHI = true>
     static DP_DEV S untangle_all(V* buf, V (&z)[16], V (&zm)[VL == 1 ? 8 : 1], const T* DP_RESTRICT wj, cx<S> wn, int Gown,
@@ -731,25 +731,8 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
             }
             chi = acc.x + acc.y;
         } else {
-            // exchange the upper halves with the partner thread (tid ^ 1) through the (now idle)
-            // group rows of the shared buffer: own elements 8..15 out, partner's 8..15 in
-#pragma unroll
-            for (int j = 0; j < 8; ++j) buf[Gown * 17 + 8 + j] = z[8 + j];
-            __syncwarp();
-            int Gp = __shfl_xor_sync(0xffffffffu, Gown, 1);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) zm[j] = buf[Gp * 17 + 15 - j];  // partner element 15 - j
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                cx<S> Xk, Xm;
-                dp_untangle(z[r], zm[r], cmul(wn, dp_w64_rt<S>(2 * r)), Xk, Xm);
-                if constexpr (WITH_CHI) {
-                    chi = dp_fma(dp_ldg(wj + (2 * r) * NT + tid), cnorm2(Xk), chi);
-                    chi = dp_fma(dp_ldg(wj + (2 * r + 1) * NT + tid), cnorm2(Xm), chi);
-                }
-                z[r] = Xk;
-                zm[r] = Xm;
-            }
+            static_assert(VL == 2, "fp64 uses the pair-wise pw_* functions");
+            (void)tid;
         }
         return special ? (S)0 : chi;
     }
@@ -781,20 +764,45 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
             DP2_FP(8) DP2_FP(9) DP2_FP(10) DP2_FP(11) DP2_FP(12) DP2_FP(13) DP2_FP(14) DP2_FP(15)
 #undef DP2_FP
         } else {
-            const int Gp = __shfl_xor_sync(0xffffffffu, Gown, 1);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const cx<S> Fk = cmul(dp_ldg(phi + (2 * r) * NT + tid), z[r]);
-                const cx<S> Fm = cmul(dp_ldg(phi + (2 * r + 1) * NT + tid), zm[r]);
-                cx<S> Ck, Cm;
-                dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
-                z[r] = Ck;
-                buf[Gp * 17 + 15 - r] = Cm;  // partner's element 15 - r
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) z[8 + j] = buf[Gown * 17 + 8 + j];
+            static_assert(VL == 2, "fp64 uses the pair-wise pw_* functions");
+            (void)tid;
         }
+    }
+
+    // ---- fp64 (VL == 1) point-wise stage, one (k, M-k) pair at a time.  A thread owns group elements
+    // 0..15; pair r = (own[r], partner[15 - r]), r < 8, where the partner thread (tid ^ 1) owns the mirror
+    // group.  Nothing but z stays in registers: the partner's element is read from its group row when the
+    // pair is processed and the pair's results go straight to their consumers (the former version kept
+    // eight more vectors alive, which left ptxas three registers' worth of filter loads in flight).
+    static DP_DEV void pw_publish(V* buf, const V (&z)[16], int Gown) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) buf[Gown * 17 + 8 + j] = z[8 + j];  // own elements 8..15 for the partner
+        __syncwarp();
+    }
+    // fn(r, Xk, Xm): 2*X at bin(own[r]) and at M - bin(own[r])
+    template <class Fn> static DP_DEV void pw_untangle(const V* buf, const V (&z)[16], cx<S> wn, int Gp, Fn&& fn) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const V Zm = buf[Gp * 17 + 15 - r];
+            cx<S> Xk, Xm;
+            dp_untangle(z[r], Zm, cmul(wn, dp_w64_rt<S>(2 * r)), Xk, Xm);
+            fn(r, Xk, Xm);
+        }
+    }
+    // filter + inverse untangle of pair r: C'[own r] -> z[r], C'[partner 15 - r] -> the partner's row
+    static DP_DEV void pw_filter_pair(V* buf, V (&z)[16], int r, cx<S> Xk, cx<S> Xm, const V* DP_RESTRICT phi, cx<S> wn, int Gp) {
+        const int tid = threadIdx.x;
+        const cx<S> Fk = cmul(dp_ldg(phi + (2 * r) * NT + tid), Xk);
+        const cx<S> Fm = cmul(dp_ldg(phi + (2 * r + 1) * NT + tid), Xm);
+        cx<S> Ck, Cm;
+        dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
+        z[r] = Ck;
+        buf[Gp * 17 + 15 - r] = Cm;
+    }
+    static DP_DEV void pw_collect(const V* buf, V (&z)[16], int Gown) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[8 + j] = buf[Gown * 17 + 8 + j];  // written by the partner
     }
 
     // MULTI: some channel has more than one template (X goes through the thread-private scratch
@@ -871,36 +879,51 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 }
                 __syncwarp();
             }
-            chi += untangle_all(sm.buf, z, zm, ch.wj + (long long)p * 16 * NT, wn, gg.x, special);
-            if (!special) {
-                // low-frequency bins for lowchi2: element 0 of each group (k4 = 0)
-                const int kA = G::bin_of(p, gg.x, 0);
-                if constexpr (VL == 2) {
-                    const int kB = G::bin_of(p, gg.y, 0);
+            const T* wjp = ch.wj + (long long)p * 16 * NT;
+            [[maybe_unused]] int Gp = 0;  // partner's group (fp64)
+            if constexpr (VL == 2) {
+                chi += untangle_all(sm.buf, z, zm, wjp, wn, gg.x, special);
+                if (!special) {
+                    // low-frequency bins for lowchi2: element 0 of each group (k4 = 0)
+                    const int kA = G::bin_of(p, gg.x, 0), kB = G::bin_of(p, gg.y, 0);
                     if (kA < prm.nlow) sm.stash[kA] = dp2_lane0(z[0]);
                     if (kB < prm.nlow) sm.stash[kB] = dp2_lane1(z[0]);
-                } else {
-                    if (kA < prm.nlow) sm.stash[kA] = z[0];
                 }
+                if constexpr (MULTI) {
+                    // X must survive the in-place inverse of the previous template (thread-private column)
+                    V* dst = scr_x + tid;
+                    const unsigned long long pol = dp2_policy_keep();
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
+                }
+            } else {
+                // fp64: pair by pair -- chi0, the lowchi2 stash and (single template) the filter + inverse
+                // untangle are applied while the pair is in registers; multi-template plans send X to the
+                // thread-private L2 column instead
+                Gp = __shfl_xor_sync(0xffffffffu, gg.x, 1);
+                const int kA = G::bin_of(p, gg.x, 0);
+                const bool stash0 = !special && kA < prm.nlow;
+                [[maybe_unused]] V* dst = scr_x + tid;
+                [[maybe_unused]] const unsigned long long pol = dp2_policy_keep();
+                [[maybe_unused]] const V* phi0 = ch.templ[0].phi + (long long)p * 16 * NT;
+                S chin = (S)0;
+                pw_publish(sm.buf, z, gg.x);
+                pw_untangle(sm.buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) {
+                    chin = dp_fma(dp_ldg(wjp + (2 * r) * NT + tid), cnorm2(Xk), chin);
+                    chin = dp_fma(dp_ldg(wjp + (2 * r + 1) * NT + tid), cnorm2(Xm), chin);
+                    if (r == 0 && stash0) sm.stash[kA] = Xk;
+                    if constexpr (MULTI) {
+                        dp2_st_keep(dst + (2 * r) * NT, Xk, pol);
+                        dp2_st_keep(dst + (2 * r + 1) * NT, Xm, pol);
+                    } else {
+                        pw_filter_pair(sm.buf, z, r, Xk, Xm, phi0, wn, Gp);
+                    }
+                });
+                if (!special) chi += chin;
             }
             // next trace -> L2 once this event's last read of its own trace is done (a whole event of
             // lead time let the scratch / table traffic of 148 SMs evict the line before its use)
             if (p == NPH - 1) prefetch_next(prm, row);
-            if constexpr (MULTI) {
-                // X must survive the in-place inverse of the previous template (thread-private column)
-                V* dst = scr_x + tid;
-                const unsigned long long pol = dp2_policy_keep();
-                if constexpr (VL == 2) {
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        dp2_st_keep(dst + (2 * r) * NT, z[r], pol);
-                        dp2_st_keep(dst + (2 * r + 1) * NT, zm[r], pol);
-                    }
-                }
-            }
 
             // ---------------- per template: filter, inverse passes 4' 3' 2' ---------------------
             const int n_templ = MULTI ? ch.n_templ : 1;
@@ -908,20 +931,6 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             for (int it = 0; it < n_templ; ++it) {
                 const Dp2TemplDev<T>& tp = ch.templ[it];
                 V* park = scr_park + (long long)it * SCR_PARK;
-                if constexpr (MULTI) {
-                    const V* src = scr_x + tid;
-                    const unsigned long long pol = dp2_policy_keep();
-                    if constexpr (VL == 2) {
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) z[r] = dp2_ld_keep(src + r * NT, pol);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            z[r] = dp2_ld_keep(src + (2 * r) * NT, pol);
-                            zm[r] = dp2_ld_keep(src + (2 * r + 1) * NT, pol);
-                        }
-                    }
-                }
                 if (p == 0 && tid < 17) {
                     const DpSelfLane<S> sp = dp_self_lane<S, 1>(tid);
                     const cx<S> Fk = cmul(dp_ldg(tp.phi_self + 2 * tid), sx[2 * tid]);
@@ -931,7 +940,27 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     sm.sp[sp.ek] = Ck;
                     if (sp.ek != sp.em) sm.sp[sp.em] = Cm;
                 }
-                filter_all(sm.buf, z, zm, tp.phi + (long long)p * 16 * NT, wn, gg.x);
+                if constexpr (VL == 2) {
+                    if constexpr (MULTI) {
+                        const V* src = scr_x + tid;
+                        const unsigned long long pol = dp2_policy_keep();
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) z[r] = dp2_ld_keep(src + r * NT, pol);
+                    }
+                    filter_all(sm.buf, z, zm, tp.phi + (long long)p * 16 * NT, wn, gg.x);
+                } else {
+                    if constexpr (MULTI) {
+                        const V* src = scr_x + tid;
+                        const unsigned long long pol = dp2_policy_keep();
+                        const V* phit = tp.phi + (long long)p * 16 * NT;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const V Xk = dp2_ld_keep(src + (2 * r) * NT, pol), Xm = dp2_ld_keep(src + (2 * r + 1) * NT, pol);
+                            pw_filter_pair(sm.buf, z, r, Xk, Xm, phit, wn, Gp);
+                        }
+                    }
+                    pw_collect(sm.buf, z, gg.x);
+                }
                 if (p == 0 && tid < 32) {
                     __syncwarp();
                     if constexpr (VL == 2) {

@@ -94,9 +94,9 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
                     }
                     __syncwarp();
                 }
-                OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
-                if (!special) {
-                    if constexpr (VL == 2) {
+                if constexpr (VL == 2) {
+                    OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+                    if (!special) {
                         double2* dst = reinterpret_cast<double2*>(part) + (long long)p * 16 * NT + tid;
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
@@ -106,14 +106,17 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
                             a.y += (double)pw.y * inv_s2;
                             dst[r * NT] = a;
                         }
-                    } else {
-                        double* dst = part + (long long)p * 16 * NT + tid;
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            dst[(2 * r) * NT] += cnorm2(z[r]) * inv_s2;
-                            dst[(2 * r + 1) * NT] += cnorm2(zm[r]) * inv_s2;
-                        }
                     }
+                } else {
+                    const int Gp = __shfl_xor_sync(0xffffffffu, gg.x, 1);
+                    double* dst = part + (long long)p * 16 * NT + tid;
+                    OF::pw_publish(buf, z, gg.x);
+                    OF::pw_untangle(buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) {
+                        if (!special) {
+                            dst[(2 * r) * NT] += cnorm2(Xk) * inv_s2;
+                            dst[(2 * r + 1) * NT] += cnorm2(Xm) * inv_s2;
+                        }
+                    });
                 }
                 __syncthreads();  // group rows of buf are rewritten by the next pass 1
             }

@@ -138,7 +138,15 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                     }
                     __syncwarp();
                 }
-                OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+                if constexpr (VL == 2) {
+                    OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+                } else {
+                    // fp64: untangle, filter and inverse untangle pair by pair
+                    const int Gp = __shfl_xor_sync(0xffffffffu, gg.x, 1);
+                    const V* phip = prm.phi + (long long)p * 16 * NT;
+                    OF::pw_publish(buf, z, gg.x);
+                    OF::pw_untangle(buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) { OF::pw_filter_pair(buf, z, r, Xk, Xm, phip, wn, Gp); });
+                }
                 if (p == 0 && tid < 17) {
                     const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
                     const cx<S> Fk = cmul(dp_ldg(prm.phi_self + 2 * tid), sx[2 * tid]);
@@ -148,7 +156,10 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                     sp[sl.ek] = Ck;
                     if (sl.ek != sl.em) sp[sl.em] = Cm;
                 }
-                OF::filter_all(buf, z, zm, prm.phi + (long long)p * 16 * NT, wn, gg.x);
+                if constexpr (VL == 2)
+                    OF::filter_all(buf, z, zm, prm.phi + (long long)p * 16 * NT, wn, gg.x);
+                else
+                    OF::pw_collect(buf, z, gg.x);
                 if (p == 0 && tid < 32) {
                     __syncwarp();
                     if constexpr (VL == 2) {
