@@ -281,96 +281,115 @@ struct DpTrigGroupParams {
 
 #ifndef DP_HOST_EMU
 #ifdef DP_TRIG_DEFINE_GROUP_KERNEL  // exactly one translation unit (dp_trig_inst.cu, float64)
+// inclusive scan over the 1024 threads of the CTA (warp shuffles + one shared exchange)
+__device__ __forceinline__ int dp_trig_scan1024(int v, int* s_warp /* [33] */, int& total) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // previous users of s_warp are done
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int x = s_warp[lane];
+        int ix = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, ix, o);
+            if (lane >= o) ix += t;
+        }
+        s_warp[lane] = ix - x;
+        if (lane == 31) s_warp[32] = ix;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return inc + s_warp[w];
+}
+
 // single CTA of 1024 threads; candidates are globally ordered by stream index
 __global__ void __launch_bounds__(1024, 1) dp_trig_group_kernel(const DpTrigGroupParams prm) {
     constexpr int NTG = 1024;
+    constexpr int OFF_CACHE = 1024;                  // chunk offsets kept in shared memory (binary search)
+    __shared__ long long s_coff[OFF_CACHE + 1];
     __shared__ long long s_off[NTG + 1];
     // slot 0 = group carried in from the previous tile, slots 1..1024 = groups that start in this tile
     __shared__ unsigned long long s_best[NTG + 1];   // ordered bits of |amp| per group
     __shared__ long long s_bidx[NTG + 1];            // smallest stream index attaining it
     __shared__ double s_bamp[NTG + 1];
-    __shared__ int s_scan[NTG];
+    __shared__ int s_warp[33];
     __shared__ long long s_carry_idx, s_prev_idx, s_total;
     __shared__ unsigned long long s_carry_best;
     __shared__ double s_carry_amp;
     __shared__ int s_open, s_nout;
     const int tid = threadIdx.x;
-    // 1) exclusive prefix of the chunk counts (sequential over tiles of 1024 chunks)
+    // 1) exclusive prefix of the chunk counts (tiles of 1024 chunks)
     if (tid == 0) s_total = 0;
     __syncthreads();
     for (int c0 = 0; c0 < prm.n_chunks; c0 += NTG) {
         const int c = c0 + tid;
         const int v = c < prm.n_chunks ? prm.cand_count[c] : 0;
-        s_scan[tid] = v;
-        __syncthreads();
-        for (int o = 1; o < NTG; o <<= 1) {
-            const int t = tid >= o ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += t;
-            __syncthreads();
+        int tot;
+        const int inc = dp_trig_scan1024(v, s_warp, tot);
+        if (c < prm.n_chunks) {
+            const long long o = s_total + inc - v;
+            prm.chunk_offset[c] = o;
+            if (c < OFF_CACHE) s_coff[c] = o;
         }
-        if (c < prm.n_chunks) prm.chunk_offset[c] = s_total + s_scan[tid] - v;
         __syncthreads();
-        if (tid == NTG - 1) s_total += s_scan[tid];
+        if (tid == 0) s_total += tot;
         __syncthreads();
     }
     if (tid == 0) {
         prm.chunk_offset[prm.n_chunks] = s_total;
+        if (prm.n_chunks <= OFF_CACHE) s_coff[prm.n_chunks] = s_total;
         s_open = 0;
         s_nout = 0;
         s_prev_idx = 0;
     }
     __syncthreads();
     const long long K = s_total;
+    const bool cached = prm.n_chunks <= OFF_CACHE;
     // 2) tiles of 1024 candidates
-    int chunk_lo = 0;  // first chunk that can contain candidate g0 (monotone)
     for (long long g0 = 0; g0 < K; g0 += NTG) {
         const long long g = g0 + tid;
         long long idx = 0;
         double amp = 0.0;
-        bool have = g < K;
+        const bool have = g < K;
         if (have) {
-            // chunk of candidate g: binary search in chunk_offset
-            int lo = chunk_lo, hi = prm.n_chunks - 1;
+            // chunk of candidate g: last chunk whose offset is <= g
+            int lo = 0, hi = prm.n_chunks - 1;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if (prm.chunk_offset[mid] <= g) lo = mid; else hi = mid - 1;
+                const long long om = cached ? s_coff[mid] : prm.chunk_offset[mid];
+                if (om <= g) lo = mid; else hi = mid - 1;
             }
-            const long long pos = g - prm.chunk_offset[lo];
+            const long long pos = g - (cached ? s_coff[lo] : prm.chunk_offset[lo]);
             idx = (long long)lo * prm.hop + prm.cand_idx[(long long)lo * prm.hop + pos];
             amp = prm.cand_amp[(long long)lo * prm.hop + pos];
-            if (tid == 0) chunk_lo = lo;
         }
-        chunk_lo = __shfl_sync(0xffffffffu, chunk_lo, 0);  // warp 0 only matters; others keep a valid lower bound
         s_off[tid + 1] = idx;
         if (tid == 0) s_off[0] = s_prev_idx;
         __syncthreads();
         const bool head = have && ((g == 0) || (idx - s_off[tid] > prm.pileup_window));
-        // tile-local group id = number of heads at or before this candidate
-        s_scan[tid] = head ? 1 : 0;
-        __syncthreads();
-        for (int o = 1; o < NTG; o <<= 1) {
-            const int t = tid >= o ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += t;
-            __syncthreads();
-        }
-        const int gid = s_scan[tid];              // 0: continues the carried group
-        const int ngroups = s_scan[NTG - 1];      // heads in this tile
+        // tile-local group id = number of heads at or before this candidate (0: continues the carried group)
+        int ngroups;
+        const int gid = dp_trig_scan1024(head ? 1 : 0, s_warp, ngroups);
         s_best[tid] = 0ull;
         s_bidx[tid] = 0x7fffffffffffffffll;
         if (tid == 0) {
             s_best[NTG] = 0ull;
             s_bidx[NTG] = 0x7fffffffffffffffll;
-        }
-        if (tid == 0 && s_open) {                 // slot 0 starts from the carried group
-            s_best[0] = s_carry_best;
-            s_bidx[0] = s_carry_idx;
-            s_bamp[0] = s_carry_amp;
+            if (s_open) {  // slot 0 starts from the carried group
+                s_best[0] = s_carry_best;
+                s_bidx[0] = s_carry_idx;
+                s_bamp[0] = s_carry_amp;
+            }
         }
         __syncthreads();
         const unsigned long long key = have ? (unsigned long long)__double_as_longlong(fabs(amp)) : 0ull;
-        // slot of a group: gid (slot 0 = carried group; tile groups 1..ngroups)
         if (have) atomicMax(&s_best[gid], key);
         __syncthreads();
         // a member beat the carried maximum: the carried index no longer counts
@@ -397,11 +416,10 @@ __global__ void __launch_bounds__(1024, 1) dp_trig_group_kernel(const DpTrigGrou
         __syncthreads();
         if (tid == 0) {
             s_nout += n_closed;
-            const int last = ngroups > 0 ? ngroups : 0;
             if (ngroups > 0 || s_open) {
-                s_carry_best = s_best[last];
-                s_carry_idx = s_bidx[last];
-                s_carry_amp = s_bamp[last];
+                s_carry_best = s_best[ngroups];
+                s_carry_idx = s_bidx[ngroups];
+                s_carry_amp = s_bamp[ngroups];
                 s_open = 1;
             }
             const long long nk = K - g0 < NTG ? K - g0 : NTG;
