@@ -54,6 +54,7 @@ SIGNATURES = {
     'dp_of_plan_get_template_fft': (_i, [_vp, _i, _i, _vp]),
     'dp_of1x1_batch': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _vp]),
     'dp_of1x1_batch_host': (_i, [_vp, _vp, _i, _ll, _ll, _vp]),
+    'dp_of1x1_windows': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _vp]),
     'dp_of_plan_last_kernel_ms': (_i, [_vp, _fp]),
     'dp_of_plan_launch_count': (_i, [_vp, C.POINTER(_ll)]),
     'dp_reduce_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i]),

@@ -25,7 +25,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3',
 # (precision, input type) in separate translation units so they compile in parallel
 UNITS = [('dp_capi', 'dp_capi.cu', [])] + [
     (f'dp_of2_inst_p{p}_{i}', 'dp_of2_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_IN={i}'])
-    for p in (1, 0) for i in (0, 1, 2)] + [
+    for p in (1, 0) for i in (0, 1, 2, 3)] + [
     (f'dp_trig_inst_p{p}', 'dp_trig_inst.cu', [f'-DDP_INST_PREC={p}']) for p in (1, 0)] + [
     (f'dp_of_inst_p{p}_{i}', 'dp_of_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_IN={i}'])
     for p in (1, 0) for i in (0, 1, 2)]

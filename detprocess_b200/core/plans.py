@@ -175,6 +175,25 @@ class OFPlan:
                                  self.nb_samples, C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
         return out
 
+    def run_windows(self, stream, start_index, out=None):
+        """Features of the windows ``stream[s : s + nb_samples]`` for every ``s`` in ``start_index`` (CUDA int64),
+        read straight from the continuous CUDA float64 ``stream`` -- no staging copy.  ``s = trigger_index -
+        nb_pretrigger_samples``.  Windows leaving the stream get -999999.0 in every column.  Async."""
+        torch = _torch()
+        if not self.finalized:
+            raise _lib.DetprocessB200Error('plan not finalized')
+        if not stream.is_cuda or stream.dtype != torch.float64 or stream.ndim != 1:
+            raise ValueError('run_windows() takes a 1-D float64 CUDA stream')
+        start_index = start_index.to(device=stream.device, dtype=torch.int64).contiguous()
+        stream = stream.contiguous()
+        nev = start_index.shape[0]
+        if out is None:
+            out = torch.empty((nev, self.n_out), dtype=torch.float64, device=stream.device)
+        check(lib.dp_of1x1_windows(self._h, C.c_void_p(stream.data_ptr()), stream.shape[0],
+                                   C.c_void_p(start_index.data_ptr()), nev, C.c_void_p(out.data_ptr()),
+                                   _stream_ptr(stream.device)))
+        return out
+
     def run_host(self, traces, out=None):
         """traces: host ndarray or (pinned) CPU tensor.  Returns ndarray [B, n_out].  Synchronous."""
         torch = _torch()

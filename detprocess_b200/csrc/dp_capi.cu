@@ -287,7 +287,7 @@ template <class T> int of2_finalize(dp_of_plan* p) {
     if ((rc = upload(p->owned, cd, &dcd))) return rc;
     p->d_chans = dcd;
     const int prec = sizeof(S) == 8 ? 0 : 1;
-    for (int in = 0; in < 3; ++in) {
+    for (int in = 0; in < 4; ++in) {
         size_t smem = 0;
         int grid_max = 0, occ = 0, threads = 0;
         const int src = dp_of2_setup_table[prec][in](p->v2_r1, p->device, &smem, &grid_max, &occ, &threads);
@@ -312,7 +312,7 @@ template <class T> int of2_finalize(dp_of_plan* p) {
 
 template <class T>
 int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride, double* out_dev,
-            cudaStream_t st, bool timed) {
+            cudaStream_t st, bool timed, const long long* row_start = nullptr, long long stream_len = 0) {
     using S = typename Dp2Traits<T>::S;
     Dp2Params<T> prm;
     std::memset(&prm, 0, sizeof(prm));
@@ -333,6 +333,8 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     prm.nlow = p->nlow;
     prm.scale = p->scale;
     prm.subtract_first = p->subtract_first;
+    prm.row_start = row_start;
+    prm.stream_len = stream_len;
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
     const int prec = sizeof(S) == 8 ? 0 : 1;
@@ -577,6 +579,23 @@ int dp_of1x1_batch(dp_of_plan* p, const void* traces_dev, int in_dtype, long lon
     if (n_events * p->n_chan > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return of_dispatch(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, true);
+}
+
+int dp_of1x1_windows(dp_of_plan* p, const double* stream_dev, long long n_stream_samples, const long long* start_index_dev,
+                     long long n_events, double* out_dev, void* stream) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (!p->v2_r1) return fail(DP_ERR_UNSUPPORTED, "window mode needs nb_samples 16384, 32768 or 65536");
+    if (p->n_chan != 1) return fail(DP_ERR_UNSUPPORTED, "window mode is single channel");
+    if (n_events < 0 || n_stream_samples < 0) return fail(DP_ERR_INVALID, "negative size");
+    if (n_events == 0) return DP_OK;
+    if (!stream_dev || !start_index_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(stream_dev) & 7) != 0) return fail(DP_ERR_INVALID, "stream buffer misaligned");
+    if (n_events > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // IN = 3: float64 rows that are only 8-byte aligned (a window may start at an odd sample)
+    if (p->precision == DP_PREC_F32)
+        return of2_run<f2>(p, stream_dev, 3, n_events, 0, out_dev, st, true, start_index_dev, n_stream_samples);
+    return of2_run<double>(p, stream_dev, 3, n_events, 0, out_dev, st, true, start_index_dev, n_stream_samples);
 }
 
 int dp_of_plan_last_kernel_ms(dp_of_plan* p, float* ms) {

@@ -198,6 +198,11 @@ template <class T> struct Dp2Params {
     int nlow;
     double scale;
     int subtract_first;
+    // window mode (single channel): event r is the N-sample window of one continuous stream that starts
+    // at sample row_start[r] (the step between the trigger and the features in the reference,
+    // processing_data.py:643-688); windows that stick out of [0, stream_len) get the -999999 sentinels
+    const long long* row_start;
+    long long stream_len;
 };
 
 // --------------------------------------------------------------------- helpers
@@ -283,6 +288,10 @@ template <int IN> DP_DEV typename DpRaw<IN>::type dp2_load_pair(const void* row,
     const typename DpRaw<IN>::type* ptr = reinterpret_cast<const typename DpRaw<IN>::type*>(row) + j;
     if constexpr (IN == 0) {
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(pol));
+    } else if constexpr (IN == 3) {
+        const double* p1 = reinterpret_cast<const double*>(row) + 2 * j;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v.x) : "l"(p1), "l"(pol));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v.y) : "l"(p1 + 1), "l"(pol));
     } else if constexpr (IN == 1) {
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(ptr), "l"(pol));
     } else {
@@ -681,7 +690,12 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
         const int nrow = row + gridDim.x;
         if (nrow < prm.n_rows) {
-            const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * ESZ;
+            long long first = (long long)nrow * prm.row_stride;
+            if (prm.row_start != nullptr) {
+                first = prm.row_start[nrow];
+                if (first < 0 || first + N > prm.stream_len) return;
+            }
+            const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)first * ESZ;
 #ifndef DP_HOST_EMU
             if ((reinterpret_cast<unsigned long long>(nx) & 15ull) == 0) {
                 if (threadIdx.x == 0)
@@ -834,7 +848,15 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
         evpar ^= 1;
         if (tid < CH_WORDS) chs[tid] = reinterpret_cast<const int*>(prm.chans + chan)[tid];
         const Dp2ChanDev<T>& ch = *reinterpret_cast<const Dp2ChanDev<T>*>(chs);
-        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
+        long long first = (long long)row * prm.row_stride;
+        if (prm.row_start != nullptr) {
+            first = prm.row_start[row];
+            if (first < 0 || first + N > prm.stream_len) {  // CTA-uniform
+                for (int o = tid; o < prm.n_out; o += NT) prm.out[(long long)ev * prm.n_out + o] = -999999.0;
+                continue;
+            }
+        }
+        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)first * ESZ;
         const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
         S chi = (S)0;
 

@@ -171,9 +171,15 @@ template <int IN> struct DpRaw;
 template <> struct DpRaw<0> { using type = double2; using scalar = double; };
 template <> struct DpRaw<1> { using type = float2; using scalar = float; };
 template <> struct DpRaw<2> { using type = short2; using scalar = short; };
+template <> struct DpRaw<3> { using type = double2; using scalar = double; };  // float64, rows only 8-byte aligned
 
 template <int IN> DP_DEV typename DpRaw<IN>::type dp_load_raw(const void* row, long long j) {
-    return __ldg(reinterpret_cast<const typename DpRaw<IN>::type*>(row) + j);
+    if constexpr (IN == 3) {
+        const double* p = reinterpret_cast<const double*>(row) + 2 * j;
+        return make_double2(__ldg(p), __ldg(p + 1));
+    } else {
+        return __ldg(reinterpret_cast<const typename DpRaw<IN>::type*>(row) + j);
+    }
 }
 template <class T, int IN> DP_DEV cx<T> dp_convert_raw(typename DpRaw<IN>::type d, double x0, double sc) {
     return cx<T>{(T)(((double)d.x - x0) * sc), (T)(((double)d.y - x0) * sc)};

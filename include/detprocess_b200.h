@@ -113,6 +113,16 @@ int dp_of1x1_batch(dp_of_plan* plan, const void* traces_dev, int in_dtype, long 
 /* Host-buffer convenience used by the plugin layer and the end-to-end benchmark:
  * copies traces_host (pageable or pinned) to the device in chunks on two streams,
  * runs the batch and copies the feature table back.  Synchronous. */
+/* Window mode: event i is the nb_samples window of ONE continuous float64 stream that starts at sample
+ * start_index_dev[i] -- what ProcessingData.read_next_event does with a trigger dataframe row
+ * (detprocess/process/processing_data.py:643-688: read_single_event(trigger_index, trace_length_samples,
+ * pretrigger_length_samples)), fused into the kernel's trace load so the [n_events][nb_samples] staging copy
+ * never exists.  start = trigger_index - nb_pretrigger_samples; windows that leave [0, n_stream_samples) get
+ * -999999.0 in every output column.  Single channel, nb_samples 16384 / 32768 / 65536.
+ */
+int dp_of1x1_windows(dp_of_plan* plan, const double* stream_dev, long long n_stream_samples,
+                     const long long* start_index_dev, long long n_events, double* out_dev, void* stream);
+
 int dp_of1x1_batch_host(dp_of_plan* plan, const void* traces_host, int in_dtype, long long n_events,
                         long long row_stride, double* out_host);
 
