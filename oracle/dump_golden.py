@@ -1,0 +1,62 @@
+"""
+Close the "parity unpinned" loop where the real reference stack is installed.
+
+    python oracle/dump_golden.py tests/golden/of1x1_qetpy.npz
+
+Runs UPSTREAM QETpy (``qetpy>=1.8.6``, the package detprocess delegates the OF maths to,
+reference setup.py:73) on the seeded synthetic inputs of ``detprocess_b200.synth`` through exactly the
+calls the reference makes (processing_data.py:278-381, 731-772; algorithms.py:331-341, 410-421, 533-558;
+noise.py:344) and stores inputs' seeds + outputs.  ``tests/test_oracle_of.py::test_against_qetpy_golden``
+compares ``oracle/of1x1.py`` with the file when it exists (it is skipped otherwise).  QETpy is NOT
+available in this build environment (no network), so the file is not committed: the oracle stays
+pinned by its known-answer tests only, as stated in DESIGN.md section 2.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from detprocess_b200.synth import SynthSetup, make_traces  # noqa: E402
+
+
+def main(out_path, nb_samples=4096, n_events=16, seed=12345):
+    try:
+        import qetpy as qp
+    except ImportError as e:                                           # pragma: no cover
+        raise SystemExit(f'qetpy is not installed here ({e}); run this where detprocess+QETpy are available')
+    S = SynthSetup(nb_samples)
+    pre = S.nb_pretrigger
+    traces = make_traces(n_events, S.template, S.psd, S.fs, np.random.default_rng(seed))
+    ofb = qp.OFBase(S.fs)
+    ofb.set_csd('ch', S.psd, coupling='AC')
+    ofb.add_template('ch', S.template, template_tag='default', pretrigger_samples=pre)
+    ofb.calc_phi('ch', template_tag='default')
+    res = {k: [] for k in ('amp_nodelay', 'chi2_nodelay', 'amp_un', 't0_un', 'chi2_un', 'lowchi2_un',
+                           'amp_con', 't0_con', 'chi2_con', 'chi2nopulse', 'ampres', 'timeres')}
+    for x in traces:
+        ofb.clear_signal()
+        ofb.update_signal('ch', x, calc_fft=True)
+        ofb.calc_signal_filt('ch')
+        ofb.calc_signal_filt_td('ch')
+        OF = qp.OF1x1(of_base=ofb, channel='ch', template_tag='default')
+        OF.calc(lowchi2_fcutoff=10000, lgc_fit_withdelay=False, lgc_fit_nodelay=True)
+        a, _, c, _ = OF.get_result_nodelay()
+        res['amp_nodelay'].append(a), res['chi2_nodelay'].append(c)
+        OF.calc(lowchi2_fcutoff=10000, lgc_fit_withdelay=True, lgc_fit_nodelay=False)
+        a, t, c, lc = OF.get_result_withdelay()
+        res['amp_un'].append(a), res['t0_un'].append(t), res['chi2_un'].append(c), res['lowchi2_un'].append(lc)
+        OF.calc(window_min_index=pre - 500, window_max_index=pre + 500, lowchi2_fcutoff=10000,
+                lgc_fit_withdelay=True, lgc_fit_nodelay=False)
+        a, t, c, _ = OF.get_result_withdelay()
+        res['amp_con'].append(a), res['t0_con'].append(t), res['chi2_con'].append(c)
+        res['chi2nopulse'].append(OF.get_chisq_nopulse())
+        res['ampres'].append(OF.get_energy_resolution()), res['timeres'].append(OF.get_time_resolution())
+    freqs, psd = qp.calc_psd(traces, fs=S.fs, folded_over=False)
+    np.savez(out_path, nb_samples=nb_samples, n_events=n_events, seed=seed, qetpy_version=getattr(qp, '__version__', '?'),
+             psd_of_traces=psd, **{k: np.asarray(v) for k, v in res.items()})
+    print('wrote', out_path)
+
+
+if __name__ == '__main__':
+    main(sys.argv[1] if len(sys.argv) > 1 else 'tests/golden/of1x1_qetpy.npz')

@@ -109,3 +109,24 @@ def test_outside_window_and_integralnorm(setup):
     # integralnorm rescales the template by 1/s[0]: amplitude scales by s[0]
     s0 = np.fft.fft(S.template)[0] / S.nb_samples / (S.fs / S.nb_samples)
     assert o2['amp'][0, 0] == pytest.approx(2.0 * s0.real, rel=1e-9)
+
+
+def test_against_qetpy_golden():
+    """Upstream parity, where someone has run oracle/dump_golden.py with real QETpy (file not committed here)."""
+    import os
+    import pytest
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'of1x1_qetpy.npz')
+    if not os.path.exists(path):
+        pytest.skip('tests/golden/of1x1_qetpy.npz not present: QETpy is not installable in this environment')
+    g = np.load(path)
+    from detprocess_b200.synth import SynthSetup, make_traces
+    from oracle.of1x1 import of1x1_batch
+    S = SynthSetup(int(g['nb_samples']))
+    pre = S.nb_pretrigger
+    tr = make_traces(int(g['n_events']), S.template, S.psd, S.fs, np.random.default_rng(int(g['seed'])))
+    o = of1x1_batch(tr, S.template, S.psd, S.fs, pre, windows=[(pre, pre + 1, False), (None, None, False), (pre - 500, pre + 500, False)])
+    assert np.allclose(o['amp'][0], g['amp_nodelay'], rtol=1e-9)
+    assert np.allclose(o['amp'][1], g['amp_un'], rtol=1e-9)
+    assert np.allclose((o['ind'][1] - pre) / S.fs, g['t0_un'], rtol=0, atol=1e-12)
+    assert np.allclose(o['amp'][2], g['amp_con'], rtol=1e-9)
+    assert np.allclose(o['chi2'][1], g['chi2_un'], rtol=1e-9)
