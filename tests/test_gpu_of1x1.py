@@ -68,6 +68,7 @@ def _compare(plan, fit, out, o, iw, tol, amp_floor):
 
 
 @pytest.mark.parametrize('precision,nb_samples', [('f64', 2048), ('f64', 4096), ('f64', 16384), ('f64', 32768),
+                                                  ('f64', 65536), ('f64', 8192),
                                                   ('f32', 2048), ('f32', 8192), ('f32', 16384), ('f32', 32768),
                                                   ('f32', 65536)])
 def test_of1x1_parity_single_template(precision, nb_samples):
@@ -154,6 +155,53 @@ def test_of1x1_two_channels_sharded_equals_single():
     off1 = plan.fit_offset(1, f1)
     assert np.array_equal(out[:, off1 + 1].astype(int), o1['ind'][0])
     assert np.max(np.abs(out[:, off1] - o1['amp'][0]) / np.maximum(np.abs(o1['amp'][0]), 5 * o1['ampres'])) < 1e-9
+
+
+@pytest.mark.parametrize('precision', ['f64', 'f32'])
+def test_of1x1_c3_shape_eight_channels_16384(precision):
+    """BASELINE config C3: 8 channels x 16384 samples, every channel with its own PSD / templates / fits;
+    float32 and int16 trace buffers give the same numbers as float64 ones (v2 kernels)."""
+    import torch
+    from detprocess_b200.core.plans import OFPlan
+    n, nch, nev = 16384, 8, 40
+    S = SynthSetup(n)
+    pre = S.nb_pretrigger
+    rng = np.random.default_rng(77)
+    traces = np.stack([make_traces(nev, S.template if c % 2 == 0 else S.template_glitch, S.psd * (1 + c), S.fs, rng)
+                       for c in range(nch)], axis=1)
+    plan = OFPlan(n, S.fs, nch, precision)
+    fits = []
+    for c in range(nch):
+        plan.set_psd(c, S.psd * (1 + c))
+        t0 = plan.add_template(c, S.template, pre)
+        f = [plan.add_fit(c, t0, pre - 500, pre + 500), plan.add_fit_nodelay(c, t0)]
+        if c % 2:
+            t1 = plan.add_template(c, S.template_glitch, pre)
+            f.append(plan.add_fit(c, t1, None, None))
+        fits.append(f)
+    plan.finalize()
+    out = plan.run(torch.from_numpy(traces).cuda()).cpu().numpy()
+    tol = TOL[precision]
+    for c in range(nch):
+        o = of1x1_batch(traces[:, c], S.template, S.psd * (1 + c), S.fs, pre, windows=[(pre - 500, pre + 500, False), (pre, pre + 1, False)])
+        off = plan.fit_offset(c, fits[c][0])
+        assert (out[:, off + 1].astype(np.int64) == o['ind'][0]).mean() > (0.99 if precision == 'f32' else 0.9999)
+        den = np.maximum(np.abs(o['amp'][0]), 5 * o['ampres'])
+        assert np.max(np.abs(out[:, off] - o['amp'][0]) / den) < tol['amp'] * (20 if precision == 'f32' else 1)
+        assert np.max(np.abs(out[:, plan.chi0_offset(c)] / o['chi0'] - 1)) < tol['chi2']
+        if c % 2:
+            og = of1x1_batch(traces[:, c], S.template_glitch, S.psd * (1 + c), S.fs, pre, windows=[(None, None, False)])
+            offg = plan.fit_offset(c, fits[c][2])
+            deng = np.maximum(np.abs(og['amp'][0]), 5 * og['ampres'])
+            same = out[:, offg + 1].astype(np.int64) == og['ind'][0]
+            assert same.mean() > 0.97
+            assert np.max((np.abs(out[:, offg] - og['amp'][0]) / deng)[same]) < tol['amp'] * (20 if precision == 'f32' else 1)
+    # exactly representable samples: f32 and i16 buffers == f64 buffer
+    adc = rng.integers(-2000, 2000, size=(6, nch, n)).astype(np.int16)
+    ref = plan.run(torch.from_numpy(adc.astype(np.float64)).cuda()).cpu().numpy()
+    for dt in (torch.float32, torch.int16):
+        got = plan.run(torch.from_numpy(adc.astype(np.float64)).to(dt).cuda()).cpu().numpy()
+        assert np.array_equal(got, ref)
 
 
 def test_of1x1_empty_and_ragged_batches():
