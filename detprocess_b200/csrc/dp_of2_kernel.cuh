@@ -103,56 +103,61 @@ template <class T, int R1_> struct Dp2Geom {
         const int b = G >> 8, k2 = (G >> 4) & 15, k3 = G & 15;
         return k1_of(p, b) + R1 * (k2 + 16 * k3 + 256 * r);
     }
-    // i-th (g, g') pair of phase p.  Pair 0 of phase 0 is the special one: both groups
-    // ((0,0,0) and (0,0,8) of block 0) are self-paired.
-    static DP_HD void pair_of(int p, int i, int& GA, int& GB) {
-        for (int b = 0; b < NB; ++b) {
-            const int mb = mirror_b(p, b);
-            if (mb < b) continue;
-            const int k1 = k1_of(p, b);
-            if (mb > b) {
-                if (i < 256) {
-                    const int k2 = i >> 4, k3 = i & 15;
-                    GA = b * 256 + k2 * 16 + k3;
-                    GB = mb * 256 + (15 - k2) * 16 + (15 - k3);
-                    return;
-                }
-                i -= 256;
-            } else {
-                if (i < 128) {
-                    int k2, k3, k2m, k3m;
-                    if (k1 != 0) {
-                        k2 = i >> 4, k3 = i & 15, k2m = 15 - k2, k3m = 15 - k3;
-                    } else if (i == 0) {
-                        k2 = 0, k3 = 0, k2m = 0, k3m = 8;
-                    } else if (i < 8) {
-                        k2 = 0, k3 = i, k2m = 0, k3m = 16 - i;
-                    } else if (i < 16) {
-                        k2 = 8, k3 = i - 8, k2m = 8, k3m = 15 - k3;
-                    } else {
-                        k2 = i >> 4, k3 = i & 15, k2m = 16 - k2, k3m = 15 - k3;
-                    }
-                    GA = b * 256 + k2 * 16 + k3;
-                    GB = b * 256 + k2m * 16 + k3m;
-                    return;
-                }
-                i -= 128;
-            }
-        }
-        GA = GB = -1;
-    }
-    // groups of thread t in phase p: VL == 2: (GA, GB) of pair t; VL == 1: own group and the
-    // partner's (thread t ^ 1)
-    static DP_HD void groups_of(int p, int t, int& Gown, int& Gother) {
-        if (VL == 2) {
-            pair_of(p, t, Gown, Gother);
+    // Threads are tied to blocks: in passes 2, 3 (and 3', 2') thread t works on local block t / CV.  Pass 4 and
+    // the point-wise stage work on (group, mirror group) pairs; pair -> thread assignment keeps every thread
+    // inside its own mirror-closed block set {b, mirror_b(b)}, so between pass 1 and pass 1' the sets only
+    // ever touch their own part of the shared buffer and synchronise with NAMED barriers (block / set) --
+    // the sets drift apart and overlap each other's shared-memory, FP and global-latency phases.
+    //
+    // i-th pair of a self-mirrored block (128 pairs) / of a swapped block pair (256 pairs): (k2,k3) of the
+    // group in the lower block and of its mirror.  Pair 0 of block k1 = 0 is the special one: both groups
+    // ((0,0,0) and (0,0,8)) are self-paired.
+    static DP_HD void self_pair(bool k1_zero, int i, int& gA, int& gB) {
+        int k2, k3, k2m, k3m;
+        if (!k1_zero) {
+            k2 = i >> 4, k3 = i & 15, k2m = 15 - k2, k3m = 15 - k3;
+        } else if (i == 0) {
+            k2 = 0, k3 = 0, k2m = 0, k3m = 8;
+        } else if (i < 8) {
+            k2 = 0, k3 = i, k2m = 0, k3m = 16 - i;
+        } else if (i < 16) {
+            k2 = 8, k3 = i - 8, k2m = 8, k3m = 15 - k3;
         } else {
-            int GA, GB;
-            pair_of(p, t >> 1, GA, GB);
-            Gown = (t & 1) ? GB : GA;
-            Gother = (t & 1) ? GA : GB;
+            k2 = i >> 4, k3 = i & 15, k2m = 16 - k2, k3m = 15 - k3;
         }
+        gA = k2 * 16 + k3;
+        gB = k2m * 16 + k3m;
     }
+    // groups of thread t in phase p: VL == 2: (GA, GB) lanes; VL == 1: own group and the partner's (thread t ^ 1)
+    static DP_HD void groups_of(int p, int t, int& Gown, int& Gother) {
+        const int b = t / CV, u = t % CV, mb = mirror_b(p, b);
+        int GA, GB, side = 0, i;
+        if (mb == b) {
+            i = (VL == 2) ? u : (u >> 1);
+            side = (VL == 2) ? 0 : (u & 1);
+            int gA, gB;
+            self_pair(k1_of(p, b) == 0, i, gA, gB);
+            GA = b * 256 + gA;
+            GB = b * 256 + gB;
+        } else {
+            const int lo = b < mb ? b : mb, hi = b < mb ? mb : b;
+            const int o = (b == lo ? 0 : CV) + u;  // ordinal inside the two-block set
+            i = (VL == 2) ? o : (o >> 1);
+            side = (VL == 2) ? 0 : (o & 1);
+            const int k2 = i >> 4, k3 = i & 15;
+            GA = lo * 256 + k2 * 16 + k3;
+            GB = hi * 256 + (15 - k2) * 16 + (15 - k3);
+        }
+        Gown = side ? GB : GA;
+        Gother = side ? GA : GB;
+    }
+    // named barriers of thread t in phase p: its block (CV threads) and its mirror-closed block set
+    static DP_HD int bar_block_id(int t) { return 1 + t / CV; }
+    static DP_HD int bar_set_id(int p, int t) {
+        const int b = t / CV, mb = mirror_b(p, b);
+        return 1 + NB + (b < mb ? b : mb);
+    }
+    static DP_HD int bar_set_count(int p, int t) { return mirror_b(p, t / CV) == t / CV ? CV : 2 * CV; }
 };
 
 // --------------------------------------------------------------- device tables
@@ -422,7 +427,7 @@ template <class T, int R1, int IN> struct Dp2Core {
 
     // ---- passes 2..4 (caller has synchronised after pass 1); result: pass-4 outputs of the
     // thread's group(s) in z[16] (VL == 2: lane 0 = group GA, lane 1 = group GB)
-    static DP_DEV void fwd_234(V* buf, const V* DP_RESTRICT tw2, const V* DP_RESTRICT tw3, int GA, int GB, V (&z)[16]) {
+    static DP_DEV void fwd_234(V* buf, const V* DP_RESTRICT tw2, const V* DP_RESTRICT tw3, int GA, int GB, V (&z)[16], int p) {
         const int tid = threadIdx.x;
         {
             const int b = tid / CV, cc = tid % CV;
@@ -434,7 +439,7 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
             for (int k = 0; k < 16; ++k) pb[k * PC] = z[k];
         }
-        __syncthreads();
+        dp_bar_sync(G::bar_block_id(tid), CV);  // pass 3 reads what the threads of this block wrote
         {
             const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV;
             V* pb = buf + G::phys(b * VPB + k2 * CV + q);
@@ -445,7 +450,7 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
             for (int k = 0; k < 16; ++k) pb[k * PG] = z[k];
         }
-        __syncthreads();
+        dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 4 reads the thread's block and its mirror block
         load_groups(buf, GA, GB, z);
         dp_dft<16, -1, T>::run(z);
     }
@@ -486,11 +491,11 @@ template <class T, int R1, int IN> struct Dp2Core {
 
     // ---- inverse passes 4', 3', 2': consumes group values z; leaves the pass-2' outputs of
     // column (b, cc) in z[n2] (V index b*VPB + n2*CV + cc).  No trailing barrier.
-    static DP_DEV void inv_432(V* buf, const V* DP_RESTRICT tw2, const V* DP_RESTRICT tw3, int GA, int GB, V (&z)[16]) {
+    static DP_DEV void inv_432(V* buf, const V* DP_RESTRICT tw2, const V* DP_RESTRICT tw3, int GA, int GB, V (&z)[16], int p) {
         const int tid = threadIdx.x;
         dp_dft<16, +1, T>::run(z);
         store_groups(buf, GA, GB, z);
-        __syncthreads();
+        dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));
         {
             const int q = tid % GV, k2 = (tid / GV) % 16, b = tid / CV;
             V* pb = buf + G::phys(b * VPB + k2 * CV + q);
@@ -501,7 +506,7 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
             for (int n = 0; n < 16; ++n) pb[n * PG] = z[n];
         }
-        __syncthreads();
+        dp_bar_sync(G::bar_block_id(tid), CV);
         {
             const int b = tid / CV, cc = tid % CV;
             const V* pb = buf + G::phys(b * VPB + cc);
@@ -870,7 +875,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             const bool special = (p == 0) && (tid < NSPECIAL);
             Core::pass1_any(p, xrow, x0, prm.scale, sm.buf, prm.tw1);
             __syncthreads();
-            Core::fwd_234(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+            Core::fwd_234(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
             if (p == 0 && tid < 32) {
                 // self-paired groups -> 17 lanes of warp 0
                 if constexpr (VL == 2) {
@@ -998,7 +1003,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     }
                     __syncwarp();
                 }
-                Core::inv_432(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                Core::inv_432(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                 if (p < NPH - 1) {
                     Core::park_pass2(park, p, z);
                     __syncthreads();  // pass-2' reads of buf precede the next group / pass-1 stores

@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -35,6 +37,8 @@ struct Cta {
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
     std::vector<uint64_t> slots;  // [nthreads]
+    std::map<std::pair<int, int>, std::unique_ptr<std::barrier<>>> named;  // bar.sync (id, count), created on first use
+    std::mutex named_mu;
     explicit Cta(int nt) : nthreads(nt), slots(nt) {
         bar = std::make_unique<std::barrier<>>(nt);
         for (int w = 0; w < (nt + 31) / 32; ++w) {
@@ -54,6 +58,18 @@ extern thread_local dp_dim3 tIdx, bIdx, bDim, gDim;
 
 static inline void __syncthreads() { dpemu::cta->bar->arrive_and_wait(); }
 static inline void __syncwarp() { dpemu::cta->warp_bar[dpemu::tIdx.x / 32]->arrive_and_wait(); }
+// named barrier: `count` threads of the CTA meet at barrier `id` (1..15)
+static inline void dp_bar_sync(int id, int count) {
+    auto* c = dpemu::cta;
+    std::barrier<>* b;
+    {
+        std::lock_guard<std::mutex> g(c->named_mu);
+        auto& slot = c->named[{id, count}];
+        if (!slot) slot = std::make_unique<std::barrier<>>(count);
+        b = slot.get();
+    }
+    b->arrive_and_wait();
+}
 
 template <class V>
 static inline V dp_shfl_impl(V v, int src_lane) {
@@ -93,6 +109,8 @@ static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 #define DP_HD __host__ __device__ __forceinline__
 #define DP_GLOBAL __global__
 #define DP_RESTRICT __restrict__
+// named barrier: `count` threads (a multiple of 32) of the CTA meet at barrier `id` (1..15)
+__device__ __forceinline__ void dp_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 #endif
 
 // ------------------------------------------------------------- scalar type traits

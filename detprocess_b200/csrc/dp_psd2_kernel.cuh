@@ -62,7 +62,7 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
                 const bool special = (p == 0) && (tid < NSPECIAL);
                 Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
                 __syncthreads();
-                Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                 if (p == 0 && tid < 32) {
                     if constexpr (VL == 2) {
                         if (tid == 0) {

@@ -112,7 +112,7 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                 else
                     Core::template pass1_any<false>(p, xrow, x0, prm.scale, buf, prm.tw1);
                 __syncthreads();
-                Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                 if (p == 0 && tid < 32) {
                     if constexpr (VL == 2) {
                         if (tid == 0) {
@@ -175,7 +175,7 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                     }
                     __syncwarp();
                 }
-                Core::inv_432(buf, prm.tw2, prm.tw3, gg.x, gg.y, z);
+                Core::inv_432(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                 if (p < NPH - 1) {
                     Core::park_pass2(park, p, z);
                     __syncthreads();
