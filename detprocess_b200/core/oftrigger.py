@@ -72,7 +72,7 @@ class TriggerPlan:
         check(lib.dp_trigger_plan_set_scale(self._h, float(typical_rms)))
 
     def run(self, trace, chi2_threshold, pileup_window_samples=0, index_shift=0, padding=True, max_triggers=65536):
-        """trace: CUDA float64 [L] (L even).  Returns (index int64 [n], amplitude [n], delta_chi2 [n]) CUDA tensors."""
+        """trace: CUDA float64 [L].  Returns (index int64 [n], amplitude [n], delta_chi2 [n]) CUDA tensors."""
         torch = _torch()
         if not trace.is_cuda or trace.dtype != torch.float64 or trace.ndim != 1:
             raise ValueError('run() takes a 1-D float64 CUDA tensor')
@@ -158,8 +158,6 @@ class OptimumFilterTrigger:
             if trace.shape[0] != 1:
                 raise ValueError(f'ERROR: "trace" has shape {tuple(trace.shape)}, but we have 1 channels!')
             trace = trace[0]
-        if trace.shape[0] % 2:
-            trace = trace[:-1]
         self._trace = trace
         self._padding = bool(padding)
 

@@ -1283,7 +1283,6 @@ int dp_trigger_run(dp_trigger_plan* p, const double* trace_dev, long long n_samp
     if (!p) return fail(DP_ERR_INVALID, "null plan");
     if (!trace_dev || !trig_index_dev || !trig_amp_dev || !trig_dchi2_dev || !n_triggers_dev) return fail(DP_ERR_INVALID, "null buffer");
     if (n_samples < 2 || n_samples > p->max_samples) return fail(DP_ERR_INVALID, "n_samples out of the plan's range");
-    if (n_samples & 1) return fail(DP_ERR_INVALID, "n_samples must be even");
     if ((reinterpret_cast<uintptr_t>(trace_dev) & 15) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
     if (max_triggers < 0 || pileup_window_samples < 0) return fail(DP_ERR_INVALID, "negative argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -330,16 +330,21 @@ template <int IN, int VL> DP_DEV Dp2Raw<IN, VL> dp2_load_raw(const void* row, in
 // stream base, jbase the (possibly negative) pair index of the chunk start; out-of-range
 // pairs read as zero (zero-padded linear convolution, like scipy's oaconvolve)
 template <int IN, int VL>
-DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, long long jmax, int n1, int c, unsigned long long pol) {
+DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, long long n_samples, int n1, int c, unsigned long long pol) {
     Dp2Raw<IN, VL> r;
     const long long j0 = jbase + (long long)n1 * 4096 + (long long)VL * c;
 #pragma unroll
     for (int l = 0; l < VL; ++l) {
         const long long j = j0 + l;
-        typename DpRaw<IN>::type zero;
-        zero.x = 0;
-        zero.y = 0;
-        r.q[l] = (j < 0 || j > jmax) ? zero : dp2_load_pair<IN>(row, j, pol);
+        typename DpRaw<IN>::type v;
+        v.x = 0;
+        v.y = 0;
+        if (j >= 0 && 2 * j + 1 < n_samples) {
+            v = dp2_load_pair<IN>(row, j, pol);
+        } else if (j >= 0 && 2 * j < n_samples) {  // last sample of an odd-length stream
+            v.x = reinterpret_cast<const typename DpRaw<IN>::scalar*>(row)[2 * j];
+        }
+        r.q[l] = v;
     }
     return r;
 }
@@ -370,7 +375,8 @@ template <class T, int R1, int IN> struct Dp2Core {
     static constexpr int PG = GV + 1, PC = CV + CV / GV, PB = VPB + VPB / GV;
 
     // ---- pass 1 of phase PH: global -> radix-R1 over n1 (only the phase's blocks) -> twiddle -> smem
-    // CLAMP: `row` is a stream base and (jbase, jmax) place / bound the chunk (dp2_load_raw_clamped)
+    // CLAMP: `row` is a stream base of n_samples samples and jbase the (possibly negative) pair index of
+    // the chunk start (dp2_load_raw_clamped)
     template <int PH, bool CLAMP = false>
     static DP_DEV void pass1(const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1, long long jbase = 0,
                              long long jmax = 0) {

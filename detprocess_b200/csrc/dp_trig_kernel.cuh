@@ -88,7 +88,7 @@ template <class T, int R1, int IN> struct DpTrigKernel {
         constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
         V* park = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
         const S wS = (S)prm.w, thrS = (S)prm.thr;
-        const long long jmax = prm.n_samples / 2 - 1;
+        const long long jmax = prm.n_samples;  // the clamped loader bounds by the sample count
 
         for (int q = blockIdx.x; q < prm.n_chunks; q += gridDim.x) {
             const long long s0 = (long long)q * prm.hop - prm.lead;  // first sample of the chunk (even)

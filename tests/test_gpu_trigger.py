@@ -24,7 +24,7 @@ def _oracle(trig, x, thresh, window, padding=True):
 
 
 @pytest.mark.parametrize('nt,L,pre', [(4096, 300_000, 2048), (16384, 400_000, 8192), (32768, 700_000, 16000),
-                                      (5000, 250_000, 2000)])
+                                      (5000, 250_000, 2000), (4095, 123_457, 1000)])
 def test_trigger_f64_matches_oracle(nt, L, pre):
     from detprocess_b200.core.oftrigger import OptimumFilterTrigger
     fs, template, psd, x = _make(nt, L, 3, offset=2e-7)
@@ -45,7 +45,7 @@ def test_trigger_f64_matches_oracle(nt, L, pre):
 def test_trigger_dense_candidates_and_no_padding():
     """1-sigma threshold: a third of all samples are candidates (ordered compaction + grouping under load)."""
     from detprocess_b200.core.oftrigger import OptimumFilterTrigger
-    nt, L = 4096, 120_000
+    nt, L = 4096, 120_001          # odd stream length
     fs, template, psd, x = _make(nt, L, 5)
     trig = OptimumFilterTrigger('ch', fs, template, psd, nt // 2, max_samples=L)
     for padding in (True, False):
