@@ -325,10 +325,8 @@ def gpu_main(a):
         plan = build_plan(S, prec)
         out = torch.empty((B, plan.n_out), dtype=torch.float64, device=device)
         if prec == 'f64' and sampler:
-            sampler.start()
+            sampler.start()         # samples clocks / throttle reasons over every timed region below
         ms, kms = time_steps(plan, x, out, a.steps, a.warmup, dist, world)
-        if prec == 'f64' and sampler:
-            sampler.stop_flag = True
         kms_avg = float(np.mean(kms))
         results[prec] = {'ms_total': ms, 'ms_per_step': ms / a.steps, 'value': world * B * a.steps / (ms * 1e-3),
                          'kernel_ms': kms_avg, 'achieved_gbs': B * BYTES_PER_EVENT / (kms_avg * 1e-3) / 1e9,
@@ -363,6 +361,8 @@ def gpu_main(a):
     ex = None
     if not a.no_extras:
         ex = extras(device, dist, world, hbm_peak)
+    if sampler:
+        sampler.stop_flag = True
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -26,10 +26,6 @@
 #include "dp_f2.cuh"
 #include "dp_of_kernel.cuh"
 
-#ifndef DP2_TBL_BATCH
-#define DP2_TBL_BATCH 8
-#endif
-
 template <class T> struct Dp2Traits;
 template <> struct Dp2Traits<double> {
     using S = double;
@@ -211,14 +207,6 @@ template <class T> struct Dp2Params {
 };
 
 // --------------------------------------------------------------------- helpers
-// compiler-level fence: keeps ptxas from hoisting the next batch of table loads above the
-// work in front of it (the hoisted loads otherwise push the 16 register-resident points
-// into local memory; there is no L1 left to catch those spills)
-DP_DEV void dp2_sched_fence() {
-#ifndef DP_HOST_EMU
-    asm volatile("" ::: "memory");
-#endif
-}
 template <class T> DP_DEV cx<T> dp2_csq(cx<T> a) { return cx<T>{dp_fma(a.re, a.re, -(a.im * a.im)), (a.re + a.re) * a.im}; }
 
 // powers w^0..w^(R-1) (only the used ones survive dead-code elimination)
@@ -745,14 +733,7 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
             f2 acc = f2(0.0f);
             if constexpr (WITH_CHI) {
 #pragma unroll
-            for (int h = 0; h < 16; h += DP2_TBL_BATCH) {
-                dp2_sched_fence();
-                f2 w[DP2_TBL_BATCH];
-#pragma unroll
-                for (int j = 0; j < DP2_TBL_BATCH; ++j) w[j] = dp_ldg(wj + (h + j) * NT + tid);
-#pragma unroll
-                for (int j = 0; j < DP2_TBL_BATCH; ++j) acc = dp_fma(w[j], cnorm2(z[h + j]), acc);
-            }
+                for (int r = 0; r < 16; ++r) acc = dp_fma(dp_ldg(wj + r * NT + tid), cnorm2(z[r]), acc);
             }
             chi = acc.x + acc.y;
         } else {
@@ -770,14 +751,7 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
             (void)Gown;
             (void)buf;
 #pragma unroll
-            for (int h = 0; h < 16; h += DP2_TBL_BATCH) {
-                dp2_sched_fence();
-                V ph[DP2_TBL_BATCH];
-#pragma unroll
-                for (int j = 0; j < DP2_TBL_BATCH; ++j) ph[j] = dp_ldg(phi + (h + j) * NT + tid);
-#pragma unroll
-                for (int j = 0; j < DP2_TBL_BATCH; ++j) z[h + j] = cmul(ph[j], z[h + j]);
-            }
+            for (int r = 0; r < 16; ++r) z[r] = cmul(dp_ldg(phi + r * NT + tid), z[r]);
 #define DP2_FP(r)                                                                          \
     {                                                                                      \
         cx<S> Ck, Cm;                                                                      \
