@@ -100,6 +100,7 @@ static inline V __ldg(const V* p) { return *p; }
 static inline void sincospi(double a, double* s, double* c) { *s = std::sin(M_PI * a); *c = std::cos(M_PI * a); }
 static inline void sincospif(float a, float* s, float* c) { *s = (float)std::sin(M_PI * (double)a); *c = (float)std::cos(M_PI * (double)a); }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
 #else
 // ------------------------------------------------------------------------- CUDA

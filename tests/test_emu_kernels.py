@@ -84,6 +84,27 @@ def test_of_v2_kernel_emulated(nb_samples, precision):
     _check(out, o2, [16], *tol)
 
 
+@pytest.mark.parametrize('nb_samples,precision', [(16384, 'f32'), (32768, 'f64'), (65536, 'f32')])
+def test_of_v2_kernel_emulated_constrained_only(nb_samples, precision):
+    """C2 shape (only constrained fits): exercises the pruned inverse (pass 2' evaluated for the one or two
+    outputs a +-500-sample window needs, pass 1' for the columns it touches)."""
+    S = SynthSetup(nb_samples)
+    pre = S.nb_pretrigger
+    tr = make_traces(3, S.template, S.psd, S.fs, np.random.default_rng(6),
+                     offset=(1e-6 if precision == 'f64' else 0.0), amp_max=2e-7)
+    w_def = [(pre - 500, pre + 500, False), (pre, pre + 1, False)]
+    w_gl = [(pre - 300, pre + 200, False)]
+    fits = [(0, w[0], w[1], 0) for w in w_def] + [(1, w[0], w[1], 0) for w in w_gl]
+    out = run_emu.run(tr, S.psd, [(S.template, pre, False), (S.template_glitch, pre, False)], fits, S.fs,
+                      precision=precision, subtract_first=(precision == 'f32'),
+                      scale=(2.0 ** 26 if precision == 'f32' else 1.0), v2=True)
+    o1 = of1x1_batch(tr, S.template, S.psd, S.fs, pre, windows=w_def)
+    o2 = of1x1_batch(tr, S.template_glitch, S.psd, S.fs, pre, windows=w_gl)
+    tol = (1e-11, 1e-11, 1e-11) if precision == 'f64' else (1e-5, 1e-4, 1e-4)
+    _check(out, o1, [1, 6], *tol)
+    _check(out, o2, [11], *tol)
+
+
 def test_reduce_kernel_emulated_bit_exact():
     exe = os.path.join(HERE, 'emu', '_build', 'emu_reduce')
     src = os.path.join(HERE, 'emu', 'emu_reduce.cpp')
