@@ -42,12 +42,32 @@ template <int R1> int setup_one(int device, size_t* smem, int* grid_max, int* oc
     *grid_max = sms * occ;
     return 0;
 }
-template <int R1> int launch_one(const Dp2Params<InstT>& prm, int multi, int grid, size_t smem, cudaStream_t st) {
+// persist_bytes > 0: the launch carries an access-policy window that makes the scratch area (X column,
+// parked block results) persisting in L2 and everything else streaming -- the set-aside was reserved by
+// the plan (cudaLimitPersistingL2CacheSize)
+template <int R1> int launch_one(const Dp2Params<InstT>& prm, int multi, int grid, size_t smem, cudaStream_t st, size_t persist_bytes) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Dp2Geom<InstT, R1>::NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (persist_bytes > 0) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = prm.scratch;
+        attr[0].val.accessPolicyWindow.num_bytes = persist_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t e;
     if (multi)
-        dp_of2_kernel<InstT, R1, DP_INST_IN, true><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+        e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, true>, prm);
     else
-        dp_of2_kernel<InstT, R1, DP_INST_IN, false><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
-    return (int)cudaGetLastError();
+        e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, false>, prm);
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 }  // namespace
 
@@ -59,13 +79,13 @@ int DP_CAT(dp_of2_setup_p, DP_INST_PREC, DP_INST_IN)(int R1, int device, size_t*
         default: return -1;
     }
 }
-int DP_CAT(dp_of2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, int multi, const void* prm_v, int grid, size_t smem, void* st_v) {
+int DP_CAT(dp_of2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, int multi, const void* prm_v, int grid, size_t smem, void* st_v, size_t persist_bytes) {
     const Dp2Params<InstT>& prm = *reinterpret_cast<const Dp2Params<InstT>*>(prm_v);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
     switch (R1) {
-        case 2: return launch_one<2>(prm, multi, grid, smem, st);
-        case 4: return launch_one<4>(prm, multi, grid, smem, st);
-        case 8: return launch_one<8>(prm, multi, grid, smem, st);
+        case 2: return launch_one<2>(prm, multi, grid, smem, st, persist_bytes);
+        case 4: return launch_one<4>(prm, multi, grid, smem, st, persist_bytes);
+        case 8: return launch_one<8>(prm, multi, grid, smem, st, persist_bytes);
         default: return -1;
     }
 }
