@@ -378,7 +378,12 @@ def gpu_main(a):
                    'l2': f'inputs ({B * BYTES_PER_EVENT / 2**30:.1f} GiB/GPU) larger than L2, no flush needed',
                    'sharding': 'events sharded by rank, no data-path collective'},
         'roofline': {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': r['achieved_gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                     'frac': r['achieved_gbs'] / hbm_peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: 822.5 MB + 559.0 MB for 2048 events in
+                     # profiles/r1_prof_of2_f64_32k_c2_r6.txt (ncu --set full), scaled to the events of one launch
+                     'traffic': (822.486016e6 + 558.953216e6) / 2048 * B,
+                     'traffic_source': 'profiles/r1_prof_of2_f64_32k_c2_r6.txt (per event x events per launch)',
+                     'peak_source': peak_src,
                      'kernel': 'dp_of2_kernel<double,4,0,true>', 'kernel_ms': r['kernel_ms'],
                      'algorithmic_bytes_per_event': BYTES_PER_EVENT,
                      'note': 'FFT path is FP64-pipe / issue bound, not HBM bound (10 FLOP/B); see DESIGN.md 4.1'},
@@ -391,6 +396,7 @@ def gpu_main(a):
         line['fast_mode'] = {'dtype': 'f32', 'value': f['value'], 'unit': UNIT, 'ms_per_step': f['ms_per_step'],
                              'roofline_frac': f['achieved_gbs'] / hbm_peak, 'achieved_gbs': f['achieved_gbs'],
                              'kernel': 'dp_of2_kernel<f2,4,0,true>', 'e2e': f['e2e']['value'],
+                             'traffic': (537.799168e6 + 6.095104e6) / 2048 * B,      # profiles/r1_prof_of2_f32_32k_c2_r6.txt
                              'tolerance': 'amp 1e-5, chi2 1e-4 rel vs float64 oracle'}
     if ex is not None:
         line['other_rows'] = ex
