@@ -534,10 +534,12 @@ template <class T, int R1, int IN> struct Dp2Core {
     // ---- pass 1' for columns [i0, i0 + GC): y[i*R1 + n1] = c'[n1*4096 + VL*(tid + (i0+i)*NT) + lane].
     // Only columns that hold a complex point n in [nlo, nhi] are computed (constrained delay windows
     // touch ~1/8 of the columns); the others keep stale registers, which no window scan selects.
-    static DP_DEV void inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1], int nlo = 0,
-                                 int nhi = 0x7fffffff) {
+    // Returns the mask of the columns it computed.
+    static DP_DEV unsigned inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1], int nlo = 0,
+                                     int nhi = 0x7fffffff) {
         const int tid = threadIdx.x;
         constexpr int LP = NPH - 1;
+        unsigned computed = 0;
 #pragma unroll
         for (int i = 0; i < G::GC; ++i) {
             const int c = tid + (i0 + i) * NT;
@@ -548,6 +550,7 @@ template <class T, int R1, int IN> struct Dp2Core {
                 need = need || (a + VL - 1 >= nlo && a <= nhi);
             }
             if (!need) continue;
+            computed |= 1u << i;
             V u[R1];
 #pragma unroll
             for (int b = 0; b < NB; ++b) u[G::k1_of(LP, b)] = buf[G::phys(c) + b * PB];
@@ -565,6 +568,7 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
             for (int n = 0; n < R1; ++n) y[i * R1 + n] = u[n];
         }
+        return computed;
     }
 };
 
@@ -602,7 +606,9 @@ template <class T, int R1> struct Dp2Scan {
         DpBest<S> c{vb, 2 * VL * tid + pb};
         dp_best_merge(out, c);
     }
-    static DP_DEV void window(const cx<T> (&y)[GC * R1], int tid, int i0, int lo, unsigned len, bool outside, DpBest<S>& out) {
+    // `computed`: columns pass 1' produced (the others hold no candidate of any fit)
+    static DP_DEV void window(const cx<T> (&y)[GC * R1], int tid, int i0, int lo, unsigned len, bool outside, DpBest<S>& out,
+                              unsigned computed = 0xffffffffu) {
         S kb = (S)-1, vb = (S)0;
         int pb = -1;
         const int rb = 2 * VL * tid;
@@ -615,6 +621,7 @@ template <class T, int R1> struct Dp2Scan {
             if (hit) {
 #pragma unroll
                 for (int i = 0; i < GC; ++i) {
+                    if (!(computed & (1u << i))) continue;
                     const int r0 = rb + 2 * (n * 4096 + VL * (i0 + i) * NT);
                     const cx<T>& v = y[i * R1 + n];
 #define DP2_CAND(val, rr)                                                  \
@@ -1033,7 +1040,8 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     V y[GC * R1];
 #pragma unroll
                     for (int j = 0; j < GC * R1; ++j) y[j] = V{(T)0.0f, (T)0.0f};
-                    Core::inv_pass1(sm.buf, park, prm.tw1, i0, y, nlo, nhi);
+                    const unsigned computed = Core::inv_pass1(sm.buf, park, prm.tw1, i0, y, nlo, nhi);
+                    if (computed == 0) continue;  // this thread holds no candidate delay of this template
 #pragma unroll
                     for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
                         if (q < nts) {
@@ -1041,7 +1049,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                             if (sl.lo == 0 && sl.hi == N && !sl.outside)
                                 Dp2Scan<T, R1>::full(y, tid, i0, tb[q]);
                             else
-                                Dp2Scan<T, R1>::window(y, tid, i0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, tb[q]);
+                                Dp2Scan<T, R1>::window(y, tid, i0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, tb[q], computed);
                         }
                     }
                 }
