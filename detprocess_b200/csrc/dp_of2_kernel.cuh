@@ -340,12 +340,18 @@ DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, lon
     }
     return r;
 }
+// fp64 mode computes on the samples as they are (the plans never scale or offset them: x0 = 0, sc = 1)
 template <int IN> DP_DEV cx<double> dp2_convert(const Dp2Raw<IN, 1>& r, double x0, double sc) {
-    return cx<double>{((double)r.q[0].x - x0) * sc, ((double)r.q[0].y - x0) * sc};
+    (void)x0;
+    (void)sc;
+    return cx<double>{(double)r.q[0].x, (double)r.q[0].y};
 }
+// fp32 mode: the first sample is removed in float64 (AC coupling; keeps the fp32 mantissa for the signal),
+// the power-of-two scale is applied after the conversion as one packed multiply
 template <int IN> DP_DEV cx<f2> dp2_convert(const Dp2Raw<IN, 2>& r, double x0, double sc) {
-    return cx<f2>{f2((float)(((double)r.q[0].x - x0) * sc), (float)(((double)r.q[1].x - x0) * sc)),
-                  f2((float)(((double)r.q[0].y - x0) * sc), (float)(((double)r.q[1].y - x0) * sc))};
+    const f2 s = f2((float)sc);
+    return cx<f2>{f2((float)((double)r.q[0].x - x0), (float)((double)r.q[1].x - x0)) * s,
+                  f2((float)((double)r.q[0].y - x0), (float)((double)r.q[1].y - x0)) * s};
 }
 
 // tie-aware running best (|val| larger, or equal and smaller index)
