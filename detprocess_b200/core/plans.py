@@ -343,10 +343,10 @@ class PSDPlan:
         check(lib.dp_psd_reset(self._h, _stream_ptr(self.device)))
 
     def accumulate(self, traces, mask=None):
-        """traces: CUDA float64 [n, N]; mask: optional CUDA bool/uint8 [n] (True = keep)."""
+        """traces: CUDA float64 / float32 / int16 [n, N]; mask: optional CUDA bool/uint8 [n] (True = keep)."""
         torch = _torch()
-        if not traces.is_cuda or traces.dtype != torch.float64:
-            raise ValueError('accumulate() takes float64 CUDA tensors')
+        if not traces.is_cuda:
+            raise ValueError('accumulate() takes CUDA tensors')
         if traces.ndim != 2 or traces.shape[1] != self.nb_samples:
             raise ValueError('traces must be [n_traces, nb_samples]')
         traces = traces.contiguous()
@@ -356,7 +356,7 @@ class PSDPlan:
             if mask.shape != (traces.shape[0],):
                 raise ValueError('mask must be [n_traces]')
             mptr = C.c_void_p(mask.data_ptr())
-        check(lib.dp_psd_accumulate(self._h, C.c_void_p(traces.data_ptr()), _lib.DP_IN_F64, traces.shape[0],
+        check(lib.dp_psd_accumulate(self._h, C.c_void_p(traces.data_ptr()), _in_dtype_of(traces), traces.shape[0],
                                     self.nb_samples, mptr, _stream_ptr(traces.device)))
 
     def sums(self):

@@ -944,10 +944,13 @@ template <class T> int psd2_finalize(dp_psd_plan* p) {
         default: rc = psd2_tables<T, 8>(p); break;
     }
     if (rc) return rc;
-    const int src = sizeof(typename Dp2Traits<T>::S) == 8
-                        ? dp_psd2_setup_p0_0(p->v2_r1, p->device, &p->smem, &p->grid_max, &p->partial_per_cta)
-                        : dp_psd2_setup_p1_0(p->v2_r1, p->device, &p->smem, &p->grid_max, &p->partial_per_cta);
-    if (src != 0) return fail(DP_ERR_CUDA, "PSD kernel setup failed");
+    const int prec = sizeof(typename Dp2Traits<T>::S) == 8 ? 0 : 1;
+    for (int in = 0; in < 3; ++in) {
+        int gm = 0;
+        const int src = dp_psd2_setup_table[prec][in](p->v2_r1, p->device, &p->smem, &gm, &p->partial_per_cta);
+        if (src != 0) return fail(DP_ERR_CUDA, "PSD kernel setup failed");
+        p->grid_max = in == 0 ? gm : std::min(p->grid_max, gm);
+    }
     DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->partial), sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
     p->owned.push_back(p->partial);
     DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->count), sizeof(unsigned long long) * (size_t)(p->grid_max + 1)));
@@ -1021,7 +1024,12 @@ int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long
     if (n_traces < 0) return fail(DP_ERR_INVALID, "negative n_traces");
     if (n_traces == 0) return DP_OK;
     if (!traces_dev) return fail(DP_ERR_INVALID, "null buffer");
-    if (in_dtype != DP_IN_F64) return fail(DP_ERR_UNSUPPORTED, "PSD accumulation takes float64 traces");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
+    if (in_dtype != DP_IN_F64 && !p->v2_r1) return fail(DP_ERR_UNSUPPORTED, "float32 / int16 traces need nb_samples 16384, 32768 or 65536");
+    {
+        const size_t esz = in_dtype == DP_IN_F64 ? 8 : (in_dtype == DP_IN_F32 ? 4 : 2);
+        if ((reinterpret_cast<uintptr_t>(traces_dev) % (2 * esz)) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
+    }
     if (row_stride < p->N || (row_stride & 1)) return fail(DP_ERR_INVALID, "row_stride must be even and >= nb_samples");
     if (n_traces > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1060,13 +1068,13 @@ int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long
             fill2(prm);
             prm.tw1 = (const cx<f2>*)p->tw1; prm.tw2 = (const cx<f2>*)p->tw2; prm.tw3 = (const cx<f2>*)p->tw3;
             prm.twn = (const cx<float>*)p->twn;
-            rc = dp_psd2_launch_p1_0(p->v2_r1, &prm, grid, p->smem, st);
+            rc = dp_psd2_launch_table[1][in_dtype](p->v2_r1, &prm, grid, p->smem, st);
         } else {
             DpPsd2Params<double> prm;
             fill2(prm);
             prm.tw1 = (const cx<double>*)p->tw1; prm.tw2 = (const cx<double>*)p->tw2; prm.tw3 = (const cx<double>*)p->tw3;
             prm.twn = (const cx<double>*)p->twn;
-            rc = dp_psd2_launch_p0_0(p->v2_r1, &prm, grid, p->smem, st);
+            rc = dp_psd2_launch_table[0][in_dtype](p->v2_r1, &prm, grid, p->smem, st);
         }
     } else if (p->precision == DP_PREC_F32) {
         DpPsdParams<float> prm;

@@ -91,12 +91,12 @@ int DP_CAT(dp_of2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, int multi, const v
 }
 
 // ------------------------------------------------------------------------ PSD kernels
-// built for float64 traces only (IN = 0)
-#if DP_INST_IN == 0
+// (float64 / float32 / int16 traces; not for the 8-byte-aligned window instantiation)
+#if DP_INST_IN <= 2
 namespace {
 template <int R1> int psd_setup_one(int device, size_t* smem, int* grid_max, long long* partial_per_cta) {
-    using K = DpPsd2Kernel<InstT, R1, 0>;
-    auto kern = dp_psd2_kernel<InstT, R1, 0>;
+    using K = DpPsd2Kernel<InstT, R1, DP_INST_IN>;
+    auto kern = dp_psd2_kernel<InstT, R1, DP_INST_IN>;
     *smem = K::SMEM_BYTES;
     *partial_per_cta = K::PARTIAL;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
@@ -111,12 +111,12 @@ template <int R1> int psd_setup_one(int device, size_t* smem, int* grid_max, lon
     return 0;
 }
 template <int R1> int psd_launch_one(const DpPsd2Params<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
-    dp_psd2_kernel<InstT, R1, 0><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+    dp_psd2_kernel<InstT, R1, DP_INST_IN><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
     return (int)cudaGetLastError();
 }
 }  // namespace
 
-int DP_CAT(dp_psd2_setup_p, DP_INST_PREC, 0)(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta) {
+int DP_CAT(dp_psd2_setup_p, DP_INST_PREC, DP_INST_IN)(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta) {
     switch (R1) {
         case 2: return psd_setup_one<2>(device, smem, grid_max, partial_per_cta);
         case 4: return psd_setup_one<4>(device, smem, grid_max, partial_per_cta);
@@ -124,7 +124,7 @@ int DP_CAT(dp_psd2_setup_p, DP_INST_PREC, 0)(int R1, int device, size_t* smem, i
         default: return -1;
     }
 }
-int DP_CAT(dp_psd2_launch_p, DP_INST_PREC, 0)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
+int DP_CAT(dp_psd2_launch_p, DP_INST_PREC, DP_INST_IN)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
     const DpPsd2Params<InstT>& prm = *reinterpret_cast<const DpPsd2Params<InstT>*>(prm_v);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
     switch (R1) {

@@ -16,8 +16,15 @@ static const dp_of2_setup_fn dp_of2_setup_table[2][4] = {{dp_of2_setup_p0_0, dp_
 static const dp_of2_launch_fn dp_of2_launch_table[2][4] = {{dp_of2_launch_p0_0, dp_of2_launch_p0_1, dp_of2_launch_p0_2, dp_of2_launch_p0_3},
                                                            {dp_of2_launch_p1_0, dp_of2_launch_p1_1, dp_of2_launch_p1_2, dp_of2_launch_p1_3}};
 
-// PSD accumulation on the v2 core (float64 traces)
-int dp_psd2_setup_p0_0(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta);
-int dp_psd2_setup_p1_0(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta);
-int dp_psd2_launch_p0_0(int R1, const void* prm, int grid, size_t smem, void* stream);
-int dp_psd2_launch_p1_0(int R1, const void* prm, int grid, size_t smem, void* stream);
+// PSD accumulation on the v2 core; second index = input type (0 f64, 1 f32, 2 i16)
+#define DP_PSD2_DECL(P, I)                                                                                          \
+    int dp_psd2_setup_p##P##_##I(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_cta);       \
+    int dp_psd2_launch_p##P##_##I(int R1, const void* prm, int grid, size_t smem, void* stream);
+DP_PSD2_DECL(0, 0) DP_PSD2_DECL(0, 1) DP_PSD2_DECL(0, 2) DP_PSD2_DECL(1, 0) DP_PSD2_DECL(1, 1) DP_PSD2_DECL(1, 2)
+#undef DP_PSD2_DECL
+typedef int (*dp_psd2_setup_fn)(int, int, size_t*, int*, long long*);
+typedef int (*dp_psd2_launch_fn)(int, const void*, int, size_t, void*);
+static const dp_psd2_setup_fn dp_psd2_setup_table[2][3] = {{dp_psd2_setup_p0_0, dp_psd2_setup_p0_1, dp_psd2_setup_p0_2},
+                                                           {dp_psd2_setup_p1_0, dp_psd2_setup_p1_1, dp_psd2_setup_p1_2}};
+static const dp_psd2_launch_fn dp_psd2_launch_table[2][3] = {{dp_psd2_launch_p0_0, dp_psd2_launch_p0_1, dp_psd2_launch_p0_2},
+                                                             {dp_psd2_launch_p1_0, dp_psd2_launch_p1_1, dp_psd2_launch_p1_2}};

@@ -154,7 +154,7 @@ int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* plan, float* ms);
 /* ------------------------------------------------------------------ noise PSD
  * Replaces qp.calc_psd(traces[cut], fs, folded_over=False) as called by Noise.calc_psd
  * (detprocess/core/noise.py:344): the plan accumulates sum_traces |fft(x)_k|^2 for
- * k = 0..N/2 over any number of dp_psd_accumulate calls (mask_dev selects the traces that
+ * k = 0..N/2 over any number of dp_psd_accumulate calls (float64, float32 or int16 traces; mask_dev selects the traces that
  * passed the cut, noise.py:331; NULL = all).  dp_psd_get_sums returns the per-GPU sums and
  * the number of accepted traces; the host layer all-reduces both over NCCL and forms
  * psd[k] = sum[k] / (count * N * fs), mirrored to the two-sided layout.

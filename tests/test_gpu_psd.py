@@ -54,3 +54,21 @@ def test_psd_offset_and_reset():
     _, psd2 = est.finalize()
     _, p0 = P.calc_psd(tr[:10], fs)
     assert np.abs(psd2 / p0 - 1).max() < 1e-11
+
+
+def test_psd_int16_and_float32_traces():
+    """Raw ADC (int16) and float32 buffers give the PSD of the same numbers (exactly representable samples)."""
+    from detprocess_b200.core.noise import NoisePSD
+    n, fs = 16384, 1.25e6
+    adc = np.random.default_rng(10).integers(-2000, 2000, size=(64, n)).astype(np.int16)
+    dev = torch.device('cuda', 0)
+    ref = NoisePSD(n, fs, device=dev)
+    ref.update(torch.from_numpy(adc.astype(np.float64)).to(dev))
+    _, p_ref = ref.finalize()
+    _, p0 = P.calc_psd(adc.astype(np.float64), fs)
+    assert np.abs(p_ref / p0 - 1).max() < 1e-11
+    for dt in (torch.int16, torch.float32):
+        est = NoisePSD(n, fs, device=dev)
+        est.update(torch.from_numpy(adc).to(dev).to(dt))
+        _, p = est.finalize()
+        assert np.array_equal(p, p_ref)
