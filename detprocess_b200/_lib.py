@@ -77,6 +77,7 @@ SIGNATURES = {
     'dp_trigger_plan_set_scale': (_i, [_vp, _d]),
     'dp_trigger_plan_geometry': (_i, [_vp, _ip, _ip]),
     'dp_trigger_run': (_i, [_vp, _vp, _ll, _d, _ll, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'dp_trigger_run_raw': (_i, [_vp, _vp, _i, _ll, _d, _ll, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'dp_trigger_plan_last_kernel_ms': (_i, [_vp, _fp, _fp]),
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 
 from .. import _lib
 from .._lib import lib, check
-from .plans import _PREC, _stream_ptr
+from .plans import _PREC, _stream_ptr, _in_dtype_of
 
 
 def _torch():
@@ -72,16 +72,16 @@ class TriggerPlan:
         check(lib.dp_trigger_plan_set_scale(self._h, float(typical_rms)))
 
     def run(self, trace, chi2_threshold, pileup_window_samples=0, index_shift=0, padding=True, max_triggers=65536):
-        """trace: CUDA float64 [L].  Returns (index int64 [n], amplitude [n], delta_chi2 [n]) CUDA tensors."""
+        """trace: CUDA float64 / float32 / int16 [L].  Returns (index int64 [n], amplitude [n], delta_chi2 [n]) CUDA tensors."""
         torch = _torch()
-        if not trace.is_cuda or trace.dtype != torch.float64 or trace.ndim != 1:
-            raise ValueError('run() takes a 1-D float64 CUDA tensor')
+        if not trace.is_cuda or trace.ndim != 1:
+            raise ValueError('run() takes a 1-D CUDA tensor')
         trace = trace.contiguous()
         idx = torch.empty(max_triggers, dtype=torch.int64, device=trace.device)
         amp = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
         dchi2 = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
         n = torch.zeros(1, dtype=torch.int32, device=trace.device)
-        check(lib.dp_trigger_run(self._h, C.c_void_p(trace.data_ptr()), trace.shape[0], float(chi2_threshold),
+        check(lib.dp_trigger_run_raw(self._h, C.c_void_p(trace.data_ptr()), _in_dtype_of(trace), trace.shape[0], float(chi2_threshold),
                                  int(pileup_window_samples), int(index_shift), int(bool(padding)),
                                  C.c_void_p(idx.data_ptr()), C.c_void_p(amp.data_ptr()), C.c_void_p(dchi2.data_ptr()),
                                  int(max_triggers), C.c_void_p(n.data_ptr()), _stream_ptr(trace.device)))

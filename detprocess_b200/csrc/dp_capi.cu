@@ -1307,7 +1307,15 @@ int dp_trigger_plan_geometry(const dp_trigger_plan* p, int* fft_size, int* hop) 
 int dp_trigger_run(dp_trigger_plan* p, const double* trace_dev, long long n_samples, double chi2_threshold,
                    long long pileup_window_samples, long long index_shift, int padding, long long* trig_index_dev,
                    double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream) {
+    return dp_trigger_run_raw(p, trace_dev, DP_IN_F64, n_samples, chi2_threshold, pileup_window_samples, index_shift, padding,
+                              trig_index_dev, trig_amp_dev, trig_dchi2_dev, max_triggers, n_triggers_dev, stream);
+}
+
+int dp_trigger_run_raw(dp_trigger_plan* p, const void* trace_dev, int in_dtype, long long n_samples, double chi2_threshold,
+                       long long pileup_window_samples, long long index_shift, int padding, long long* trig_index_dev,
+                       double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
     if (!trace_dev || !trig_index_dev || !trig_amp_dev || !trig_dchi2_dev || !n_triggers_dev) return fail(DP_ERR_INVALID, "null buffer");
     if (n_samples < 2 || n_samples > p->max_samples) return fail(DP_ERR_INVALID, "n_samples out of the plan's range");
     if ((reinterpret_cast<uintptr_t>(trace_dev) & 15) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
@@ -1349,7 +1357,7 @@ int dp_trigger_run(dp_trigger_plan* p, const double* trace_dev, long long n_samp
         prm.twn = (const cx<float>*)p->twn;
         prm.phi = (const cx<f2>*)p->phi; prm.phi_self = (const cx<float>*)p->phi_self;
         prm.scratch = (cx<f2>*)p->scratch;
-        rc = dp_trig_launch_p1(p->r1, &prm, grid, p->smem, st);
+        rc = dp_trig_launch_p1(p->r1, in_dtype, &prm, grid, p->smem, st);
     } else {
         DpTrigParams<double> prm;
         fill(prm);
@@ -1357,7 +1365,7 @@ int dp_trigger_run(dp_trigger_plan* p, const double* trace_dev, long long n_samp
         prm.twn = (const cx<double>*)p->twn;
         prm.phi = (const cx<double>*)p->phi; prm.phi_self = (const cx<double>*)p->phi_self;
         prm.scratch = (cx<double>*)p->scratch;
-        rc = dp_trig_launch_p0(p->r1, &prm, grid, p->smem, st);
+        rc = dp_trig_launch_p0(p->r1, in_dtype, &prm, grid, p->smem, st);
     }
     if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger filter launch: ") + cudaGetErrorString((cudaError_t)rc));
     DP_CUDA(cudaEventRecord(p->ev1, st));

@@ -1,5 +1,5 @@
 // Translation unit of the continuous-stream trigger kernels (dp_trig_kernel.cuh), one per
-// precision:  -DDP_INST_PREC=0|1 (double | packed float).  The stream is float64.
+// precision:  -DDP_INST_PREC=0|1 (double | packed float).  Streams: float64, float32 or int16.
 #ifndef DP_INST_PREC
 #error "DP_INST_PREC must be defined"
 #endif
@@ -21,15 +21,26 @@ using InstT = f2;
 #define DP_CAT(a, b) DP_CAT_(a, b)
 
 namespace {
+template <int R1, int IN> cudaError_t prep_one(int* occ) {
+    using K = DpTrigKernel<InstT, R1, IN>;
+    auto kern = dp_trig_filter_kernel<InstT, R1, IN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    int o = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, K::NT, K::SMEM_BYTES);
+    if (o < *occ) *occ = o;
+    return e;
+}
 template <int R1> int setup_one(int device, size_t* smem, int* grid_max, long long* scratch_per_cta) {
     using K = DpTrigKernel<InstT, R1, 0>;
-    auto kern = dp_trig_filter_kernel<InstT, R1, 0>;
     *smem = K::SMEM_BYTES;
     *scratch_per_cta = K::SCR_PARK;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    int occ = 1 << 20, sms = 0;
+    cudaError_t e = prep_one<R1, 0>(&occ);
     if (e != cudaSuccess) return (int)e;
-    int occ = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::NT, K::SMEM_BYTES);
+    e = prep_one<R1, 1>(&occ);
+    if (e != cudaSuccess) return (int)e;
+    e = prep_one<R1, 2>(&occ);
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return (int)e;
@@ -37,8 +48,13 @@ template <int R1> int setup_one(int device, size_t* smem, int* grid_max, long lo
     *grid_max = sms * occ;
     return 0;
 }
-template <int R1> int launch_one(const DpTrigParams<InstT>& prm, int grid, size_t smem, cudaStream_t st) {
-    dp_trig_filter_kernel<InstT, R1, 0><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm);
+template <int R1> int launch_one(const DpTrigParams<InstT>& prm, int in_dtype, int grid, size_t smem, cudaStream_t st) {
+    switch (in_dtype) {
+        case 0: dp_trig_filter_kernel<InstT, R1, 0><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm); break;
+        case 1: dp_trig_filter_kernel<InstT, R1, 1><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm); break;
+        case 2: dp_trig_filter_kernel<InstT, R1, 2><<<grid, Dp2Geom<InstT, R1>::NT, smem, st>>>(prm); break;
+        default: return -1;
+    }
     return (int)cudaGetLastError();
 }
 }  // namespace
@@ -51,13 +67,13 @@ int DP_CAT(dp_trig_setup_p, DP_INST_PREC)(int R1, int device, size_t* smem, int*
         default: return -1;
     }
 }
-int DP_CAT(dp_trig_launch_p, DP_INST_PREC)(int R1, const void* prm_v, int grid, size_t smem, void* st_v) {
+int DP_CAT(dp_trig_launch_p, DP_INST_PREC)(int R1, int in_dtype, const void* prm_v, int grid, size_t smem, void* st_v) {
     const DpTrigParams<InstT>& prm = *reinterpret_cast<const DpTrigParams<InstT>*>(prm_v);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
     switch (R1) {
-        case 2: return launch_one<2>(prm, grid, smem, st);
-        case 4: return launch_one<4>(prm, grid, smem, st);
-        case 8: return launch_one<8>(prm, grid, smem, st);
+        case 2: return launch_one<2>(prm, in_dtype, grid, smem, st);
+        case 4: return launch_one<4>(prm, in_dtype, grid, smem, st);
+        case 8: return launch_one<8>(prm, in_dtype, grid, smem, st);
         default: return -1;
     }
 }

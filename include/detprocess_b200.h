@@ -191,6 +191,10 @@ int dp_trigger_plan_geometry(const dp_trigger_plan* plan, int* fft_size, int* ho
 int dp_trigger_run(dp_trigger_plan* plan, const double* trace_dev, long long n_samples, double chi2_threshold,
                    long long pileup_window_samples, long long index_shift, int padding, long long* trig_index_dev,
                    double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream);
+/* same on a stream of in_dtype samples (DP_IN_F64 / DP_IN_F32 / DP_IN_I16, e.g. raw ADC counts) */
+int dp_trigger_run_raw(dp_trigger_plan* plan, const void* trace_dev, int in_dtype, long long n_samples, double chi2_threshold,
+                       long long pileup_window_samples, long long index_shift, int padding, long long* trig_index_dev,
+                       double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream);
 int dp_trigger_plan_last_kernel_ms(dp_trigger_plan* plan, float* filter_ms, float* group_ms);
 
 #ifdef __cplusplus

@@ -85,3 +85,17 @@ def test_trigger_f32_fast_mode():
     assert len(d['trigger_index']) == len(o['trigger_index'])
     assert np.max(np.abs(np.asarray(d['trigger_index']) - o['trigger_index'])) <= 1
     assert np.allclose(d['trigger_amplitude'], o['trigger_amplitude'], rtol=2e-4)
+
+
+def test_trigger_int16_and_float32_streams():
+    """Raw-ADC (int16) and float32 streams trigger exactly like the float64 stream of the same numbers."""
+    from detprocess_b200.core.oftrigger import OptimumFilterTrigger
+    nt, L = 4096, 150_000
+    fs, template, psd, x = _make(nt, L, 9, rate=80.0)
+    adc = np.round(x / 1e-10).astype(np.int16)              # 0.1 nA per count
+    trig = OptimumFilterTrigger('ch', fs, template, psd * 1e20, nt // 2, max_samples=L)
+    ref = trig._plan.run(torch.from_numpy(adc.astype(np.float64)).cuda(), 25.0, 1250, 0)
+    assert ref[0].shape[0] > 3
+    for dt in (torch.int16, torch.float32):
+        got = trig._plan.run(torch.from_numpy(adc).cuda().to(dt), 25.0, 1250, 0)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
