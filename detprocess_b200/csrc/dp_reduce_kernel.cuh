@@ -84,11 +84,22 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
             if (valid) lf = prm.leaves[L];
             const bool small = lf.len < 8;
             const int nfull = small ? 0 : lf.len - (lf.len & 7);
-            double r = 0.0;
-            if (nfull > 0) {
-                r = dp_red_elem(x, lf.off + lane8, lf.trapz);
-                for (int i = 8; i < nfull; i += 8) r = dp_add_rn(r, dp_red_elem(x, lf.off + i + lane8, lf.trapz));
+            // a leaf has at most 128 elements = 16 rows of 8: all 16 loads of the lane are issued before the first
+            // addition (the additions keep numpy's order; one load in flight per thread left the kernel latency bound)
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (8 * j < nfull) ? __ldg(x + lf.off + 8 * j + lane8) : 0.0;
+            if (lf.trapz) {  // element i is (y[i+1] + y[i]) / 2 (exact halving == numpy's / 2.0)
+                double w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = (8 * j < nfull) ? __ldg(x + lf.off + 8 * j + lane8 + 1) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = dp_add_rn(w[j], v[j]) * 0.5;
             }
+            double r = v[0];
+#pragma unroll
+            for (int j = 1; j < 16; ++j)
+                if (8 * j < nfull) r = dp_add_rn(r, v[j]);
             r = dp_add_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
             r = dp_add_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
             r = dp_add_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
@@ -119,6 +130,7 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
                 const bool is_max = ft.op == DP_OP_MAX;
                 double m = is_max ? -INFINITY : INFINITY;
                 int has_nan = 0;
+#pragma unroll 4
                 for (int i = ft.lo + tid; i < ft.hi; i += NT) {
                     const double v = __ldg(x + i);
                     if (v != v) has_nan = 1;
