@@ -239,6 +239,28 @@ def extras(device, dist, world, hbm_peak):
     from detprocess_b200.core.oftrigger import OptimumFilterTrigger
     from detprocess_b200.synth import make_template, make_psd
     out = {}
+    # ---- C1 window reductions (baseline_pre + integral, README.md:87-96 windows), bit-exact numpy arithmetic
+    from detprocess_b200.core.plans import ReducePlan
+    n, B = NB_SAMPLES, 8192
+    red = ReducePlan(n, FS, 1)
+    red.add(0, 'baseline', 0, n // 2 - 1250)
+    red.add(0, 'integral', n // 2 - 625, n // 2 + 625)
+    red.finalize(device)
+    xr = torch.randn((B, n), dtype=torch.float64, device=device)
+    ro = torch.empty((B, red.n_out), dtype=torch.float64, device=device)
+    for _ in range(3):
+        red.run(xr, ro)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        red.run(xr, ro)
+        ms.append(red.last_kernel_ms())
+    m = float(np.median(ms))
+    wbytes = B * ((n // 2 - 1250) + 1250) * 8
+    out['c1_window_reductions'] = {'events_per_s_per_gpu': B / (m * 1e-3), 'achieved_gbs': wbytes / (m * 1e-3) / 1e9,
+                                   'roofline_frac': wbytes / (m * 1e-3) / 1e9 / hbm_peak, 'bound': 'hbm',
+                                   'algorithmic_bytes_per_event': wbytes // B, 'kernel': 'dp_reduce_kernel<256>'}
+    del xr, ro, red
     # ---- C5
     n, B = 65536, 4096
     x = torch.randn((B, n), dtype=torch.float64, device=device) * 1e-10
