@@ -6,9 +6,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EXE = os.path.join(HERE, '_build', 'emu_of')
 
 
-def build(tsan=False, v2=False):
+def build(tsan=False, v2=False, asan=False):
     os.makedirs(os.path.join(HERE, '_build'), exist_ok=True)
-    exe = EXE + ('2' if v2 else '') + ('_tsan' if tsan else '')
+    exe = EXE + ('2' if v2 else '') + ('_tsan' if tsan else '') + ('_asan' if asan else '')
     src = os.path.join(HERE, 'emu_of2.cpp' if v2 else 'emu_of.cpp')
     deps = [src] + [os.path.join(HERE, '../../detprocess_b200/csrc', f) for f in
                     ('dp_of_kernel.cuh', 'dp_fft.cuh', 'dp_platform.cuh', 'dp_plan.hpp', 'dp_of2_kernel.cuh',
@@ -18,14 +18,16 @@ def build(tsan=False, v2=False):
     cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-o', exe, src]
     if tsan:
         cmd[3:3] = ['-fsanitize=thread', '-g']
+    if asan:
+        cmd[3:3] = ['-fsanitize=address', '-fno-omit-frame-pointer', '-g']
     subprocess.check_call(cmd)
     return exe
 
 
 def run(traces, psd, templates, fits, fs, fcut=10000.0, precision='f64', ac=True,
-        subtract_first=False, scale=1.0, tsan=False, force_p2=False, v2=False):
+        subtract_first=False, scale=1.0, tsan=False, force_p2=False, v2=False, asan=False):
     """templates: list of (template, pretrigger, integralnorm); fits: list of (templ, lo, hi, outside)."""
-    exe = build(tsan, v2)
+    exe = build(tsan, v2, asan)
     traces = np.ascontiguousarray(traces, dtype=np.float64)
     nev, n = traces.shape
     with tempfile.TemporaryDirectory() as td:

@@ -105,6 +105,19 @@ def test_of_v2_kernel_emulated_constrained_only(nb_samples, precision):
     _check(out, o2, [11], *tol)
 
 
+def test_of_v2_kernel_emulated_address_sanitizer():
+    """The kernel source under AddressSanitizer (compute-sanitizer is closed on the GPU pool): every shared-memory,
+    scratch and table access of a two-phase, two-template fp64 run stays inside its buffer."""
+    S = SynthSetup(32768)
+    pre = S.nb_pretrigger
+    tr = make_traces(2, S.template, S.psd, S.fs, np.random.default_rng(8))
+    fits = [(0, 0, S.nb_samples, 0), (0, pre - 500, pre + 500, 0), (1, pre - 100, pre + 300, 1)]
+    out = run_emu.run(tr, S.psd, [(S.template, pre, False), (S.template_glitch, pre, False)], fits, S.fs,
+                      precision='f64', v2=True, asan=True)     # a finding aborts the emulator: CalledProcessError
+    o1 = of1x1_batch(tr, S.template, S.psd, S.fs, pre, windows=[(None, None, False)])
+    assert np.array_equal(out[:, 2].astype(np.int64), o1['ind'][0])
+
+
 def test_reduce_kernel_emulated_bit_exact():
     exe = os.path.join(HERE, 'emu', '_build', 'emu_reduce')
     src = os.path.join(HERE, 'emu', 'emu_reduce.cpp')
