@@ -185,11 +185,13 @@ def make_device_traces(S, n_events, device, seed):
     return out
 
 
-def build_plan(S, precision):
+def build_plan(S, precision, adc=None):
     from detprocess_b200.core.plans import OFPlan
     pre = S.nb_pretrigger
     plan = OFPlan(S.nb_samples, S.fs, 1, precision)
     plan.set_psd(0, S.psd, 'AC')
+    if adc is not None:
+        plan.set_adc_conversion(0, *adc)
     t0 = plan.add_template(0, S.template, pre)
     t1 = plan.add_template(0, S.template_glitch, pre)
     plan.add_fit(0, t0, pre - WINDOW, pre + WINDOW)
@@ -379,6 +381,28 @@ def gpu_main(a):
                                 'api': 'OFPlan.run_host -> dp_of1x1_batch_host (pinned host buffers)'}
         results[prec]['n_out'] = plan.n_out
         del plan, out
+        # ---- the same with the traces as they are on disk: int16 ADC counts, converted in the kernel's load ----
+        gain = 1.0e-11
+        aplan = build_plan(S, prec, adc=(gain, 0.0))
+        ahost = torch.empty((E, NB_SAMPLES), dtype=torch.int16).pin_memory()
+        ahost.copy_(torch.clamp(torch.round(x[:E] / gain), -32768, 32767).to(torch.int16).cpu())
+        aplan.run_host(ahost, hout)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            aplan.run_host(ahost, hout)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        results[prec]['e2e_adc'] = {'value': world * E * reps / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(E * NB_SAMPLES * 2),
+                                    'd2h_bytes_per_step': int(E * aplan.n_out * 8),
+                                    'input': 'pinned host int16 ADC counts, adc->amps in the kernel (set_adc_conversion)'}
+        del aplan
 
     ex = None
     if not a.no_extras:
@@ -410,6 +434,7 @@ def gpu_main(a):
                      'algorithmic_bytes_per_event': BYTES_PER_EVENT,
                      'note': 'FFT path is FP64-pipe / issue bound, not HBM bound (10 FLOP/B); see DESIGN.md 4.1'},
         'e2e': {k: r['e2e'][k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')},
+        'e2e_adc_i16': r['e2e_adc'],
         'gpu_launches': r['launches'] * world,
         'clocks': sampler.summary() if sampler else None,
     }
@@ -418,6 +443,7 @@ def gpu_main(a):
         line['fast_mode'] = {'dtype': 'f32', 'value': f['value'], 'unit': UNIT, 'ms_per_step': f['ms_per_step'],
                              'roofline_frac': f['achieved_gbs'] / hbm_peak, 'achieved_gbs': f['achieved_gbs'],
                              'kernel': 'dp_of2_kernel<f2,4,0,true>', 'e2e': f['e2e']['value'],
+                             'e2e_adc_i16': f['e2e_adc']['value'],
                              'traffic': (537.799168e6 + 6.095104e6) / 2048 * B,      # profiles/r1_prof_of2_f32_32k_c2_r6.txt
                              'tolerance': 'amp 1e-5, chi2 1e-4 rel vs float64 oracle'}
     if ex is not None:

@@ -45,6 +45,7 @@ SIGNATURES = {
     'dp_of_plan_add_template': (_i, [_vp, _i, _vp, _i, _i, _ip]),
     'dp_of_plan_add_fit': (_i, [_vp, _i, _i, _i, _i, _i, _ip]),
     'dp_of_plan_set_lowchi2_fcutoff': (_i, [_vp, _d]),
+    'dp_of_plan_set_adc_conversion': (_i, [_vp, _i, _d, _d]),
     'dp_of_plan_finalize': (_i, [_vp, _i]),
     'dp_of_plan_n_out': (_i, [_vp, _ip]),
     'dp_of_plan_fit_offset': (_i, [_vp, _i, _i, _ip]),

@@ -103,6 +103,11 @@ class OFPlan:
     def set_lowchi2_fcutoff(self, fcutoff):
         check(lib.dp_of_plan_set_lowchi2_fcutoff(self._h, float(fcutoff)))
 
+    def set_adc_conversion(self, chan, gain, offset=0.0):
+        """int16 traces of this channel are raw ADC counts: sample = adc * gain + offset, converted in the kernel's
+        load (what H5Reader.read_single_event(adctoamp=True) does on the host, reference processing_data.py:674-684)."""
+        check(lib.dp_of_plan_set_adc_conversion(self._h, int(chan), float(gain), float(offset)))
+
     def finalize(self, device=None):
         torch = _torch()
         if not torch.cuda.is_available():

@@ -81,6 +81,7 @@ struct dp_of_plan {
     int nlow = 0;
     double scale = 1.0;
     int subtract_first = 0;
+    std::vector<double> adc_gain, adc_offset;  // per channel, int16 traces only
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     long long launches = 0;
@@ -258,6 +259,8 @@ template <class T> int of2_finalize(dp_of_plan* p) {
         dc.wj_low = ws;
         if ((rc = upload(p->owned, dt.chans[c].wj_self, &ws))) return rc;
         dc.wj_self = ws;
+        dc.adc_gain = c < (int)p->adc_gain.size() ? p->adc_gain[c] : 1.0;
+        dc.adc_offset = c < (int)p->adc_offset.size() ? p->adc_offset[c] : 0.0;
         dc.n_templ = (int)p->chans[c].templ.size();
         dc.n_slots = (int)p->chans[c].fits.size();
         dc.out_base = base;
@@ -493,6 +496,18 @@ int dp_of_plan_set_lowchi2_fcutoff(dp_of_plan* p, double fcutoff_hz) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
     if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
     p->fcut = fcutoff_hz;
+    return DP_OK;
+}
+
+int dp_of_plan_set_adc_conversion(dp_of_plan* p, int chan, double gain, double offset) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    if (!(gain > 0) || !std::isfinite(gain) || !std::isfinite(offset)) return fail(DP_ERR_INVALID, "adc gain must be finite and > 0");
+    p->adc_gain.resize(p->n_chan, 1.0);
+    p->adc_offset.resize(p->n_chan, 0.0);
+    p->adc_gain[chan] = gain;
+    p->adc_offset[chan] = offset;
     return DP_OK;
 }
 

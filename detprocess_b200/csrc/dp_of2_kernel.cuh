@@ -177,6 +177,8 @@ template <class T> struct Dp2ChanDev {
     const T* wj;       // [NPH][16][NT] thread-order chi0 weights
     const S* wj_self;  // [17][2]
     const S* wj_low;   // [nlow]
+    double adc_gain;   // int16 traces (raw ADC counts): sample = adc * adc_gain + adc_offset
+    double adc_offset;
     int n_templ;
     int n_slots;
     int out_base;
@@ -340,11 +342,16 @@ DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, lon
     }
     return r;
 }
-// fp64 mode computes on the samples as they are (the plans never scale or offset them: x0 = 0, sc = 1)
+// fp64 mode computes on the samples as they are (the plans never scale or offset them); raw ADC counts (IN == 2)
+// become adc * sc - x0 with the channel's conversion (sc = gain, x0 = -offset)
 template <int IN> DP_DEV cx<double> dp2_convert(const Dp2Raw<IN, 1>& r, double x0, double sc) {
-    (void)x0;
-    (void)sc;
-    return cx<double>{(double)r.q[0].x, (double)r.q[0].y};
+    if constexpr (IN == 2) {
+        return cx<double>{dp_fma((double)r.q[0].x, sc, -x0), dp_fma((double)r.q[0].y, sc, -x0)};
+    } else {
+        (void)x0;
+        (void)sc;
+        return cx<double>{(double)r.q[0].x, (double)r.q[0].y};
+    }
 }
 // fp32 mode: the first sample is removed in float64 (AC coupling; keeps the fp32 mantissa for the signal),
 // the power-of-two scale is applied after the conversion as one packed multiply
@@ -859,7 +866,20 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             }
         }
         const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)first * ESZ;
-        const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+        double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+        double xsc = prm.scale;
+        if constexpr (IN == 2) {
+            // ADC counts -> samples.  fp64: adc * gain + offset; fp32: (adc - x0) * (gain * scale) with x0 the first
+            // count (AC coupling) or the count the offset cancels
+            const double gain = dp_ldg(&prm.chans[chan].adc_gain), offs = dp_ldg(&prm.chans[chan].adc_offset);
+            if constexpr (VL == 1) {
+                x0 = -offs;
+                xsc = gain;
+            } else {
+                if (!prm.subtract_first) x0 = -offs / gain;
+                xsc = gain * prm.scale;
+            }
+        }
         S chi = (S)0;
 
 #pragma unroll 1
@@ -870,7 +890,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             const int2 gg = prm.groups[p * NT + tid];
             const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
             const bool special = (p == 0) && (tid < NSPECIAL);
-            Core::pass1_any(p, xrow, x0, prm.scale, sm.buf, prm.tw1);
+            Core::pass1_any(p, xrow, x0, xsc, sm.buf, prm.tw1);
             __syncthreads();
 #ifndef DP_HOST_EMU
             // every second block starts its passes a little late so that the block sets' LDS / FP / STS phases

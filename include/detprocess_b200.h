@@ -84,6 +84,12 @@ int dp_of_plan_add_fit(dp_of_plan* plan, int chan, int templ_index, int window_l
 /* lowchi2_fcutoff of qp.OF1x1.calc (default 10000 Hz, algorithms.py:280) */
 int dp_of_plan_set_lowchi2_fcutoff(dp_of_plan* plan, double fcutoff_hz);
 
+/* DP_IN_I16 traces are raw ADC counts: sample = adc * gain + offset, converted in the kernel's load (float64 mode: one
+ * fused multiply-add in float64; float32 mode: the offset cancels with the AC coupling).  Replaces the host-side
+ * conversion of pytesio H5Reader.read_single_event(..., adctoamp=True) (processing_data.py:674-684) so that a
+ * quarter of the bytes cross PCIe.  Default gain 1, offset 0.  Before finalize. */
+int dp_of_plan_set_adc_conversion(dp_of_plan* plan, int chan, double gain, double offset);
+
 /* builds the device tables on `device`; the plan is immutable afterwards */
 int dp_of_plan_finalize(dp_of_plan* plan, int device);
 

@@ -47,8 +47,8 @@ def _run_plan(S, traces, precision, templates, windows_per_template, in_dtype=No
     return plan, fits, out.cpu().numpy()
 
 
-def _compare(plan, fit, out, o, iw, tol, amp_floor):
-    off = plan.fit_offset(0, fit)
+def _compare(plan, fit, out, o, iw, tol, amp_floor, chan=0):
+    off = plan.fit_offset(chan, fit)
     amp, ind, chi2, low, tres = (out[:, off + i] for i in range(5))
     ind = ind.astype(np.int64)
     same = ind == o['ind'][iw]
@@ -129,6 +129,32 @@ def test_of1x1_float32_and_int16_inputs():
     for dt in (torch.float32, torch.int16):
         got = _run_plan(S, adc.astype(np.float64), 'f64', [S.template], [wins], in_dtype=dt)[2]
         assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize('precision', ['f64', 'f32'])
+def test_of1x1_adc_counts_with_channel_conversion(precision):
+    """int16 ADC counts + per-channel gain / offset (set_adc_conversion) == the oracle on the traces converted on
+    the host the way H5Reader(adctoamp=True) hands them to the reference (adc * gain + offset, float64)."""
+    import torch
+    from detprocess_b200.core.plans import OFPlan
+    S = SynthSetup(32768)
+    pre = S.nb_pretrigger
+    gains, offs = (1.0e-11, 1.3e-11), (-3.0e-9, 1.7e-8)
+    amps = [make_traces(40, S.template, S.psd, S.fs, np.random.default_rng(20 + c)) for c in range(2)]
+    adc = np.stack([np.clip(np.round((amps[c] - offs[c]) / gains[c]), -32768, 32767).astype(np.int16) for c in range(2)], axis=1)
+    conv = [adc[:, c].astype(np.float64) * gains[c] + offs[c] for c in range(2)]
+    plan = OFPlan(S.nb_samples, S.fs, 2, precision)
+    fits = []
+    for c in range(2):
+        plan.set_psd(c, S.psd)
+        plan.set_adc_conversion(c, gains[c], offs[c])
+        t = plan.add_template(c, S.template, pre)
+        fits.append(plan.add_fit(c, t, pre - 500, pre + 500))
+    plan.finalize()
+    out = plan.run(torch.from_numpy(adc).cuda()).cpu().numpy()
+    for c in range(2):
+        o = of1x1_batch(conv[c], S.template, S.psd, S.fs, pre, windows=[(pre - 500, pre + 500, False)])
+        _compare(plan, fits[c], out, o, 0, TOL[precision], 5 * o['ampres'], chan=c)
 
 
 def test_of1x1_two_channels_sharded_equals_single():
