@@ -46,6 +46,15 @@ SIGNATURES = {
     'dp_of_plan_add_fit': (_i, [_vp, _i, _i, _i, _i, _i, _ip]),
     'dp_of_plan_set_lowchi2_fcutoff': (_i, [_vp, _d]),
     'dp_of_plan_set_adc_conversion': (_i, [_vp, _i, _d, _d]),
+    'dp_nxm_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i, _i]),
+    'dp_nxm_plan_destroy': (None, [_vp]),
+    'dp_nxm_plan_set_filter': (_i, [_vp, _vp, _vp, _i, _i]),
+    'dp_nxm_plan_set_window': (_i, [_vp, _i, _i, _i]),
+    'dp_nxm_plan_finalize': (_i, [_vp, _i]),
+    'dp_nxm_plan_n_out': (_i, [_vp, _ip]),
+    'dp_nxm_plan_get_p_matrix': (_i, [_vp, _vp, _vp]),
+    'dp_ofnxm_batch': (_i, [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp]),
+    'dp_nxm_plan_last_kernel_ms': (_i, [_vp, C.POINTER(C.c_float)]),
     'dp_of_plan_finalize': (_i, [_vp, _i]),
     'dp_of_plan_n_out': (_i, [_vp, _ip]),
     'dp_of_plan_fit_offset': (_i, [_vp, _i, _i, _ip]),

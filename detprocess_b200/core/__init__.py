@@ -1,4 +1,4 @@
-from .plans import OFPlan, ReducePlan
+from .plans import OFPlan, ReducePlan, NxMPlan
 from .ofbase import OFBaseBatch
 from .algorithms import FeatureExtractors
 from .filterdata import FilterData

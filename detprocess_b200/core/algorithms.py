@@ -5,6 +5,7 @@
 
     of1x1_nodelay :278   of1x1_unconstrained :355   of1x1_constrained :436
     baseline :651        integral :709              maximum :771        minimum :830
+    ofnxm :141 (joint channels 'a|b', templates [n, m, N], csd [n, n, N])
 
 OF methods take ``(channel, of_base, ...)`` where ``of_base`` is an ``OFBaseBatch`` holding a
 batch of B events on the device; trace methods take ``(trace, ...)`` where ``trace`` is
@@ -127,6 +128,49 @@ class FeatureExtractors:
                             window_max_from_trig_usec, window_min_index, window_max_index)
         r = of_base.results(of_base.request_fit(channel, template_tag, lo, hi, lgc_outside_window))
         return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
+
+    @staticmethod
+    def ofnxm(channel, of_base, available_channels=None, feature_base_name='ofnxm', template_tag=None,
+              amplitude_names=None, window_min_from_trig_usec=None, window_max_from_trig_usec=None,
+              window_min_index=None, window_max_index=None, lgc_outside_window=False, lowchi2_fcutoff=10000,
+              interpolate_t0=False, **kwargs):
+        if template_tag is None:
+            raise ValueError(f'ERROR: Missing "template_tag" argument for channel {channel}, '
+                             f'algorithm "{feature_base_name}"')
+        template = of_base.template(channel, template_tag=template_tag)
+        if template is None:
+            raise ValueError(f'ERROR: Missing template for channel {channel}, tag "{template_tag}", '
+                             f'algorithm "{feature_base_name}"')
+        ntmps = template.shape[1]
+        if amplitude_names is None:
+            amplitude_names = [f'amp{i + 1}' for i in range(ntmps)]
+        else:
+            if isinstance(amplitude_names, str):
+                amplitude_names = [amplitude_names]
+            if len(amplitude_names) != ntmps:
+                raise ValueError(f'ERROR: Wrong length for "amplitude_names" argument. Expecting {ntmps} name '
+                                 f'for  channel {channel}, algorithm "{feature_base_name}"')
+        retdict = {f'chi2_{feature_base_name}_constrained': _SENTINEL, f't0_{feature_base_name}_constrained': _SENTINEL}
+        for name in amplitude_names:
+            retdict[f'{name}_{feature_base_name}_constrained'] = _SENTINEL
+        retdict[f'chi2_{feature_base_name}_nodelay'] = _SENTINEL
+        for name in amplitude_names:
+            retdict[f'{name}_{feature_base_name}_nodelay'] = _SENTINEL
+        if not of_base.is_signal_stored(channel):
+            return retdict
+        if interpolate_t0:
+            raise NotImplementedError('interpolate_t0=True is not built')
+        lo, hi = _of_window(of_base, channel, template_tag, window_min_from_trig_usec, window_max_from_trig_usec,
+                            window_min_index, window_max_index)
+        r = of_base.nxm_results(channel, template_tag, lo, hi, lgc_outside_window)
+        retdict[f'chi2_{feature_base_name}_constrained'] = r['chi2']
+        retdict[f't0_{feature_base_name}_constrained'] = r['t0']
+        for i, name in enumerate(amplitude_names):
+            retdict[f'{name}_{feature_base_name}_constrained'] = r['amps'][:, i]
+        retdict[f'chi2_{feature_base_name}_nodelay'] = r['chi2_nodelay']
+        for i, name in enumerate(amplitude_names):
+            retdict[f'{name}_{feature_base_name}_nodelay'] = r['amps_nodelay'][:, i]
+        return _scalarize(of_base, retdict)
 
     @staticmethod
     def baseline(trace, window_min_index=None, window_max_index=None,

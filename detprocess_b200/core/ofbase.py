@@ -12,7 +12,7 @@ the result columns.  The kernel launch is lazy: the first extractor call after
 """
 import numpy as np
 
-from .plans import OFPlan
+from .plans import OFPlan, NxMPlan
 
 __all__ = ['OFBaseBatch']
 
@@ -34,6 +34,11 @@ class OFBaseBatch:
         self._handles = {}
         self._signals = {}     # chan -> tensor [B, N]
         self._out = None       # host ndarray [B, n_out]
+        # joint channels 'a|b|c' (NxM filter): csd [n, n, N], templates {tag: ([n, m, N], pretrigger)}
+        self._nxm_csd = {}
+        self._nxm_templates = {}
+        self._nxm_plans = {}   # (chan, tag) -> NxMPlan
+        self._nxm_out = {}     # (chan, tag, lo, hi, outside) -> host ndarray
 
     # ---- reference-shaped setup -------------------------------------------------
     def sample_rate(self):
@@ -52,6 +57,16 @@ class OFBaseBatch:
             raise ValueError('ERROR: inconsistent number of samples')
 
     def set_csd(self, channel, csd, coupling='AC', ignored_frequency_peaks=None, ignore_harmonics=False):
+        if '|' in channel:
+            csd = np.asarray(csd, dtype=np.complex128)
+            if csd.ndim != 3 or csd.shape[0] != csd.shape[1] or csd.shape[0] != len(channel.split('|')):
+                raise ValueError(f'ERROR: csd of "{channel}" must be [n, n, N]')
+            if ignored_frequency_peaks is not None:
+                raise NotImplementedError('ignored_frequency_peaks for joint channels is not built')
+            self._check_n(csd.shape[-1])
+            self._nxm_csd[channel] = (csd, coupling)
+            self._nxm_plans = {k: v for k, v in self._nxm_plans.items() if k[0] != channel}
+            return
         psd = np.array(np.real(np.asarray(csd)), dtype=np.float64).reshape(-1)
         self._check_n(psd.shape[-1])
         if ignored_frequency_peaks is not None:
@@ -68,10 +83,25 @@ class OFBaseBatch:
         self._plan = None
 
     def csd(self, channel):
+        if '|' in channel:
+            return self._nxm_csd[channel][0] if channel in self._nxm_csd else None
         return self._psd[channel][0] if channel in self._psd else None
 
     def add_template(self, channel, template, template_tag='default', pretrigger_samples=None,
                      integralnorm=False, overwrite=False, **kwargs):
+        if '|' in channel:
+            template = np.asarray(template, dtype=np.float64)
+            if template.ndim != 3 or template.shape[0] != len(channel.split('|')):
+                raise ValueError(f'ERROR: template of "{channel}" must be [n_chan, n_templ, N]')
+            if integralnorm:
+                raise NotImplementedError('integralnorm for joint channels is not built')
+            self._check_n(template.shape[-1])
+            tags = self._nxm_templates.setdefault(channel, {})
+            if template_tag in tags and not overwrite:
+                raise ValueError(f'ERROR: template "{template_tag}" already exists (use overwrite=True)')
+            tags[template_tag] = (template, self._nbins // 2 if pretrigger_samples is None else int(pretrigger_samples))
+            self._nxm_plans.pop((channel, template_tag), None)
+            return
         template = np.asarray(template, dtype=np.float64).reshape(-1)
         self._check_n(template.shape[-1])
         tags = self._templates.setdefault(channel, {})
@@ -85,6 +115,9 @@ class OFBaseBatch:
         self._plan = None
 
     def template(self, channel, template_tag='default'):
+        if '|' in channel:
+            t = self._nxm_templates.get(channel, {}).get(template_tag)
+            return None if t is None else t[0]
         t = self._templates.get(channel, {}).get(template_tag)
         return None if t is None else t[0]
 
@@ -92,9 +125,14 @@ class OFBaseBatch:
         return list(self._templates.get(channel, {}).keys())
 
     def pretrigger_samples(self, channel, template_tag='default'):
+        if '|' in channel:
+            return self._nxm_templates[channel][template_tag][1]
         return self._templates[channel][template_tag][1]
 
     def calc_phi(self, channel, template_tag='default'):
+        if '|' in channel:
+            self._nxm_plan(channel, template_tag)
+            return
         self._ensure_plan()
 
     def phi(self, channel, template_tag='default'):
@@ -155,6 +193,7 @@ class OFBaseBatch:
     def clear_signal(self):
         self._signals = {}
         self._out = None
+        self._nxm_out = {}
 
     def is_signal_stored(self, channel):
         return channel in self._signals
@@ -164,6 +203,15 @@ class OFBaseBatch:
         import torch
         if isinstance(signal, np.ndarray):
             signal = torch.from_numpy(np.ascontiguousarray(signal))
+        if '|' in channel:
+            self._single = signal.ndim == 2
+            if signal.ndim == 2:
+                signal = signal[None]
+            if signal.ndim != 3 or signal.shape[1] != len(channel.split('|')) or signal.shape[-1] != self._nbins:
+                raise ValueError(f'ERROR: signal of "{channel}" must be [B, n_chan, N]')
+            self._signals[channel] = signal
+            self._nxm_out = {k: v for k, v in self._nxm_out.items() if k[0] != channel}
+            return
         self._single = signal.ndim == 1
         if signal.ndim == 1:
             signal = signal[None, :]
@@ -210,6 +258,35 @@ class OFBaseBatch:
                'chi2nopulse': o[:, self._plan.chi0_offset(ci)],
                'ampres': 1.0 / np.sqrt(self.norm(chan, tag))}
         return res
+
+    # ---- joint channels: NxM filter --------------------------------------------
+    def _nxm_plan(self, channel, template_tag):
+        plan = self._nxm_plans.get((channel, template_tag))
+        if plan is None:
+            if channel not in self._nxm_csd:
+                raise ValueError(f'ERROR: no csd for channel {channel}')
+            templ, pre = self._nxm_templates[channel][template_tag]
+            csd, coupling = self._nxm_csd[channel]
+            plan = NxMPlan(self._nbins, self._fs, templ.shape[0], templ.shape[1], self._precision)
+            plan.set_filter(templ, csd, pre, coupling)
+            plan.finalize(self._device)
+            self._nxm_plans[(channel, template_tag)] = plan
+        return plan
+
+    def nxm_results(self, channel, template_tag, lo, hi, outside=False):
+        """dict of arrays for one NxM fit: chi0, chi2, ind, t0, amps [B, m], chi2_nodelay, amps_nodelay [B, m]"""
+        import torch
+        key = (channel, template_tag, lo, hi, bool(outside))
+        o = self._nxm_out.get(key)
+        plan = self._nxm_plan(channel, template_tag)
+        if o is None:
+            plan.set_window(lo, hi, outside)
+            x = self._signals[channel].to(device=plan.device, dtype=torch.float64)
+            o = self._nxm_out[key] = plan.run(x).cpu().numpy()
+        m = plan.n_templ
+        ind = o[:, 2].astype(np.int64)
+        return {'chi0': o[:, 0], 'chi2': o[:, 1], 'ind': ind, 't0': np.where(ind >= 0, (ind - plan.pretrigger) / self._fs, -999999.0),
+                'amps': o[:, 3:3 + m], 'chi2_nodelay': o[:, 3 + m], 'amps_nodelay': o[:, 4 + m:4 + 2 * m]}
 
     @property
     def single(self):

@@ -231,6 +231,88 @@ class OFPlan:
         return n.value
 
 
+class NxMPlan:
+    """Batched NxM optimal filter (``qp.OFnxm``): n channels with an [n, n, N] cross-spectral density, m templates
+    [n, m, N] sharing one time delay.  Output row: chi0, chi2, index, amps[m], chi2_nodelay, amps_nodelay[m]."""
+
+    def __init__(self, nb_samples, sample_rate, n_chan, n_templ, precision='f64'):
+        if precision not in _PREC:
+            raise ValueError(f'unknown precision "{precision}"')
+        self.nb_samples, self.sample_rate = int(nb_samples), float(sample_rate)
+        self.n_chan, self.n_templ = int(n_chan), int(n_templ)
+        self._h = C.c_void_p()
+        check(lib.dp_nxm_plan_create(C.byref(self._h), self.nb_samples, self.sample_rate, self.n_chan, self.n_templ,
+                                     _PREC[precision]))
+        self.finalized = False
+        self.n_out = 4 + 2 * self.n_templ
+        self.pretrigger = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib.dp_nxm_plan_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def set_filter(self, templates, csd, pretrigger_samples=None, coupling='AC'):
+        templates = np.ascontiguousarray(templates, dtype=np.float64)
+        csd = np.ascontiguousarray(csd, dtype=np.complex128)
+        if templates.shape != (self.n_chan, self.n_templ, self.nb_samples):
+            raise ValueError(f'templates must be [n_chan, n_templ, nb_samples], got {templates.shape}')
+        if csd.shape != (self.n_chan, self.n_chan, self.nb_samples):
+            raise ValueError(f'csd must be [n_chan, n_chan, nb_samples], got {csd.shape}')
+        pre = self.nb_samples // 2 if pretrigger_samples is None else int(pretrigger_samples)
+        check(lib.dp_nxm_plan_set_filter(self._h, C.c_void_p(templates.ctypes.data), C.c_void_p(csd.ctypes.data), pre,
+                                         int(coupling == 'AC')))
+        self.pretrigger = pre
+
+    def set_window(self, window_lo=None, window_hi=None, outside=False):
+        lo = 0 if window_lo is None else int(window_lo)
+        hi = self.nb_samples if window_hi is None else int(window_hi)
+        check(lib.dp_nxm_plan_set_window(self._h, lo, hi, int(bool(outside))))
+
+    def finalize(self, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.DetprocessB200Error('no CUDA device: detprocess_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        check(lib.dp_nxm_plan_finalize(self._h, device.index or 0))
+        self.device = device
+        self.finalized = True
+        return self
+
+    def p_matrix(self):
+        P = np.empty((self.n_templ, self.n_templ))
+        Pinv = np.empty_like(P)
+        check(lib.dp_nxm_plan_get_p_matrix(self._h, C.c_void_p(P.ctypes.data), C.c_void_p(Pinv.ctypes.data)))
+        return P, Pinv
+
+    def run(self, traces, out=None):
+        """traces: CUDA float64 [B, n_chan, N].  Returns CUDA float64 [B, n_out].  Async."""
+        torch = _torch()
+        if not self.finalized:
+            raise _lib.DetprocessB200Error('plan not finalized')
+        if not traces.is_cuda or traces.dtype != torch.float64:
+            raise ValueError('run() takes CUDA float64 tensors')
+        if traces.ndim != 3 or traces.shape[1] != self.n_chan or traces.shape[2] != self.nb_samples:
+            raise ValueError(f'traces must be [B, {self.n_chan}, {self.nb_samples}], got {tuple(traces.shape)}')
+        traces = traces.contiguous()
+        nev = traces.shape[0]
+        if out is None:
+            out = torch.empty((nev, self.n_out), dtype=torch.float64, device=traces.device)
+        check(lib.dp_ofnxm_batch(self._h, C.c_void_p(traces.data_ptr()), nev, self.n_chan * self.nb_samples, self.nb_samples,
+                                 C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
+        return out
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(lib.dp_nxm_plan_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
 class ReducePlan:
     """Bit-exact windowed baseline / integral / maximum / minimum for ``n_chan`` channels."""
 

@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "../../include/detprocess_b200.h"
+#include "dp_nxm_launch.hpp"
+#include "dp_nxm_plan.hpp"
 #include "dp_of2_launch.hpp"
 #include "dp_of_launch.hpp"
 #include "dp_plan.hpp"
@@ -654,8 +656,10 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
     DP_CUDA(cudaSetDevice(p->device));
     const size_t esz = in_dtype == DP_IN_F64 ? 8 : (in_dtype == DP_IN_F32 ? 4 : 2);
     const size_t ev_bytes = (size_t)p->n_chan * (size_t)row_stride * esz;
-    // chunk: ~256 MiB of traces per stage
+    // chunk: <= 256 MiB of traces per stage and at least four stages per call (the copy of one overlaps the kernel of
+    // the previous one), but no fewer than 512 events (a few per CTA)
     long long chunk = std::max<long long>(1, (256LL << 20) / (long long)ev_bytes);
+    chunk = std::min(chunk, std::max<long long>(512, (n_events + 3) / 4));
     chunk = std::min(chunk, n_events);
     if (p->stage_events < chunk || p->stage_dtype != in_dtype || p->stage_stride != row_stride) {
         for (int i = 0; i < 2; ++i) {
@@ -1411,6 +1415,213 @@ int dp_trigger_plan_last_kernel_ms(dp_trigger_plan* p, float* filter_ms, float* 
     DP_CUDA(cudaEventSynchronize(p->ev2));
     if (filter_ms) DP_CUDA(cudaEventElapsedTime(filter_ms, p->ev0, p->ev1));
     if (group_ms) DP_CUDA(cudaEventElapsedTime(group_ms, p->ev1, p->ev2));
+    return DP_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================= NxM plan
+struct dp_nxm_plan {
+    int N = 0, n = 0, m = 0, precision = DP_PREC_F64;
+    double fs = 0;
+    int r1 = 0;
+    dpnxm::Setup setup;
+    bool have_filter = false, finalized = false;
+    double rms = 1.0;
+    bool ac = true;
+    int lo = 0, hi = 0, outside = 0;
+    int device = 0;
+    double scale = 1.0;
+    int subtract_first = 0;
+    std::vector<void*> owned;
+    DpNxmParams<double> prm64;
+    DpNxmParams<f2> prm32;
+    int grid_max = 0, threads = 0;
+    size_t smem = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+template <class T> int nxm_finalize(dp_nxm_plan* p, DpNxmParams<T>& prm) {
+    using S = typename Dp2Traits<T>::S;
+    dpnxm::Tables<T> dt;
+    try {
+        switch (p->r1) {
+            case 2: dt = dpnxm::build_tables<T, 2>(p->setup, p->scale); break;
+            case 4: dt = dpnxm::build_tables<T, 4>(p->setup, p->scale); break;
+            default: dt = dpnxm::build_tables<T, 8>(p->setup, p->scale); break;
+        }
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_INVALID, e.what());
+    }
+    std::memset(&prm, 0, sizeof(prm));
+    int rc;
+    if ((rc = upload(p->owned, dt.tw1, &prm.tw1))) return rc;
+    if ((rc = upload(p->owned, dt.tw2, &prm.tw2))) return rc;
+    if ((rc = upload(p->owned, dt.tw3, &prm.tw3))) return rc;
+    if ((rc = upload(p->owned, dt.twn, &prm.twn))) return rc;
+    if ((rc = upload(p->owned, dt.groups, &prm.groups))) return rc;
+    for (int i = 0; i < p->m; ++i)
+        for (int a = 0; a < p->n; ++a) {
+            if ((rc = upload(p->owned, dt.g[(size_t)i * p->n + a], &prm.g[i][a]))) return rc;
+            if ((rc = upload(p->owned, dt.g_self[(size_t)i * p->n + a], &prm.g_self[i][a]))) return rc;
+        }
+    for (int a = 0; a < p->n; ++a) {
+        if ((rc = upload(p->owned, dt.wd[a], &prm.wd[a]))) return rc;
+        if ((rc = upload(p->owned, dt.wd_self[a], &prm.wd_self[a]))) return rc;
+    }
+    for (size_t k = 0; k < dt.wo.size(); ++k) {
+        if ((rc = upload(p->owned, dt.wo[k], &prm.wo[k]))) return rc;
+        if ((rc = upload(p->owned, dt.wo_self[k], &prm.wo_self[k]))) return rc;
+    }
+    std::memcpy(prm.cmat, dt.cmat, sizeof(prm.cmat));
+    std::memcpy(prm.amat, dt.amat, sizeof(prm.amat));
+    const int prec = sizeof(S) == 8 ? 0 : 1;
+    const int src = dp_nxm_setup_table[prec](p->r1, p->device, &p->smem, &p->grid_max, &p->threads);
+    if (src == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");
+    if (src != 0) return fail(DP_ERR_CUDA, std::string("NxM kernel setup: ") + cudaGetErrorString((cudaError_t)src));
+    prm.scratch_per_cta = dp_nxm_scratch_table[prec](p->r1, p->n, p->m);
+    void* scr = nullptr;
+    DP_CUDA(cudaMalloc(&scr, sizeof(cx<T>) * (size_t)prm.scratch_per_cta * (size_t)p->grid_max));
+    p->owned.push_back(scr);
+    prm.scratch = reinterpret_cast<cx<T>*>(scr);
+    prm.n_chan = p->n;
+    prm.n_templ = p->m;
+    prm.pretrigger = p->setup.pretrigger;
+    prm.n_out = 4 + 2 * p->m;
+    prm.scale = p->scale;
+    prm.subtract_first = p->subtract_first;
+    return DP_OK;
+}
+template <class T> int nxm_run(dp_nxm_plan* p, DpNxmParams<T> prm, const double* traces, long long n_events, long long ev_stride,
+                               long long chan_stride, double* out, cudaStream_t st) {
+    prm.traces = traces;
+    prm.ev_stride = ev_stride;
+    prm.chan_stride = chan_stride;
+    prm.n_events = (int)n_events;
+    prm.lo = p->lo;
+    prm.hi = p->hi;
+    prm.outside = p->outside;
+    prm.out = out;
+    const int grid = (int)std::min<long long>(n_events, p->grid_max);
+    DP_CUDA(cudaEventRecord(p->ev0, st));
+    const int prec = sizeof(typename Dp2Traits<T>::S) == 8 ? 0 : 1;
+    const int rc = dp_nxm_launch_table[prec](p->r1, &prm, grid, p->smem, st);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("NxM kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    DP_CUDA(cudaEventRecord(p->ev1, st));
+    p->timed = true;
+    return DP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dp_nxm_plan_create(dp_nxm_plan** plan, int nb_samples, double sample_rate, int n_chan, int n_templ, int precision) {
+    if (!plan) return fail(DP_ERR_INVALID, "null plan pointer");
+    if (!dpplan2::r1_of(nb_samples)) return fail(DP_ERR_UNSUPPORTED, "the NxM filter needs nb_samples 16384, 32768 or 65536");
+    if (n_chan < 1 || n_chan > DP_NXM_MAX_CHAN) return fail(DP_ERR_INVALID, "n_chan must be 1.." + std::to_string(DP_NXM_MAX_CHAN));
+    if (n_templ < 1 || n_templ > DP_NXM_MAX_TEMPL) return fail(DP_ERR_INVALID, "n_templ must be 1.." + std::to_string(DP_NXM_MAX_TEMPL));
+    if (!(sample_rate > 0)) return fail(DP_ERR_INVALID, "sample_rate must be > 0");
+    if (precision != DP_PREC_F64 && precision != DP_PREC_F32) return fail(DP_ERR_INVALID, "unknown precision");
+    auto p = std::make_unique<dp_nxm_plan>();
+    p->N = nb_samples;
+    p->fs = sample_rate;
+    p->n = n_chan;
+    p->m = n_templ;
+    p->precision = precision;
+    p->r1 = dpplan2::r1_of(nb_samples);
+    p->hi = nb_samples;
+    *plan = p.release();
+    return DP_OK;
+}
+
+void dp_nxm_plan_destroy(dp_nxm_plan* p) {
+    if (!p) return;
+    for (void* d : p->owned) cudaFree(d);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+int dp_nxm_plan_set_filter(dp_nxm_plan* p, const double* templates, const double* csd, int pretrigger_samples, int coupling_ac) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    if (!templates || !csd) return fail(DP_ERR_INVALID, "null templates / csd");
+    if (pretrigger_samples < 0 || pretrigger_samples >= p->N) return fail(DP_ERR_INVALID, "pretrigger_samples out of range");
+    try {
+        p->setup = dpnxm::make_setup(p->N, p->fs, p->n, p->m, templates, csd, pretrigger_samples, coupling_ac != 0);
+        p->rms = dpnxm::typical_rms(p->setup, csd);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_INVALID, e.what());
+    }
+    p->ac = coupling_ac != 0;
+    p->have_filter = true;
+    return DP_OK;
+}
+
+int dp_nxm_plan_set_window(dp_nxm_plan* p, int window_lo, int window_hi, int outside) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (window_lo < 0 || window_hi > p->N || window_lo > window_hi) return fail(DP_ERR_INVALID, "bad delay window");
+    p->lo = window_lo;
+    p->hi = window_hi;
+    p->outside = outside ? 1 : 0;
+    return DP_OK;
+}
+
+int dp_nxm_plan_finalize(dp_nxm_plan* p, int device) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    if (!p->have_filter) return fail(DP_ERR_STATE, "set the templates and the csd first");
+    p->device = device;
+    DP_CUDA(cudaSetDevice(device));
+    if (p->precision == DP_PREC_F32) {
+        p->scale = std::exp2(-std::round(std::log2(p->rms)));
+        p->subtract_first = p->ac ? 1 : 0;
+    }
+    const int rc = p->precision == DP_PREC_F32 ? nxm_finalize<f2>(p, p->prm32) : nxm_finalize<double>(p, p->prm64);
+    if (rc) return rc;
+    DP_CUDA(cudaEventCreate(&p->ev0));
+    DP_CUDA(cudaEventCreate(&p->ev1));
+    p->finalized = true;
+    return DP_OK;
+}
+
+int dp_nxm_plan_n_out(const dp_nxm_plan* p, int* n_out) {
+    if (!p || !n_out) return fail(DP_ERR_INVALID, "null argument");
+    *n_out = 4 + 2 * p->m;
+    return DP_OK;
+}
+
+int dp_nxm_plan_get_p_matrix(const dp_nxm_plan* p, double* p_matrix, double* p_inverse) {
+    if (!p || !p->have_filter) return fail(DP_ERR_STATE, "no filter set");
+    for (int i = 0; i < p->m * p->m; ++i) {
+        if (p_matrix) p_matrix[i] = p->setup.P[i];
+        if (p_inverse) p_inverse[i] = p->setup.Pinv[i];
+    }
+    return DP_OK;
+}
+
+int dp_ofnxm_batch(dp_nxm_plan* p, const double* traces_dev, long long n_events, long long event_stride, long long chan_stride,
+                   double* out_dev, void* stream) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
+    if (n_events == 0) return DP_OK;
+    if (!traces_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if (chan_stride < p->N || (chan_stride & 1) || (event_stride & 1) || event_stride < chan_stride * (p->n - 1) + p->N)
+        return fail(DP_ERR_INVALID, "strides must be even, chan_stride >= nb_samples, event_stride >= the channels of an event");
+    if ((reinterpret_cast<uintptr_t>(traces_dev) & 15) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
+    if (n_events > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    DP_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p->precision == DP_PREC_F32) return nxm_run<f2>(p, p->prm32, traces_dev, n_events, event_stride, chan_stride, out_dev, st);
+    return nxm_run<double>(p, p->prm64, traces_dev, n_events, event_stride, chan_stride, out_dev, st);
+}
+
+int dp_nxm_plan_last_kernel_ms(dp_nxm_plan* p, float* ms) {
+    if (!p || !p->finalized || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
+    DP_CUDA(cudaEventSynchronize(p->ev1));
+    DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
     return DP_OK;
 }
 

@@ -1,0 +1,416 @@
+// Fused N-channel x M-template optimal filter (OFnxm) on the v2 FFT core (nb_samples 16384 / 32768 / 65536).
+//
+// One CTA fits one event: the n channel traces are transformed one after the other (forward half of
+// dp_of2_kernel.cuh), their spectra X_a parked in a thread-private L2 column, and per template i
+//     Q_i[k] = sum_a G_ia[k] X_a[k]          (G = conj(S)^T Sigma^-1, hermitian-folded, roll / scalings folded in)
+// goes through the inverse passes; the time series q~_i(t) = q_i(t) / P_ii of the first m - 1 templates are parked
+// too, and while the last one is in registers
+//     dchi2(t) = sum_ij C_ij q~_i(t) q~_j(t)     (C = P^-1 scaled by P_ii P_jj)
+// is scanned for its first maximum inside / outside the delay window.  chi0 is the CSD quadratic form
+// sum_k X^H Sigma^-1 X on the same spectra (Parseval), chi2 = chi0 - dchi2(t_best), amps = P^-1 q(t_best); the
+// no-delay fit reads q~(pretrigger).
+//
+// Replaces qp.OFnxm(of_base, channels, template_tag).calc() + get_fit_withdelay(...) + get_fit_nodelay() as driven by
+// FeatureExtractors.ofnxm (reference detprocess/core/algorithms.py:141-274).
+#pragma once
+#include "dp_of2_kernel.cuh"
+
+#define DP_NXM_MAX_CHAN 4
+#define DP_NXM_MAX_TEMPL 3
+#define DP_NXM_MAX_PAIRS (DP_NXM_MAX_CHAN * (DP_NXM_MAX_CHAN - 1) / 2)
+
+template <class T> struct DpNxmParams {
+    using S = typename Dp2Traits<T>::S;
+    const double* traces;    // [n_events][n_chan][N] float64
+    long long ev_stride;     // elements between events
+    long long chan_stride;   // elements between the channels of an event
+    int n_events;
+    int n_chan, n_templ;
+    const cx<T>* tw1;
+    const cx<T>* tw2;
+    const cx<T>* tw3;
+    const cx<S>* twn;
+    const int2* groups;
+    const cx<T>* g[DP_NXM_MAX_TEMPL][DP_NXM_MAX_CHAN];       // [NPH][16][NT] thread-order filters
+    const cx<S>* g_self[DP_NXM_MAX_TEMPL][DP_NXM_MAX_CHAN];  // [17][2]
+    const T* wd[DP_NXM_MAX_CHAN];                            // chi0 weights, diagonal (real)
+    const S* wd_self[DP_NXM_MAX_CHAN];
+    const cx<T>* wo[DP_NXM_MAX_PAIRS];                       // chi0 weights, a < b: 2 * W_ab
+    const cx<S>* wo_self[DP_NXM_MAX_PAIRS];
+    double cmat[DP_NXM_MAX_TEMPL][DP_NXM_MAX_TEMPL];         // dchi2 = sum_ij cmat_ij q~_i q~_j
+    double amat[DP_NXM_MAX_TEMPL][DP_NXM_MAX_TEMPL];         // amps_i = sum_j amat_ij q~_j
+    int pretrigger;
+    int lo, hi, outside;     // delay window in rolled indices
+    cx<T>* scratch;
+    long long scratch_per_cta;  // V units
+    double* out;             // [n_events][n_out]: chi0, chi2, index, amps[m], chi2_nodelay, amps_nodelay[m]
+    int n_out;
+    double scale;
+    int subtract_first;
+};
+
+template <class T, int R1> struct DpNxmKernel {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    using V = cx<T>;
+    using Core = Dp2Core<T, R1, 0>;
+    using OF = Dp2OfKernel<T, R1, 0>;
+    static constexpr int NT = G::NT, VL = G::VL, NB = G::NB, NPH = G::NPH, VPB = G::VPB, GC = G::GC, NC = G::NC, N = G::N;
+    static constexpr int NW = NT / 32;
+    static constexpr int SX = 34;  // X of the 17 self pairs, per channel
+    static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (32 + SX * DP_NXM_MAX_CHAN) + sizeof(double) * 32 +
+                                         sizeof(DpBest<S>) * 32 + 64;
+    // scratch per CTA (V units)
+    static constexpr long long SCR_X = (long long)16 * NT;              // per channel: X of the current phase
+    static constexpr long long SCR_PARK = (long long)(NPH - 1) * NB * VPB;  // per template: parked block results
+    static constexpr long long SCR_Q = (long long)NC * R1 * NT;         // per template: q~_i(t), thread order
+    static DP_HD long long scratch_v(int n_chan, int n_templ) { return SCR_X * n_chan + (SCR_PARK + SCR_Q) * n_templ; }
+
+    // the real sample with rolled index r of a parked series
+    static DP_DEV S sample_at(const V* q, int r) {
+        const int part = r & 1, c2 = r >> 1;
+        const int n1 = c2 / 4096, rem = c2 % 4096;
+        const int lane = rem % VL, col = rem / VL;
+        const int t = col % NT, ii = col / NT;
+        const S* ps = reinterpret_cast<const S*>(q + (long long)(ii * R1 + n1) * NT + t);
+#ifdef DP_HOST_EMU
+        return ps[part * VL + lane];
+#else
+        return __ldcg(ps + part * VL + lane);  // written by other threads of the CTA: read at L2
+#endif
+    }
+
+    static DP_DEV void retangle_all(V (&z)[16], cx<S> wn) {
+        static_assert(VL == 2, "packed fp32 only");
+#define DP2_FP(r)                                                                          \
+    {                                                                                      \
+        cx<S> Ck, Cm;                                                                      \
+        dp_retangle(dp2_lane0(z[r]), dp2_lane1(z[15 - r]), cmul(wn, dp_w64<S, 2 * r, -1>()), Ck, Cm); \
+        dp2_set0(z[r], Ck);                                                                \
+        dp2_set1(z[15 - r], Cm);                                                           \
+    }
+        DP2_FP(0) DP2_FP(1) DP2_FP(2) DP2_FP(3) DP2_FP(4) DP2_FP(5) DP2_FP(6) DP2_FP(7)
+        DP2_FP(8) DP2_FP(9) DP2_FP(10) DP2_FP(11) DP2_FP(12) DP2_FP(13) DP2_FP(14) DP2_FP(15)
+#undef DP2_FP
+    }
+
+    static DP_DEV void run(const DpNxmParams<T>& prm, unsigned char* smem_raw) {
+        V* const buf = reinterpret_cast<V*>(smem_raw);
+        cx<S>* const sp = reinterpret_cast<cx<S>*>(buf + G::SMEM_V);  // [32] self-paired group values
+        cx<S>* const sx = sp + 32;                                    // [n_chan][17][2]
+        double* const red = reinterpret_cast<double*>(sx + SX * DP_NXM_MAX_CHAN);
+        DpBest<S>* const best = reinterpret_cast<DpBest<S>*>(red + 32);
+        const int tid = threadIdx.x;
+        const int nch = prm.n_chan, ntm = prm.n_templ;
+        V* const scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
+        V* const scr_park = scr_x + SCR_X * nch;
+        V* const scr_q = scr_park + SCR_PARK * ntm;
+        constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
+        const unsigned long long pol = dp2_policy_keep();
+
+        for (int ev = blockIdx.x; ev < prm.n_events; ev += gridDim.x) {
+            const double* xev = prm.traces + (long long)ev * prm.ev_stride;
+            S chi = (S)0;
+            DpBest<S> tb{(S)0, -1};
+
+#pragma unroll 1
+            for (int p = 0; p < NPH; ++p) {
+                V z[16];
+                [[maybe_unused]] V zm[VL == 1 ? 8 : 1];
+                const int2 gg = prm.groups[p * NT + tid];
+                const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
+                const bool special = (p == 0) && (tid < NSPECIAL);
+                [[maybe_unused]] int Gp = 0;
+                if constexpr (VL == 1) Gp = __shfl_xor_sync(0xffffffffu, gg.x, 1);
+
+                // ---------------- forward of phase p, channel by channel: X_a -> scratch column -------------
+#pragma unroll 1
+                for (int a = 0; a < nch; ++a) {
+                    const double* xrow = xev + (long long)a * prm.chan_stride;
+                    const double x0 = prm.subtract_first ? dp_load_first<0>(xrow) : 0.0;
+                    Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
+                    __syncthreads();
+                    Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+                    if (p == 0 && tid < 32) {
+                        if constexpr (VL == 2) {
+                            if (tid == 0) {
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) {
+                                    sp[r] = dp2_lane0(z[r]);
+                                    sp[16 + r] = dp2_lane1(z[r]);
+                                }
+                            }
+                        } else {
+                            if (tid < 2) {
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) sp[16 * tid + r] = z[r];
+                            }
+                        }
+                        __syncwarp();
+                        if (tid < 17) {
+                            const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
+                            cx<S> sXk, sXm;
+                            dp_untangle(sp[sl.ek], sp[sl.em], sl.w, sXk, sXm);
+                            sx[a * SX + 2 * tid] = sXk;
+                            sx[a * SX + 2 * tid + 1] = sXm;
+                        }
+                        __syncwarp();
+                    }
+                    V* dst = scr_x + SCR_X * a + tid;
+                    if constexpr (VL == 2) {
+                        (void)OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
+                    } else {
+                        OF::pw_publish(buf, z, gg.x);
+                        OF::pw_untangle(buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) {
+                            dp2_st_keep(dst + (2 * r) * NT, Xk, pol);
+                            dp2_st_keep(dst + (2 * r + 1) * NT, Xm, pol);
+                        });
+                    }
+                    __syncthreads();  // group-row reads of this channel precede the next pass-1 stores
+                }
+
+                // ---------------- chi0: the CSD quadratic form at the thread's bins ------------------------
+                {
+                    T acc = (T)0.0f;
+#pragma unroll 2
+                    for (int r = 0; r < 16; ++r) {
+                        V X[DP_NXM_MAX_CHAN];
+#pragma unroll
+                        for (int a = 0; a < DP_NXM_MAX_CHAN; ++a)
+                            if (a < nch) X[a] = dp2_ld_keep(scr_x + SCR_X * a + r * NT + tid, pol);
+                        const long long e = ((long long)p * 16 + r) * NT + tid;
+                        int pi = 0;
+#pragma unroll
+                        for (int a = 0; a < DP_NXM_MAX_CHAN; ++a) {
+                            if (a < nch) {
+                                acc = dp_fma(dp_ldg(prm.wd[a] + e), cnorm2(X[a]), acc);
+#pragma unroll
+                                for (int b = a + 1; b < DP_NXM_MAX_CHAN; ++b) {
+                                    if (b < nch) {
+                                        const V t = cmul(dp_ldg(prm.wo[pi] + e), X[b]);
+                                        acc = dp_fma(X[a].re, t.re, acc);
+                                        acc = dp_fma(X[a].im, t.im, acc);
+                                        ++pi;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (!special) {
+                        if constexpr (VL == 2) chi += acc.x + acc.y; else chi += acc;
+                    }
+                    if (p == 0 && tid < 17) {
+                        int pi = 0;
+                        for (int a = 0; a < nch; ++a) {
+                            const cx<S> Xk = sx[a * SX + 2 * tid], Xm = sx[a * SX + 2 * tid + 1];
+                            chi = dp_fma(dp_ldg(prm.wd_self[a] + 2 * tid), cnorm2(Xk), chi);
+                            chi = dp_fma(dp_ldg(prm.wd_self[a] + 2 * tid + 1), cnorm2(Xm), chi);
+                            for (int b = a + 1; b < nch; ++b, ++pi) {
+                                const cx<S> tk = cmul(dp_ldg(prm.wo_self[pi] + 2 * tid), sx[b * SX + 2 * tid]);
+                                const cx<S> tm = cmul(dp_ldg(prm.wo_self[pi] + 2 * tid + 1), sx[b * SX + 2 * tid + 1]);
+                                chi = dp_fma(Xk.re, tk.re, chi);
+                                chi = dp_fma(Xk.im, tk.im, chi);
+                                chi = dp_fma(Xm.re, tm.re, chi);
+                                chi = dp_fma(Xm.im, tm.im, chi);
+                            }
+                        }
+                    }
+                }
+
+                // ---------------- per template: Q_i = sum_a G_ia X_a, inverse passes 4' 3' 2' ---------------
+#pragma unroll 1
+                for (int it = 0; it < ntm; ++it) {
+                    V* park = scr_park + SCR_PARK * it;
+                    V* qout = scr_q + SCR_Q * it;
+                    if (p == 0 && tid < 17) {
+                        const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
+                        cx<S> Fk{(S)0, (S)0}, Fm{(S)0, (S)0};
+                        for (int a = 0; a < nch; ++a) {
+                            const cx<S> gk = dp_ldg(prm.g_self[it][a] + 2 * tid), gm = dp_ldg(prm.g_self[it][a] + 2 * tid + 1);
+                            const cx<S> tk = cmul(gk, sx[a * SX + 2 * tid]), tm = cmul(gm, sx[a * SX + 2 * tid + 1]);
+                            Fk.re += tk.re;
+                            Fk.im += tk.im;
+                            Fm.re += tm.re;
+                            Fm.im += tm.im;
+                        }
+                        cx<S> Ck, Cm;
+                        dp_retangle(Fk, Fm, sl.w, Ck, Cm);
+                        sp[sl.ek] = Ck;
+                        if (sl.ek != sl.em) sp[sl.em] = Cm;
+                    }
+                    const long long e0 = (long long)p * 16 * NT + tid;
+                    if constexpr (VL == 2) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            V f = cmul(dp_ldg(prm.g[it][0] + e0 + r * NT), dp2_ld_keep(scr_x + r * NT + tid, pol));
+#pragma unroll
+                            for (int a = 1; a < DP_NXM_MAX_CHAN; ++a) {
+                                if (a < nch) {
+                                    const V t = cmul(dp_ldg(prm.g[it][a] + e0 + r * NT), dp2_ld_keep(scr_x + SCR_X * a + r * NT + tid, pol));
+                                    f.re = f.re + t.re;
+                                    f.im = f.im + t.im;
+                                }
+                            }
+                            z[r] = f;
+                        }
+                        retangle_all(z, wn);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            V Fk = cmul(dp_ldg(prm.g[it][0] + e0 + (2 * r) * NT), dp2_ld_keep(scr_x + (2 * r) * NT + tid, pol));
+                            V Fm = cmul(dp_ldg(prm.g[it][0] + e0 + (2 * r + 1) * NT), dp2_ld_keep(scr_x + (2 * r + 1) * NT + tid, pol));
+#pragma unroll
+                            for (int a = 1; a < DP_NXM_MAX_CHAN; ++a) {
+                                if (a < nch) {
+                                    const V tk = cmul(dp_ldg(prm.g[it][a] + e0 + (2 * r) * NT),
+                                                      dp2_ld_keep(scr_x + SCR_X * a + (2 * r) * NT + tid, pol));
+                                    const V tm = cmul(dp_ldg(prm.g[it][a] + e0 + (2 * r + 1) * NT),
+                                                      dp2_ld_keep(scr_x + SCR_X * a + (2 * r + 1) * NT + tid, pol));
+                                    Fk.re = Fk.re + tk.re;
+                                    Fk.im = Fk.im + tk.im;
+                                    Fm.re = Fm.re + tm.re;
+                                    Fm.im = Fm.im + tm.im;
+                                }
+                            }
+                            cx<S> Ck, Cm;
+                            dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
+                            z[r] = Ck;
+                            buf[Gp * 17 + 15 - r] = Cm;
+                        }
+                        OF::pw_collect(buf, z, gg.x);
+                    }
+                    if (p == 0 && tid < 32) {
+                        __syncwarp();
+                        if constexpr (VL == 2) {
+                            if (tid == 0) {
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) z[r] = V{f2(sp[r].re, sp[16 + r].re), f2(sp[r].im, sp[16 + r].im)};
+                            }
+                        } else {
+                            if (tid < 2) {
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) z[r] = sp[16 * tid + r];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    Core::inv_432(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+                    if (p < NPH - 1) {
+                        Core::park_pass2(park, p, z);
+                        __syncthreads();
+                        continue;
+                    }
+                    // ------------ last phase: pass 1' over all blocks -> q~_i(t); last template: dchi2 scan ------
+                    Core::store_pass2(buf, z);
+                    __syncthreads();
+                    const bool last = it == ntm - 1;
+                    const bool everything = prm.outside || (prm.lo == 0 && prm.hi == N);
+                    int nlo = everything ? 0 : (prm.lo >> 1), nhi = everything ? 0x7fffffff : ((prm.hi - 1) >> 1);
+                    {   // the no-delay sample is always needed
+                        const int np = prm.pretrigger >> 1;
+                        nlo = np < nlo ? np : nlo;
+                        nhi = np > nhi ? np : nhi;
+                    }
+#pragma unroll 1
+                    for (int i0 = 0; i0 < NC; i0 += GC) {
+                        V y[GC * R1];
+#pragma unroll
+                        for (int j = 0; j < GC * R1; ++j) y[j] = V{(T)0.0f, (T)0.0f};
+                        const unsigned computed = Core::inv_pass1(buf, park, prm.tw1, i0, y, nlo, nhi);
+                        if (computed == 0) continue;
+#pragma unroll
+                        for (int j = 0; j < GC * R1; ++j) dp2_st_keep(qout + (long long)(i0 * R1 + j) * NT + tid, y[j], pol);
+                        if (!last) continue;
+                        // dchi2 at the thread's samples (other templates from the thread's own parked values)
+                        const int il = ntm - 1;
+#pragma unroll
+                        for (int j = 0; j < GC * R1; ++j) {
+                            const V yl = y[j];
+                            const T cll = (T)(S)prm.cmat[il][il];
+                            T dre = cll * yl.re * yl.re, dim = cll * yl.im * yl.im;
+                            V yo[DP_NXM_MAX_TEMPL - 1];
+#pragma unroll
+                            for (int i = 0; i < DP_NXM_MAX_TEMPL - 1; ++i)
+                                if (i < il) yo[i] = dp2_ld_keep(scr_q + SCR_Q * i + (long long)(i0 * R1 + j) * NT + tid, pol);
+#pragma unroll
+                            for (int i = 0; i < DP_NXM_MAX_TEMPL - 1; ++i) {
+                                if (i < il) {
+                                    const T cil = (T)(S)(2.0 * prm.cmat[i][il]);
+                                    dre = dp_fma(cil * yo[i].re, yl.re, dre);
+                                    dim = dp_fma(cil * yo[i].im, yl.im, dim);
+#pragma unroll
+                                    for (int k = i; k < DP_NXM_MAX_TEMPL - 1; ++k) {
+                                        if (k < il) {
+                                            const T cik = (T)(S)((k == i ? 1.0 : 2.0) * prm.cmat[i][k]);
+                                            dre = dp_fma(cik * yo[i].re, yo[k].re, dre);
+                                            dim = dp_fma(cik * yo[i].im, yo[k].im, dim);
+                                        }
+                                    }
+                                }
+                            }
+                            y[j] = V{dre, dim};
+                        }
+                        if (prm.lo == 0 && prm.hi == N && !prm.outside)
+                            Dp2Scan<T, R1>::full(y, tid, i0, tb);
+                        else
+                            Dp2Scan<T, R1>::window(y, tid, i0, prm.lo, (unsigned)(prm.hi - prm.lo), prm.outside != 0, tb, computed);
+                    }
+                    if (!last) {
+                        __syncthreads();  // pass-1' reads of buf precede the next template's group stores
+                        continue;
+                    }
+                    // ------------ winner, chi0, outputs ---------------------------------------------------
+                    {
+                        const DpBest<S> b = dp_warp_best(tb);
+                        const double c = dp_warp_sum((double)chi);
+                        if ((tid & 31) == 0) {
+                            best[tid >> 5] = b;
+                            red[tid >> 5] = c;
+                        }
+                    }
+                    __syncthreads();  // also orders the parked q~ values (global memory) within the CTA
+                    if (tid == 0) {
+                        double chi0 = 0.0;
+                        for (int w = 0; w < NW; ++w) chi0 += red[w];
+                        DpBest<S> b = best[0];
+                        for (int w = 1; w < NW; ++w) dp_best_merge(b, best[w]);
+                        double* o = prm.out + (long long)ev * prm.n_out;
+                        o[0] = chi0;
+                        for (int f = 0; f < 2; ++f) {
+                            const int idx = f == 0 ? b.idx : prm.pretrigger;
+                            double* of = o + 1 + f * (2 + ntm);
+                            if (idx < 0) {  // empty window
+                                for (int i = 0; i < (f == 0 ? 2 : 1) + ntm; ++i) of[i] = -999999.0;
+                                continue;
+                            }
+                            double q[DP_NXM_MAX_TEMPL];
+                            for (int i = 0; i < ntm; ++i) q[i] = (double)sample_at(scr_q + SCR_Q * i, idx);
+                            double d = 0.0;
+                            for (int i = 0; i < ntm; ++i)
+                                for (int k = 0; k < ntm; ++k) d += prm.cmat[i][k] * q[i] * q[k];
+                            int oi = 0;
+                            of[oi++] = chi0 - d;
+                            if (f == 0) of[oi++] = (double)idx;
+                            for (int i = 0; i < ntm; ++i) {
+                                double am = 0.0;
+                                for (int k = 0; k < ntm; ++k) am += prm.amat[i][k] * q[k];
+                                of[oi++] = am;
+                            }
+                        }
+                    }
+                    __syncthreads();  // red / best / scratch are reused by the next event
+                }
+            }
+        }
+    }
+};
+
+#ifndef DP_HOST_EMU
+template <class T, int R1>
+__global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, Dp2Geom<T, R1>::NT <= 256 ? 2 : 1) dp_nxm_kernel(const DpNxmParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char dp_smem_raw[];
+    DpNxmKernel<T, R1>::run(prm, dp_smem_raw);
+}
+#endif

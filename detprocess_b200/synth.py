@@ -115,3 +115,52 @@ class SynthSetup:
     def traces(self, nb_events, rank=0, **kwargs):
         rng = np.random.default_rng(self.seed + rank)
         return make_traces(nb_events, self.template, self.psd, self.fs, rng, **kwargs)
+
+
+class SynthNxM:
+    """n-channel, m-template setup for the NxM optimal filter: templates [n, m, N], a cross-spectral density [n, n, N]
+    (independent channel noise + a common-mode source that reaches channel a with gain c_a and a delay of a samples,
+    so the off-diagonal terms are complex), and correlated-noise traces [B, n, N] with both templates injected at one
+    common delay."""
+
+    def __init__(self, nb_samples=32768, n_chan=2, n_templ=2, fs=FS_DEFAULT, nb_pretrigger=None):
+        N = self.nb_samples = int(nb_samples)
+        self.fs = float(fs)
+        self.n_chan, self.n_templ = int(n_chan), int(n_templ)
+        self.nb_pretrigger = N // 2 if nb_pretrigger is None else int(nb_pretrigger)
+        shapes = [make_template(N, fs, self.nb_pretrigger),
+                  make_glitch_template(N, fs, self.nb_pretrigger),
+                  make_template(N, fs, self.nb_pretrigger, tau_rise=5e-6, tau_fall=60e-6)]
+        self.templates = np.zeros((self.n_chan, self.n_templ, N))
+        for a in range(self.n_chan):
+            for i in range(self.n_templ):
+                share = 1.0 if (a % self.n_templ) == i else 0.25 / (1 + abs(a - i))
+                self.templates[a, i] = share * shapes[i % 3]
+        self.psd_chan = [make_psd(N, fs, sigma=1e-11 * (1.0 + 0.3 * a)) for a in range(self.n_chan)]
+        self.psd_common = make_psd(N, fs, sigma=0.7e-11, f_corner=3e3)
+        self.gain_common = np.array([1.0, -0.6, 0.8, 0.5][:self.n_chan])
+        f = np.fft.fftfreq(N, d=1.0 / fs)
+        self.delay_phase = [np.exp(-2j * np.pi * f * (a / fs)) for a in range(self.n_chan)]   # delay of a samples
+        self.csd = np.zeros((self.n_chan, self.n_chan, N), dtype=np.complex128)
+        for a in range(self.n_chan):
+            for b in range(self.n_chan):
+                self.csd[a, b] = (self.gain_common[a] * self.gain_common[b] * self.psd_common
+                                  * self.delay_phase[a] * np.conj(self.delay_phase[b]))
+            self.csd[a, a] += self.psd_chan[a]
+
+    def traces(self, nb_events, rng=None, amp_max=2e-7, max_delay=300, pulse_fraction=0.9, return_truth=False):
+        rng = np.random.default_rng(SEED_DEFAULT) if rng is None else rng
+        N = self.nb_samples
+        common = make_noise(nb_events, self.psd_common, self.fs, rng)
+        x = np.zeros((nb_events, self.n_chan, N))
+        for a in range(self.n_chan):
+            x[:, a] = make_noise(nb_events, self.psd_chan[a], self.fs, rng) + self.gain_common[a] * np.roll(common, a, axis=-1)
+        has = rng.random(nb_events) < pulse_fraction
+        amps = np.where(has[:, None], rng.random((nb_events, self.n_templ)) * amp_max, 0.0)
+        delays = np.where(has, rng.integers(-max_delay, max_delay + 1, nb_events), 0)
+        for e in np.nonzero(has)[0]:
+            for i in range(self.n_templ):
+                x[e] += amps[e, i] * np.roll(self.templates[:, i], int(delays[e]), axis=-1)
+        if return_truth:
+            return x, amps, delays
+        return x

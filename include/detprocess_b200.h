@@ -203,6 +203,34 @@ int dp_trigger_run_raw(dp_trigger_plan* plan, const void* trace_dev, int in_dtyp
                        double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream);
 int dp_trigger_plan_last_kernel_ms(dp_trigger_plan* plan, float* filter_ms, float* group_ms);
 
+/* ------------------------------------------------------------------ NxM optimal filter
+ * Replaces qp.OFnxm(of_base, channels, template_tag).calc() + get_fit_withdelay(window...) + get_fit_nodelay() as driven
+ * per event by FeatureExtractors.ofnxm (reference detprocess/core/algorithms.py:141-274): n channels with an n x n
+ * cross-spectral density, m templates that share one time delay.  Output row per event (float64, n_out = 4 + 2 m):
+ *   chi0, chi2_constrained, index_constrained (rolled: zero delay = pretrigger_samples), amps_constrained[m],
+ *   chi2_nodelay, amps_nodelay[m].           t0 = (index - pretrigger_samples) / sample_rate. */
+typedef struct dp_nxm_plan dp_nxm_plan;
+int dp_nxm_plan_create(dp_nxm_plan** plan, int nb_samples, double sample_rate, int n_chan, int n_templ, int precision);
+void dp_nxm_plan_destroy(dp_nxm_plan* plan);
+/* templates: [n_chan][n_templ][nb_samples] float64 (of_base.template(channel, tag), algorithms.py:196);
+ * csd: [n_chan][n_chan][nb_samples] complex128 as (re, im) pairs, two-sided, fftfreq order (filterdata.py:380 get_csd);
+ * coupling_ac != 0 drops the DC bin as OFBase.set_csd(coupling='AC') does (processing_data.py:321-326) */
+int dp_nxm_plan_set_filter(dp_nxm_plan* plan, const double* templates, const double* csd, int pretrigger_samples,
+                           int coupling_ac);
+/* delay window [window_lo, window_hi) in rolled indices, outside != 0 searches the complement
+ * (window_min_index / window_max_index / lgc_outside_window of algorithms.py:146-150); default: every delay.
+ * May be changed between batches. */
+int dp_nxm_plan_set_window(dp_nxm_plan* plan, int window_lo, int window_hi, int outside);
+int dp_nxm_plan_finalize(dp_nxm_plan* plan, int device);
+int dp_nxm_plan_n_out(const dp_nxm_plan* plan, int* n_out);
+/* the m x m template matrix P (row major) and its inverse (qp.OFBase.calc_p_and_p_inverse) */
+int dp_nxm_plan_get_p_matrix(const dp_nxm_plan* plan, double* p_matrix, double* p_inverse);
+/* traces_dev: float64 [n_events][n_chan][nb_samples] with element strides event_stride / chan_stride;
+ * out_dev: [n_events][n_out] */
+int dp_ofnxm_batch(dp_nxm_plan* plan, const double* traces_dev, long long n_events, long long event_stride,
+                   long long chan_stride, double* out_dev, void* stream);
+int dp_nxm_plan_last_kernel_ms(dp_nxm_plan* plan, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

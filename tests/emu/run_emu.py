@@ -45,3 +45,41 @@ def run(traces, psd, templates, fits, fs, fcut=10000.0, precision='f64', ac=True
         subprocess.check_call([exe, fin, fout, precision] + (['p2'] if force_p2 else []))
         out = np.fromfile(fout, dtype=np.float64).reshape(nev, 1 + 5 * len(fits))
     return out
+
+
+def build_nxm(asan=False):
+    os.makedirs(os.path.join(HERE, '_build'), exist_ok=True)
+    exe = os.path.join(HERE, '_build', 'emu_nxm' + ('_asan' if asan else ''))
+    src = os.path.join(HERE, 'emu_nxm.cpp')
+    deps = [src] + [os.path.join(HERE, '../../detprocess_b200/csrc', f) for f in
+                    ('dp_of_kernel.cuh', 'dp_fft.cuh', 'dp_platform.cuh', 'dp_plan.hpp', 'dp_of2_kernel.cuh',
+                     'dp_plan2.hpp', 'dp_f2.cuh', 'dp_nxm_kernel.cuh', 'dp_nxm_plan.hpp')]
+    if os.path.exists(exe) and all(os.path.getmtime(exe) > os.path.getmtime(d) for d in deps):
+        return exe
+    cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-o', exe, src]
+    if asan:
+        cmd[3:3] = ['-fsanitize=address', '-fno-omit-frame-pointer', '-g']
+    subprocess.check_call(cmd)
+    return exe
+
+
+def run_nxm(traces, templates, csd, fs, pretrigger, window=(None, None, False), precision='f64', ac=True, asan=False):
+    """traces [B, n, N]; templates [n, m, N]; csd [n, n, N] complex; window (lo, hi, outside) in rolled indices."""
+    exe = build_nxm(asan)
+    traces = np.ascontiguousarray(traces, dtype=np.float64)
+    nev, n, N = traces.shape
+    m = templates.shape[1]
+    lo, hi, outside = window
+    lo = 0 if lo is None else lo
+    hi = N if hi is None else hi
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fin, 'wb') as f:
+            f.write(struct.pack('<9i', N, nev, n, m, pretrigger, int(ac), lo, hi, int(outside)))
+            f.write(struct.pack('<d', fs))
+            f.write(np.ascontiguousarray(templates, dtype=np.float64).tobytes())
+            f.write(np.ascontiguousarray(csd, dtype=np.complex128).tobytes())
+            f.write(traces.tobytes())
+        subprocess.check_call([exe, fin, fout, precision])
+        out = np.fromfile(fout, dtype=np.float64).reshape(nev, 4 + 2 * m)
+    return out

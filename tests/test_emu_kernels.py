@@ -118,6 +118,27 @@ def test_of_v2_kernel_emulated_address_sanitizer():
     assert np.array_equal(out[:, 2].astype(np.int64), o1['ind'][0])
 
 
+@pytest.mark.parametrize('precision,nb_samples,n,m', [('f64', 32768, 2, 2), ('f32', 16384, 3, 2), ('f64', 16384, 1, 3)])
+def test_nxm_kernel_emulated(precision, nb_samples, n, m):
+    """The NxM kernel source on host threads == the NxM oracle (tables, channel / template bookkeeping, barriers)."""
+    from detprocess_b200.synth import SynthNxM
+    from oracle.ofnxm import ofnxm_setup, ofnxm_batch
+    S = SynthNxM(nb_samples, n, m)
+    pre = S.nb_pretrigger
+    st = ofnxm_setup(S.templates, S.csd, S.fs, pre)
+    x = S.traces(3, np.random.default_rng(1))
+    tol = 1e-10 if precision == 'f64' else 2e-5
+    for win in [(pre - 500, pre + 500, False), (None, None, False), (pre - 100, pre + 50, True)]:
+        out = run_emu.run_nxm(x, S.templates, S.csd, S.fs, pre, win, precision=precision)
+        o = ofnxm_batch(x, st, win)
+        assert np.array_equal(out[:, 2].astype(np.int64), o['ind'])
+        assert np.max(np.abs(out[:, 0] / o['chi0'] - 1)) < tol
+        assert np.max(np.abs(out[:, 1] / o['chi2'] - 1)) < tol * 10
+        assert np.max(np.abs(out[:, 3:3 + m] - o['amps'])) < tol * np.max(np.abs(o['amps']))
+        assert np.max(np.abs(out[:, 3 + m] / o['chi2_0'] - 1)) < tol * 10
+        assert np.max(np.abs(out[:, 4 + m:] - o['amps0'])) < tol * np.max(np.abs(o['amps0']))
+
+
 def test_reduce_kernel_emulated_bit_exact():
     exe = os.path.join(HERE, 'emu', '_build', 'emu_reduce')
     src = os.path.join(HERE, 'emu', 'emu_reduce.cpp')

@@ -1,0 +1,108 @@
+"""GPU: fused NxM optimal filter (dp_nxm_kernel.cuh through dp_ofnxm_batch) == oracle/ofnxm.py.
+Tolerances: float64 mode amplitudes and chi2 to 1e-9 relative with identical delay index; float32 mode amplitudes to
+1e-5 of the largest amplitude and chi2 to 1e-4, index identical except on near-ties (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from detprocess_b200.synth import SynthNxM
+from oracle.ofnxm import ofnxm_setup, ofnxm_batch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'f64': dict(amp=1e-9, chi2=1e-9), 'f32': dict(amp=1e-5, chi2=1e-4)}
+
+
+def _plan(S, precision):
+    from detprocess_b200.core.plans import NxMPlan
+    plan = NxMPlan(S.nb_samples, S.fs, S.n_chan, S.n_templ, precision)
+    plan.set_filter(S.templates, S.csd, S.nb_pretrigger, 'AC')
+    plan.finalize()
+    return plan
+
+
+def _check(out, o, m, precision):
+    tol = TOL[precision]
+    same = out[:, 2].astype(np.int64) == o['ind']
+    if precision == 'f64':
+        assert same.all()
+    else:
+        assert same.mean() > 0.98
+    scale = np.max(np.abs(o['amps']))
+    assert np.max(np.abs(out[:, 0] / o['chi0'] - 1)) < tol['chi2']
+    assert np.max(np.abs(out[:, 1] / o['chi2'] - 1)[same]) < tol['chi2']
+    assert np.max(np.abs(out[:, 3:3 + m] - o['amps'])[same]) < tol['amp'] * scale
+    assert np.max(np.abs(out[:, 3 + m] / o['chi2_0'] - 1)) < tol['chi2']
+    assert np.max(np.abs(out[:, 4 + m:4 + 2 * m] - o['amps0'])) < tol['amp'] * scale
+
+
+@pytest.mark.parametrize('precision,nb_samples,n,m', [('f64', 32768, 2, 2), ('f32', 32768, 2, 2), ('f64', 16384, 3, 3),
+                                                      ('f32', 16384, 4, 1), ('f64', 65536, 2, 1), ('f32', 65536, 1, 2),
+                                                      ('f64', 16384, 4, 3)])
+def test_ofnxm_parity(precision, nb_samples, n, m):
+    import torch
+    S = SynthNxM(nb_samples, n, m)
+    pre = S.nb_pretrigger
+    st = ofnxm_setup(S.templates, S.csd, S.fs, pre)
+    x = S.traces(300 if nb_samples < 65536 else 150, np.random.default_rng(12345))
+    plan = _plan(S, precision)
+    P, Pinv = plan.p_matrix()
+    assert np.allclose(P, st['P'], rtol=1e-10) and np.allclose(Pinv, st['Pinv'], rtol=1e-8)
+    xd = torch.from_numpy(x).cuda()
+    for win in [(pre - 500, pre + 500, False), (None, None, False), (pre - 100, pre + 50, True)]:
+        plan.set_window(*win)
+        out = plan.run(xd).cpu().numpy()
+        _check(out, ofnxm_batch(x, st, win), m, precision)
+
+
+def test_ofnxm_noiseless_recovery_and_empty_window():
+    """Injected amplitudes / delay come back exactly (convention independent); an empty window gives the sentinel for
+    the delay fit and leaves the no-delay fit intact."""
+    import torch
+    S = SynthNxM(16384, 2, 2)
+    pre = S.nb_pretrigger
+    amps = np.array([[1.5, -0.5], [0.2, 3.0], [-2.0, 1e-3]])
+    delays = [0, 123, -250]
+    x = np.stack([sum(a[i] * np.roll(S.templates[:, i], d, axis=-1) for i in range(2)) for a, d in zip(amps, delays)])
+    plan = _plan(S, 'f64')
+    out = plan.run(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(out[:, 2].astype(int) - pre, delays)
+    assert np.allclose(out[:, 3:5], amps, rtol=1e-9)
+    assert np.all(np.abs(out[:, 1]) < 1e-8 * out[:, 0])
+    plan.set_window(pre, pre, False)
+    out2 = plan.run(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.all(out2[:, 1:5] == -999999.0)
+    assert np.allclose(out2[:, 5:], out[:, 5:], rtol=1e-12)
+
+
+def test_ofnxm_extractor_mirrors_reference_keys():
+    """FeatureExtractors.ofnxm(channel='a|b', of_base, template_tag=...) returns the reference's keys
+    (algorithms.py:229-272) with the oracle's numbers."""
+    from detprocess_b200.core import FeatureExtractors, OFBaseBatch
+    S = SynthNxM(16384, 2, 2)
+    pre = S.nb_pretrigger
+    x = S.traces(32, np.random.default_rng(7))
+    ofb = OFBaseBatch(S.fs)
+    ofb.set_csd('a|b', S.csd, coupling='AC')
+    ofb.add_template('a|b', S.templates, template_tag='shared', pretrigger_samples=pre)
+    ofb.calc_phi('a|b', template_tag='shared')
+    empty = FeatureExtractors.ofnxm('a|b', ofb, template_tag='shared', amplitude_names=['phonon', 'glitch'])
+    assert empty['chi2_ofnxm_constrained'] == -999999.0 and empty['glitch_ofnxm_nodelay'] == -999999.0
+    ofb.update_signal('a|b', x)
+    r = FeatureExtractors.ofnxm('a|b', ofb, template_tag='shared', amplitude_names=['phonon', 'glitch'],
+                                window_min_from_trig_usec=-400, window_max_from_trig_usec=400)
+    assert set(r) == {'chi2_ofnxm_constrained', 't0_ofnxm_constrained', 'phonon_ofnxm_constrained', 'glitch_ofnxm_constrained',
+                      'chi2_ofnxm_nodelay', 'phonon_ofnxm_nodelay', 'glitch_ofnxm_nodelay'}
+    o = ofnxm_batch(x, ofnxm_setup(S.templates, S.csd, S.fs, pre), (pre - 500, pre + 500, False))
+    assert np.allclose(r['t0_ofnxm_constrained'], o['t0'], rtol=0, atol=1e-12)
+    assert np.allclose(r['phonon_ofnxm_constrained'], o['amps'][:, 0], rtol=1e-8, atol=1e-9 * np.max(np.abs(o['amps'])))
+    assert np.allclose(r['chi2_ofnxm_nodelay'], o['chi2_0'], rtol=1e-9)
+    with pytest.raises(ValueError):
+        FeatureExtractors.ofnxm('a|b', ofb)                                   # template_tag is mandatory
+    with pytest.raises(ValueError):
+        FeatureExtractors.ofnxm('a|b', ofb, template_tag='shared', amplitude_names=['one'])
+    one = OFBaseBatch(S.fs)
+    one.set_csd('a|b', S.csd)
+    one.add_template('a|b', S.templates, template_tag='shared', pretrigger_samples=pre)
+    one.update_signal('a|b', x[0])
+    r1 = FeatureExtractors.ofnxm('a|b', one, template_tag='shared')
+    assert np.isscalar(r1['amp1_ofnxm_constrained']) or r1['amp1_ofnxm_constrained'].ndim == 0

@@ -72,10 +72,42 @@ def time_psd(N, prec, B):
     print(f'PSD N={N} {prec} B={B}: {m:.3f} ms {B/(m*1e-3)/1e6:.3f} Mtraces/s {B*N*8/(m*1e-3)/1e9:.0f} GB/s ({B*N*8/(m*1e-3)/1e9/6551*100:.1f}% HBM)', flush=True)
 
 
+def time_nxm(N, prec, B, n, m):
+    from detprocess_b200.synth import SynthNxM
+    from detprocess_b200.core.plans import NxMPlan
+    S = SynthNxM(N, n, m)
+    pre = S.nb_pretrigger
+    plan = NxMPlan(N, S.fs, n, m, prec)
+    plan.set_filter(S.templates, S.csd, pre, 'AC')
+    plan.set_window(pre - 500, pre + 500)
+    plan.finalize()
+    base = torch.from_numpy(S.traces(64, np.random.default_rng(1))).cuda()
+    x = base.repeat((B + 63) // 64, 1, 1)[:B].contiguous()
+    out = torch.empty((B, plan.n_out), dtype=torch.float64, device='cuda')
+    for _ in range(3):
+        plan.run(x, out)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        plan.run(x, out)
+        ms.append(plan.last_kernel_ms())
+    mm = float(np.median(ms))
+    gbs = B * n * N * 8 / (mm * 1e-3) / 1e9
+    print(f'NxM N={N} {prec} B={B} n={n} m={m}: {mm:.3f} ms  {B/(mm*1e-3)/1e6:.3f} Mev/s  {gbs:.0f} GB/s ({gbs/6551*100:.1f}% HBM)', flush=True)
+
+
 if __name__ == '__main__':
     import os
     print(torch.cuda.get_device_name(0), 'DP_OF_KERNEL=' + os.environ.get('DP_OF_KERNEL', 'v2'))
     only = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    if only == 'nxm':
+        time_nxm(32768, 'f32', 4096, 2, 2)
+        time_nxm(32768, 'f64', 4096, 2, 2)
+        time_nxm(16384, 'f32', 4096, 4, 1)
+        time_nxm(16384, 'f64', 4096, 3, 3)
+        time_nxm(32768, 'f32', 4096, 1, 1)
+        time_nxm(32768, 'f64', 4096, 1, 1)
+        sys.exit(0)
     time_of(32768, 'f32', 8192)
     time_of(32768, 'f32', 8192, windows='c2')
     time_of(32768, 'f32', 8192, two_templ=True, windows='c2')
