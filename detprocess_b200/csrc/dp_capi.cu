@@ -1462,11 +1462,8 @@ template <class T> int nxm_finalize(dp_nxm_plan* p, DpNxmParams<T>& prm) {
     if ((rc = upload(p->owned, dt.tw3, &prm.tw3))) return rc;
     if ((rc = upload(p->owned, dt.twn, &prm.twn))) return rc;
     if ((rc = upload(p->owned, dt.groups, &prm.groups))) return rc;
-    for (int i = 0; i < p->m; ++i)
-        for (int a = 0; a < p->n; ++a) {
-            if ((rc = upload(p->owned, dt.g[(size_t)i * p->n + a], &prm.g[i][a]))) return rc;
-            if ((rc = upload(p->owned, dt.g_self[(size_t)i * p->n + a], &prm.g_self[i][a]))) return rc;
-        }
+    if ((rc = upload(p->owned, dt.g, &prm.g))) return rc;
+    if ((rc = upload(p->owned, dt.g_self, &prm.g_self))) return rc;
     for (int a = 0; a < p->n; ++a) {
         if ((rc = upload(p->owned, dt.wd[a], &prm.wd[a]))) return rc;
         if ((rc = upload(p->owned, dt.wd_self[a], &prm.wd_self[a]))) return rc;

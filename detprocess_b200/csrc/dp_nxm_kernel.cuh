@@ -31,8 +31,8 @@ template <class T> struct DpNxmParams {
     const cx<T>* tw3;
     const cx<S>* twn;
     const int2* groups;
-    const cx<T>* g[DP_NXM_MAX_TEMPL][DP_NXM_MAX_CHAN];       // [NPH][16][NT] thread-order filters
-    const cx<S>* g_self[DP_NXM_MAX_TEMPL][DP_NXM_MAX_CHAN];  // [17][2]
+    const cx<T>* g;       // [n_templ][n_chan][NPH][16][NT] thread-order filters (one array: no run-time indexed
+    const cx<S>* g_self;  // [n_templ][n_chan][17][2]          kernel-parameter pointers)
     const T* wd[DP_NXM_MAX_CHAN];                            // chi0 weights, diagonal (real)
     const S* wd_self[DP_NXM_MAX_CHAN];
     const cx<T>* wo[DP_NXM_MAX_PAIRS];                       // chi0 weights, a < b: 2 * W_ab
@@ -58,6 +58,7 @@ template <class T, int R1> struct DpNxmKernel {
     static constexpr int NT = G::NT, VL = G::VL, NB = G::NB, NPH = G::NPH, VPB = G::VPB, GC = G::GC, NC = G::NC, N = G::N;
     static constexpr int NW = NT / 32;
     static constexpr int SX = 34;  // X of the 17 self pairs, per channel
+    static constexpr long long GSTRIDE = (long long)NPH * 16 * NT;  // one thread-order table
     static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (32 + SX * DP_NXM_MAX_CHAN) + sizeof(double) * 32 +
                                          sizeof(DpBest<S>) * 32 + 64;
     // scratch per CTA (V units)
@@ -171,36 +172,21 @@ template <class T, int R1> struct DpNxmKernel {
                     __syncthreads();  // group-row reads of this channel precede the next pass-1 stores
                 }
 
-                // ---------------- chi0: the CSD quadratic form at the thread's bins ------------------------
+                // next event's traces -> L2 once this event's last read of its own traces is done
+                if (p == NPH - 1 && ev + (int)gridDim.x < prm.n_events) {
+                    const double* nx = prm.traces + (long long)(ev + gridDim.x) * prm.ev_stride;
+#ifndef DP_HOST_EMU
+                    if (tid < nch)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx + (long long)tid * prm.chan_stride),
+                                     "r"((unsigned)((size_t)N * sizeof(double)))
+                                     : "memory");
+#else
+                    (void)nx;
+#endif
+                }
+
+                // ---------------- chi0 (self lanes; the regular bins are folded into the first template's filter pass) ----
                 {
-                    T acc = (T)0.0f;
-#pragma unroll 2
-                    for (int r = 0; r < 16; ++r) {
-                        V X[DP_NXM_MAX_CHAN];
-#pragma unroll
-                        for (int a = 0; a < DP_NXM_MAX_CHAN; ++a)
-                            if (a < nch) X[a] = dp2_ld_keep(scr_x + SCR_X * a + r * NT + tid, pol);
-                        const long long e = ((long long)p * 16 + r) * NT + tid;
-                        int pi = 0;
-#pragma unroll
-                        for (int a = 0; a < DP_NXM_MAX_CHAN; ++a) {
-                            if (a < nch) {
-                                acc = dp_fma(dp_ldg(prm.wd[a] + e), cnorm2(X[a]), acc);
-#pragma unroll
-                                for (int b = a + 1; b < DP_NXM_MAX_CHAN; ++b) {
-                                    if (b < nch) {
-                                        const V t = cmul(dp_ldg(prm.wo[pi] + e), X[b]);
-                                        acc = dp_fma(X[a].re, t.re, acc);
-                                        acc = dp_fma(X[a].im, t.im, acc);
-                                        ++pi;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (!special) {
-                        if constexpr (VL == 2) chi += acc.x + acc.y; else chi += acc;
-                    }
                     if (p == 0 && tid < 17) {
                         int pi = 0;
                         for (int a = 0; a < nch; ++a) {
@@ -228,7 +214,8 @@ template <class T, int R1> struct DpNxmKernel {
                         const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
                         cx<S> Fk{(S)0, (S)0}, Fm{(S)0, (S)0};
                         for (int a = 0; a < nch; ++a) {
-                            const cx<S> gk = dp_ldg(prm.g_self[it][a] + 2 * tid), gm = dp_ldg(prm.g_self[it][a] + 2 * tid + 1);
+                            const cx<S>* gs = prm.g_self + (it * nch + a) * SX;
+                            const cx<S> gk = dp_ldg(gs + 2 * tid), gm = dp_ldg(gs + 2 * tid + 1);
                             const cx<S> tk = cmul(gk, sx[a * SX + 2 * tid]), tm = cmul(gm, sx[a * SX + 2 * tid + 1]);
                             Fk.re += tk.re;
                             Fk.im += tk.im;
@@ -241,45 +228,63 @@ template <class T, int R1> struct DpNxmKernel {
                         if (sl.ek != sl.em) sp[sl.em] = Cm;
                     }
                     const long long e0 = (long long)p * 16 * NT + tid;
-                    if constexpr (VL == 2) {
+                    const cx<T>* const git = prm.g + (long long)it * nch * GSTRIDE;
+                    // X_a of one table entry -> registers; the first template's pass also takes the CSD quadratic form
+                    // sum_ab conj(X_a) W_ab X_b (chi0) from them
+                    T chi_acc = (T)0.0f;
+                    auto entry = [&](int ent) -> V {
+                        V X[DP_NXM_MAX_CHAN];
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            V f = cmul(dp_ldg(prm.g[it][0] + e0 + r * NT), dp2_ld_keep(scr_x + r * NT + tid, pol));
+                        for (int a = 0; a < DP_NXM_MAX_CHAN; ++a)
+                            if (a < nch) X[a] = dp2_ld_keep(scr_x + SCR_X * a + ent * NT + tid, pol);
+                        const long long e = e0 + (long long)ent * NT;
+                        if (it == 0) {
+                            int pi = 0;
 #pragma unroll
-                            for (int a = 1; a < DP_NXM_MAX_CHAN; ++a) {
+                            for (int a = 0; a < DP_NXM_MAX_CHAN; ++a) {
                                 if (a < nch) {
-                                    const V t = cmul(dp_ldg(prm.g[it][a] + e0 + r * NT), dp2_ld_keep(scr_x + SCR_X * a + r * NT + tid, pol));
-                                    f.re = f.re + t.re;
-                                    f.im = f.im + t.im;
+                                    chi_acc = dp_fma(dp_ldg(prm.wd[a] + e), cnorm2(X[a]), chi_acc);
+#pragma unroll
+                                    for (int b = a + 1; b < DP_NXM_MAX_CHAN; ++b) {
+                                        if (b < nch) {
+                                            const V t = cmul(dp_ldg(prm.wo[pi] + e), X[b]);
+                                            chi_acc = dp_fma(X[a].re, t.re, chi_acc);
+                                            chi_acc = dp_fma(X[a].im, t.im, chi_acc);
+                                            ++pi;
+                                        }
+                                    }
                                 }
                             }
-                            z[r] = f;
                         }
+                        V f = cmul(dp_ldg(git + e), X[0]);
+#pragma unroll
+                        for (int a = 1; a < DP_NXM_MAX_CHAN; ++a) {
+                            if (a < nch) {
+                                const V t = cmul(dp_ldg(git + a * GSTRIDE + e), X[a]);
+                                f.re = f.re + t.re;
+                                f.im = f.im + t.im;
+                            }
+                        }
+                        return f;
+                    };
+                    if constexpr (VL == 2) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) z[r] = entry(r);
                         retangle_all(z, wn);
                     } else {
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            V Fk = cmul(dp_ldg(prm.g[it][0] + e0 + (2 * r) * NT), dp2_ld_keep(scr_x + (2 * r) * NT + tid, pol));
-                            V Fm = cmul(dp_ldg(prm.g[it][0] + e0 + (2 * r + 1) * NT), dp2_ld_keep(scr_x + (2 * r + 1) * NT + tid, pol));
-#pragma unroll
-                            for (int a = 1; a < DP_NXM_MAX_CHAN; ++a) {
-                                if (a < nch) {
-                                    const V tk = cmul(dp_ldg(prm.g[it][a] + e0 + (2 * r) * NT),
-                                                      dp2_ld_keep(scr_x + SCR_X * a + (2 * r) * NT + tid, pol));
-                                    const V tm = cmul(dp_ldg(prm.g[it][a] + e0 + (2 * r + 1) * NT),
-                                                      dp2_ld_keep(scr_x + SCR_X * a + (2 * r + 1) * NT + tid, pol));
-                                    Fk.re = Fk.re + tk.re;
-                                    Fk.im = Fk.im + tk.im;
-                                    Fm.re = Fm.re + tm.re;
-                                    Fm.im = Fm.im + tm.im;
-                                }
-                            }
+                            const V Fk = entry(2 * r);
+                            const V Fm = entry(2 * r + 1);
                             cx<S> Ck, Cm;
                             dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
                             z[r] = Ck;
                             buf[Gp * 17 + 15 - r] = Cm;
                         }
                         OF::pw_collect(buf, z, gg.x);
+                    }
+                    if (it == 0 && !special) {
+                        if constexpr (VL == 2) chi += chi_acc.x + chi_acc.y; else chi += chi_acc;
                     }
                     if (p == 0 && tid < 32) {
                         __syncwarp();

@@ -128,8 +128,8 @@ template <class T> struct Tables {
     std::vector<cx<T>> tw1, tw2, tw3;
     std::vector<cx<S>> twn;
     std::vector<int2> groups;
-    std::vector<std::vector<cx<T>>> g;       // [m*n]
-    std::vector<std::vector<cx<S>>> g_self;  // [m*n]
+    std::vector<cx<T>> g;       // [m][n][NPH*16*NT]
+    std::vector<cx<S>> g_self;  // [m][n][17*2]
     std::vector<std::vector<T>> wd;          // [n]
     std::vector<std::vector<S>> wd_self;
     std::vector<std::vector<cx<T>>> wo;      // [pairs a < b]
@@ -156,8 +156,6 @@ template <class T, int R1> Tables<T> build_tables(const Setup& s, double scale) 
     const double df = s.fs / N;
     const int n = s.n, m = s.m;
     // filters: q~_i(t) = sum_a sum_k Phi_ia[k] fft(x_a)_k e^{2 pi i k t / N} / (N P_ii), kernel feeds 2*scale*fft(x)
-    dt.g.resize((size_t)m * n);
-    dt.g_self.resize((size_t)m * n);
     for (int i = 0; i < m; ++i)
         for (int a = 0; a < n; ++a) {
             const auto& ph = s.phi[(size_t)i * n + a];
@@ -169,7 +167,11 @@ template <class T, int R1> Tables<T> build_tables(const Setup& s, double scale) 
             }
             pe[0] = cplx(pe[0].real(), 0.0);
             pe[M] = cplx(pe[M].real(), 0.0);
-            dpplan2::pack_onesided<T, R1>(pe, dt.g[(size_t)i * n + a], dt.g_self[(size_t)i * n + a]);
+            std::vector<cx<T>> g1;
+            std::vector<cx<S>> gs1;
+            dpplan2::pack_onesided<T, R1>(pe, g1, gs1);
+            dt.g.insert(dt.g.end(), g1.begin(), g1.end());
+            dt.g_self.insert(dt.g_self.end(), gs1.begin(), gs1.end());
         }
     // chi0 = sum_k X^H iS X df on the one-sided bins of X~ = 2*scale*fft(x)
     const double wsc = 1.0 / ((double)N * (double)N * df) / (4.0 * scale * scale);

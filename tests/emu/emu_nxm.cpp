@@ -52,11 +52,8 @@ static void run_all(const dpnxm::Setup& s, double scale, int subtract_first, int
     prm.tw3 = dt.tw3.data();
     prm.twn = dt.twn.data();
     prm.groups = dt.groups.data();
-    for (int i = 0; i < s.m; ++i)
-        for (int a = 0; a < s.n; ++a) {
-            prm.g[i][a] = dt.g[(size_t)i * s.n + a].data();
-            prm.g_self[i][a] = dt.g_self[(size_t)i * s.n + a].data();
-        }
+    prm.g = dt.g.data();
+    prm.g_self = dt.g_self.data();
     for (int a = 0; a < s.n; ++a) {
         prm.wd[a] = dt.wd[a].data();
         prm.wd_self[a] = dt.wd_self[a].data();
