@@ -309,6 +309,32 @@ def extras(device, dist, world, hbm_peak):
                                      'roofline_frac': L * 8 / (fms * 1e-3) / 1e9 / hbm_peak,
                                      'fft_size': trig._plan.fft_size, 'hop': trig._plan.hop}
         del trig
+    # ---- (f)3 NxM optimal filter: 2 channels x 2 templates, 32768 samples, +-400 us window + no-delay fit
+    from detprocess_b200.core.plans import NxMPlan
+    from detprocess_b200.synth import SynthNxM
+    SN = SynthNxM(NB_SAMPLES, 2, 2, FS)
+    B = 4096
+    base = torch.from_numpy(SN.traces(64, np.random.default_rng(12345))).to(device)
+    xn = base.repeat(B // 64, 1, 1).contiguous()        # 2.0 GiB > L2
+    for prec in ('f64', 'f32'):
+        nx = NxMPlan(NB_SAMPLES, FS, 2, 2, prec)
+        nx.set_filter(SN.templates, SN.csd, SN.nb_pretrigger, 'AC')
+        nx.set_window(SN.nb_pretrigger - WINDOW, SN.nb_pretrigger + WINDOW)
+        nx.finalize(device)
+        no = torch.empty((B, nx.n_out), dtype=torch.float64, device=device)
+        for _ in range(3):
+            nx.run(xn, no)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(5):
+            nx.run(xn, no)
+            ms.append(nx.last_kernel_ms())
+        m = float(np.median(ms))
+        gbs = B * 2 * NB_SAMPLES * 8 / (m * 1e-3) / 1e9
+        out[f'f3_ofnxm_2x2_{prec}'] = {'events_per_s_per_gpu': B / (m * 1e-3), 'achieved_gbs': gbs, 'roofline_frac': gbs / hbm_peak,
+                                       'algorithmic_bytes_per_event': 2 * NB_SAMPLES * 8, 'kernel': 'dp_nxm_kernel<%s,4,2>' % ('double' if prec == 'f64' else 'f2')}
+        del nx, no
+    del xn, base
     return out
 
 

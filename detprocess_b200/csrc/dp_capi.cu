@@ -1475,10 +1475,10 @@ template <class T> int nxm_finalize(dp_nxm_plan* p, DpNxmParams<T>& prm) {
     std::memcpy(prm.cmat, dt.cmat, sizeof(prm.cmat));
     std::memcpy(prm.amat, dt.amat, sizeof(prm.amat));
     const int prec = sizeof(S) == 8 ? 0 : 1;
-    const int src = dp_nxm_setup_table[prec](p->r1, p->device, &p->smem, &p->grid_max, &p->threads);
+    const int src = dp_nxm_setup_table[prec][p->n - 1](p->r1, p->device, &p->smem, &p->grid_max, &p->threads);
     if (src == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");
     if (src != 0) return fail(DP_ERR_CUDA, std::string("NxM kernel setup: ") + cudaGetErrorString((cudaError_t)src));
-    prm.scratch_per_cta = dp_nxm_scratch_table[prec](p->r1, p->n, p->m);
+    prm.scratch_per_cta = dp_nxm_scratch_table[prec][p->n - 1](p->r1, p->n, p->m);
     void* scr = nullptr;
     DP_CUDA(cudaMalloc(&scr, sizeof(cx<T>) * (size_t)prm.scratch_per_cta * (size_t)p->grid_max));
     p->owned.push_back(scr);
@@ -1489,6 +1489,10 @@ template <class T> int nxm_finalize(dp_nxm_plan* p, DpNxmParams<T>& prm) {
     prm.n_out = 4 + 2 * p->m;
     prm.scale = p->scale;
     prm.subtract_first = p->subtract_first;
+    {
+        const char* e = std::getenv("DP_NXM_PREFETCH");  // development switch, default on
+        prm.prefetch = (e && std::string(e) == "0") ? 0 : 1;
+    }
     return DP_OK;
 }
 template <class T> int nxm_run(dp_nxm_plan* p, DpNxmParams<T> prm, const double* traces, long long n_events, long long ev_stride,
@@ -1504,7 +1508,7 @@ template <class T> int nxm_run(dp_nxm_plan* p, DpNxmParams<T> prm, const double*
     const int grid = (int)std::min<long long>(n_events, p->grid_max);
     DP_CUDA(cudaEventRecord(p->ev0, st));
     const int prec = sizeof(typename Dp2Traits<T>::S) == 8 ? 0 : 1;
-    const int rc = dp_nxm_launch_table[prec](p->r1, &prm, grid, p->smem, st);
+    const int rc = dp_nxm_launch_table[prec][p->n - 1](p->r1, &prm, grid, p->smem, st);
     if (rc != 0) return fail(DP_ERR_CUDA, std::string("NxM kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     DP_CUDA(cudaEventRecord(p->ev1, st));
     p->timed = true;

@@ -47,9 +47,10 @@ template <class T> struct DpNxmParams {
     int n_out;
     double scale;
     int subtract_first;
+    int prefetch;            // 0: no L2 prefetch of the next trace row
 };
 
-template <class T, int R1> struct DpNxmKernel {
+template <class T, int R1, int NCH> struct DpNxmKernel {
     using G = Dp2Geom<T, R1>;
     using S = typename G::S;
     using V = cx<T>;
@@ -102,7 +103,8 @@ template <class T, int R1> struct DpNxmKernel {
         double* const red = reinterpret_cast<double*>(sx + SX * DP_NXM_MAX_CHAN);
         DpBest<S>* const best = reinterpret_cast<DpBest<S>*>(red + 32);
         const int tid = threadIdx.x;
-        const int nch = prm.n_chan, ntm = prm.n_templ;
+        constexpr int nch = NCH;  // compile-time channel count: the per-entry loops unroll without branches
+        const int ntm = prm.n_templ;
         V* const scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
         V* const scr_park = scr_x + SCR_X * nch;
         V* const scr_q = scr_park + SCR_PARK * ntm;
@@ -131,6 +133,21 @@ template <class T, int R1> struct DpNxmKernel {
                     const double x0 = prm.subtract_first ? dp_load_first<0>(xrow) : 0.0;
                     Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
                     __syncthreads();
+#ifndef DP_HOST_EMU
+                    if (tid == 0) {
+                        // rolling prefetch, one row ahead (one TMA bulk-prefetch instruction): the next channel of this
+                        // event before its first read, the next event's first channel after this event's last read.
+                        // A whole event ahead (n rows per CTA) does not fit in L2 next to the scratch columns.
+                        const double* nx = nullptr;
+                        if (p == 0 && a + 1 < nch)
+                            nx = xrow + prm.chan_stride;
+                        else if (p == NPH - 1 && a == nch - 1 && ev + (int)gridDim.x < prm.n_events)
+                            nx = prm.traces + (long long)(ev + gridDim.x) * prm.ev_stride;
+                        if (nx != nullptr && prm.prefetch)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)((size_t)N * sizeof(double)))
+                                         : "memory");
+                    }
+#endif
                     Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                     if (p == 0 && tid < 32) {
                         if constexpr (VL == 2) {
@@ -170,19 +187,6 @@ template <class T, int R1> struct DpNxmKernel {
                         });
                     }
                     __syncthreads();  // group-row reads of this channel precede the next pass-1 stores
-                }
-
-                // next event's traces -> L2 once this event's last read of its own traces is done
-                if (p == NPH - 1 && ev + (int)gridDim.x < prm.n_events) {
-                    const double* nx = prm.traces + (long long)(ev + gridDim.x) * prm.ev_stride;
-#ifndef DP_HOST_EMU
-                    if (tid < nch)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx + (long long)tid * prm.chan_stride),
-                                     "r"((unsigned)((size_t)N * sizeof(double)))
-                                     : "memory");
-#else
-                    (void)nx;
-#endif
                 }
 
                 // ---------------- chi0 (self lanes; the regular bins are folded into the first template's filter pass) ----
@@ -233,37 +237,29 @@ template <class T, int R1> struct DpNxmKernel {
                     // sum_ab conj(X_a) W_ab X_b (chi0) from them
                     T chi_acc = (T)0.0f;
                     auto entry = [&](int ent) -> V {
-                        V X[DP_NXM_MAX_CHAN];
+                        V X[NCH];
 #pragma unroll
-                        for (int a = 0; a < DP_NXM_MAX_CHAN; ++a)
-                            if (a < nch) X[a] = dp2_ld_keep(scr_x + SCR_X * a + ent * NT + tid, pol);
+                        for (int a = 0; a < NCH; ++a) X[a] = dp2_ld_keep(scr_x + SCR_X * a + ent * NT + tid, pol);
                         const long long e = e0 + (long long)ent * NT;
                         if (it == 0) {
-                            int pi = 0;
 #pragma unroll
-                            for (int a = 0; a < DP_NXM_MAX_CHAN; ++a) {
-                                if (a < nch) {
-                                    chi_acc = dp_fma(dp_ldg(prm.wd[a] + e), cnorm2(X[a]), chi_acc);
+                            for (int a = 0; a < NCH; ++a) {
+                                chi_acc = dp_fma(dp_ldg(prm.wd[a] + e), cnorm2(X[a]), chi_acc);
 #pragma unroll
-                                    for (int b = a + 1; b < DP_NXM_MAX_CHAN; ++b) {
-                                        if (b < nch) {
-                                            const V t = cmul(dp_ldg(prm.wo[pi] + e), X[b]);
-                                            chi_acc = dp_fma(X[a].re, t.re, chi_acc);
-                                            chi_acc = dp_fma(X[a].im, t.im, chi_acc);
-                                            ++pi;
-                                        }
-                                    }
+                                for (int b = a + 1; b < NCH; ++b) {
+                                    const int pi = a * NCH - a * (a + 1) / 2 + (b - a - 1);  // pair index of (a, b), a < b
+                                    const V t = cmul(dp_ldg(prm.wo[pi] + e), X[b]);
+                                    chi_acc = dp_fma(X[a].re, t.re, chi_acc);
+                                    chi_acc = dp_fma(X[a].im, t.im, chi_acc);
                                 }
                             }
                         }
                         V f = cmul(dp_ldg(git + e), X[0]);
 #pragma unroll
-                        for (int a = 1; a < DP_NXM_MAX_CHAN; ++a) {
-                            if (a < nch) {
-                                const V t = cmul(dp_ldg(git + a * GSTRIDE + e), X[a]);
-                                f.re = f.re + t.re;
-                                f.im = f.im + t.im;
-                            }
+                        for (int a = 1; a < NCH; ++a) {
+                            const V t = cmul(dp_ldg(git + a * GSTRIDE + e), X[a]);
+                            f.re = f.re + t.re;
+                            f.im = f.im + t.im;
                         }
                         return f;
                     };
@@ -413,9 +409,9 @@ template <class T, int R1> struct DpNxmKernel {
 };
 
 #ifndef DP_HOST_EMU
-template <class T, int R1>
+template <class T, int R1, int NCH>
 __global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, Dp2Geom<T, R1>::NT <= 256 ? 2 : 1) dp_nxm_kernel(const DpNxmParams<T> prm) {
     extern __shared__ __align__(16) unsigned char dp_smem_raw[];
-    DpNxmKernel<T, R1>::run(prm, dp_smem_raw);
+    DpNxmKernel<T, R1, NCH>::run(prm, dp_smem_raw);
 }
 #endif

@@ -34,10 +34,10 @@ template <class F> static void run_cta(int nthreads, int bid, int grid, F&& fn) 
 
 template <class V> static void rd(std::ifstream& f, V* p, size_t n) { f.read(reinterpret_cast<char*>(p), sizeof(V) * n); }
 
-template <class T, int R1>
+template <class T, int R1, int NCH>
 static void run_all(const dpnxm::Setup& s, double scale, int subtract_first, int lo, int hi, int outside, const std::vector<double>& traces,
                     int n_events, std::vector<double>& out) {
-    using K = DpNxmKernel<T, R1>;
+    using K = DpNxmKernel<T, R1, NCH>;
     using G = Dp2Geom<T, R1>;
     auto dt = dpnxm::build_tables<T, R1>(s, scale);
     DpNxmParams<T> prm{};
@@ -105,10 +105,19 @@ template <class T> static int main_t(const char* in, const char* outp, bool f32)
         subtract_first = ac ? 1 : 0;
     }
     std::vector<double> out((size_t)n_events * (4 + 2 * m), -1.0);
+#define DP_EMU_RUN(R1_, NCH_) run_all<T, R1_, NCH_>(s, scale, subtract_first, lo, hi, outside, traces, n_events, out)
+#define DP_EMU_NCH(R1_)                                                              \
+    switch (n) {                                                                     \
+        case 1: DP_EMU_RUN(R1_, 1); break;                                           \
+        case 2: DP_EMU_RUN(R1_, 2); break;                                           \
+        case 3: DP_EMU_RUN(R1_, 3); break;                                           \
+        case 4: DP_EMU_RUN(R1_, 4); break;                                           \
+        default: std::fprintf(stderr, "unsupported n_chan\n"); return 3;             \
+    }
     switch (dpplan2::r1_of(N)) {
-        case 2: run_all<T, 2>(s, scale, subtract_first, lo, hi, outside, traces, n_events, out); break;
-        case 4: run_all<T, 4>(s, scale, subtract_first, lo, hi, outside, traces, n_events, out); break;
-        case 8: run_all<T, 8>(s, scale, subtract_first, lo, hi, outside, traces, n_events, out); break;
+        case 2: DP_EMU_NCH(2) break;
+        case 4: DP_EMU_NCH(4) break;
+        case 8: DP_EMU_NCH(8) break;
         default: std::fprintf(stderr, "unsupported N\n"); return 3;
     }
     std::ofstream o(outp, std::ios::binary);
