@@ -5,3 +5,4 @@ from .filterdata import FilterData
 from .plans import PSDPlan
 from .noise import NoisePSD
 from .oftrigger import OptimumFilterTrigger, TriggerPlan
+from .eventbuilder import EventBuilder

@@ -21,7 +21,12 @@ class FilterData:
                      pretrigger_length_samples=None, metadata=None, tag='default'):
         if not isinstance(template, np.ndarray):
             raise ValueError('ERROR: "template" argument should be a numpy array!')
-        if template.ndim != 1:
+        nchan = len(channels.split('|')) if isinstance(channels, str) else 1
+        if nchan > 1:
+            # joint channels 'a|b': [n_chan, n_templ, N] (reference filterdata.py:539-633, NxM templates)
+            if template.ndim != 3 or template.shape[0] != nchan:
+                raise ValueError('ERROR: For multi-channels, expecting a 3D array [nchans, ntemplates, nsamples]')
+        elif template.ndim != 1:
             raise ValueError('ERROR: For single channel, expecting and 1D array ')
         if sample_rate is None:
             raise ValueError('ERROR: "sample_rate" argument required!')
@@ -49,6 +54,23 @@ class FilterData:
         d[f'psd_{tag}'] = np.array(psd, dtype=np.float64)
         d[f'psd_{tag}_metadata'] = meta
 
+    def set_csd(self, channels, csd, csd_freqs=None, sample_rate=None, metadata=None, tag='default'):
+        """Two-sided cross-spectral density [n, n, N] (complex) of joint channels 'a|b|...' (reference
+        filterdata.py:754-828)."""
+        csd = np.asarray(csd)
+        nchan = len(channels.split('|'))
+        if csd.ndim != 3 or csd.shape[0] != nchan or csd.shape[1] != nchan:
+            raise ValueError('ERROR: Expecting a "csd" array [nchans, nchans, nsamples] matching the channel list')
+        if sample_rate is None and csd_freqs is not None:
+            sample_rate = 2.0 * float(np.max(np.abs(csd_freqs)))
+        if sample_rate is None:
+            raise ValueError('ERROR: "sample_rate" argument required!')
+        meta = dict(metadata or {})
+        meta.update({'sample_rate': sample_rate, 'nb_samples': csd.shape[-1], 'channel': channels})
+        d = self._filter_data.setdefault(channels, {})
+        d[f'csd_{tag}'] = np.array(csd, dtype=np.complex128)
+        d[f'csd_{tag}_metadata'] = meta
+
     # ---- getters ----------------------------------------------------------------
     def _get(self, channel, name, tag):
         key = f'{name}_{tag}'
@@ -73,7 +95,13 @@ class FilterData:
         return (arr, f, meta) if return_metadata else (arr, f)
 
     def get_csd(self, channels, tag='default', fold=False, return_metadata=False):
-        """Single-channel CSD = the PSD as a [1, 1, N] array (the reference's 1x1 case)."""
+        """Joint channels: the stored [n, n, N] array; single channel: the PSD as a [1, 1, N] array."""
+        if isinstance(channels, str) and '|' in channels:
+            if fold:
+                raise NotImplementedError('fold=True for a multi-channel csd is not built')
+            arr, meta = self._get(channels, 'csd', tag)
+            f = np.fft.fftfreq(arr.shape[-1], d=1.0 / meta['sample_rate'])
+            return (arr, f, meta) if return_metadata else (arr, f)
         out = self.get_psd(channels, tag=tag, fold=fold, return_metadata=return_metadata)
         return (out[0][None, None, :],) + tuple(out[1:])
 

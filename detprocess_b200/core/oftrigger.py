@@ -186,5 +186,42 @@ class OptimumFilterTrigger:
         self._trigger_data = {self._trigger_name: d}
         return self._trigger_data
 
+    def find_triggers(self, thresh, pileup_window_msec=None, pileup_window_samples=None, positive_pulses=True,
+                      dynamic=False, dynamic_threshold_function=None, residual=False,
+                      saturation_amplitudes_LPF_50kHz=None, edge_exclusion_msec=None, livetime=None,
+                      return_trigger_data=False, max_triggers=65536):
+        """``OptimumFilterTrigger.find_triggers`` (reference core/oftrigger.py:682-883) without the residual re-trigger
+        and the dynamic pile-up window: one ``find_triggers_once`` pass, then the edge exclusion and the livetime /
+        edge-exclusion columns of :854-883."""
+        if residual:
+            raise NotImplementedError('residual=True (re-trigger on the residual chi2 trace) is not built')
+        if dynamic or dynamic_threshold_function is not None:
+            raise NotImplementedError('dynamic pile-up windows are not built')
+        self.find_triggers_once(thresh, pileup_window_msec, pileup_window_samples, max_triggers=max_triggers)
+        if edge_exclusion_msec is not None:
+            tmin = edge_exclusion_msec * 1e-3
+            tmax = (self._trace.shape[-1] / self._fs) - edge_exclusion_msec * 1e-3
+            for chan, data in list(self._trigger_data.items()):
+                times = data['trigger_time']
+                if len(times) == 0:
+                    continue
+                keep = [i for i, t in enumerate(times) if tmin < t < tmax]
+                kept = {k: [v[i] for i in keep] for k, v in data.items()}
+                kept[f'trigger_edge_exclusion_time_{chan}'] = [edge_exclusion_msec * 1e-3] * len(keep)
+                if livetime is not None:
+                    kept[f'trigger_livetime_{chan}'] = [livetime] * len(keep)
+                self._trigger_data[chan] = kept
+
     def get_trigger_data(self):
         return self._trigger_data
+
+    def get_trigger_data_df(self):
+        """The trigger table of the last ``find_triggers`` call as a pandas DataFrame (the reference returns a vaex frame
+        of the same columns, core/oftrigger.py:318-321 / get_trigger_data_df); None without triggers."""
+        import pandas as pd
+        if not self._trigger_data:
+            return None
+        data = self._trigger_data[self._trigger_name]
+        if len(data.get('trigger_index', [])) == 0:
+            return None
+        return pd.DataFrame({k: np.asarray(v) for k, v in data.items()})

@@ -138,7 +138,7 @@ class FeatureProcessing:
                 base = params.get('base_algorithm', algo)
                 if not any(p in base for p in _OF_PREFIXES):
                     continue
-                if not base.startswith('of1x1'):
+                if not (base.startswith('of1x1') or base == 'ofnxm'):
                     raise NotImplementedError(f'algorithm "{base}" is outside the built hot path')
                 key = self._of_key(params)
                 entry = self._of_bases.setdefault(key, {
@@ -149,7 +149,10 @@ class FeatureProcessing:
                     entry['channels'].append(chan)
                 ofb = entry['OF']
                 csd_tag = params.get('csd_tag', 'default')
-                psd, _, meta = self._filter_data.get_psd(chan, tag=csd_tag, return_metadata=True)
+                if base == 'ofnxm':
+                    psd, _, meta = self._filter_data.get_csd(chan, tag=csd_tag, return_metadata=True)
+                else:
+                    psd, _, meta = self._filter_data.get_psd(chan, tag=csd_tag, return_metadata=True)
                 if meta.get('sample_rate', self._fs) != self._fs:
                     raise ValueError(f'Sample rate is not consistent between raw data and csd for channel {chan}!')
                 if params['nb_samples'] != psd.shape[-1]:
@@ -200,7 +203,9 @@ class FeatureProcessing:
             return traces[:, idx[0], :] - traces[:, idx[1], :]
         if sep is None:
             return traces[:, idx[0], :]
-        raise NotImplementedError(f'channel operator "{sep}" (NxM) is outside the built hot path')
+        if sep == '|':
+            return traces[:, idx, :]            # [B, n, N] in the listed order (NxM filter)
+        raise NotImplementedError(f'channel operator "{sep}" is outside the built hot path')
 
     # ------------------------------------------------------------------ process
     def process(self, nevents=-1, lgc_save=False, lgc_output=True, save_path=None, ncores=1,
@@ -283,7 +288,7 @@ class FeatureProcessing:
                 wmin, wmax = utils.get_window_indices(**kw)
                 kw['window_min_index'], kw['window_max_index'] = wmin, wmax
                 kw['feature_base_name'] = algorithm
-                entry = self._of_bases.get(self._of_key(params)) if base.startswith('of1x1') else None
+                entry = self._of_bases.get(self._of_key(params)) if (base.startswith('of1x1') or base == 'ofnxm') else None
                 if entry is not None and algorithm in entry['algorithms']:
                     feats = extractor(channel, entry['OF'], **kw)
                     for name, val in feats.items():

@@ -106,3 +106,55 @@ def test_ofnxm_extractor_mirrors_reference_keys():
     one.update_signal('a|b', x[0])
     r1 = FeatureExtractors.ofnxm('a|b', one, template_tag='shared')
     assert np.isscalar(r1['amp1_ofnxm_constrained']) or r1['amp1_ofnxm_constrained'].ndim == 0
+
+
+def test_yaml_pipeline_with_joint_channel_ofnxm_block(tmp_path):
+    """A YAML feature block on channel 'chanA|chanB' with base_algorithm: ofnxm (reference
+    examples/salting/run46_salting_test.yaml:182-197) through FeatureProcessing: csd / templates come from FilterData
+    (get_csd / get_template of the joint channel), the columns carry the feature_channel rename."""
+    import torch
+    from detprocess_b200.core.filterdata import FilterData
+    from detprocess_b200.process.features import FeatureProcessing
+    S = SynthNxM(16384, 2, 2)
+    pre = S.nb_pretrigger
+    x = S.traces(48, np.random.default_rng(11))
+    yml = tmp_path / 'nxm.yaml'
+    yml.write_text('''
+global:
+    trace_length_samples: 16384
+    pretrigger_length_samples: 8192
+chanA:
+    of1x1_nodelay:
+        run: True
+        template_tag: default
+    baseline:
+        run: True
+        window_min_from_start_usec: 0
+        window_max_from_trig_usec: -1000
+chanA|chanB:
+    feature_channel: pair
+    of2x2_test:
+        run: True
+        base_algorithm: ofnxm
+        window_min_from_trig_usec: -100
+        window_max_from_trig_usec: 100
+        noise_tag: default
+        template_tag: shared
+        amplitude_names: [phonon, glitch]
+''')
+    fd = FilterData()
+    fd.set_psd('chanA', np.real(S.csd[0, 0]), sample_rate=S.fs)
+    fd.set_template('chanA', S.templates[0, 0] / S.templates[0, 0].max(), sample_rate=S.fs, pretrigger_length_samples=pre)
+    fd.set_csd('chanA|chanB', S.csd, sample_rate=S.fs)
+    fd.set_template('chanA|chanB', S.templates, sample_rate=S.fs, pretrigger_length_samples=pre, tag='shared')
+    fp = FeatureProcessing({'traces': torch.from_numpy(x), 'channels': ['chanA', 'chanB'], 'sample_rate': S.fs},
+                           str(yml), filter_data=fd, verbose=False)
+    df = fp.process()
+    lo, hi = pre - 125, pre + 125
+    o = ofnxm_batch(x, ofnxm_setup(S.templates, S.csd, S.fs, pre), (lo, hi, False))
+    assert np.allclose(df['phonon_of2x2_test_constrained_pair'], o['amps'][:, 0], rtol=1e-8, atol=1e-9 * np.max(np.abs(o['amps'])))
+    assert np.allclose(df['glitch_of2x2_test_nodelay_pair'], o['amps0'][:, 1], rtol=1e-8, atol=1e-9 * np.max(np.abs(o['amps'])))
+    assert np.allclose(df['t0_of2x2_test_constrained_pair'], o['t0'], atol=1e-12)
+    assert np.allclose(df['chi2_of2x2_test_constrained_pair'], o['chi2'], rtol=1e-9)
+    assert 'amp_of1x1_nodelay_chanA' in df and 'baseline_chanA' in df
+    assert np.allclose(df['baseline_chanA'], x[:, 0, :pre - 1250].mean(axis=1), rtol=1e-12)
