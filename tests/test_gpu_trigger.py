@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip('torch')
 
-from detprocess_b200.synth import make_template, make_psd, make_continuous  # noqa: E402
+from detprocess_b200.synth import make_template, make_psd, make_continuous, SynthSetup  # noqa: E402
 from oracle import trigger as T  # noqa: E402
 
 
@@ -110,10 +110,14 @@ def test_two_channel_streams_through_the_event_builder():
     S = SynthSetup(16384)
     pre, fs, n = S.nb_pretrigger, S.fs, S.nb_samples
     L = 2_000_000
-    xa, ta, aa = make_continuous(L, S.template, S.psd, fs, np.random.default_rng(21), pulse_rate_hz=20.0,
-                                 amp_range=(1e-7, 2e-7), return_truth=True)
+    xa = make_continuous(L, S.template, S.psd, fs, np.random.default_rng(21), pulse_rate_hz=0.0)
     xb = make_continuous(L, S.template, S.psd, fs, np.random.default_rng(22), pulse_rate_hz=0.0)
+    ta = 10_000 + 52_000 * np.arange(38)                   # well separated pulses; the first and last fall in the edges
+    aa = np.random.default_rng(23).uniform(1e-7, 2e-7, len(ta))
     shared = ta[::2]                                       # every second pulse of A is also seen by B, 3 samples later
+    for t, a in zip(ta, aa):
+        m = min(n - pre, L - t)
+        xa[t:t + m] += a * S.template[pre:pre + m]
     for t, a in zip(shared, aa[::2]):
         m = min(n - pre, L - (t + 3))
         xb[t + 3:t + 3 + m] += 0.8 * a * S.template[pre:pre + m]
