@@ -100,7 +100,8 @@ class OptimumFilterTrigger:
     """1x1 mirror of the reference class (oftrigger.py:255-499, 588-679, 884-1034)."""
 
     def __init__(self, trigger_channel, fs, template, noisecsd, pretrigger_samples, trigger_name=None,
-                 coupling='AC', iw=None, w=None, precision='f64', max_samples=12_500_000, device=None):
+                 coupling='AC', iw=None, w=None, precision='f64', max_samples=12_500_000, device=None,
+                 ignored_frequency_peaks=None, ignore_harmonics=False):
         template = np.asarray(template, dtype=np.float64).reshape(-1)
         noisecsd = np.real(np.asarray(noisecsd)).reshape(-1)
         if template.shape[0] != noisecsd.shape[0]:
@@ -122,6 +123,11 @@ class OptimumFilterTrigger:
             raise ValueError('psd must be strictly positive')
         if coupling == 'AC':
             J[0] = np.inf
+        if ignored_frequency_peaks is not None:         # bins on an ignored peak carry no weight (OFBase.set_csd)
+            f = np.abs(np.fft.fftfreq(self._nb_samples, d=1.0 / self._fs))
+            for pk in np.atleast_1d(np.asarray(ignored_frequency_peaks, dtype=float)):
+                for fpk in (np.arange(pk, self._fs / 2, pk) if ignore_harmonics else [pk]):
+                    J[np.abs(f - fpk) <= df / 2] = np.inf
         s_fd = np.fft.fft(template) / self._nb_samples / df
         self._phi_fd = np.conj(s_fd) / J
         norm = float(np.real(np.sum(self._phi_fd * s_fd)) * df)

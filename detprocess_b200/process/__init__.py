@@ -1,2 +1,3 @@
 from .config import YamlConfig
 from .features import FeatureProcessing
+from .triggers import TriggerProcessing

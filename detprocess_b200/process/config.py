@@ -150,8 +150,8 @@ class YamlConfig:
             cfg[field]['channels'] = new
 
         cfg['feature'] = self._configure_features(cfg['feature'], cfg['global'])
-        for field in ('trigger', 'salting'):
-            cfg[field] = self._configure_simple(cfg[field], cfg['global'], field)
+        cfg['trigger'] = self._configure_triggers(cfg['trigger'], cfg['global'])
+        cfg['salting'] = self._configure_simple(cfg['salting'], cfg['global'], 'salting')
         self._processing_config = cfg
 
     def _configure_simple(self, section, global_config, label):
@@ -165,6 +165,38 @@ class YamlConfig:
             parts, _ = utils.split_channel_name(chan, available_channels=self._available_channels, label=label)
             chans.extend(parts)
         out['channel_list'] = utils.unique_list(chans)
+        return out
+
+    def _configure_triggers(self, trigger_config, global_config):
+        """Trigger section (reference config.py:324-408): one entry per trigger -- the channel itself when the block has
+        a 'run' key, else '<algorithm>_<trigger channel>' per algorithm sub-block; 'trigger_channel' renames the
+        channel; every entry carries the raw 'channel_name'."""
+        out = copy.deepcopy(trigger_config)
+        for k, v in (global_config or {}).items():
+            out['overall'].setdefault(k, v)
+        split, entries = [], {}
+        for chan, cc in trigger_config['channels'].items():
+            cc = copy.deepcopy(cc)
+            if not isinstance(cc, dict):
+                raise ValueError(f'ERROR: Channel {chan} has no configuration! Remove from yaml file or disable it!')
+            parts, _ = utils.split_channel_name(chan, available_channels=self._available_channels, label='trigger')
+            split.extend(parts)
+            trigger_channel = cc.pop('trigger_channel', chan)
+            if 'run' in cc:
+                if not cc['run']:
+                    continue
+                cc['channel_name'] = chan
+                entries[trigger_channel] = cc
+            else:
+                for algo, ad in cc.items():
+                    if not isinstance(ad, dict) or 'run' not in ad:
+                        raise ValueError(f'ERROR: Missing "run" parameter for trigger channel {chan}')
+                    if not ad['run']:
+                        continue
+                    ad['channel_name'] = chan
+                    entries[f'{algo}_{trigger_channel}'] = ad
+        out['channels'] = entries
+        out['channel_list'] = utils.unique_list(split)
         return out
 
     def _length(self, cfg, kind, default):

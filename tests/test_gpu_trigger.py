@@ -152,3 +152,62 @@ def test_two_channel_streams_through_the_event_builder():
     isA = (df['trigger_channel'] == 'A').values
     amp_trig = df['trigger_amplitude_A'].values
     assert np.all(np.abs(feats[ok & isA, off] / amp_trig[ok & isA] - 1) < 0.05)
+
+
+def test_trigger_processing_yaml_driver(tmp_path):
+    """TriggerProcessing (reference process/triggers.py:228, trigger loop :714-800) on two continuous events of two
+    channels, driven by the YAML trigger section: per-event EventBuilder, coincidence merge, ids running across
+    events, event_time = admin event_time + trigger_time."""
+    import torch
+    from detprocess_b200.core.filterdata import FilterData
+    from detprocess_b200.process import TriggerProcessing
+    S = SynthSetup(16384)
+    pre, fs, n = S.nb_pretrigger, S.fs, S.nb_samples
+    L = 1_000_000
+    rng = np.random.default_rng(31)
+    ev = np.zeros((2, 2, L))
+    truth = []
+    for e in range(2):
+        for c in range(2):
+            ev[e, c] = make_continuous(L, S.template, S.psd, fs, np.random.default_rng(40 + 2 * e + c), pulse_rate_hz=0.0)
+        pos = 40_000 + 60_000 * np.arange(15)
+        amps = rng.uniform(1e-7, 2e-7, len(pos))
+        for k, (t, a) in enumerate(zip(pos, amps)):
+            ev[e, 0, t:t + n - pre] += a * S.template[pre:]
+            if k % 3 == 0:                                  # coincident in B, 5 samples later, larger
+                ev[e, 1, t + 5:t + 5 + n - pre] += 1.5 * a * S.template[pre:]
+        truth.append(pos)
+    yml = tmp_path / 'trig.yaml'
+    yml.write_text('''
+trigger:
+    coincident_window_msec: 0.1
+    chanA:
+        run: True
+        threshold_sigma: 10
+        pileup_window_msec: 2
+    chanB:
+        run: True
+        threshold_sigma: 10
+        pileup_window_msec: 2
+''')
+    fd = FilterData()
+    for c in ('chanA', 'chanB'):
+        fd.set_psd(c, S.psd, sample_rate=fs)
+        fd.set_template(c, S.template, sample_rate=fs, pretrigger_length_samples=pre)
+    admin = [{'event_time': 1_700_000_000, 'series_num': 5, 'event_num': 1, 'dump_num': 1},
+             {'event_time': 1_700_000_001, 'series_num': 5, 'event_num': 2, 'dump_num': 1}]
+    tp = TriggerProcessing({'traces': torch.from_numpy(ev), 'channels': ['chanA', 'chanB'], 'sample_rate': fs, 'admin': admin},
+                           str(yml), filter_data=fd, processing_id='unit', verbose=False)
+    df = tp.process()
+    assert len(df) == 30
+    assert list(df['trigger_prod_id']) == list(range(1, 31))
+    assert list(df['event_number']) == [1] * 15 + [2] * 15
+    for e in range(2):
+        d = df[df['event_number'] == e + 1].reset_index(drop=True)
+        merged = d['trigger_index_chanB'].notnull()
+        assert list(np.nonzero(merged.values)[0]) == list(range(0, 15, 3))
+        assert (d.loc[merged, 'trigger_channel'] == 'chanB').all() and (d.loc[~merged, 'trigger_channel'] == 'chanA').all()
+        assert np.all(np.abs(d['trigger_index_chanA'].values - truth[e]) <= 2)
+        assert np.all(d['event_time'] == np.int64(np.around(admin[e]['event_time'] + d['trigger_time'])))
+    assert (df['processing_id'] == 'unit').all() and (df['series_number'] == 5).all()
+    assert len(tp.process(ntriggers=7)) == 7

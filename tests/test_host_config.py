@@ -142,3 +142,41 @@ def test_extractor_sentinels_and_errors_without_gpu():
     r = FE.of1x1_constrained('A', ofb, feature_base_name='c')
     assert set(r) == {f'{k}_c' for k in ('amp', 't0', 'chi2', 'lowchi2', 'chi2nopulse', 'ampres', 'timeres')}
     assert all(v == -999999.0 for v in r.values())
+
+
+def test_trigger_section_of_the_yaml(tmp_path):
+    """Trigger section semantics of the reference's YamlConfig._configure_triggers (process/config.py:324-408)."""
+    from detprocess_b200.process.config import YamlConfig
+    yml = tmp_path / 'trig.yaml'
+    yml.write_text('''
+trigger:
+    coincident_window_msec: 0.1
+    chanA:
+        run: True
+        threshold_sigma: 10
+        pileup_window_msec: 2
+    chanB:
+        trigger_name: B
+        fast:
+            run: True
+            threshold_sigma: 8
+            pileup_window_samples: 2500
+        slow:
+            run: False
+            threshold_sigma: 8
+    chanA+chanB:
+        run: False
+        threshold_sigma: 5
+chanA:
+    baseline:
+        run: True
+''')
+    cfg = YamlConfig(str(yml), ['chanA', 'chanB'], sample_rate=1.25e6, verbose=False).get_config('trigger')
+    assert list(cfg['channels']) == ['chanA', 'fast_B']
+    assert cfg['channels']['fast_B']['channel_name'] == 'chanB'
+    assert cfg['channels']['chanA'] == {'run': True, 'threshold_sigma': 10, 'pileup_window_msec': 2, 'channel_name': 'chanA'}
+    assert cfg['overall']['coincident_window_msec'] == 0.1
+    bad = tmp_path / 'bad.yaml'
+    bad.write_text('trigger:\n    chanA:\n        fast:\n            threshold_sigma: 8\n')
+    with pytest.raises(ValueError):
+        YamlConfig(str(bad), ['chanA'], sample_rate=1.25e6, verbose=False)
