@@ -46,6 +46,13 @@ SIGNATURES = {
     'dp_of_plan_add_fit': (_i, [_vp, _i, _i, _i, _i, _i, _ip]),
     'dp_of_plan_set_lowchi2_fcutoff': (_i, [_vp, _d]),
     'dp_of_plan_set_adc_conversion': (_i, [_vp, _i, _d, _d]),
+    'dp_csd_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i, _i]),
+    'dp_csd_plan_destroy': (None, [_vp]),
+    'dp_csd_plan_set_scale': (_i, [_vp, _d]),
+    'dp_csd_reset': (_i, [_vp, _vp]),
+    'dp_csd_accumulate': (_i, [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp]),
+    'dp_csd_get_sums': (_i, [_vp, _vp, _vp, _vp]),
+    'dp_csd_plan_last_kernel_ms': (_i, [_vp, C.POINTER(C.c_float)]),
     'dp_nxm_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i, _i]),
     'dp_nxm_plan_destroy': (None, [_vp]),
     'dp_nxm_plan_set_filter': (_i, [_vp, _vp, _vp, _i, _i]),

@@ -28,6 +28,7 @@ UNITS = [('dp_capi', 'dp_capi.cu', [])] + [
     for p in (1, 0) for i in (0, 1, 2, 3)] + [
     (f'dp_trig_inst_p{p}', 'dp_trig_inst.cu', [f'-DDP_INST_PREC={p}']) for p in (1, 0)] + [
     (f'dp_nxm_inst_p{p}_{c}', 'dp_nxm_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_NCH={c}']) for p in (1, 0) for c in (1, 2, 3, 4)] + [
+    (f'dp_csd_inst_p{p}_{c}', 'dp_csd_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_NCH={c}']) for p in (1, 0) for c in (2, 3, 4)] + [
     (f'dp_of_inst_p{p}_{i}', 'dp_of_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_IN={i}'])
     for p in (1, 0) for i in (0, 1, 2)]
 

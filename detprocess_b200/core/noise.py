@@ -105,3 +105,57 @@ def calc_psd(traces, fs, cut=None, precision='f64', batch=4096):
     for i in range(0, traces.shape[0], batch):
         est.update(traces[i:i + batch], None if cut is None else cut[i:i + batch])
     return est.finalize()
+
+
+def csd_from_sums(sums, count, n_chan, nb_samples, fs):
+    """[n*n, N/2+1] component sums (CSDPlan.sums layout) -> two-sided complex csd [n, n, N] in fftfreq order:
+    csd[a, b, k] = mean_events X_a[k] conj(X_b[k]) / (N fs); csd[b, a] = conj(csd[a, b]); csd[.., N-k] = conj(csd[.., k])."""
+    sums = np.asarray(sums, dtype=np.float64) / (float(count) * nb_samples * fs)
+    nh = nb_samples // 2 + 1
+    half = np.zeros((n_chan, n_chan, nh), dtype=np.complex128)
+    pi = 0
+    for a in range(n_chan):
+        half[a, a] = sums[a]
+        for b in range(a + 1, n_chan):
+            half[a, b] = sums[n_chan + 2 * pi] + 1j * sums[n_chan + 2 * pi + 1]
+            half[b, a] = np.conj(half[a, b])
+            pi += 1
+    neg = np.conj(half[:, :, 1:nb_samples - nb_samples // 2][:, :, ::-1])
+    return np.concatenate([half, neg], axis=-1)
+
+
+class NoiseCSD:
+    """Streaming, multi-GPU ``calc_csd`` (reference Noise.calc_csd, core/noise.py:374-470: qp.calc_csd(traces[cut], fs,
+    folded_over=False) on [n_events, n_chan, N] randoms).  Same flow as ``NoisePSD``: per-rank sums, one all-reduce
+    (NCCL over NVLink) of the [n*n, N/2+1] float64 sums and the count, CSD formed on every rank.
+
+    Convention: csd[a, b] = E[X_a conj(X_b)] -- the noise covariance the NxM filter inverts (oracle/ofnxm.py);
+    scipy.signal.csd, which QETpy's calc_csd is built on, returns the complex conjugate (= the transpose)."""
+
+    def __init__(self, nb_samples, fs, n_chan, precision='f64', device=None, typical_rms=None):
+        from .plans import CSDPlan
+        self.nb_samples, self.fs, self.n_chan = int(nb_samples), float(fs), int(n_chan)
+        self.plan = CSDPlan(nb_samples, fs, n_chan, precision=precision, device=device)
+        if typical_rms is not None:
+            self.plan.set_scale(typical_rms)
+
+    def update(self, traces, cut=None):
+        self.plan.accumulate(traces, cut)
+
+    def finalize(self, group=None):
+        sums, count = self.plan.sums()
+        sums, count = allreduce_sums(sums, count, group)
+        n = int(count.item())
+        if n == 0:
+            raise ValueError('ERROR: No events selected after pileup cut!')
+        self.count = n
+        csd = csd_from_sums(sums.cpu().numpy(), n, self.n_chan, self.nb_samples, self.fs)
+        return np.fft.fftfreq(self.nb_samples, 1.0 / self.fs), csd
+
+
+def calc_csd(traces, fs, cut=None, precision='f64', batch=2048):
+    """One-call form on a CUDA tensor [n_events, n_chan, N]."""
+    est = NoiseCSD(traces.shape[-1], fs, traces.shape[1], precision=precision, device=traces.device)
+    for i in range(0, traces.shape[0], batch):
+        est.update(traces[i:i + batch], None if cut is None else cut[i:i + batch])
+    return est.finalize()

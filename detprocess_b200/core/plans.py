@@ -459,3 +459,65 @@ class PSDPlan:
         ms = C.c_float()
         check(lib.dp_psd_plan_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+class CSDPlan:
+    """Per-GPU accumulation of sum_events X_a[k] conj(X_b[k]), k = 0..N/2, for n_chan channels (``dp_csd_plan``).
+    ``sums`` returns [n_chan * n_chan, N/2 + 1] float64 (diagonal rows, then (re, im) rows per pair a < b) and the
+    accepted-event count, as CUDA tensors, so that the host layer can all-reduce them before forming the CSD."""
+
+    def __init__(self, nb_samples, sample_rate, n_chan, precision='f64', device=None):
+        torch = _torch()
+        if precision not in _PREC:
+            raise ValueError(f'unknown precision "{precision}"')
+        if not torch.cuda.is_available():
+            raise _lib.DetprocessB200Error('no CUDA device: detprocess_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        self.device = device
+        self.nb_samples, self.sample_rate, self.n_chan = int(nb_samples), float(sample_rate), int(n_chan)
+        self._h = C.c_void_p()
+        check(lib.dp_csd_plan_create(C.byref(self._h), self.nb_samples, self.sample_rate, self.n_chan, _PREC[precision],
+                                     device.index or 0))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            lib.dp_csd_plan_destroy(h)
+            self._h = C.c_void_p()
+
+    def set_scale(self, typical_rms):
+        check(lib.dp_csd_plan_set_scale(self._h, float(typical_rms)))
+
+    def reset(self):
+        check(lib.dp_csd_reset(self._h, _stream_ptr(self.device)))
+
+    def accumulate(self, traces, mask=None):
+        """traces: CUDA float64 [n_events, n_chan, N]; mask: optional CUDA bool/uint8 [n_events] (True = keep)."""
+        torch = _torch()
+        if not traces.is_cuda or traces.dtype != torch.float64:
+            raise ValueError('accumulate() takes CUDA float64 tensors')
+        if traces.ndim != 3 or traces.shape[1] != self.n_chan or traces.shape[2] != self.nb_samples:
+            raise ValueError('traces must be [n_events, n_chan, nb_samples]')
+        traces = traces.contiguous()
+        mptr = C.c_void_p(0)
+        if mask is not None:
+            mask = mask.to(device=traces.device, dtype=torch.uint8).contiguous()
+            if mask.shape != (traces.shape[0],):
+                raise ValueError('mask must be [n_events]')
+            mptr = C.c_void_p(mask.data_ptr())
+        check(lib.dp_csd_accumulate(self._h, C.c_void_p(traces.data_ptr()), traces.shape[0], self.n_chan * self.nb_samples,
+                                    self.nb_samples, mptr, _stream_ptr(traces.device)))
+
+    def sums(self):
+        torch = _torch()
+        sums = torch.empty((self.n_chan * self.n_chan, self.nb_samples // 2 + 1), dtype=torch.float64, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        check(lib.dp_csd_get_sums(self._h, C.c_void_p(sums.data_ptr()), C.c_void_p(count.data_ptr()), _stream_ptr(self.device)))
+        return sums, count
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(lib.dp_csd_plan_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value

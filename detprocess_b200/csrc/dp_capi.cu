@@ -12,6 +12,8 @@
 #include <vector>
 
 #include "../../include/detprocess_b200.h"
+#include "dp_csd_kernel.cuh"
+#include "dp_csd_launch.hpp"
 #include "dp_nxm_launch.hpp"
 #include "dp_nxm_plan.hpp"
 #include "dp_of2_launch.hpp"
@@ -1621,6 +1623,222 @@ int dp_ofnxm_batch(dp_nxm_plan* p, const double* traces_dev, long long n_events,
 
 int dp_nxm_plan_last_kernel_ms(dp_nxm_plan* p, float* ms) {
     if (!p || !p->finalized || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
+    DP_CUDA(cudaEventSynchronize(p->ev1));
+    DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return DP_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================= CSD plan
+struct dp_csd_plan {
+    int N = 0, n = 0, precision = DP_PREC_F64, r1 = 0, device = 0;
+    double fs = 0, scale = 1.0;
+    std::vector<void*> owned;
+    const void *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twn = nullptr, *groups = nullptr;
+    const int* loc = nullptr;
+    void* scratch = nullptr;
+    long long scratch_per_cta = 0;
+    double* partial = nullptr;
+    long long partial_per_comp = 0, partial_per_cta = 0;
+    unsigned long long *count = nullptr, *count_out = nullptr;
+    int grid_max = 0;
+    size_t smem = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+template <class T, int R1> int csd_tables(dp_csd_plan* p) {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    std::vector<dpplan::Channel> none;
+    dpplan2::Tables2<T> dt;
+    try {
+        dt = dpplan2::build_tables2<T, R1>(p->fs, none, 0.0, 1.0);
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_STATE, e.what());
+    }
+    int rc;
+    const cx<T>* d;
+    if ((rc = upload(p->owned, dt.tw1, &d))) return rc;
+    p->tw1 = d;
+    if ((rc = upload(p->owned, dt.tw2, &d))) return rc;
+    p->tw2 = d;
+    if ((rc = upload(p->owned, dt.tw3, &d))) return rc;
+    p->tw3 = d;
+    const cx<S>* ds;
+    if ((rc = upload(p->owned, dt.twn, &ds))) return rc;
+    p->twn = ds;
+    const int2* dg;
+    if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
+    p->groups = dg;
+    // natural bin k -> slot of one component in a CTA's partial array (same map as the PSD plan)
+    std::vector<int> loc(G::M + 1, -1);
+    const int nspecial = G::VL == 2 ? 1 : 2;
+    for (int ph = 0; ph < G::NPH; ++ph)
+        for (int t = 0; t < G::NT; ++t) {
+            if (ph == 0 && t < nspecial) continue;
+            for (int e = 0; e < 16; ++e) {
+                int b[2];
+                dpplan2::entry_bins<G>(ph, t, e, b);
+                for (int l = 0; l < G::VL; ++l) loc[b[l]] = ((ph * 16 + e) * G::NT + t) * G::VL + l;
+            }
+        }
+    for (int l = 0; l < 17; ++l) {
+        int b[2];
+        bool dup[2];
+        dpplan2::self_bins<G>(l, b, dup);
+        for (int j = 0; j < 2; ++j)
+            if (!dup[j]) loc[b[j]] = G::NPH * 16 * G::NT * G::VL + 2 * l + j;
+    }
+    for (int k = 0; k <= G::M; ++k)
+        if (loc[k] < 0) return fail(DP_ERR_STATE, "internal: CSD bin map incomplete");
+    if ((rc = upload(p->owned, loc, &p->loc))) return rc;
+    return DP_OK;
+}
+template <class T> int csd_finalize(dp_csd_plan* p) {
+    int rc;
+    switch (p->r1) {
+        case 2: rc = csd_tables<T, 2>(p); break;
+        case 4: rc = csd_tables<T, 4>(p); break;
+        default: rc = csd_tables<T, 8>(p); break;
+    }
+    if (rc) return rc;
+    const int prec = sizeof(typename Dp2Traits<T>::S) == 8 ? 0 : 1;
+    const int src = dp_csd_setup_table[prec][p->n - 2](p->r1, p->device, &p->smem, &p->grid_max, &p->partial_per_comp, &p->scratch_per_cta);
+    if (src != 0) return fail(DP_ERR_CUDA, "CSD kernel setup failed");
+    p->partial_per_cta = p->partial_per_comp * p->n * p->n;
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->partial), sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
+    p->owned.push_back(p->partial);
+    DP_CUDA(cudaMalloc(&p->scratch, sizeof(cx<T>) * (size_t)p->scratch_per_cta * (size_t)p->grid_max));
+    p->owned.push_back(p->scratch);
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->count), sizeof(unsigned long long) * (size_t)(p->grid_max + 1)));
+    p->owned.push_back(p->count);
+    p->count_out = p->count + p->grid_max;
+    return DP_OK;
+}
+template <class T> int csd_launch(dp_csd_plan* p, const double* traces, long long n_events, long long ev_stride, long long chan_stride,
+                                  const unsigned char* mask, cudaStream_t st) {
+    using S = typename Dp2Traits<T>::S;
+    DpCsdParams<T> prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.traces = traces;
+    prm.ev_stride = ev_stride;
+    prm.chan_stride = chan_stride;
+    prm.n_events = (int)n_events;
+    prm.mask = mask;
+    prm.tw1 = (const cx<T>*)p->tw1;
+    prm.tw2 = (const cx<T>*)p->tw2;
+    prm.tw3 = (const cx<T>*)p->tw3;
+    prm.twn = (const cx<S>*)p->twn;
+    prm.groups = (const int2*)p->groups;
+    prm.scratch = (cx<T>*)p->scratch;
+    prm.scratch_per_cta = p->scratch_per_cta;
+    prm.partial = p->partial;
+    prm.partial_per_cta = p->partial_per_cta;
+    prm.count = p->count;
+    prm.scale = p->scale;
+    prm.subtract_first = p->precision == DP_PREC_F32 ? 1 : 0;
+    const int grid = (int)std::min<long long>(n_events, p->grid_max);
+    const int prec = sizeof(S) == 8 ? 0 : 1;
+    return dp_csd_launch_table[prec][p->n - 2](p->r1, &prm, grid, p->smem, st);
+}
+}  // namespace
+
+extern "C" {
+
+int dp_csd_plan_create(dp_csd_plan** plan, int nb_samples, double sample_rate, int n_chan, int precision, int device) {
+    if (!plan) return fail(DP_ERR_INVALID, "null plan pointer");
+    if (!(sample_rate > 0)) return fail(DP_ERR_INVALID, "sample_rate must be > 0");
+    if (precision != DP_PREC_F64 && precision != DP_PREC_F32) return fail(DP_ERR_INVALID, "unknown precision");
+    if (!dpplan2::r1_of(nb_samples)) return fail(DP_ERR_UNSUPPORTED, "the CSD estimator needs nb_samples 16384, 32768 or 65536");
+    if (n_chan < 2 || n_chan > DP_CSD_MAX_CHAN) return fail(DP_ERR_INVALID, "n_chan must be 2.." + std::to_string(DP_CSD_MAX_CHAN));
+    auto p = std::make_unique<dp_csd_plan>();
+    p->N = nb_samples;
+    p->fs = sample_rate;
+    p->n = n_chan;
+    p->precision = precision;
+    p->device = device;
+    p->r1 = dpplan2::r1_of(nb_samples);
+    DP_CUDA(cudaSetDevice(device));
+    const int rc = precision == DP_PREC_F32 ? csd_finalize<f2>(p.get()) : csd_finalize<double>(p.get());
+    if (rc) {
+        for (void* d : p->owned) cudaFree(d);
+        return rc;
+    }
+    DP_CUDA(cudaEventCreate(&p->ev0));
+    DP_CUDA(cudaEventCreate(&p->ev1));
+    DP_CUDA(cudaMemset(p->partial, 0, sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
+    DP_CUDA(cudaMemset(p->count, 0, sizeof(unsigned long long) * (size_t)(p->grid_max + 1)));
+    *plan = p.release();
+    return DP_OK;
+}
+void dp_csd_plan_destroy(dp_csd_plan* p) {
+    if (!p) return;
+    for (void* d : p->owned) cudaFree(d);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+int dp_csd_plan_set_scale(dp_csd_plan* p, double typical_rms) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (!(typical_rms > 0)) return fail(DP_ERR_INVALID, "typical_rms must be > 0");
+    p->scale = p->precision == DP_PREC_F32 ? std::exp2(-std::round(std::log2(typical_rms))) : 1.0;
+    return DP_OK;
+}
+int dp_csd_reset(dp_csd_plan* p, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DP_CUDA(cudaMemsetAsync(p->partial, 0, sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max, st));
+    DP_CUDA(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long) * (size_t)(p->grid_max + 1), st));
+    return DP_OK;
+}
+int dp_csd_accumulate(dp_csd_plan* p, const double* traces_dev, long long n_events, long long event_stride, long long chan_stride,
+                      const unsigned char* mask_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
+    if (n_events == 0) return DP_OK;
+    if (!traces_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if (chan_stride < p->N || (chan_stride & 1) || (event_stride & 1) || event_stride < chan_stride * (p->n - 1) + p->N)
+        return fail(DP_ERR_INVALID, "strides must be even, chan_stride >= nb_samples, event_stride >= the channels of an event");
+    if ((reinterpret_cast<uintptr_t>(traces_dev) & 15) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
+    if (n_events > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    DP_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DP_CUDA(cudaEventRecord(p->ev0, st));
+    const int rc = p->precision == DP_PREC_F32 ? csd_launch<f2>(p, traces_dev, n_events, event_stride, chan_stride, mask_dev, st)
+                                               : csd_launch<double>(p, traces_dev, n_events, event_stride, chan_stride, mask_dev, st);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("CSD kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    DP_CUDA(cudaEventRecord(p->ev1, st));
+    p->timed = true;
+    return DP_OK;
+}
+int dp_csd_get_sums(dp_csd_plan* p, double* sums_dev, unsigned long long* count_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (!sums_dev || !count_dev) return fail(DP_ERR_INVALID, "null buffer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nbins = p->N / 2 + 1, ncomp = p->n * p->n;
+    DP_CUDA(cudaMemsetAsync(sums_dev, 0, sizeof(double) * (size_t)nbins * ncomp, st));
+    DP_CUDA(cudaMemsetAsync(p->count_out, 0, sizeof(unsigned long long), st));
+    DpCsdReduceParams prm;
+    prm.partial = p->partial;
+    prm.partial_per_cta = p->partial_per_cta;
+    prm.partial_per_comp = p->partial_per_comp;
+    prm.grid = p->grid_max;
+    prm.loc = p->loc;
+    prm.nbins = nbins;
+    prm.ncomp = ncomp;
+    prm.sum_out = sums_dev;
+    prm.count = p->count;
+    prm.count_out = p->count_out;
+    const int rc = dp_csd_reduce_launch(&prm, st);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("CSD reduce launch: ") + cudaGetErrorString((cudaError_t)rc));
+    DP_CUDA(cudaMemcpyAsync(count_dev, p->count_out, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    return DP_OK;
+}
+int dp_csd_plan_last_kernel_ms(dp_csd_plan* p, float* ms) {
+    if (!p || !p->timed) return fail(DP_ERR_STATE, "no timed launch");
     DP_CUDA(cudaEventSynchronize(p->ev1));
     DP_CUDA(cudaEventElapsedTime(ms, p->ev0, p->ev1));
     return DP_OK;

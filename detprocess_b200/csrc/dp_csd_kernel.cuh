@@ -1,0 +1,204 @@
+// Noise cross-spectral density accumulation on the v2 FFT core (nb_samples 16384 / 32768 / 65536), NCH channels per
+// event: the channels go through the forward half of the fused OF kernel one after the other (their spectra parked in a
+// thread-private L2 column, as in dp_nxm_kernel.cuh), then the thread adds X_a conj(X_b) of its bins into per-CTA
+// partial sums kept in thread order -- NCH real arrays (a == b) and a (re, im) pair of arrays per a < b; coalesced
+// read-modify-write of thread-private slots, no atomics.  dp_csd_reduce_kernel folds the CTAs and maps thread order ->
+// natural k; the per-GPU sums are all-reduced over NCCL by the host layer and turned into the two-sided [n, n, N] array.
+//
+// Replaces qp.calc_csd(traces[cut], fs, folded_over=False) as called from Noise.calc_csd
+// (reference detprocess/core/noise.py:374-470; the cut of :431-450 enters as the event mask).
+#pragma once
+#include "dp_of2_kernel.cuh"
+
+#define DP_CSD_MAX_CHAN 4
+
+template <class T> struct DpCsdParams {
+    using S = typename Dp2Traits<T>::S;
+    const double* traces;    // [n_events][n_chan][N] float64
+    long long ev_stride;     // elements
+    long long chan_stride;
+    int n_events;
+    const unsigned char* mask;  // [n_events] 1 = use the event (nullptr: all)
+    const cx<T>* tw1;
+    const cx<T>* tw2;
+    const cx<T>* tw3;
+    const cx<S>* twn;
+    const int2* groups;
+    cx<T>* scratch;
+    long long scratch_per_cta;  // V units
+    double* partial;            // [grid][n_comp][PARTIAL]
+    long long partial_per_cta;
+    unsigned long long* count;  // [grid] accepted events per CTA
+    double scale;
+    int subtract_first;
+};
+
+template <class T, int R1, int NCH> struct DpCsdKernel {
+    using G = Dp2Geom<T, R1>;
+    using S = typename G::S;
+    using V = cx<T>;
+    using Core = Dp2Core<T, R1, 0>;
+    using OF = Dp2OfKernel<T, R1, 0>;
+    static constexpr int NT = G::NT, VL = G::VL, NPH = G::NPH, N = G::N;
+    static constexpr int SX = 34;
+    static constexpr int NCOMP = NCH * NCH;  // NCH diagonal arrays + (re, im) per pair a < b
+    static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (32 + SX * NCH) + sizeof(double) * NCH + 64;
+    static constexpr long long PARTIAL = (long long)NPH * 16 * NT * VL + 17 * 2;  // slots of one component
+    static constexpr long long SCR_X = (long long)16 * NT;
+    static DP_HD long long scratch_v() { return SCR_X * NCH; }
+    static DP_HD int pair_index(int a, int b) { return a * NCH - a * (a + 1) / 2 + (b - a - 1); }
+
+    static DP_DEV void run(const DpCsdParams<T>& prm, unsigned char* smem_raw) {
+        V* const buf = reinterpret_cast<V*>(smem_raw);
+        cx<S>* const sp = reinterpret_cast<cx<S>*>(buf + G::SMEM_V);
+        cx<S>* const sx = sp + 32;                                        // [NCH][17][2]
+        double* const dcv = reinterpret_cast<double*>(sx + SX * NCH);     // [NCH] DC bin in double (thread 0)
+        const int tid = threadIdx.x;
+        constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
+        V* const scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
+        double* const part = prm.partial + (long long)blockIdx.x * prm.partial_per_cta;
+        const double inv_s2 = 1.0 / (4.0 * prm.scale * prm.scale);  // kernel values are 2*scale*X
+        const unsigned long long pol = dp2_policy_keep();
+        unsigned long long n_acc = 0;
+
+        for (int ev = blockIdx.x; ev < prm.n_events; ev += gridDim.x) {
+            if (prm.mask != nullptr && prm.mask[ev] == 0) continue;  // CTA-uniform
+            ++n_acc;
+            const double* xev = prm.traces + (long long)ev * prm.ev_stride;
+#pragma unroll 1
+            for (int p = 0; p < NPH; ++p) {
+                V z[16];
+                [[maybe_unused]] V zm[VL == 1 ? 8 : 1];
+                const int2 gg = prm.groups[p * NT + tid];
+                const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
+                const bool special = (p == 0) && (tid < NSPECIAL);
+                [[maybe_unused]] int Gp = 0;
+                if constexpr (VL == 1) Gp = __shfl_xor_sync(0xffffffffu, gg.x, 1);
+#pragma unroll 1
+                for (int a = 0; a < NCH; ++a) {
+                    const double* xrow = xev + (long long)a * prm.chan_stride;
+                    const double x0 = prm.subtract_first ? dp_load_first<0>(xrow) : 0.0;
+                    Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
+                    __syncthreads();
+                    Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+                    if (p == 0 && tid < 32) {
+                        if constexpr (VL == 2) {
+                            if (tid == 0) {
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) {
+                                    sp[r] = dp2_lane0(z[r]);
+                                    sp[16 + r] = dp2_lane1(z[r]);
+                                }
+                            }
+                        } else {
+                            if (tid < 2) {
+#pragma unroll
+                                for (int r = 0; r < 16; ++r) sp[16 * tid + r] = z[r];
+                            }
+                        }
+                        __syncwarp();
+                        if (tid < 17) {
+                            const DpSelfLane<S> sl = dp_self_lane<S, 1>(tid);
+                            cx<S> Xk, Xm;
+                            dp_untangle(sp[sl.ek], sp[sl.em], sl.w, Xk, Xm);
+                            sx[a * SX + 2 * tid] = Xk;
+                            sx[a * SX + 2 * tid + 1] = Xm;
+                            // DC bin in double, with the subtracted first sample put back: X[0] += N*x0
+                            if (tid == 0) dcv[a] = (double)Xk.re / (2.0 * prm.scale) + (double)N * x0;
+                        }
+                        __syncwarp();
+                    }
+                    V* dst = scr_x + SCR_X * a + tid;
+                    if constexpr (VL == 2) {
+                        (void)OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
+                    } else {
+                        OF::pw_publish(buf, z, gg.x);
+                        OF::pw_untangle(buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) {
+                            dp2_st_keep(dst + (2 * r) * NT, Xk, pol);
+                            dp2_st_keep(dst + (2 * r + 1) * NT, Xm, pol);
+                        });
+                    }
+                    __syncthreads();  // group-row reads of this channel precede the next pass-1 stores
+                }
+
+                // ---------------- X_a conj(X_b) of the thread's bins -> its partial-sum slots ----------------
+                if (!special) {
+#pragma unroll 2
+                    for (int r = 0; r < 16; ++r) {
+                        V X[NCH];
+#pragma unroll
+                        for (int a = 0; a < NCH; ++a) X[a] = dp2_ld_keep(scr_x + SCR_X * a + r * NT + tid, pol);
+                        const long long slot = ((long long)p * 16 + r) * NT + tid;
+                        auto add = [&](int comp, T v) {
+                            if constexpr (VL == 2) {
+                                double2* q = reinterpret_cast<double2*>(part + (long long)comp * PARTIAL) + slot;
+                                double2 s = *q;
+                                s.x += (double)v.x * inv_s2;
+                                s.y += (double)v.y * inv_s2;
+                                *q = s;
+                            } else {
+                                part[(long long)comp * PARTIAL + slot] += v * inv_s2;
+                            }
+                        };
+#pragma unroll
+                        for (int a = 0; a < NCH; ++a) {
+                            add(a, cnorm2(X[a]));
+#pragma unroll
+                            for (int b = a + 1; b < NCH; ++b) {
+                                const int c = NCH + 2 * pair_index(a, b);
+                                add(c, dp_fma(X[a].re, X[b].re, X[a].im * X[b].im));
+                                add(c + 1, dp_fma(X[a].im, X[b].re, -(X[a].re * X[b].im)));
+                            }
+                        }
+                    }
+                }
+                if (p == 0 && tid < 17) {
+                    const long long base = (long long)NPH * 16 * NT * VL + 2 * tid;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const bool dc = (tid == 0 && j == 0);
+#pragma unroll
+                        for (int a = 0; a < NCH; ++a) {
+                            const cx<S> Xa = sx[a * SX + 2 * tid + j];
+                            part[(long long)a * PARTIAL + base + j] += dc ? dcv[a] * dcv[a] : (double)cnorm2(Xa) * inv_s2;
+#pragma unroll
+                            for (int b = a + 1; b < NCH; ++b) {
+                                const cx<S> Xb = sx[b * SX + 2 * tid + j];
+                                const int c = NCH + 2 * pair_index(a, b);
+                                const double re = (double)Xa.re * (double)Xb.re + (double)Xa.im * (double)Xb.im;
+                                const double im = (double)Xa.im * (double)Xb.re - (double)Xa.re * (double)Xb.im;
+                                part[(long long)c * PARTIAL + base + j] += dc ? dcv[a] * dcv[b] : re * inv_s2;
+                                part[(long long)(c + 1) * PARTIAL + base + j] += dc ? 0.0 : im * inv_s2;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();  // sx / dcv / the scratch columns are rewritten by the next phase or event
+            }
+        }
+        if (tid == 0) prm.count[blockIdx.x] += n_acc;
+    }
+};
+
+struct DpCsdReduceParams {
+    const double* partial;
+    long long partial_per_cta;
+    long long partial_per_comp;
+    int grid;
+    const int* loc;   // [nbins] natural bin k -> slot of one component
+    int nbins;
+    int ncomp;
+    double* sum_out;  // [ncomp][nbins], zeroed by the caller
+    const unsigned long long* count;
+    unsigned long long* count_out;
+};
+
+#ifndef DP_HOST_EMU
+template <class T, int R1, int NCH>
+__global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, Dp2Geom<T, R1>::NT <= 256 ? 2 : 1) dp_csd_kernel(const DpCsdParams<T> prm) {
+    extern __shared__ __align__(16) unsigned char dp_smem_raw[];
+    DpCsdKernel<T, R1, NCH>::run(prm, dp_smem_raw);
+}
+#endif

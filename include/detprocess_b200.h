@@ -231,6 +231,22 @@ int dp_ofnxm_batch(dp_nxm_plan* plan, const double* traces_dev, long long n_even
                    long long chan_stride, double* out_dev, void* stream);
 int dp_nxm_plan_last_kernel_ms(dp_nxm_plan* plan, float* ms);
 
+/* ------------------------------------------------------------------ noise cross-spectral density
+ * Replaces qp.calc_csd(traces[cut], fs=fs, folded_over=False) of Noise.calc_csd (reference detprocess/core/noise.py:374-470;
+ * mask = the per-channel autocuts AND-ed at :431-445).  Accumulates sum_e X_a[k] conj(X_b[k]) on the one-sided bins
+ * k = 0..N/2 over any number of dp_csd_accumulate calls.  dp_csd_get_sums writes [n_chan * n_chan][N/2 + 1] float64:
+ * rows 0..n-1 the diagonal sums |X_a|^2, then for every pair a < b (lexicographic) a row of real parts and a row of
+ * imaginary parts of X_a conj(X_b); csd[a][b][k] = sums / (count * N * fs), csd[b][a] = conj, csd[..][N - k] = conj. */
+typedef struct dp_csd_plan dp_csd_plan;
+int dp_csd_plan_create(dp_csd_plan** plan, int nb_samples, double sample_rate, int n_chan, int precision, int device);
+void dp_csd_plan_destroy(dp_csd_plan* plan);
+int dp_csd_plan_set_scale(dp_csd_plan* plan, double typical_rms);
+int dp_csd_reset(dp_csd_plan* plan, void* stream);
+int dp_csd_accumulate(dp_csd_plan* plan, const double* traces_dev, long long n_events, long long event_stride,
+                      long long chan_stride, const unsigned char* mask_dev, void* stream);
+int dp_csd_get_sums(dp_csd_plan* plan, double* sums_dev, unsigned long long* count_dev, void* stream);
+int dp_csd_plan_last_kernel_ms(dp_csd_plan* plan, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

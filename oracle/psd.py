@@ -47,3 +47,23 @@ def offset(traces, cut=None):
     if cut is not None:
         traces = traces[np.asarray(cut, dtype=bool)]
     return float(np.average(np.median(traces, axis=-1)))
+
+
+def calc_csd(traces, fs, cut=None):
+    """Cross-spectral density of [n_events, n_chan, N] traces, two-sided complex [n, n, N] in fftfreq order -- restates
+    ``qp.calc_csd(traces[cut], fs=fs, folded_over=False)`` of ``Noise.calc_csd`` (reference core/noise.py:374-470):
+
+        csd[a, b, k] = mean_events fft(x_a)[k] conj(fft(x_b)[k]) / (N fs)
+
+    i.e. the noise covariance E[X_a conj(X_b)] that ``oracle/ofnxm.py`` inverts; its diagonal is ``calc_psd``.
+    PARITY UNPINNED: scipy.signal.csd (which QETpy builds on) defines P_xy = conj(X) Y, the complex conjugate of this;
+    the choice is isolated here and in ``detprocess_b200/core/noise.py::csd_from_sums``."""
+    traces = np.asarray(traces, dtype=np.float64)
+    if cut is not None:
+        traces = traces[np.asarray(cut, dtype=bool)]
+    ne, n, N = traces.shape
+    acc = np.zeros((n, n, N), dtype=np.complex128)
+    for x in traces:
+        X = np.fft.fft(x, axis=-1)
+        acc += X[:, None, :] * np.conj(X[None, :, :])
+    return np.fft.fftfreq(N, 1.0 / fs), acc / (ne * N * fs)

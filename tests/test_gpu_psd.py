@@ -72,3 +72,31 @@ def test_psd_int16_and_float32_traces():
         est.update(torch.from_numpy(adc).to(dev).to(dt))
         _, p = est.finalize()
         assert np.array_equal(p, p_ref)
+
+
+@pytest.mark.parametrize('precision,nb_samples,n_chan', [('f64', 16384, 2), ('f32', 32768, 3), ('f64', 65536, 2), ('f32', 16384, 4),
+                                                         ('f64', 32768, 4)])
+def test_csd_parity(precision, nb_samples, n_chan):
+    """dp_csd_accumulate / dp_csd_get_sums == oracle calc_csd (Noise.calc_csd, noise.py:374-470): full two-sided
+    [n, n, N] array, event mask, two accumulate calls."""
+    import torch
+    from detprocess_b200.core.noise import NoiseCSD
+    from detprocess_b200.synth import SynthNxM
+    from oracle.psd import calc_csd
+    S = SynthNxM(nb_samples, n_chan, 1)
+    x = S.traces(96, np.random.default_rng(9), pulse_fraction=0.0) + 3e-8     # DC offset: exercises the DC bin
+    cut = np.arange(96) % 5 != 0
+    est = NoiseCSD(nb_samples, S.fs, n_chan, precision=precision, typical_rms=1e-8)
+    xd = torch.from_numpy(x).cuda()
+    cd = torch.from_numpy(cut).cuda()
+    est.update(xd[:40], cd[:40])
+    est.update(xd[40:], cd[40:])
+    f, csd = est.finalize()
+    fo, ref = calc_csd(x, S.fs, cut)
+    assert est.count == int(cut.sum())
+    assert np.array_equal(f, fo)
+    tol = 1e-11 if precision == 'f64' else 3e-5
+    scale = np.sqrt(np.abs(ref[np.arange(n_chan), np.arange(n_chan)])[:, None, :] * np.abs(ref[np.arange(n_chan), np.arange(n_chan)])[None, :, :])
+    assert np.max(np.abs(csd - ref) / scale) < tol
+    # its inverse drives the NxM filter: the estimate is a valid (hermitian, positive) csd at every bin
+    assert np.allclose(csd, np.conj(np.transpose(csd, (1, 0, 2))))

@@ -96,3 +96,51 @@ def test_two_rank_psd_allreduce_equals_single():
         assert p.exitcode == 0
     assert count == nref
     assert np.allclose(psd, ref, rtol=1e-12, atol=0)
+
+
+def _csd_component_sums(x):
+    """what one GPU accumulates for its shard, in the CSDPlan.sums layout"""
+    ne, n, N = x.shape
+    X = np.fft.rfft(x, axis=-1)
+    rows = [np.sum(np.abs(X[:, a]) ** 2, axis=0) for a in range(n)]
+    for a in range(n):
+        for b in range(a + 1, n):
+            z = np.sum(X[:, a] * np.conj(X[:, b]), axis=0)
+            rows += [z.real, z.imag]
+    return np.stack(rows)
+
+
+def _csd_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from detprocess_b200.core.noise import allreduce_sums, csd_from_sums
+    from oracle import psd as P
+    n, fs, n_ev = 512, 1.25e6, 70
+    x = np.random.default_rng(31).standard_normal((n_ev, 3, n)) * 1e-10
+    x[:, 1] += 0.5 * np.roll(x[:, 0], 2, axis=-1)             # correlated, delayed: complex off-diagonal terms
+    lo, hi = shard_range(n_ev, rank, world)
+    sums, count = allreduce_sums(torch.from_numpy(_csd_component_sums(x[lo:hi])), torch.tensor([hi - lo], dtype=torch.int64))
+    csd = csd_from_sums(sums.numpy(), int(count.item()), 3, n, fs)
+    if rank == 0:
+        q.put((csd, P.calc_csd(x, fs)[1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_csd_allreduce_equals_single():
+    """Noise.calc_csd host path: per-rank component sums all-reduced and unfolded == CSD of the whole set."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_csd_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    csd, ref = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.allclose(csd, ref, rtol=1e-11, atol=1e-40)

@@ -45,3 +45,24 @@ def test_offset_matches_numpy():
     rng = np.random.default_rng(3)
     tr = rng.standard_normal((10, 100)) + 4.0
     assert P.offset(tr) == np.average(np.median(tr, axis=-1))
+
+
+def test_csd_oracle_diagonal_is_the_psd_and_matches_the_generating_csd():
+    """calc_csd: hermitian in (a, b), conjugate-symmetric in k, diagonal == calc_psd, and its expectation is the CSD the
+    synthetic traces were drawn from (complex off-diagonal terms included)."""
+    from detprocess_b200.synth import SynthNxM
+    from oracle.psd import calc_csd
+    S = SynthNxM(2048, 3, 1)
+    x = S.traces(600, np.random.default_rng(3), pulse_fraction=0.0)
+    f, csd = calc_csd(x, S.fs)
+    assert csd.shape == (3, 3, 2048)
+    assert np.allclose(csd, np.conj(np.transpose(csd, (1, 0, 2))))
+    assert np.allclose(csd[:, :, 1:], np.conj(csd[:, :, :0:-1]))
+    for a in range(3):
+        assert np.allclose(csd[a, a].real, P.calc_psd(x[:, a], S.fs)[1], rtol=1e-12)
+    band = slice(4, 200)
+    for a, b in [(0, 1), (0, 2), (1, 2)]:
+        r = np.mean(csd[a, b, band] / S.csd[a, b, band])
+        assert abs(r - 1) < 0.1
+    cut = np.arange(600) % 3 != 0
+    assert np.allclose(calc_csd(x, S.fs, cut)[1], calc_csd(x[cut], S.fs)[1])
