@@ -334,6 +334,25 @@ def extras(device, dist, world, hbm_peak):
         out[f'f3_ofnxm_2x2_{prec}'] = {'events_per_s_per_gpu': B / (m * 1e-3), 'achieved_gbs': gbs, 'roofline_frac': gbs / hbm_peak,
                                        'algorithmic_bytes_per_event': 2 * NB_SAMPLES * 8, 'kernel': 'dp_nxm_kernel<%s,4,2>' % ('double' if prec == 'f64' else 'f2')}
         del nx, no
+    # ---- noise CSD of the same 2-channel shape (Noise.calc_csd)
+    from detprocess_b200.core.noise import NoiseCSD
+    for prec in ('f64', 'f32'):
+        est = NoiseCSD(NB_SAMPLES, FS, 2, precision=prec, device=device, typical_rms=1e-8)
+        for _ in range(2):
+            est.update(xn)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(3):
+            est.update(xn)
+            ms.append(est.plan.last_kernel_ms())
+        m = float(np.median(ms))
+        t0 = time.perf_counter()
+        est.finalize()                   # reduce over CTAs + all-reduce over ranks + unfold to [2, 2, N]
+        fin_ms = (time.perf_counter() - t0) * 1e3
+        gbs = B * 2 * NB_SAMPLES * 8 / (m * 1e-3) / 1e9
+        out[f'csd_2ch_{prec}'] = {'events_per_s_per_gpu': B / (m * 1e-3), 'achieved_gbs': gbs, 'roofline_frac': gbs / hbm_peak,
+                                  'finalize_ms_incl_allreduce': fin_ms, 'nb_samples': NB_SAMPLES}
+        del est
     del xn, base
     return out
 

@@ -158,3 +158,30 @@ chanA|chanB:
     assert np.allclose(df['chi2_of2x2_test_constrained_pair'], o['chi2'], rtol=1e-9)
     assert 'amp_of1x1_nodelay_chanA' in df and 'baseline_chanA' in df
     assert np.allclose(df['baseline_chanA'], x[:, 0, :pre - 1250].mean(axis=1), rtol=1e-12)
+
+
+def test_estimated_csd_feeds_the_nxm_filter():
+    """Noise randoms -> NoiseCSD (device) -> NxM filter built from the estimate -> amplitudes of injected pulses come
+    back within their resolution; the oracle run on the same estimated csd agrees to 1e-9."""
+    import torch
+    from detprocess_b200.core.noise import NoiseCSD
+    S = SynthNxM(16384, 2, 2)
+    pre = S.nb_pretrigger
+    noise = S.traces(400, np.random.default_rng(50), pulse_fraction=0.0)
+    est = NoiseCSD(S.nb_samples, S.fs, 2)
+    est.update(torch.from_numpy(noise).cuda())
+    _, csd = est.finalize()
+    x, amps, delays = S.traces(64, np.random.default_rng(51), pulse_fraction=1.0, return_truth=True)
+    from detprocess_b200.core.plans import NxMPlan
+    plan = NxMPlan(S.nb_samples, S.fs, 2, 2, 'f64')
+    plan.set_filter(S.templates, csd, pre, 'AC')
+    plan.set_window(pre - 400, pre + 400)
+    plan.finalize()
+    out = plan.run(torch.from_numpy(x).cuda()).cpu().numpy()
+    o = ofnxm_batch(x, ofnxm_setup(S.templates, csd, S.fs, pre), (pre - 400, pre + 400, False))
+    assert np.array_equal(out[:, 2].astype(np.int64), o['ind'])
+    assert np.max(np.abs(out[:, 3:5] - o['amps'])) < 1e-9 * np.max(np.abs(o['amps']))
+    P, Pinv = plan.p_matrix()
+    sigma = np.sqrt(np.diag(Pinv))
+    assert np.all(np.abs(out[:, 3:5] - amps) < 6 * sigma)
+    assert np.mean(np.abs(out[:, 2] - pre - delays) <= 2) > 0.9
