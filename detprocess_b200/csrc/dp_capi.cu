@@ -1170,6 +1170,12 @@ struct dp_trigger_plan {
     double* cand_amp = nullptr;
     int* cand_count = nullptr;
     long long* chunk_offset = nullptr;
+    // parallel grouping workspace
+    int* tile_heads = nullptr;
+    unsigned long long *best_key = nullptr, *best_g = nullptr;
+    int best_cap = 0;
+    int n_sm = 0;
+    bool group_serial = false;  // DP_TRIG_GROUP=serial: the single-CTA grouping kernel (development cross-check)
     int grid_max = 0;
     size_t smem = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -1289,6 +1295,12 @@ int dp_trigger_plan_create(dp_trigger_plan** plan, const double* phi_td, int nb_
     alloc(reinterpret_cast<void**>(&p->cand_amp), sizeof(double) * (size_t)p->max_chunks * (size_t)p->hop);
     alloc(reinterpret_cast<void**>(&p->cand_count), sizeof(int) * (size_t)p->max_chunks);
     alloc(reinterpret_cast<void**>(&p->chunk_offset), sizeof(long long) * (size_t)(p->max_chunks + 1));
+    alloc(reinterpret_cast<void**>(&p->tile_heads), sizeof(int) * ((size_t)p->max_chunks * (size_t)p->hop / 1024 + 2));
+    {
+        const char* e = std::getenv("DP_TRIG_GROUP");
+        p->group_serial = e && std::string(e) == "serial";
+        cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, p->device);
+    }
     if (rc) {
         for (void* dptr : p->owned) cudaFree(dptr);
         return rc;
@@ -1405,7 +1417,21 @@ int dp_trigger_run_raw(dp_trigger_plan* p, const void* trace_dev, int in_dtype, 
     gp.max_triggers = max_triggers;
     gp.n_triggers = n_triggers_dev;
     gp.chunk_offset = p->chunk_offset;
-    rc = dp_trig_group_launch(&gp, st);
+    gp.tile_heads = p->tile_heads;
+    if (!p->group_serial && p->best_cap < max_triggers) {
+        void* a = nullptr;
+        void* b = nullptr;
+        DP_CUDA(cudaMalloc(&a, sizeof(unsigned long long) * (size_t)max_triggers));
+        DP_CUDA(cudaMalloc(&b, sizeof(unsigned long long) * (size_t)max_triggers));
+        p->owned.push_back(a);
+        p->owned.push_back(b);
+        p->best_key = reinterpret_cast<unsigned long long*>(a);
+        p->best_g = reinterpret_cast<unsigned long long*>(b);
+        p->best_cap = max_triggers;
+    }
+    gp.best_key = p->best_key;
+    gp.best_g = p->best_g;
+    rc = p->group_serial ? dp_trig_group_launch(&gp, st) : dp_trig_group_par_launch(&gp, std::max(1, 2 * p->n_sm), st);
     if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger group launch: ") + cudaGetErrorString((cudaError_t)rc));
     DP_CUDA(cudaEventRecord(p->ev2, st));
     p->timed = true;

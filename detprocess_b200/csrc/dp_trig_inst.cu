@@ -83,4 +83,20 @@ int dp_trig_group_launch(const void* prm_v, void* st_v) {
     dp_trig_group_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(st_v)>>>(prm);
     return (int)cudaGetLastError();
 }
+// the same grouping from multi-CTA kernels (grid: CTAs for the per-candidate kernels)
+int dp_trig_group_par_launch(const void* prm_v, int grid, void* st_v) {
+    const DpTrigGroupParams& prm = *reinterpret_cast<const DpTrigGroupParams*>(prm_v);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
+    cudaError_t e = cudaMemsetAsync(prm.best_key, 0, sizeof(unsigned long long) * (size_t)prm.max_triggers, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(prm.best_g, 0xff, sizeof(unsigned long long) * (size_t)prm.max_triggers, st);
+    if (e != cudaSuccess) return (int)e;
+    dp_trig_par_offsets_kernel<<<1, 1024, 0, st>>>(prm);
+    dp_trig_par_heads_kernel<<<grid, 1024, 0, st>>>(prm);
+    dp_trig_par_scan_kernel<<<1, 1024, 0, st>>>(prm);
+    dp_trig_par_best_kernel<0><<<grid, 1024, 0, st>>>(prm);
+    dp_trig_par_best_kernel<1><<<grid, 1024, 0, st>>>(prm);
+    dp_trig_par_emit_kernel<<<64, 256, 0, st>>>(prm);
+    return (int)cudaGetLastError();
+}
 #endif

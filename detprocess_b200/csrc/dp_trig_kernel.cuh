@@ -277,6 +277,10 @@ struct DpTrigGroupParams {
     int max_triggers;
     int* n_triggers;          // [1] total number of groups found (may exceed max_triggers)
     long long* chunk_offset;  // [n_chunks + 1] scratch: exclusive prefix of cand_count
+    // parallel grouping (dp_trig_par_* kernels) workspace
+    int* tile_heads;               // [max_tiles + 1] group heads per tile of 1024 candidates -> exclusive prefix
+    unsigned long long* best_key;  // [max_triggers] ordered bits of the largest |amp| of the group
+    unsigned long long* best_g;    // [max_triggers] smallest candidate number attaining it
 };
 
 #ifndef DP_HOST_EMU
@@ -390,12 +394,37 @@ __global__ void __launch_bounds__(1024, 1) dp_trig_group_kernel(const DpTrigGrou
         }
         __syncthreads();
         const unsigned long long key = have ? (unsigned long long)__double_as_longlong(fabs(amp)) : 0ull;
-        if (have) atomicMax(&s_best[gid], key);
+        // The candidates are ordered, so the lanes of a warp that belong to one group are contiguous: reduce them with a
+        // segmented shuffle scan and let only the last lane of each segment touch shared memory (a pulse puts ~1000
+        // candidates into ONE group -- 1024 same-address 64-bit atomics per tile otherwise).
+        const int lane = tid & 31;
+        const int seg = have ? gid : -1;
+        const int seg_next = __shfl_down_sync(0xffffffffu, seg, 1);
+        const bool seg_tail = have && (lane == 31 || seg_next != seg);
+        {
+            unsigned long long k = key;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long kk = __shfl_up_sync(0xffffffffu, k, off);
+                const int ss = __shfl_up_sync(0xffffffffu, seg, off);
+                if (lane >= off && ss == seg && kk > k) k = kk;
+            }
+            if (seg_tail) atomicMax(&s_best[gid], k);
+        }
         __syncthreads();
         // a member beat the carried maximum: the carried index no longer counts
         if (tid == 0 && s_open && s_best[0] != s_carry_best) s_bidx[0] = 0x7fffffffffffffffll;
         __syncthreads();
-        if (have && key == s_best[gid]) atomicMin(reinterpret_cast<unsigned long long*>(&s_bidx[gid]), (unsigned long long)idx);
+        {
+            unsigned long long m = (have && key == s_best[gid]) ? (unsigned long long)idx : 0xffffffffffffffffull;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long mm = __shfl_up_sync(0xffffffffu, m, off);
+                const int ss = __shfl_up_sync(0xffffffffu, seg, off);
+                if (lane >= off && ss == seg && mm < m) m = mm;
+            }
+            if (seg_tail && m != 0xffffffffffffffffull) atomicMin(reinterpret_cast<unsigned long long*>(&s_bidx[gid]), m);
+        }
         __syncthreads();
         if (have && key == s_best[gid] && idx == s_bidx[gid]) s_bamp[gid] = amp;
         __syncthreads();
@@ -440,6 +469,161 @@ __global__ void __launch_bounds__(1024, 1) dp_trig_group_kernel(const DpTrigGrou
         *prm.n_triggers = s_nout;
     }
 }
+
+// ---- parallel grouping: the same result as dp_trig_group_kernel from five small multi-CTA kernels.
+// A group is a maximal run of candidates whose neighbours are at most pileup_window apart; its id is the number of
+// group heads before it.  (1) offsets: prefix of the chunk counts; (2) heads: head flags counted per tile of 1024
+// candidates; (3) scan: prefix of the tile counts = first group id of every tile, total = number of triggers;
+// (4) max: 64-bit atomicMax of the ordered |amp| bits per group (after a segmented warp reduction: a pulse puts ~1000
+// candidates into one group); (5) arg: atomicMin of the candidate number among those that attain it (first arg-max);
+// (6) emit.
+struct DpTrigTile {
+    bool have;
+    long long g;     // candidate number
+    long long idx;   // stream index
+    double amp;
+    bool head;
+};
+__device__ __forceinline__ void dp_trig_locate(const DpTrigGroupParams& prm, const long long* coff, long long g, long long& idx, double& amp) {
+    int lo = 0, hi = prm.n_chunks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (coff[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const long long pos = (long long)lo * prm.hop + (g - coff[lo]);
+    idx = (long long)lo * prm.hop + prm.cand_idx[pos];
+    amp = prm.cand_amp[pos];
+}
+// candidate tid of tile t, and whether it starts a group (needs its predecessor's index)
+__device__ __forceinline__ DpTrigTile dp_trig_tile_load(const DpTrigGroupParams& prm, const long long* coff, long long K, long long t,
+                                                        long long* s_idx /* [1025] */) {
+    const int tid = threadIdx.x;
+    DpTrigTile c;
+    c.g = t * 1024 + tid;
+    c.have = c.g < K;
+    c.idx = 0;
+    c.amp = 0.0;
+    if (c.have) dp_trig_locate(prm, coff, c.g, c.idx, c.amp);
+    __syncthreads();  // previous users of s_idx are done
+    s_idx[tid + 1] = c.idx;
+    if (tid == 0) {
+        long long pi = 0;
+        double pa;
+        if (c.g > 0 && c.have) dp_trig_locate(prm, coff, c.g - 1, pi, pa);
+        s_idx[0] = pi;
+    }
+    __syncthreads();
+    c.head = c.have && (c.g == 0 || c.idx - s_idx[tid] > prm.pileup_window);
+    return c;
+}
+// chunk offsets -> shared memory when they fit (binary search per candidate), else read from global memory
+#define DP_TRIG_OFFSETS()                                                                          \
+    __shared__ long long s_coff[1024 + 1];                                                         \
+    const bool cached = prm.n_chunks <= 1024;                                                      \
+    if (cached)                                                                                    \
+        for (int c = threadIdx.x; c <= prm.n_chunks; c += blockDim.x) s_coff[c] = prm.chunk_offset[c]; \
+    __syncthreads();                                                                               \
+    const long long* coff = cached ? s_coff : prm.chunk_offset;                                    \
+    const long long K = prm.chunk_offset[prm.n_chunks];                                            \
+    const long long n_tiles = (K + 1023) / 1024;
+
+__global__ void __launch_bounds__(1024, 1) dp_trig_par_offsets_kernel(const DpTrigGroupParams prm) {
+    __shared__ int s_warp[33];
+    __shared__ long long s_total;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < prm.n_chunks; c0 += 1024) {
+        const int c = c0 + tid;
+        const int v = c < prm.n_chunks ? prm.cand_count[c] : 0;
+        int tot;
+        const int inc = dp_trig_scan1024(v, s_warp, tot);
+        if (c < prm.n_chunks) prm.chunk_offset[c] = s_total + inc - v;
+        __syncthreads();
+        if (tid == 0) s_total += tot;
+        __syncthreads();
+    }
+    if (tid == 0) prm.chunk_offset[prm.n_chunks] = s_total;
+}
+__global__ void __launch_bounds__(1024, 1) dp_trig_par_heads_kernel(const DpTrigGroupParams prm) {
+    DP_TRIG_OFFSETS()
+    __shared__ long long s_idx[1025];
+    __shared__ int s_warp[33];
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const DpTrigTile c = dp_trig_tile_load(prm, coff, K, t, s_idx);
+        int tot;
+        (void)dp_trig_scan1024(c.head ? 1 : 0, s_warp, tot);
+        if (threadIdx.x == 0) prm.tile_heads[t] = tot;
+    }
+}
+__global__ void __launch_bounds__(1024, 1) dp_trig_par_scan_kernel(const DpTrigGroupParams prm) {
+    __shared__ int s_warp[33];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const long long K = prm.chunk_offset[prm.n_chunks];
+    const long long n_tiles = (K + 1023) / 1024;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (long long t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const long long t = t0 + tid;
+        const int v = t < n_tiles ? prm.tile_heads[t] : 0;
+        int tot;
+        const int inc = dp_trig_scan1024(v, s_warp, tot);
+        if (t < n_tiles) prm.tile_heads[t] = s_total + inc - v;  // groups that start before tile t
+        __syncthreads();
+        if (tid == 0) s_total += tot;
+        __syncthreads();
+    }
+    if (tid == 0) *prm.n_triggers = s_total;
+}
+template <int PHASE> __global__ void __launch_bounds__(1024, 1) dp_trig_par_best_kernel(const DpTrigGroupParams prm) {
+    DP_TRIG_OFFSETS()
+    __shared__ long long s_idx[1025];
+    __shared__ int s_warp[33];
+    const int lane = threadIdx.x & 31;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const DpTrigTile c = dp_trig_tile_load(prm, coff, K, t, s_idx);
+        int tot;
+        const int inc = dp_trig_scan1024(c.head ? 1 : 0, s_warp, tot);
+        const long long gid = (long long)prm.tile_heads[t] + inc - 1;  // inc == 0: continues the previous tile's last group
+        const bool use = c.have && gid < prm.max_triggers;
+        const int seg = use ? (int)gid : -1;
+        const int seg_next = __shfl_down_sync(0xffffffffu, seg, 1);
+        const bool seg_tail = use && (lane == 31 || seg_next != seg);
+        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(c.amp));
+        if (PHASE == 0) {
+            unsigned long long k = use ? key : 0ull;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long kk = __shfl_up_sync(0xffffffffu, k, off);
+                const int ss = __shfl_up_sync(0xffffffffu, seg, off);
+                if (lane >= off && ss == seg && kk > k) k = kk;
+            }
+            if (seg_tail) atomicMax(&prm.best_key[gid], k);
+        } else {
+            unsigned long long m = (use && key == prm.best_key[gid]) ? (unsigned long long)c.g : 0xffffffffffffffffull;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long mm = __shfl_up_sync(0xffffffffu, m, off);
+                const int ss = __shfl_up_sync(0xffffffffu, seg, off);
+                if (lane >= off && ss == seg && mm < m) m = mm;
+            }
+            if (seg_tail && m != 0xffffffffffffffffull) atomicMin(&prm.best_g[gid], m);
+        }
+    }
+}
+__global__ void dp_trig_par_emit_kernel(const DpTrigGroupParams prm) {
+    const int n = *prm.n_triggers < prm.max_triggers ? *prm.n_triggers : prm.max_triggers;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+        long long idx;
+        double amp;
+        dp_trig_locate(prm, prm.chunk_offset, (long long)prm.best_g[o], idx, amp);
+        prm.trig_index[o] = idx + prm.index_shift;
+        prm.trig_amp[o] = amp;
+        prm.trig_dchi2[o] = amp * amp * prm.w;
+    }
+}
+#undef DP_TRIG_OFFSETS
 #endif  // DP_TRIG_DEFINE_GROUP_KERNEL
 
 template <class T, int R1, int IN>

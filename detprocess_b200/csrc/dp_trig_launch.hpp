@@ -6,3 +6,4 @@ int dp_trig_setup_p1(int R1, int device, size_t* smem, int* grid_max, long long*
 int dp_trig_launch_p0(int R1, int in_dtype, const void* prm, int grid, size_t smem, void* stream);
 int dp_trig_launch_p1(int R1, int in_dtype, const void* prm, int grid, size_t smem, void* stream);
 int dp_trig_group_launch(const void* prm, void* stream);
+int dp_trig_group_par_launch(const void* prm, int grid, void* stream);

@@ -211,3 +211,31 @@ trigger:
         assert np.all(d['event_time'] == np.int64(np.around(admin[e]['event_time'] + d['trigger_time'])))
     assert (df['processing_id'] == 'unit').all() and (df['series_number'] == 5).all()
     assert len(tp.process(ntriggers=7)) == 7
+
+
+@pytest.mark.parametrize('window', [0, 7, 1250, 400000])
+def test_parallel_grouping_equals_the_single_cta_walk(window, monkeypatch):
+    """The multi-CTA grouping (heads -> prefix -> atomic max / first arg-max -> emit) gives exactly the triggers of the
+    serial single-CTA walk and of the oracle: many pile-ups, groups that span tiles of 1024 candidates, window 0 (every
+    candidate its own trigger, output truncated at max_triggers)."""
+    import torch
+    from detprocess_b200.core.oftrigger import OptimumFilterTrigger
+    S = SynthSetup(16384)
+    fs = S.fs
+    L = 3_000_000
+    x = make_continuous(L, S.template, S.psd, fs, np.random.default_rng(77), pulse_rate_hz=120.0, amp_range=(2e-8, 2e-7))
+    xd = torch.from_numpy(x).cuda()
+    res = {}
+    for mode in ('parallel', 'serial'):
+        monkeypatch.setenv('DP_TRIG_GROUP', mode)
+        trig = OptimumFilterTrigger('ch', fs, S.template, S.psd, S.nb_pretrigger, max_samples=L)
+        trig.update_trace(xd)
+        d = trig.find_triggers_once(5.0, pileup_window_samples=window, max_triggers=5000)['ch']
+        res[mode] = (np.asarray(d['trigger_index']), np.asarray(d['trigger_amplitude']))
+    assert len(res['parallel'][0]) > (100 if window else 4999)
+    assert np.array_equal(res['parallel'][0], res['serial'][0])
+    assert np.array_equal(res['parallel'][1], res['serial'][1])
+    if window:
+        filt, dchi2 = T.filter_trace(x, trig._phi_td, trig._iw_matrix, trig._w_matrix)
+        ot = T.find_triggers_once(dchi2, filt, T.chi2_threshold(5.0), window, trig._trigger_index_shift, fs)
+        assert np.array_equal(res['parallel'][0], ot['trigger_index'])
