@@ -60,8 +60,8 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
     static constexpr int NW = NT / 32;
     static constexpr int SX = 34;  // X of the 17 self pairs, per channel
     static constexpr long long GSTRIDE = (long long)NPH * 16 * NT;  // one thread-order table
-    static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (32 + SX * DP_NXM_MAX_CHAN) + sizeof(double) * 32 +
-                                         sizeof(DpBest<S>) * 32 + 64;
+    static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (32 + SX * DP_NXM_MAX_CHAN) + 2 * sizeof(double) * 32 +
+                                         2 * sizeof(DpBest<S>) * 32 + 64;
     // scratch per CTA (V units)
     static constexpr long long SCR_X = (long long)16 * NT;              // per channel: X of the current phase
     static constexpr long long SCR_PARK = (long long)(NPH - 1) * NB * VPB;  // per template: parked block results
@@ -101,7 +101,8 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
         cx<S>* const sp = reinterpret_cast<cx<S>*>(buf + G::SMEM_V);  // [32] self-paired group values
         cx<S>* const sx = sp + 32;                                    // [n_chan][17][2]
         double* const red = reinterpret_cast<double*>(sx + SX * DP_NXM_MAX_CHAN);
-        DpBest<S>* const best = reinterpret_cast<DpBest<S>*>(red + 32);
+        DpBest<S>* const best = reinterpret_cast<DpBest<S>*>(red + 64);  // red / best: [2][32], double buffered
+        int par = 0;
         const int tid = threadIdx.x;
         constexpr int nch = NCH;  // compile-time channel count: the per-entry loops unroll without branches
         const int ntm = prm.n_templ;
@@ -363,45 +364,67 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                         continue;
                     }
                     // ------------ winner, chi0, outputs ---------------------------------------------------
+                    // red / best are double buffered and warp 0 finishes the event alone, so the other warps start the
+                    // next event's forward passes right away (they do not touch scr_q before its last phase)
+                    DpBest<S>* const bestp = best + par * 32;
+                    double* const redp = red + par * 32;
+                    par ^= 1;
                     {
                         const DpBest<S> b = dp_warp_best(tb);
                         const double c = dp_warp_sum((double)chi);
                         if ((tid & 31) == 0) {
-                            best[tid >> 5] = b;
-                            red[tid >> 5] = c;
+                            bestp[tid >> 5] = b;
+                            redp[tid >> 5] = c;
                         }
                     }
                     __syncthreads();  // also orders the parked q~ values (global memory) within the CTA
-                    if (tid == 0) {
-                        double chi0 = 0.0;
-                        for (int w = 0; w < NW; ++w) chi0 += red[w];
-                        DpBest<S> b = best[0];
-                        for (int w = 1; w < NW; ++w) dp_best_merge(b, best[w]);
-                        double* o = prm.out + (long long)ev * prm.n_out;
-                        o[0] = chi0;
-                        for (int f = 0; f < 2; ++f) {
-                            const int idx = f == 0 ? b.idx : prm.pretrigger;
-                            double* of = o + 1 + f * (2 + ntm);
-                            if (idx < 0) {  // empty window
-                                for (int i = 0; i < (f == 0 ? 2 : 1) + ntm; ++i) of[i] = -999999.0;
-                                continue;
-                            }
-                            double q[DP_NXM_MAX_TEMPL];
-                            for (int i = 0; i < ntm; ++i) q[i] = (double)sample_at(scr_q + SCR_Q * i, idx);
-                            double d = 0.0;
-                            for (int i = 0; i < ntm; ++i)
-                                for (int k = 0; k < ntm; ++k) d += prm.cmat[i][k] * q[i] * q[k];
-                            int oi = 0;
-                            of[oi++] = chi0 - d;
-                            if (f == 0) of[oi++] = (double)idx;
-                            for (int i = 0; i < ntm; ++i) {
-                                double am = 0.0;
-                                for (int k = 0; k < ntm; ++k) am += prm.amat[i][k] * q[k];
-                                of[oi++] = am;
+                    if (tid < 32) {
+                        const double chi0 = dp_warp_sum(tid < NW ? redp[tid] : 0.0);
+                        DpBest<S> b = tid < NW ? bestp[tid] : DpBest<S>{(S)0, -1};
+                        b = dp_warp_best(b);
+                        // lane f * ntm + i reads q~_i at the delay of fit f (0: windowed arg-max, 1: no delay)
+                        const int f_l = tid / ntm, i_l = tid % ntm;
+                        const int idx_l = f_l == 0 ? b.idx : prm.pretrigger;
+                        double ql = 0.0;
+                        if (tid < 2 * ntm && idx_l >= 0) ql = (double)sample_at(scr_q + SCR_Q * i_l, idx_l);
+                        double q[2][DP_NXM_MAX_TEMPL];
+#pragma unroll
+                        for (int f = 0; f < 2; ++f)
+#pragma unroll
+                            for (int i = 0; i < DP_NXM_MAX_TEMPL; ++i) q[f][i] = __shfl_sync(0xffffffffu, ql, (f * ntm + i) & 31);
+                        if (tid == 0) {
+                            double* o = prm.out + (long long)ev * prm.n_out;
+                            o[0] = chi0;
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) {
+                                const int idx = f == 0 ? b.idx : prm.pretrigger;
+                                double* of = o + 1 + f * (2 + ntm);
+                                if (idx < 0) {  // empty window
+                                    for (int i = 0; i < (f == 0 ? 2 : 1) + ntm; ++i) of[i] = -999999.0;
+                                    continue;
+                                }
+                                double d = 0.0;
+#pragma unroll
+                                for (int i = 0; i < DP_NXM_MAX_TEMPL; ++i)
+#pragma unroll
+                                    for (int k = 0; k < DP_NXM_MAX_TEMPL; ++k)
+                                        if (i < ntm && k < ntm) d += prm.cmat[i][k] * q[f][i] * q[f][k];
+                                int oi = 0;
+                                of[oi++] = chi0 - d;
+                                if (f == 0) of[oi++] = (double)idx;
+#pragma unroll
+                                for (int i = 0; i < DP_NXM_MAX_TEMPL; ++i) {
+                                    if (i < ntm) {
+                                        double am = 0.0;
+#pragma unroll
+                                        for (int k = 0; k < DP_NXM_MAX_TEMPL; ++k)
+                                            if (k < ntm) am += prm.amat[i][k] * q[f][k];
+                                        of[oi++] = am;
+                                    }
+                                }
                             }
                         }
                     }
-                    __syncthreads();  // red / best / scratch are reused by the next event
                 }
             }
         }
