@@ -22,15 +22,20 @@ struct Setup {
     std::vector<double> P, Pinv;         // [m*m]
 };
 
-// in-place inverse of a small complex / real matrix (Gauss-Jordan with partial pivoting); false if singular
+// in-place inverse of a small complex / real matrix (Gauss-Jordan with partial pivoting); false if (numerically) singular
 template <class Z> inline bool invert(std::vector<Z>& a, int n) {
     std::vector<Z> inv((size_t)n * n, Z(0));
     for (int i = 0; i < n; ++i) inv[(size_t)i * n + i] = Z(1);
+    // a pivot below 1e-12 of the largest entry of its (original) column counts as singular: rank-deficient csd,
+    // degenerate templates
+    std::vector<double> colmax(n, 0.0);
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) colmax[c] = std::max(colmax[c], (double)std::abs(a[(size_t)r * n + c]));
     for (int c = 0; c < n; ++c) {
         int piv = c;
         for (int r = c + 1; r < n; ++r)
             if (std::abs(a[(size_t)r * n + c]) > std::abs(a[(size_t)piv * n + c])) piv = r;
-        if (!(std::abs(a[(size_t)piv * n + c]) > 0)) return false;
+        if (!(std::abs(a[(size_t)piv * n + c]) > 1e-12 * colmax[c])) return false;
         if (piv != c)
             for (int k = 0; k < n; ++k) {
                 std::swap(a[(size_t)piv * n + k], a[(size_t)c * n + k]);

@@ -53,3 +53,42 @@ def test_plan_argument_errors_without_gpu():
     with pytest.raises(ValueError):
         r.add(0, 'maximum', 5, 5)                 # numpy: zero-size array to reduction operation
     r.add(0, 'baseline', 5, 5)                    # numpy: nan + warning, allowed
+
+
+def test_nxm_plan_argument_errors_and_p_matrix_without_gpu():
+    """NxM plan: host-side validation and the template matrix P (no device needed before finalize): P equals the
+    oracle's, a singular csd and degenerate templates are refused."""
+    import numpy as np
+    from detprocess_b200 import _lib
+    from detprocess_b200.core.plans import NxMPlan
+    from detprocess_b200.synth import SynthNxM
+    from oracle.ofnxm import ofnxm_setup
+    S = SynthNxM(16384, 2, 2)
+    with pytest.raises(NotImplementedError):
+        NxMPlan(4096, S.fs, 2, 2)                              # unsupported trace length
+    with pytest.raises(ValueError):
+        NxMPlan(16384, S.fs, 5, 1)                             # more channels than the kernel is built for
+    p = NxMPlan(16384, S.fs, 2, 2)
+    with pytest.raises(ValueError):
+        p.set_filter(S.templates[:, :1], S.csd)                # wrong template shape
+    with pytest.raises(_lib.DetprocessB200Error):
+        p.p_matrix()                                           # no filter yet
+    p.set_filter(S.templates, S.csd, S.nb_pretrigger, 'AC')
+    P, Pinv = p.p_matrix()
+    st = ofnxm_setup(S.templates, S.csd, S.fs, S.nb_pretrigger)
+    assert np.allclose(P, st['P'], rtol=1e-10) and np.allclose(Pinv, st['Pinv'], rtol=1e-8)
+    with pytest.raises(ValueError):
+        p.set_window(100, 50)                                  # lo > hi
+    with pytest.raises(ValueError):
+        p.set_window(0, 16385)
+    bad = S.csd.copy()
+    bad[1] = bad[0]                                            # rank-deficient at every bin
+    bad[:, 1] = bad[:, 0]
+    with pytest.raises(ValueError):
+        NxMPlan(16384, S.fs, 2, 2).set_filter(S.templates, bad)
+    same = S.templates.copy()
+    same[:, 1] = same[:, 0]                                    # two identical templates: P is singular
+    with pytest.raises(ValueError):
+        NxMPlan(16384, S.fs, 2, 2).set_filter(same, S.csd)
+    with pytest.raises(_lib.DetprocessB200Error):
+        p.finalize()                                           # no CUDA device here: no CPU fallback
