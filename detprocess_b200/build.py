@@ -49,6 +49,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
+def _unit_deps(src, seen=None):
+    """the source and every local header it includes (transitively)"""
+    import re
+    seen = set() if seen is None else seen
+    path = os.path.normpath(src)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as f:
+        for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', f.read(), flags=re.M):
+            _unit_deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
 def build(force=False, verbose=True):
     if not force and not needs_build():
         return LIB
@@ -64,6 +78,10 @@ def build(force=False, verbose=True):
         name, src, defs = unit
         obj = os.path.join(obj_dir, name + '.o')
         cmd = [nvcc] + NVCC_FLAGS + EXTRA_DEFS + defs + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        # an object newer than its source, every header it includes and this script is reused
+        deps = list(_unit_deps(os.path.join(CSRC, src))) + [os.path.abspath(__file__)]
+        if not force and os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in deps):
+            return name, obj, ' '.join(cmd) + '   # up to date', 0, ''
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return name, obj, ' '.join(cmd), res.returncode, res.stdout
 
