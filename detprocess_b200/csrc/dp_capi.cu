@@ -658,10 +658,16 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
     DP_CUDA(cudaSetDevice(p->device));
     const size_t esz = in_dtype == DP_IN_F64 ? 8 : (in_dtype == DP_IN_F32 ? 4 : 2);
     const size_t ev_bytes = (size_t)p->n_chan * (size_t)row_stride * esz;
-    // chunk: <= 256 MiB of traces per stage and at least four stages per call (the copy of one overlaps the kernel of
-    // the previous one), but no fewer than 512 events (a few per CTA)
+    // chunk: <= 256 MiB of traces per stage and about eight stages per call (the copy of one overlaps the kernel of
+    // the previous one; the first copy and the last kernel are exposed), a multiple of the persistent grid with at
+    // least four events per CTA
     long long chunk = std::max<long long>(1, (256LL << 20) / (long long)ev_bytes);
-    chunk = std::min(chunk, std::max<long long>(512, (n_events + 3) / 4));
+    {
+        const long long g = std::max(1, p->grid_max);
+        long long want = std::max<long long>(4 * g, (n_events + 7) / 8);
+        want = (want + g - 1) / g * g;
+        chunk = std::min(chunk, want);
+    }
     chunk = std::min(chunk, n_events);
     if (p->stage_events < chunk || p->stage_dtype != in_dtype || p->stage_stride != row_stride) {
         for (int i = 0; i < 2; ++i) {
