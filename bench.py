@@ -239,7 +239,7 @@ def extras(device, dist, world, hbm_peak):
     import torch
     from detprocess_b200.core.noise import NoisePSD
     from detprocess_b200.core.oftrigger import OptimumFilterTrigger
-    from detprocess_b200.synth import make_template, make_psd
+    from detprocess_b200.synth import make_template, make_psd, SynthSetup
     out = {}
     # ---- C1 window reductions (baseline_pre + integral, README.md:87-96 windows), bit-exact numpy arithmetic
     from detprocess_b200.core.plans import ReducePlan
@@ -309,6 +309,75 @@ def extras(device, dist, world, hbm_peak):
                                      'roofline_frac': L * 8 / (fms * 1e-3) / 1e9 / hbm_peak,
                                      'fft_size': trig._plan.fft_size, 'hop': trig._plan.hop}
         del trig
+    # ---- C1 OF part (nodelay + unconstrained, one template) and C3 (8 channels x 16384, the full YAML feature set:
+    # nodelay, constrained, unconstrained, constrained glitch + baseline, baseline_end, maximum, minimum, integral)
+    from detprocess_b200.core.plans import OFPlan
+    S1 = SynthSetup(NB_SAMPLES, FS)
+    B = 8192
+    x1 = make_device_traces(S1, B, device, 777)
+    for prec in ('f64', 'f32'):
+        pl = OFPlan(NB_SAMPLES, FS, 1, prec)
+        pl.set_psd(0, S1.psd, 'AC')
+        t0 = pl.add_template(0, S1.template, S1.nb_pretrigger)
+        pl.add_fit_nodelay(0, t0)
+        pl.add_fit(0, t0, None, None)
+        pl.finalize(device)
+        o1 = torch.empty((B, pl.n_out), dtype=torch.float64, device=device)
+        for _ in range(3):
+            pl.run(x1, o1)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(5):
+            pl.run(x1, o1)
+            ms.append(pl.last_kernel_ms())
+        m = float(np.median(ms))
+        gbs = B * BYTES_PER_EVENT / (m * 1e-3) / 1e9
+        out[f'c1_of_nodelay_unconstrained_{prec}'] = {'events_per_s_per_gpu': B / (m * 1e-3), 'achieved_gbs': gbs,
+                                                      'roofline_frac': gbs / hbm_peak, 'algorithmic_bytes_per_event': BYTES_PER_EVENT}
+        del pl, o1
+    del x1
+    n3, c3, B = 16384, 8, 2048
+    S3 = SynthSetup(n3, FS)
+    x3 = make_device_traces(S3, B * c3, device, 778).reshape(B, c3, n3)
+    pre3 = S3.nb_pretrigger
+    red3 = ReducePlan(n3, FS, c3)
+    for c in range(c3):
+        red3.add(c, 'baseline', 0, pre3 - 1250)
+        red3.add(c, 'baseline', n3 - 1250, n3)
+        red3.add(c, 'maximum', None, None)
+        red3.add(c, 'minimum', None, None)
+        red3.add(c, 'integral', pre3 - 625, pre3 + 625)
+    red3.finalize(device)
+    r3 = torch.empty((B, red3.n_out), dtype=torch.float64, device=device)
+    for prec in ('f64', 'f32'):
+        pl = OFPlan(n3, FS, c3, prec)
+        for c in range(c3):
+            pl.set_psd(c, S3.psd, 'AC')
+            t0 = pl.add_template(c, S3.template, pre3)
+            t1 = pl.add_template(c, S3.template_glitch, pre3)
+            pl.add_fit_nodelay(c, t0)
+            pl.add_fit(c, t0, pre3 - WINDOW, pre3 + WINDOW)
+            pl.add_fit(c, t0, None, None)
+            pl.add_fit(c, t1, pre3 - WINDOW, pre3 + WINDOW)
+        pl.finalize(device)
+        o3 = torch.empty((B, pl.n_out), dtype=torch.float64, device=device)
+        for _ in range(3):
+            pl.run(x3, o3)
+            red3.run(x3, r3)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(5):
+            pl.run(x3, o3)
+            red3.run(x3, r3)
+            ms.append((pl.last_kernel_ms(), red3.last_kernel_ms()))
+        mo, mr = (float(v) for v in np.median(np.array(ms), axis=0))
+        byt = c3 * n3 * 8
+        out[f'c3_8ch_16384_full_yaml_{prec}'] = {'events_per_s_per_gpu': B / ((mo + mr) * 1e-3), 'of_ms': mo, 'reduce_ms': mr,
+                                                'achieved_gbs': B * byt / ((mo + mr) * 1e-3) / 1e9,
+                                                'roofline_frac': B * byt / ((mo + mr) * 1e-3) / 1e9 / hbm_peak,
+                                                'algorithmic_bytes_per_event': byt, 'features_per_event': pl.n_out + red3.n_out}
+        del pl, o3
+    del x3, red3, r3
     # ---- (f)3 NxM optimal filter: 2 channels x 2 templates, 32768 samples, +-400 us window + no-delay fit
     from detprocess_b200.core.plans import NxMPlan
     from detprocess_b200.synth import SynthNxM
