@@ -780,7 +780,7 @@ int dp_reduce_plan_finalize(dp_reduce_plan* p, int device) {
     if ((rc = upload(p->owned, p->plan.nodes, &p->d_nodes))) return rc;
     if ((rc = upload(p->owned, p->plan.level_off, &p->d_level_off))) return rc;
     if ((rc = upload(p->owned, p->plan.feats, &p->d_feats))) return rc;
-    p->smem = sizeof(double) * (size_t)(p->plan.max_nodes + 64);
+    p->smem = sizeof(double) * (size_t)(p->plan.max_nodes + 96);
     int occ = 0, sms = 0;
     DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_reduce_kernel<256>, 256, p->smem));
     DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));

@@ -126,35 +126,52 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
             } else if (ft.op == DP_OP_TRAPZ) {
                 if (tid == 0) *o = nodeval[ft.root] / prm.fs;
             } else {
-                // max / min with numpy NaN propagation
-                const bool is_max = ft.op == DP_OP_MAX;
-                double m = is_max ? -INFINITY : INFINITY;
+                // max / min with numpy NaN propagation.  A maximum and a minimum over the same window (the usual YAML
+                // pair) share one pass over the samples: the later one of the pair is produced here.
+                bool done_earlier = false;
+                for (int g = ch.feat_begin; g < f; ++g) {
+                    const DpRedFeat fg = prm.feats[g];
+                    if ((fg.op == DP_OP_MAX || fg.op == DP_OP_MIN) && fg.op != ft.op && fg.lo == ft.lo && fg.hi == ft.hi) done_earlier = true;
+                }
+                if (done_earlier) continue;  // CTA-uniform
+                int partner = -1;
+                for (int g = f + 1; g < ch.feat_end && partner < 0; ++g) {
+                    const DpRedFeat fg = prm.feats[g];
+                    if ((fg.op == DP_OP_MAX || fg.op == DP_OP_MIN) && fg.op != ft.op && fg.lo == ft.lo && fg.hi == ft.hi) partner = g;
+                }
+                double mx = -INFINITY, mn = INFINITY;
                 int has_nan = 0;
 #pragma unroll 4
                 for (int i = ft.lo + tid; i < ft.hi; i += NT) {
                     const double v = __ldg(x + i);
                     if (v != v) has_nan = 1;
-                    m = is_max ? fmax(m, v) : fmin(m, v);
+                    mx = fmax(mx, v);
+                    mn = fmin(mn, v);
                 }
 #pragma unroll
                 for (int o2 = 16; o2 > 0; o2 >>= 1) {
-                    const double mo = __shfl_xor_sync(0xffffffffu, m, o2);
                     has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o2);
-                    m = is_max ? fmax(m, mo) : fmin(m, mo);
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o2));
                 }
                 if ((tid & 31) == 0) {
-                    red[tid >> 5] = m;
+                    red[tid >> 5] = mx;
                     red[32 + (tid >> 5)] = (double)has_nan;
+                    red[64 + (tid >> 5)] = mn;
                 }
                 __syncthreads();
                 if (tid == 0) {
-                    double mm = red[0];
+                    double amx = red[0], amn = red[64];
                     double nn = red[32];
                     for (int w = 1; w < NT / 32; ++w) {
-                        mm = is_max ? fmax(mm, red[w]) : fmin(mm, red[w]);
+                        amx = fmax(amx, red[w]);
+                        amn = fmin(amn, red[64 + w]);
                         nn += red[32 + w];
                     }
-                    *o = (nn > 0.0) ? NAN : mm;
+                    const bool is_max = ft.op == DP_OP_MAX;
+                    *o = (nn > 0.0) ? NAN : (is_max ? amx : amn);
+                    if (partner >= 0)
+                        prm.out[(long long)ev * prm.n_out + prm.feats[partner].out] = (nn > 0.0) ? NAN : (is_max ? amn : amx);
                 }
                 __syncthreads();
             }

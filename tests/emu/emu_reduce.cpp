@@ -70,7 +70,7 @@ int main(int argc, char** argv) {
     constexpr int NT = 128;
     const int grid = 2;
     for (int b = 0; b < grid; ++b) {
-        std::vector<double> nodeval(plan.max_nodes + 8), red(64);
+        std::vector<double> nodeval(plan.max_nodes + 8), red(96);
         run_cta(NT, b, grid, [&] { dp_reduce_rows<NT>(prm, nodeval.data(), red.data()); });
     }
     std::ofstream o(argv[2], std::ios::binary);
