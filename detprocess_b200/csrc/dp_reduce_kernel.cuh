@@ -127,18 +127,13 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
                 if (tid == 0) *o = nodeval[ft.root] / prm.fs;
             } else {
                 // max / min with numpy NaN propagation.  A maximum and a minimum over the same window (the usual YAML
-                // pair) share one pass over the samples: the later one of the pair is produced here.
+                // pair) share one pass over the samples: the first of them in feature order produces the others.
                 bool done_earlier = false;
                 for (int g = ch.feat_begin; g < f; ++g) {
                     const DpRedFeat fg = prm.feats[g];
-                    if ((fg.op == DP_OP_MAX || fg.op == DP_OP_MIN) && fg.op != ft.op && fg.lo == ft.lo && fg.hi == ft.hi) done_earlier = true;
+                    if ((fg.op == DP_OP_MAX || fg.op == DP_OP_MIN) && fg.lo == ft.lo && fg.hi == ft.hi) done_earlier = true;
                 }
                 if (done_earlier) continue;  // CTA-uniform
-                int partner = -1;
-                for (int g = f + 1; g < ch.feat_end && partner < 0; ++g) {
-                    const DpRedFeat fg = prm.feats[g];
-                    if ((fg.op == DP_OP_MAX || fg.op == DP_OP_MIN) && fg.op != ft.op && fg.lo == ft.lo && fg.hi == ft.hi) partner = g;
-                }
                 double mx = -INFINITY, mn = INFINITY;
                 int has_nan = 0;
 #pragma unroll 4
@@ -170,8 +165,11 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
                     }
                     const bool is_max = ft.op == DP_OP_MAX;
                     *o = (nn > 0.0) ? NAN : (is_max ? amx : amn);
-                    if (partner >= 0)
-                        prm.out[(long long)ev * prm.n_out + prm.feats[partner].out] = (nn > 0.0) ? NAN : (is_max ? amn : amx);
+                    for (int g = f + 1; g < ch.feat_end; ++g) {  // every other extremum over the same window
+                        const DpRedFeat fg = prm.feats[g];
+                        if ((fg.op == DP_OP_MAX || fg.op == DP_OP_MIN) && fg.lo == ft.lo && fg.hi == ft.hi)
+                            prm.out[(long long)ev * prm.n_out + fg.out] = (nn > 0.0) ? NAN : (fg.op == DP_OP_MAX ? amx : amn);
+                    }
                 }
                 __syncthreads();
             }

@@ -150,7 +150,7 @@ def test_reduce_kernel_emulated_bit_exact():
     tr[1, 500] = np.nan
     feats = [(0, 0, 3000), (1, 3500, 4750), (2, 0, n - 1), (3, 0, n - 1), (0, 100, 105), (1, 7, 8), (0, 3, 3 + 129),
              (1, 1, 1 + 1025), (0, 0, n), (2, 501, 600), (0, 17, 17 + 8), (1, 40, 40 + 10), (0, 9, 9),
-             (3, 501, 600), (3, 10, 20), (2, 490, 510), (3, 0, n - 1)]
+             (3, 501, 600), (3, 10, 20), (2, 490, 510), (3, 0, n - 1), (3, 490, 510), (2, 490, 510), (3, 490, 510)]
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         fin, fout = os.path.join(td, 'i.bin'), os.path.join(td, 'o.bin')
