@@ -939,26 +939,7 @@ template <class T, int R1> int psd2_tables(dp_psd_plan* p) {
     if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
     p->groups = dg;
     // natural bin k -> slot in one CTA's partial array
-    std::vector<int> loc(G::M + 1, -1);
-    const int nspecial = G::VL == 2 ? 1 : 2;
-    for (int ph = 0; ph < G::NPH; ++ph)
-        for (int t = 0; t < G::NT; ++t) {
-            if (ph == 0 && t < nspecial) continue;
-            for (int e = 0; e < 16; ++e) {
-                int b[2];
-                dpplan2::entry_bins<G>(ph, t, e, b);
-                for (int l = 0; l < G::VL; ++l) loc[b[l]] = ((ph * 16 + e) * G::NT + t) * G::VL + l;
-            }
-        }
-    for (int l = 0; l < 17; ++l) {
-        int b[2];
-        bool dup[2];
-        dpplan2::self_bins<G>(l, b, dup);
-        for (int j = 0; j < 2; ++j)
-            if (!dup[j]) loc[b[j]] = G::NPH * 16 * G::NT * G::VL + 2 * l + j;
-    }
-    for (int k = 0; k <= G::M; ++k)
-        if (loc[k] < 0) return fail(DP_ERR_STATE, "internal: PSD bin map incomplete");
+    const std::vector<int> loc = dpplan2::partial_slot_of_bin<G>();
     if ((rc = upload(p->owned, loc, &p->loc))) return rc;
     return DP_OK;
 }
@@ -1706,26 +1687,7 @@ template <class T, int R1> int csd_tables(dp_csd_plan* p) {
     if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
     p->groups = dg;
     // natural bin k -> slot of one component in a CTA's partial array (same map as the PSD plan)
-    std::vector<int> loc(G::M + 1, -1);
-    const int nspecial = G::VL == 2 ? 1 : 2;
-    for (int ph = 0; ph < G::NPH; ++ph)
-        for (int t = 0; t < G::NT; ++t) {
-            if (ph == 0 && t < nspecial) continue;
-            for (int e = 0; e < 16; ++e) {
-                int b[2];
-                dpplan2::entry_bins<G>(ph, t, e, b);
-                for (int l = 0; l < G::VL; ++l) loc[b[l]] = ((ph * 16 + e) * G::NT + t) * G::VL + l;
-            }
-        }
-    for (int l = 0; l < 17; ++l) {
-        int b[2];
-        bool dup[2];
-        dpplan2::self_bins<G>(l, b, dup);
-        for (int j = 0; j < 2; ++j)
-            if (!dup[j]) loc[b[j]] = G::NPH * 16 * G::NT * G::VL + 2 * l + j;
-    }
-    for (int k = 0; k <= G::M; ++k)
-        if (loc[k] < 0) return fail(DP_ERR_STATE, "internal: CSD bin map incomplete");
+    const std::vector<int> loc = dpplan2::partial_slot_of_bin<G>();
     if ((rc = upload(p->owned, loc, &p->loc))) return rc;
     return DP_OK;
 }

@@ -104,6 +104,32 @@ template <class G> inline void verify_geometry() {
         if (seen[k] != 1) throw std::logic_error("v2 geometry: bin " + std::to_string(k) + " covered " + std::to_string(seen[k]) + " times");
 }
 
+// natural one-sided bin k -> slot in a CTA's thread-order partial-sum array (PSD / CSD accumulation kernels):
+// regular entries [NPH][16][NT][VL], then the 17 self lanes [17][2]
+template <class G> inline std::vector<int> partial_slot_of_bin() {
+    std::vector<int> loc(G::M + 1, -1);
+    const int nspecial = G::VL == 2 ? 1 : 2;
+    for (int ph = 0; ph < G::NPH; ++ph)
+        for (int t = 0; t < G::NT; ++t) {
+            if (ph == 0 && t < nspecial) continue;
+            for (int e = 0; e < 16; ++e) {
+                int b[2];
+                entry_bins<G>(ph, t, e, b);
+                for (int l = 0; l < G::VL; ++l) loc[b[l]] = ((ph * 16 + e) * G::NT + t) * G::VL + l;
+            }
+        }
+    for (int l = 0; l < 17; ++l) {
+        int b[2];
+        bool dup[2];
+        self_bins<G>(l, b, dup);
+        for (int j = 0; j < 2; ++j)
+            if (!dup[j]) loc[b[j]] = G::NPH * 16 * G::NT * G::VL + 2 * l + j;
+    }
+    for (int k = 0; k <= G::M; ++k)
+        if (loc[k] < 0) throw std::logic_error("v2 geometry: partial-sum bin map incomplete");
+    return loc;
+}
+
 // a one-sided filter pe[0..M] (applied to 2*sc*fft(x), see dpplan::filter_onesided) in thread order
 template <class T, int R1>
 void pack_onesided(const std::vector<cplx>& pe, std::vector<cx<T>>& phi, std::vector<cx<typename Dp2Traits<T>::S>>& phi_self) {

@@ -83,3 +83,31 @@ def run_nxm(traces, templates, csd, fs, pretrigger, window=(None, None, False), 
         subprocess.check_call([exe, fin, fout, precision])
         out = np.fromfile(fout, dtype=np.float64).reshape(nev, 4 + 2 * m)
     return out
+
+
+def run_csd(traces, fs, mask=None, precision='f64', typical_rms=1e-8, asan=False):
+    """traces [B, n, N] -> (component sums [n*n, N/2+1] in the CSDPlan.sums layout, accepted-event count)"""
+    os.makedirs(os.path.join(HERE, '_build'), exist_ok=True)
+    exe = os.path.join(HERE, '_build', 'emu_csd' + ('_asan' if asan else ''))
+    src = os.path.join(HERE, 'emu_csd.cpp')
+    deps = [src] + [os.path.join(HERE, '../../detprocess_b200/csrc', f) for f in
+                    ('dp_of_kernel.cuh', 'dp_fft.cuh', 'dp_platform.cuh', 'dp_plan.hpp', 'dp_of2_kernel.cuh',
+                     'dp_plan2.hpp', 'dp_f2.cuh', 'dp_csd_kernel.cuh')]
+    if not (os.path.exists(exe) and all(os.path.getmtime(exe) > os.path.getmtime(d) for d in deps)):
+        cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-o', exe, src]
+        if asan:
+            cmd[3:3] = ['-fsanitize=address', '-fno-omit-frame-pointer', '-g']
+        subprocess.check_call(cmd)
+    traces = np.ascontiguousarray(traces, dtype=np.float64)
+    nev, n, N = traces.shape
+    mask = np.ones(nev, dtype=np.uint8) if mask is None else np.asarray(mask, dtype=np.uint8)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, 'in.bin'), os.path.join(td, 'out.bin')
+        with open(fin, 'wb') as f:
+            f.write(struct.pack('<4i', N, nev, n, int(precision == 'f32')))
+            f.write(struct.pack('<2d', fs, typical_rms))
+            f.write(mask.tobytes())
+            f.write(traces.tobytes())
+        subprocess.check_call([exe, fin, fout])
+        out = np.fromfile(fout, dtype=np.float64)
+    return out[:-1].reshape(n * n, N // 2 + 1), int(out[-1])

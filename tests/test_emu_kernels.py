@@ -139,6 +139,39 @@ def test_nxm_kernel_emulated(precision, nb_samples, n, m):
         assert np.max(np.abs(out[:, 4 + m:] - o['amps0'])) < tol * np.max(np.abs(o['amps0']))
 
 
+def test_nxm_kernel_emulated_address_sanitizer():
+    """The NxM kernel source under AddressSanitizer: every shared-memory, scratch (X columns, parked blocks, parked
+    q~ series) and table access of a two-phase fp64 run with 3 channels x 2 templates stays inside its buffer."""
+    from detprocess_b200.synth import SynthNxM
+    from oracle.ofnxm import ofnxm_setup, ofnxm_batch
+    S = SynthNxM(32768, 3, 2)
+    pre = S.nb_pretrigger
+    x = S.traces(3, np.random.default_rng(2))
+    out = run_emu.run_nxm(x, S.templates, S.csd, S.fs, pre, (pre - 300, pre + 700, False), precision='f64', asan=True)
+    o = ofnxm_batch(x, ofnxm_setup(S.templates, S.csd, S.fs, pre), (pre - 300, pre + 700, False))
+    assert np.array_equal(out[:, 2].astype(np.int64), o['ind'])
+    out = run_emu.run_nxm(x, S.templates, S.csd, S.fs, pre, (None, None, False), precision='f32', asan=True)
+    assert np.mean(out[:, 2].astype(np.int64) == ofnxm_batch(x, ofnxm_setup(S.templates, S.csd, S.fs, pre))['ind']) == 1.0
+
+
+@pytest.mark.parametrize('precision,nb_samples,n', [('f64', 32768, 2), ('f32', 16384, 3)])
+def test_csd_kernel_emulated(precision, nb_samples, n):
+    """The noise-CSD kernel source on host threads (under AddressSanitizer) + the host fold == oracle calc_csd."""
+    from detprocess_b200.core.noise import csd_from_sums
+    from detprocess_b200.synth import SynthNxM
+    from oracle.psd import calc_csd
+    S = SynthNxM(nb_samples, n, 1)
+    x = S.traces(5, np.random.default_rng(4), pulse_fraction=0.0) + 2e-8
+    mask = np.array([1, 1, 0, 1, 1], dtype=np.uint8)
+    sums, count = run_emu.run_csd(x, S.fs, mask, precision=precision, asan=True)
+    assert count == 4
+    csd = csd_from_sums(sums, count, n, nb_samples, S.fs)
+    ref = calc_csd(x, S.fs, mask)[1]
+    d = np.arange(n)
+    scale = np.sqrt(np.abs(ref[d, d])[:, None, :] * np.abs(ref[d, d])[None, :, :])
+    assert np.max(np.abs(csd - ref) / scale) < (1e-11 if precision == 'f64' else 3e-5)
+
+
 def test_reduce_kernel_emulated_bit_exact():
     exe = os.path.join(HERE, 'emu', '_build', 'emu_reduce')
     src = os.path.join(HERE, 'emu', 'emu_reduce.cpp')
