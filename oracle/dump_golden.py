@@ -56,6 +56,36 @@ def main(out_path, nb_samples=4096, n_events=16, seed=12345):
     np.savez(out_path, nb_samples=nb_samples, n_events=n_events, seed=seed, qetpy_version=getattr(qp, '__version__', '?'),
              psd_of_traces=psd, **{k: np.asarray(v) for k, v in res.items()})
     print('wrote', out_path)
+    dump_nxm(qp, os.path.join(os.path.dirname(out_path), 'ofnxm_qetpy.npz'), nb_samples, n_events, seed)
+
+
+def dump_nxm(qp, out_path, nb_samples, n_events, seed):
+    """NxM filter and CSD through the calls the reference makes: OFBase.set_csd / add_template on the joint channel
+    (processing_data.py:294-381), qp.OFnxm(...).calc() / get_fit_withdelay / get_fit_nodelay (algorithms.py:246-263),
+    qp.calc_csd (noise.py:452).  Settles the csd convention (E[X_a conj X_b] here, its conjugate in scipy.signal.csd)
+    and the chi2 normalisation of oracle/ofnxm.py."""
+    from detprocess_b200.synth import SynthNxM
+    S = SynthNxM(nb_samples, 2, 2)
+    pre = S.nb_pretrigger
+    x = S.traces(n_events, np.random.default_rng(seed))
+    chan = 'a|b'
+    ofb = qp.OFBase(S.fs)
+    ofb.set_csd(chan, S.csd, coupling='AC')
+    ofb.add_template(chan, S.templates, template_tag='shared', pretrigger_samples=pre)
+    res = {k: [] for k in ('amps', 't0', 'chi2', 'amps0', 'chi2_0')}
+    for ev in x:
+        ofb.clear_signal()
+        ofb.update_signal(chan, ev, calc_fft=True)
+        OF = qp.OFnxm(of_base=ofb, channels=chan, template_tag='shared', verbose=False)
+        OF.calc()
+        a, t, c = OF.get_fit_withdelay(window_min_index=pre - 500, window_max_index=pre + 500, lgc_outside_window=False)
+        a0, _, c0 = OF.get_fit_nodelay()
+        res['amps'].append(a), res['t0'].append(t), res['chi2'].append(c), res['amps0'].append(a0), res['chi2_0'].append(c0)
+    noise = S.traces(64, np.random.default_rng(seed + 1), pulse_fraction=0.0)
+    _, csd = qp.calc_csd(noise, fs=S.fs, folded_over=False)
+    np.savez(out_path, nb_samples=nb_samples, n_events=n_events, seed=seed, csd_of_noise=csd,
+             **{k: np.asarray(v) for k, v in res.items()})
+    print('wrote', out_path)
 
 
 if __name__ == '__main__':

@@ -53,3 +53,24 @@ def test_nxm_oracle_chi2_is_the_residual_of_the_fit():
         R = _fft_norm(x[e] - model, S.fs)                      # [n, N]
         chi2 = np.real(np.einsum('ak,kab,bk->', np.conj(R), st['iS'], R)) * df
         assert chi2 == pytest.approx(o['chi2'][e], rel=1e-9)
+
+
+def test_against_qetpy_golden():
+    """Upstream parity of the NxM oracle and the csd convention, where someone has run oracle/dump_golden.py with real
+    QETpy (the file cannot be produced in this environment and is not committed)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ofnxm_qetpy.npz')
+    if not os.path.exists(path):
+        pytest.skip('tests/golden/ofnxm_qetpy.npz not present: QETpy is not installable in this environment')
+    from oracle.psd import calc_csd
+    g = np.load(path)
+    S = SynthNxM(int(g['nb_samples']), 2, 2)
+    pre = S.nb_pretrigger
+    x = S.traces(int(g['n_events']), np.random.default_rng(int(g['seed'])))
+    o = ofnxm_batch(x, ofnxm_setup(S.templates, S.csd, S.fs, pre), (pre - 500, pre + 500, False))
+    assert np.allclose(o['amps'], g['amps'], rtol=1e-9)
+    assert np.allclose(o['t0'], g['t0'], rtol=0, atol=1e-12)
+    assert np.allclose(o['chi2'], g['chi2'], rtol=1e-9)
+    assert np.allclose(o['amps0'], g['amps0'], rtol=1e-9)
+    noise = S.traces(64, np.random.default_rng(int(g['seed']) + 1), pulse_fraction=0.0)
+    assert np.allclose(calc_csd(noise, S.fs)[1], g['csd_of_noise'], rtol=1e-9)
