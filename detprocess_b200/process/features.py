@@ -75,9 +75,15 @@ class FeatureProcessing:
         filter_data : FilterData with the templates / PSDs the YAML refers to
         """
         self._verbose = verbose
-        self._raw = raw_data
-        self._channels = list(raw_data['channels'])
-        self._fs = float(raw_data['sample_rate'])
+        from ..io.readers import EventReader, ArrayReader
+        if isinstance(raw_data, EventReader):
+            self._reader = raw_data
+        else:
+            self._reader = ArrayReader(raw_data['traces'], raw_data['channels'], raw_data['sample_rate'],
+                                       admin=raw_data.get('admin'), adc_gain=raw_data.get('adc_gain'),
+                                       adc_offset=raw_data.get('adc_offset'))
+        self._channels = self._reader.channels
+        self._fs = self._reader.sample_rate
         self._filter_data = filter_data
         self._precision = precision
         self._device = device
@@ -209,45 +215,43 @@ class FeatureProcessing:
 
     # ------------------------------------------------------------------ process
     def process(self, nevents=-1, lgc_save=False, lgc_output=True, save_path=None, ncores=1,
-                batch_size=8192, gather=True, **kwargs):
+                batch_size=8192, gather=True, memory_limit=2.0, **kwargs):
+        """Events are read batch by batch through the reader (int16 ADC counts cross PCIe as they are stored and become
+        amps on the device), sharded over ranks in contiguous blocks.  lgc_save: every rank writes its own dumps
+        ``<prefix>_rank<r>_F000k.parquet`` when ``memory_limit`` (GB) of rows is queued (reference features.py:584-629:
+        one file set per worker, no merge); lgc_output: the gathered table is returned."""
         import pandas as pd
-        import torch
-        traces = self._raw['traces']
-        if isinstance(traces, np.ndarray):
-            traces = torch.from_numpy(traces)
-        if traces.ndim == 2:
-            traces = traces[:, None, :]
-        nev_total = traces.shape[0] if nevents is None or nevents < 0 else min(nevents, traces.shape[0])
+        reader = self._reader
+        nev_total = len(reader) if nevents is None or nevents < 0 else min(nevents, len(reader))
         # ---- shard events over ranks (one process per GPU), contiguous blocks -----------------
         rank, world = dist_info()
         lo, hi = shard_range(nev_total, rank, world)
+        writer = None
+        if lgc_save:
+            from ..io.writers import FeatureWriter
+            writer = FeatureWriter(save_path or '.', prefix=self._processing_id or 'feature',
+                                   series_name=(f'rank{rank}' if world > 1 else None), memory_limit_gb=memory_limit)
         frames = []
         for b0 in range(lo, hi, batch_size):
             b1 = min(b0 + batch_size, hi)
-            frames.append(self._process_batch(traces[b0:b1], b0, b1))
+            df = self._process_batch(reader.read_batch(b0, b1), b0, b1)
+            if writer is not None:
+                writer.add(df)
+            if lgc_output:
+                frames.append(df)
+        self.output_files = writer.close() if writer is not None else []
+        if not lgc_output:
+            return None
         df = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame()
-        if gather:
-            df = gather_frames(df)
-        if lgc_save and rank == 0:
-            save_path = save_path or '.'
-            os.makedirs(save_path, exist_ok=True)
-            prefix = self._processing_id or 'feature'
-            df.to_parquet(os.path.join(save_path, f'{prefix}_F0001.parquet'))
-        return df if lgc_output else None
+        return gather_frames(df) if gather else df
 
     def _process_batch(self, traces, ev0, ev1):
         import pandas as pd
         import torch
         dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
-        traces = traces.to(dev, non_blocking=True)
+        traces = self._reader.to_amps(traces.to(dev, non_blocking=True))      # ADC -> amps on the device
         nb, _, n = traces.shape
-        cols = {}
-        admin = self._raw.get('admin')
-        if admin is not None:
-            for k, v in admin.items():
-                cols[k] = np.asarray(v)[ev0:ev1]
-        else:
-            cols['event_number'] = np.arange(ev0, ev1, dtype=np.int64)
+        cols = {k: np.asarray(v) for k, v in self._reader.admin(ev0, ev1).items()}
         if self._processing_id is not None:
             cols['processing_id'] = np.full(nb, self._processing_id)
 

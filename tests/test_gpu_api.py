@@ -207,3 +207,56 @@ def test_feature_processing_yaml_pipeline(tmp_path):
     diff = tr_a * 2.0 - tr_b * 0.5
     assert np.array_equal(df['minimum_chanA-chanB'].to_numpy(), R.minimum_batch(diff, 0, n - 1))
     assert np.allclose(df['user_rms_A'].to_numpy(), tr_a.std(axis=1))
+
+
+def test_pipeline_from_raw_adc_file_to_feature_dumps(tmp_path):
+    """File -> features -> file without HDF5: int16 ADC events in a raw-binary container (detprocess_b200.io) go through
+    the YAML pipeline (ADC -> amps on the device) and come out as parquet dumps; the numbers equal the pipeline run on the
+    float64 amps the reference's reader would have produced (processing_data.py:674-684, adctoamp=True)."""
+    import pandas as pd
+    import torch
+    from detprocess_b200.core.filterdata import FilterData
+    from detprocess_b200.io import RawBinaryReader, write_raw_binary
+    from detprocess_b200.process.features import FeatureProcessing
+    from detprocess_b200.synth import SynthSetup, make_traces
+    S = SynthSetup(16384)
+    pre = S.nb_pretrigger
+    gain, off = [1.0e-11, 1.3e-11], [2.0e-9, -1.0e-9]
+    amps = np.stack([make_traces(300, S.template, S.psd, S.fs, np.random.default_rng(60 + c)) for c in range(2)], axis=1)
+    adc = np.stack([np.clip(np.round((amps[:, c] - off[c]) / gain[c]), -32768, 32767) for c in range(2)], axis=1).astype(np.int16)
+    base = str(tmp_path / 'raw_series')
+    write_raw_binary(base, adc, ['chanA', 'chanB'], S.fs, adc_gain=gain, adc_offset=off,
+                     admin={'event_number': np.arange(300) + 1, 'series_number': np.full(300, 42)})
+    yml = tmp_path / 'cfg.yaml'
+    yml.write_text('''
+global:
+    trace_length_samples: 16384
+    pretrigger_length_samples: 8192
+chanA,chanB:
+    of1x1_constrained:
+        run: True
+        template_tag: default
+        window_min_from_trig_usec: -400
+        window_max_from_trig_usec: 400
+    baseline:
+        run: True
+        window_min_from_start_usec: 0
+        window_max_from_trig_usec: -1000
+    maximum:
+        run: True
+''')
+    fd = FilterData()
+    for c in ('chanA', 'chanB'):
+        fd.set_psd(c, S.psd, sample_rate=S.fs)
+        fd.set_template(c, S.template, sample_rate=S.fs, pretrigger_length_samples=pre)
+    fp = FeatureProcessing(RawBinaryReader(base), str(yml), filter_data=fd, processing_id='unit', verbose=False)
+    df = fp.process(lgc_save=True, save_path=str(tmp_path / 'out'), batch_size=128, memory_limit=2e-5)
+    assert len(df) == 300 and list(df['event_number']) == list(range(1, 301)) and (df['series_number'] == 42).all()
+    assert len(fp.output_files) >= 2
+    back = pd.concat([pd.read_parquet(f) for f in fp.output_files], ignore_index=True)
+    assert back.equals(df)
+    conv = np.stack([adc[:, c].astype(np.float64) * gain[c] + off[c] for c in range(2)], axis=1)
+    ref = FeatureProcessing({'traces': torch.from_numpy(conv), 'channels': ['chanA', 'chanB'], 'sample_rate': S.fs},
+                            str(yml), filter_data=fd, verbose=False).process()
+    for col in ('amp_of1x1_constrained_chanA', 'chi2_of1x1_constrained_chanB', 'baseline_chanA', 'maximum_chanB'):
+        assert np.array_equal(df[col].values, ref[col].values), col
