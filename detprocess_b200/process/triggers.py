@@ -27,7 +27,7 @@ class TriggerProcessing:
     def __init__(self, raw_data, config_file, filter_data=None, processing_id=None, edge_exclusion_msec=None,
                  livetime=None, precision='f64', device=None, verbose=True):
         """
-        raw_data : dict with
+        raw_data : a ``detprocess_b200.io.EventReader`` of continuous events, or a dict with
             'traces'      ndarray / torch tensor [n_events, n_chan, L] continuous events (float64 / float32 / int16)
             'channels'    list of channel names (length n_chan)
             'sample_rate' float
@@ -36,9 +36,19 @@ class TriggerProcessing:
         filter_data : FilterData with the templates / PSDs the YAML refers to
         """
         self._verbose = verbose
-        self._raw = raw_data
-        self._channels = list(raw_data['channels'])
-        self._fs = float(raw_data['sample_rate'])
+        from ..io.readers import EventReader, ArrayReader
+        if isinstance(raw_data, EventReader):
+            self._reader = raw_data
+            self._admin = None
+        else:
+            tr = raw_data['traces']
+            if tr.ndim == 2:          # one continuous event [n_chan, L]
+                tr = tr[None]
+            self._reader = ArrayReader(tr, raw_data['channels'], raw_data['sample_rate'],
+                                       adc_gain=raw_data.get('adc_gain'), adc_offset=raw_data.get('adc_offset'))
+            self._admin = raw_data.get('admin')
+        self._channels = self._reader.channels
+        self._fs = self._reader.sample_rate
         self._filter_data = filter_data
         self._processing_id = processing_id
         self._edge_exclusion_msec = edge_exclusion_msec
@@ -95,22 +105,18 @@ class TriggerProcessing:
     def process(self, ntriggers=-1, lgc_output=True, lgc_save=False, save_path=None, ncores=1, gather=True, **kwargs):
         import pandas as pd
         import torch
-        traces = self._raw['traces']
-        if isinstance(traces, np.ndarray):
-            traces = torch.from_numpy(traces)
-        if traces.ndim == 2:
-            traces = traces[None]
-        n_events, _, L = traces.shape
+        reader = self._reader
+        n_events, L = len(reader), int(reader.metadata['nb_samples'])
         dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
         eb = self._build_triggers(L)
-        admin = self._raw.get('admin')
+        admin = self._admin
         rank, world = dist_info()
         lo, hi = shard_range(n_events, rank, world)
         frames = []
         ntrig = 0
         for ev in range(lo, hi):
             eb.clear_event()
-            x = traces[ev].to(dev, non_blocking=True)
+            x = reader.to_amps(reader.read_batch(ev, ev + 1).to(dev, non_blocking=True))[0]   # [n_chan, L] amps on the device
             for trig_chan, td in self._trigger_config.items():
                 if 'threshold_sigma' in td:
                     thr = float(td['threshold_sigma'])
@@ -125,7 +131,11 @@ class TriggerProcessing:
                                     pileup_window_samples=(int(td['pileup_window_samples']) if 'pileup_window_samples' in td else None),
                                     positive_pulses=td.get('positive_pulses', True),
                                     edge_exclusion_msec=self._edge_exclusion_msec, livetime=self._livetime)
-            info = copy.deepcopy(admin[ev]) if admin is not None else {'event_num': ev + 1}
+            if admin is not None:
+                info = copy.deepcopy(admin[ev])
+            else:      # per-event columns of the reader (event_time, series_num, event_num, dump_num, ...)
+                info = {k: (v[0].item() if hasattr(v[0], 'item') else v[0]) for k, v in reader.admin(ev, ev + 1).items()}
+                info.setdefault('event_num', info.get('event_number', ev + 1))
             info.setdefault('sample_rate', self._fs)
             info.setdefault('nb_samples', L)
             if self._processing_id is not None:
