@@ -81,6 +81,8 @@ SIGNATURES = {
     'dp_reduce_plan_finalize': (_i, [_vp, _i]),
     'dp_reduce_plan_n_out': (_i, [_vp, _ip]),
     'dp_window_reduce_batch': (_i, [_vp, _vp, _ll, _ll, _vp, _vp]),
+    'dp_reduce_plan_set_adc_conversion': (_i, [_vp, _i, _d, _d]),
+    'dp_window_reduce_batch_raw': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _vp]),
     'dp_reduce_plan_last_kernel_ms': (_i, [_vp, _fp]),
     'dp_psd_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i]),
     'dp_psd_plan_destroy': (None, [_vp]),

@@ -342,6 +342,11 @@ class ReducePlan:
         self._added.append((int(chan), idx.value))
         return len(self._added) - 1
 
+    def set_adc_conversion(self, chan, gain, offset=0.0):
+        """int16 traces of this channel are raw ADC counts: sample = adc * gain + offset, rounded like numpy's
+        ``adc.astype(float64) * gain + offset``, so the reductions stay bit-identical to numpy on the converted trace."""
+        check(lib.dp_reduce_plan_set_adc_conversion(self._h, int(chan), float(gain), float(offset)))
+
     def finalize(self, device=None):
         torch = _torch()
         if not torch.cuda.is_available():
@@ -369,8 +374,8 @@ class ReducePlan:
         torch = _torch()
         if not self.finalized:
             raise _lib.DetprocessB200Error('plan not finalized')
-        if not traces.is_cuda or traces.dtype != torch.float64:
-            raise ValueError('run() takes float64 CUDA tensors')
+        if not traces.is_cuda or traces.dtype not in (torch.float64, torch.int16):
+            raise ValueError('run() takes float64 or int16 CUDA tensors')
         if traces.ndim == 2 and self.n_chan == 1:
             nev = traces.shape[0]
         elif traces.ndim == 3 and traces.shape[1] == self.n_chan:
@@ -382,8 +387,8 @@ class ReducePlan:
         traces = traces.contiguous()
         if out is None:
             out = torch.empty((nev, self.n_out), dtype=torch.float64, device=traces.device)
-        check(lib.dp_window_reduce_batch(self._h, C.c_void_p(traces.data_ptr()), nev, self.nb_samples,
-                                         C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
+        check(lib.dp_window_reduce_batch_raw(self._h, C.c_void_p(traces.data_ptr()), _in_dtype_of(traces), nev, self.nb_samples,
+                                             C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
         return out
 
     def last_kernel_ms(self):

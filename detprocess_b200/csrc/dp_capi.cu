@@ -713,6 +713,8 @@ struct dp_reduce_plan {
     const DpNode* d_nodes = nullptr;
     const int* d_level_off = nullptr;
     const DpRedFeat* d_feats = nullptr;
+    std::vector<double> adc;  // [n_chan][2] gain, offset of int16 traces
+    const double* d_adc = nullptr;
     int grid_max = 0;
     size_t smem = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -780,6 +782,11 @@ int dp_reduce_plan_finalize(dp_reduce_plan* p, int device) {
     if ((rc = upload(p->owned, p->plan.nodes, &p->d_nodes))) return rc;
     if ((rc = upload(p->owned, p->plan.level_off, &p->d_level_off))) return rc;
     if ((rc = upload(p->owned, p->plan.feats, &p->d_feats))) return rc;
+    if (p->adc.empty()) {
+        p->adc.assign(2 * (size_t)p->n_chan, 0.0);
+        for (int c = 0; c < p->n_chan; ++c) p->adc[2 * c] = 1.0;
+    }
+    if ((rc = upload(p->owned, p->adc, &p->d_adc))) return rc;
     p->smem = sizeof(double) * (size_t)(p->plan.max_nodes + 96);
     int occ = 0, sms = 0;
     DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_reduce_kernel<256>, 256, p->smem));
@@ -795,9 +802,27 @@ int dp_reduce_plan_n_out(const dp_reduce_plan* p, int* n_out) {
     *n_out = p->plan.n_out;
     return DP_OK;
 }
+int dp_reduce_plan_set_adc_conversion(dp_reduce_plan* p, int chan, double gain, double offset) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    if (chan < 0 || chan >= p->n_chan) return fail(DP_ERR_INVALID, "channel index out of range");
+    if (!(gain > 0) || !std::isfinite(gain) || !std::isfinite(offset)) return fail(DP_ERR_INVALID, "adc gain must be finite and > 0");
+    if (p->adc.empty()) {
+        p->adc.assign(2 * (size_t)p->n_chan, 0.0);
+        for (int c = 0; c < p->n_chan; ++c) p->adc[2 * c] = 1.0;
+    }
+    p->adc[2 * chan] = gain;
+    p->adc[2 * chan + 1] = offset;
+    return DP_OK;
+}
 int dp_window_reduce_batch(dp_reduce_plan* p, const double* traces_dev, long long n_events, long long row_stride,
                            double* out_dev, void* stream) {
+    return dp_window_reduce_batch_raw(p, traces_dev, DP_IN_F64, n_events, row_stride, out_dev, stream);
+}
+int dp_window_reduce_batch_raw(dp_reduce_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride,
+                               double* out_dev, void* stream) {
     if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (in_dtype != DP_IN_F64 && in_dtype != DP_IN_I16) return fail(DP_ERR_UNSUPPORTED, "window reductions take float64 or int16 traces");
     if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
     if (n_events == 0 || p->plan.n_out == 0) return DP_OK;
     if (!traces_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
@@ -806,6 +831,7 @@ int dp_window_reduce_batch(dp_reduce_plan* p, const double* traces_dev, long lon
     DpReduceParams prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.traces = traces_dev;
+    prm.adc = p->d_adc;
     prm.row_stride = row_stride;
     prm.n_rows = (int)(n_events * p->n_chan);
     prm.n_chan = p->n_chan;
@@ -821,7 +847,10 @@ int dp_window_reduce_batch(dp_reduce_plan* p, const double* traces_dev, long lon
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     DP_CUDA(cudaEventRecord(p->ev0, st));
-    dp_reduce_kernel<256><<<grid, 256, p->smem, st>>>(prm);
+    if (in_dtype == DP_IN_I16)
+        dp_reduce_kernel<256, 2><<<grid, 256, p->smem, st>>>(prm);
+    else
+        dp_reduce_kernel<256, 0><<<grid, 256, p->smem, st>>>(prm);
     DP_CUDA(cudaGetLastError());
     DP_CUDA(cudaEventRecord(p->ev1, st));
     p->timed = true;

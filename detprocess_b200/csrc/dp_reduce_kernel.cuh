@@ -38,7 +38,8 @@ struct DpRedChan {
     int pad0, pad1;
 };
 struct DpReduceParams {
-    const double* traces;
+    const void* traces;     // float64, or int16 ADC counts (sample = adc * gain + offset, rounded like numpy: product, then sum)
+    const double* adc;      // [n_chan][2] gain, offset (int16 input only)
     long long row_stride;
     int n_rows, n_chan;
     const DpRedChan* chans;
@@ -58,14 +59,35 @@ DP_DEV double dp_add_rn(double a, double b) { return __dadd_rn(a, b); }
 DP_DEV double dp_add_rn(double a, double b) { return a + b; }
 #endif
 
-DP_DEV double dp_red_elem(const double* DP_RESTRICT x, int i, int trapz) {
-    const double a = __ldg(x + i);
+#ifndef DP_HOST_EMU
+DP_DEV double dp_mul_rn(double a, double b) { return __dmul_rn(a, b); }
+#else
+DP_DEV double dp_mul_rn(double a, double b) { return a * b; }
+#endif
+
+// sample i of the row: IN = 0 float64, IN = 2 int16 ADC counts converted as numpy does (adc.astype(float64) * gain + offset:
+// two roundings, never contracted into an FMA), so that every reduction stays bit-identical to numpy on the converted trace
+template <int IN> struct DpRedRow {
+    const void* x;
+    double gain, offs;
+    DP_DEV double operator[](int i) const {
+        if constexpr (IN == 0) {
+            return __ldg(reinterpret_cast<const double*>(x) + i);
+        } else {
+            const short v = __ldg(reinterpret_cast<const short*>(x) + i);
+            return dp_add_rn(dp_mul_rn((double)v, gain), offs);
+        }
+    }
+};
+
+template <int IN> DP_DEV double dp_red_elem(const DpRedRow<IN>& x, int i, int trapz) {
+    const double a = x[i];
     if (!trapz) return a;
-    const double b = __ldg(x + i + 1);
+    const double b = x[i + 1];
     return dp_add_rn(b, a) * 0.5;  // exact halving == numpy's / 2.0
 }
 
-template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* nodeval, double* red) {
+template <int NT, int IN = 0> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* nodeval, double* red) {
     const int tid = threadIdx.x;
     const int lane8 = tid & 7;
     const int grp = tid >> 3;
@@ -74,7 +96,10 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
         const int chan = row % prm.n_chan;
         const int ev = row / prm.n_chan;
         const DpRedChan ch = prm.chans[chan];
-        const double* DP_RESTRICT x = prm.traces + (long long)row * prm.row_stride;
+        DpRedRow<IN> x;
+        x.x = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * (IN == 0 ? 8 : 2);
+        x.gain = IN == 0 ? 1.0 : prm.adc[2 * chan];
+        x.offs = IN == 0 ? 0.0 : prm.adc[2 * chan + 1];
         // ---- leaves: 8 lanes = numpy's 8 accumulators -------------------------------
         // (loop bounds are CTA-uniform so the shuffles below are never divergent)
         for (int L0 = ch.leaf_begin; L0 < ch.leaf_end; L0 += NG) {
@@ -88,11 +113,11 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
             // addition (the additions keep numpy's order; one load in flight per thread left the kernel latency bound)
             double v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (8 * j < nfull) ? __ldg(x + lf.off + 8 * j + lane8) : 0.0;
+            for (int j = 0; j < 16; ++j) v[j] = (8 * j < nfull) ? x[lf.off + 8 * j + lane8] : 0.0;
             if (lf.trapz) {  // element i is (y[i+1] + y[i]) / 2 (exact halving == numpy's / 2.0)
                 double w[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) w[j] = (8 * j < nfull) ? __ldg(x + lf.off + 8 * j + lane8 + 1) : 0.0;
+                for (int j = 0; j < 16; ++j) w[j] = (8 * j < nfull) ? x[lf.off + 8 * j + lane8 + 1] : 0.0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = dp_add_rn(w[j], v[j]) * 0.5;
             }
@@ -138,7 +163,7 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
                 int has_nan = 0;
 #pragma unroll 4
                 for (int i = ft.lo + tid; i < ft.hi; i += NT) {
-                    const double v = __ldg(x + i);
+                    const double v = x[i];
                     if (v != v) has_nan = 1;
                     mx = fmax(mx, v);
                     mn = fmin(mn, v);
@@ -179,10 +204,10 @@ template <int NT> DP_DEV void dp_reduce_rows(const DpReduceParams& prm, double* 
 }
 
 #ifndef DP_HOST_EMU
-template <int NT> __global__ void __launch_bounds__(NT) dp_reduce_kernel(const DpReduceParams prm) {
+template <int NT, int IN = 0> __global__ void __launch_bounds__(NT) dp_reduce_kernel(const DpReduceParams prm) {
     extern __shared__ __align__(16) unsigned char dp_red_smem[];
     double* nodeval = reinterpret_cast<double*>(dp_red_smem);
     double* red = nodeval + prm.max_nodes;
-    dp_reduce_rows<NT>(prm, nodeval, red);
+    dp_reduce_rows<NT, IN>(prm, nodeval, red);
 }
 #endif

@@ -155,6 +155,13 @@ int dp_reduce_plan_n_out(const dp_reduce_plan* plan, int* n_out);
 /* traces_dev: float64 [n_events][n_chan][row_stride]; out_dev: float64 [n_events][n_out] */
 int dp_window_reduce_batch(dp_reduce_plan* plan, const double* traces_dev, long long n_events, long long row_stride,
                            double* out_dev, void* stream);
+/* int16 traces are raw ADC counts: sample = adc * gain + offset, converted in the load with numpy's two roundings
+ * (adc.astype(float64) * gain + offset), so that every reduction is bit-identical to numpy on the trace the reference's
+ * reader converts on the host (H5Reader adctoamp=True, processing_data.py:674-684).  Before finalize. */
+int dp_reduce_plan_set_adc_conversion(dp_reduce_plan* plan, int chan, double gain, double offset);
+/* in_dtype DP_IN_F64 or DP_IN_I16 */
+int dp_window_reduce_batch_raw(dp_reduce_plan* plan, const void* traces_dev, int in_dtype, long long n_events,
+                               long long row_stride, double* out_dev, void* stream);
 int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* plan, float* ms);
 
 /* ------------------------------------------------------------------ noise PSD

@@ -64,3 +64,32 @@ def test_reductions_multichannel_layout():
     for c in range(nch):
         assert _bits_equal(out[:, plan.column(hs[(c, 'b')])], R.baseline_batch(traces[:, c], 0, 1000 + c))
         assert _bits_equal(out[:, plan.column(hs[(c, 'i')])], R.integral_batch(traces[:, c], fs, 10 * c, 3000))
+
+
+@pytest.mark.parametrize('nb_samples', [1000, 32768])
+def test_reductions_on_adc_counts_bit_exact(nb_samples):
+    """int16 ADC counts + per-channel conversion (dp_reduce_plan_set_adc_conversion) == numpy on the trace the reference's
+    reader converts on the host (adc.astype(float64) * gain + offset): bit for bit, two channels with different gains."""
+    import torch
+    from detprocess_b200.core.plans import ReducePlan
+    rng = np.random.default_rng(5)
+    n, fs = nb_samples, 1.25e6
+    adc = rng.integers(-32768, 32767, size=(129, 2, n), dtype=np.int16)
+    gains, offs = (3.0517578125e-11 * 1.7, 1.234e-11), (-2.5e-9, 7.7e-8)
+    conv = np.stack([adc[:, c].astype(np.float64) * gains[c] + offs[c] for c in range(2)], axis=1)
+    feats = [('baseline', 0, n // 2 - 100), ('integral', n // 2 - 62, n // 2 + 62), ('maximum', None, None), ('minimum', None, None),
+             ('baseline', 3, 3 + 129), ('integral', 1, min(n, 1026)), ('baseline', 0, n), ('maximum', 5, 70)]
+    plan = ReducePlan(n, fs, 2)
+    hs = []
+    for c in range(2):
+        plan.set_adc_conversion(c, gains[c], offs[c])
+        for op, a, b in feats:
+            hs.append((c, op, a, b, plan.add(c, op, a, b)))
+    plan.finalize()
+    out = plan.run(torch.from_numpy(adc).cuda()).cpu().numpy()
+    ref = plan.run(torch.from_numpy(conv).cuda()).cpu().numpy()          # the float64 path of the same plan
+    assert _bits_equal(out, ref)
+    for c, op, a, b, h in hs:
+        lo = 0 if a is None else a
+        hi = n - 1 if b is None else b
+        assert _bits_equal(out[:, plan.column(h)], _oracle(op, conv[:, c], fs, lo, hi)), (c, op, a, b)
