@@ -39,6 +39,7 @@ class OFBaseBatch:
         self._nxm_templates = {}
         self._nxm_plans = {}   # (chan, tag) -> NxMPlan
         self._nxm_out = {}     # (chan, tag, lo, hi, outside) -> host ndarray
+        self._adc = {}         # chan -> (gain, offset): int16 signals of the channel are raw ADC counts
 
     # ---- reference-shaped setup -------------------------------------------------
     def sample_rate(self):
@@ -149,6 +150,13 @@ class OFBaseBatch:
         c, t = self._handles[('templ', channel, template_tag)]
         return self._plan.norm(c, t)
 
+    def set_adc_conversion(self, channel, gain, offset=0.0):
+        """int16 signals of ``channel`` are raw ADC counts, converted in the kernel's load: sample = adc * gain + offset
+        (what the reference's reader does on the host with adctoamp=True, processing_data.py:674-684)."""
+        if self._adc.get(channel) != (float(gain), float(offset)):
+            self._adc[channel] = (float(gain), float(offset))
+            self._plan = None
+
     def set_lowchi2_fcutoff(self, fcutoff):
         if float(fcutoff) != self._fcut:
             self._fcut = float(fcutoff)
@@ -178,6 +186,8 @@ class OFBaseBatch:
             for ci, chan in enumerate(chans):
                 psd, coupling = self._psd[chan]
                 plan.set_psd(ci, psd, coupling)
+                if chan in self._adc:
+                    plan.set_adc_conversion(ci, *self._adc[chan])
                 for tag, (tmpl, pre, inorm) in self._templates[chan].items():
                     handles[('templ', chan, tag)] = (ci, plan.add_template(ci, tmpl, pre, inorm))
             for key in self._fits:

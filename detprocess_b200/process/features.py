@@ -103,6 +103,19 @@ class FeatureProcessing:
             if dup:
                 raise ValueError(f'ERROR: External feature extractor(s) {sorted(dup)} duplicate internal names')
         self._of_bases = {}     # key_tuple -> {'OF': OFBaseBatch, 'channels': [...], 'algorithms': [...]}
+        # int16 ADC events stay int16 on the device (the fused kernels convert in their loads) when every configured
+        # channel is a plain channel and every algorithm is built in; channel algebra / NxM / external extractors take
+        # the float64 path (ADC -> amps by a torch kernel first)
+        meta = self._reader.metadata
+        self._adc = None
+        if meta.get('dtype') == 'int16' and 'adc_gain' in meta:
+            plain = all(utils.split_channel_name(c, available_channels=self._channels)[1] is None
+                        for c, cc in self._processing_config.items() if isinstance(cc, dict))
+            builtin = all(params.get('base_algorithm', algo) in self._algorithm_list
+                          for cc in self._processing_config.values() if isinstance(cc, dict)
+                          for algo, params in cc.items() if isinstance(params, dict) and params.get('run'))
+            if plain and builtin:
+                self._adc = {c: (float(meta['adc_gain'][i]), float(meta['adc_offset'][i])) for i, c in enumerate(self._channels)}
         self._instantiate_of_bases()
 
     # ------------------------------------------------------------------ setup
@@ -154,6 +167,8 @@ class FeatureProcessing:
                 if chan not in entry['channels']:
                     entry['channels'].append(chan)
                 ofb = entry['OF']
+                if self._adc is not None and chan in self._adc:
+                    ofb.set_adc_conversion(chan, *self._adc[chan])
                 csd_tag = params.get('csd_tag', 'default')
                 if base == 'ofnxm':
                     psd, _, meta = self._filter_data.get_csd(chan, tag=csd_tag, return_metadata=True)
@@ -249,7 +264,9 @@ class FeatureProcessing:
         import pandas as pd
         import torch
         dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
-        traces = self._reader.to_amps(traces.to(dev, non_blocking=True))      # ADC -> amps on the device
+        traces = traces.to(dev, non_blocking=True)
+        if self._adc is None:
+            traces = self._reader.to_amps(traces)                             # ADC -> amps on the device (torch)
         nb, _, n = traces.shape
         cols = {k: np.asarray(v) for k, v in self._reader.admin(ev0, ev1).items()}
         if self._processing_id is not None:
@@ -304,6 +321,9 @@ class FeatureProcessing:
         if red_jobs:
             chans = utils.unique_list([j[0] for j in red_jobs])
             red = ReducePlan(n, self._fs, len(chans))
+            if self._adc is not None:
+                for i, c in enumerate(chans):
+                    red.set_adc_conversion(i, *self._adc[c])
             handles = [red.add(chans.index(c), op, a, b) for c, op, a, b, _ in red_jobs]
             red.finalize(dev)
             x = torch.stack([self._channel_trace(traces, c) for c in chans], dim=1).contiguous()
