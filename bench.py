@@ -378,6 +378,49 @@ def extras(device, dist, world, hbm_peak):
                                                 'algorithmic_bytes_per_event': byt, 'features_per_event': pl.n_out + red3.n_out}
         del pl, o3
     del x3, red3, r3
+    # ---- the YAML-driven pipeline (FeatureProcessing: reader -> H2D -> fused kernels -> feature table) on the C2 feature
+    # set + baseline / integral, from pinned host events: int16 ADC counts (as stored on disk) and float64 amps
+    import tempfile
+    from detprocess_b200.core.filterdata import FilterData
+    from detprocess_b200.io import ArrayReader
+    from detprocess_b200.process.features import FeatureProcessing
+    S2 = SynthSetup(NB_SAMPLES, FS)
+    E = 4096
+    gain = 1.0e-11
+    xa = make_device_traces(S2, E, device, 779)
+    host_f64 = torch.empty((E, 1, NB_SAMPLES), dtype=torch.float64).pin_memory()
+    host_f64[:, 0].copy_(xa.cpu())
+    host_i16 = torch.empty((E, 1, NB_SAMPLES), dtype=torch.int16).pin_memory()
+    host_i16[:, 0].copy_(torch.clamp(torch.round(xa / gain), -32768, 32767).to(torch.int16).cpu())
+    del xa
+    fd = FilterData()
+    fd.set_psd('chan1', S2.psd, sample_rate=FS)
+    fd.set_template('chan1', S2.template, sample_rate=FS, pretrigger_length_samples=S2.nb_pretrigger)
+    fd.set_template('chan1', S2.template_glitch, sample_rate=FS, pretrigger_length_samples=S2.nb_pretrigger, tag='glitch')
+    with tempfile.TemporaryDirectory() as td:
+        yml = os.path.join(td, 'c2.yaml')
+        with open(yml, 'w') as f:
+            f.write('global:\n    trace_length_samples: %d\n    pretrigger_length_samples: %d\n' % (NB_SAMPLES, S2.nb_pretrigger)
+                    + 'chan1:\n'
+                    + '    of1x1_constrained:\n        run: True\n        template_tag: default\n'
+                    + '        window_min_from_trig_usec: -400\n        window_max_from_trig_usec: 400\n'
+                    + '    of1x1_glitch:\n        run: True\n        base_algorithm: of1x1_constrained\n        template_tag: glitch\n'
+                    + '        window_min_from_trig_usec: -400\n        window_max_from_trig_usec: 400\n'
+                    + '    baseline:\n        run: True\n        window_min_from_start_usec: 0\n        window_max_from_trig_usec: -1000\n'
+                    + '    integral:\n        run: True\n        window_min_from_trig_usec: -500\n        window_max_from_trig_usec: 500\n')
+        for name, host, kw in (('int16', host_i16, {'adc_gain': [gain], 'adc_offset': [0.0]}), ('float64', host_f64, {})):
+            fp = FeatureProcessing(ArrayReader(host, ['chan1'], FS, **kw), yml, filter_data=fd, verbose=False)
+            fp.process(batch_size=2048, gather=False)          # warm-up (plans, staging)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            df = fp.process(batch_size=2048, gather=False)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out[f'pipeline_yaml_c2_{name}'] = {'events_per_s_per_gpu': E / dt, 'events': E, 'columns': int(df.shape[1]),
+                                               'h2d_bytes': int(host.numel() * host.element_size()),
+                                               'api': 'FeatureProcessing.process (YAML, FilterData, pinned host events)'}
+            del fp, df
+    del host_f64, host_i16
     # ---- (f)3 NxM optimal filter: 2 channels x 2 templates, 32768 samples, +-400 us window + no-delay fit
     from detprocess_b200.core.plans import NxMPlan
     from detprocess_b200.synth import SynthNxM
