@@ -159,3 +159,42 @@ def calc_csd(traces, fs, cut=None, precision='f64', batch=2048):
     for i in range(0, traces.shape[0], batch):
         est.update(traces[i:i + batch], None if cut is None else cut[i:i + batch])
     return est.finalize()
+
+
+def calc_psd_from_reader(reader, channel, cut=None, precision='f64', batch=4096, device=None):
+    """``Noise.calc_psd`` on the randoms behind a ``detprocess_b200.io.EventReader`` (reference core/noise.py:216-370:
+    the events are read in one shot there, in batches here; ranks take contiguous shards and all-reduce the sums).
+    ADC counts become amps on the device.  Returns (freqs, psd two-sided)."""
+    torch = _torch()
+    from ..process.features import dist_info, shard_range
+    ci = reader.channels.index(channel)
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    est = NoisePSD(int(reader.metadata['nb_samples']), reader.sample_rate, precision=precision, device=dev)
+    rank, world = dist_info()
+    lo, hi = shard_range(len(reader), rank, world)
+    for i0 in range(lo, hi, batch):
+        i1 = min(i0 + batch, hi)
+        x = reader.to_amps(reader.read_batch(i0, i1).to(dev, non_blocking=True))[:, ci].contiguous()
+        est.update(x, None if cut is None else torch.as_tensor(np.asarray(cut[i0:i1]), device=dev))
+    return est.finalize()
+
+
+def calc_csd_from_reader(reader, channels, cut=None, precision='f64', batch=2048, device=None):
+    """``Noise.calc_csd`` (core/noise.py:374-470) on the randoms behind an ``EventReader``; ``channels`` is the list (or
+    'a|b' string) of joint channels in the order of the csd's rows.  Returns (freqs, csd [n, n, N])."""
+    torch = _torch()
+    from ..process.features import dist_info, shard_range
+    if isinstance(channels, str):
+        channels = [c.strip() for c in channels.split('|')]
+    if len(channels) < 2:
+        raise ValueError('ERROR: At least 2 channels required to calculate csd')
+    idx = [reader.channels.index(c) for c in channels]
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    est = NoiseCSD(int(reader.metadata['nb_samples']), reader.sample_rate, len(idx), precision=precision, device=dev)
+    rank, world = dist_info()
+    lo, hi = shard_range(len(reader), rank, world)
+    for i0 in range(lo, hi, batch):
+        i1 = min(i0 + batch, hi)
+        x = reader.to_amps(reader.read_batch(i0, i1).to(dev, non_blocking=True))[:, idx].contiguous()
+        est.update(x, None if cut is None else torch.as_tensor(np.asarray(cut[i0:i1]), device=dev))
+    return est.finalize()

@@ -100,3 +100,27 @@ def test_csd_parity(precision, nb_samples, n_chan):
     assert np.max(np.abs(csd - ref) / scale) < tol
     # its inverse drives the NxM filter: the estimate is a valid (hermitian, positive) csd at every bin
     assert np.allclose(csd, np.conj(np.transpose(csd, (1, 0, 2))))
+
+
+def test_psd_and_csd_from_a_raw_adc_file(tmp_path):
+    """Noise randoms stored as int16 ADC counts in the raw-binary container -> PSD / CSD estimators through the reader
+    interface == the oracle on the host-converted traces."""
+    from detprocess_b200.core.noise import calc_psd_from_reader, calc_csd_from_reader
+    from detprocess_b200.io import RawBinaryReader, write_raw_binary
+    from detprocess_b200.synth import SynthNxM
+    from oracle.psd import calc_csd
+    S = SynthNxM(16384, 2, 1)
+    x = S.traces(150, np.random.default_rng(13), pulse_fraction=0.0)
+    gain, off = [2.0e-12, 3.0e-12], [1.0e-9, -4.0e-9]
+    adc = np.stack([np.clip(np.round((x[:, c] - off[c]) / gain[c]), -32768, 32767) for c in range(2)], axis=1).astype(np.int16)
+    base = str(tmp_path / 'randoms')
+    write_raw_binary(base, adc, ['chanA', 'chanB'], S.fs, adc_gain=gain, adc_offset=off)
+    conv = np.stack([adc[:, c].astype(np.float64) * gain[c] + off[c] for c in range(2)], axis=1)
+    cut = np.arange(150) % 7 != 0
+    r = RawBinaryReader(base)
+    f, psd = calc_psd_from_reader(r, 'chanB', cut=cut, batch=64)
+    assert np.allclose(psd, P.calc_psd(conv[:, 1], S.fs, cut)[1], rtol=1e-11)
+    f, csd = calc_csd_from_reader(r, 'chanA|chanB', cut=cut, batch=64)
+    ref = calc_csd(conv, S.fs, cut)[1]
+    scale = np.sqrt(np.abs(ref[0, 0]) * np.abs(ref[1, 1]))
+    assert np.max(np.abs(csd - ref) / scale[None, None, :]) < 1e-11
