@@ -80,6 +80,11 @@ template <class T, int R1, int NCH> struct DpCsdKernel {
                     const double x0 = prm.subtract_first ? dp_load_first<0>(xrow) : 0.0;
                     Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
                     __syncthreads();
+#ifndef DP_HOST_EMU
+                    // every second block starts its passes a little late (see dp_of2_kernel.cuh: the block sets' LDS / FP /
+                    // STS phases interleave instead of hitting the same pipe at the same time)
+                    if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);
+#endif
                     Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                     if (p == 0 && tid < 32) {
                         if constexpr (VL == 2) {

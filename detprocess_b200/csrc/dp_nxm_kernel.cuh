@@ -149,6 +149,11 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                                          : "memory");
                     }
 #endif
+#ifndef DP_HOST_EMU
+                    // every second block starts its passes a little late (see dp_of2_kernel.cuh: the block sets' LDS / FP /
+                    // STS phases interleave instead of hitting the same pipe at the same time)
+                    if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);
+#endif
                     Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                     if (p == 0 && tid < 32) {
                         if constexpr (VL == 2) {
