@@ -112,6 +112,9 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                 else
                     Core::template pass1_any<false>(p, xrow, x0, prm.scale, buf, prm.tw1);
                 __syncthreads();
+#ifndef DP_HOST_EMU
+                if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);  // see dp_of2_kernel.cuh
+#endif
                 Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
                 if (p == 0 && tid < 32) {
                     if constexpr (VL == 2) {
