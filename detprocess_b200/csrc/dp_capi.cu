@@ -359,6 +359,10 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     prm.nlow = p->nlow;
     prm.scale = p->scale;
     prm.subtract_first = p->subtract_first;
+    {
+        const char* e = std::getenv("DP2_SKEW_NS");  // development switch
+        prm.skew_ns = e ? std::atoi(e) : DP2_SKEW_NS;
+    }
     prm.row_start = row_start;
     prm.stream_len = stream_len;
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);

@@ -205,6 +205,7 @@ template <class T> struct Dp2Params {
     int nlow;
     double scale;
     int subtract_first;
+    int skew_ns;  // start delay of every second block (DP2_SKEW_NS unless the plan overrides it)
     // window mode (single channel): event r is the N-sample window of one continuous stream that starts
     // at sample row_start[r] (the step between the trigger and the features in the reference,
     // processing_data.py:643-688); windows that stick out of [0, stream_len) get the -999999 sentinels
@@ -895,7 +896,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
 #ifndef DP_HOST_EMU
             // every second block starts its passes a little late so that the block sets' LDS / FP / STS phases
             // interleave instead of hitting the same pipe at the same time (+3 % measured, 600 ns; 0 disables)
-            if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);
+            if (prm.skew_ns > 0 && ((tid / G::CV) & 1)) __nanosleep(prm.skew_ns);
 #endif
             Core::fwd_234(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
             if (p == 0 && tid < 32) {
