@@ -1687,6 +1687,7 @@ struct dp_csd_plan {
     long long scratch_per_cta = 0;
     double* partial = nullptr;
     long long partial_per_comp = 0, partial_per_cta = 0;
+    int ncp = 0;  // components per partial-sum slot (n*n padded to even)
     unsigned long long *count = nullptr, *count_out = nullptr;
     int grid_max = 0;
     size_t smem = 0;
@@ -1733,9 +1734,9 @@ template <class T> int csd_finalize(dp_csd_plan* p) {
     }
     if (rc) return rc;
     const int prec = sizeof(typename Dp2Traits<T>::S) == 8 ? 0 : 1;
-    const int src = dp_csd_setup_table[prec][p->n - 2](p->r1, p->device, &p->smem, &p->grid_max, &p->partial_per_comp, &p->scratch_per_cta);
+    const int src = dp_csd_setup_table[prec][p->n - 2](p->r1, p->device, &p->smem, &p->grid_max, &p->partial_per_comp, &p->scratch_per_cta, &p->ncp);
     if (src != 0) return fail(DP_ERR_CUDA, "CSD kernel setup failed");
-    p->partial_per_cta = p->partial_per_comp * p->n * p->n;
+    p->partial_per_cta = p->partial_per_comp * p->ncp;
     DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->partial), sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
     p->owned.push_back(p->partial);
     DP_CUDA(cudaMalloc(&p->scratch, sizeof(cx<T>) * (size_t)p->scratch_per_cta * (size_t)p->grid_max));
@@ -1851,7 +1852,7 @@ int dp_csd_get_sums(dp_csd_plan* p, double* sums_dev, unsigned long long* count_
     DpCsdReduceParams prm;
     prm.partial = p->partial;
     prm.partial_per_cta = p->partial_per_cta;
-    prm.partial_per_comp = p->partial_per_comp;
+    prm.ncp = p->ncp;
     prm.grid = p->grid_max;
     prm.loc = p->loc;
     prm.nbins = nbins;

@@ -21,11 +21,12 @@ using InstT = f2;
 #define DP_CAT(a, b, c) DP_CAT_(a, b, c)
 
 namespace {
-template <int R1> int setup_one(int device, size_t* smem, int* grid_max, long long* partial_per_comp, long long* scratch_per_cta) {
+template <int R1> int setup_one(int device, size_t* smem, int* grid_max, long long* partial_per_comp, long long* scratch_per_cta, int* ncp) {
     using K = DpCsdKernel<InstT, R1, DP_INST_NCH>;
     auto kern = dp_csd_kernel<InstT, R1, DP_INST_NCH>;
     *smem = K::SMEM_BYTES;
-    *partial_per_comp = K::PARTIAL;
+    *partial_per_comp = K::PARTIAL;  // slots; the plan multiplies by the padded component count
+    *ncp = K::NCP;
     *scratch_per_cta = K::scratch_v();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -45,11 +46,11 @@ template <int R1> int launch_one(const DpCsdParams<InstT>& prm, int grid, size_t
 }  // namespace
 
 int DP_CAT(dp_csd_setup_p, DP_INST_PREC, DP_INST_NCH)(int R1, int device, size_t* smem, int* grid_max, long long* partial_per_comp,
-                                                      long long* scratch_per_cta) {
+                                                      long long* scratch_per_cta, int* ncp) {
     switch (R1) {
-        case 2: return setup_one<2>(device, smem, grid_max, partial_per_comp, scratch_per_cta);
-        case 4: return setup_one<4>(device, smem, grid_max, partial_per_comp, scratch_per_cta);
-        case 8: return setup_one<8>(device, smem, grid_max, partial_per_comp, scratch_per_cta);
+        case 2: return setup_one<2>(device, smem, grid_max, partial_per_comp, scratch_per_cta, ncp);
+        case 4: return setup_one<4>(device, smem, grid_max, partial_per_comp, scratch_per_cta, ncp);
+        case 8: return setup_one<8>(device, smem, grid_max, partial_per_comp, scratch_per_cta, ncp);
         default: return -1;
     }
 }
@@ -70,7 +71,7 @@ __global__ void dp_csd_reduce_kernel(const DpCsdReduceParams prm) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int comp = blockIdx.y;
     if (k < prm.nbins) {
-        const long long l = (long long)comp * prm.partial_per_comp + prm.loc[k];
+        const long long l = (long long)prm.loc[k] * prm.ncp + comp;
         double s = 0.0;
         for (int c = 0; c < prm.grid; ++c) s += prm.partial[(long long)c * prm.partial_per_cta + l];
         prm.sum_out[(long long)comp * prm.nbins + k] += s;

@@ -26,7 +26,7 @@ template <class T> struct DpCsdParams {
     const int2* groups;
     cx<T>* scratch;
     long long scratch_per_cta;  // V units
-    double* partial;            // [grid][n_comp][PARTIAL]
+    double* partial;            // [grid][PARTIAL slots][NCP components]
     long long partial_per_cta;
     unsigned long long* count;  // [grid] accepted events per CTA
     double scale;
@@ -41,7 +41,8 @@ template <class T, int R1, int NCH> struct DpCsdKernel {
     using OF = Dp2OfKernel<T, R1, 0>;
     static constexpr int NT = G::NT, VL = G::VL, NPH = G::NPH, N = G::N;
     static constexpr int SX = 34;
-    static constexpr int NCOMP = NCH * NCH;  // NCH diagonal arrays + (re, im) per pair a < b
+    static constexpr int NCOMP = NCH * NCH;  // NCH diagonal sums + (re, im) per pair a < b
+    static constexpr int NCP = (NCOMP + 1) & ~1;  // components of one bin are adjacent (padded to 16-byte pairs)
     static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (32 + SX * NCH) + sizeof(double) * NCH + 64;
     static constexpr long long PARTIAL = (long long)NPH * 16 * NT * VL + 17 * 2;  // slots of one component
     static constexpr long long SCR_X = (long long)16 * NT;
@@ -130,52 +131,63 @@ template <class T, int R1, int NCH> struct DpCsdKernel {
 
                 // ---------------- X_a conj(X_b) of the thread's bins -> its partial-sum slots ----------------
                 if (!special) {
-#pragma unroll 2
+#pragma unroll 1
                     for (int r = 0; r < 16; ++r) {
                         V X[NCH];
 #pragma unroll
                         for (int a = 0; a < NCH; ++a) X[a] = dp2_ld_keep(scr_x + SCR_X * a + r * NT + tid, pol);
-                        const long long slot = ((long long)p * 16 + r) * NT + tid;
-                        auto add = [&](int comp, T v) {
-                            if constexpr (VL == 2) {
-                                double2* q = reinterpret_cast<double2*>(part + (long long)comp * PARTIAL) + slot;
-                                double2 s = *q;
-                                s.x += (double)v.x * inv_s2;
-                                s.y += (double)v.y * inv_s2;
-                                *q = s;
-                            } else {
-                                part[(long long)comp * PARTIAL + slot] += v * inv_s2;
-                            }
-                        };
+                        T vals[NCP];
+                        if constexpr (NCP != NCOMP) vals[NCP - 1] = (T)0.0f;
 #pragma unroll
                         for (int a = 0; a < NCH; ++a) {
-                            add(a, cnorm2(X[a]));
+                            vals[a] = cnorm2(X[a]);
 #pragma unroll
                             for (int b = a + 1; b < NCH; ++b) {
                                 const int c = NCH + 2 * pair_index(a, b);
-                                add(c, dp_fma(X[a].re, X[b].re, X[a].im * X[b].im));
-                                add(c + 1, dp_fma(X[a].im, X[b].re, -(X[a].re * X[b].im)));
+                                vals[c] = dp_fma(X[a].re, X[b].re, X[a].im * X[b].im);
+                                vals[c + 1] = dp_fma(X[a].im, X[b].re, -(X[a].re * X[b].im));
+                            }
+                        }
+                        // read-modify-write of the bin's component vector: 16-byte accesses kept in L2 (evict_last)
+                        const long long slot = ((long long)p * 16 + r) * NT + tid;
+#pragma unroll
+                        for (int l = 0; l < VL; ++l) {
+                            cx<double>* q = reinterpret_cast<cx<double>*>(part + (slot * VL + l) * NCP);
+#pragma unroll
+                            for (int c2 = 0; c2 < NCP / 2; ++c2) {
+                                cx<double> acc = dp2_ld_keep(q + c2, pol);
+                                double v0, v1;
+                                if constexpr (VL == 2) {
+                                    v0 = (double)(l == 0 ? vals[2 * c2].x : vals[2 * c2].y);
+                                    v1 = (double)(l == 0 ? vals[2 * c2 + 1].x : vals[2 * c2 + 1].y);
+                                } else {
+                                    v0 = vals[2 * c2];
+                                    v1 = vals[2 * c2 + 1];
+                                }
+                                acc.re += v0 * inv_s2;
+                                acc.im += v1 * inv_s2;
+                                dp2_st_keep(q + c2, acc, pol);
                             }
                         }
                     }
                 }
                 if (p == 0 && tid < 17) {
-                    const long long base = (long long)NPH * 16 * NT * VL + 2 * tid;
+                    const long long base = ((long long)NPH * 16 * NT * VL + 2 * tid) * NCP;  // slot-major: [slot][component]
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const bool dc = (tid == 0 && j == 0);
 #pragma unroll
                         for (int a = 0; a < NCH; ++a) {
                             const cx<S> Xa = sx[a * SX + 2 * tid + j];
-                            part[(long long)a * PARTIAL + base + j] += dc ? dcv[a] * dcv[a] : (double)cnorm2(Xa) * inv_s2;
+                            part[base + j * NCP + a] += dc ? dcv[a] * dcv[a] : (double)cnorm2(Xa) * inv_s2;
 #pragma unroll
                             for (int b = a + 1; b < NCH; ++b) {
                                 const cx<S> Xb = sx[b * SX + 2 * tid + j];
                                 const int c = NCH + 2 * pair_index(a, b);
                                 const double re = (double)Xa.re * (double)Xb.re + (double)Xa.im * (double)Xb.im;
                                 const double im = (double)Xa.im * (double)Xb.re - (double)Xa.re * (double)Xb.im;
-                                part[(long long)c * PARTIAL + base + j] += dc ? dcv[a] * dcv[b] : re * inv_s2;
-                                part[(long long)(c + 1) * PARTIAL + base + j] += dc ? 0.0 : im * inv_s2;
+                                part[base + j * NCP + c] += dc ? dcv[a] * dcv[b] : re * inv_s2;
+                                part[base + j * NCP + c + 1] += dc ? 0.0 : im * inv_s2;
                             }
                         }
                     }
@@ -190,7 +202,7 @@ template <class T, int R1, int NCH> struct DpCsdKernel {
 struct DpCsdReduceParams {
     const double* partial;
     long long partial_per_cta;
-    long long partial_per_comp;
+    int ncp;          // components per slot (padded)
     int grid;
     const int* loc;   // [nbins] natural bin k -> slot of one component
     int nbins;

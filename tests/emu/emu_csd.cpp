@@ -43,7 +43,7 @@ static void run_all(double fs, double scale, int subtract_first, const std::vect
     auto dt = dpplan2::build_tables2<T, R1>(fs, none, 0.0, 1.0);
     const std::vector<int> loc = dpplan2::partial_slot_of_bin<G>();
     const int grid = 2;
-    const long long ppc = K::PARTIAL * K::NCOMP;
+    const long long ppc = K::PARTIAL * K::NCP;
     std::vector<double> partial((size_t)grid * ppc, 0.0);
     std::vector<cx<T>> scratch((size_t)grid * K::scratch_v());
     std::vector<unsigned long long> cnt(grid, 0);
@@ -75,7 +75,7 @@ static void run_all(double fs, double scale, int subtract_first, const std::vect
     sums.assign((size_t)K::NCOMP * nbins, 0.0);
     for (int comp = 0; comp < K::NCOMP; ++comp)
         for (int k = 0; k < nbins; ++k)
-            for (int b = 0; b < grid; ++b) sums[(size_t)comp * nbins + k] += partial[(size_t)b * ppc + (size_t)comp * K::PARTIAL + loc[k]];
+            for (int b = 0; b < grid; ++b) sums[(size_t)comp * nbins + k] += partial[(size_t)b * ppc + (size_t)loc[k] * K::NCP + comp];
     count = 0;
     for (int b = 0; b < grid; ++b) count += (double)cnt[b];
 }
