@@ -239,3 +239,41 @@ def test_parallel_grouping_equals_the_single_cta_walk(window, monkeypatch):
         filt, dchi2 = T.filter_trace(x, trig._phi_td, trig._iw_matrix, trig._w_matrix)
         ot = T.find_triggers_once(dchi2, filt, T.chi2_threshold(5.0), window, trig._trigger_index_shift, fs)
         assert np.array_equal(res['parallel'][0], ot['trigger_index'])
+
+
+def test_trigger_processing_from_a_raw_adc_file(tmp_path):
+    """Continuous events stored as int16 ADC counts in the raw-binary container -> TriggerProcessing through the reader
+    interface: same triggers as the run on the host-converted float64 streams; the reader's admin columns feed
+    EventBuilder.build_event."""
+    import torch
+    from detprocess_b200.core.filterdata import FilterData
+    from detprocess_b200.io import RawBinaryReader, write_raw_binary
+    from detprocess_b200.process import TriggerProcessing
+    S = SynthSetup(16384)
+    pre, fs, n = S.nb_pretrigger, S.fs, S.nb_samples
+    L = 600_000
+    gain, off = 2.0e-11, 5.0e-9
+    ev = np.zeros((2, 1, L))
+    for e in range(2):
+        ev[e, 0] = make_continuous(L, S.template, S.psd, fs, np.random.default_rng(90 + e), pulse_rate_hz=0.0)
+        for t in 40_000 + 70_000 * np.arange(8):
+            ev[e, 0, t:t + n - pre] += 1.5e-7 * S.template[pre:]
+    adc = np.clip(np.round((ev - off) / gain), -32768, 32767).astype(np.int16)
+    base = str(tmp_path / 'cont')
+    write_raw_binary(base, adc, ['chanA'], fs, adc_gain=[gain], adc_offset=[off],
+                     admin={'event_time': [1_700_000_000, 1_700_000_010], 'series_num': [3, 3], 'event_num': [1, 2]})
+    yml = tmp_path / 'trig.yaml'
+    yml.write_text('trigger:\n    chanA:\n        run: True\n        threshold_sigma: 10\n        pileup_window_msec: 2\n')
+    fd = FilterData()
+    fd.set_psd('chanA', S.psd, sample_rate=fs)
+    fd.set_template('chanA', S.template, sample_rate=fs, pretrigger_length_samples=pre)
+    df = TriggerProcessing(RawBinaryReader(base), str(yml), filter_data=fd, verbose=False).process()
+    conv = adc.astype(np.float64) * gain + off
+    ref = TriggerProcessing({'traces': torch.from_numpy(conv), 'channels': ['chanA'], 'sample_rate': fs,
+                             'admin': [{'event_time': 1_700_000_000, 'series_num': 3, 'event_num': 1},
+                                       {'event_time': 1_700_000_010, 'series_num': 3, 'event_num': 2}]},
+                            str(yml), filter_data=fd, verbose=False).process()
+    assert len(df) == 16 and list(df['event_number']) == [1] * 8 + [2] * 8
+    assert np.array_equal(df['trigger_index'].values, ref['trigger_index'].values)
+    assert np.array_equal(df['trigger_amplitude'].values, ref['trigger_amplitude'].values)
+    assert np.array_equal(df['event_time'].values, ref['event_time'].values) and (df['series_number'] == 3).all()
