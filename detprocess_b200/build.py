@@ -42,11 +42,28 @@ def _deps():
     return out
 
 
+def _source_hash():
+    """sha256 over the contents of every source / header and the compiler flags: the library is rebuilt when what it
+    was built from changed, not when a copy of the tree shuffled the file times"""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(' '.join(NVCC_FLAGS + EXTRA_DEFS + [repr(u) for u in UNITS]).encode())
+    for path in sorted(_deps()):
+        h.update(os.path.basename(path).encode())
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stamp_path():
+    return LIB + '.stamp'
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(_stamp_path()):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    with open(_stamp_path()) as f:
+        return f.read().strip() != _source_hash()
 
 
 def _unit_deps(src, seen=None):
@@ -104,6 +121,8 @@ def build(force=False, verbose=True):
     if not ok:
         sys.stderr.write('\n'.join(log)[-8000:])
         raise RuntimeError('nvcc failed building libdetprocess_b200.so')
+    with open(_stamp_path(), 'w') as f:
+        f.write(_source_hash())
     return LIB
 
 
