@@ -92,6 +92,8 @@ struct dp_of_plan {
     // staging for dp_of1x1_batch_host
     void* stage_dev[2] = {nullptr, nullptr};
     double* stage_out[2] = {nullptr, nullptr};
+    double* stage_out_host = nullptr;  // pinned: the result rows of one call (a D2H copy into pageable memory blocks the
+    long long stage_out_host_rows = 0; // host until the chunk's kernel is done and the next chunk's H2D would not overlap it)
     long long stage_events = 0;
     int stage_dtype = -1;
     long long stage_stride = 0;
@@ -439,6 +441,7 @@ void dp_of_plan_destroy(dp_of_plan* p) {
         if (p->stage_out[i]) cudaFree(p->stage_out[i]);
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
     }
+    if (p->stage_out_host) cudaFreeHost(p->stage_out_host);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;
@@ -668,7 +671,9 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
     long long chunk = std::max<long long>(1, (256LL << 20) / (long long)ev_bytes);
     {
         const long long g = std::max(1, p->grid_max);
-        long long want = std::max<long long>(4 * g, (n_events + 7) / 8);
+        int stages = 8;
+        if (const char* e = std::getenv("DP_HOST_STAGES")) stages = std::max(1, std::atoi(e));  // development switch
+        long long want = std::max<long long>(4 * g, (n_events + stages - 1) / stages);
         want = (want + g - 1) / g * g;
         chunk = std::min(chunk, want);
     }
@@ -687,6 +692,13 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
         p->stage_dtype = in_dtype;
         p->stage_stride = row_stride;
     }
+    if (p->stage_out_host_rows < n_events) {
+        if (p->stage_out_host) cudaFreeHost(p->stage_out_host);
+        p->stage_out_host = nullptr;
+        p->stage_out_host_rows = 0;
+        DP_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->stage_out_host), sizeof(double) * (size_t)p->n_out * (size_t)n_events));
+        p->stage_out_host_rows = n_events;
+    }
     const unsigned char* src = reinterpret_cast<const unsigned char*>(traces_host);
     int k = 0;
     for (long long e0 = 0; e0 < n_events; e0 += chunk, k ^= 1) {
@@ -695,11 +707,12 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
         DP_CUDA(cudaMemcpyAsync(p->stage_dev[k], src + (size_t)e0 * ev_bytes, ev_bytes * (size_t)ne, cudaMemcpyHostToDevice, st));
         int rc = of_dispatch(p, p->stage_dev[k], in_dtype, ne, row_stride, p->stage_out[k], st, false);
         if (rc) return rc;
-        DP_CUDA(cudaMemcpyAsync(out_host + (size_t)e0 * p->n_out, p->stage_out[k], sizeof(double) * (size_t)p->n_out * (size_t)ne,
+        DP_CUDA(cudaMemcpyAsync(p->stage_out_host + (size_t)e0 * p->n_out, p->stage_out[k], sizeof(double) * (size_t)p->n_out * (size_t)ne,
                                 cudaMemcpyDeviceToHost, st));
     }
     DP_CUDA(cudaStreamSynchronize(p->streams[0]));
     DP_CUDA(cudaStreamSynchronize(p->streams[1]));
+    std::memcpy(out_host, p->stage_out_host, sizeof(double) * (size_t)p->n_out * (size_t)n_events);
     return DP_OK;
 }
 
