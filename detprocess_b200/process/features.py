@@ -247,9 +247,26 @@ class FeatureProcessing:
             writer = FeatureWriter(save_path or '.', prefix=self._processing_id or 'feature',
                                    series_name=(f'rank{rank}' if world > 1 else None), memory_limit_gb=memory_limit)
         frames = []
-        for b0 in range(lo, hi, batch_size):
+        import torch
+        dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
+        copy_stream = torch.cuda.Stream(dev)
+
+        def fetch(b0):
+            # the next batch is uploaded on a side stream while the current one is processed
             b1 = min(b0 + batch_size, hi)
-            df = self._process_batch(reader.read_batch(b0, b1), b0, b1)
+            with torch.cuda.stream(copy_stream):
+                t = reader.read_batch(b0, b1).to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return t, ev, b0, b1
+
+        nxt = fetch(lo) if lo < hi else None
+        while nxt is not None:
+            t, ev, b0, b1 = nxt
+            nxt = fetch(b1) if b1 < hi else None
+            torch.cuda.current_stream(dev).wait_event(ev)
+            t.record_stream(torch.cuda.current_stream(dev))
+            df = self._process_batch(t, b0, b1)
             if writer is not None:
                 writer.add(df)
             if lgc_output:
