@@ -24,7 +24,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# BLAS / OpenMP pools pinned to one thread per process BEFORE numpy is imported, exactly as the reference does
+# (detprocess/process/features.py:31-38): the CPU arm parallelises over processes, one per host core; a pool per
+# worker process oversubscribed the host 16-32x in round 1 (63 events/s instead of ~1000 on the same 32 cores).
+for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS', 'VECLIB_MAXIMUM_THREADS'):
+    os.environ[_v] = '1'
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -56,7 +62,6 @@ def parse():
 def _cpu_worker(args):
     """Per-event loop shaped like FeatureProcessing._process (reference features.py:533-851):
     per event clear/update/filter (processing_data.py:731-772), then one qp.OF1x1 per algorithm."""
-    os.environ.setdefault('OMP_NUM_THREADS', '1')       # the reference pins pools to 1 (features.py:31-38)
     traces, template, glitch, psd, pre = args
     from oracle.of1x1 import OFBaseOracle, OF1x1Oracle
     ofb = OFBaseOracle(FS)
@@ -103,7 +108,9 @@ def cpu_arm(n_events, steps, warmup, cores=None):
     return {'value': n_events * steps / t, 'unit': UNIT, 'cores': len(jobs), 'kind': 'port',
             'sample': f'{n_events} events/step x {steps} steps of the same C2 workload, '
                       f'CPU oracle restatement (not upstream detprocess+QETpy), per-event loop, '
-                      f'multiprocessing.Pool({len(jobs)})', 'ms_per_step': 1e3 * t / steps}
+                      f'multiprocessing.Pool({len(jobs)}), BLAS/OpenMP threads per process = '
+                      f'{os.environ.get("OPENBLAS_NUM_THREADS")}/{os.environ.get("OMP_NUM_THREADS")} (set before numpy import)',
+            'ms_per_step': 1e3 * t / steps}
 
 
 def reference_main(a):

@@ -174,7 +174,7 @@ def calc_psd_from_reader(reader, channel, cut=None, precision='f64', batch=4096,
     lo, hi = shard_range(len(reader), rank, world)
     for i0 in range(lo, hi, batch):
         i1 = min(i0 + batch, hi)
-        x = reader.to_amps(reader.read_batch(i0, i1).to(dev, non_blocking=True))[:, ci].contiguous()
+        x = reader.to_amps(reader.upload(i0, i1, dev))[:, ci].contiguous()
         est.update(x, None if cut is None else torch.as_tensor(np.asarray(cut[i0:i1]), device=dev))
     return est.finalize()
 
@@ -195,6 +195,6 @@ def calc_csd_from_reader(reader, channels, cut=None, precision='f64', batch=2048
     lo, hi = shard_range(len(reader), rank, world)
     for i0 in range(lo, hi, batch):
         i1 = min(i0 + batch, hi)
-        x = reader.to_amps(reader.read_batch(i0, i1).to(dev, non_blocking=True))[:, idx].contiguous()
+        x = reader.to_amps(reader.upload(i0, i1, dev))[:, idx].contiguous()
         est.update(x, None if cut is None else torch.as_tensor(np.asarray(cut[i0:i1]), device=dev))
     return est.finalize()

@@ -77,18 +77,23 @@ class TriggerPlan:
         if not trace.is_cuda or trace.ndim != 1:
             raise ValueError('run() takes a 1-D CUDA tensor')
         trace = trace.contiguous()
-        idx = torch.empty(max_triggers, dtype=torch.int64, device=trace.device)
-        amp = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
-        dchi2 = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
-        n = torch.zeros(1, dtype=torch.int32, device=trace.device)
-        check(lib.dp_trigger_run_raw(self._h, C.c_void_p(trace.data_ptr()), _in_dtype_of(trace), trace.shape[0], float(chi2_threshold),
-                                 int(pileup_window_samples), int(index_shift), int(bool(padding)),
-                                 C.c_void_p(idx.data_ptr()), C.c_void_p(amp.data_ptr()), C.c_void_p(dchi2.data_ptr()),
-                                 int(max_triggers), C.c_void_p(n.data_ptr()), _stream_ptr(trace.device)))
-        nt = int(n.item())
-        self.n_found = nt
-        nt = min(nt, max_triggers)
-        return idx[:nt], amp[:nt], dchi2[:nt]
+        # the reference returns EVERY trigger (oftrigger.py:996-1019): when the stream holds more groups than the output
+        # buffers the run is repeated once with buffers sized to the count the kernel reported -- never truncated
+        for attempt in range(2):
+            idx = torch.empty(max_triggers, dtype=torch.int64, device=trace.device)
+            amp = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
+            dchi2 = torch.empty(max_triggers, dtype=torch.float64, device=trace.device)
+            n = torch.zeros(1, dtype=torch.int32, device=trace.device)
+            check(lib.dp_trigger_run_raw(self._h, C.c_void_p(trace.data_ptr()), _in_dtype_of(trace), trace.shape[0], float(chi2_threshold),
+                                     int(pileup_window_samples), int(index_shift), int(bool(padding)),
+                                     C.c_void_p(idx.data_ptr()), C.c_void_p(amp.data_ptr()), C.c_void_p(dchi2.data_ptr()),
+                                     int(max_triggers), C.c_void_p(n.data_ptr()), _stream_ptr(trace.device)))
+            nt = int(n.item())
+            self.n_found = nt
+            if nt <= max_triggers:
+                return idx[:nt], amp[:nt], dchi2[:nt]
+            max_triggers = nt
+        raise RuntimeError(f'trigger count changed between two runs on the same stream ({nt} > {max_triggers})')
 
     def last_kernel_ms(self):
         a, b = C.c_float(), C.c_float()

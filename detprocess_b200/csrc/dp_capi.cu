@@ -34,6 +34,28 @@ int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+
+// Every entry point that allocates or launches runs with the plan's device current and puts the caller's device back
+// afterwards (the process-wide current device also belongs to PyTorch).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false, ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) {
+            ok = cudaSetDevice(dev) == cudaSuccess;
+            changed = ok;
+        }
+    }
+    ~DeviceGuard() {
+        if (changed && prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DP_ON_DEVICE(dev)        \
+    DeviceGuard dp_dev_guard(dev); \
+    if (!dp_dev_guard.ok) return fail(DP_ERR_CUDA, "cudaSetDevice failed")
 #define DP_CUDA(call)                                                                                  \
     do {                                                                                               \
         cudaError_t e_ = (call);                                                                       \
@@ -76,6 +98,7 @@ struct dp_of_plan {
     std::vector<void*> owned;
     const void* d_chans = nullptr;
     const void *tw1 = nullptr, *tw2 = nullptr, *twn = nullptr, *twp = nullptr, *tw3 = nullptr, *groups = nullptr;
+    const void *chunk3 = nullptr, *zones = nullptr;
     void* scratch = nullptr;
     long long scratch_per_cta = 0;
     int grid_max = 0;
@@ -155,6 +178,8 @@ template <class T> int of_finalize(dp_of_plan* p) {
         dc.wj_low = w;
         if ((rc = upload(p->owned, dt.chans[c].wj_self, &w))) return rc;
         dc.wj_self = w;
+        dc.adc_gain = c < (int)p->adc_gain.size() ? p->adc_gain[c] : 1.0;
+        dc.adc_offset = c < (int)p->adc_offset.size() ? p->adc_offset[c] : 0.0;
         dc.n_templ = (int)p->chans[c].templ.size();
         dc.n_slots = (int)p->chans[c].fits.size();
         dc.out_base = base;
@@ -251,6 +276,12 @@ template <class T> int of2_finalize(dp_of_plan* p) {
     const int2* dg;
     if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
     p->groups = dg;
+    const int* dc3;
+    if ((rc = upload(p->owned, dt.chunk3, &dc3))) return rc;
+    p->chunk3 = dc3;
+    const uint4* dzo;
+    if ((rc = upload(p->owned, dt.zones, &dzo))) return rc;
+    p->zones = dzo;
     std::vector<Dp2ChanDev<T>> cd(p->n_chan);
     p->chan_out_base.assign(p->n_chan, 0);
     int base = 0, max_templ = 1;
@@ -354,6 +385,8 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     prm.tw3 = reinterpret_cast<const cx<T>*>(p->tw3);
     prm.twn = reinterpret_cast<const cx<S>*>(p->twn);
     prm.groups = reinterpret_cast<const int2*>(p->groups);
+    prm.chunk3 = reinterpret_cast<const int*>(p->chunk3);
+    prm.zones = reinterpret_cast<const uint4*>(p->zones);
     prm.scratch = reinterpret_cast<cx<T>*>(p->scratch);
     prm.scratch_per_cta = p->scratch_per_cta;
     prm.out = out_dev;
@@ -539,7 +572,7 @@ int dp_of_plan_finalize(dp_of_plan* p, int device) {
             }
     }
     p->device = device;
-    DP_CUDA(cudaSetDevice(device));
+    DP_ON_DEVICE(device);
     if (p->precision == DP_PREC_F32) {
         // power-of-two pre-scale so fp32 sees O(1) samples; exact, undone in the tables
         const double rms = std::sqrt(std::max(jsum / std::max<long long>(jn, 1) * p->fs, 1e-300));
@@ -614,6 +647,7 @@ int dp_of_plan_get_norm(const dp_of_plan* p, int chan, int ti, double* norm) {
 int dp_of1x1_batch(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride,
                    double* out_dev, void* stream) {
     if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    DP_ON_DEVICE(p->device);
     if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
     if (n_events == 0) return DP_OK;
     if (!traces_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
@@ -629,6 +663,7 @@ int dp_of1x1_batch(dp_of_plan* p, const void* traces_dev, int in_dtype, long lon
 int dp_of1x1_windows(dp_of_plan* p, const double* stream_dev, long long n_stream_samples, const long long* start_index_dev,
                      long long n_events, double* out_dev, void* stream) {
     if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    DP_ON_DEVICE(p->device);
     if (!p->v2_r1) return fail(DP_ERR_UNSUPPORTED, "window mode needs nb_samples 16384, 32768 or 65536");
     if (p->n_chan != 1) return fail(DP_ERR_UNSUPPORTED, "window mode is single channel");
     if (n_events < 0 || n_stream_samples < 0) return fail(DP_ERR_INVALID, "negative size");
@@ -662,7 +697,7 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
     if (!traces_host || !out_host) return fail(DP_ERR_INVALID, "null buffer");
     if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
     if (row_stride < p->N || (row_stride & 1)) return fail(DP_ERR_INVALID, "row_stride must be even and >= nb_samples");
-    DP_CUDA(cudaSetDevice(p->device));
+    DP_ON_DEVICE(p->device);
     const size_t esz = in_dtype == DP_IN_F64 ? 8 : (in_dtype == DP_IN_F32 ? 4 : 2);
     const size_t ev_bytes = (size_t)p->n_chan * (size_t)row_stride * esz;
     // chunk: <= 256 MiB of traces per stage and about eight stages per call (the copy of one overlaps the kernel of
@@ -792,7 +827,7 @@ int dp_reduce_plan_finalize(dp_reduce_plan* p, int device) {
         return fail(DP_ERR_INVALID, e.what());
     }
     p->device = device;
-    DP_CUDA(cudaSetDevice(device));
+    DP_ON_DEVICE(device);
     int rc;
     if ((rc = upload(p->owned, p->plan.chans, &p->d_chans))) return rc;
     if ((rc = upload(p->owned, p->plan.leaves, &p->d_leaves))) return rc;
@@ -839,6 +874,7 @@ int dp_window_reduce_batch(dp_reduce_plan* p, const double* traces_dev, long lon
 int dp_window_reduce_batch_raw(dp_reduce_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride,
                                double* out_dev, void* stream) {
     if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    DP_ON_DEVICE(p->device);
     if (in_dtype != DP_IN_F64 && in_dtype != DP_IN_I16) return fail(DP_ERR_UNSUPPORTED, "window reductions take float64 or int16 traces");
     if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
     if (n_events == 0 || p->plan.n_out == 0) return DP_OK;
@@ -1035,7 +1071,7 @@ int dp_psd_plan_create(dp_psd_plan** plan, int nb_samples, double sample_rate, i
     p->fs = sample_rate;
     p->precision = precision;
     p->device = device;
-    DP_CUDA(cudaSetDevice(device));
+    DP_ON_DEVICE(device);
     int rc;
     if (p->v2_r1)
         rc = precision == DP_PREC_F32 ? psd2_finalize<f2>(p.get()) : psd2_finalize<double>(p.get());
@@ -1067,6 +1103,7 @@ int dp_psd_plan_set_scale(dp_psd_plan* p, double typical_rms) {
 }
 int dp_psd_reset(dp_psd_plan* p, void* stream) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
+    DP_ON_DEVICE(p->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DP_CUDA(cudaMemsetAsync(p->partial, 0, sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max, st));
     DP_CUDA(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long) * (size_t)(p->grid_max + 1), st));
@@ -1075,6 +1112,7 @@ int dp_psd_reset(dp_psd_plan* p, void* stream) {
 int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long long n_traces, long long row_stride,
                       const unsigned char* mask_dev, void* stream) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
+    DP_ON_DEVICE(p->device);
     if (n_traces < 0) return fail(DP_ERR_INVALID, "negative n_traces");
     if (n_traces == 0) return DP_OK;
     if (!traces_dev) return fail(DP_ERR_INVALID, "null buffer");
@@ -1152,6 +1190,7 @@ int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long
 }
 int dp_psd_get_sums(dp_psd_plan* p, double* sums_dev, unsigned long long* count_dev, void* stream) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
+    DP_ON_DEVICE(p->device);
     if (!sums_dev || !count_dev) return fail(DP_ERR_INVALID, "null buffer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nbins = p->N / 2 + 1;
@@ -1308,7 +1347,7 @@ int dp_trigger_plan_create(dp_trigger_plan** plan, const double* phi_td, int nb_
     p->hop = (p->F - p->lead - c) & ~1;
     p->max_samples = max_samples;
     p->max_chunks = (int)((max_samples + p->hop - 1) / p->hop);
-    DP_CUDA(cudaSetDevice(device));
+    DP_ON_DEVICE(device);
     int rc = precision == DP_PREC_F32 ? trig_tables_r1<f2>(p.get(), false) : trig_tables_r1<double>(p.get(), false);
     if (!rc) {
         const int src = precision == DP_PREC_F32 ? dp_trig_setup_p1(p->r1, device, &p->smem, &p->grid_max, &p->scratch_per_cta)
@@ -1359,7 +1398,7 @@ int dp_trigger_plan_set_scale(dp_trigger_plan* p, double typical_rms) {
     if (!(typical_rms > 0)) return fail(DP_ERR_INVALID, "typical_rms must be > 0");
     if (p->precision != DP_PREC_F32) return DP_OK;
     p->scale = std::exp2(-std::round(std::log2(typical_rms)));
-    DP_CUDA(cudaSetDevice(p->device));
+    DP_ON_DEVICE(p->device);
     return trig_tables_r1<f2>(p, true);
 }
 
@@ -1381,6 +1420,7 @@ int dp_trigger_run_raw(dp_trigger_plan* p, const void* trace_dev, int in_dtype, 
                        long long pileup_window_samples, long long index_shift, int padding, long long* trig_index_dev,
                        double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
+    DP_ON_DEVICE(p->device);
     if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
     if (!trace_dev || !trig_index_dev || !trig_amp_dev || !trig_dchi2_dev || !n_triggers_dev) return fail(DP_ERR_INVALID, "null buffer");
     if (n_samples < 2 || n_samples > p->max_samples) return fail(DP_ERR_INVALID, "n_samples out of the plan's range");
@@ -1636,7 +1676,7 @@ int dp_nxm_plan_finalize(dp_nxm_plan* p, int device) {
     if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
     if (!p->have_filter) return fail(DP_ERR_STATE, "set the templates and the csd first");
     p->device = device;
-    DP_CUDA(cudaSetDevice(device));
+    DP_ON_DEVICE(device);
     if (p->precision == DP_PREC_F32) {
         p->scale = std::exp2(-std::round(std::log2(p->rms)));
         p->subtract_first = p->ac ? 1 : 0;
@@ -1674,7 +1714,7 @@ int dp_ofnxm_batch(dp_nxm_plan* p, const double* traces_dev, long long n_events,
         return fail(DP_ERR_INVALID, "strides must be even, chan_stride >= nb_samples, event_stride >= the channels of an event");
     if ((reinterpret_cast<uintptr_t>(traces_dev) & 15) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
     if (n_events > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
-    DP_CUDA(cudaSetDevice(p->device));
+    DP_ON_DEVICE(p->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p->precision == DP_PREC_F32) return nxm_run<f2>(p, p->prm32, traces_dev, n_events, event_stride, chan_stride, out_dev, st);
     return nxm_run<double>(p, p->prm64, traces_dev, n_events, event_stride, chan_stride, out_dev, st);
@@ -1802,7 +1842,7 @@ int dp_csd_plan_create(dp_csd_plan** plan, int nb_samples, double sample_rate, i
     p->precision = precision;
     p->device = device;
     p->r1 = dpplan2::r1_of(nb_samples);
-    DP_CUDA(cudaSetDevice(device));
+    DP_ON_DEVICE(device);
     const int rc = precision == DP_PREC_F32 ? csd_finalize<f2>(p.get()) : csd_finalize<double>(p.get());
     if (rc) {
         for (void* d : p->owned) cudaFree(d);
@@ -1830,6 +1870,7 @@ int dp_csd_plan_set_scale(dp_csd_plan* p, double typical_rms) {
 }
 int dp_csd_reset(dp_csd_plan* p, void* stream) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
+    DP_ON_DEVICE(p->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DP_CUDA(cudaMemsetAsync(p->partial, 0, sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max, st));
     DP_CUDA(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long) * (size_t)(p->grid_max + 1), st));
@@ -1845,7 +1886,7 @@ int dp_csd_accumulate(dp_csd_plan* p, const double* traces_dev, long long n_even
         return fail(DP_ERR_INVALID, "strides must be even, chan_stride >= nb_samples, event_stride >= the channels of an event");
     if ((reinterpret_cast<uintptr_t>(traces_dev) & 15) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
     if (n_events > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
-    DP_CUDA(cudaSetDevice(p->device));
+    DP_ON_DEVICE(p->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DP_CUDA(cudaEventRecord(p->ev0, st));
     const int rc = p->precision == DP_PREC_F32 ? csd_launch<f2>(p, traces_dev, n_events, event_stride, chan_stride, mask_dev, st)
@@ -1857,6 +1898,7 @@ int dp_csd_accumulate(dp_csd_plan* p, const double* traces_dev, long long n_even
 }
 int dp_csd_get_sums(dp_csd_plan* p, double* sums_dev, unsigned long long* count_dev, void* stream) {
     if (!p) return fail(DP_ERR_INVALID, "null plan");
+    DP_ON_DEVICE(p->device);
     if (!sums_dev || !count_dev) return fail(DP_ERR_INVALID, "null buffer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int nbins = p->N / 2 + 1, ncomp = p->n * p->n;

@@ -198,6 +198,8 @@ template <class T> struct Dp2Params {
     const cx<T>* tw3;      // [GV]   exp(-2 pi i n4 / 256)
     const cx<S>* twn;      // [NPH][NT] exp(-2 pi i k(own group, 0) / N)
     const int2* groups;    // [NPH][NT] (own / A group, other / B group)
+    const int* chunk3;     // [NPH][NT] phase-local 256-element chunk (b*16 + k2) the thread transforms in passes 3 / 3'
+    const uint4* zones;    // [NPH][NW] byte offsets (into the FFT buffer) of the warp's four 2048-byte landing pieces
     cx<T>* scratch;        // [grid][scratch_per_cta]
     long long scratch_per_cta;
     double* out;
@@ -265,6 +267,97 @@ template <class V> DP_DEV V dp2_ld_keep(const V* ptr, unsigned long long pol) {
     *reinterpret_cast<uint4*>(&v) = u;
     return v;
 #endif
+}
+
+
+
+// 16-byte read-only load of a table row that is used once per event (filter rows that were not staged): no L1
+// allocation, so that the small per-pass tables (twiddles, group ids) keep the ~60 KB of L1 the CTA leaves
+template <class V> DP_DEV V dp2_ld_stream(const V* ptr) {
+    static_assert(sizeof(V) == 16, "table vectors are 16 bytes");
+#if defined(DP_HOST_EMU) || defined(DP2_TAB_ALLOC)
+    return dp_ldg(ptr);
+#else
+    uint4 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(ptr));
+    V v;
+    *reinterpret_cast<uint4*>(&v) = u;
+    return v;
+#endif
+}
+
+// ---- per-warp asynchronous staging (TMA bulk copies global -> shared, completion on an mbarrier).
+// The filter / chi0-weight tables of the point-wise stage (and the X column of multi-template plans) are
+// fetched by ONE lane per warp into shared memory the warp owns at that moment -- the group rows it has just
+// emptied into registers (pass 4) plus a small private area -- while the warp computes its radix-16
+// butterflies; the loads cost no registers, no issue slots and no scoreboard stall (round 1: 19 % of all
+// warp-time in the point-wise stage was `long_scoreboard` on these tables).
+#define DP2_PIECE 2048  // bytes per bulk copy
+struct alignas(8) Dp2Mbar {
+    unsigned long long v;
+};
+DP_DEV void dp2_mbar_init(Dp2Mbar* bar) {
+#ifndef DP_HOST_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+#else
+    bar->v = 0;
+#endif
+}
+DP_DEV void dp2_mbar_init_fence() {
+#ifndef DP_HOST_EMU
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+}
+// generic-proxy writes (X column stores) -> visible to later bulk copies of this CTA
+DP_DEV void dp2_fence_async() {
+#ifndef DP_HOST_EMU
+    asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+}
+// one lane: announce `bytes` on the warp's barrier (its single arrival of this round)
+DP_DEV void dp2_stage_begin(Dp2Mbar* bar, unsigned bytes) {
+#ifndef DP_HOST_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+#else
+    (void)bar;
+    (void)bytes;
+#endif
+}
+DP_DEV void dp2_stage_copy(void* dst_smem, const void* src_global, unsigned bytes, Dp2Mbar* bar) {
+#ifndef DP_HOST_EMU
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src_global),
+                 "r"(bytes), "r"(a)
+                 : "memory");
+#else
+    (void)bar;
+    std::memcpy(dst_smem, src_global, bytes);
+#endif
+}
+// all lanes: wait for the round with parity `par` (emulation: the issuing lane copied synchronously)
+DP_DEV void dp2_stage_wait(Dp2Mbar* bar, unsigned par) {
+#ifndef DP_HOST_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "DP2_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra DP2_WAIT_%=;\n\t}" ::"r"(a),
+        "r"(par)
+        : "memory");
+#else
+    (void)bar;
+    (void)par;
+    __syncwarp();
+#endif
+}
+// exchange with the partner lane (lane ^ 1)
+DP_DEV cx<double> dp2_swap1(cx<double> v) {
+    return cx<double>{__shfl_xor_sync(0xffffffffu, v.re, 1), __shfl_xor_sync(0xffffffffu, v.im, 1)};
 }
 
 // streaming policy for the LAST read of a trace (evict_first) / earlier reads (evict_normal)
@@ -370,6 +463,30 @@ template <class S> DP_DEV void dp2_consider(DpBest<S>& b, S kabs, S v, int idx) 
         b.idx = idx;
     }
 }
+
+
+// exp(+2 pi i n / 16): output-row rotation of the pruned pass 2' (Dp2Core::inv_2_rows)
+#ifdef DP_HOST_EMU
+static const double dp2_w16_tab[16][2] = {
+#else
+static __constant__ double dp2_w16_tab[16][2] = {
+#endif
+    {1.0, 0.0},
+    {0.92387953251128675613, 0.38268343236508977173},
+    {0.70710678118654752440, 0.70710678118654752440},
+    {0.38268343236508977173, 0.92387953251128675613},
+    {0.0, 1.0},
+    {-0.38268343236508977173, 0.92387953251128675613},
+    {-0.70710678118654752440, 0.70710678118654752440},
+    {-0.92387953251128675613, 0.38268343236508977173},
+    {-1.0, 0.0},
+    {-0.92387953251128675613, -0.38268343236508977173},
+    {-0.70710678118654752440, -0.70710678118654752440},
+    {-0.38268343236508977173, -0.92387953251128675613},
+    {0.0, -1.0},
+    {0.38268343236508977173, -0.92387953251128675613},
+    {0.70710678118654752440, -0.70710678118654752440},
+    {0.92387953251128675613, -0.38268343236508977173}};
 
 // ======================================================================== core
 template <class T, int R1, int IN> struct Dp2Core {
@@ -528,6 +645,84 @@ template <class T, int R1, int IN> struct Dp2Core {
             dp_dft<16, +1, T>::run(z);
         }
     }
+
+    // ---- warp-local variant of passes 2..4 / 4'..2' (OF kernel).  Pass 3 of a 256-element chunk (fixed block,
+    // k2) is done by the warp that owns the chunk's 16 groups in pass 4 -- a warp owns whole chunks: a chunk
+    // and its mirror chunk -- so pass 3 -> pass 4 and pass 4' -> pass 3' only need __syncwarp(), and between the
+    // set barrier after pass 2 and the one before pass 2' every warp runs on its own (pass 3, pass 4, the
+    // point-wise stage with its staged tables, pass 4', pass 3'): the warps drift apart and overlap each
+    // other's shared-memory, FP and wait phases instead of meeting at a barrier after every pass.
+    // `chunk` = phase-local chunk id (b*16 + k2) of this thread's sub-warp, from Dp2Params::chunk3.
+    static DP_DEV void fwd_2(V* buf, const V* DP_RESTRICT tw2, V (&z)[16]) {
+        const int tid = threadIdx.x;
+        const int b = tid / CV, cc = tid % CV;
+        V* pb = buf + G::phys(b * VPB + cc);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) z[n] = pb[n * PC];
+        dp_dft<16, -1, T>::run(z);
+        dp_twiddle<16, false, T>(z, dp_ldg(tw2 + cc));
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pb[k * PC] = z[k];
+    }
+    static DP_DEV void fwd_3w(V* buf, const V* DP_RESTRICT tw3, int chunk, V (&z)[16]) {
+        const int q = threadIdx.x % GV;
+        V* pb = buf + G::phys(chunk * CV + q);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) z[n] = pb[n * PG];
+        dp_dft<16, -1, T>::run(z);
+        dp_twiddle<16, false, T>(z, dp_ldg(tw3 + q));
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pb[k * PG] = z[k];
+    }
+    static DP_DEV void inv_3w(V* buf, const V* DP_RESTRICT tw3, int chunk, V (&z)[16]) {
+        const int q = threadIdx.x % GV;
+        V* pb = buf + G::phys(chunk * CV + q);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) z[k] = pb[k * PG];
+        dp_twiddle<16, true, T>(z, dp_ldg(tw3 + q));
+        dp_dft<16, +1, T>::run(z);
+#pragma unroll
+        for (int n = 0; n < 16; ++n) pb[n * PG] = z[n];
+    }
+    static DP_DEV void inv_2(const V* buf, const V* DP_RESTRICT tw2, V (&z)[16]) {
+        const int tid = threadIdx.x;
+        const int b = tid / CV, cc = tid % CV;
+        const V* pb = buf + G::phys(b * VPB + cc);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) z[k] = pb[k * PC];
+        dp_twiddle<16, true, T>(z, dp_ldg(tw2 + cc));
+        dp_dft<16, +1, T>::run(z);
+    }
+    // pass 2' for the one or two output rows n2 a narrow delay window needs (rowmask, CTA-uniform): out[n] = sum_k in[k] u^k with
+    // u = conj(w) exp(2 pi i n / 16), evaluated by Horner's rule straight from the 16 inputs (4 FMA per step instead of
+    // the twiddle powers + radix-16 butterflies of the full pass), and stored where the full pass would have put it:
+    // in place (last phase) or in the parked block results (PARK).
+    template <bool PARK> static DP_DEV void inv_2_rows(V* buf, V* scr, int p, const V* DP_RESTRICT tw2, unsigned rowmask) {
+        const int tid = threadIdx.x;
+        const int b = tid / CV, cc = tid % CV;
+        V* pb = buf + G::phys(b * VPB + cc);
+        V in[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) in[k] = pb[k * PC];
+        V w = dp_ldg(tw2 + cc);
+        w.im = -w.im;
+        [[maybe_unused]] V* dst = scr + (long long)(p * NB + b) * VPB + cc;
+        [[maybe_unused]] const unsigned long long pol = dp2_policy_keep();
+#pragma unroll 1
+        for (unsigned m = rowmask; m != 0; m &= m - 1) {
+            const int n = __ffs((int)m) - 1;
+            const T orr = (T)(S)dp2_w16_tab[n][0], oi = (T)(S)dp2_w16_tab[n][1];
+            const V u = V{dp_fma(w.re, orr, -(w.im * oi)), dp_fma(w.re, oi, w.im * orr)};
+            V acc = in[15];
+#pragma unroll
+            for (int k = 14; k >= 0; --k)
+                acc = V{dp_fma(acc.re, u.re, dp_fma(-acc.im, u.im, in[k].re)), dp_fma(acc.re, u.im, dp_fma(acc.im, u.re, in[k].im))};
+            if constexpr (PARK)
+                dp2_st_keep(dst + n * CV, acc, pol);
+            else
+                pb[n * PC] = acc;
+        }
+    }
     // pass-2' outputs -> smem (own positions, in place)
     static DP_DEV void store_pass2(V* buf, const V (&z)[16]) {
         const int tid = threadIdx.x;
@@ -545,26 +740,64 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
         for (int n = 0; n < 16; ++n) dp2_st_keep(dst + n * CV, z[n], pol);
     }
+    // the same two stores restricted to the rows n2 (256 consecutive complex points each) that hold a candidate delay of
+    // some fit (CTA-uniform mask; a +-500-sample window needs 2 of the 16 rows): the other rows are never read by pass 1'
+    static DP_DEV void store_pass2(V* buf, const V (&z)[16], unsigned rowmask) {
+        const int tid = threadIdx.x;
+        const int b = tid / CV, cc = tid % CV;
+        V* pb = buf + G::phys(b * VPB + cc);
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+            if (rowmask & (1u << n)) pb[n * PC] = z[n];
+    }
+    static DP_DEV void park_pass2(V* scr, int p, const V (&z)[16], unsigned rowmask) {
+        const int tid = threadIdx.x;
+        const int b = tid / CV, cc = tid % CV;
+        V* dst = scr + (long long)(p * NB + b) * VPB + cc;
+        const unsigned long long pol = dp2_policy_keep();
+#pragma unroll
+        for (int n = 0; n < 16; ++n)
+            if (rowmask & (1u << n)) dp2_st_keep(dst + n * CV, z[n], pol);
+    }
+    // rows of the complex points [nlo, nhi] (cyclic in the 4096-point block)
+    static DP_DEV unsigned rows_of(int nlo, int nhi) {
+        if (nhi < nlo) return 0u;
+        if (nhi - nlo >= 4095) return 0xffffu;
+        const int ra = (nlo & 4095) >> 8, rb = (nhi & 4095) >> 8;
+        const unsigned upto_b = (2u << rb) - 1u, from_a = 0xffffu & ~((1u << ra) - 1u);
+        return ((nlo & 4095) <= (nhi & 4095)) ? (upto_b & from_a) : (upto_b | from_a);
+    }
     // ---- pass 1' for columns [i0, i0 + GC): y[i*R1 + n1] = c'[n1*4096 + VL*(tid + (i0+i)*NT) + lane].
     // Only columns that hold a complex point n in [nlo, nhi] are computed (constrained delay windows
     // touch ~1/8 of the columns); the others keep stale registers, which no window scan selects.
     // Returns the mask of the columns it computed.
-    static DP_DEV unsigned inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1], int nlo = 0,
-                                     int nhi = 0x7fffffff) {
+    // columns (bit j = column tid + j*NT, j < NC) of this thread that hold a complex point of [nlo, nhi]: a column holds
+    // the points n1*4096 + m, m = VL*c .. VL*c + VL - 1, of every n1, so it is needed when m falls into the cyclic
+    // interval [nlo, nhi] mod 4096 (CTA-uniform bounds, two compares per column)
+    static DP_DEV unsigned need_cols(int nlo, int nhi) {
+        const int tid = threadIdx.x;
+        if (nhi < nlo) return 0u;
+        if (nhi - nlo >= 4095) return (1u << NC) - 1u;
+        const int ma = nlo & 4095, mb = nhi & 4095;
+        const bool wrap = ma > mb;
+        unsigned m = 0;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const int c = tid + j * NT;
+            const int m0 = VL * c, m1 = VL * c + VL - 1;
+            const bool need = wrap ? (m1 >= ma || m0 <= mb) : (m1 >= ma && m0 <= mb);
+            m |= need ? (1u << j) : 0u;
+        }
+        return m;
+    }
+    // pass 1' of the columns i0 + i, i < GC, whose bit i is set in `cols`; returns `cols`
+    static DP_DEV unsigned inv_pass1m(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1], unsigned cols) {
         const int tid = threadIdx.x;
         constexpr int LP = NPH - 1;
-        unsigned computed = 0;
 #pragma unroll
         for (int i = 0; i < G::GC; ++i) {
+            if (!(cols & (1u << i))) continue;
             const int c = tid + (i0 + i) * NT;
-            bool need = false;
-#pragma unroll
-            for (int n = 0; n < R1; ++n) {
-                const int a = n * 4096 + VL * c;
-                need = need || (a + VL - 1 >= nlo && a <= nhi);
-            }
-            if (!need) continue;
-            computed |= 1u << i;
             V u[R1];
 #pragma unroll
             for (int b = 0; b < NB; ++b) u[G::k1_of(LP, b)] = buf[G::phys(c) + b * PB];
@@ -582,7 +815,11 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
             for (int n = 0; n < R1; ++n) y[i * R1 + n] = u[n];
         }
-        return computed;
+        return cols;
+    }
+    static DP_DEV unsigned inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1], int nlo = 0,
+                                     int nhi = 0x7fffffff) {
+        return inv_pass1m(buf, scr, tw1, i0, y, (need_cols(nlo, nhi) >> i0) & ((1u << G::GC) - 1u));
     }
 };
 
@@ -673,14 +910,27 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
     static constexpr int BEST_ELEMS = DP_MAX_TSLOTS * 32;
     static constexpr int SP_ELEMS = 32 + 34 + 2;  // self-paired group values, X of the 17 self pairs, chi0 (as one cx slot)
     static constexpr int CH_WORDS = (int)(sizeof(Dp2ChanDev<T>) / 4);  // channel descriptor, 32-bit words
+    // staged tables: per warp four 2048-byte pieces inside the group rows it owns (its chunks, Dp2Params::zones) and
+    // NSP private pieces.  Round A (fused untangle + first template): wj rows 0..15 | phi rows 0..7 in the owned rows,
+    // phi rows 8.. in the private pieces; round B (further templates): X rows 0..15 in the owned rows, phi rows 0.. in
+    // the private pieces.  Rows that do not fit are read through the read-only path when they are used.
+#ifndef DP2_NSP
+#define DP2_NSP 0
+#endif
+    static constexpr int NSP = (NT > 256) ? DP2_NSP : (DP2_NSP > 1 ? 1 : DP2_NSP);  // two 256-thread CTAs per SM leave room for one
+    static constexpr int PHI_ROWS_A = 8 + 4 * NSP, PHI_ROWS_B = 4 * NSP;
+    static constexpr unsigned BYTES_A = 4 * DP2_PIECE + NSP * DP2_PIECE, BYTES_B = 4 * DP2_PIECE + NSP * DP2_PIECE;
+    static_assert(sizeof(T) == 8 && sizeof(V) == 16, "table rows are 256 / 512 bytes per warp");
     static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (DP_NLOW_MAX + SP_ELEMS) +
                                          2 * (sizeof(double) * RED_DOUBLES + sizeof(DpBest<S>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS) +
-                                         2 * sizeof(int) * CH_WORDS + 64;
-    // scratch per CTA (V units): X spill [16][NT] (multi-template) + per template the parked
-    // block results of the non-final phases [(NPH-1)*NB][VPB]
+                                         2 * sizeof(int) * CH_WORDS + 64 + (size_t)NW * NSP * DP2_PIECE + sizeof(Dp2Mbar) * NW + 16;
+    // scratch per CTA (V units): X spill [NW][16][32] (multi-template; warp-sliced so that a warp's column is one
+    // contiguous 8 KB block) + per template the parked block results of the non-final phases [(NPH-1)*NB][VPB]
     static constexpr long long SCR_X = (long long)16 * NT;
     static constexpr long long SCR_PARK = (long long)(NPH - 1) * NB * VPB;
     static DP_HD long long scratch_v(int n_templ) { return SCR_X + SCR_PARK * n_templ; }
+    // first element of warp w's rows in a thread-order table [NPH][NW][16][32]
+    static DP_HD long long tab_block(int p, int w) { return ((long long)(p * NW + w) * 16) * 32; }
 
     struct Smem {
         V* buf;
@@ -691,6 +941,8 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         int* slot0;
         int* chs0;  // [2][CH_WORDS] this event's channel descriptor (table pointers are read from
                     // shared memory, not through a dependent global load)
+        unsigned char* spare;  // [NW][NSP][2048] private landing pieces
+        Dp2Mbar* mbar;         // [NW]
         DP_DEV double* red(int par) const { return red0 + par * RED_DOUBLES; }
         DP_DEV DpBest<S>* best(int par) const { return best0 + par * BEST_ELEMS; }
         DP_DEV int* slot_id(int par) const { return slot0 + par * DP_MAX_TSLOTS; }
@@ -704,6 +956,10 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         s.best0 = reinterpret_cast<DpBest<S>*>(s.red0 + 2 * RED_DOUBLES);
         s.slot0 = reinterpret_cast<int*>(s.best0 + 2 * BEST_ELEMS);
         s.chs0 = s.slot0 + 2 * DP_MAX_TSLOTS + ((2 * DP_MAX_TSLOTS) & 3 ? 4 - ((2 * DP_MAX_TSLOTS) & 3) : 0);
+        unsigned char* e = reinterpret_cast<unsigned char*>(s.chs0 + 2 * CH_WORDS);
+        e += (16 - (reinterpret_cast<unsigned long long>(e) & 15)) & 15;
+        s.spare = e;
+        s.mbar = reinterpret_cast<Dp2Mbar*>(e + (size_t)NW * NSP * DP2_PIECE);
         return s;
     }
 
@@ -732,6 +988,123 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         }
     }
 
+    // ---- this lane's view of the warp's staged tables: byte offsets from the start of the dynamic shared memory
+    // (32-bit each; the lane's own offset folded in)
+    struct Staged {
+        unsigned char* base;
+        unsigned v[4];      // pieces inside the warp's own group rows (valid between pass 4 and pass 4')
+        unsigned s[NSP > 0 ? NSP : 1];    // private pieces
+        const V* phi_g;     // the same filter rows in global memory (rows that were not staged), this lane
+        template <class Q> DP_DEV Q at(unsigned off) const { return *reinterpret_cast<const Q*>(base + off); }
+        // round A
+        DP_DEV T wj(int e) const { return at<T>(v[e >> 3] + (e & 7) * 256); }
+        DP_DEV V phi_a(int e) const {
+            if (e < 8) return at<V>(v[2 + (e >> 2)] + (e & 3) * 512);
+            if (e < PHI_ROWS_A) return at<V>(s[(e - 8) >> 2] + ((e - 8) & 3) * 512);
+            return dp2_ld_stream(phi_g + e * 32);
+        }
+        // round B
+        DP_DEV V x(int e) const { return at<V>(v[e >> 2] + (e & 3) * 512); }
+        DP_DEV V phi_b(int e) const {
+            if (e < PHI_ROWS_B) return at<V>(s[e >> 2] + (e & 3) * 512);
+            return dp2_ld_stream(phi_g + e * 32);
+        }
+    };
+    // lane offsets folded in: wj pieces (round A, v[0], v[1]) are 8-byte rows, everything else 16-byte rows
+    static DP_DEV Staged staged_view(unsigned char* smem_raw, uint4 zo, unsigned spoff, int lane, bool round_a, const V* phi_lane) {
+        Staged t;
+        const unsigned l16 = lane * 16, l8 = lane * 8;
+        t.base = smem_raw;
+        t.v[0] = zo.x + (round_a ? l8 : l16);
+        t.v[1] = zo.y + (round_a ? l8 : l16);
+        t.v[2] = zo.z + l16;
+        t.v[3] = zo.w + l16;
+#pragma unroll
+        for (int j = 0; j < NSP; ++j) t.s[j] = spoff + j * DP2_PIECE + l16;
+        t.phi_g = phi_lane;
+        return t;
+    }
+    // one lane: round A = wj block (4096 B) + the first PHI_ROWS_A rows of the phi block
+    static DP_DEV void issue_a(Dp2Mbar* bar, unsigned char* bufb, uint4 zo, unsigned char* spw, const T* wj_blk, const V* phi_blk) {
+        const unsigned char* w = reinterpret_cast<const unsigned char*>(wj_blk);
+        const unsigned char* f = reinterpret_cast<const unsigned char*>(phi_blk);
+        dp2_stage_begin(bar, BYTES_A);
+        dp2_stage_copy(bufb + zo.x, w, DP2_PIECE, bar);
+        dp2_stage_copy(bufb + zo.y, w + DP2_PIECE, DP2_PIECE, bar);
+        dp2_stage_copy(bufb + zo.z, f, DP2_PIECE, bar);
+        dp2_stage_copy(bufb + zo.w, f + DP2_PIECE, DP2_PIECE, bar);
+#pragma unroll
+        for (int j = 0; j < NSP; ++j) dp2_stage_copy(spw + j * DP2_PIECE, f + (2 + j) * DP2_PIECE, DP2_PIECE, bar);
+    }
+    // one lane: round B = the warp's X column (8192 B) + the first PHI_ROWS_B rows of the phi block
+    static DP_DEV void issue_b(Dp2Mbar* bar, unsigned char* bufb, uint4 zo, unsigned char* spw, const V* x_blk, const V* phi_blk) {
+        const unsigned char* x = reinterpret_cast<const unsigned char*>(x_blk);
+        const unsigned char* f = reinterpret_cast<const unsigned char*>(phi_blk);
+        dp2_stage_begin(bar, BYTES_B);
+        dp2_stage_copy(bufb + zo.x, x, DP2_PIECE, bar);
+        dp2_stage_copy(bufb + zo.y, x + DP2_PIECE, DP2_PIECE, bar);
+        dp2_stage_copy(bufb + zo.z, x + 2 * DP2_PIECE, DP2_PIECE, bar);
+        dp2_stage_copy(bufb + zo.w, x + 3 * DP2_PIECE, DP2_PIECE, bar);
+#pragma unroll
+        for (int j = 0; j < NSP; ++j) dp2_stage_copy(spw + j * DP2_PIECE, f + j * DP2_PIECE, DP2_PIECE, bar);
+    }
+
+    // ---- packed fp32 (VL == 2) point-wise stage on whole register arrays: z[r] lanes = (group A, group B) elements.
+    // forward half: z (pass-4 outputs) -> 2*X at the thread's bins, in place; returns the chi0 partial sum
+    static DP_DEV S untangle_st(V (&z)[16], const Staged& tb, cx<S> wn) {
+        S chi = (S)0;
+        if constexpr (VL == 2) {
+#define DP2_XP(r)                                                                         \
+    {                                                                                     \
+        cx<S> Xk, Xm;                                                                     \
+        dp_untangle(dp2_lane0(z[r]), dp2_lane1(z[15 - r]), cmul(wn, dp_w64<S, 2 * r, -1>()), Xk, Xm); \
+        dp2_set0(z[r], Xk);                                                               \
+        dp2_set1(z[15 - r], Xm);                                                          \
+    }
+            DP2_XP(0) DP2_XP(1) DP2_XP(2) DP2_XP(3) DP2_XP(4) DP2_XP(5) DP2_XP(6) DP2_XP(7)
+            DP2_XP(8) DP2_XP(9) DP2_XP(10) DP2_XP(11) DP2_XP(12) DP2_XP(13) DP2_XP(14) DP2_XP(15)
+#undef DP2_XP
+            f2 acc = f2(0.0f);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc = dp_fma(tb.wj(r), cnorm2(z[r]), acc);
+            chi = acc.x + acc.y;
+        }
+        return chi;
+    }
+    // filter multiply + inverse untangle, in place: z X -> Z' (group values for pass 4'); ROUND_A selects the table view
+    template <bool ROUND_A> static DP_DEV void filter_st(V (&z)[16], const Staged& tb, cx<S> wn) {
+        if constexpr (VL == 2) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) z[r] = cmul(ROUND_A ? tb.phi_a(r) : tb.phi_b(r), z[r]);
+#define DP2_FP(r)                                                                          \
+    {                                                                                      \
+        cx<S> Ck, Cm;                                                                      \
+        dp_retangle(dp2_lane0(z[r]), dp2_lane1(z[15 - r]), cmul(wn, dp_w64<S, 2 * r, -1>()), Ck, Cm); \
+        dp2_set0(z[r], Ck);                                                                \
+        dp2_set1(z[15 - r], Cm);                                                           \
+    }
+            DP2_FP(0) DP2_FP(1) DP2_FP(2) DP2_FP(3) DP2_FP(4) DP2_FP(5) DP2_FP(6) DP2_FP(7)
+            DP2_FP(8) DP2_FP(9) DP2_FP(10) DP2_FP(11) DP2_FP(12) DP2_FP(13) DP2_FP(14) DP2_FP(15)
+#undef DP2_FP
+        }
+    }
+    // ---- fp64 (VL == 1): a thread owns one group (elements 0..15), its partner lane (lane ^ 1) the mirror group;
+    // pair r = (own[r], partner[15 - r]), r < 8.  The partner's element and the partner's half of the result travel
+    // by warp shuffle, so the stage touches shared memory only for the staged tables.
+    // filter + inverse untangle of pair r: C'[own r] -> z[r], C'[partner 15 - r] -> the partner's z[15 - r]
+    static DP_DEV void pair_filter(V (&z)[16], int r, cx<S> Xk, cx<S> Xm, V phk, V phm, cx<S> w) {
+        if constexpr (VL == 1) {
+            const cx<S> Fk = cmul(phk, Xk);
+            const cx<S> Fm = cmul(phm, Xm);
+            cx<S> Ck, Cm;
+            dp_retangle(Fk, Fm, w, Ck, Cm);
+            z[r] = Ck;
+            z[15 - r] = dp2_swap1(Cm);
+        }
+    }
+
+    // ---- point-wise helpers of the PSD / CSD / NxM / trigger kernels (tables in [phase][16][NT] order read through the
+    // read-only path, partner exchange through the idle group rows); the OF kernel itself uses the staged variants above
     // ---- point-wise stage, forward half: z (pass-4 outputs) -> 2*X at the thread's bins.
     // VL == 2: z[r] lanes = X at (bin of A[r], bin of B[r]).
     // (packed fp32 only; fp64 goes pair by pair through pw_untangle / pw_filter_pair below)
@@ -829,8 +1202,8 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         for (int j = 0; j < 8; ++j) z[8 + j] = buf[Gown * 17 + 8 + j];  // written by the partner
     }
 
-    // MULTI: some channel has more than one template (X goes through the thread-private scratch
-    // column so that nothing is live across the template loop)
+    // MULTI: some channel has more than one template (X goes through the warp's scratch column and comes back by
+    // bulk copy for the second and later templates)
     template <bool MULTI> static DP_DEV void run(const Dp2Params<T>& prm, unsigned char* smem_raw);
 };
 
@@ -838,16 +1211,25 @@ template <class T, int R1, int IN>
 template <bool MULTI>
 DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* smem_raw) {
     const Smem sm = carve(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
-    V* scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;  // [16][NT] X of the current phase (multi-template)
+    V* scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;  // [NW][16][32] X of the current phase (multi-template)
     V* scr_park = scr_x + SCR_X;                                           // [n_templ][(NPH-1)*NB][VPB] parked block results
+    V* const xs = scr_x + (long long)warp * 16 * 32 + lane;                // this lane's X column (rows 32 apart)
     // special threads: the self-paired groups (0,0,0) and (0,0,8) of block 0 (phase 0)
     constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
     int par = 0;
     int evpar = 0;
     cx<S>* const sx = sm.sp + 32;                                        // [17][2] X of the self pairs
     double* const chi0_keep = reinterpret_cast<double*>(sm.sp + 32 + 34);  // chi0 of the current event (thread 0)
+    unsigned char* const bufb = reinterpret_cast<unsigned char*>(sm.buf);
+    unsigned char* const spw = sm.spare + (size_t)warp * NSP * DP2_PIECE;
+    const unsigned spoff = (unsigned)(spw - bufb);  // the FFT buffer starts the dynamic shared memory
+    Dp2Mbar* const bar = sm.mbar + warp;
+    unsigned spar = 0;  // parity of the warp's next staging round
+    if (lane == 0) dp2_mbar_init(bar);
+    dp2_mbar_init_fence();
+    __syncthreads();
 
     for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
         const int chan = row % prm.n_chan;
@@ -887,18 +1269,25 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
         for (int p = 0; p < NPH; ++p) {
             // ---------------- forward of phase p: X at the phase's bins, in registers ----------
             V z[16];
-            V zm[VL == 1 ? 8 : 1];
             const int2 gg = prm.groups[p * NT + tid];
+            const int chunk = prm.chunk3[p * NT + tid];
             const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
             const bool special = (p == 0) && (tid < NSPECIAL);
             Core::pass1_any(p, xrow, x0, xsc, sm.buf, prm.tw1);
             __syncthreads();
 #ifndef DP_HOST_EMU
             // every second block starts its passes a little late so that the block sets' LDS / FP / STS phases
-            // interleave instead of hitting the same pipe at the same time (+3 % measured, 600 ns; 0 disables)
+            // interleave instead of hitting the same pipe at the same time (0 disables)
             if (prm.skew_ns > 0 && ((tid / G::CV) & 1)) __nanosleep(prm.skew_ns);
 #endif
-            Core::fwd_234(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+            Core::fwd_2(sm.buf, prm.tw2, z);
+            dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 3 reads the chunks of the warp's block set
+            Core::fwd_3w(sm.buf, prm.tw3, chunk, z);
+            __syncwarp();  // pass 4 reads the warp's own chunks
+            Core::load_groups(sm.buf, gg.x, gg.y, z);
+            __syncwarp();  // the group rows of this warp are now free: land the point-wise tables in them
+            if (lane == 0) issue_a(bar, bufb, prm.zones[p * NW + warp], spw, ch.wj + tab_block(p, warp), ch.templ[0].phi + tab_block(p, warp));
+            dp_dft<16, -1, T>::run(z);
             if (p == 0 && tid < 32) {
                 // self-paired groups -> 17 lanes of warp 0
                 if constexpr (VL == 2) {
@@ -929,89 +1318,74 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 }
                 __syncwarp();
             }
-            const T* wjp = ch.wj + (long long)p * 16 * NT;
-            [[maybe_unused]] int Gp = 0;  // partner's group (fp64)
-            if constexpr (VL == 2) {
-                chi += untangle_all(sm.buf, z, zm, wjp, wn, gg.x, special);
-                if (!special) {
-                    // low-frequency bins for lowchi2: element 0 of each group (k4 = 0)
-                    const int kA = G::bin_of(p, gg.x, 0), kB = G::bin_of(p, gg.y, 0);
-                    if (kA < prm.nlow) sm.stash[kA] = dp2_lane0(z[0]);
-                    if (kB < prm.nlow) sm.stash[kB] = dp2_lane1(z[0]);
-                }
-                if constexpr (MULTI) {
-                    // X must survive the in-place inverse of the previous template (thread-private column)
-                    V* dst = scr_x + tid;
-                    const unsigned long long pol = dp2_policy_keep();
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
-                }
-            } else {
-                // fp64: pair by pair -- chi0, the lowchi2 stash and (single template) the filter + inverse
-                // untangle are applied while the pair is in registers; multi-template plans send X to the
-                // thread-private L2 column instead
-                Gp = __shfl_xor_sync(0xffffffffu, gg.x, 1);
-                const int kA = G::bin_of(p, gg.x, 0);
-                const bool stash0 = !special && kA < prm.nlow;
-                [[maybe_unused]] V* dst = scr_x + tid;
-                [[maybe_unused]] const unsigned long long pol = dp2_policy_keep();
-                [[maybe_unused]] const V* phi0 = ch.templ[0].phi + (long long)p * 16 * NT;
-                S chin = (S)0;
-                pw_publish(sm.buf, z, gg.x);
-                pw_untangle(sm.buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) {
-                    chin = dp_fma(dp_ldg(wjp + (2 * r) * NT + tid), cnorm2(Xk), chin);
-                    chin = dp_fma(dp_ldg(wjp + (2 * r + 1) * NT + tid), cnorm2(Xm), chin);
-                    if (r == 0 && stash0) sm.stash[kA] = Xk;
-                    if constexpr (MULTI) {
-                        dp2_st_keep(dst + (2 * r) * NT, Xk, pol);
-                        dp2_st_keep(dst + (2 * r + 1) * NT, Xm, pol);
-                    } else {
-                        pw_filter_pair(sm.buf, z, r, Xk, Xm, phi0, wn, Gp);
+            dp2_stage_wait(bar, spar);
+            spar ^= 1;
+            {
+                const Staged tb = staged_view(bufb, prm.zones[p * NW + warp], spoff, lane, true, ch.templ[0].phi + tab_block(p, warp) + lane);
+                if constexpr (VL == 2) {
+                    const S c = untangle_st(z, tb, wn);
+                    if (!special) {
+                        chi += c;
+                        // low-frequency bins for lowchi2: element 0 of each group (k4 = 0)
+                        const int kA = G::bin_of(p, gg.x, 0), kB = G::bin_of(p, gg.y, 0);
+                        if (kA < prm.nlow) sm.stash[kA] = dp2_lane0(z[0]);
+                        if (kB < prm.nlow) sm.stash[kB] = dp2_lane1(z[0]);
                     }
-                });
-                if (!special) chi += chin;
+                    if constexpr (MULTI) {
+                        // X must survive the in-place inverse of the first template
+                        const unsigned long long pol = dp2_policy_keep();
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) dp2_st_keep(xs + r * 32, z[r], pol);
+                    }
+                    filter_st<true>(z, tb, wn);
+                } else {
+                    // fp64: pair by pair -- chi0, the lowchi2 stash, the X column (multi-template plans) and the first
+                    // template's filter + inverse untangle while the pair is in registers
+                    const int kA = G::bin_of(p, gg.x, 0);
+                    const bool stash0 = !special && kA < prm.nlow;
+                    [[maybe_unused]] const unsigned long long pol = dp2_policy_keep();
+                    S chin = (S)0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const V Zm = dp2_swap1(z[15 - r]);  // the partner's element 15 - r
+                        const cx<S> w = cmul(wn, dp_w64_rt<S>(2 * r));
+                        cx<S> Xk, Xm;
+                        dp_untangle(z[r], Zm, w, Xk, Xm);
+                        chin = dp_fma(tb.wj(2 * r), cnorm2(Xk), chin);
+                        chin = dp_fma(tb.wj(2 * r + 1), cnorm2(Xm), chin);
+                        if (r == 0 && stash0) sm.stash[kA] = Xk;
+                        if constexpr (MULTI) {
+                            dp2_st_keep(xs + (2 * r) * 32, Xk, pol);
+                            dp2_st_keep(xs + (2 * r + 1) * 32, Xm, pol);
+                        }
+                        pair_filter(z, r, Xk, Xm, tb.phi_a(2 * r), tb.phi_a(2 * r + 1), w);
+                    }
+                    if (!special) chi += chin;
+                }
             }
+            __syncwarp();  // every lane is done with the staged tables before the rows take the pass-4' group values
             // next trace -> L2 once this event's last read of its own trace is done (a whole event of
             // lead time let the scratch / table traffic of 148 SMs evict the line before its use)
             if (p == NPH - 1) prefetch_next(prm, row);
 
-            // ---------------- per template: filter, inverse passes 4' 3' 2' ---------------------
+            // ---------------- per template: inverse passes 4' 3' 2' (the first template's filter is done) -------
             const int n_templ = MULTI ? ch.n_templ : 1;
+            int it = 0;
 #pragma unroll 1
-            for (int it = 0; it < n_templ; ++it) {
+            for (;;) {
                 const Dp2TemplDev<T>& tp = ch.templ[it];
                 V* park = scr_park + (long long)it * SCR_PARK;
-                if (p == 0 && tid < 17) {
-                    const DpSelfLane<S> sp = dp_self_lane<S, 1>(tid);
-                    const cx<S> Fk = cmul(dp_ldg(tp.phi_self + 2 * tid), sx[2 * tid]);
-                    const cx<S> Fm = cmul(dp_ldg(tp.phi_self + 2 * tid + 1), sx[2 * tid + 1]);
-                    cx<S> Ck, Cm;
-                    dp_retangle(Fk, Fm, sp.w, Ck, Cm);
-                    sm.sp[sp.ek] = Ck;
-                    if (sp.ek != sp.em) sm.sp[sp.em] = Cm;
-                }
-                if constexpr (VL == 2) {
-                    if constexpr (MULTI) {
-                        const V* src = scr_x + tid;
-                        const unsigned long long pol = dp2_policy_keep();
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) z[r] = dp2_ld_keep(src + r * NT, pol);
-                    }
-                    filter_all(sm.buf, z, zm, tp.phi + (long long)p * 16 * NT, wn, gg.x);
-                } else {
-                    if constexpr (MULTI) {
-                        const V* src = scr_x + tid;
-                        const unsigned long long pol = dp2_policy_keep();
-                        const V* phit = tp.phi + (long long)p * 16 * NT;
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const V Xk = dp2_ld_keep(src + (2 * r) * NT, pol), Xm = dp2_ld_keep(src + (2 * r + 1) * NT, pol);
-                            pw_filter_pair(sm.buf, z, r, Xk, Xm, phit, wn, Gp);
-                        }
-                    }
-                    pw_collect(sm.buf, z, gg.x);
-                }
+                const bool more = MULTI && (it + 1 < n_templ);
                 if (p == 0 && tid < 32) {
+                    if (tid < 17) {
+                        const DpSelfLane<S> sp = dp_self_lane<S, 1>(tid);
+                        const cx<S> Fk = cmul(dp_ldg(tp.phi_self + 2 * tid), sx[2 * tid]);
+                        const cx<S> Fm = cmul(dp_ldg(tp.phi_self + 2 * tid + 1), sx[2 * tid + 1]);
+                        cx<S> Ck, Cm;
+                        dp_retangle(Fk, Fm, sp.w, Ck, Cm);
+                        sm.sp[sp.ek] = Ck;
+                        if (sp.ek != sp.em) sm.sp[sp.em] = Cm;
+                    }
                     __syncwarp();
                     if constexpr (VL == 2) {
                         if (tid == 0) {
@@ -1026,134 +1400,181 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     }
                     __syncwarp();
                 }
-                Core::inv_432(sm.buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
-                if (p < NPH - 1) {
-                    Core::park_pass2(park, p, z);
-                    __syncthreads();  // pass-2' reads of buf precede the next group / pass-1 stores
-                    continue;
-                }
-                // ------------ last phase: pass 1' over all blocks, arg-max, outputs --------------
-                Core::store_pass2(sm.buf, z);
-                __syncthreads();  // also orders the parked block results (global memory) within the CTA
+                dp_dft<16, +1, T>::run(z);
+                Core::store_groups(sm.buf, gg.x, gg.y, z);
+                __syncwarp();  // pass 3' reads the warp's own chunks
+                Core::inv_3w(sm.buf, prm.tw3, chunk, z);
+                // fits of this template (at most DP_MAX_TSLOTS) and the complex points n = r/2 that some of them can select
                 int slot_of[DP_MAX_TSLOTS];
                 int nts = 0;
 #pragma unroll
                 for (int q = 0; q < DP_MAX_TSLOTS; ++q) slot_of[q] = -1;
+                int nlo = 0x7fffffff, nhi = -1;
                 for (int s = 0; s < ch.n_slots; ++s) {
-                    if (ch.slots[s].templ == it) {
+                    const DpSlot sl = ch.slots[s];
+                    if (sl.templ == it) {
 #pragma unroll
                         for (int q = 0; q < DP_MAX_TSLOTS; ++q)
                             if (q == nts) slot_of[q] = s;
                         ++nts;
-                    }
-                }
-                DpBest<S> tb[DP_MAX_TSLOTS];
-#pragma unroll
-                for (int q = 0; q < DP_MAX_TSLOTS; ++q) tb[q] = DpBest<S>{(S)0, -1};
-                // complex points n = r/2 that some fit of this template can select
-                int nlo = 0x7fffffff, nhi = -1;
-#pragma unroll
-                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
-                    if (q < nts) {
-                        const DpSlot sl = ch.slots[slot_of[q]];
                         const bool everything = sl.outside || (sl.lo == 0 && sl.hi == N);
                         const int a = everything ? 0 : (sl.lo >> 1), b = everything ? 0x7fffffff : ((sl.hi - 1) >> 1);
                         nlo = a < nlo ? a : nlo;
                         nhi = b > nhi ? b : nhi;
                     }
                 }
-#pragma unroll 1
-                for (int i0 = 0; i0 < NC; i0 += GC) {
-                    V y[GC * R1];
+                const unsigned rowmask = Core::rows_of(nlo, nhi);
+                const bool few_rows = __popc(rowmask) <= 2;  // narrow delay window(s): Horner evaluation of the rows it touches
+                dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 2' reads columns across the set's chunks
+                if (p < NPH - 1) {
+                    if (few_rows) {
+                        Core::template inv_2_rows<true>(sm.buf, park, p, prm.tw2, rowmask);
+                    } else {
+                        Core::inv_2(sm.buf, prm.tw2, z);
+                        Core::park_pass2(park, p, z, rowmask);
+                    }
+                    if (MULTI && it == 0) dp2_fence_async();  // the X column (stored long ago: cheap by now) is read back by bulk copy
+                    __syncthreads();  // pass-2' reads of buf precede the next group / pass-1 stores
+                    if (more && lane == 0)
+                        issue_b(bar, bufb, prm.zones[p * NW + warp], spw, scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
+                } else {
+                    // ------------ last phase: pass 1' over all blocks, arg-max, outputs --------------
+                    if (few_rows) {
+                        Core::template inv_2_rows<false>(sm.buf, nullptr, p, prm.tw2, rowmask);
+                    } else {
+                        Core::inv_2(sm.buf, prm.tw2, z);
+                        Core::store_pass2(sm.buf, z, rowmask);
+                    }
+                    if (MULTI && it == 0) dp2_fence_async();
+                    __syncthreads();  // also orders the parked block results (global memory) within the CTA
+                    DpBest<S> tb[DP_MAX_TSLOTS];
 #pragma unroll
-                    for (int j = 0; j < GC * R1; ++j) y[j] = V{(T)0.0f, (T)0.0f};
-                    const unsigned computed = Core::inv_pass1(sm.buf, park, prm.tw1, i0, y, nlo, nhi);
-                    if (computed == 0) continue;  // this thread holds no candidate delay of this template
+                    for (int q = 0; q < DP_MAX_TSLOTS; ++q) tb[q] = DpBest<S>{(S)0, -1};
+                    const unsigned colneed = Core::need_cols(nlo, nhi);
+#pragma unroll 1
+                    for (int i0 = 0; i0 < NC; i0 += GC) {
+                        const unsigned computed = (colneed >> i0) & ((1u << GC) - 1u);
+                        if (computed == 0) continue;  // this thread holds no candidate delay of this template in these columns
+                        // (all of y is written here, not only the columns pass 1' computes: registers that are not
+                        // defined on every path stay live across the whole event loop -- 2.6 KB of spills)
+                        V y[GC * R1];
+#pragma unroll
+                        for (int j = 0; j < GC * R1; ++j) y[j] = V{(T)0.0f, (T)0.0f};
+                        Core::inv_pass1m(sm.buf, park, prm.tw1, i0, y, computed);
+#pragma unroll
+                        for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                            if (q < nts) {
+                                const DpSlot sl = ch.slots[slot_of[q]];
+                                if (sl.lo == 0 && sl.hi == N && !sl.outside)
+                                    Dp2Scan<T, R1>::full(y, tid, i0, tb[q]);
+                                else
+                                    Dp2Scan<T, R1>::window(y, tid, i0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, tb[q], computed);
+                            }
+                        }
+                    }
+                    DpBest<S>* best = sm.best(par);
+                    double* red = sm.red(par);
 #pragma unroll
                     for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
                         if (q < nts) {
-                            const DpSlot sl = ch.slots[slot_of[q]];
-                            if (sl.lo == 0 && sl.hi == N && !sl.outside)
-                                Dp2Scan<T, R1>::full(y, tid, i0, tb[q]);
-                            else
-                                Dp2Scan<T, R1>::window(y, tid, i0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, tb[q], computed);
+                            const DpBest<S> b = dp_warp_best(tb[q]);
+                            if ((tid & 31) == 0) best[q * 32 + (tid >> 5)] = b;
+                            if (tid == 0) sm.slot_id(par)[q] = slot_of[q];
                         }
                     }
-                }
-                DpBest<S>* best = sm.best(par);
-                double* red = sm.red(par);
+                    __syncthreads();  // winners + the lowchi2 stash are visible; pass-1' reads of buf are done
+                    // the FFT buffer is free: the next template's X column and filter rows land while the outputs are formed
+                    if (more && lane == 0)
+                        issue_b(bar, bufb, prm.zones[p * NW + warp], spw, scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
+                    // ---- low-frequency chi2 at each fit's (amp, delay); chi0; outputs ----------------
+                    double part[DP_MAX_TSLOTS + 1];
 #pragma unroll
-                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
-                    if (q < nts) {
-                        const DpBest<S> b = dp_warp_best(tb[q]);
-                        if ((tid & 31) == 0) best[q * 32 + (tid >> 5)] = b;
-                        if (tid == 0) sm.slot_id(par)[q] = slot_of[q];
-                    }
-                }
-                __syncthreads();  // winners + the lowchi2 stash are visible; pass-1' reads of buf are done
-                // ---- low-frequency chi2 at each fit's (amp, delay); chi0; outputs ----------------
-                double part[DP_MAX_TSLOTS + 1];
-#pragma unroll
-                for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
-                    part[q] = 0.0;
-                    if (q < nts && tid < prm.nlow) {
-                        DpBest<S> b = best[q * 32];
-                        for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
-                        const int d = b.idx - tp.pretrigger;
-                        for (int k = tid; k < prm.nlow; k += NT) {
-                            const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
-                            S sn, cs;
-                            if constexpr (sizeof(S) == 8) {
-                                double s_, c_;
-                                sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
-                                sn = (S)s_;
-                                cs = (S)c_;
-                            } else {
-                                float s_, c_;
-                                sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
-                                sn = (S)s_;
-                                cs = (S)c_;
+                    for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                        part[q] = 0.0;
+                        if (q < nts && tid < prm.nlow) {
+                            DpBest<S> b = best[q * 32];
+                            for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
+                            const int d = b.idx - tp.pretrigger;
+                            for (int k = tid; k < prm.nlow; k += NT) {
+                                const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
+                                S sn, cs;
+                                if constexpr (sizeof(S) == 8) {
+                                    double s_, c_;
+                                    sincospi(2.0 * (double)ph / (double)N, &s_, &c_);
+                                    sn = (S)s_;
+                                    cs = (S)c_;
+                                } else {
+                                    float s_, c_;
+                                    sincospif(2.0f * (float)ph / (float)N, &s_, &c_);
+                                    sn = (S)s_;
+                                    cs = (S)c_;
+                                }
+                                const cx<S> mdl = cmul(cx<S>{cs, -sn}, dp_ldg(tp.s_low + k));
+                                const cx<S> X = sm.stash[k];
+                                const cx<S> R = cx<S>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
+                                part[q] += (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
                             }
-                            const cx<S> mdl = cmul(cx<S>{cs, -sn}, dp_ldg(tp.s_low + k));
-                            const cx<S> X = sm.stash[k];
-                            const cx<S> R = cx<S>{dp_fma(-b.val, mdl.re, X.re), dp_fma(-b.val, mdl.im, X.im)};
-                            part[q] += (double)(dp_ldg(ch.wj_low + k) * cnorm2(R));
+                        }
+                    }
+                    part[DP_MAX_TSLOTS] = (it == 0) ? (double)chi : 0.0;
+#pragma unroll
+                    for (int q = 0; q <= DP_MAX_TSLOTS; ++q) {
+                        if (q < nts || (q == DP_MAX_TSLOTS && it == 0)) {
+                            const double v = dp_warp_sum(part[q]);
+                            if ((tid & 31) == 0) red[q * 32 + (tid >> 5)] = v;
+                        }
+                    }
+                    // only thread 0 needs the partial sums: warp 0 waits for them, the other warps check in and go on
+                    // (next template / next event; red / best are double buffered by `par`)
+                    if (warp == 0)
+                        dp_bar_sync(15, NT);
+                    else
+                        dp_bar_arrive(15, NT);
+                    if (tid == 0) {
+                        double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
+                        if (it == 0) {
+                            double c0 = 0.0;
+                            for (int w = 0; w < NW; ++w) c0 += red[DP_MAX_TSLOTS * 32 + w];
+                            *chi0_keep = c0;
+                            o[0] = c0;
+                        }
+                        const double chi0 = *chi0_keep;
+                        for (int q = 0; q < nts; ++q) {
+                            double low = 0.0;
+                            for (int w = 0; w < NW; ++w) low += red[q * 32 + w];
+                            DpBest<S> b = best[q * 32];
+                            for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
+                            double* os = o + 1 + sm.slot_id(par)[q] * DP_SLOT_NOUT;
+                            const double amp = (double)b.val;
+                            os[0] = amp;
+                            os[1] = (double)b.idx;
+                            os[2] = chi0 - amp * amp * tp.norm;
+                            os[3] = low;
+                            os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
+                        }
+                    }
+                    par ^= 1;
+                }
+                if (!more) break;
+                ++it;
+                // ---------------- next template: X (staged) times its filter, inverse untangle -> z ----------------
+                dp2_stage_wait(bar, spar);
+                spar ^= 1;
+                {
+                    const Staged tb = staged_view(bufb, prm.zones[p * NW + warp], spoff, lane, false, ch.templ[it].phi + tab_block(p, warp) + lane);
+                    if constexpr (VL == 2) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) z[r] = tb.x(r);
+                        filter_st<false>(z, tb, wn);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const cx<S> w = cmul(wn, dp_w64_rt<S>(2 * r));
+                            pair_filter(z, r, tb.x(2 * r), tb.x(2 * r + 1), tb.phi_b(2 * r), tb.phi_b(2 * r + 1), w);
                         }
                     }
                 }
-                part[DP_MAX_TSLOTS] = (it == 0) ? (double)chi : 0.0;
-#pragma unroll
-                for (int q = 0; q <= DP_MAX_TSLOTS; ++q) {
-                    if (q < nts || (q == DP_MAX_TSLOTS && it == 0)) {
-                        const double v = dp_warp_sum(part[q]);
-                        if ((tid & 31) == 0) red[q * 32 + (tid >> 5)] = v;
-                    }
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    double* o = prm.out + (long long)ev * prm.n_out + ch.out_base;
-                    if (it == 0) {
-                        double c0 = 0.0;
-                        for (int w = 0; w < NW; ++w) c0 += red[DP_MAX_TSLOTS * 32 + w];
-                        *chi0_keep = c0;
-                        o[0] = c0;
-                    }
-                    const double chi0 = *chi0_keep;
-                    for (int q = 0; q < nts; ++q) {
-                        double low = 0.0;
-                        for (int w = 0; w < NW; ++w) low += red[q * 32 + w];
-                        DpBest<S> b = best[q * 32];
-                        for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
-                        double* os = o + 1 + sm.slot_id(par)[q] * DP_SLOT_NOUT;
-                        const double amp = (double)b.val;
-                        os[0] = amp;
-                        os[1] = (double)b.idx;
-                        os[2] = chi0 - amp * amp * tp.norm;
-                        os[3] = low;
-                        os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
-                    }
-                }
-                par ^= 1;
+                __syncwarp();  // staged rows are consumed before pass 4' stores into them
             }
         }
     }

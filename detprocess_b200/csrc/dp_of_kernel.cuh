@@ -50,9 +50,12 @@ template <class T> struct DpChanDev {
     const T* wj;       // [32*P][NT] thread-order chi0 weights
     const T* wj_self;  // [17][2*P] weights at the bins of the self-paired butterflies (0 for duplicates)
     const T* wj_low;   // [nlow] natural order
+    double adc_gain;   // int16 traces (raw ADC counts): sample = adc * adc_gain + adc_offset
+    double adc_offset;
     int n_templ;
     int n_slots;
     int out_base;  // offset (doubles) of this channel's block in an event's output row
+    int pad_;
     DpTemplDev<T> templ[DP_MAX_TEMPLATES];
     DpSlot slots[DP_MAX_SLOTS];
 };
@@ -186,6 +189,20 @@ template <class T, int IN> DP_DEV cx<T> dp_convert_raw(typename DpRaw<IN>::type 
 }
 template <int IN> DP_DEV double dp_load_first(const void* row) {
     return (double)__ldg(reinterpret_cast<const typename DpRaw<IN>::scalar*>(row));
+}
+
+// Conversion of a raw sample to the kernel's working value: (raw - x0) * sc.  Float traces: x0 = first sample (fp32 mode,
+// AC coupling) or 0, sc = the plan's power-of-two scale.  int16 ADC counts (IN == 2): sample = adc * gain + offset
+// = (adc + offset / gain) * gain, so x0 = -offset / gain (or the first count when it is subtracted anyway) and
+// sc = gain * scale -- the same conversion pytesio applies at read time (adctoamp=True, processing_data.py:675-684).
+template <class T, int IN> DP_DEV void dp_row_conversion(const DpOfParams<T>& prm, int chan, const void* xrow, double& x0, double& sc) {
+    x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+    sc = prm.scale;
+    if constexpr (IN == 2) {
+        const double gain = dp_ldg(&prm.chans[chan].adc_gain), offs = dp_ldg(&prm.chans[chan].adc_offset);
+        if (!prm.subtract_first) x0 = -offs / gain;
+        sc = gain * prm.scale;
+    }
 }
 
 // ------------------------------------------------------------- forward sub-FFT
@@ -593,11 +610,12 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run_p1(const DpOfParams<T>& prm, unsigned 
         const int ev = row / prm.n_chan;
         const DpChanDev<T>& ch = prm.chans[chan];
         const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
-        const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+        double x0, xsc;
+        dp_row_conversion<T, IN>(prm, chan, xrow, x0, xsc);
 
         cx<T> za[16], zb[16];
         T chi = (T)0;
-        dp_fwd_subfft<T, R1, 1, IN>(xrow, 0, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+        dp_fwd_subfft<T, R1, 1, IN>(xrow, 0, x0, xsc, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
 
         // ---- self-paired butterflies of thread 0, cooperatively in warp 0 ------------------
         cx<T> sXk = cx<T>{(T)0, (T)0}, sXm = sXk;  // lanes 0..16 of warp 0: 2*X of their pair
@@ -728,7 +746,8 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run_p2(const DpOfParams<T>& prm, unsigned 
         const int ev = row / prm.n_chan;
         const DpChanDev<T>& ch = prm.chans[chan];
         const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
-        const double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
+        double x0, xsc;
+        dp_row_conversion<T, IN>(prm, chan, xrow, x0, xsc);
 
         cx<T> za[16], zb[16];
         T chi = (T)0;
@@ -737,7 +756,7 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run_p2(const DpOfParams<T>& prm, unsigned 
         //  the 8-warp fp64 CTA, see profiles/)
 #pragma unroll 1
         for (int p = 0; p < 2; ++p) {
-            dp_fwd_subfft<T, R1, 2, IN>(xrow, p, x0, prm.scale, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
+            dp_fwd_subfft<T, R1, 2, IN>(xrow, p, x0, xsc, sm.buf, prm.tw1, prm.tw2, bA, bB, za, zb);
             if (p == 0) {
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {

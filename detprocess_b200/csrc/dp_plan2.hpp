@@ -6,6 +6,7 @@
 #pragma once
 #include "dp_of2_kernel.cuh"
 #include "dp_plan.hpp"
+#include <map>
 
 namespace dpplan2 {
 
@@ -28,6 +29,8 @@ template <class T> struct Tables2 {
     std::vector<cx<T>> tw1, tw2, tw3;
     std::vector<cx<S>> twn;
     std::vector<int2> groups;
+    std::vector<int> chunk3;   // [NPH][NT] chunk (b*16 + k2) a thread transforms in the warp-local passes 3 / 3'
+    std::vector<uint4> zones;  // [NPH][NW] byte offsets of the warp's four 2048-byte landing pieces in the FFT buffer
     struct Templ {
         std::vector<cx<T>> phi;
         std::vector<cx<S>> phi_self, s_low;
@@ -130,6 +133,58 @@ template <class G> inline std::vector<int> partial_slot_of_bin() {
     return loc;
 }
 
+
+// position of (phase p, entry e, thread t) in the OF kernel's thread-order tables [NPH][NW][16][32]: the 16 rows of
+// a warp are one contiguous block (4 KB of chi0 weights, 8 KB of filter values) that the warp fetches by bulk copy
+template <class G> inline size_t ws_index(int p, int e, int t) { return ((((size_t)p * (G::NT / 32) + t / 32) * 16 + e) * 32) + (t % 32); }
+
+// Warp-local passes 3 / 3' (Dp2Core::fwd_3w / inv_3w): every warp must own whole 256-element chunks in pass 4 (all
+// 16 groups of the chunk, i.e. a chunk together with its mirror chunk); thread lane l of the warp then transforms
+// chunk S[l / GV] in pass 3, S = the warp's chunks in ascending order.  The same chunks are the shared memory the
+// warp may overwrite between pass 4 and pass 4' (its own group rows): cut into 2048-byte landing pieces.
+template <class G> inline void build_chunks(std::vector<int>& chunk3, std::vector<uint4>& zones) {
+    constexpr int NT = G::NT, NW = NT / 32, GV = G::GV, NPH = G::NPH;
+    constexpr int CPW = 32 / GV;                        // chunks per warp
+    constexpr unsigned CHUNK_BYTES = 16u * (GV + 1) * 16u;  // 16 padded group rows of GV + 1 vectors
+    constexpr unsigned PIECE = 2048;
+    static_assert(CPW * (CHUNK_BYTES / PIECE) == 4, "a warp's chunks must hold four landing pieces");
+    chunk3.assign((size_t)NPH * NT, -1);
+    zones.assign((size_t)NPH * NW, uint4{0, 0, 0, 0});
+    for (int p = 0; p < NPH; ++p) {
+        std::vector<int> owner(G::NB * 16, -1);
+        for (int w = 0; w < NW; ++w) {
+            std::map<int, int> cnt;
+            for (int l = 0; l < 32; ++l) {
+                int Ga, Gb;
+                G::groups_of(p, w * 32 + l, Ga, Gb);
+                ++cnt[Ga >> 4];
+                if (G::VL == 2) ++cnt[Gb >> 4];
+            }
+            if ((int)cnt.size() != CPW) throw std::logic_error("v2 geometry: a warp does not own whole chunks");
+            std::vector<int> S;
+            for (const auto& kv : cnt) {
+                if (kv.second != 16) throw std::logic_error("v2 geometry: chunk split between warps");
+                if (owner[kv.first] >= 0) throw std::logic_error("v2 geometry: chunk owned twice");
+                owner[kv.first] = w;
+                S.push_back(kv.first);
+            }
+            for (int l = 0; l < 32; ++l) chunk3[(size_t)p * NT + w * 32 + l] = S[l / GV];
+            unsigned off[4];
+            int n = 0;
+            for (int c : S)
+                for (unsigned q = 0; q + PIECE <= CHUNK_BYTES; q += PIECE) off[n++] = (unsigned)c * CHUNK_BYTES + q;
+            zones[(size_t)p * NW + w] = uint4{off[0], off[1], off[2], off[3]};
+        }
+        for (int c = 0; c < G::NB * 16; ++c)
+            if (owner[c] < 0) throw std::logic_error("v2 geometry: chunk without a warp");
+        // the set barrier between pass 2 and pass 3 must cover the blocks of every chunk a thread reads
+        for (int t = 0; t < NT; ++t) {
+            const int b = chunk3[(size_t)p * NT + t] >> 4, tb = t / G::CV;
+            if (b != tb && b != G::mirror_b(p, tb)) throw std::logic_error("v2 geometry: chunk outside the thread's block set");
+        }
+    }
+}
+
 // a one-sided filter pe[0..M] (applied to 2*sc*fft(x), see dpplan::filter_onesided) in thread order
 template <class T, int R1>
 void pack_onesided(const std::vector<cplx>& pe, std::vector<cx<T>>& phi, std::vector<cx<typename Dp2Traits<T>::S>>& phi_self) {
@@ -187,6 +242,7 @@ Tables2<T> build_tables2(double fs, const std::vector<dpplan::Channel>& chans, d
             dt.groups[(size_t)p * NT + t] = int2{Ga, Gb};
             dt.twn[(size_t)p * NT + t] = cxS(dpplan::unit_root(G::bin_of(p, Ga, 0), N));
         }
+    build_chunks<G>(dt.chunk3, dt.zones);
     for (const auto& ch : chans) {
         typename Tables2<T>::Chan dc;
         if ((int)ch.J.size() != N) throw std::invalid_argument("psd not set for a channel");
@@ -198,7 +254,7 @@ Tables2<T> build_tables2(double fs, const std::vector<dpplan::Channel>& chans, d
                     int b[2];
                     entry_bins<G>(p, t, e, b);
                     const double v[2] = {wJ[b[0]], wJ[b[1]]};
-                    dc.wj[((size_t)p * 16 + e) * NT + t] = Pack<T>::r(v);
+                    dc.wj[ws_index<G>(p, e, t)] = Pack<T>::r(v);
                 }
         dc.wj_self.resize(17 * 2);
         for (int l = 0; l < 17; ++l) {
@@ -219,7 +275,7 @@ Tables2<T> build_tables2(double fs, const std::vector<dpplan::Channel>& chans, d
                         int b[2];
                         entry_bins<G>(p, t, e, b);
                         const cplx z[2] = {pe[b[0]], pe[b[1]]};
-                        d.phi[((size_t)p * 16 + e) * NT + t] = Pack<T>::c(z);
+                        d.phi[ws_index<G>(p, e, t)] = Pack<T>::c(z);
                     }
             d.phi_self.resize(17 * 2);
             for (int l = 0; l < 17; ++l) {

@@ -27,6 +27,7 @@ struct float2 { float x, y; };
 struct double2 { double x, y; };
 struct short2 { short x, y; };
 struct int2 { int x, y; };
+struct uint4 { unsigned x, y, z, w; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline double2 make_double2(double a, double b) { return double2{a, b}; }
 struct dp_dim3 { unsigned x = 1, y = 1, z = 1; };
@@ -71,6 +72,20 @@ static inline void dp_bar_sync(int id, int count) {
     b->arrive_and_wait();
 }
 
+// producer side of a named barrier: counts the thread in, does not wait
+static inline void dp_bar_arrive(int id, int count) {
+    auto* c = dpemu::cta;
+    std::barrier<>* b;
+    {
+        std::lock_guard<std::mutex> g(c->named_mu);
+        auto& slot = c->named[{id, count}];
+        if (!slot) slot = std::make_unique<std::barrier<>>(count);
+        b = slot.get();
+    }
+    (void)b->arrive();
+}
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+
 template <class V>
 static inline V dp_shfl_impl(V v, int src_lane) {
     static_assert(sizeof(V) <= 8, "shuffle payload");
@@ -112,6 +127,8 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 #define DP_RESTRICT __restrict__
 // named barrier: `count` threads (a multiple of 32) of the CTA meet at barrier `id` (1..15)
 __device__ __forceinline__ void dp_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// producer side: counts the thread in (its earlier writes are visible to the threads that bar.sync on `id`), does not wait
+__device__ __forceinline__ void dp_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 #endif
 
 // ------------------------------------------------------------- scalar type traits

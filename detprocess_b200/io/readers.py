@@ -34,6 +34,17 @@ class EventReader:
         """events [i0, i1) as stored: torch tensor [B, n_chan, N] on the host (pinned when requested and possible)."""
         raise NotImplementedError
 
+    def upload(self, i0, i1, device, stream=None):
+        """events [i0, i1) on ``device`` (asynchronous copy from pinned memory on ``stream`` / the current stream).
+        This, not ``read_batch(...).to(device, non_blocking=True)``, is what the pipelines call: a reader that reuses
+        its host staging orders the next overwrite of a buffer after the copy that still reads it."""
+        import torch
+        host = self.read_batch(i0, i1)
+        if stream is None:
+            return host.to(device, non_blocking=True)
+        with torch.cuda.stream(stream):
+            return host.to(device, non_blocking=True)
+
     def admin(self, i0, i1):
         """dict of per-event columns (event_number, series_number, trigger_index, ...) for events [i0, i1)"""
         return {'event_number': np.arange(i0, i1, dtype=np.int64)}
@@ -140,7 +151,9 @@ class RawBinaryReader(EventReader):
             raise ValueError(f'{path_base}.bin: size does not match the metadata ({expected} bytes expected)')
         self._mm = np.memmap(path_base + '.bin', dtype=np.dtype(meta['dtype']), mode='r', shape=shape)
         self._stage = [None, None]
+        self._copied = [None, None]   # CUDA event recorded after the last asynchronous copy out of each staging buffer
         self._flip = 0
+        self._last = None
 
     def __len__(self):
         return int(self.metadata['n_events'])
@@ -150,6 +163,10 @@ class RawBinaryReader(EventReader):
         nb = i1 - i0
         k = self._flip
         self._flip ^= 1
+        self._last = k
+        if self._copied[k] is not None:      # an upload() of this buffer may still be in flight: wait for it
+            self._copied[k].synchronize()
+            self._copied[k] = None
         buf = self._stage[k]
         if buf is None or buf.shape[0] < nb:
             buf = _pin(torch.empty((nb,) + self._mm.shape[1:], dtype=getattr(torch, self.metadata['dtype'])), pinned)
@@ -157,6 +174,18 @@ class RawBinaryReader(EventReader):
         out = buf[:nb]
         out.numpy()[...] = self._mm[i0:i1]
         return out
+
+    def upload(self, i0, i1, device, stream=None):
+        import torch
+        host = self.read_batch(i0, i1)
+        k = self._last
+        st = torch.cuda.current_stream(device) if stream is None else stream
+        with torch.cuda.stream(st):
+            dev = host.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._copied[k] = ev
+        return dev
 
     def admin(self, i0, i1):
         if not self._admin:

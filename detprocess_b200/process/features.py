@@ -254,10 +254,9 @@ class FeatureProcessing:
         def fetch(b0):
             # the next batch is uploaded on a side stream while the current one is processed
             b1 = min(b0 + batch_size, hi)
-            with torch.cuda.stream(copy_stream):
-                t = reader.read_batch(b0, b1).to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
+            t = reader.upload(b0, b1, dev, stream=copy_stream)   # the reader orders its staging reuse after this copy
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
             return t, ev, b0, b1
 
         nxt = fetch(lo) if lo < hi else None

@@ -116,7 +116,7 @@ class TriggerProcessing:
         ntrig = 0
         for ev in range(lo, hi):
             eb.clear_event()
-            x = reader.to_amps(reader.read_batch(ev, ev + 1).to(dev, non_blocking=True))[0]   # [n_chan, L] amps on the device
+            x = reader.to_amps(reader.upload(ev, ev + 1, dev))[0]   # [n_chan, L] amps on the device
             for trig_chan, td in self._trigger_config.items():
                 if 'threshold_sigma' in td:
                     thr = float(td['threshold_sigma'])

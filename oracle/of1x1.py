@@ -413,4 +413,16 @@ def of1x1_batch(traces, template, psd, fs, pretrigger_samples, windows=(),
         out['lowchi2'][iw] = lowchi2(a, t0)
         with np.errstate(divide='ignore'):
             out['timeres'][iw] = 1.0 / np.sqrt(a ** 2 * tsum)
+
+    def at(ind):
+        """the same fit evaluated at a GIVEN rolled delay index per event (near-tie bookkeeping of the fp32 parity
+        tests: what the float64 maths says at the index another implementation picked)"""
+        ind = np.asarray(ind, dtype=np.int64)
+        a = amps[rows, ind]
+        t0 = (ind - pre) / fs
+        with np.errstate(divide='ignore'):
+            tr = 1.0 / np.sqrt(a ** 2 * tsum)
+        return {'amp': a, 't0': t0, 'chi2': chi2[rows, ind], 'lowchi2': lowchi2(a, t0), 'timeres': tr}
+
+    out['at'] = at
     return out

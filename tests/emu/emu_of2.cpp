@@ -76,6 +76,8 @@ static void run_all(double fs, double fcut, double scale, const std::vector<dppl
     prm.tw3 = dt.tw3.data();
     prm.twn = dt.twn.data();
     prm.groups = dt.groups.data();
+    prm.chunk3 = dt.chunk3.data();
+    prm.zones = dt.zones.data();
     prm.scratch = scratch.data();
     prm.scratch_per_cta = per_cta;
     prm.out = out.data();

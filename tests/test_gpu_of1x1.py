@@ -47,24 +47,45 @@ def _run_plan(S, traces, precision, templates, windows_per_template, in_dtype=No
     return plan, fits, out.cpu().numpy()
 
 
-def _compare(plan, fit, out, o, iw, tol, amp_floor, chan=0):
+NEAR_TIES = []      # (test id, differing events, events) of every fp32 comparison: printed by the last test of the module
+
+
+def _compare(plan, fit, out, o, iw, tol, amp_floor, chan=0, max_diff_frac=0.01):
+    """GPU fit `fit` against window `iw` of the oracle result `o`.
+
+    fp64: identical delay index, everything else to 1e-9.
+    fp32 ("t0 index identical except on documented near-ties"): an event may come out at another index ONLY IF the
+    float64 oracle, evaluated at that index, is within the fp32 amplitude tolerance of its own optimum,
+        |chi2_oracle[i_gpu] - chi2_oracle[i_oracle]| <= 2 * tol_amp * max(amp^2, (5 ampres)^2) * norm
+    (chi2 = chi0 - amp^2 norm, so this is |amp_gpu_candidate - amp_best| <~ tol_amp * |amp|): the two delays are a tie
+    at the resolution the mode promises.  Such events stay in every check below, compared with the oracle AT THE
+    GPU's index; their number is bounded and recorded."""
     off = plan.fit_offset(chan, fit)
     amp, ind, chi2, low, tres = (out[:, off + i] for i in range(5))
     ind = ind.astype(np.int64)
     same = ind == o['ind'][iw]
+    ref = {k: np.array(o[k][iw], dtype=np.float64) for k in ('amp', 'chi2', 'lowchi2', 'timeres')}
     if tol is TOL['f64']:
         assert same.all(), 't0 index must be identical in fp64 mode'
-    else:
-        # documented near-ties: different index only if the oracle's chi2 there is
-        # indistinguishable at fp32 resolution
-        assert same.mean() > 0.99
-    sel = same
-    denom = np.maximum(np.abs(o['amp'][iw]), amp_floor)
-    assert np.max(np.abs(amp - o['amp'][iw])[sel] / denom[sel]) < tol['amp']
-    assert np.max(np.abs(chi2 / o['chi2'][iw] - 1)[sel]) < tol['chi2']
-    assert np.max(np.abs(low / o['lowchi2'][iw] - 1)[sel]) < tol['low']
-    big = np.abs(o['amp'][iw]) > amp_floor
-    assert np.max(np.abs(tres / o['timeres'][iw] - 1)[sel & big]) < max(tol['tres'], tol['amp'] * 2)
+    elif not same.all():
+        d = ~same
+        at = o['at'](ind)
+        bound = 2.0 * tol['amp'] * np.maximum(ref['amp'] ** 2, amp_floor ** 2) * o['norm']
+        dchi = np.abs(at['chi2'] - ref['chi2'])
+        assert np.all(dchi[d] <= bound[d]), f'index differs on a non-tie: dchi2 {dchi[d].max():.3e} > {bound[d].min():.3e}'
+        assert d.mean() <= max_diff_frac, f'{d.sum()} of {d.size} events on near-ties'
+        for k in ref:
+            ref[k][d] = at[k][d]
+    if tol is not TOL['f64']:
+        NEAR_TIES.append((int((~same).sum()), int(same.size)))
+    denom = np.maximum(np.abs(ref['amp']), amp_floor)
+    assert np.max(np.abs(amp - ref['amp']) / denom) < tol['amp']
+    big = np.abs(ref['amp']) > amp_floor
+    if big.any():       # pure relative error where the pulse stands above the noise (north_star: 1e-9 / 1e-5 relative)
+        assert np.max(np.abs(amp / ref['amp'] - 1)[big]) < tol['amp']
+        assert np.max(np.abs(tres / ref['timeres'] - 1)[big]) < max(tol['tres'], tol['amp'] * 2)
+    assert np.max(np.abs(chi2 / ref['chi2'] - 1)) < tol['chi2']
+    assert np.max(np.abs(low / ref['lowchi2'] - 1)) < tol['low']
 
 
 @pytest.mark.parametrize('precision,nb_samples', [('f64', 2048), ('f64', 4096), ('f64', 16384), ('f64', 32768),
@@ -131,13 +152,15 @@ def test_of1x1_float32_and_int16_inputs():
         assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize('nb_samples', [32768, 4096, 8192])
 @pytest.mark.parametrize('precision', ['f64', 'f32'])
-def test_of1x1_adc_counts_with_channel_conversion(precision):
+def test_of1x1_adc_counts_with_channel_conversion(precision, nb_samples):
     """int16 ADC counts + per-channel gain / offset (set_adc_conversion) == the oracle on the traces converted on
-    the host the way H5Reader(adctoamp=True) hands them to the reference (adc * gain + offset, float64)."""
+    the host the way H5Reader(adctoamp=True) hands them to the reference (adc * gain + offset, float64).
+    4096 / 8192 samples run on the first-generation kernel (dp_of_kernel), 32768 on dp_of2_kernel."""
     import torch
     from detprocess_b200.core.plans import OFPlan
-    S = SynthSetup(32768)
+    S = SynthSetup(nb_samples)
     pre = S.nb_pretrigger
     gains, offs = (1.0e-11, 1.3e-11), (-3.0e-9, 1.7e-8)
     amps = [make_traces(40, S.template, S.psd, S.fs, np.random.default_rng(20 + c)) for c in range(2)]
@@ -210,18 +233,14 @@ def test_of1x1_c3_shape_eight_channels_16384(precision):
     tol = TOL[precision]
     for c in range(nch):
         o = of1x1_batch(traces[:, c], S.template, S.psd * (1 + c), S.fs, pre, windows=[(pre - 500, pre + 500, False), (pre, pre + 1, False)])
-        off = plan.fit_offset(c, fits[c][0])
-        assert (out[:, off + 1].astype(np.int64) == o['ind'][0]).mean() > (0.99 if precision == 'f32' else 0.9999)
-        den = np.maximum(np.abs(o['amp'][0]), 5 * o['ampres'])
-        assert np.max(np.abs(out[:, off] - o['amp'][0]) / den) < tol['amp'] * (20 if precision == 'f32' else 1)
         assert np.max(np.abs(out[:, plan.chi0_offset(c)] / o['chi0'] - 1)) < tol['chi2']
+        _compare(plan, fits[c][0], out, o, 0, tol, 5 * o['ampres'], chan=c)
+        _compare(plan, fits[c][1], out, o, 1, tol, 5 * o['ampres'], chan=c)
         if c % 2:
+            # unconstrained fit of the glitch template on default-template pulses: many shallow optima, the near-tie
+            # rule is what decides (every differing index is checked against it), not a fraction of identical indices
             og = of1x1_batch(traces[:, c], S.template_glitch, S.psd * (1 + c), S.fs, pre, windows=[(None, None, False)])
-            offg = plan.fit_offset(c, fits[c][2])
-            deng = np.maximum(np.abs(og['amp'][0]), 5 * og['ampres'])
-            same = out[:, offg + 1].astype(np.int64) == og['ind'][0]
-            assert same.mean() > 0.97
-            assert np.max((np.abs(out[:, offg] - og['amp'][0]) / deng)[same]) < tol['amp'] * (20 if precision == 'f32' else 1)
+            _compare(plan, fits[c][2], out, og, 0, tol, 5 * og['ampres'], chan=c, max_diff_frac=0.05)
     # exactly representable samples: f32 and i16 buffers == f64 buffer
     adc = rng.integers(-2000, 2000, size=(6, nch, n)).astype(np.int16)
     ref = plan.run(torch.from_numpy(adc.astype(np.float64)).cuda()).cpu().numpy()
@@ -252,3 +271,10 @@ def test_host_buffer_path_matches_device_path():
     assert np.array_equal(host, out)
     pinned = torch.from_numpy(traces).pin_memory()
     assert np.array_equal(plan.run_host(pinned), out)
+
+
+def test_zz_report_near_ties():
+    """not a check: prints how many fp32 events of this module sat on a documented near-tie (see _compare)"""
+    n = sum(a for a, _ in NEAR_TIES)
+    tot = sum(b for _, b in NEAR_TIES)
+    print(f'\nfp32 near-ties: {n} of {tot} event-fits came out at another delay index (each within the tie bound)')

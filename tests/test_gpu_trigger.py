@@ -58,6 +58,22 @@ def test_trigger_dense_candidates_and_no_padding():
             assert np.allclose(d['trigger_amplitude'], o['trigger_amplitude'], rtol=1e-8, atol=1e-18)
 
 
+def test_trigger_overflow_of_the_output_buffer_is_never_truncated():
+    """more trigger groups than max_triggers: the run repeats with buffers sized to the reported count and returns
+    every trigger, like the reference (oftrigger.py:996-1019)"""
+    from detprocess_b200.core.oftrigger import OptimumFilterTrigger
+    nt, L = 4096, 120_000
+    fs, template, psd, x = _make(nt, L, 5)
+    trig = OptimumFilterTrigger('ch', fs, template, psd, nt // 2, max_samples=L)
+    trig.update_trace(x)
+    big = trig.find_triggers_once(1.0, pileup_window_samples=3, max_triggers=L)['ch']
+    small = trig.find_triggers_once(1.0, pileup_window_samples=3, max_triggers=7)['ch']
+    assert len(big['trigger_index']) > 1000
+    assert np.array_equal(np.asarray(small['trigger_index']), np.asarray(big['trigger_index']))
+    assert np.array_equal(np.asarray(small['trigger_amplitude']), np.asarray(big['trigger_amplitude']))
+    assert trig._plan.n_found == len(big['trigger_index'])
+
+
 def test_trigger_quiet_stream_and_errors():
     from detprocess_b200.core.oftrigger import OptimumFilterTrigger
     nt, L = 4096, 100_000
