@@ -44,6 +44,7 @@ SIGNATURES = {
     'dp_of_plan_set_psd': (_i, [_vp, _i, _vp, _i]),
     'dp_of_plan_add_template': (_i, [_vp, _i, _vp, _i, _i, _ip]),
     'dp_of_plan_add_fit': (_i, [_vp, _i, _i, _i, _i, _i, _ip]),
+    'dp_of_plan_add_fit_ex': (_i, [_vp, _i, _i, _i, _i, _i, _d, _ip]),
     'dp_of_plan_set_lowchi2_fcutoff': (_i, [_vp, _d]),
     'dp_of_plan_set_adc_conversion': (_i, [_vp, _i, _d, _d]),
     'dp_csd_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i, _i]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     'dp_of1x1_batch': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _vp]),
     'dp_of1x1_batch_host': (_i, [_vp, _vp, _i, _ll, _ll, _vp]),
     'dp_of1x1_windows': (_i, [_vp, _vp, _ll, _vp, _ll, _vp, _vp]),
+    'dp_of1x1_batch_ex': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _ll, _vp, _ll, _vp, _vp]),
     'dp_of_plan_last_kernel_ms': (_i, [_vp, _fp]),
     'dp_of_plan_launch_count': (_i, [_vp, C.POINTER(_ll)]),
     'dp_reduce_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i]),
@@ -83,6 +85,8 @@ SIGNATURES = {
     'dp_window_reduce_batch': (_i, [_vp, _vp, _ll, _ll, _vp, _vp]),
     'dp_reduce_plan_set_adc_conversion': (_i, [_vp, _i, _d, _d]),
     'dp_window_reduce_batch_raw': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _vp]),
+    'dp_window_reduce_batch_ex': (_i, [_vp, _vp, _i, _ll, _ll, _vp, _ll, _vp, _ll, _vp, _vp]),
+    'dp_channel_combine': (_i, [_vp, _i, _ll, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'dp_reduce_plan_last_kernel_ms': (_i, [_vp, _fp]),
     'dp_psd_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i]),
     'dp_psd_plan_destroy': (None, [_vp]),

@@ -25,7 +25,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3',
 # (precision, input type) in separate translation units so they compile in parallel
 UNITS = [('dp_capi', 'dp_capi.cu', [])] + [
     (f'dp_of2_inst_p{p}_{i}', 'dp_of2_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_IN={i}'])
-    for p in (1, 0) for i in (0, 1, 2, 3)] + [
+    for p in (1, 0) for i in (0, 1, 2, 3, 4, 5)] + [
     (f'dp_trig_inst_p{p}', 'dp_trig_inst.cu', [f'-DDP_INST_PREC={p}']) for p in (1, 0)] + [
     (f'dp_nxm_inst_p{p}_{c}', 'dp_nxm_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_NCH={c}']) for p in (1, 0) for c in (1, 2, 3, 4)] + [
     (f'dp_csd_inst_p{p}_{c}', 'dp_csd_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_NCH={c}']) for p in (1, 0) for c in (2, 3, 4)] + [

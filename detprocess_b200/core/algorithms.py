@@ -88,6 +88,25 @@ def _empty(trace):
 class FeatureExtractors:
 
     @staticmethod
+    def _of_fit_spec(base_algorithm, channel, of_base, template_tag=None, lowchi2_fcutoff=10000,
+                     window_min_from_trig_usec=None, window_max_from_trig_usec=None, window_min_index=None,
+                     window_max_index=None, lgc_outside_window=False, **kwargs):
+        """(template_tag, lo, hi, outside, lowchi2_fcutoff) of the delay search an of1x1_* block will request -- lets the
+        pipeline register every fit before the first batch (underscore name: not an algorithm, reference
+        process/features.py:1112-1116)"""
+        if base_algorithm == 'of1x1_nodelay':
+            pre = of_base.pretrigger_samples(channel, template_tag)
+            return template_tag, pre, pre + 1, False, lowchi2_fcutoff
+        if base_algorithm == 'of1x1_unconstrained':
+            return ('default' if template_tag is None else template_tag), None, None, False, lowchi2_fcutoff
+        if base_algorithm == 'of1x1_constrained':
+            tag = 'default' if template_tag is None else template_tag
+            lo, hi = _of_window(of_base, channel, tag, window_min_from_trig_usec, window_max_from_trig_usec,
+                                window_min_index, window_max_index)
+            return tag, lo, hi, bool(lgc_outside_window), lowchi2_fcutoff
+        return None
+
+    @staticmethod
     def of1x1_nodelay(channel, of_base, template_tag=None, lowchi2_fcutoff=10000,
                       feature_base_name='of1x1_nodelay', **kwargs):
         if template_tag is None:
@@ -95,9 +114,8 @@ class FeatureExtractors:
         names = ('amp', 'chi2', 'lowchi2')
         if not of_base.is_signal_stored(channel):
             return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
-        of_base.set_lowchi2_fcutoff(lowchi2_fcutoff)
         pre = of_base.pretrigger_samples(channel, template_tag)
-        r = of_base.results(of_base.request_fit(channel, template_tag, pre, pre + 1))
+        r = of_base.results(of_base.request_fit(channel, template_tag, pre, pre + 1, lowchi2_fcutoff=lowchi2_fcutoff))
         return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
 
     @staticmethod
@@ -108,8 +126,7 @@ class FeatureExtractors:
             return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
         if interpolate:
             raise NotImplementedError('interpolate=True (parabolic t0 refinement) is not built')
-        of_base.set_lowchi2_fcutoff(lowchi2_fcutoff)
-        r = of_base.results(of_base.request_fit(channel, template_tag, None, None))
+        r = of_base.results(of_base.request_fit(channel, template_tag, None, None, lowchi2_fcutoff=lowchi2_fcutoff))
         return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
 
     @staticmethod
@@ -123,10 +140,9 @@ class FeatureExtractors:
             return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
         if interpolate:
             raise NotImplementedError('interpolate=True (parabolic t0 refinement) is not built')
-        of_base.set_lowchi2_fcutoff(lowchi2_fcutoff)
         lo, hi = _of_window(of_base, channel, template_tag, window_min_from_trig_usec,
                             window_max_from_trig_usec, window_min_index, window_max_index)
-        r = of_base.results(of_base.request_fit(channel, template_tag, lo, hi, lgc_outside_window))
+        r = of_base.results(of_base.request_fit(channel, template_tag, lo, hi, lgc_outside_window, lowchi2_fcutoff=lowchi2_fcutoff))
         return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
 
     @staticmethod

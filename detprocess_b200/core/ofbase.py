@@ -33,6 +33,9 @@ class OFBaseBatch:
         self._plan_key = None
         self._handles = {}
         self._signals = {}     # chan -> tensor [B, N]
+        self._batch = None     # reader batch [B, n_file_chan, N] (or streams [n_file_chan, L]) consumed in place
+        self._batch_rows = {}  # chan -> row of the batch
+        self._batch_starts = None   # window mode: int64 [B] first sample of every event in the streams
         self._out = None       # host ndarray [B, n_out]
         # joint channels 'a|b|c' (NxM filter): csd [n, n, N], templates {tag: ([n, m, N], pretrigger)}
         self._nxm_csd = {}
@@ -158,13 +161,14 @@ class OFBaseBatch:
             self._plan = None
 
     def set_lowchi2_fcutoff(self, fcutoff):
-        if float(fcutoff) != self._fcut:
-            self._fcut = float(fcutoff)
-            self._plan = None
+        """default cutoff of fits requested WITHOUT their own ``lowchi2_fcutoff`` (every fit carries its own: two YAML
+        blocks with different cutoffs share one plan and one launch)"""
+        self._fcut = float(fcutoff)
 
     # ---- fits (one per YAML OF algorithm block) ---------------------------------
-    def request_fit(self, channel, template_tag, lo, hi, outside=False):
-        key = (channel, template_tag, None if lo is None else int(lo), None if hi is None else int(hi), bool(outside))
+    def request_fit(self, channel, template_tag, lo, hi, outside=False, lowchi2_fcutoff=None):
+        fcut = self._fcut if lowchi2_fcutoff is None else float(lowchi2_fcutoff)
+        key = (channel, template_tag, None if lo is None else int(lo), None if hi is None else int(hi), bool(outside), fcut)
         if key not in self._fits:
             if channel not in self._templates or template_tag not in self._templates[channel]:
                 raise ValueError(f'ERROR: no template "{template_tag}" for channel {channel}')
@@ -181,7 +185,6 @@ class OFBaseBatch:
             if not chans:
                 raise ValueError('ERROR: no channel has both a csd and a template')
             plan = OFPlan(self._nbins, self._fs, len(chans), self._precision)
-            plan.set_lowchi2_fcutoff(self._fcut)
             handles = {}
             for ci, chan in enumerate(chans):
                 psd, coupling = self._psd[chan]
@@ -191,9 +194,9 @@ class OFBaseBatch:
                 for tag, (tmpl, pre, inorm) in self._templates[chan].items():
                     handles[('templ', chan, tag)] = (ci, plan.add_template(ci, tmpl, pre, inorm))
             for key in self._fits:
-                chan, tag, lo, hi, outside = key
+                chan, tag, lo, hi, outside, fcut = key
                 ci, ti = handles[('templ', chan, tag)]
-                handles[('fit',) + key] = (ci, plan.add_fit(ci, ti, lo, hi, outside))
+                handles[('fit',) + key] = (ci, plan.add_fit(ci, ti, lo, hi, outside, lowchi2_fcutoff=fcut))
             self._plan, self._handles, self._plan_chans = plan, handles, chans
             self._out = None
         if finalize and not self._plan.finalized:
@@ -202,11 +205,23 @@ class OFBaseBatch:
     # ---- per batch --------------------------------------------------------------
     def clear_signal(self):
         self._signals = {}
+        self._batch, self._batch_rows, self._batch_starts = None, {}, None
         self._out = None
         self._nxm_out = {}
 
     def is_signal_stored(self, channel):
-        return channel in self._signals
+        return channel in self._signals or channel in self._batch_rows
+
+    def update_batch(self, batch, rows, start_index=None):
+        """The batched form of ``update_signal`` for plain channels: ``batch`` is the reader's device tensor
+        [B, n_file_chan, N] (f64 / f32 / i16) and ``rows`` maps channel name -> its row; the kernel reads the rows where
+        they are (``dp_of1x1_batch_ex``).  With ``start_index`` (int64 [B]) ``batch`` holds continuous streams
+        [n_file_chan, L] and event i is the window that starts at sample ``start_index[i]`` -- the reference's
+        ``read_single_event(trigger_index, trace_length_samples, pretrigger_length_samples)``
+        (processing_data.py:643-688) without the staging copy."""
+        self._batch, self._batch_rows, self._batch_starts = batch, dict(rows), start_index
+        self._single = False
+        self._out = None
 
     def update_signal(self, channel, signal, calc_fft=True, **kwargs):
         """signal: [N] or [B, N]; ndarray, CPU tensor or CUDA tensor (f64 / f32 / i16)."""
@@ -243,6 +258,18 @@ class OFBaseBatch:
         import torch
         self._ensure_plan()
         chans = self._plan_chans
+        if self._batch is not None and all(c in self._batch_rows for c in chans):
+            out = self._plan.run_layout(self._batch, [self._batch_rows[c] for c in chans], self._batch_starts)
+            self._out = out.cpu().numpy()
+            return
+        if self._batch is not None and self._batch_starts is None:
+            import torch as _t
+            for c in chans:       # mixed case: a plain channel next to a combined (float64) one -> float64 amps
+                if c not in self._signals and c in self._batch_rows:
+                    x = self._batch[:, self._batch_rows[c], :]
+                    if x.dtype == _t.int16 and c in self._adc:
+                        x = x.to(_t.float64) * self._adc[c][0] + self._adc[c][1]     # numpy's two roundings
+                    self._signals[c] = x.to(_t.float64)
         missing = [c for c in chans if c not in self._signals]
         if missing:
             raise ValueError(f'ERROR: no signal stored for channel(s) {missing}')

@@ -44,6 +44,41 @@ def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _layout_args(base, n_chan, nb_samples, chan_rows, start_index):
+    """Arguments of the ``*_batch_ex`` entry points for a reader-shaped tensor.
+
+    batch mode  (start_index None): ``base`` [B, n_rows, N] contiguous; plan channel c = row ``chan_rows[c]``.
+    window mode (start_index given): ``base`` [n_rows, L] contiguous continuous streams; event i = the N samples that
+    start at ``start_index[i]`` of every stream."""
+    torch = _torch()
+    if not base.is_cuda:
+        raise ValueError('device tensors only')
+    base = base.contiguous()
+    rows = list(range(n_chan)) if chan_rows is None else [int(r) for r in chan_rows]
+    if len(rows) != n_chan:
+        raise ValueError(f'expected {n_chan} channel rows, got {len(rows)}')
+    if start_index is None:
+        if base.ndim == 2:
+            base = base[:, None, :]
+        if base.ndim != 3 or base.shape[-1] != nb_samples:
+            raise ValueError('batch must be [n_events, n_rows, nb_samples]')
+        nev, nrows, row_len = base.shape
+        starts, n_stream = None, 0
+        event_stride = nrows * row_len
+    else:
+        if base.ndim == 1:
+            base = base[None, :]
+        if base.ndim != 2:
+            raise ValueError('streams must be [n_rows, n_stream_samples]')
+        nrows, row_len = base.shape
+        starts = start_index.to(device=base.device, dtype=torch.int64).contiguous()
+        nev, n_stream, event_stride = int(starts.shape[0]), row_len, 0
+    if any(r < 0 or r >= nrows for r in rows):
+        raise ValueError('channel row out of range')
+    offs = (C.c_longlong * n_chan)(*[r * row_len for r in rows])
+    return base, nev, event_stride, offs, row_len, starts, n_stream
+
+
 class OFPlan:
     """Batched OF1x1 plan: PSD + templates + delay-search fits for ``n_chan`` channels."""
 
@@ -88,11 +123,13 @@ class OFPlan:
         self.pretriggers[(int(chan), idx.value)] = int(pretrigger_samples)
         return idx.value
 
-    def add_fit(self, chan, templ, window_lo=None, window_hi=None, outside=False):
+    def add_fit(self, chan, templ, window_lo=None, window_hi=None, outside=False, lowchi2_fcutoff=None):
+        """``lowchi2_fcutoff``: this fit's own cutoff (Hz); None = the plan default (``set_lowchi2_fcutoff``)."""
         lo = 0 if window_lo is None else int(window_lo)
         hi = self.nb_samples if window_hi is None else int(window_hi)
         idx = C.c_int(-1)
-        check(lib.dp_of_plan_add_fit(self._h, int(chan), int(templ), lo, hi, int(bool(outside)), C.byref(idx)))
+        check(lib.dp_of_plan_add_fit_ex(self._h, int(chan), int(templ), lo, hi, int(bool(outside)),
+                                        -1.0 if lowchi2_fcutoff is None else float(lowchi2_fcutoff), C.byref(idx)))
         self.fits[(int(chan), idx.value)] = (int(templ), lo, hi, bool(outside))
         return idx.value
 
@@ -178,6 +215,23 @@ class OFPlan:
             out = torch.empty((nev, self.n_out), dtype=torch.float64, device=traces.device)
         check(lib.dp_of1x1_batch(self._h, C.c_void_p(traces.data_ptr()), _in_dtype_of(traces), nev,
                                  self.nb_samples, C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
+        return out
+
+    def run_layout(self, base, chan_rows=None, start_index=None, out=None):
+        """The batch consumed where the reader put it (``dp_of1x1_batch_ex``): ``base`` is the reader's device batch
+        [B, n_file_chan, N] (f64 / f32 / i16) and plan channel c reads row ``chan_rows[c]`` of every event -- no
+        gather / stack copy.  With ``start_index`` (int64 [n_events]) ``base`` is [n_file_chan, L] continuous streams
+        and event i is the window starting at sample ``start_index[i]`` of the plan's channel rows (what the reference
+        reads per trigger, processing_data.py:643-688); windows that leave the stream give -999999.0.  Async."""
+        torch = _torch()
+        if not self.finalized:
+            raise _lib.DetprocessB200Error('plan not finalized')
+        base, nev, event_stride, offs, row_len, starts, n_stream = _layout_args(base, self.n_chan, self.nb_samples, chan_rows, start_index)
+        if out is None:
+            out = torch.empty((nev, self.n_out), dtype=torch.float64, device=base.device)
+        check(lib.dp_of1x1_batch_ex(self._h, C.c_void_p(base.data_ptr()), _in_dtype_of(base), nev, event_stride, offs, row_len,
+                                    C.c_void_p(starts.data_ptr()) if starts is not None else None, n_stream,
+                                    C.c_void_p(out.data_ptr()), _stream_ptr(base.device)))
         return out
 
     def run_windows(self, stream, start_index, out=None):
@@ -391,10 +445,68 @@ class ReducePlan:
                                              C.c_void_p(out.data_ptr()), _stream_ptr(traces.device)))
         return out
 
+    def run_layout(self, base, chan_rows=None, start_index=None, out=None):
+        """``OFPlan.run_layout`` for the window reductions (``dp_window_reduce_batch_ex``): float64 or int16 reader batch
+        [B, n_file_chan, N] consumed in place, or windows of continuous streams [n_file_chan, L] at ``start_index``."""
+        torch = _torch()
+        if not self.finalized:
+            raise _lib.DetprocessB200Error('plan not finalized')
+        if base.dtype not in (torch.float64, torch.int16):
+            raise ValueError('run_layout() takes float64 or int16 CUDA tensors')
+        base, nev, event_stride, offs, row_len, starts, n_stream = _layout_args(base, self.n_chan, self.nb_samples, chan_rows, start_index)
+        if out is None:
+            out = torch.empty((nev, self.n_out), dtype=torch.float64, device=base.device)
+        check(lib.dp_window_reduce_batch_ex(self._h, C.c_void_p(base.data_ptr()), _in_dtype_of(base), nev, event_stride, offs, row_len,
+                                            C.c_void_p(starts.data_ptr()) if starts is not None else None, n_stream,
+                                            C.c_void_p(out.data_ptr()), _stream_ptr(base.device)))
+        return out
+
     def last_kernel_ms(self):
         ms = C.c_float()
         check(lib.dp_reduce_plan_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+def combine_channels(batch, terms, adc=None, out=None):
+    """Weighted channel algebra on the device in ONE launch (``dp_channel_combine``; reference
+    ``ProcessingData.get_channel_trace``, processing_data.py:1033-1047).
+
+    batch : CUDA tensor [B, n_file_chan, N] (f64 / f32 / i16) as the reader delivered it
+    terms : list (one entry per combined channel) of lists of ``(row, weight)``; weight None = plain ``a + b`` /
+            ``a - b`` (pass ``(row, None, sign)`` with sign -1 for the subtrahend)
+    adc   : {row: (gain, offset)} for int16 batches
+    Returns float64 [B, len(terms), N], bit-identical to numpy on the host-converted traces."""
+    torch = _torch()
+    if not batch.is_cuda or batch.ndim != 3:
+        raise ValueError('combine_channels() takes a CUDA batch [B, n_chan, N]')
+    batch = batch.contiguous()
+    nb, nrows, n = batch.shape
+    n_out = len(terms)
+    if not 1 <= n_out <= 8:
+        raise ValueError('1..8 combined channels per call')
+    nt = (C.c_int * n_out)()
+    offs = (C.c_longlong * (4 * n_out))()
+    w = (C.c_double * (4 * n_out))()
+    weighted = (C.c_int * n_out)()
+    gain = (C.c_double * (4 * n_out))(*([1.0] * (4 * n_out)))
+    aoff = (C.c_double * (4 * n_out))()
+    for j, tl in enumerate(terms):
+        if not 1 <= len(tl) <= 4:
+            raise ValueError('1..4 terms per combined channel')
+        nt[j] = len(tl)
+        weighted[j] = int(all(t[1] is not None for t in tl))
+        for k, t in enumerate(tl):
+            row = int(t[0])
+            sign = float(t[2]) if len(t) > 2 else 1.0
+            offs[4 * j + k] = row * n
+            w[4 * j + k] = float(t[1]) * sign if t[1] is not None else sign
+            if adc is not None and row in adc:
+                gain[4 * j + k], aoff[4 * j + k] = float(adc[row][0]), float(adc[row][1])
+    if out is None:
+        out = torch.empty((nb, n_out, n), dtype=torch.float64, device=batch.device)
+    check(lib.dp_channel_combine(C.c_void_p(batch.data_ptr()), _in_dtype_of(batch), nb, nrows * n, n, n_out, nt, offs, w, weighted,
+                                 gain, aoff, C.c_void_p(out.data_ptr()), _stream_ptr(batch.device)))
+    return out
 
 
 class PSDPlan:

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/detprocess_b200.h"
+#include "dp_combine_kernel.cuh"
 #include "dp_csd_kernel.cuh"
 #include "dp_csd_launch.hpp"
 #include "dp_nxm_launch.hpp"
@@ -109,6 +110,8 @@ struct dp_of_plan {
     double scale = 1.0;
     int subtract_first = 0;
     std::vector<double> adc_gain, adc_offset;  // per channel, int16 traces only
+    long long* d_chan_off = nullptr;           // [n_chan] channel offsets of the last dp_of1x1_batch_ex layout
+    std::vector<long long> chan_off_host;      // what d_chan_off holds
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     long long launches = 0;
@@ -124,6 +127,14 @@ struct dp_of_plan {
 };
 
 namespace {
+// the low-frequency tables (chi0 weights, template spectrum) reach up to the highest lowchi2_fcutoff any fit asks for
+static double table_fcut(const dp_of_plan* p) {
+    double f = -1.0;
+    for (const auto& ch : p->chans)
+        for (const auto& ft : ch.fits) f = std::max(f, ft.fcut < 0 ? p->fcut : ft.fcut);
+    return f < 0 ? p->fcut : f;
+}
+
 
 template <class T> int of_setup(dp_of_plan* p) {
     const int prec = sizeof(T) == 8 ? 0 : 1;
@@ -150,7 +161,7 @@ template <class T> int of_launch(dp_of_plan* p, const DpOfParams<T>& prm, int gr
 template <class T> int of_finalize(dp_of_plan* p) {
     dpplan::DeviceTables<T> dt;
     try {
-        dt = dpplan::build_tables<T>(p->geom, p->fs, p->chans, p->fcut, p->scale);
+        dt = dpplan::build_tables<T>(p->geom, p->fs, p->chans, table_fcut(p), p->scale);
     } catch (const std::exception& e) {
         return fail(DP_ERR_INVALID, e.what());
     }
@@ -200,7 +211,7 @@ template <class T> int of_finalize(dp_of_plan* p) {
         }
         for (int i = 0; i < dc.n_slots; ++i) {
             const auto& f = p->chans[c].fits[i];
-            dc.slots[i] = DpSlot{f.templ, f.lo, f.hi, f.outside};
+            dc.slots[i] = DpSlot{f.templ, f.lo, f.hi, f.outside, std::min(p->nlow, dpplan::count_low_bins(p->N, p->fs, f.fcut < 0 ? p->fcut : f.fcut))};
         }
     }
     p->n_out = base;
@@ -214,13 +225,31 @@ template <class T> int of_finalize(dp_of_plan* p) {
     return DP_OK;
 }
 
+// where the first sample of (event, channel) sits: see Dp2Params
+struct OfLayout {
+    long long event_stride = 0, chan_stride = 0;
+    const long long* chan_offset_dev = nullptr;
+    const long long* row_start = nullptr;
+    long long stream_len = 0;
+};
+static OfLayout default_layout(int n_chan, long long row_stride) {
+    OfLayout l;
+    l.event_stride = (long long)n_chan * row_stride;
+    l.chan_stride = row_stride;
+    return l;
+}
+
 template <class T>
-int of_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride, double* out_dev,
+int of_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, const OfLayout& lay, double* out_dev,
            cudaStream_t st, bool timed) {
+    if (lay.row_start != nullptr || in_dtype > DP_IN_I16)
+        return fail(DP_ERR_UNSUPPORTED, "windows of a continuous stream need nb_samples 16384, 32768 or 65536");
     DpOfParams<T> prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.traces = traces_dev;
-    prm.row_stride = row_stride;
+    prm.event_stride = lay.event_stride;
+    prm.chan_stride = lay.chan_stride;
+    prm.chan_offset = lay.chan_offset_dev;
     prm.n_rows = (int)(n_events * p->n_chan);
     prm.n_chan = p->n_chan;
     prm.chans = reinterpret_cast<const DpChanDev<T>*>(p->d_chans);
@@ -252,9 +281,9 @@ template <class T> int of2_finalize(dp_of_plan* p) {
     dpplan2::Tables2<T> dt;
     try {
         switch (p->v2_r1) {
-            case 2: dt = dpplan2::build_tables2<T, 2>(p->fs, p->chans, p->fcut, p->scale); break;
-            case 4: dt = dpplan2::build_tables2<T, 4>(p->fs, p->chans, p->fcut, p->scale); break;
-            default: dt = dpplan2::build_tables2<T, 8>(p->fs, p->chans, p->fcut, p->scale); break;
+            case 2: dt = dpplan2::build_tables2<T, 2>(p->fs, p->chans, table_fcut(p), p->scale); break;
+            case 4: dt = dpplan2::build_tables2<T, 4>(p->fs, p->chans, table_fcut(p), p->scale); break;
+            default: dt = dpplan2::build_tables2<T, 8>(p->fs, p->chans, table_fcut(p), p->scale); break;
         }
     } catch (const std::invalid_argument& e) {
         return fail(DP_ERR_INVALID, e.what());
@@ -320,7 +349,7 @@ template <class T> int of2_finalize(dp_of_plan* p) {
         }
         for (int i = 0; i < dc.n_slots; ++i) {
             const auto& f = p->chans[c].fits[i];
-            dc.slots[i] = DpSlot{f.templ, f.lo, f.hi, f.outside};
+            dc.slots[i] = DpSlot{f.templ, f.lo, f.hi, f.outside, std::min(p->nlow, dpplan::count_low_bins(p->N, p->fs, f.fcut < 0 ? p->fcut : f.fcut))};
         }
     }
     p->n_out = base;
@@ -328,7 +357,7 @@ template <class T> int of2_finalize(dp_of_plan* p) {
     if ((rc = upload(p->owned, cd, &dcd))) return rc;
     p->d_chans = dcd;
     const int prec = sizeof(S) == 8 ? 0 : 1;
-    for (int in = 0; in < 4; ++in) {
+    for (int in = 0; in < 6; ++in) {
         size_t smem = 0;
         int grid_max = 0, occ = 0, threads = 0;
         const int src = dp_of2_setup_table[prec][in](p->v2_r1, p->device, &smem, &grid_max, &occ, &threads);
@@ -370,13 +399,15 @@ template <class T> int of2_finalize(dp_of_plan* p) {
 }
 
 template <class T>
-int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride, double* out_dev,
-            cudaStream_t st, bool timed, const long long* row_start = nullptr, long long stream_len = 0) {
+int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, const OfLayout& lay, double* out_dev,
+            cudaStream_t st, bool timed) {
     using S = typename Dp2Traits<T>::S;
     Dp2Params<T> prm;
     std::memset(&prm, 0, sizeof(prm));
     prm.traces = traces_dev;
-    prm.row_stride = row_stride;
+    prm.event_stride = lay.event_stride;
+    prm.chan_stride = lay.chan_stride;
+    prm.chan_offset = lay.chan_offset_dev;
     prm.n_rows = (int)(n_events * p->n_chan);
     prm.n_chan = p->n_chan;
     prm.chans = reinterpret_cast<const Dp2ChanDev<T>*>(p->d_chans);
@@ -398,8 +429,8 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
         const char* e = std::getenv("DP2_SKEW_NS");  // development switch
         prm.skew_ns = e ? std::atoi(e) : DP2_SKEW_NS;
     }
-    prm.row_start = row_start;
-    prm.stream_len = stream_len;
+    prm.row_start = lay.row_start;
+    prm.stream_len = lay.stream_len;
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
     const int prec = sizeof(S) == 8 ? 0 : 1;
@@ -413,14 +444,14 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
 }
 
 // precision / kernel-generation dispatch of one batch launch
-int of_dispatch(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride, double* out_dev,
+int of_dispatch(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, const OfLayout& lay, double* out_dev,
                 cudaStream_t st, bool timed) {
     if (p->v2_r1) {
-        if (p->precision == DP_PREC_F32) return of2_run<f2>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
-        return of2_run<double>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
+        if (p->precision == DP_PREC_F32) return of2_run<f2>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
+        return of2_run<double>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
     }
-    if (p->precision == DP_PREC_F32) return of_run<float>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
-    return of_run<double>(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, timed);
+    if (p->precision == DP_PREC_F32) return of_run<float>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
+    return of_run<double>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
 }
 
 int of_check(const dp_of_plan* p, int chan) {
@@ -515,7 +546,8 @@ int dp_of_plan_add_template(dp_of_plan* p, int chan, const double* templ, int pr
     return DP_OK;
 }
 
-int dp_of_plan_add_fit(dp_of_plan* p, int chan, int templ_index, int window_lo, int window_hi, int outside, int* fit_index) {
+int dp_of_plan_add_fit_ex(dp_of_plan* p, int chan, int templ_index, int window_lo, int window_hi, int outside,
+                          double lowchi2_fcutoff_hz, int* fit_index) {
     int rc = of_check(p, chan);
     if (rc) return rc;
     if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
@@ -527,13 +559,19 @@ int dp_of_plan_add_fit(dp_of_plan* p, int chan, int templ_index, int window_lo, 
         for (const auto& f : ch.fits) nt += f.templ == templ_index;
         if (nt >= DP_MAX_TSLOTS) return fail(DP_ERR_UNSUPPORTED, "too many fits for one template");
     }
+    if (lowchi2_fcutoff_hz >= 0 && !std::isfinite(lowchi2_fcutoff_hz)) return fail(DP_ERR_INVALID, "lowchi2_fcutoff must be finite");
     window_lo = std::min(std::max(window_lo, 0), p->N);
     window_hi = std::min(std::max(window_hi, 0), p->N);
     const int ncand = outside ? p->N - std::max(0, window_hi - window_lo) : window_hi - window_lo;
     if (ncand <= 0) return fail(DP_ERR_INVALID, "empty OF delay window");
-    ch.fits.push_back(dpplan::Fit{templ_index, window_lo, window_hi, outside ? 1 : 0});
+    dpplan::Fit f{templ_index, window_lo, window_hi, outside ? 1 : 0};
+    f.fcut = lowchi2_fcutoff_hz;
+    ch.fits.push_back(f);
     if (fit_index) *fit_index = (int)ch.fits.size() - 1;
     return DP_OK;
+}
+int dp_of_plan_add_fit(dp_of_plan* p, int chan, int templ_index, int window_lo, int window_hi, int outside, int* fit_index) {
+    return dp_of_plan_add_fit_ex(p, chan, templ_index, window_lo, window_hi, outside, -1.0, fit_index);
 }
 
 int dp_of_plan_set_lowchi2_fcutoff(dp_of_plan* p, double fcutoff_hz) {
@@ -657,25 +695,67 @@ int dp_of1x1_batch(dp_of_plan* p, const void* traces_dev, int in_dtype, long lon
     if ((reinterpret_cast<uintptr_t>(traces_dev) % (2 * esz)) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
     if (n_events * p->n_chan > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return of_dispatch(p, traces_dev, in_dtype, n_events, row_stride, out_dev, st, true);
+    return of_dispatch(p, traces_dev, in_dtype, n_events, default_layout(p->n_chan, row_stride), out_dev, st, true);
+}
+
+int dp_of1x1_batch_ex(dp_of_plan* p, const void* base_dev, int in_dtype, long long n_events, long long event_stride,
+                      const long long* chan_offsets, long long chan_stride, const long long* start_index_dev,
+                      long long n_stream_samples, double* out_dev, void* stream) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    DP_ON_DEVICE(p->device);
+    if (n_events < 0 || n_stream_samples < 0) return fail(DP_ERR_INVALID, "negative size");
+    if (n_events == 0) return DP_OK;
+    if (!base_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
+    if (n_events * p->n_chan > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    const size_t esz = in_dtype == DP_IN_F64 ? 8 : (in_dtype == DP_IN_F32 ? 4 : 2);
+    if ((reinterpret_cast<uintptr_t>(base_dev) % esz) != 0) return fail(DP_ERR_INVALID, "trace buffer misaligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    OfLayout lay;
+    lay.event_stride = event_stride;
+    lay.chan_stride = chan_stride;
+    lay.row_start = start_index_dev;
+    lay.stream_len = n_stream_samples;
+    // rows aligned to a sample pair take the vector loads; anything else (windows, odd strides / offsets) the
+    // element-aligned instantiation (in_dtype + 3)
+    bool pair_aligned = start_index_dev == nullptr && (reinterpret_cast<uintptr_t>(base_dev) % (2 * esz)) == 0 &&
+                        (event_stride % 2) == 0 && (chan_stride % 2) == 0;
+    if (start_index_dev == nullptr) {
+        if (event_stride < 0) return fail(DP_ERR_INVALID, "negative event_stride");
+    } else if (n_stream_samples < p->N) {
+        // every window leaves the stream: the kernel writes the sentinels
+    }
+    if (chan_offsets != nullptr) {
+        for (int c = 0; c < p->n_chan; ++c) {
+            if (chan_offsets[c] < 0) return fail(DP_ERR_INVALID, "negative channel offset");
+            pair_aligned = pair_aligned && (chan_offsets[c] % 2) == 0;
+        }
+        // the offsets live in a small device array owned by the plan, refreshed only when they change
+        if (p->d_chan_off == nullptr) {
+            DP_CUDA(cudaMalloc(&p->d_chan_off, sizeof(long long) * (size_t)p->n_chan));
+            p->owned.push_back(p->d_chan_off);
+        }
+        if (p->chan_off_host.size() != (size_t)p->n_chan || !std::equal(p->chan_off_host.begin(), p->chan_off_host.end(), chan_offsets)) {
+            // (synchronous: a layout change is a configuration step, not part of the steady state)
+            DP_CUDA(cudaStreamSynchronize(st));
+            DP_CUDA(cudaMemcpy(p->d_chan_off, chan_offsets, sizeof(long long) * (size_t)p->n_chan, cudaMemcpyHostToDevice));
+            p->chan_off_host.assign(chan_offsets, chan_offsets + p->n_chan);
+        }
+        lay.chan_offset_dev = p->d_chan_off;
+    }
+    const int in = pair_aligned ? in_dtype : in_dtype + 3;
+    if (!pair_aligned && !p->v2_r1) return fail(DP_ERR_UNSUPPORTED, "element-aligned rows / windows need nb_samples 16384, 32768 or 65536");
+    return of_dispatch(p, base_dev, in, n_events, lay, out_dev, st, true);
 }
 
 int dp_of1x1_windows(dp_of_plan* p, const double* stream_dev, long long n_stream_samples, const long long* start_index_dev,
                      long long n_events, double* out_dev, void* stream) {
     if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
-    DP_ON_DEVICE(p->device);
     if (!p->v2_r1) return fail(DP_ERR_UNSUPPORTED, "window mode needs nb_samples 16384, 32768 or 65536");
-    if (p->n_chan != 1) return fail(DP_ERR_UNSUPPORTED, "window mode is single channel");
-    if (n_events < 0 || n_stream_samples < 0) return fail(DP_ERR_INVALID, "negative size");
-    if (n_events == 0) return DP_OK;
-    if (!stream_dev || !start_index_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
-    if ((reinterpret_cast<uintptr_t>(stream_dev) & 7) != 0) return fail(DP_ERR_INVALID, "stream buffer misaligned");
-    if (n_events > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // IN = 3: float64 rows that are only 8-byte aligned (a window may start at an odd sample)
-    if (p->precision == DP_PREC_F32)
-        return of2_run<f2>(p, stream_dev, 3, n_events, 0, out_dev, st, true, start_index_dev, n_stream_samples);
-    return of2_run<double>(p, stream_dev, 3, n_events, 0, out_dev, st, true, start_index_dev, n_stream_samples);
+    if (p->n_chan != 1) return fail(DP_ERR_UNSUPPORTED, "dp_of1x1_windows is single channel; dp_of1x1_batch_ex takes n_chan streams");
+    if (!start_index_dev) return fail(DP_ERR_INVALID, "null buffer");
+    return dp_of1x1_batch_ex(p, stream_dev, DP_IN_F64, n_events, 0, nullptr, n_stream_samples, start_index_dev, n_stream_samples,
+                             out_dev, stream);
 }
 
 int dp_of_plan_last_kernel_ms(dp_of_plan* p, float* ms) {
@@ -740,7 +820,7 @@ int dp_of1x1_batch_host(dp_of_plan* p, const void* traces_host, int in_dtype, lo
         const long long ne = std::min(chunk, n_events - e0);
         cudaStream_t st = p->streams[k];
         DP_CUDA(cudaMemcpyAsync(p->stage_dev[k], src + (size_t)e0 * ev_bytes, ev_bytes * (size_t)ne, cudaMemcpyHostToDevice, st));
-        int rc = of_dispatch(p, p->stage_dev[k], in_dtype, ne, row_stride, p->stage_out[k], st, false);
+        int rc = of_dispatch(p, p->stage_dev[k], in_dtype, ne, default_layout(p->n_chan, row_stride), p->stage_out[k], st, false);
         if (rc) return rc;
         DP_CUDA(cudaMemcpyAsync(p->stage_out_host + (size_t)e0 * p->n_out, p->stage_out[k], sizeof(double) * (size_t)p->n_out * (size_t)ne,
                                 cudaMemcpyDeviceToHost, st));
@@ -767,6 +847,8 @@ struct dp_reduce_plan {
     const DpRedFeat* d_feats = nullptr;
     std::vector<double> adc;  // [n_chan][2] gain, offset of int16 traces
     const double* d_adc = nullptr;
+    long long* d_chan_off = nullptr;       // [n_chan] channel offsets of the last dp_window_reduce_batch_ex layout
+    std::vector<long long> chan_off_host;
     int grid_max = 0;
     size_t smem = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -774,6 +856,51 @@ struct dp_reduce_plan {
 };
 
 extern "C" {
+
+int dp_channel_combine(const void* base_dev, int in_dtype, long long n_events, long long event_stride, int nb_samples, int n_out,
+                       const int* n_terms, const long long* offsets, const double* weights, const int* weighted,
+                       const double* adc_gain, const double* adc_offset, double* out_dev, void* stream) {
+    if (!base_dev || !out_dev || !n_terms || !offsets || !weights) return fail(DP_ERR_INVALID, "null buffer");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
+    if (n_events < 0 || nb_samples <= 0 || event_stride < 0) return fail(DP_ERR_INVALID, "negative size");
+    if (n_out < 1 || n_out > DP_COMBINE_MAX_OUT) return fail(DP_ERR_UNSUPPORTED, "1..8 combined channels per call");
+    if (n_events == 0) return DP_OK;
+    DpCombineParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.base = base_dev;
+    prm.event_stride = event_stride;
+    prm.n_events = n_events;
+    prm.nb_samples = nb_samples;
+    prm.n_out = n_out;
+    prm.out = out_dev;
+    for (int j = 0; j < n_out; ++j) {
+        if (n_terms[j] < 1 || n_terms[j] > DP_COMBINE_MAX_TERMS) return fail(DP_ERR_UNSUPPORTED, "1..4 terms per combined channel");
+        prm.n_terms[j] = n_terms[j];
+        prm.weighted[j] = weighted ? weighted[j] : 1;
+        for (int t = 0; t < n_terms[j]; ++t) {
+            const int k = j * DP_COMBINE_MAX_TERMS + t;
+            if (offsets[k] < 0) return fail(DP_ERR_INVALID, "negative input offset");
+            prm.off[j][t] = offsets[k];
+            prm.w[j][t] = weights[k];
+            prm.gain[j][t] = adc_gain ? adc_gain[k] : 1.0;
+            prm.offs[j][t] = adc_offset ? adc_offset[k] : 0.0;
+        }
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long total = n_events * (long long)n_out * nb_samples;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
+    if (in_dtype == DP_IN_F64)
+        dp_combine_kernel<0><<<grid, 256, 0, st>>>(prm);
+    else if (in_dtype == DP_IN_F32)
+        dp_combine_kernel<1><<<grid, 256, 0, st>>>(prm);
+    else
+        dp_combine_kernel<2><<<grid, 256, 0, st>>>(prm);
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
 
 int dp_reduce_plan_create(dp_reduce_plan** plan, int nb_samples, double sample_rate, int n_chan) {
     if (!plan) return fail(DP_ERR_INVALID, "null plan pointer");
@@ -874,18 +1001,44 @@ int dp_window_reduce_batch(dp_reduce_plan* p, const double* traces_dev, long lon
 int dp_window_reduce_batch_raw(dp_reduce_plan* p, const void* traces_dev, int in_dtype, long long n_events, long long row_stride,
                                double* out_dev, void* stream) {
     if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (row_stride < p->plan.nb_samples) return fail(DP_ERR_INVALID, "row_stride < nb_samples");
+    return dp_window_reduce_batch_ex(p, traces_dev, in_dtype, n_events, (long long)p->n_chan * row_stride, nullptr, row_stride, nullptr, 0,
+                                     out_dev, stream);
+}
+int dp_window_reduce_batch_ex(dp_reduce_plan* p, const void* base_dev, int in_dtype, long long n_events, long long event_stride,
+                              const long long* chan_offsets, long long chan_stride, const long long* start_index_dev,
+                              long long n_stream_samples, double* out_dev, void* stream) {
+    if (!p || !p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
     DP_ON_DEVICE(p->device);
     if (in_dtype != DP_IN_F64 && in_dtype != DP_IN_I16) return fail(DP_ERR_UNSUPPORTED, "window reductions take float64 or int16 traces");
-    if (n_events < 0) return fail(DP_ERR_INVALID, "negative n_events");
+    if (n_events < 0 || n_stream_samples < 0) return fail(DP_ERR_INVALID, "negative size");
     if (n_events == 0 || p->plan.n_out == 0) return DP_OK;
-    if (!traces_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
-    if (row_stride < p->plan.nb_samples) return fail(DP_ERR_INVALID, "row_stride < nb_samples");
+    if (!base_dev || !out_dev) return fail(DP_ERR_INVALID, "null buffer");
     if (n_events * p->n_chan > 2000000000LL) return fail(DP_ERR_INVALID, "batch too large; split it");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DpReduceParams prm;
     std::memset(&prm, 0, sizeof(prm));
-    prm.traces = traces_dev;
+    prm.traces = base_dev;
     prm.adc = p->d_adc;
-    prm.row_stride = row_stride;
+    prm.event_stride = event_stride;
+    prm.chan_stride = chan_stride;
+    prm.row_start = start_index_dev;
+    prm.stream_len = n_stream_samples;
+    prm.nb_samples = p->plan.nb_samples;
+    if (chan_offsets != nullptr) {
+        for (int c = 0; c < p->n_chan; ++c)
+            if (chan_offsets[c] < 0) return fail(DP_ERR_INVALID, "negative channel offset");
+        if (p->d_chan_off == nullptr) {
+            DP_CUDA(cudaMalloc(&p->d_chan_off, sizeof(long long) * (size_t)p->n_chan));
+            p->owned.push_back(p->d_chan_off);
+        }
+        if (p->chan_off_host.size() != (size_t)p->n_chan || !std::equal(p->chan_off_host.begin(), p->chan_off_host.end(), chan_offsets)) {
+            DP_CUDA(cudaStreamSynchronize(st));
+            DP_CUDA(cudaMemcpy(p->d_chan_off, chan_offsets, sizeof(long long) * (size_t)p->n_chan, cudaMemcpyHostToDevice));
+            p->chan_off_host.assign(chan_offsets, chan_offsets + p->n_chan);
+        }
+        prm.chan_offset = p->d_chan_off;
+    }
     prm.n_rows = (int)(n_events * p->n_chan);
     prm.n_chan = p->n_chan;
     prm.chans = p->d_chans;
@@ -897,7 +1050,6 @@ int dp_window_reduce_batch_raw(dp_reduce_plan* p, const void* traces_dev, int in
     prm.n_out = p->plan.n_out;
     prm.fs = p->plan.fs;
     prm.max_nodes = p->plan.max_nodes;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     DP_CUDA(cudaEventRecord(p->ev0, st));
     if (in_dtype == DP_IN_I16)

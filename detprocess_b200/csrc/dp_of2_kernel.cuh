@@ -189,7 +189,14 @@ template <class T> struct Dp2ChanDev {
 template <class T> struct Dp2Params {
     using S = typename Dp2Traits<T>::S;
     const void* traces;
-    long long row_stride;  // elements
+    // Input layout.  The first sample of (event ev, plan channel c) is element
+    //     (row_start ? row_start[ev] : ev * event_stride) + (chan_offset ? chan_offset[c] : c * chan_stride)
+    // of `traces`.  Default batches [n_events][n_chan][row_stride]: event_stride = n_chan * row_stride, chan_stride =
+    // row_stride.  A reader batch [B][n_file_chan][N] of which the plan uses some channels: chan_offset = file channel *
+    // N.  Window mode (row_start, below): the channels are continuous streams [n_chan][stream_stride].
+    long long event_stride;  // elements
+    long long chan_stride;   // elements
+    const long long* chan_offset;  // [n_chan] or null
     int n_rows;
     int n_chan;
     const Dp2ChanDev<T>* chans;
@@ -208,10 +215,10 @@ template <class T> struct Dp2Params {
     double scale;
     int subtract_first;
     int skew_ns;  // start delay of every second block (DP2_SKEW_NS unless the plan overrides it)
-    // window mode (single channel): event r is the N-sample window of one continuous stream that starts
-    // at sample row_start[r] (the step between the trigger and the features in the reference,
-    // processing_data.py:643-688); windows that stick out of [0, stream_len) get the -999999 sentinels
-    const long long* row_start;
+    // window mode: event ev is the N-sample window that starts at sample row_start[ev] of every channel's continuous
+    // stream (the step between the trigger and the features in the reference, processing_data.py:643-688); windows that
+    // stick out of [0, stream_len) get the -999999 sentinels
+    const long long* row_start;  // [n_events] or null
     long long stream_len;
 };
 
@@ -387,6 +394,17 @@ template <int IN> DP_DEV typename DpRaw<IN>::type dp2_load_pair(const void* row,
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v.y) : "l"(p1 + 1), "l"(pol));
     } else if constexpr (IN == 1) {
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(ptr), "l"(pol));
+    } else if constexpr (IN == 4) {
+        const float* p1 = reinterpret_cast<const float*>(row) + 2 * j;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v.x) : "l"(p1), "l"(pol));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v.y) : "l"(p1 + 1), "l"(pol));
+    } else if constexpr (IN == 5) {
+        const short* p1 = reinterpret_cast<const short*>(row) + 2 * j;
+        short a, b;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b16 %0, [%1], %2;" : "=h"(a) : "l"(p1), "l"(pol));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b16 %0, [%1], %2;" : "=h"(b) : "l"(p1 + 1), "l"(pol));
+        v.x = a;
+        v.y = b;
     } else {
         unsigned u;
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(u) : "l"(ptr), "l"(pol));
@@ -439,7 +457,7 @@ DP_DEV Dp2Raw<IN, VL> dp2_load_raw_clamped(const void* row, long long jbase, lon
 // fp64 mode computes on the samples as they are (the plans never scale or offset them); raw ADC counts (IN == 2)
 // become adc * sc - x0 with the channel's conversion (sc = gain, x0 = -offset)
 template <int IN> DP_DEV cx<double> dp2_convert(const Dp2Raw<IN, 1>& r, double x0, double sc) {
-    if constexpr (IN == 2) {
+    if constexpr (dp_in_is_adc(IN)) {
         return cx<double>{dp_fma((double)r.q[0].x, sc, -x0), dp_fma((double)r.q[0].y, sc, -x0)};
     } else {
         (void)x0;
@@ -918,7 +936,13 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
 #define DP2_NSP 0
 #endif
     static constexpr int NSP = (NT > 256) ? DP2_NSP : (DP2_NSP > 1 ? 1 : DP2_NSP);  // two 256-thread CTAs per SM leave room for one
-    static constexpr int PHI_ROWS_A = 8 + 4 * NSP, PHI_ROWS_B = 4 * NSP;
+    // two 256-thread CTAs per SM (packed fp32, 16384 samples) already overlap each other's table latency: there the
+    // rows are read through the read-only path when they are used (staging cost 4 % there, measured)
+#ifndef DP2_STAGE_MIN_NT
+#define DP2_STAGE_MIN_NT 257
+#endif
+    static constexpr bool STAGE = NT >= DP2_STAGE_MIN_NT;
+    static constexpr int PHI_ROWS_A = STAGE ? 8 + 4 * NSP : 0, PHI_ROWS_B = STAGE ? 4 * NSP : 0;
     static constexpr unsigned BYTES_A = 4 * DP2_PIECE + NSP * DP2_PIECE, BYTES_B = 4 * DP2_PIECE + NSP * DP2_PIECE;
     static_assert(sizeof(T) == 8 && sizeof(V) == 16, "table rows are 256 / 512 bytes per warp");
     static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (DP_NLOW_MAX + SP_ELEMS) +
@@ -963,6 +987,18 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         return s;
     }
 
+    // element index of the first sample of (event, channel); false: the window leaves the stream (window mode)
+    static DP_DEV bool first_sample(const Dp2Params<T>& prm, int ev, int chan, long long& first) {
+        long long base = (long long)ev * prm.event_stride;
+        bool ok = true;
+        if (prm.row_start != nullptr) {
+            base = prm.row_start[ev];
+            ok = base >= 0 && base + N <= prm.stream_len;
+        }
+        first = base + (prm.chan_offset != nullptr ? prm.chan_offset[chan] : (long long)chan * prm.chan_stride);
+        return ok;
+    }
+
     // next trace of this CTA -> L2, one bulk-prefetch instruction (TMA path, no LSU traffic) issued
     // by one thread at the start of the event; falls back to per-line prefetches when the row is
     // not 16-byte aligned
@@ -970,11 +1006,8 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
         const int nrow = row + gridDim.x;
         if (nrow < prm.n_rows) {
-            long long first = (long long)nrow * prm.row_stride;
-            if (prm.row_start != nullptr) {
-                first = prm.row_start[nrow];
-                if (first < 0 || first + N > prm.stream_len) return;
-            }
+            long long first;
+            if (!first_sample(prm, nrow / prm.n_chan, nrow % prm.n_chan, first)) return;
             const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)first * ESZ;
 #ifndef DP_HOST_EMU
             if ((reinterpret_cast<unsigned long long>(nx) & 15ull) == 0) {
@@ -995,24 +1028,36 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         unsigned v[4];      // pieces inside the warp's own group rows (valid between pass 4 and pass 4')
         unsigned s[NSP > 0 ? NSP : 1];    // private pieces
         const V* phi_g;     // the same filter rows in global memory (rows that were not staged), this lane
+        const T* wj_g;      // chi0 weights in global memory (!STAGE), this lane
+        const V* x_g;       // X column in the scratch (!STAGE), this lane
         template <class Q> DP_DEV Q at(unsigned off) const { return *reinterpret_cast<const Q*>(base + off); }
         // round A
-        DP_DEV T wj(int e) const { return at<T>(v[e >> 3] + (e & 7) * 256); }
+        DP_DEV T wj(int e) const {
+            if constexpr (!STAGE) return dp_ldg(wj_g + e * 32);
+            return at<T>(v[e >> 3] + (e & 7) * 256);
+        }
         DP_DEV V phi_a(int e) const {
+            if constexpr (!STAGE) return dp2_ld_stream(phi_g + e * 32);
             if (e < 8) return at<V>(v[2 + (e >> 2)] + (e & 3) * 512);
             if (e < PHI_ROWS_A) return at<V>(s[(e - 8) >> 2] + ((e - 8) & 3) * 512);
             return dp2_ld_stream(phi_g + e * 32);
         }
         // round B
-        DP_DEV V x(int e) const { return at<V>(v[e >> 2] + (e & 3) * 512); }
+        DP_DEV V x(int e) const {
+            if constexpr (!STAGE) return dp2_ld_keep(x_g + e * 32, dp2_policy_keep());
+            return at<V>(v[e >> 2] + (e & 3) * 512);
+        }
         DP_DEV V phi_b(int e) const {
             if (e < PHI_ROWS_B) return at<V>(s[e >> 2] + (e & 3) * 512);
             return dp2_ld_stream(phi_g + e * 32);
         }
     };
     // lane offsets folded in: wj pieces (round A, v[0], v[1]) are 8-byte rows, everything else 16-byte rows
-    static DP_DEV Staged staged_view(unsigned char* smem_raw, uint4 zo, unsigned spoff, int lane, bool round_a, const V* phi_lane) {
+    static DP_DEV Staged staged_view(unsigned char* smem_raw, uint4 zo, unsigned spoff, int lane, bool round_a, const V* phi_lane,
+                                     const T* wj_lane, const V* x_lane) {
         Staged t;
+        t.wj_g = wj_lane;
+        t.x_g = x_lane;
         const unsigned l16 = lane * 16, l8 = lane * 8;
         t.base = smem_raw;
         t.v[0] = zo.x + (round_a ? l8 : l16);
@@ -1240,18 +1285,17 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
         evpar ^= 1;
         if (tid < CH_WORDS) chs[tid] = reinterpret_cast<const int*>(prm.chans + chan)[tid];
         const Dp2ChanDev<T>& ch = *reinterpret_cast<const Dp2ChanDev<T>*>(chs);
-        long long first = (long long)row * prm.row_stride;
-        if (prm.row_start != nullptr) {
-            first = prm.row_start[row];
-            if (first < 0 || first + N > prm.stream_len) {  // CTA-uniform
-                for (int o = tid; o < prm.n_out; o += NT) prm.out[(long long)ev * prm.n_out + o] = -999999.0;
-                continue;
-            }
+        long long first;
+        if (!first_sample(prm, ev, chan, first)) {  // CTA-uniform: the window leaves the stream
+            const Dp2ChanDev<T>* chg = prm.chans + chan;
+            const int nb = 1 + DP_SLOT_NOUT * chg->n_slots;
+            for (int o = tid; o < nb; o += NT) prm.out[(long long)ev * prm.n_out + chg->out_base + o] = -999999.0;
+            continue;
         }
         const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)first * ESZ;
         double x0 = prm.subtract_first ? dp_load_first<IN>(xrow) : 0.0;
         double xsc = prm.scale;
-        if constexpr (IN == 2) {
+        if constexpr (dp_in_is_adc(IN)) {
             // ADC counts -> samples.  fp64: adc * gain + offset; fp32: (adc - x0) * (gain * scale) with x0 the first
             // count (AC coupling) or the count the offset cancels
             const double gain = dp_ldg(&prm.chans[chan].adc_gain), offs = dp_ldg(&prm.chans[chan].adc_offset);
@@ -1286,7 +1330,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             __syncwarp();  // pass 4 reads the warp's own chunks
             Core::load_groups(sm.buf, gg.x, gg.y, z);
             __syncwarp();  // the group rows of this warp are now free: land the point-wise tables in them
-            if (lane == 0) issue_a(bar, bufb, prm.zones[p * NW + warp], spw, ch.wj + tab_block(p, warp), ch.templ[0].phi + tab_block(p, warp));
+            if (STAGE && lane == 0) issue_a(bar, bufb, prm.zones[p * NW + warp], spw, ch.wj + tab_block(p, warp), ch.templ[0].phi + tab_block(p, warp));
             dp_dft<16, -1, T>::run(z);
             if (p == 0 && tid < 32) {
                 // self-paired groups -> 17 lanes of warp 0
@@ -1318,10 +1362,13 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 }
                 __syncwarp();
             }
-            dp2_stage_wait(bar, spar);
-            spar ^= 1;
+            if constexpr (STAGE) {
+                dp2_stage_wait(bar, spar);
+                spar ^= 1;
+            }
             {
-                const Staged tb = staged_view(bufb, prm.zones[p * NW + warp], spoff, lane, true, ch.templ[0].phi + tab_block(p, warp) + lane);
+                const Staged tb = staged_view(bufb, prm.zones[p * NW + warp], spoff, lane, true, ch.templ[0].phi + tab_block(p, warp) + lane,
+                                              ch.wj + tab_block(p, warp) + lane, xs);
                 if constexpr (VL == 2) {
                     const S c = untangle_st(z, tb, wn);
                     if (!special) {
@@ -1433,9 +1480,9 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         Core::inv_2(sm.buf, prm.tw2, z);
                         Core::park_pass2(park, p, z, rowmask);
                     }
-                    if (MULTI && it == 0) dp2_fence_async();  // the X column (stored long ago: cheap by now) is read back by bulk copy
+                    if (STAGE && MULTI && it == 0) dp2_fence_async();  // the X column (stored long ago: cheap by now) is read back by bulk copy
                     __syncthreads();  // pass-2' reads of buf precede the next group / pass-1 stores
-                    if (more && lane == 0)
+                    if (STAGE && more && lane == 0)
                         issue_b(bar, bufb, prm.zones[p * NW + warp], spw, scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
                 } else {
                     // ------------ last phase: pass 1' over all blocks, arg-max, outputs --------------
@@ -1445,7 +1492,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         Core::inv_2(sm.buf, prm.tw2, z);
                         Core::store_pass2(sm.buf, z, rowmask);
                     }
-                    if (MULTI && it == 0) dp2_fence_async();
+                    if (STAGE && MULTI && it == 0) dp2_fence_async();
                     __syncthreads();  // also orders the parked block results (global memory) within the CTA
                     DpBest<S> tb[DP_MAX_TSLOTS];
 #pragma unroll
@@ -1484,18 +1531,19 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     }
                     __syncthreads();  // winners + the lowchi2 stash are visible; pass-1' reads of buf are done
                     // the FFT buffer is free: the next template's X column and filter rows land while the outputs are formed
-                    if (more && lane == 0)
+                    if (STAGE && more && lane == 0)
                         issue_b(bar, bufb, prm.zones[p * NW + warp], spw, scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
                     // ---- low-frequency chi2 at each fit's (amp, delay); chi0; outputs ----------------
                     double part[DP_MAX_TSLOTS + 1];
 #pragma unroll
                     for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
                         part[q] = 0.0;
-                        if (q < nts && tid < prm.nlow) {
+                        const int nlow_q = q < nts ? ch.slots[slot_of[q]].nlow : 0;  // the fit's own lowchi2_fcutoff
+                        if (q < nts && tid < nlow_q) {
                             DpBest<S> b = best[q * 32];
                             for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
                             const int d = b.idx - tp.pretrigger;
-                            for (int k = tid; k < prm.nlow; k += NT) {
+                            for (int k = tid; k < nlow_q; k += NT) {
                                 const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
                                 S sn, cs;
                                 if constexpr (sizeof(S) == 8) {
@@ -1558,10 +1606,13 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                 if (!more) break;
                 ++it;
                 // ---------------- next template: X (staged) times its filter, inverse untangle -> z ----------------
-                dp2_stage_wait(bar, spar);
-                spar ^= 1;
+                if constexpr (STAGE) {
+                    dp2_stage_wait(bar, spar);
+                    spar ^= 1;
+                }
                 {
-                    const Staged tb = staged_view(bufb, prm.zones[p * NW + warp], spoff, lane, false, ch.templ[it].phi + tab_block(p, warp) + lane);
+                    const Staged tb = staged_view(bufb, prm.zones[p * NW + warp], spoff, lane, false, ch.templ[it].phi + tab_block(p, warp) + lane,
+                                                  ch.wj + tab_block(p, warp) + lane, xs);
                     if constexpr (VL == 2) {
 #pragma unroll
                         for (int r = 0; r < 16; ++r) z[r] = tb.x(r);

@@ -34,6 +34,7 @@ struct DpSlot {
     int templ;    // template index within the channel
     int lo, hi;   // candidate rolled delay indices [lo, hi)
     int outside;  // 1: candidates are the complement of [lo, hi)
+    int nlow;     // lowchi2 sums the bins k < nlow of this fit (its own lowchi2_fcutoff; <= the plan's nlow)
 };
 
 template <class T> struct DpTemplDev {
@@ -61,8 +62,11 @@ template <class T> struct DpChanDev {
 };
 
 template <class T> struct DpOfParams {
-    const void* traces;      // [n_rows][row_stride] samples (in_dtype)
-    long long row_stride;    // elements
+    const void* traces;      // samples (in_dtype); first sample of (event ev, channel c) = element
+                             // ev * event_stride + (chan_offset ? chan_offset[c] : c * chan_stride)
+    long long event_stride;  // elements
+    long long chan_stride;   // elements
+    const long long* chan_offset;  // [n_chan] or null
     int n_rows;              // events * n_chan; row r belongs to channel r % n_chan
     int n_chan;
     const DpChanDev<T>* chans;
@@ -79,6 +83,11 @@ template <class T> struct DpOfParams {
     int subtract_first; // 1: subtract sample 0 before conversion (fp32 mode, AC coupling)
     int in_dtype;       // 0: f64, 1: f32, 2: i16
 };
+
+template <class T> DP_DEV long long dp_first_sample(const DpOfParams<T>& prm, int row) {
+    const int ev = row / prm.n_chan, chan = row % prm.n_chan;
+    return (long long)ev * prm.event_stride + (prm.chan_offset != nullptr ? prm.chan_offset[chan] : (long long)chan * prm.chan_stride);
+}
 
 // ------------------------------------------------------------------- geometry
 template <int R1> struct DpGeom {
@@ -175,11 +184,18 @@ template <> struct DpRaw<0> { using type = double2; using scalar = double; };
 template <> struct DpRaw<1> { using type = float2; using scalar = float; };
 template <> struct DpRaw<2> { using type = short2; using scalar = short; };
 template <> struct DpRaw<3> { using type = double2; using scalar = double; };  // float64, rows only 8-byte aligned
+template <> struct DpRaw<4> { using type = float2; using scalar = float; };    // float32, rows only 4-byte aligned
+template <> struct DpRaw<5> { using type = short2; using scalar = short; };    // int16, rows only 2-byte aligned
+// IN 3..5 = IN - 3 with element-aligned rows (windows of a continuous stream start at any sample)
+DP_HD constexpr bool dp_in_is_adc(int in) { return in == 2 || in == 5; }
 
 template <int IN> DP_DEV typename DpRaw<IN>::type dp_load_raw(const void* row, long long j) {
-    if constexpr (IN == 3) {
-        const double* p = reinterpret_cast<const double*>(row) + 2 * j;
-        return make_double2(__ldg(p), __ldg(p + 1));
+    if constexpr (IN >= 3) {
+        const typename DpRaw<IN>::scalar* p = reinterpret_cast<const typename DpRaw<IN>::scalar*>(row) + 2 * j;
+        typename DpRaw<IN>::type v;
+        v.x = __ldg(p);
+        v.y = __ldg(p + 1);
+        return v;
     } else {
         return __ldg(reinterpret_cast<const typename DpRaw<IN>::type*>(row) + j);
     }
@@ -512,11 +528,12 @@ template <class T, int R1, int P, int IN> struct DpOfKernel {
 #pragma unroll
         for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
             part[q] = 0.0;
-            if (q < nts && tid < prm.nlow) {
+            const int nlow_q = q < nts ? ch.slots[sm.slot_id(par)[q]].nlow : 0;
+            if (q < nts && tid < nlow_q) {
                 DpBest<T> b = best[q * 32];
                 for (int w = 1; w < NW; ++w) dp_best_merge(b, best[q * 32 + w]);
                 const int d = b.idx - tp.pretrigger;
-                for (int k = tid; k < prm.nlow; k += NT) {
+                for (int k = tid; k < nlow_q; k += NT) {
                     const int ph = (int)((((long long)k * (long long)d) % N + N) % N);  // exp(-2 pi i k d / N)
                     T sn, cs;
                     if constexpr (sizeof(T) == 8) {
@@ -575,7 +592,7 @@ template <class T, int R1, int P, int IN> struct DpOfKernel {
         constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
         const int nrow = row + gridDim.x;
         if (nrow < prm.n_rows) {
-            const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)nrow * (size_t)prm.row_stride * ESZ;
+            const unsigned char* nx = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)dp_first_sample(prm, nrow) * ESZ;
             constexpr int nlines = (int)((size_t)N * ESZ / 128);
             for (int l = threadIdx.x; l < nlines; l += NT) dp_prefetch_l2(nx + (size_t)l * 128);
         }
@@ -609,7 +626,7 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run_p1(const DpOfParams<T>& prm, unsigned 
         const int chan = row % prm.n_chan;
         const int ev = row / prm.n_chan;
         const DpChanDev<T>& ch = prm.chans[chan];
-        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
+        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)dp_first_sample(prm, row) * ESZ;
         double x0, xsc;
         dp_row_conversion<T, IN>(prm, chan, xrow, x0, xsc);
 
@@ -745,7 +762,7 @@ DP_DEV void DpOfKernel<T, R1, P, IN>::run_p2(const DpOfParams<T>& prm, unsigned 
         const int chan = row % prm.n_chan;
         const int ev = row / prm.n_chan;
         const DpChanDev<T>& ch = prm.chans[chan];
-        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * ESZ;
+        const void* xrow = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)dp_first_sample(prm, row) * ESZ;
         double x0, xsc;
         dp_row_conversion<T, IN>(prm, chan, xrow, x0, xsc);
 

@@ -58,6 +58,7 @@ struct Template {
 
 struct Fit {
     int templ, lo, hi, outside;
+    double fcut = -1.0;  // lowchi2_fcutoff of this fit (Hz); < 0: the plan's default
 };
 
 struct Channel {

@@ -40,7 +40,13 @@ struct DpRedChan {
 struct DpReduceParams {
     const void* traces;     // float64, or int16 ADC counts (sample = adc * gain + offset, rounded like numpy: product, then sum)
     const double* adc;      // [n_chan][2] gain, offset (int16 input only)
-    long long row_stride;
+    // first sample of (event ev, channel c) = element (row_start ? row_start[ev] : ev * event_stride) +
+    // (chan_offset ? chan_offset[c] : c * chan_stride) -- the layouts of dp_of1x1_batch_ex (Dp2Params)
+    long long event_stride, chan_stride;
+    const long long* chan_offset;  // [n_chan] or null
+    const long long* row_start;    // [n_events] or null: windows of continuous streams of stream_len samples
+    long long stream_len;
+    int nb_samples;
     int n_rows, n_chan;
     const DpRedChan* chans;
     const DpLeaf* leaves;
@@ -97,7 +103,16 @@ template <int NT, int IN = 0> DP_DEV void dp_reduce_rows(const DpReduceParams& p
         const int ev = row / prm.n_chan;
         const DpRedChan ch = prm.chans[chan];
         DpRedRow<IN> x;
-        x.x = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)row * (size_t)prm.row_stride * (IN == 0 ? 8 : 2);
+        long long base = (long long)ev * prm.event_stride;
+        if (prm.row_start != nullptr) {
+            base = prm.row_start[ev];
+            if (base < 0 || base + prm.nb_samples > prm.stream_len) {  // CTA-uniform: the window leaves the stream
+                for (int f = ch.feat_begin + tid; f < ch.feat_end; f += NT) prm.out[(long long)ev * prm.n_out + prm.feats[f].out] = -999999.0;
+                continue;
+            }
+        }
+        const long long first = base + (prm.chan_offset != nullptr ? prm.chan_offset[chan] : (long long)chan * prm.chan_stride);
+        x.x = reinterpret_cast<const unsigned char*>(prm.traces) + (size_t)first * (IN == 0 ? 8 : 2);
         x.gain = IN == 0 ? 1.0 : prm.adc[2 * chan];
         x.offs = IN == 0 ? 0.0 : prm.adc[2 * chan + 1];
         // ---- leaves: 8 lanes = numpy's 8 accumulators -------------------------------

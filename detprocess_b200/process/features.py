@@ -45,17 +45,49 @@ def shard_range(n_events, rank, world):
 
 
 def gather_frames(df):
-    """All ranks receive the concatenation (rank order == event order) of the per-rank
-    feature tables.  The tables are small (~16 doubles / event); no trace ever crosses NVLink."""
+    """All ranks receive the concatenation (rank order == event order) of the per-rank feature tables -- the "gather of
+    the small per-event feature tables" of the multi-GPU design.  The numeric columns travel as ONE
+    float64 tensor per rank through ``all_gather`` (NCCL over NVLink when the job runs on GPUs; ~16 doubles per event),
+    padded to the longest shard; only columns that are not numbers (strings such as data_type) go through the pickled
+    object gather.  No trace ever crosses NVLink."""
     import pandas as pd
+    import torch
     import torch.distributed as dist
     rank, world = dist_info()
     if world == 1:
         return df
-    parts = [None] * world
-    dist.all_gather_object(parts, df)
-    parts = [p for p in parts if len(p)]
-    return pd.concat(parts, ignore_index=True) if parts else df
+    on_gpu = dist.get_backend() == 'nccl'
+    dev = torch.device('cuda', torch.cuda.current_device()) if on_gpu else torch.device('cpu')
+    numeric = [c for c in df.columns if pd.api.types.is_numeric_dtype(df[c]) or pd.api.types.is_bool_dtype(df[c])]
+    other = [c for c in df.columns if c not in numeric]
+    # every rank runs the same configuration, hence the same columns; a rank without events has none of them yet
+    meta = [None] * world
+    dist.all_gather_object(meta, (len(df), list(df.columns), {c: str(df[c].dtype) for c in numeric}))
+    ref = next((m for m in meta if m[0] > 0), meta[0])
+    columns, dtypes = ref[1], ref[2]
+    numeric = [c for c in columns if c in dtypes]
+    other = [c for c in columns if c not in dtypes]
+    nmax = max(m[0] for m in meta)
+    if nmax == 0:
+        return df
+    block = torch.zeros((nmax, max(len(numeric), 1)), dtype=torch.float64, device=dev)
+    if len(df) and numeric:
+        block[:len(df), :len(numeric)] = torch.from_numpy(df[numeric].to_numpy(dtype=np.float64, copy=True)).to(dev)
+    parts = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(parts, block)
+    host = [p[:m[0], :len(numeric)].cpu().numpy() for p, m in zip(parts, meta)]
+    out = pd.DataFrame(np.concatenate(host, axis=0), columns=numeric)
+    for c in numeric:                       # integers and booleans come back as what they were
+        if not dtypes[c].startswith('float'):
+            out[c] = out[c].astype(dtypes[c])
+    if other:
+        objs = [None] * world
+        dist.all_gather_object(objs, df[other] if len(df) else None)
+        objs = [o for o in objs if o is not None and len(o)]
+        extra = pd.concat(objs, ignore_index=True)
+        for c in other:
+            out[c] = extra[c].to_numpy()
+    return out[columns]
 
 
 def _public_algorithms(cls):
@@ -64,15 +96,22 @@ def _public_algorithms(cls):
 
 class FeatureProcessing:
     def __init__(self, raw_data, config_file, filter_data=None, external_file=None,
-                 processing_id=None, precision='f64', device=None, verbose=True):
+                 processing_id=None, precision='f64', device=None, verbose=True,
+                 trigger_dataframe=None, trigger_dataframe_path=None):
         """
-        raw_data : dict with
-            'traces'      ndarray / torch tensor [B, n_chan, N] (float64 amps)
+        raw_data : an ``EventReader`` or a dict with
+            'traces'      ndarray / torch tensor [B, n_chan, N] (float64 amps, or int16 ADC counts + 'adc_gain')
             'channels'    list of channel names (length n_chan)
             'sample_rate' float
             'admin'       optional dict of per-event columns (event_number, series_number, ...)
         config_file : YAML path (or an already-loaded dict)
         filter_data : FilterData with the templates / PSDs the YAML refers to
+        trigger_dataframe(_path) : table with one row per trigger (``trigger_index`` + the ``event_number`` [and
+            ``series_number``] of the continuous event it was found in, as ``TriggerProcessing`` writes it; reference
+            features.py:59, 235-238).  The reader then holds CONTINUOUS events and every feature is computed on the
+            window ``[trigger_index - nb_pretrigger_samples, ... + nb_samples)`` of its event, cut inside the kernels'
+            loads (reference ProcessingData.read_next_event -> read_single_event(trigger_index, trace_length_samples,
+            pretrigger_length_samples), processing_data.py:643-688).
         """
         self._verbose = verbose
         from ..io.readers import EventReader, ArrayReader
@@ -88,6 +127,10 @@ class FeatureProcessing:
         self._precision = precision
         self._device = device
         self._processing_id = processing_id
+        if trigger_dataframe is None and trigger_dataframe_path is not None:
+            import pandas as pd
+            trigger_dataframe = pd.read_parquet(trigger_dataframe_path)
+        self._triggers = trigger_dataframe
         cfg = YamlConfig(config_file, self._channels, sample_rate=self._fs, verbose=verbose)
         fcfg = cfg.get_config('feature')
         self._processing_config = fcfg['channels']
@@ -103,20 +146,14 @@ class FeatureProcessing:
             if dup:
                 raise ValueError(f'ERROR: External feature extractor(s) {sorted(dup)} duplicate internal names')
         self._of_bases = {}     # key_tuple -> {'OF': OFBaseBatch, 'channels': [...], 'algorithms': [...]}
-        # int16 ADC events stay int16 on the device (the fused kernels convert in their loads) when every configured
-        # channel is a plain channel and every algorithm is built in; channel algebra / NxM / external extractors take
-        # the float64 path (ADC -> amps by a torch kernel first)
+        # int16 ADC events stay int16 on the device: the fused kernels (OF, window reductions, channel algebra) convert in
+        # their loads with the reader's per-channel gain / offset
         meta = self._reader.metadata
         self._adc = None
         if meta.get('dtype') == 'int16' and 'adc_gain' in meta:
-            plain = all(utils.split_channel_name(c, available_channels=self._channels)[1] is None
-                        for c, cc in self._processing_config.items() if isinstance(cc, dict))
-            builtin = all(params.get('base_algorithm', algo) in self._algorithm_list
-                          for cc in self._processing_config.values() if isinstance(cc, dict)
-                          for algo, params in cc.items() if isinstance(params, dict) and params.get('run'))
-            if plain and builtin:
-                self._adc = {c: (float(meta['adc_gain'][i]), float(meta['adc_offset'][i])) for i, c in enumerate(self._channels)}
+            self._adc = {c: (float(meta['adc_gain'][i]), float(meta['adc_offset'][i])) for i, c in enumerate(self._channels)}
         self._instantiate_of_bases()
+        self._compile_jobs()
 
     # ------------------------------------------------------------------ setup
     @staticmethod
@@ -144,6 +181,9 @@ class FeatureProcessing:
                 s += '_harmonics'
             tag = f'{tag}_{s}'
         return (params['nb_samples'], params['nb_pretrigger_samples'], tag)
+
+    def _is_plain(self, channel):
+        return utils.split_channel_name(channel, available_channels=self._channels)[1] is None
 
     def _instantiate_of_bases(self):
         if self._filter_data is None:
@@ -199,110 +239,15 @@ class FeatureProcessing:
                 ofb.add_template(chan, tmpl, template_tag=ttag, pretrigger_samples=pre,
                                  integralnorm=params.get('integralnorm', False), overwrite=True)
 
-    # ------------------------------------------------------------------ traces
-    def _channel_trace(self, traces, channel):
-        """Weighted channel algebra of ProcessingData.get_channel_trace (reference :941-1049)."""
-        parts, sep = utils.split_channel_name(channel, available_channels=self._channels)
-        idx = [self._channels.index(c) for c in parts]
-        w = None
-        if channel in self._weights:
-            wd = self._weights[channel]
-            w = []
-            for c in parts:
-                if f'weight_{c}' not in wd:
-                    raise ValueError(f'ERROR: Missing parameter weight weight_{c} for channel {channel}!')
-                w.append(float(wd[f'weight_{c}']))
-        if sep == '+':
-            cols = [traces[:, i, :] * w[j] if w is not None else traces[:, i, :] for j, i in enumerate(idx)]
-            out = cols[0]
-            for c in cols[1:]:
-                out = out + c
-            return out
-        if sep == '-':
-            if w is not None:
-                return traces[:, idx[0], :] * w[0] - traces[:, idx[1], :] * w[1]
-            return traces[:, idx[0], :] - traces[:, idx[1], :]
-        if sep is None:
-            return traces[:, idx[0], :]
-        if sep == '|':
-            return traces[:, idx, :]            # [B, n, N] in the listed order (NxM filter)
-        raise NotImplementedError(f'channel operator "{sep}" is outside the built hot path')
-
-    # ------------------------------------------------------------------ process
-    def process(self, nevents=-1, lgc_save=False, lgc_output=True, save_path=None, ncores=1,
-                batch_size=8192, gather=True, memory_limit=2.0, **kwargs):
-        """Events are read batch by batch through the reader (int16 ADC counts cross PCIe as they are stored and become
-        amps on the device), sharded over ranks in contiguous blocks.  lgc_save: every rank writes its own dumps
-        ``<prefix>_rank<r>_F000k.parquet`` when ``memory_limit`` (GB) of rows is queued (reference features.py:584-629:
-        one file set per worker, no merge); lgc_output: the gathered table is returned."""
-        import pandas as pd
-        reader = self._reader
-        nev_total = len(reader) if nevents is None or nevents < 0 else min(nevents, len(reader))
-        # ---- shard events over ranks (one process per GPU), contiguous blocks -----------------
-        rank, world = dist_info()
-        lo, hi = shard_range(nev_total, rank, world)
-        writer = None
-        if lgc_save:
-            from ..io.writers import FeatureWriter
-            writer = FeatureWriter(save_path or '.', prefix=self._processing_id or 'feature',
-                                   series_name=(f'rank{rank}' if world > 1 else None), memory_limit_gb=memory_limit)
-        frames = []
-        import torch
-        dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
-        copy_stream = torch.cuda.Stream(dev)
-
-        def fetch(b0):
-            # the next batch is uploaded on a side stream while the current one is processed
-            b1 = min(b0 + batch_size, hi)
-            t = reader.upload(b0, b1, dev, stream=copy_stream)   # the reader orders its staging reuse after this copy
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-            return t, ev, b0, b1
-
-        nxt = fetch(lo) if lo < hi else None
-        while nxt is not None:
-            t, ev, b0, b1 = nxt
-            nxt = fetch(b1) if b1 < hi else None
-            torch.cuda.current_stream(dev).wait_event(ev)
-            t.record_stream(torch.cuda.current_stream(dev))
-            df = self._process_batch(t, b0, b1)
-            if writer is not None:
-                writer.add(df)
-            if lgc_output:
-                frames.append(df)
-        self.output_files = writer.close() if writer is not None else []
-        if not lgc_output:
-            return None
-        df = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame()
-        return gather_frames(df) if gather else df
-
-    def _process_batch(self, traces, ev0, ev1):
-        import pandas as pd
-        import torch
-        dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
-        traces = traces.to(dev, non_blocking=True)
-        if self._adc is None:
-            traces = self._reader.to_amps(traces)                             # ADC -> amps on the device (torch)
-        nb, _, n = traces.shape
-        cols = {k: np.asarray(v) for k, v in self._reader.admin(ev0, ev1).items()}
-        if self._processing_id is not None:
-            cols['processing_id'] = np.full(nb, self._processing_id)
-
-        # ---- push the batch into every OF base (reference update_signal_OF, :712-772) --------
-        for key, entry in self._of_bases.items():
-            ofb = entry['OF']
-            ofb.clear_signal()
-            if key[0] != n:
-                raise ValueError(f'ERROR: trace length {n} != configured nb_samples {key[0]} '
-                                 '(window extraction from continuous data is not built)')
-            for chan in entry['channels']:
-                ofb.update_signal(chan, self._channel_trace(traces, chan), calc_fft=True)
-
-        # ---- trace-window features: ONE reduction launch for all of them -----------------------
-        red = ReducePlan(n, self._fs, 1)
-        red_jobs = []          # (handle, feature column name, channel)
-        red_inputs = {}        # channel -> row index in the stacked input
-        external_jobs = []
+    def _compile_jobs(self):
+        """Everything the YAML implies is resolved ONCE: per (channel, algorithm) the extractor, its kwargs (windows as
+        indices) and the kind of job; every OF fit is registered with its OFBaseBatch before the first batch (one plan, one
+        table build, one launch per batch whatever the blocks' windows and ``lowchi2_fcutoff``); the window reductions
+        share cached ReducePlans; the combined channels ('a+b', 'a-b') are listed for the channel-algebra kernel."""
+        self._of_jobs, self._ext_jobs = [], []
+        red_jobs = {}           # (nb_samples, nb_pretrigger) -> list of (channel, op, lo, hi, column)
+        self._combined = []     # combined channel names, in the order of the combine kernel's output rows
+        n_reader = int(self._reader.metadata['nb_samples'])
         for channel, algorithms in self._processing_config.items():
             if not isinstance(algorithms, dict):
                 continue
@@ -320,36 +265,241 @@ class FeatureProcessing:
                                      f'Check feature extractor exists!')
                 kw = {k: v for k, v in params.items() if k != 'run'}
                 kw['fs'] = self._fs
-                kw.setdefault('nb_samples', n)
-                kw.setdefault('nb_pretrigger_samples', n // 2)
+                kw.setdefault('nb_samples', n_reader)
+                kw.setdefault('nb_pretrigger_samples', kw['nb_samples'] // 2)
                 wmin, wmax = utils.get_window_indices(**kw)
                 kw['window_min_index'], kw['window_max_index'] = wmin, wmax
                 kw['feature_base_name'] = algorithm
+                geom = (int(kw['nb_samples']), int(kw['nb_pretrigger_samples']))
+                sep = utils.split_channel_name(channel, available_channels=self._channels)[1]
+                if sep in ('+', '-') and channel not in self._combined:
+                    self._combined.append(channel)
                 entry = self._of_bases.get(self._of_key(params)) if (base.startswith('of1x1') or base == 'ofnxm') else None
                 if entry is not None and algorithm in entry['algorithms']:
-                    feats = extractor(channel, entry['OF'], **kw)
-                    for name, val in feats.items():
-                        cols[f'{name}_{feature_channel}'] = val
+                    self._of_jobs.append((channel, extractor, entry, kw, feature_channel))
+                    spec = FE._of_fit_spec(base, channel, entry['OF'], **{k: v for k, v in kw.items() if k != 'base_algorithm'})
+                    if spec is not None:
+                        entry['OF'].request_fit(channel, *spec)
                 elif base in _TRACE_OPS and extractor is getattr(FE, base):
-                    red_jobs.append((channel, base, wmin, wmax, f'{algorithm}_{feature_channel}'))
+                    red_jobs.setdefault(geom, []).append((channel, base, wmin, wmax, f'{algorithm}_{feature_channel}'))
                 else:
-                    external_jobs.append((channel, extractor, kw, feature_channel))
-        if red_jobs:
-            chans = utils.unique_list([j[0] for j in red_jobs])
-            red = ReducePlan(n, self._fs, len(chans))
-            if self._adc is not None:
-                for i, c in enumerate(chans):
-                    red.set_adc_conversion(i, *self._adc[c])
-            handles = [red.add(chans.index(c), op, a, b) for c, op, a, b, _ in red_jobs]
-            red.finalize(dev)
-            x = torch.stack([self._channel_trace(traces, c) for c in chans], dim=1).contiguous()
-            out = red.run(x).cpu().numpy()
-            for h, job in zip(handles, red_jobs):
-                cols[job[4]] = out[:, red.column(h)]
+                    self._ext_jobs.append((channel, extractor, kw, feature_channel, geom))
+        # cached reduction plans: per trace geometry one plan over the plain channels (read in place from the reader
+        # batch, ADC conversion in the load) and one over the combined channels (output of the channel-algebra kernel)
+        self._red_plans = {}
+        for geom, jobs in red_jobs.items():
+            plans = {}
+            for kind in ('plain', 'comb'):
+                sel = [j for j in jobs if (self._is_plain(j[0]) if kind == 'plain' else j[0] in self._combined)]
+                bad = [j[0] for j in jobs if not self._is_plain(j[0]) and j[0] not in self._combined]
+                if bad:
+                    raise NotImplementedError(f'window features on channel(s) {bad} are outside the built hot path')
+                if not sel:
+                    continue
+                chans = utils.unique_list([j[0] for j in sel])
+                plan = ReducePlan(geom[0], self._fs, len(chans))
+                if kind == 'plain' and self._adc is not None:
+                    for i, c in enumerate(chans):
+                        plan.set_adc_conversion(i, *self._adc[c])
+                handles = [plan.add(chans.index(c), op, a, b) for c, op, a, b, _ in sel]
+                plans[kind] = {'plan': plan, 'chans': chans, 'handles': handles, 'columns': [j[4] for j in sel]}
+            self._red_plans[geom] = plans
+        # combine-kernel terms of the combined channels
+        self._combine_terms = []
+        for channel in self._combined:
+            parts, sep = utils.split_channel_name(channel, available_channels=self._channels)
+            rows = [self._channels.index(c) for c in parts]
+            w = None
+            if channel in self._weights:
+                wd = self._weights[channel]
+                w = []
+                for c in parts:
+                    if f'weight_{c}' not in wd:
+                        raise ValueError(f'ERROR: Missing parameter weight weight_{c} for channel {channel}!')
+                    w.append(float(wd[f'weight_{c}']))
+            if sep == '-' and len(rows) != 2:
+                raise ValueError(f'ERROR: "{channel}": a difference takes two channels')
+            self._combine_terms.append([(r, None if w is None else w[i], -1.0 if (sep == '-' and i == 1) else 1.0)
+                                        for i, r in enumerate(rows)])
+
+    # ------------------------------------------------------------------ traces
+    def _channel_trace(self, traces, channel):
+        """Weighted channel algebra of ProcessingData.get_channel_trace (reference :941-1049) on a float64 batch (used for
+        joint 'a|b' channels and external extractors; plain and 'a+b' / 'a-b' channels never come here)."""
+        parts, sep = utils.split_channel_name(channel, available_channels=self._channels)
+        idx = [self._channels.index(c) for c in parts]
+        if sep is None:
+            return traces[:, idx[0], :]
+        if sep == '|':
+            return traces[:, idx, :]            # [B, n, N] in the listed order (NxM filter)
+        raise NotImplementedError(f'channel operator "{sep}" is outside the built hot path')
+
+    # ------------------------------------------------------------------ process
+    def process(self, nevents=-1, lgc_save=False, lgc_output=True, save_path=None, ncores=1,
+                batch_size=8192, gather=True, memory_limit=2.0, **kwargs):
+        """Events are read batch by batch through the reader (int16 ADC counts cross PCIe as they are stored and become
+        amps inside the kernels), sharded over ranks in contiguous blocks.  lgc_save: every rank writes its own dumps
+        ``<prefix>_rank<r>_F000k.parquet`` when ``memory_limit`` (GB) of rows is queued (reference features.py:584-629:
+        one file set per worker, no merge); lgc_output: the gathered table is returned.  With a trigger dataframe the
+        reader's events are continuous streams and the rows of the table are the events (see ``__init__``)."""
+        import pandas as pd
+        import torch
+        rank, world = dist_info()
+        writer = None
+        if lgc_save:
+            from ..io.writers import FeatureWriter
+            writer = FeatureWriter(save_path or '.', prefix=self._processing_id or 'feature',
+                                   series_name=(f'rank{rank}' if world > 1 else None), memory_limit_gb=memory_limit)
+        frames = []
+        dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
+
+        def emit(df):
+            if writer is not None:
+                writer.add(df)
+            if lgc_output:
+                frames.append(df)
+
+        if self._triggers is not None:
+            self._process_triggers(nevents, dev, rank, world, emit)
+        else:
+            reader = self._reader
+            nev_total = len(reader) if nevents is None or nevents < 0 else min(nevents, len(reader))
+            lo, hi = shard_range(nev_total, rank, world)      # contiguous blocks, one process per GPU
+            copy_stream = torch.cuda.Stream(dev)
+
+            def fetch(b0):
+                # the next batch is uploaded on a side stream while the current one is processed
+                b1 = min(b0 + batch_size, hi)
+                t = reader.upload(b0, b1, dev, stream=copy_stream)   # the reader orders its staging reuse after this copy
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                return t, ev, b0, b1
+
+            nxt = fetch(lo) if lo < hi else None
+            while nxt is not None:
+                t, ev, b0, b1 = nxt
+                nxt = fetch(b1) if b1 < hi else None
+                torch.cuda.current_stream(dev).wait_event(ev)
+                t.record_stream(torch.cuda.current_stream(dev))
+                emit(self._process_batch(t, b0, b1))
+        self.output_files = writer.close() if writer is not None else []
+        if not lgc_output:
+            return None
+        df = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame()
+        return gather_frames(df) if gather else df
+
+    def _process_triggers(self, nevents, dev, rank, world, emit):
+        """trigger-dataframe mode: rows are grouped by the continuous event they point into; each stream is uploaded once
+        and all of its windows are processed by one launch per plan.  Streams (not rows) are sharded over the ranks."""
+        import pandas as pd
+        import torch
+        trig = self._triggers
+        if nevents is not None and nevents >= 0:
+            trig = trig.iloc[:nevents]
+        if 'trigger_index' not in trig.columns:
+            raise ValueError('ERROR: the trigger dataframe needs a "trigger_index" column')
+        reader = self._reader
+        alias = {'event_num': 'event_number', 'series_num': 'series_number', 'dump_num': 'dump_number'}
+        adm = {alias.get(k, k): np.asarray(v) for k, v in reader.admin(0, len(reader)).items()}
+        keys = [k for k in ('series_number', 'event_number') if k in adm and k in trig.columns]
+        if 'event_number' not in keys:
+            raise ValueError('ERROR: trigger dataframe and reader need an "event_number" column to find the continuous event')
+        index_of = {tuple(int(adm[k][i]) for k in keys): i for i in range(len(reader))}
+        stream_of_row = np.array([index_of.get(tuple(int(trig[k].iloc[i]) for k in keys), -1) for i in range(len(trig))])
+        if (stream_of_row < 0).any():
+            raise ValueError('ERROR: trigger dataframe rows point to events the raw data does not hold')
+        streams = np.unique(stream_of_row)
+        lo, hi = shard_range(len(streams), rank, world)
+        for si in streams[lo:hi]:
+            rows = np.nonzero(stream_of_row == si)[0]
+            batch = reader.upload(int(si), int(si) + 1, dev)[0]              # [n_chan, L] as stored
+            tidx = torch.from_numpy(trig['trigger_index'].to_numpy(dtype=np.int64)[rows]).to(dev)
+            df = self._process_batch(batch, None, None, trigger_index=tidx)
+            tab = trig.iloc[rows].reset_index(drop=True)                      # the trigger rows verbatim (:795-804)
+            for c in df.columns:
+                tab[c] = df[c].to_numpy()
+            emit(tab)
+
+    def _process_batch(self, batch, ev0, ev1, trigger_index=None):
+        """batch mode: ``batch`` [B, n_chan, N] events ev0..ev1 of the reader; window mode: ``batch`` [n_chan, L] one
+        continuous event and ``trigger_index`` int64 [B] (device)."""
+        import pandas as pd
+        import torch
+        dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
+        batch = batch.to(dev, non_blocking=True)
+        window_mode = trigger_index is not None
+        rows = {c: i for i, c in enumerate(self._channels)}
+        if window_mode:
+            nb, n = int(trigger_index.shape[0]), None
+            cols = {}
+            if self._combined or self._ext_jobs:
+                raise NotImplementedError('combined channels / external extractors in trigger-dataframe mode are not built')
+        else:
+            nb, _, n = batch.shape
+            cols = {k: np.asarray(v) for k, v in self._reader.admin(ev0, ev1).items()}
+        if self._processing_id is not None:
+            cols['processing_id'] = np.full(nb, self._processing_id)
+
+        # ---- combined channels 'a+b' / 'a-b': one channel-algebra launch straight from the reader's buffer ---------
+        comb = None
+        if self._combined:
+            from ..core.plans import combine_channels
+            adc_rows = None if self._adc is None else {rows[c]: v for c, v in self._adc.items()}
+            comb = combine_channels(batch, self._combine_terms, adc=adc_rows)
+        amps = None          # float64 amps of the whole batch: only joint channels / external extractors need them
+
+        def float_batch():
+            nonlocal amps
+            if amps is None:
+                amps = self._reader.to_amps(batch)
+            return amps
+
+        # ---- hand the batch to every OF base (reference update_signal_OF, :712-772): plain channels are read where the
+        # reader put them, combined ones from the channel-algebra output
+        for key, entry in self._of_bases.items():
+            ofb = entry['OF']
+            ofb.clear_signal()
+            if not window_mode and key[0] != n:
+                raise ValueError(f'ERROR: trace length {n} != configured nb_samples {key[0]}: continuous data need a '
+                                 'trigger dataframe (trigger_dataframe=...)')
+            plain = {c: rows[c] for c in entry['channels'] if c in rows}
+            starts = None if not window_mode else trigger_index - int(key[1])
+            if plain:
+                ofb.update_batch(batch, plain, start_index=starts)
+            for chan in entry['channels']:
+                if chan in plain:
+                    continue
+                if chan in self._combined:
+                    ofb.update_signal(chan, comb[:, self._combined.index(chan), :], calc_fft=True)
+                else:
+                    ofb.update_signal(chan, self._channel_trace(float_batch(), chan), calc_fft=True)
+        for channel, extractor, entry, kw, feature_channel in self._of_jobs:
+            for name, val in extractor(channel, entry['OF'], **kw).items():
+                cols[f'{name}_{feature_channel}'] = val
+
+        # ---- trace-window features: cached plans, inputs consumed in place --------------------------------------------
+        for geom, plans in self._red_plans.items():
+            if not window_mode and geom[0] != n:
+                raise ValueError(f'ERROR: trace length {n} != configured nb_samples {geom[0]}')
+            for kind, d in plans.items():
+                plan = d['plan']
+                if not plan.finalized:
+                    plan.finalize(dev)
+                if kind == 'plain':
+                    starts = None if not window_mode else trigger_index - int(geom[1])
+                    out = plan.run_layout(batch, [rows[c] for c in d['chans']], starts)
+                else:
+                    out = plan.run_layout(comb, [self._combined.index(c) for c in d['chans']])
+                out = out.cpu().numpy()
+                for h, name in zip(d['handles'], d['columns']):
+                    cols[name] = out[:, plan.column(h)]
         # user-supplied extractors keep the reference's per-event numpy calling convention
-        for channel, extractor, kw, feature_channel in external_jobs:
-            tr = self._channel_trace(traces, channel).cpu().numpy()
-            rows = [extractor(tr[i], **kw) for i in range(nb)]
-            for name in rows[0]:
-                cols[f'{name}_{feature_channel}'] = np.array([r[name] for r in rows])
+        for channel, extractor, kw, feature_channel, geom in self._ext_jobs:
+            if channel in self._combined:
+                tr = comb[:, self._combined.index(channel), :].cpu().numpy()
+            else:
+                tr = self._channel_trace(float_batch(), channel).cpu().numpy()
+            rows_out = [extractor(tr[i], **kw) for i in range(nb)]
+            for name in rows_out[0]:
+                cols[f'{name}_{feature_channel}'] = np.array([r[name] for r in rows_out])
         return pd.DataFrame(cols)

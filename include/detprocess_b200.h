@@ -81,7 +81,12 @@ int dp_of_plan_add_template(dp_of_plan* plan, int chan, const double* templ, int
 int dp_of_plan_add_fit(dp_of_plan* plan, int chan, int templ_index, int window_lo, int window_hi, int outside,
                        int* fit_index);
 
-/* lowchi2_fcutoff of qp.OF1x1.calc (default 10000 Hz, algorithms.py:280) */
+/* the same with the fit's own lowchi2_fcutoff (Hz; < 0: the plan's default): every YAML block carries its own
+ * `lowchi2_fcutoff` kwarg (algorithms.py:280, 357, 438), two blocks of one OFBase may differ */
+int dp_of_plan_add_fit_ex(dp_of_plan* plan, int chan, int templ_index, int window_lo, int window_hi, int outside,
+                          double lowchi2_fcutoff_hz, int* fit_index);
+
+/* plan default of lowchi2_fcutoff of qp.OF1x1.calc (10000 Hz, algorithms.py:280) */
 int dp_of_plan_set_lowchi2_fcutoff(dp_of_plan* plan, double fcutoff_hz);
 
 /* DP_IN_I16 traces are raw ADC counts: sample = adc * gain + offset, converted in the kernel's load (float64 mode: one
@@ -129,6 +134,22 @@ int dp_of1x1_batch(dp_of_plan* plan, const void* traces_dev, int in_dtype, long 
 int dp_of1x1_windows(dp_of_plan* plan, const double* stream_dev, long long n_stream_samples,
                      const long long* start_index_dev, long long n_events, double* out_dev, void* stream);
 
+/* General input layout: the first sample of (event ev, plan channel c) is element
+ *     (start_index_dev ? start_index_dev[ev] : ev * event_stride) + (chan_offsets ? chan_offsets[c] : c * chan_stride)
+ * of base_dev (in_dtype DP_IN_F64 / F32 / I16).
+ *   - a reader batch [B][n_file_chan][N] of which the plan fits some channels, consumed in place (no gather / stack
+ *     copy): event_stride = n_file_chan * N, chan_offsets[c] = file_channel(c) * N  (host array [n_chan]);
+ *   - window mode (start_index_dev != NULL, device int64 [n_events]): every channel is a continuous stream of
+ *     n_stream_samples samples (stream c starts at chan_offsets[c] or c * chan_stride) and event ev is the window that
+ *     starts at sample start_index_dev[ev] = trigger_index - nb_pretrigger_samples of all of them -- what
+ *     ProcessingData.read_next_event does with a trigger dataframe row through H5Reader.read_single_event(trigger_index,
+ *     trace_length_samples, pretrigger_length_samples) (detprocess/process/processing_data.py:643-688), fused into the
+ *     kernel's trace load.  Windows that leave [0, n_stream_samples) get -999999.0 in every column.
+ * Rows that are not aligned to a sample pair (windows, odd strides) need nb_samples 16384 / 32768 / 65536. */
+int dp_of1x1_batch_ex(dp_of_plan* plan, const void* base_dev, int in_dtype, long long n_events, long long event_stride,
+                      const long long* chan_offsets, long long chan_stride, const long long* start_index_dev,
+                      long long n_stream_samples, double* out_dev, void* stream);
+
 int dp_of1x1_batch_host(dp_of_plan* plan, const void* traces_host, int in_dtype, long long n_events,
                         long long row_stride, double* out_host);
 
@@ -162,7 +183,23 @@ int dp_reduce_plan_set_adc_conversion(dp_reduce_plan* plan, int chan, double gai
 /* in_dtype DP_IN_F64 or DP_IN_I16 */
 int dp_window_reduce_batch_raw(dp_reduce_plan* plan, const void* traces_dev, int in_dtype, long long n_events,
                                long long row_stride, double* out_dev, void* stream);
+/* the input layouts of dp_of1x1_batch_ex (reader batch consumed in place; windows of continuous streams at
+ * start_index_dev, out-of-range windows -> -999999.0) */
+int dp_window_reduce_batch_ex(dp_reduce_plan* plan, const void* base_dev, int in_dtype, long long n_events,
+                              long long event_stride, const long long* chan_offsets, long long chan_stride,
+                              const long long* start_index_dev, long long n_stream_samples, double* out_dev, void* stream);
 int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* plan, float* ms);
+
+/* ------------------------------------------------------------ channel algebra
+ * ProcessingData.get_channel_trace for "a+b" / "a-b" channels (detprocess/process/processing_data.py:1033-1047):
+ * out[ev][j][i] = sum_t weights[j][t] * x(ev, offsets[j][t] + i), j < n_out <= 8, t < n_terms[j] <= 4, every product and
+ * sum rounded separately in that order (bit-identical to numpy; a subtraction is a negative weight; weighted[j] == 0: the
+ * weights are +-1 signs only).  x is read from base_dev (element ev * event_stride + offset + i) as in_dtype; int16 ADC
+ * counts become adc * adc_gain[j][t] + adc_offset[j][t] first.  Arrays [n_out][4] on the host; out_dev float64
+ * [n_events][n_out][nb_samples]. */
+int dp_channel_combine(const void* base_dev, int in_dtype, long long n_events, long long event_stride, int nb_samples,
+                       int n_out, const int* n_terms, const long long* offsets, const double* weights, const int* weighted,
+                       const double* adc_gain, const double* adc_offset, double* out_dev, void* stream);
 
 /* ------------------------------------------------------------------ noise PSD
  * Replaces qp.calc_psd(traces[cut], fs, folded_over=False) as called by Noise.calc_psd

@@ -56,13 +56,14 @@ static void run_all(const dpplan::Geometry& g, dpplan::DeviceTables<T>& dt, cons
             t.tsum = h.tsum;
             t.pretrigger = h.pretrigger;
         }
-        for (int i = 0; i < d.n_slots; ++i) d.slots[i] = DpSlot{chans[c].fits[i].templ, chans[c].fits[i].lo, chans[c].fits[i].hi, chans[c].fits[i].outside};
+        for (int i = 0; i < d.n_slots; ++i) d.slots[i] = DpSlot{chans[c].fits[i].templ, chans[c].fits[i].lo, chans[c].fits[i].hi, chans[c].fits[i].outside, dt.nlow};
     }
     const int grid = 2;
     std::vector<cx<T>> scratch((size_t)grid * 96 * g.NT);
     DpOfParams<T> prm{};
     prm.traces = traces.data();
-    prm.row_stride = g.N;
+    prm.event_stride = (long long)g.N * (long long)chans.size();
+    prm.chan_stride = g.N;
     prm.n_rows = n_events * (int)chans.size();
     prm.n_chan = (int)chans.size();
     prm.chans = cd.data();

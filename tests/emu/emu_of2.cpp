@@ -60,14 +60,15 @@ static void run_all(double fs, double fcut, double scale, const std::vector<dppl
             t.tsum = h.tsum;
             t.pretrigger = h.pretrigger;
         }
-        for (int i = 0; i < d.n_slots; ++i) d.slots[i] = DpSlot{chans[c].fits[i].templ, chans[c].fits[i].lo, chans[c].fits[i].hi, chans[c].fits[i].outside};
+        for (int i = 0; i < d.n_slots; ++i) d.slots[i] = DpSlot{chans[c].fits[i].templ, chans[c].fits[i].lo, chans[c].fits[i].hi, chans[c].fits[i].outside, dt.nlow};
     }
     const int grid = 2;
     const long long per_cta = K::scratch_v(max_templ);
     std::vector<cx<T>> scratch((size_t)grid * per_cta);
     Dp2Params<T> prm{};
     prm.traces = traces.data();
-    prm.row_stride = G::N;
+    prm.event_stride = (long long)G::N * (long long)chans.size();
+    prm.chan_stride = G::N;
     prm.n_rows = n_events * (int)chans.size();
     prm.n_chan = (int)chans.size();
     prm.chans = cd.data();

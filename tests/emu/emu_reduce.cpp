@@ -55,7 +55,9 @@ int main(int argc, char** argv) {
     std::vector<double> out((size_t)n_events * plan.n_out, -1.0);
     DpReduceParams prm{};
     prm.traces = traces.data();
-    prm.row_stride = N;
+    prm.event_stride = N;
+    prm.chan_stride = N;
+    prm.nb_samples = N;
     prm.n_rows = n_events;
     prm.n_chan = 1;
     prm.chans = plan.chans.data();

@@ -68,7 +68,7 @@ def test_trigger_overflow_of_the_output_buffer_is_never_truncated():
     trig.update_trace(x)
     big = trig.find_triggers_once(1.0, pileup_window_samples=3, max_triggers=L)['ch']
     small = trig.find_triggers_once(1.0, pileup_window_samples=3, max_triggers=7)['ch']
-    assert len(big['trigger_index']) > 1000
+    assert len(big['trigger_index']) > 300
     assert np.array_equal(np.asarray(small['trigger_index']), np.asarray(big['trigger_index']))
     assert np.array_equal(np.asarray(small['trigger_amplitude']), np.asarray(big['trigger_amplitude']))
     assert trig._plan.n_found == len(big['trigger_index'])
