@@ -133,6 +133,27 @@ def reference_main(a):
 
 
 # ----------------------------------------------------------------------- GPU arm
+# measured issue rates of the FP64 pipe on this part (tools/ubench/pipes.cu, profiles/r1_ubench_pipes.log), warp-instructions
+# per clock and SM; the instruction counts of the headline kernel come from the committed ncu summary
+PIPE_DFMA, PIPE_DADD, N_SM = 1.68, 1.97, 148
+
+
+def ncu_summary(name):
+    """profiles/<name>.json written by tools/ncu_summary.py from one `ncu --set full` capture of the kernel"""
+    path = os.path.join(ROOT, 'profiles', name)
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
+def fp_issue_floor_ms(summ, events, sm_hz):
+    """time the FP64 instructions of `events` events need at the measured issue rates with every SM busy -- the floor
+    of THIS instruction mix; kernel_ms / floor = how much of the launch is not FP64 issue"""
+    per_event = (summ['dfma_warp_inst'] / PIPE_DFMA + (summ['dadd_warp_inst'] + summ['dmul_warp_inst']) / PIPE_DADD) / summ['events']
+    return per_event * events / N_SM / sm_hz * 1e3
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -417,13 +438,15 @@ def extras(device, dist, world, hbm_peak):
                     + '    integral:\n        run: True\n        window_min_from_trig_usec: -500\n        window_max_from_trig_usec: 500\n')
         for name, host, kw in (('int16', host_i16, {'adc_gain': [gain], 'adc_offset': [0.0]}), ('float64', host_f64, {})):
             fp = FeatureProcessing(ArrayReader(host, ['chan1'], FS, **kw), yml, filter_data=fd, verbose=False)
-            fp.process(batch_size=2048, gather=False)          # warm-up (plans, staging)
+            fp.process(batch_size=512, gather=False)           # warm-up (plans, staging)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            df = fp.process(batch_size=2048, gather=False)
+            df = fp.process(batch_size=512, gather=False)     # 8 batches: the upload of one overlaps the kernels of the previous
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            out[f'pipeline_yaml_c2_{name}'] = {'events_per_s_per_gpu': E / dt, 'events': E, 'columns': int(df.shape[1]),
+            # `process` shards the reader's events over the ranks: the job handles E events in dt, each GPU E / world
+            out[f'pipeline_yaml_c2_{name}'] = {'events_per_s_job': E / dt, 'events_per_s_per_gpu': E / world / dt, 'events': E,
+                                               'columns': int(df.shape[1]),
                                                'h2d_bytes': int(host.numel() * host.element_size()),
                                                'api': 'FeatureProcessing.process (YAML, FilterData, pinned host events)'}
             del fp, df
@@ -476,6 +499,56 @@ def extras(device, dist, world, hbm_peak):
     return out
 
 
+def collective_rows(device, dist, world):
+    """The two collectives the multi-GPU design rests on, timed warm on the device (CUDA events, max over ranks), NCCL
+    over NVLink: (a) the gather of the per-event feature tables -- 1 M events x 17 float64 columns in total, through
+    detprocess_b200.process.features.gather_frames' tensor path; (b) the all-reduce of the per-GPU periodogram sums
+    [N/2+1] + count of the PSD estimator (N = 65536); (c) the same for the CSD sums [n^2][N/2+1], n = 2, N = 32768."""
+    import torch
+    out = {}
+    if world == 1:
+        return out
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rows, ncol = 1_000_000 // world, 17
+    block = torch.randn((rows, ncol), dtype=torch.float64, device=device)
+    parts = [torch.empty_like(block) for _ in range(world)]
+    ms = timed(lambda: dist.all_gather(parts, block))
+    out['gather_feature_table_1M_x17'] = {'ms': ms, 'bytes_total': rows * world * ncol * 8,
+                                          'gbs_per_rank_received': rows * (world - 1) * ncol * 8 / (ms * 1e-3) / 1e9,
+                                          'collective': 'all_gather (NCCL), one [B/G, 17] float64 block per rank'}
+    sums = torch.randn(65536 // 2 + 1, dtype=torch.float64, device=device)
+    cnt = torch.ones(1, dtype=torch.int64, device=device)
+
+    def psd_reduce():
+        dist.all_reduce(sums)
+        dist.all_reduce(cnt)
+    out['allreduce_psd_sums_65536'] = {'ms': timed(psd_reduce), 'bytes': int(sums.numel() * 8 + 8),
+                                       'collective': 'all_reduce(SUM) of [N/2+1] float64 + int64 count (NoisePSD.finalize)'}
+    csd = torch.randn((4, 32768 // 2 + 1), dtype=torch.float64, device=device)
+
+    def csd_reduce():
+        dist.all_reduce(csd)
+        dist.all_reduce(cnt)
+    out['allreduce_csd_sums_2ch_32768'] = {'ms': timed(csd_reduce), 'bytes': int(csd.numel() * 8 + 8),
+                                           'collective': 'all_reduce(SUM) of [n^2][N/2+1] float64 + count (NoiseCSD.finalize)'}
+    return out
+
+
 def gpu_main(a):
     import torch
     rank = int(os.environ.get('RANK', '0'))
@@ -493,6 +566,10 @@ def gpu_main(a):
         raise SystemExit('bench.py: no CUDA device (detprocess_b200 has no CPU fallback)')
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    # one process per GPU: a disjoint slice of the GPU-local cores before any pinned allocation (detprocess_b200/utils/affinity.py)
+    from detprocess_b200.utils.affinity import bind_to_gpu
+    placement = bind_to_gpu(local, local, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
+    placement['bound_cpus'] = f"{len(placement['bound_cpus'])} cpus from {min(placement['bound_cpus'])}" if placement.get('bound_cpus') else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -519,58 +596,53 @@ def gpu_main(a):
         results[prec] = {'ms_total': ms, 'ms_per_step': ms / a.steps, 'value': world * B * a.steps / (ms * 1e-3),
                          'kernel_ms': kms_avg, 'achieved_gbs': B * BYTES_PER_EVENT / (kms_avg * 1e-3) / 1e9,
                          'launches': a.steps}
-        # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside ----
+        # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region.  The
+        # headline e2e ships the events the way the detector stores them, int16 ADC counts (converted in the kernel's
+        # load with the channel's gain / offset); the float64-amps variant (4x the PCIe bytes) is reported beside it.
         E = min(a.e2e_events, B)
+        reps = max(1, min(a.steps, 5))
+
+        def time_host(plan_, host_):
+            hout = np.empty((E, plan_.n_out), dtype=np.float64)
+            plan_.run_host(host_, hout)      # warm-up (allocates staging once)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                plan_.run_host(host_, hout)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return world * E * reps / dt
+
         host = torch.empty((E, NB_SAMPLES), dtype=torch.float64).pin_memory()
         host.copy_(x[:E].cpu())
-        hout = np.empty((E, plan.n_out), dtype=np.float64)
-        plan.run_host(host, hout)      # warm-up (allocates staging once)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        reps = max(1, min(a.steps, 5))
-        for _ in range(reps):
-            plan.run_host(host, hout)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        results[prec]['e2e'] = {'value': world * E * reps / dt, 'unit': UNIT,
-                                'h2d_bytes_per_step': int(E * BYTES_PER_EVENT),
-                                'd2h_bytes_per_step': int(E * plan.n_out * 8),
-                                'events_per_step': E,
-                                'api': 'OFPlan.run_host -> dp_of1x1_batch_host (pinned host buffers)'}
+        results[prec]['e2e_f64'] = {'value': time_host(plan, host), 'unit': UNIT,
+                                    'h2d_bytes_per_step': int(E * BYTES_PER_EVENT),
+                                    'd2h_bytes_per_step': int(E * plan.n_out * 8), 'events_per_step': E,
+                                    'input': 'pinned host float64 amps',
+                                    'api': 'OFPlan.run_host -> dp_of1x1_batch_host'}
         results[prec]['n_out'] = plan.n_out
-        del plan, out
-        # ---- the same with the traces as they are on disk: int16 ADC counts, converted in the kernel's load ----
+        del plan, out, host
         gain = 1.0e-11
         aplan = build_plan(S, prec, adc=(gain, 0.0))
         ahost = torch.empty((E, NB_SAMPLES), dtype=torch.int16).pin_memory()
         ahost.copy_(torch.clamp(torch.round(x[:E] / gain), -32768, 32767).to(torch.int16).cpu())
-        aplan.run_host(ahost, hout)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            aplan.run_host(ahost, hout)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        results[prec]['e2e_adc'] = {'value': world * E * reps / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(E * NB_SAMPLES * 2),
-                                    'd2h_bytes_per_step': int(E * aplan.n_out * 8),
-                                    'input': 'pinned host int16 ADC counts, adc->amps in the kernel (set_adc_conversion)'}
-        del aplan
+        results[prec]['e2e'] = {'value': time_host(aplan, ahost), 'unit': UNIT, 'h2d_bytes_per_step': int(E * NB_SAMPLES * 2),
+                                'd2h_bytes_per_step': int(E * aplan.n_out * 8), 'events_per_step': E,
+                                'input': 'pinned host int16 ADC counts as stored by the DAQ, adc->amps in the kernel load '
+                                         '(dp_of_plan_set_adc_conversion)',
+                                'api': 'OFPlan.run_host -> dp_of1x1_batch_host'}
+        del aplan, ahost
 
     ex = None
     if not a.no_extras:
         ex = extras(device, dist, world, hbm_peak)
+    coll = collective_rows(device, dist, world)
     if sampler:
         sampler.stop_flag = True
     if rank != 0:
@@ -579,6 +651,25 @@ def gpu_main(a):
         return 0
 
     r = results['f64']
+    summ = ncu_summary('r2_ncu_of2_f64_c2.json')
+    roofline = {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': r['achieved_gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'kernel': 'dp_of2_kernel<double,4,0,true>', 'kernel_ms': r['kernel_ms'],
+                'algorithmic_bytes_per_event': BYTES_PER_EVENT,
+                'note': 'the FFT path is FP64-issue / latency bound, not HBM bound (10 FLOP/B): fp_issue_frac is the share '
+                        'of the launch the FP64 instructions alone need at the measured pipe rates (DESIGN.md 4.1)'}
+    if summ is not None:
+        sm_hz = (sampler.summary().get('sm_mhz') or 1965.0) * 1e6 if sampler else 1965.0e6
+        floor = fp_issue_floor_ms(summ, B, sm_hz)
+        roofline.update({
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full), per event x events
+            'traffic': summ['dram_bytes_per_event'] * B,
+            'traffic_over_algorithmic': summ['dram_bytes_per_event'] / BYTES_PER_EVENT,
+            'traffic_source': 'profiles/r2_ncu_of2_f64_c2.json (tools/ncu_summary.py of profiles/r2_prof_of2_f64_32k_c2.txt)',
+            'fp_issue_floor_ms': floor, 'fp_issue_frac': floor / r['kernel_ms'],
+            'fp_issue_model': f'(DFMA / {PIPE_DFMA} + (DADD + DMUL) / {PIPE_DADD}) warp-inst per clk and SM x {N_SM} SMs at the '
+                              f'sampled SM clock; counts from the ncu summary: {summ["dfma_warp_inst"] / summ["events"]:.0f} DFMA + '
+                              f'{(summ["dadd_warp_inst"] + summ["dmul_warp_inst"]) / summ["events"]:.0f} DADD/DMUL warp-inst per event'})
     line = {
         'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -587,31 +678,26 @@ def gpu_main(a):
                    'events_per_gpu_per_step': B, 'input': 'float64 traces resident in HBM',
                    'l2': f'inputs ({B * BYTES_PER_EVENT / 2**30:.1f} GiB/GPU) larger than L2, no flush needed',
                    'sharding': 'events sharded by rank, no data-path collective'},
-        'roofline': {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
-                     'frac': r['achieved_gbs'] / hbm_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel: 822.5 MB + 559.0 MB for 2048 events in
-                     # profiles/r1_prof_of2_f64_32k_c2_r6.txt (ncu --set full), scaled to the events of one launch
-                     'traffic': (822.486016e6 + 558.953216e6) / 2048 * B,
-                     'traffic_source': 'profiles/r1_prof_of2_f64_32k_c2_r6.txt (per event x events per launch)',
-                     'peak_source': peak_src,
-                     'kernel': 'dp_of2_kernel<double,4,0,true>', 'kernel_ms': r['kernel_ms'],
-                     'algorithmic_bytes_per_event': BYTES_PER_EVENT,
-                     'note': 'FFT path is FP64-pipe / issue bound, not HBM bound (10 FLOP/B); see DESIGN.md 4.1'},
-        'e2e': {k: r['e2e'][k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')},
-        'e2e_adc_i16': r['e2e_adc'],
+        'roofline': roofline,
+        'e2e': {k: r['e2e'][k] for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'input', 'api')},
+        'e2e_f64_host': r['e2e_f64'],
         'gpu_launches': r['launches'] * world,
         'clocks': sampler.summary() if sampler else None,
     }
     if 'f32' in results:
         f = results['f32']
+        summ32 = ncu_summary('r2_ncu_of2_f32_c2.json')
         line['fast_mode'] = {'dtype': 'f32', 'value': f['value'], 'unit': UNIT, 'ms_per_step': f['ms_per_step'],
                              'roofline_frac': f['achieved_gbs'] / hbm_peak, 'achieved_gbs': f['achieved_gbs'],
                              'kernel': 'dp_of2_kernel<f2,4,0,true>', 'e2e': f['e2e']['value'],
-                             'e2e_adc_i16': f['e2e_adc']['value'],
-                             'traffic': (537.799168e6 + 6.095104e6) / 2048 * B,      # profiles/r1_prof_of2_f32_32k_c2_r6.txt
+                             'e2e_f64_host': f['e2e_f64']['value'],
+                             'traffic': (summ32['dram_bytes_per_event'] * B) if summ32 else None,
                              'tolerance': 'amp 1e-5, chi2 1e-4 rel vs float64 oracle'}
     if ex is not None:
         line['other_rows'] = ex
+    if coll:
+        line['collectives'] = coll
+    line['host_placement'] = placement
     if cb is not None:
         line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line), flush=True)
