@@ -19,6 +19,8 @@
 #include "dp_nxm_plan.hpp"
 #include "dp_of2_launch.hpp"
 #include "dp_of_launch.hpp"
+#include "dp_ofg_launch.hpp"
+#include "dp_ofg_plan.hpp"
 #include "dp_plan.hpp"
 #include "dp_plan2.hpp"
 #include "dp_psd2_kernel.cuh"
@@ -94,6 +96,10 @@ struct dp_of_plan {
     dpplan::Geometry geom;
     int v2_r1 = 0;  // != 0: the v2 kernels (dp_of2_kernel.cuh) serve this plan, M = v2_r1 * 4096
     int v2_multi = 0;  // some channel has more than one template
+    bool generic = false;  // nb_samples is not a power of two: the mixed-radix kernel (dp_ofg_kernel.cuh) serves this plan
+    const void *g_tw = nullptr, *g_wn = nullptr, *g_pos_k = nullptr, *g_pos_m = nullptr;
+    std::vector<int> g_radix;
+    int g_pairs = 0;
     size_t persist_bytes = 0;  // scratch bytes kept persisting in L2 (0: no access-policy window)
     // device state
     std::vector<void*> owned;
@@ -443,12 +449,130 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     return DP_OK;
 }
 
+// ------------------------------------------------------------------ mixed-radix kernel (nb_samples not 2^k)
+template <class T> int ofg_finalize(dp_of_plan* p) {
+    dpgen::Tables<T> dt;
+    try {
+        dt = dpgen::build_tables<T>(p->N, p->fs, p->chans, table_fcut(p), p->scale);
+    } catch (const std::invalid_argument& e) {
+        return fail(DP_ERR_INVALID, e.what());
+    } catch (const std::exception& e) {
+        return fail(DP_ERR_STATE, e.what());
+    }
+    p->nlow = dt.nlow;
+    p->g_radix = dt.radix;
+    p->g_pairs = dt.n_pairs;
+    int rc;
+    const cx<T>* d;
+    const int* di;
+    if ((rc = upload(p->owned, dt.tw, &d))) return rc;
+    p->g_tw = d;
+    if ((rc = upload(p->owned, dt.wn, &d))) return rc;
+    p->g_wn = d;
+    if ((rc = upload(p->owned, dt.pos_k, &di))) return rc;
+    p->g_pos_k = di;
+    if ((rc = upload(p->owned, dt.pos_m, &di))) return rc;
+    p->g_pos_m = di;
+    std::vector<DpGenChanDev<T>> cd(p->n_chan);
+    p->chan_out_base.assign(p->n_chan, 0);
+    int base = 0;
+    for (int c = 0; c < p->n_chan; ++c) {
+        DpGenChanDev<T>& dc = cd[c];
+        std::memset(&dc, 0, sizeof(dc));
+        const T* w;
+        if ((rc = upload(p->owned, dt.chans[c].wj_k, &w))) return rc;
+        dc.wj_k = w;
+        if ((rc = upload(p->owned, dt.chans[c].wj_m, &w))) return rc;
+        dc.wj_m = w;
+        if ((rc = upload(p->owned, dt.chans[c].wj_low, &w))) return rc;
+        dc.wj_low = w;
+        dc.adc_gain = c < (int)p->adc_gain.size() ? p->adc_gain[c] : 1.0;
+        dc.adc_offset = c < (int)p->adc_offset.size() ? p->adc_offset[c] : 0.0;
+        dc.n_templ = (int)p->chans[c].templ.size();
+        dc.n_slots = (int)p->chans[c].fits.size();
+        dc.out_base = base;
+        p->chan_out_base[c] = base;
+        base += 1 + DP_SLOT_NOUT * dc.n_slots;
+        for (int i = 0; i < dc.n_templ; ++i) {
+            auto& h = dt.chans[c].templ[i];
+            const cx<T>* ph;
+            if ((rc = upload(p->owned, h.phi_k, &ph))) return rc;
+            dc.templ[i].phi_k = ph;
+            if ((rc = upload(p->owned, h.phi_m, &ph))) return rc;
+            dc.templ[i].phi_m = ph;
+            if ((rc = upload(p->owned, h.s_low, &ph))) return rc;
+            dc.templ[i].s_low = ph;
+            dc.templ[i].norm = h.norm;
+            dc.templ[i].tsum = h.tsum;
+            dc.templ[i].pretrigger = h.pretrigger;
+        }
+        for (int i = 0; i < dc.n_slots; ++i) {
+            const auto& f = p->chans[c].fits[i];
+            dc.slots[i] = DpSlot{f.templ, f.lo, f.hi, f.outside, std::min(p->nlow, dpplan::count_low_bins(p->N, p->fs, f.fcut < 0 ? p->fcut : f.fcut))};
+        }
+    }
+    p->n_out = base;
+    const DpGenChanDev<T>* dcd;
+    if ((rc = upload(p->owned, cd, &dcd))) return rc;
+    p->d_chans = dcd;
+    size_t smem = 0;
+    int grid_max = 0;
+    const int src = dp_ofg_setup(sizeof(T) == 8 ? 0 : 1, p->N / 2, p->device, &smem, &grid_max);
+    if (src == -2) return fail(DP_ERR_UNSUPPORTED, "event does not fit one SM's shared memory");
+    if (src != 0) return fail(DP_ERR_CUDA, std::string("OF kernel setup: ") + cudaGetErrorString((cudaError_t)src));
+    p->smem = smem;
+    p->grid_max = grid_max;
+    return DP_OK;
+}
+
+template <class T>
+int ofg_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, const OfLayout& lay, double* out_dev,
+            cudaStream_t st, bool timed) {
+    DpGenParams<T> prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.traces = traces_dev;
+    prm.in_dtype = in_dtype % 3;        // element-wise loads: the pair-aligned / element-aligned variants coincide
+    prm.event_stride = lay.event_stride;
+    prm.chan_stride = lay.chan_stride;
+    prm.chan_offset = lay.chan_offset_dev;
+    prm.row_start = lay.row_start;
+    prm.stream_len = lay.stream_len;
+    prm.n_rows = (int)(n_events * p->n_chan);
+    prm.n_chan = p->n_chan;
+    prm.chans = reinterpret_cast<const DpGenChanDev<T>*>(p->d_chans);
+    prm.M = p->N / 2;
+    prm.n_pass = (int)p->g_radix.size();
+    for (int j = 0; j < prm.n_pass; ++j) prm.radix[j] = p->g_radix[j];
+    prm.tw = reinterpret_cast<const cx<T>*>(p->g_tw);
+    prm.wn = reinterpret_cast<const cx<T>*>(p->g_wn);
+    prm.pos_k = reinterpret_cast<const int*>(p->g_pos_k);
+    prm.pos_m = reinterpret_cast<const int*>(p->g_pos_m);
+    prm.n_pairs = p->g_pairs;
+    prm.out = out_dev;
+    prm.n_out = p->n_out;
+    prm.nlow = p->nlow;
+    prm.scale = p->scale;
+    prm.subtract_first = p->subtract_first;
+    const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
+    if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
+    const int rc = dp_ofg_launch(sizeof(T) == 8 ? 0 : 1, &prm, grid, p->smem, st);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    if (timed) DP_CUDA(cudaEventRecord(p->ev1, st));
+    p->timed = timed;
+    p->launches += 1;
+    return DP_OK;
+}
+
 // precision / kernel-generation dispatch of one batch launch
 int of_dispatch(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_events, const OfLayout& lay, double* out_dev,
                 cudaStream_t st, bool timed) {
     if (p->v2_r1) {
         if (p->precision == DP_PREC_F32) return of2_run<f2>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
         return of2_run<double>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
+    }
+    if (p->generic) {
+        if (p->precision == DP_PREC_F32) return ofg_run<float>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
+        return ofg_run<double>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
     }
     if (p->precision == DP_PREC_F32) return of_run<float>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
     return of_run<double>(p, traces_dev, in_dtype, n_events, lay, out_dev, st, timed);
@@ -482,10 +606,14 @@ int dp_of_plan_create(dp_of_plan** plan, int nb_samples, double sample_rate, int
     const char* gen = std::getenv("DP_OF_KERNEL");
     p->v2_r1 = (gen && std::string(gen) == "v1") ? 0 : dpplan2::r1_of(nb_samples);
     if (!p->v2_r1) {
-        try {
-            p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
-        } catch (const std::exception& e) {
-            return fail(DP_ERR_UNSUPPORTED, e.what());
+        if (!dpplan::is_pow2(nb_samples) && dpgen::supported(nb_samples, precision == DP_PREC_F64)) {
+            p->generic = true;      // e.g. 25000 / 12500 samples (reference examples/processing/process_example.yaml:93-94)
+        } else {
+            try {
+                p->geom = dpplan::pick_geometry(nb_samples, precision == DP_PREC_F64);
+            } catch (const std::exception& e) {
+                return fail(DP_ERR_UNSUPPORTED, std::string(e.what()) + " (or an even length whose half factors into 2, 3, 4, 5 and fits one SM)");
+            }
         }
     }
     p->N = nb_samples;
@@ -623,6 +751,8 @@ int dp_of_plan_finalize(dp_of_plan* p, int device) {
     int rc;
     if (p->v2_r1)
         rc = (p->precision == DP_PREC_F32) ? of2_finalize<f2>(p) : of2_finalize<double>(p);
+    else if (p->generic)
+        rc = (p->precision == DP_PREC_F32) ? ofg_finalize<float>(p) : ofg_finalize<double>(p);
     else
         rc = (p->precision == DP_PREC_F32) ? of_finalize<float>(p) : of_finalize<double>(p);
     if (rc) return rc;
@@ -744,7 +874,8 @@ int dp_of1x1_batch_ex(dp_of_plan* p, const void* base_dev, int in_dtype, long lo
         lay.chan_offset_dev = p->d_chan_off;
     }
     const int in = pair_aligned ? in_dtype : in_dtype + 3;
-    if (!pair_aligned && !p->v2_r1) return fail(DP_ERR_UNSUPPORTED, "element-aligned rows / windows need nb_samples 16384, 32768 or 65536");
+    if (!pair_aligned && !p->v2_r1 && !p->generic)
+        return fail(DP_ERR_UNSUPPORTED, "element-aligned rows / windows need nb_samples 16384, 32768, 65536 or a non power of two");
     return of_dispatch(p, base_dev, in, n_events, lay, out_dev, st, true);
 }
 

@@ -45,6 +45,34 @@ inline void fft_pow2(std::vector<cplx>& a) {
     }
 }
 
+
+// forward DFT of any length: radix-2 when n is a power of two, Bluestein's chirp-z through fft_pow2 otherwise
+// (one-time setup of a template spectrum; trace lengths such as 25000 = 2^3 5^5)
+inline void fft_any(std::vector<cplx>& a) {
+    const size_t n = a.size();
+    if ((n & (n - 1)) == 0) {
+        fft_pow2(a);
+        return;
+    }
+    size_t f = 1;
+    while (f < 2 * n - 1) f <<= 1;
+    std::vector<cplx> chirp(n);   // exp(-i pi j^2 / n), j^2 reduced mod 2n in integers
+    for (size_t j = 0; j < n; ++j) {
+        const unsigned long long q = ((unsigned long long)j * j) % (2ull * n);
+        const long double ang = -3.14159265358979323846264338327950288L * (long double)q / (long double)n;
+        chirp[j] = cplx((double)cosl(ang), (double)sinl(ang));
+    }
+    std::vector<cplx> x(f, cplx(0, 0)), y(f, cplx(0, 0));
+    for (size_t j = 0; j < n; ++j) x[j] = a[j] * chirp[j];
+    y[0] = std::conj(chirp[0]);
+    for (size_t j = 1; j < n; ++j) y[j] = y[f - j] = std::conj(chirp[j]);
+    fft_pow2(x);
+    fft_pow2(y);
+    for (size_t j = 0; j < f; ++j) x[j] = std::conj(x[j] * y[j]);   // inverse transform as conj(fft(conj(.))) / f
+    fft_pow2(x);
+    for (size_t k = 0; k < n; ++k) a[k] = std::conj(x[k]) / (double)f * chirp[k];
+}
+
 struct Template {
     std::vector<double> trace;  // [N]
     int pretrigger = 0;
@@ -160,7 +188,7 @@ inline void finalize_template(Template& tp, const std::vector<double>& J, double
     const double df = fs / N;
     std::vector<cplx> a(N);
     for (int i = 0; i < N; ++i) a[i] = cplx(tp.trace[i], 0.0);
-    fft_pow2(a);
+    fft_any(a);
     tp.s.resize(N);
     for (int i = 0; i < N; ++i) tp.s[i] = a[i] / (double)N / df;
     if (tp.integralnorm) {

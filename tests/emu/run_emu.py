@@ -24,10 +24,23 @@ def build(tsan=False, v2=False, asan=False):
     return exe
 
 
+def build_generic():
+    """emulator of the mixed-radix kernel (dp_ofg_kernel.cuh)"""
+    os.makedirs(os.path.join(HERE, '_build'), exist_ok=True)
+    exe = os.path.join(HERE, '_build', 'emu_ofg')
+    src = os.path.join(HERE, 'emu_ofg.cpp')
+    deps = [src] + [os.path.join(HERE, '../../detprocess_b200/csrc', f) for f in
+                    ('dp_of_kernel.cuh', 'dp_fft.cuh', 'dp_platform.cuh', 'dp_plan.hpp', 'dp_ofg_kernel.cuh', 'dp_ofg_plan.hpp')]
+    if os.path.exists(exe) and all(os.path.getmtime(exe) > os.path.getmtime(d) for d in deps):
+        return exe
+    subprocess.check_call(['g++', '-std=c++20', '-O1', '-pthread', '-o', exe, src])
+    return exe
+
+
 def run(traces, psd, templates, fits, fs, fcut=10000.0, precision='f64', ac=True,
-        subtract_first=False, scale=1.0, tsan=False, force_p2=False, v2=False, asan=False):
+        subtract_first=False, scale=1.0, tsan=False, force_p2=False, v2=False, asan=False, generic=False):
     """templates: list of (template, pretrigger, integralnorm); fits: list of (templ, lo, hi, outside)."""
-    exe = build(tsan, v2, asan)
+    exe = build_generic() if generic else build(tsan, v2, asan)
     traces = np.ascontiguousarray(traces, dtype=np.float64)
     nev, n = traces.shape
     with tempfile.TemporaryDirectory() as td:

@@ -105,6 +105,32 @@ def test_of_v2_kernel_emulated_constrained_only(nb_samples, precision):
     _check(out, o2, [11], *tol)
 
 
+@pytest.mark.parametrize('nb_samples,precision', [(1000, 'f64'), (2500, 'f64'), (1200, 'f32'), (25000, 'f64')])
+def test_of_mixed_radix_kernel_emulated(nb_samples, precision):
+    """mixed-radix kernel (dp_ofg_kernel.cuh) for trace lengths that are not powers of two -- 25000 = 2^3 5^5 is the
+    reference's example configuration (process_example.yaml:93-94): radix 2/3/4/5 passes, digit-reversed pair tables,
+    Bluestein template spectrum on the host, two templates, all window kinds"""
+    S = SynthSetup(nb_samples)
+    pre = S.nb_pretrigger
+    w = max(20, nb_samples // 60)
+    tr = make_traces(3, S.template, S.psd, S.fs, np.random.default_rng(7), offset=(1e-6 if precision == 'f64' else 0.0),
+                     amp_max=2e-7, max_delay=w // 2)
+    w_def = [(None, None, False), (pre - w, pre + w, False), (pre, pre + 1, False)]
+    w_gl = [(pre - w // 3, pre + w, True)]
+    fits = [(0, 0 if x[0] is None else x[0], nb_samples if x[1] is None else x[1], int(x[2])) for x in w_def]
+    fits += [(1, x[0], x[1], int(x[2])) for x in w_gl]
+    fcut = 10000.0 if nb_samples >= 8000 else 40000.0
+    out = run_emu.run(tr, S.psd, [(S.template, pre, False), (S.template_glitch, pre, False)], fits, S.fs, fcut=fcut,
+                      precision=precision, subtract_first=(precision == 'f32'),
+                      scale=(2.0 ** 26 if precision == 'f32' else 1.0), generic=True)
+    o1 = of1x1_batch(tr, S.template, S.psd, S.fs, pre, windows=w_def, lowchi2_fcutoff=fcut)
+    o2 = of1x1_batch(tr, S.template_glitch, S.psd, S.fs, pre, windows=w_gl, lowchi2_fcutoff=fcut)
+    tol = (1e-10, 1e-10, 1e-10) if precision == 'f64' else (1e-5, 1e-4, 1e-4)
+    assert np.max(np.abs(out[:, 0] / o1['chi0'] - 1)) < tol[1]
+    _check(out, o1, [1, 6, 11], *tol)
+    _check(out, o2, [16], *tol)
+
+
 def test_of_v2_kernel_emulated_address_sanitizer():
     """The kernel source under AddressSanitizer (compute-sanitizer is closed on the GPU pool): every shared-memory,
     scratch and table access of a two-phase, two-template fp64 run stays inside its buffer."""

@@ -276,3 +276,106 @@ chanA+chanB:
     o0 = of1x1_batch(conv[:, 0], S.template, S.psd, fs, pre, windows=[(pre, pre + 1, False)])
     assert np.allclose(df['amp_of1x1_nodelay_chanA'], o0['amp'][0], rtol=1e-9, atol=1e-9 * o0['ampres'])
     assert np.array_equal(df['baseline_chanA'].values, R.baseline_batch(conv[:, 0], 0, n - 1))
+
+
+@pytest.mark.parametrize('nb_samples,precision', [(25000, 'f64'), (12500, 'f64'), (25000, 'f32'), (20000, 'f64')])
+def test_non_power_of_two_trace_lengths(nb_samples, precision):
+    """25000 / 12500 samples (20 ms / 10 ms at 1.25 MHz) are the reference's own example configuration
+    (examples/processing/process_example.yaml:93-94); served by the mixed-radix kernel (dp_ofg_kernel.cuh)"""
+    from detprocess_b200.core.plans import OFPlan
+    S = SynthSetup(nb_samples)
+    pre = S.nb_pretrigger
+    traces = make_traces(64, S.template, S.psd, S.fs, np.random.default_rng(11), offset=(3e-7 if precision == 'f64' else 0.0))
+    plan = OFPlan(nb_samples, S.fs, 1, precision)
+    plan.set_psd(0, S.psd)
+    t0 = plan.add_template(0, S.template, pre)
+    t1 = plan.add_template(0, S.template_glitch, pre)
+    wins0 = [(None, None, False), (pre - 500, pre + 500, False), (pre, pre + 1, False)]
+    wins1 = [(pre - 100, pre + 300, True)]
+    f0 = [plan.add_fit(0, t0, lo, hi, outside) for lo, hi, outside in wins0]
+    f1 = [plan.add_fit(0, t1, lo, hi, outside) for lo, hi, outside in wins1]
+    plan.finalize()
+    out = plan.run(torch.from_numpy(traces).cuda()).cpu().numpy()
+    o0 = of1x1_batch(traces, S.template, S.psd, S.fs, pre, windows=wins0)
+    o1 = of1x1_batch(traces, S.template_glitch, S.psd, S.fs, pre, windows=wins1)
+    tol = dict(f64=(1e-9, 1e-9, 1e-9), f32=(1e-5, 1e-4, 1e-3))[precision]
+    assert np.max(np.abs(out[:, plan.chi0_offset(0)] / o0['chi0'] - 1)) < tol[1]
+    for fits, o in ((f0, o0), (f1, o1)):
+        for iw, fi in enumerate(fits):
+            off = plan.fit_offset(0, fi)
+            ind = out[:, off + 1].astype(np.int64)
+            ref = {k: o[k][iw] for k in ('amp', 'chi2', 'lowchi2')}
+            if precision == 'f64':
+                assert np.array_equal(ind, o['ind'][iw])
+            elif not np.array_equal(ind, o['ind'][iw]):      # fp32 near-ties, same rule as tests/test_gpu_of1x1.py
+                at = o['at'](ind)
+                bound = 2 * tol[0] * np.maximum(o['amp'][iw] ** 2, (5 * o['ampres']) ** 2) * o['norm']
+                assert np.all(np.abs(at['chi2'] - o['chi2'][iw]) <= bound)
+                ref = {k: at[k] for k in ref}
+            assert np.max(np.abs(out[:, off] - ref['amp']) / np.maximum(np.abs(ref['amp']), 5 * o['ampres'])) < tol[0]
+            assert np.max(np.abs(out[:, off + 2] / ref['chi2'] - 1)) < tol[1]
+            assert np.max(np.abs(out[:, off + 3] / ref['lowchi2'] - 1)) < tol[2]
+    # int16 windows of a continuous stream through the same kernel
+    if precision == 'f64':
+        L = 5 * nb_samples + 3
+        gain, offs = 1.0e-11, 2.0e-9
+        stream = make_continuous(L, S.template, S.psd, S.fs, np.random.default_rng(12), pulse_rate_hz=100.0)
+        adc = np.clip(np.round((stream - offs) / gain), -32768, 32767).astype(np.int16)
+        plan2 = OFPlan(nb_samples, S.fs, 1, precision)
+        plan2.set_psd(0, S.psd)
+        plan2.set_adc_conversion(0, gain, offs)
+        fi = plan2.add_fit(0, plan2.add_template(0, S.template, pre), pre - 500, pre + 500)
+        plan2.finalize()
+        starts = np.array([0, 1, nb_samples + 7, L - nb_samples, L - nb_samples + 1], dtype=np.int64)
+        got = plan2.run_layout(torch.from_numpy(adc[None, :]).cuda(), [0], torch.from_numpy(starts).cuda()).cpu().numpy()
+        assert np.all(got[-1] == -999999.0)
+        win = np.stack([adc[s:s + nb_samples].astype(np.float64) * gain + offs for s in starts[:-1]])
+        o = of1x1_batch(win, S.template, S.psd, S.fs, pre, windows=[(pre - 500, pre + 500, False)])
+        off = plan2.fit_offset(0, fi)
+        assert np.array_equal(got[:-1, off + 1].astype(np.int64), o['ind'][0])
+        assert np.max(np.abs(got[:-1, off + 2] / o['chi2'][0] - 1)) < 1e-9
+
+
+def test_reference_example_yaml_lengths_end_to_end(tmp_path):
+    """the feature section of the reference's example YAML asks for 20 ms traces with 10 ms pretrigger at 1.25 MHz
+    (25000 / 12500 samples): the pipeline processes them (OF blocks on the mixed-radix kernel, window features)"""
+    from detprocess_b200.core.filterdata import FilterData
+    from detprocess_b200.process import FeatureProcessing
+    fs = 1.25e6
+    S = SynthSetup(25000, fs, nb_pretrigger=12500)
+    n, pre = S.nb_samples, S.nb_pretrigger
+    traces = make_traces(40, S.template, S.psd, fs, np.random.default_rng(3))
+    fd = FilterData()
+    fd.set_psd('chan1', S.psd, sample_rate=fs)
+    fd.set_template('chan1', S.template, sample_rate=fs, pretrigger_length_samples=pre)
+    y = tmp_path / 'ex.yaml'
+    y.write_text('''
+global:
+    trace_length_msec: 20
+    pretrigger_length_msec: 10
+chan1:
+    of1x1_nodelay:
+        run: True
+        template_tag: default
+    of1x1_constrained:
+        run: True
+        template_tag: default
+        window_min_from_trig_usec: -400
+        window_max_from_trig_usec: 400
+    baseline:
+        run: True
+        window_min_from_start_usec: 0
+        window_max_from_trig_usec: -1000
+    integral:
+        run: True
+        window_min_from_trig_usec: -500
+        window_max_from_trig_usec: 500
+''')
+    df = FeatureProcessing({'traces': traces[:, None, :], 'channels': ['chan1'], 'sample_rate': fs}, str(y), filter_data=fd, verbose=False).process()
+    o = of1x1_batch(traces, S.template, S.psd, fs, pre, windows=[(pre - 500, pre + 500, False), (pre, pre + 1, False)])
+    assert np.allclose(df['amp_of1x1_constrained_chan1'], o['amp'][0], rtol=1e-9, atol=1e-9 * o['ampres'])
+    assert np.allclose(df['chi2_of1x1_constrained_chan1'], o['chi2'][0], rtol=1e-9)
+    assert np.allclose(df['t0_of1x1_constrained_chan1'], o['t0'][0], rtol=0, atol=1e-12)
+    assert np.allclose(df['amp_of1x1_nodelay_chan1'], o['amp'][1], rtol=1e-9, atol=1e-9 * o['ampres'])
+    assert np.array_equal(df['baseline_chan1'].values, R.baseline_batch(traces, 0, pre - 1250))
+    assert np.array_equal(df['integral_chan1'].values, R.integral_batch(traces, fs, pre - 625, pre + 625))
