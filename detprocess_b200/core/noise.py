@@ -9,8 +9,14 @@ batches (each trace is read from HBM exactly once); every rank accumulates
 all-reduced (NCCL over NVLink when ``torch.distributed`` is initialised with the nccl
 backend) and the two-sided PSD is formed on every rank.
 
-The noise autocut (``qp.autocuts_noise``, noise.py:331) is QETpy code that is not part of
-the reference tree; its result enters here as the boolean ``cut`` mask.
+The noise autocut (``qp.autocuts_noise``, noise.py:331) is a POPULATION-level, data-dependent cut: it does not
+decompose over ranks.  ``trace_statistics`` + ``global_autocut`` give the two-pass form that does (SURVEY.md hard part 6):
+pass 1 computes per-trace statistics on every rank (window reductions of the fused kernels, bit-identical to numpy, so
+the numbers do not depend on the sharding), one ``all_gather`` makes the whole population visible to every rank, every
+rank derives the SAME global mask and keeps its own slice; pass 2 accumulates the periodograms of the accepted traces.
+The cut function itself is pluggable: QETpy's ``autocuts_noise`` is not part of the reference tree (parity unpinned);
+the default below is an iterative n-sigma clip on baseline, slope and range in the manner of ``qetpy.cut.IterCut``.
+A caller-supplied boolean ``cut`` mask still works as before.
 """
 import numpy as np
 
@@ -99,6 +105,77 @@ class NoisePSD:
         return freqs, psd
 
 
+# ------------------------------------------------------------------------------------------ global autocut (two pass)
+def trace_statistics(traces, fs):
+    """Per-trace statistics of a CUDA batch [n, N] (float64 amps or int16 ADC counts are not distinguished here: pass
+    amps): baseline of the first and last eighth, their difference (slope) and the peak-to-peak range.  Computed with
+    the window-reduction kernels (numpy's pairwise sums, bit exact), so a trace gives the same numbers on any rank.
+    Returns a CUDA float64 tensor [n, 3] = (baseline, slope, range)."""
+    torch = _torch()
+    from .plans import ReducePlan
+    n = int(traces.shape[-1])
+    key = (n, float(fs), traces.device.index)
+    plan = _stat_plans.get(key)
+    if plan is None:
+        plan = ReducePlan(n, fs, 1)
+        plan.add(0, 'baseline', 0, n // 8)
+        plan.add(0, 'baseline', n - n // 8, n)
+        plan.add(0, 'maximum', 0, n - 1)
+        plan.add(0, 'minimum', 0, n - 1)
+        plan.finalize(traces.device)
+        _stat_plans[key] = plan
+    o = plan.run(traces.to(torch.float64))
+    c = [plan.column(i) for i in range(4)]
+    return torch.stack([o[:, c[0]], o[:, c[1]] - o[:, c[0]], o[:, c[2]] - o[:, c[3]]], dim=1)
+
+
+_stat_plans = {}
+
+
+def sigma_clip_cut(stats, nsig=2.0, max_iter=20):
+    """Iterative n-sigma clipping on every column of ``stats`` [n, k] (numpy): a trace survives when all of its statistics
+    stay within nsig standard deviations of the surviving population's mean; repeated until the selection is stable
+    (the scheme of qetpy.cut.IterCut, which autocuts_noise is built from).  Deterministic function of the population."""
+    stats = np.asarray(stats, dtype=np.float64)
+    keep = np.all(np.isfinite(stats), axis=1)
+    for _ in range(max_iter):
+        if keep.sum() < 2:
+            break
+        mu, sd = stats[keep].mean(axis=0), stats[keep].std(axis=0)
+        new = keep & np.all(np.abs(stats - mu) <= nsig * np.where(sd > 0, sd, np.inf), axis=1)
+        if np.array_equal(new, keep):
+            break
+        keep = new
+    return keep
+
+
+def global_autocut(stats_local, cut_fn=sigma_clip_cut, group=None):
+    """The population-wide cut for a rank-sharded sample: ``stats_local`` [n_local, k] (torch tensor, any device) of the
+    rank's traces in shard order -> boolean numpy mask [n_local].  All ranks all_gather the statistics (padded to the
+    longest shard), evaluate ``cut_fn`` on the concatenation in rank order -- i.e. on exactly the array a single process
+    would have -- and keep their own slice: the sharded PSD equals the single-process one."""
+    torch = _torch()
+    import torch.distributed as dist
+    st = stats_local.detach()
+    if not (dist.is_available() and dist.is_initialized()):
+        return cut_fn(st.cpu().numpy())
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = st.device if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    n_local = torch.tensor([st.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    nmax, k = max(sizes + [1]), st.shape[1]
+    pad = torch.zeros((nmax, k), dtype=torch.float64, device=dev)
+    pad[:st.shape[0]] = st.to(dev)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    population = np.concatenate([p[:m].cpu().numpy() for p, m in zip(parts, sizes)], axis=0)
+    mask = cut_fn(population)
+    lo = sum(sizes[:rank])
+    return mask[lo:lo + sizes[rank]]
+
+
 def calc_psd(traces, fs, cut=None, precision='f64', batch=4096):
     """One-call form on a CUDA tensor [n, N] (what ``qp.calc_psd(traces[cut], fs, folded_over=False)`` returns)."""
     est = NoisePSD(traces.shape[-1], fs, precision=precision, device=traces.device)
@@ -161,7 +238,7 @@ def calc_csd(traces, fs, cut=None, precision='f64', batch=2048):
     return est.finalize()
 
 
-def calc_psd_from_reader(reader, channel, cut=None, precision='f64', batch=4096, device=None):
+def calc_psd_from_reader(reader, channel, cut=None, precision='f64', batch=4096, device=None, autocut=False, cut_fn=sigma_clip_cut):
     """``Noise.calc_psd`` on the randoms behind a ``detprocess_b200.io.EventReader`` (reference core/noise.py:216-370:
     the events are read in one shot there, in batches here; ranks take contiguous shards and all-reduce the sums).
     ADC counts become amps on the device.  Returns (freqs, psd two-sided)."""
@@ -172,6 +249,18 @@ def calc_psd_from_reader(reader, channel, cut=None, precision='f64', batch=4096,
     est = NoisePSD(int(reader.metadata['nb_samples']), reader.sample_rate, precision=precision, device=dev)
     rank, world = dist_info()
     lo, hi = shard_range(len(reader), rank, world)
+    if autocut:
+        # pass 1: per-trace statistics of this rank's shard -> one all_gather -> the global mask (reference noise.py:331:
+        # qp.autocuts_noise on the whole population)
+        stats = []
+        for i0 in range(lo, hi, batch):
+            i1 = min(i0 + batch, hi)
+            stats.append(trace_statistics(reader.to_amps(reader.upload(i0, i1, dev))[:, ci].contiguous(), reader.sample_rate))
+        st = torch.cat(stats) if stats else torch.zeros((0, 3), dtype=torch.float64, device=dev)
+        mask = global_autocut(st, cut_fn)
+        full = np.zeros(len(reader), dtype=bool)
+        full[lo:hi] = mask
+        cut = full if cut is None else (np.asarray(cut, dtype=bool) & full)
     for i0 in range(lo, hi, batch):
         i1 = min(i0 + batch, hi)
         x = reader.to_amps(reader.upload(i0, i1, dev))[:, ci].contiguous()

@@ -65,9 +65,19 @@ class OFBaseBatch:
             csd = np.asarray(csd, dtype=np.complex128)
             if csd.ndim != 3 or csd.shape[0] != csd.shape[1] or csd.shape[0] != len(channel.split('|')):
                 raise ValueError(f'ERROR: csd of "{channel}" must be [n, n, N]')
-            if ignored_frequency_peaks is not None:
-                raise NotImplementedError('ignored_frequency_peaks for joint channels is not built')
             self._check_n(csd.shape[-1])
+            if ignored_frequency_peaks is not None:
+                # bins on an ignored peak carry no weight: the csd diagonal is marked inf there (both signs of f) and the
+                # plan builder zeroes the inverse covariance of the bin
+                csd = csd.copy()
+                f = np.abs(self.fft_freqs())
+                df = self._fs / self._nbins
+                for pk in np.atleast_1d(np.asarray(ignored_frequency_peaks, dtype=float)):
+                    lines = np.arange(pk, self._fs / 2, pk) if ignore_harmonics else [pk]
+                    for fpk in lines:
+                        sel = np.abs(f - fpk) <= df / 2
+                        for a in range(csd.shape[0]):
+                            csd[a, a, sel] = np.inf
             self._nxm_csd[channel] = (csd, coupling)
             self._nxm_plans = {k: v for k, v in self._nxm_plans.items() if k[0] != channel}
             return
@@ -97,9 +107,10 @@ class OFBaseBatch:
             template = np.asarray(template, dtype=np.float64)
             if template.ndim != 3 or template.shape[0] != len(channel.split('|')):
                 raise ValueError(f'ERROR: template of "{channel}" must be [n_chan, n_templ, N]')
-            if integralnorm:
-                raise NotImplementedError('integralnorm for joint channels is not built')
             self._check_n(template.shape[-1])
+            if integralnorm:
+                # s /= s[0] with s = fft(template) / N / df: s[0] = sum(template) / fs, a scale of the time-domain template
+                template = template / (template.sum(axis=-1, keepdims=True) / self._fs)
             tags = self._nxm_templates.setdefault(channel, {})
             if template_tag in tags and not overwrite:
                 raise ValueError(f'ERROR: template "{template_tag}" already exists (use overwrite=True)')

@@ -87,6 +87,14 @@ inline Setup make_setup(int N, double fs, int n, int m, const double* templates,
             continue;
         }
         for (int ab = 0; ab < n * n; ++ab) mat[ab] = cplx(csd[((size_t)ab * N + k) * 2], csd[((size_t)ab * N + k) * 2 + 1]);
+        // a bin whose csd diagonal is not finite carries no weight (ignored_frequency_peaks of OFBase.set_csd,
+        // reference processing_data.py:321-326: the host marks the peak bins with inf)
+        bool ignored = false;
+        for (int a = 0; a < n; ++a) ignored = ignored || !std::isfinite(mat[(size_t)a * n + a].real());
+        if (ignored) {
+            for (int ab = 0; ab < n * n; ++ab) s.isig[ab][k] = cplx(0, 0);
+            continue;
+        }
         if (!invert(mat, n)) throw std::invalid_argument("csd is singular at bin " + std::to_string(k));
         for (int ab = 0; ab < n * n; ++ab) s.isig[ab][k] = mat[ab];
     }

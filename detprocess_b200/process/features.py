@@ -90,6 +90,48 @@ def gather_frames(df):
     return out[columns]
 
 
+def standard_admin(admin, nb, group_name=None):
+    """The reference's fixed admin column set and dtypes (``ProcessingData.get_event_admin``,
+    detprocess/process/processing_data.py:811-887) from whatever per-event columns a reader supplies.  Reader names as
+    pytesio reports them (event_num, series_num, dump_num, event_index, event_id, event_time, run_type, data_mode,
+    trigger_type, trigger_amplitude, trigger_time, fridge_run, fridge_run_start, series_start, group_start) and their
+    already-renamed forms are both accepted.  What the reader does not know is derived the way the DAQ defines it
+    (event_number = dump_number * 100000 + event_index) or left as NaN like the reference does; columns the reference
+    has no name for pass through unchanged after the standard ones."""
+    alias = {'event_num': 'event_number', 'series_num': 'series_number', 'dump_num': 'dump_number',
+             'fridge_run': 'fridge_run_number', 'fridge_run_start': 'fridge_run_start_time',
+             'series_start': 'series_start_time', 'group_start': 'group_start_time'}
+    src = {alias.get(k, k): np.asarray(v) for k, v in admin.items()}
+    out = {}
+    ev = src['event_number'].astype(np.int64) if 'event_number' in src else np.arange(nb, dtype=np.int64)
+    out['event_number'] = ev
+    out['event_index'] = (src['event_index'] if 'event_index' in src else ev % 100000).astype(np.int32)
+    out['dump_number'] = (src['dump_number'] if 'dump_number' in src else ev // 100000).astype(np.int16)
+    out['series_number'] = (src['series_number'] if 'series_number' in src else np.zeros(nb)).astype(np.int64)
+    out['event_id'] = (src['event_id'] if 'event_id' in src else out['event_index']).astype(np.int32)
+    out['event_time'] = (src['event_time'] if 'event_time' in src else np.zeros(nb)).astype(np.int64)
+    run_type = src['run_type'].astype(str) if 'run_type' in src else np.full(nb, 'nan')
+    out['run_type'] = run_type
+    out['data_type'] = run_type.copy()            # the reference fills data_type from run_type (:819)
+    out['group_name'] = np.full(nb, group_name if group_name is not None else np.nan, dtype=object if group_name is not None else float)
+    if 'trigger_type' in src:
+        out['trigger_type'] = src['trigger_type'].astype(np.int16)
+    elif 'data_mode' in src:
+        modes = ['cont', 'trig-ext', 'rand', 'threshold']
+        out['trigger_type'] = np.array([modes.index(m) + 1 if m in modes else np.nan for m in src['data_mode'].astype(str)])
+    else:
+        out['trigger_type'] = np.full(nb, np.nan)
+    for k in ('trigger_amplitude', 'trigger_time'):
+        out[k] = src[k].astype(np.float64) if k in src else np.full(nb, np.nan)
+    for k in ('fridge_run_number', 'fridge_run_start_time', 'series_start_time', 'group_start_time'):
+        out[k] = src[k].astype(np.int64) if k in src else np.full(nb, np.nan)
+    known = set(out) | {'data_mode'}
+    for k, v in src.items():
+        if k not in known:
+            out[k] = v
+    return out
+
+
 def _public_algorithms(cls):
     return [m for m in dir(cls) if not m.startswith('_')]
 
@@ -436,9 +478,19 @@ class FeatureProcessing:
                 raise NotImplementedError('combined channels / external extractors in trigger-dataframe mode are not built')
         else:
             nb, _, n = batch.shape
-            cols = {k: np.asarray(v) for k, v in self._reader.admin(ev0, ev1).items()}
+            cols = {}
         if self._processing_id is not None:
             cols['processing_id'] = np.full(nb, self._processing_id)
+        if not window_mode:
+            # admin columns (reference get_event_admin :811-887) and detector settings (get_channel_settings :891-937)
+            cols.update(standard_admin(self._reader.admin(ev0, ev1), nb, group_name=self._reader.metadata.get('group_name')))
+            det = self._reader.metadata.get('detector_config')
+            if det:
+                for channel in self._processing_config:
+                    for c in utils.split_channel_name(channel, available_channels=self._channels)[0]:
+                        if c in det:
+                            cols[f'tes_bias_{c}'] = np.full(nb, det[c].get('tes_bias', np.nan))
+                            cols[f'output_gain_{c}'] = np.full(nb, det[c].get('output_gain', np.nan))
 
         # ---- combined channels 'a+b' / 'a-b': one channel-algebra launch straight from the reader's buffer ---------
         comb = None

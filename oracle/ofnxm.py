@@ -44,7 +44,7 @@ from .of1x1 import _fft_norm, of_window_bounds
 __all__ = ['ofnxm_setup', 'ofnxm_batch']
 
 
-def ofnxm_setup(templates, csd, fs, pretrigger_samples, coupling='AC'):
+def ofnxm_setup(templates, csd, fs, pretrigger_samples, coupling='AC', integralnorm=False):
     """templates [n, m, N] float64, csd [n, n, N] complex (two-sided, fftfreq order)."""
     templates = np.asarray(templates, dtype=np.float64)
     csd = np.asarray(csd, dtype=np.complex128)
@@ -52,7 +52,13 @@ def ofnxm_setup(templates, csd, fs, pretrigger_samples, coupling='AC'):
     assert csd.shape == (n, n, N)
     df = fs / N
     S = _fft_norm(templates, fs)                                   # [n, m, N]
-    iS = np.linalg.inv(np.transpose(csd, (2, 0, 1)))               # [N, n, n]
+    if integralnorm:
+        S = S / S[:, :, :1]
+    # bins with a non-finite csd diagonal (ignored_frequency_peaks of OFBase.set_csd) carry no weight
+    ignored = ~np.all(np.isfinite(np.real(csd[np.arange(n), np.arange(n), :])), axis=0)
+    safe = np.where(ignored[None, None, :], np.eye(n)[:, :, None], csd)
+    iS = np.linalg.inv(np.transpose(safe, (2, 0, 1)))              # [N, n, n]
+    iS[ignored] = 0.0
     if coupling == 'AC':
         iS[0] = 0.0
     Phi = np.einsum('bik,kba->iak', np.conj(S), iS)                # [m, n, N]

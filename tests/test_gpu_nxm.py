@@ -185,3 +185,36 @@ def test_estimated_csd_feeds_the_nxm_filter():
     sigma = np.sqrt(np.diag(Pinv))
     assert np.all(np.abs(out[:, 3:5] - amps) < 6 * sigma)
     assert np.mean(np.abs(out[:, 2] - pre - delays) <= 2) > 0.9
+
+
+def test_ofnxm_integralnorm_and_ignored_frequency_peaks():
+    """OFBase.add_template(..., integralnorm=True) and OFBase.set_csd(..., ignored_frequency_peaks=, ignore_harmonics=)
+    for joint channels (reference processing_data.py:321-326, 369-376) through OFBaseBatch == the oracle with the same
+    options"""
+    import torch
+    from detprocess_b200.core.ofbase import OFBaseBatch
+    S = SynthNxM(16384, 2, 2)
+    pre, fs, N = S.nb_pretrigger, S.fs, S.nb_samples
+    x = S.traces(60, np.random.default_rng(5))
+    peaks = [60.0e3]
+    ofb = OFBaseBatch(fs)
+    ofb.set_csd('a|b', S.csd, coupling='AC', ignored_frequency_peaks=peaks, ignore_harmonics=True)
+    ofb.add_template('a|b', S.templates, template_tag='t', pretrigger_samples=pre, integralnorm=True)
+    ofb.update_signal('a|b', torch.from_numpy(x).cuda())
+    r = ofb.nxm_results('a|b', 't', pre - 300, pre + 300)
+    f = np.abs(np.fft.fftfreq(N, 1 / fs))
+    csd = np.array(S.csd, dtype=np.complex128)
+    for fpk in np.arange(peaks[0], fs / 2, peaks[0]):
+        sel = np.abs(f - fpk) <= fs / N / 2
+        for a in range(2):
+            csd[a, a, sel] = np.inf
+    assert np.isinf(csd.real).sum() > 10
+    st = ofnxm_setup(S.templates, csd, fs, pre, integralnorm=True)
+    o = ofnxm_batch(x, st, (pre - 300, pre + 300, False))
+    assert np.array_equal(r['ind'], o['ind'])
+    assert np.allclose(r['chi0'], o['chi0'], rtol=1e-9) and np.allclose(r['chi2'], o['chi2'], rtol=1e-9)
+    assert np.max(np.abs(r['amps'] - o['amps'])) < 1e-9 * np.max(np.abs(o['amps']))
+    # and the options matter: without them the numbers differ
+    o_plain = ofnxm_batch(x, ofnxm_setup(S.templates, S.csd, fs, pre), (pre - 300, pre + 300, False))
+    assert np.max(np.abs(o_plain['chi0'] / o['chi0'] - 1)) > 1e-6
+    assert np.max(np.abs(o_plain['amps'] - o['amps'])) > 1e-6 * np.max(np.abs(o['amps']))

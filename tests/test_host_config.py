@@ -180,3 +180,24 @@ chanA:
     bad.write_text('trigger:\n    chanA:\n        fast:\n            threshold_sigma: 8\n')
     with pytest.raises(ValueError):
         YamlConfig(str(bad), ['chanA'], sample_rate=1.25e6, verbose=False)
+
+
+def test_admin_columns_follow_the_reference_set_and_dtypes():
+    """ProcessingData.get_event_admin (reference processing_data.py:811-887): fixed names and dtypes"""
+    from detprocess_b200.process.features import standard_admin
+    raw = {'event_num': [200003, 200004], 'series_num': [220230510153045] * 2, 'dump_num': [2, 2], 'event_index': [3, 4],
+           'event_id': [3, 4], 'event_time': [1_700_000_000, 1_700_000_001], 'run_type': [1, 1], 'data_mode': ['cont', 'rand'],
+           'fridge_run': [24, 24], 'series_start': [1_699_999_000] * 2, 'my_extra': [0.5, 1.5]}
+    a = standard_admin(raw, 2, group_name='grp')
+    names = ['event_number', 'event_index', 'dump_number', 'series_number', 'event_id', 'event_time', 'run_type', 'data_type',
+             'group_name', 'trigger_type', 'trigger_amplitude', 'trigger_time', 'fridge_run_number', 'fridge_run_start_time',
+             'series_start_time', 'group_start_time']
+    assert list(a)[:len(names)] == names and list(a)[-1] == 'my_extra'
+    assert a['event_number'].dtype == np.int64 and a['event_index'].dtype == np.int32 and a['dump_number'].dtype == np.int16
+    assert a['series_number'].dtype == np.int64 and a['event_id'].dtype == np.int32 and a['event_time'].dtype == np.int64
+    assert list(a['trigger_type']) == [1, 3] and np.isnan(a['trigger_amplitude']).all() and np.isnan(a['group_start_time']).all()
+    assert list(a['run_type']) == ['1', '1'] and list(a['data_type']) == ['1', '1'] and list(a['group_name']) == ['grp', 'grp']
+    assert a['fridge_run_number'].dtype == np.int64 and list(a['series_start_time']) == [1_699_999_000] * 2
+    # a reader that only numbers its events: the DAQ's numbering convention fills the rest
+    b = standard_admin({'event_number': np.array([300007])}, 1)
+    assert b['event_index'][0] == 7 and b['dump_number'][0] == 3 and np.isnan(b['group_name'][0]) and np.isnan(b['trigger_type'][0])

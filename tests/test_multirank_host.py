@@ -144,3 +144,50 @@ def test_two_rank_csd_allreduce_equals_single():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert np.allclose(csd, ref, rtol=1e-11, atol=1e-40)
+
+
+def _autocut_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from detprocess_b200.core.noise import global_autocut, sigma_clip_cut
+    rng = np.random.default_rng(77)
+    stats = rng.standard_normal((101, 3))
+    stats[::9] += 15.0                                 # outliers: pile-up / baseline jumps
+    lo, hi = shard_range(len(stats), rank, world)
+    mask = global_autocut(torch.from_numpy(stats[lo:hi]), sigma_clip_cut)
+    got = [None] * world
+    dist.all_gather_object(got, (lo, hi, mask))
+    if rank == 0:
+        full = np.zeros(len(stats), dtype=bool)
+        for a, b, m in got:
+            full[a:b] = m
+        q.put((full, sigma_clip_cut(stats)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_global_autocut_equals_single():
+    """the population-level noise cut (reference noise.py:331) on rank-sharded statistics: per-rank statistics ->
+    all_gather -> identical global mask on every rank; sharded == single process (SURVEY hard part 6)"""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_autocut_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full, ref = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(full, ref)
+    assert (~ref)[::9].all() and ref.sum() > 20          # every outlier is gone, a population survives
+    # a per-rank cut would NOT be the same thing: the two halves have different populations
+    from detprocess_b200.core.noise import sigma_clip_cut
+    rng = np.random.default_rng(77)
+    stats = rng.standard_normal((101, 3))
+    stats[::9] += 15.0
+    assert ref.shape == (101,) and sigma_clip_cut(stats[:50]).shape == (50,)
