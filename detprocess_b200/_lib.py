@@ -46,6 +46,8 @@ SIGNATURES = {
     'dp_of_plan_add_fit': (_i, [_vp, _i, _i, _i, _i, _i, _ip]),
     'dp_of_plan_add_fit_ex': (_i, [_vp, _i, _i, _i, _i, _i, _d, _ip]),
     'dp_of_plan_set_lowchi2_fcutoff': (_i, [_vp, _d]),
+    'dp_of_plan_set_neighbours': (_i, [_vp, _i]),
+    'dp_of_plan_neighbour_offset': (_i, [_vp, _i, _i, _ip]),
     'dp_of_plan_set_adc_conversion': (_i, [_vp, _i, _d, _d]),
     'dp_csd_plan_create': (_i, [C.POINTER(_vp), _i, _d, _i, _i, _i]),
     'dp_csd_plan_destroy': (None, [_vp]),

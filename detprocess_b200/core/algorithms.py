@@ -90,20 +90,20 @@ class FeatureExtractors:
     @staticmethod
     def _of_fit_spec(base_algorithm, channel, of_base, template_tag=None, lowchi2_fcutoff=10000,
                      window_min_from_trig_usec=None, window_max_from_trig_usec=None, window_min_index=None,
-                     window_max_index=None, lgc_outside_window=False, **kwargs):
-        """(template_tag, lo, hi, outside, lowchi2_fcutoff) of the delay search an of1x1_* block will request -- lets the
+                     window_max_index=None, lgc_outside_window=False, interpolate=False, **kwargs):
+        """(template_tag, lo, hi, outside, lowchi2_fcutoff, interpolate) of the delay search an of1x1_* block will request -- lets the
         pipeline register every fit before the first batch (underscore name: not an algorithm, reference
         process/features.py:1112-1116)"""
         if base_algorithm == 'of1x1_nodelay':
             pre = of_base.pretrigger_samples(channel, template_tag)
             return template_tag, pre, pre + 1, False, lowchi2_fcutoff
         if base_algorithm == 'of1x1_unconstrained':
-            return ('default' if template_tag is None else template_tag), None, None, False, lowchi2_fcutoff
+            return ('default' if template_tag is None else template_tag), None, None, False, lowchi2_fcutoff, bool(interpolate)
         if base_algorithm == 'of1x1_constrained':
             tag = 'default' if template_tag is None else template_tag
             lo, hi = _of_window(of_base, channel, tag, window_min_from_trig_usec, window_max_from_trig_usec,
                                 window_min_index, window_max_index)
-            return tag, lo, hi, bool(lgc_outside_window), lowchi2_fcutoff
+            return tag, lo, hi, bool(lgc_outside_window), lowchi2_fcutoff, bool(interpolate)
         return None
 
     @staticmethod
@@ -124,9 +124,8 @@ class FeatureExtractors:
         names = ('amp', 't0', 'chi2', 'lowchi2')
         if not of_base.is_signal_stored(channel):
             return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
-        if interpolate:
-            raise NotImplementedError('interpolate=True (parabolic t0 refinement) is not built')
-        r = of_base.results(of_base.request_fit(channel, template_tag, None, None, lowchi2_fcutoff=lowchi2_fcutoff))
+        r = of_base.results(of_base.request_fit(channel, template_tag, None, None, lowchi2_fcutoff=lowchi2_fcutoff,
+                                                interpolate=interpolate), interpolate=interpolate)
         return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
 
     @staticmethod
@@ -138,11 +137,10 @@ class FeatureExtractors:
         names = ('amp', 't0', 'chi2', 'lowchi2', 'chi2nopulse', 'ampres', 'timeres')
         if not of_base.is_signal_stored(channel):
             return {f'{k}_{feature_base_name}': _SENTINEL for k in names}
-        if interpolate:
-            raise NotImplementedError('interpolate=True (parabolic t0 refinement) is not built')
         lo, hi = _of_window(of_base, channel, template_tag, window_min_from_trig_usec,
                             window_max_from_trig_usec, window_min_index, window_max_index)
-        r = of_base.results(of_base.request_fit(channel, template_tag, lo, hi, lgc_outside_window, lowchi2_fcutoff=lowchi2_fcutoff))
+        r = of_base.results(of_base.request_fit(channel, template_tag, lo, hi, lgc_outside_window, lowchi2_fcutoff=lowchi2_fcutoff,
+                                                interpolate=interpolate), interpolate=interpolate)
         return _scalarize(of_base, {f'{k}_{feature_base_name}': r[k] for k in names})
 
     @staticmethod

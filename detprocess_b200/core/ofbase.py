@@ -29,6 +29,7 @@ class OFBaseBatch:
         self._templates = {}   # chan -> {tag: (template, pretrigger, integralnorm)}
         self._fits = {}        # (chan, tag, lo, hi, outside) -> None
         self._fcut = 10000.0
+        self._interpolate = False
         self._plan = None
         self._plan_key = None
         self._handles = {}
@@ -177,7 +178,10 @@ class OFBaseBatch:
         self._fcut = float(fcutoff)
 
     # ---- fits (one per YAML OF algorithm block) ---------------------------------
-    def request_fit(self, channel, template_tag, lo, hi, outside=False, lowchi2_fcutoff=None):
+    def request_fit(self, channel, template_tag, lo, hi, outside=False, lowchi2_fcutoff=None, interpolate=False):
+        if interpolate and not self._interpolate:
+            self._interpolate = True       # the plan must report the neighbour amplitudes: rebuild it once
+            self._plan = None
         fcut = self._fcut if lowchi2_fcutoff is None else float(lowchi2_fcutoff)
         key = (channel, template_tag, None if lo is None else int(lo), None if hi is None else int(hi), bool(outside), fcut)
         if key not in self._fits:
@@ -196,6 +200,8 @@ class OFBaseBatch:
             if not chans:
                 raise ValueError('ERROR: no channel has both a csd and a template')
             plan = OFPlan(self._nbins, self._fs, len(chans), self._precision)
+            if self._interpolate:
+                plan.set_neighbours(True)
             handles = {}
             for ci, chan in enumerate(chans):
                 psd, coupling = self._psd[chan]
@@ -289,7 +295,19 @@ class OFBaseBatch:
         x = cols[0] if len(cols) == 1 else torch.stack(cols, dim=1)
         self._out = self._plan.run(x.contiguous()).cpu().numpy()
 
-    def results(self, fit_key):
+    @staticmethod
+    def _parabola(v_prev, v_best, v_next, delta, t_interp=None):
+        """three-point parabola of QETpy's interpolate_t0 (same single-function convention as
+        oracle/of1x1.py::interpolate_parabola; QETpy is not in the reference tree: unpinned)"""
+        sf = 1.0 / (v_best * 100.0)
+        a = sf * (v_next - 2.0 * v_best + v_prev) / (2.0 * delta ** 2)
+        b = sf * (v_next - v_prev) / (2.0 * delta)
+        c = sf * v_best
+        if t_interp is None:
+            t_interp = -b / (2.0 * a)
+        return t_interp, (a * t_interp ** 2 + b * t_interp + c) / sf
+
+    def results(self, fit_key, interpolate=False):
         """dict of arrays for one fit: amp, ind, t0, chi2, lowchi2, timeres, chi2nopulse, ampres"""
         if fit_key not in self._fits:
             raise ValueError('ERROR: unknown fit (call request_fit first)')
@@ -305,6 +323,21 @@ class OFBaseBatch:
                'lowchi2': o[:, off + 3], 'timeres': o[:, off + 4],
                'chi2nopulse': o[:, self._plan.chi0_offset(ci)],
                'ampres': 1.0 / np.sqrt(self.norm(chan, tag))}
+        if interpolate:
+            # qp.OF1x1.calc(interpolate_t0=True): parabola through the chi2 at the best delay and its two neighbours ->
+            # refined time and chi2; the amplitude parabola is evaluated at that time (the kernel reports the two neighbour
+            # amplitudes, chi2 = chi0 - amp^2 norm); events whose best delay is the first / last sample stay as they are
+            no = self._plan.neighbour_offset(ci, fi)
+            norm = self.norm(chan, tag)
+            chi0 = res['chi2nopulse']
+            ap, an = o[:, no], o[:, no + 1]
+            inner = np.isfinite(ap) & np.isfinite(an)
+            with np.errstate(all='ignore'):
+                dt, c2 = self._parabola(chi0 - ap ** 2 * norm, res['chi2'], chi0 - an ** 2 * norm, 1.0 / self._fs)
+                _, a2 = self._parabola(ap, res['amp'], an, 1.0 / self._fs, t_interp=dt)
+            res['amp'] = np.where(inner, a2, res['amp'])
+            res['chi2'] = np.where(inner, c2, res['chi2'])
+            res['t0'] = np.where(inner, res['t0'] + dt, res['t0'])
         return res
 
     # ---- joint channels: NxM filter --------------------------------------------

@@ -145,6 +145,16 @@ class OFPlan:
         load (what H5Reader.read_single_event(adctoamp=True) does on the host, reference processing_data.py:674-684)."""
         check(lib.dp_of_plan_set_adc_conversion(self._h, int(chan), float(gain), float(offset)))
 
+    def set_neighbours(self, on=True):
+        """every fit also reports the amplitude one sample before / after its best delay (for ``interpolate_t0``)"""
+        check(lib.dp_of_plan_set_neighbours(self._h, int(bool(on))))
+        self.neighbours = bool(on)
+
+    def neighbour_offset(self, chan, fit):
+        o = C.c_int()
+        check(lib.dp_of_plan_neighbour_offset(self._h, int(chan), int(fit), C.byref(o)))
+        return o.value
+
     def finalize(self, device=None):
         torch = _torch()
         if not torch.cuda.is_available():

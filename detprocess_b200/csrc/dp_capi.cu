@@ -96,6 +96,7 @@ struct dp_of_plan {
     dpplan::Geometry geom;
     int v2_r1 = 0;  // != 0: the v2 kernels (dp_of2_kernel.cuh) serve this plan, M = v2_r1 * 4096
     int v2_multi = 0;  // some channel has more than one template
+    int neighbours = 0;    // every fit also reports the amplitude one sample before / after its best delay (interpolate_t0)
     bool generic = false;  // nb_samples is not a power of two: the mixed-radix kernel (dp_ofg_kernel.cuh) serves this plan
     const void *g_tw = nullptr, *g_wn = nullptr, *g_pos_k = nullptr, *g_pos_m = nullptr;
     std::vector<int> g_radix;
@@ -165,6 +166,7 @@ template <class T> int of_launch(dp_of_plan* p, const DpOfParams<T>& prm, int gr
 }
 
 template <class T> int of_finalize(dp_of_plan* p) {
+    if (p->neighbours) return fail(DP_ERR_UNSUPPORTED, "interpolate_t0 needs nb_samples 16384, 32768, 65536 or a non power of two");
     dpplan::DeviceTables<T> dt;
     try {
         dt = dpplan::build_tables<T>(p->geom, p->fs, p->chans, table_fcut(p), p->scale);
@@ -201,7 +203,7 @@ template <class T> int of_finalize(dp_of_plan* p) {
         dc.n_slots = (int)p->chans[c].fits.size();
         dc.out_base = base;
         p->chan_out_base[c] = base;
-        base += 1 + DP_SLOT_NOUT * dc.n_slots;
+        base += 1 + (DP_SLOT_NOUT + (p->neighbours ? 2 : 0)) * dc.n_slots;
         for (int i = 0; i < dc.n_templ; ++i) {
             auto& h = dt.chans[c].templ[i];
             const cx<T>* ph;
@@ -337,7 +339,7 @@ template <class T> int of2_finalize(dp_of_plan* p) {
         dc.n_slots = (int)p->chans[c].fits.size();
         dc.out_base = base;
         p->chan_out_base[c] = base;
-        base += 1 + DP_SLOT_NOUT * dc.n_slots;
+        base += 1 + (DP_SLOT_NOUT + (p->neighbours ? 2 : 0)) * dc.n_slots;
         max_templ = std::max(max_templ, dc.n_templ);
         for (int i = 0; i < dc.n_templ; ++i) {
             auto& h = dt.chans[c].templ[i];
@@ -437,6 +439,7 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     }
     prm.row_start = lay.row_start;
     prm.stream_len = lay.stream_len;
+    prm.neighbours = p->neighbours;
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
     const int prec = sizeof(S) == 8 ? 0 : 1;
@@ -492,7 +495,7 @@ template <class T> int ofg_finalize(dp_of_plan* p) {
         dc.n_slots = (int)p->chans[c].fits.size();
         dc.out_base = base;
         p->chan_out_base[c] = base;
-        base += 1 + DP_SLOT_NOUT * dc.n_slots;
+        base += 1 + (DP_SLOT_NOUT + (p->neighbours ? 2 : 0)) * dc.n_slots;
         for (int i = 0; i < dc.n_templ; ++i) {
             auto& h = dt.chans[c].templ[i];
             const cx<T>* ph;
@@ -553,6 +556,7 @@ int ofg_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     prm.nlow = p->nlow;
     prm.scale = p->scale;
     prm.subtract_first = p->subtract_first;
+    prm.neighbours = p->neighbours;
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
     const int rc = dp_ofg_launch(sizeof(T) == 8 ? 0 : 1, &prm, grid, p->smem, st);
@@ -780,6 +784,22 @@ int dp_of_plan_fit_offset(const dp_of_plan* p, int chan, int fit_index, int* off
     if (!p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
     if (fit_index < 0 || fit_index >= (int)p->chans[chan].fits.size()) return fail(DP_ERR_INVALID, "fit index out of range");
     *offset = p->chan_out_base[chan] + 1 + DP_SLOT_NOUT * fit_index;
+    return DP_OK;
+}
+int dp_of_plan_set_neighbours(dp_of_plan* p, int on) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->finalized) return fail(DP_ERR_STATE, "plan already finalized");
+    p->neighbours = on ? 1 : 0;
+    return DP_OK;
+}
+int dp_of_plan_neighbour_offset(const dp_of_plan* p, int chan, int fit_index, int* offset) {
+    int rc = of_check(p, chan);
+    if (rc) return rc;
+    if (!p->finalized) return fail(DP_ERR_STATE, "plan not finalized");
+    if (!p->neighbours) return fail(DP_ERR_STATE, "the plan does not report neighbour amplitudes (dp_of_plan_set_neighbours)");
+    const int nf = (int)p->chans[chan].fits.size();
+    if (fit_index < 0 || fit_index >= nf) return fail(DP_ERR_INVALID, "fit index out of range");
+    *offset = p->chan_out_base[chan] + 1 + DP_SLOT_NOUT * nf + 2 * fit_index;
     return DP_OK;
 }
 int dp_of_plan_get_phi(const dp_of_plan* p, int chan, int ti, double* out) {

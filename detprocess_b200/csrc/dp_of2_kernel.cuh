@@ -214,6 +214,7 @@ template <class T> struct Dp2Params {
     int nlow;
     double scale;
     int subtract_first;
+    int neighbours;  // also report the amplitude one sample before / after each fit's best delay (interpolate_t0)
     int skew_ns;  // start delay of every second block (DP2_SKEW_NS unless the plan overrides it)
     // window mode: event ev is the N-sample window that starts at sample row_start[ev] of every channel's continuous
     // stream (the step between the trigger and the features in the reference, processing_data.py:643-688); windows that
@@ -835,6 +836,39 @@ template <class T, int R1, int IN> struct Dp2Core {
         }
         return cols;
     }
+    // pass 1' of ONE column c (any thread): u[n1] = c'[n1*4096 + VL*c + lane]
+    static DP_DEV void inv_pass1_col(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int c, V (&u)[R1]) {
+        constexpr int LP = NPH - 1;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) u[G::k1_of(LP, b)] = buf[G::phys(c) + b * PB];
+#pragma unroll
+        for (int p = 0; p < LP; ++p)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) u[G::k1_of(p, b)] = dp2_ld_keep(scr + (long long)(p * NB + b) * VPB + c, dp2_policy_keep());
+        V w = dp_ldg(tw1 + c);
+        w.im = -w.im;
+        V pw[R1];
+        dp2_powers<R1, T>(w, pw);
+#pragma unroll
+        for (int k = 1; k < R1; ++k) u[k] = cmul(u[k], pw[k]);
+        dp_dft<R1, +1, T>::run(u);
+    }
+    // amplitude sample with rolled index r from the pass-1' outputs of its column
+    static DP_DEV S sample_of(const V (&u)[R1], int r) {
+        const int n = r >> 1, n1 = n / 4096;
+        S v = (S)0;
+#pragma unroll
+        for (int q = 0; q < R1; ++q)
+            if (q == n1) {
+                if constexpr (VL == 1) {
+                    v = (r & 1) ? u[q].im : u[q].re;
+                } else {
+                    const bool hi = (n & 1) != 0;
+                    v = (r & 1) ? (hi ? u[q].im.y : u[q].im.x) : (hi ? u[q].re.y : u[q].re.x);
+                }
+            }
+        return v;
+    }
     static DP_DEV unsigned inv_pass1(const V* buf, const V* scr, const V* DP_RESTRICT tw1, int i0, V (&y)[G::GC * R1], int nlo = 0,
                                      int nhi = 0x7fffffff) {
         return inv_pass1m(buf, scr, tw1, i0, y, (need_cols(nlo, nhi) >> i0) & ((1u << G::GC) - 1u));
@@ -947,7 +981,7 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
     static_assert(sizeof(T) == 8 && sizeof(V) == 16, "table rows are 256 / 512 bytes per warp");
     static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (DP_NLOW_MAX + SP_ELEMS) +
                                          2 * (sizeof(double) * RED_DOUBLES + sizeof(DpBest<S>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS) +
-                                         2 * sizeof(int) * CH_WORDS + 64 + (size_t)NW * NSP * DP2_PIECE + sizeof(Dp2Mbar) * NW + 16;
+                                         2 * sizeof(int) * CH_WORDS + 64 + sizeof(double) * 4 * DP_MAX_TSLOTS + (size_t)NW * NSP * DP2_PIECE + sizeof(Dp2Mbar) * NW + 16;
     // scratch per CTA (V units): X spill [NW][16][32] (multi-template; warp-sliced so that a warp's column is one
     // contiguous 8 KB block) + per template the parked block results of the non-final phases [(NPH-1)*NB][VPB]
     static constexpr long long SCR_X = (long long)16 * NT;
@@ -965,11 +999,13 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         int* slot0;
         int* chs0;  // [2][CH_WORDS] this event's channel descriptor (table pointers are read from
                     // shared memory, not through a dependent global load)
+        double* neigh0;        // [2][2 * DP_MAX_TSLOTS] amplitudes next to each fit's best delay (interpolate_t0)
         unsigned char* spare;  // [NW][NSP][2048] private landing pieces
         Dp2Mbar* mbar;         // [NW]
         DP_DEV double* red(int par) const { return red0 + par * RED_DOUBLES; }
         DP_DEV DpBest<S>* best(int par) const { return best0 + par * BEST_ELEMS; }
         DP_DEV int* slot_id(int par) const { return slot0 + par * DP_MAX_TSLOTS; }
+        DP_DEV double* neigh(int par) const { return neigh0 + par * 2 * DP_MAX_TSLOTS; }
     };
     static DP_DEV Smem carve(unsigned char* raw) {
         Smem s;
@@ -982,6 +1018,8 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
         s.chs0 = s.slot0 + 2 * DP_MAX_TSLOTS + ((2 * DP_MAX_TSLOTS) & 3 ? 4 - ((2 * DP_MAX_TSLOTS) & 3) : 0);
         unsigned char* e = reinterpret_cast<unsigned char*>(s.chs0 + 2 * CH_WORDS);
         e += (16 - (reinterpret_cast<unsigned long long>(e) & 15)) & 15;
+        s.neigh0 = reinterpret_cast<double*>(e);
+        e += sizeof(double) * 4 * DP_MAX_TSLOTS;
         s.spare = e;
         s.mbar = reinterpret_cast<Dp2Mbar*>(e + (size_t)NW * NSP * DP2_PIECE);
         return s;
@@ -1288,7 +1326,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
         long long first;
         if (!first_sample(prm, ev, chan, first)) {  // CTA-uniform: the window leaves the stream
             const Dp2ChanDev<T>* chg = prm.chans + chan;
-            const int nb = 1 + DP_SLOT_NOUT * chg->n_slots;
+            const int nb = 1 + (DP_SLOT_NOUT + (prm.neighbours ? 2 : 0)) * chg->n_slots;
             for (int o = tid; o < nb; o += NT) prm.out[(long long)ev * prm.n_out + chg->out_base + o] = -999999.0;
             continue;
         }
@@ -1470,6 +1508,10 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         nhi = b > nhi ? b : nhi;
                     }
                 }
+                if (prm.neighbours && nhi >= nlo && nhi - nlo < 4095) {   // the samples next to a window edge must exist as well
+                    nlo = nlo > 0 ? nlo - 1 : 0;
+                    nhi = nhi < G::M - 1 ? nhi + 1 : G::M - 1;
+                }
                 const unsigned rowmask = Core::rows_of(nlo, nhi);
                 const bool few_rows = __popc(rowmask) <= 2;  // narrow delay window(s): Horner evaluation of the rows it touches
                 dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 2' reads columns across the set's chunks
@@ -1530,6 +1572,33 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         }
                     }
                     __syncthreads();  // winners + the lowchi2 stash are visible; pass-1' reads of buf are done
+                    if (prm.neighbours) {
+                        // amplitude one sample before / after each fit's best delay: the thread that owns the sample's column
+                        // runs pass 1' for it once more (the pass-2' rows are still in the buffer) and leaves the value where
+                        // thread 0 forms the outputs
+#pragma unroll
+                        for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                            if (q >= nts) continue;
+                            DpBest<S> bb = best[q * 32];
+                            for (int w = 1; w < NW; ++w) dp_best_merge(bb, best[q * 32 + w]);
+#pragma unroll
+                            for (int side = 0; side < 2; ++side) {
+                                const int r = bb.idx + (side ? 1 : -1);
+                                const bool ok = bb.idx >= 0 && r >= 0 && r < N;
+                                const int c = ok ? (((r >> 1) & 4095) / VL) : 0;
+                                if (tid == (c % NT)) {
+                                    double v = NAN;
+                                    if (ok) {
+                                        V u[R1];
+                                        Core::inv_pass1_col(sm.buf, park, prm.tw1, c, u);
+                                        v = (double)Core::sample_of(u, r);
+                                    }
+                                    sm.neigh(par)[2 * q + side] = v;
+                                }
+                            }
+                        }
+                        if (more) __syncthreads();  // these reads of the buffer precede the next template's bulk copies into it
+                    }
                     // the FFT buffer is free: the next template's X column and filter rows land while the outputs are formed
                     if (STAGE && more && lane == 0)
                         issue_b(bar, bufb, prm.zones[p * NW + warp], spw, scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
@@ -1599,6 +1668,11 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                             os[2] = chi0 - amp * amp * tp.norm;
                             os[3] = low;
                             os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
+                            if (prm.neighbours) {
+                                double* on = o + 1 + DP_SLOT_NOUT * ch.n_slots + 2 * sm.slot_id(par)[q];
+                                on[0] = sm.neigh(par)[2 * q];
+                                on[1] = sm.neigh(par)[2 * q + 1];
+                            }
                         }
                     }
                     par ^= 1;

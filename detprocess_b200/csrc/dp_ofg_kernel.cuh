@@ -55,6 +55,7 @@ template <class T> struct DpGenParams {
     int n_out, nlow;
     double scale;
     int subtract_first;
+    int neighbours;          // also report the amplitude one sample before / after each fit's best delay
 };
 
 // ---- small DFTs.  SIGN = -1 forward, +1 inverse.
@@ -188,7 +189,7 @@ template <class T> struct DpGenKernel {
             if (prm.row_start != nullptr) {
                 base = prm.row_start[ev];
                 if (base < 0 || base + N > prm.stream_len) {  // CTA-uniform: the window leaves the stream
-                    const int nb = 1 + DP_SLOT_NOUT * ch.n_slots;
+                    const int nb = 1 + (DP_SLOT_NOUT + (prm.neighbours ? 2 : 0)) * ch.n_slots;
                     for (int o = tid; o < nb; o += NT) prm.out[(long long)ev * prm.n_out + ch.out_base + o] = -999999.0;
                     continue;
                 }
@@ -334,6 +335,12 @@ template <class T> struct DpGenKernel {
                         os[2] = chi0 - amp * amp * tp.norm;
                         os[3] = low;
                         os[4] = 1.0 / sqrt(amp * amp * tp.tsum);
+                        if (prm.neighbours) {   // the whole amplitude series is still in shared memory
+                            double* on = o + 1 + DP_SLOT_NOUT * ch.n_slots + 2 * slot_of[q];
+                            const int r0 = b.idx - 1, r1 = b.idx + 1;
+                            on[0] = (b.idx < 0 || r0 < 0) ? (double)NAN : (double)((r0 & 1) ? buf[r0 >> 1].im : buf[r0 >> 1].re);
+                            on[1] = (b.idx < 0 || r1 >= N) ? (double)NAN : (double)((r1 & 1) ? buf[r1 >> 1].im : buf[r1 >> 1].re);
+                        }
                     }
                 }
                 __syncthreads();  // red / best / buf are reused by the next template / event

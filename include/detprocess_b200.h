@@ -95,6 +95,13 @@ int dp_of_plan_set_lowchi2_fcutoff(dp_of_plan* plan, double fcutoff_hz);
  * quarter of the bytes cross PCIe.  Default gain 1, offset 0.  Before finalize. */
 int dp_of_plan_set_adc_conversion(dp_of_plan* plan, int chan, double gain, double offset);
 
+/* interpolate_t0 of qp.OF1x1.calc (parabolic refinement of the best delay, detprocess/core/algorithms.py:415, 543): with
+ * on != 0 every fit also reports the amplitude ONE SAMPLE BEFORE and AFTER its best delay (NaN at the ends of the trace),
+ * two doubles per fit behind the channel's regular block, at dp_of_plan_neighbour_offset; the three-point parabola itself
+ * is host arithmetic.  nb_samples 16384 / 32768 / 65536 or a non power of two.  Before finalize. */
+int dp_of_plan_set_neighbours(dp_of_plan* plan, int on);
+int dp_of_plan_neighbour_offset(const dp_of_plan* plan, int chan, int fit_index, int* offset);
+
 /* builds the device tables on `device`; the plan is immutable afterwards */
 int dp_of_plan_finalize(dp_of_plan* plan, int device);
 

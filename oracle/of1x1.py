@@ -46,7 +46,7 @@ includes ``window_max_index``).
 
 import numpy as np
 
-__all__ = ['OFBaseOracle', 'OF1x1Oracle', 'of1x1_batch', 'OF_WINDOW_MAX_INCLUSIVE']
+__all__ = ['OFBaseOracle', 'OF1x1Oracle', 'of1x1_batch', 'OF_WINDOW_MAX_INCLUSIVE', 'interpolate_parabola']
 
 # Whether the delay-search window [window_min_index, window_max_index] includes its
 # upper end.  QETpy builds the candidate set with a python slice (end exclusive),
@@ -54,6 +54,21 @@ __all__ = ['OFBaseOracle', 'OF1x1Oracle', 'of1x1_batch', 'OF_WINDOW_MAX_INCLUSIV
 OF_WINDOW_MAX_INCLUSIVE = False
 
 SENTINEL = -999999.0
+
+
+def interpolate_parabola(v_prev, v_best, v_next, delta, t_interp=None):
+    """The three-point parabola of QETpy's ``interpolate_t0`` option (``_interpolate_parabola`` of the optimum-filter
+    classes, as recalled -- QETpy is not in the reference tree: PARITY UNPINNED, the whole convention lives in this one
+    function): values at the best delay and one sample before / after it, spacing ``delta``; returns the vertex time
+    relative to the best sample and the parabola's value there (or at a given ``t_interp``).  ``calc`` applies it to the
+    chi2 series first (-> t_interp, chi2) and then evaluates the amplitude parabola at that same t_interp."""
+    sf = 1.0 / (v_best * 100.0)                    # scale factor QETpy applies "for precision purposes"
+    a = sf * (v_next - 2.0 * v_best + v_prev) / (2.0 * delta ** 2)
+    b = sf * (v_next - v_prev) / (2.0 * delta)
+    c = sf * v_best
+    if t_interp is None:
+        t_interp = -b / (2.0 * a)
+    return t_interp, (a * t_interp ** 2 + b * t_interp + c) / sf
 
 
 def _fft_norm(x, fs):
@@ -271,9 +286,6 @@ class OF1x1Oracle:
              lowchi2_fcutoff=10000, interpolate_t0=False,
              lgc_outside_window=False, pulse_direction_constraint=0,
              lgc_fit_withdelay=True, lgc_fit_nodelay=True, lgc_plot=False, **kwargs):
-        if interpolate_t0:
-            raise NotImplementedError('interpolate_t0 not restated (default False on '
-                                      'every in-scope call site)')
         ofb, ch, tag = self._of_base, self._channel, self._tag
         amps, chi2, pre = self._arrays()
         n = amps.shape[-1]
@@ -308,6 +320,10 @@ class OF1x1Oracle:
             ind = int(np.argmin(masked))
             a, c = float(amps[ind]), float(chi2[ind])
             t0 = (ind - pre) / fs
+            if interpolate_t0 and 0 < ind < n - 1:
+                dt, c = interpolate_parabola(float(chi2[ind - 1]), c, float(chi2[ind + 1]), 1.0 / fs)
+                _, a = interpolate_parabola(float(amps[ind - 1]), a, float(amps[ind + 1]), 1.0 / fs, t_interp=dt)
+                t0 = t0 + dt
             self._withdelay = (a, t0, c, self.get_chisq_lowfreq(a, t0, lowchi2_fcutoff))
 
     def get_result_nodelay(self):
@@ -348,7 +364,7 @@ def of_window_bounds(n, wmin, wmax):
 
 
 def of1x1_batch(traces, template, psd, fs, pretrigger_samples, windows=(),
-                coupling='AC', integralnorm=False, lowchi2_fcutoff=10000):
+                coupling='AC', integralnorm=False, lowchi2_fcutoff=10000, interpolate=False):
     """
     Vectorised float64 evaluation of the same maths for a [B, N] batch -- used by
     the parity tests so that thousands of events finish in seconds.
@@ -406,10 +422,20 @@ def of1x1_batch(traces, template, psd, fs, pretrigger_samples, windows=(),
         ind = np.argmin(np.where(mask[None, :], chi2, np.inf), axis=-1)
         a = amps[rows, ind]
         t0 = (ind - pre) / fs
+        c2 = chi2[rows, ind]
+        if interpolate:
+            inner = (ind > 0) & (ind < n - 1)
+            im, ip = np.clip(ind - 1, 0, n - 1), np.clip(ind + 1, 0, n - 1)
+            with np.errstate(all='ignore'):
+                dt, ci = interpolate_parabola(chi2[rows, im], c2, chi2[rows, ip], 1.0 / fs)
+                _, ai = interpolate_parabola(amps[rows, im], a, amps[rows, ip], 1.0 / fs, t_interp=dt)
+            a = np.where(inner, ai, a)
+            c2 = np.where(inner, ci, c2)
+            t0 = np.where(inner, t0 + dt, t0)
         out['ind'][iw] = ind
         out['amp'][iw] = a
         out['t0'][iw] = t0
-        out['chi2'][iw] = chi2[rows, ind]
+        out['chi2'][iw] = c2
         out['lowchi2'][iw] = lowchi2(a, t0)
         with np.errstate(divide='ignore'):
             out['timeres'][iw] = 1.0 / np.sqrt(a ** 2 * tsum)

@@ -379,3 +379,50 @@ chan1:
     assert np.allclose(df['amp_of1x1_nodelay_chan1'], o['amp'][1], rtol=1e-9, atol=1e-9 * o['ampres'])
     assert np.array_equal(df['baseline_chan1'].values, R.baseline_batch(traces, 0, pre - 1250))
     assert np.array_equal(df['integral_chan1'].values, R.integral_batch(traces, fs, pre - 625, pre + 625))
+
+
+@pytest.mark.parametrize('nb_samples,precision', [(32768, 'f64'), (16384, 'f64'), (65536, 'f64'), (32768, 'f32'), (25000, 'f64')])
+def test_interpolate_t0_parabola(nb_samples, precision):
+    """interpolate / interpolate_t0 (reference algorithms.py:415, 543 -> qp.OF1x1.calc(interpolate_t0=True)): the kernel
+    reports the amplitudes one sample before / after the best delay, the parabola (oracle.interpolate_parabola convention)
+    refines amp, t0 and chi2.  Sub-sample delays are recovered better than the sample grid allows."""
+    from detprocess_b200.core.ofbase import OFBaseBatch
+    from detprocess_b200.core.algorithms import FeatureExtractors as FE
+    from detprocess_b200.synth import make_template
+    S = SynthSetup(nb_samples)
+    pre, fs = S.nb_pretrigger, S.fs
+    rng = np.random.default_rng(21)
+    traces = make_traces(48, S.template, S.psd, fs, rng, amp_max=2e-7, max_delay=200)
+    # a noiseless pulse delayed by a fraction of a sample: only the interpolated fit can see the fraction
+    frac = 0.37
+    t = (np.arange(nb_samples) - pre - frac) / fs
+    tp = np.where(t > 0, t, 0.0)
+    shifted = np.where(t > 0, np.exp(-tp / 200e-6) - np.exp(-tp / 20e-6), 0.0)
+    traces[0] = 1.5e-7 * shifted / shifted.max()
+    ofb = OFBaseBatch(fs, precision=precision)
+    ofb.set_csd('c', S.psd)
+    ofb.add_template('c', S.template, template_tag='default', pretrigger_samples=pre)
+    ofb.update_signal('c', torch.from_numpy(traces).cuda())
+    got_c = FE.of1x1_constrained('c', ofb, template_tag='default', window_min_from_trig_usec=-400, window_max_from_trig_usec=400,
+                                 interpolate=True, feature_base_name='con')
+    got_u = FE.of1x1_unconstrained('c', ofb, template_tag='default', interpolate=True, feature_base_name='unc')
+    plain = FE.of1x1_constrained('c', ofb, template_tag='default', window_min_from_trig_usec=-400, window_max_from_trig_usec=400,
+                                 feature_base_name='con')
+    oc = of1x1_batch(traces, S.template, S.psd, fs, pre, windows=[(pre - 500, pre + 500, False)], interpolate=True)
+    ou = of1x1_batch(traces, S.template, S.psd, fs, pre, windows=[(None, None, False)], interpolate=True)
+    tol = dict(f64=(1e-9, 1e-9, 1e-12), f32=(2e-5, 2e-4, 2e-9))[precision]
+    for got, o, name in ((got_c, oc, 'con'), (got_u, ou, 'unc')):
+        same = np.abs(got[f't0_{name}'] - o['t0'][0]) < 0.6 / fs       # fp32: a near-tie may sit on the neighbouring sample
+        assert same.mean() > (0.999 if precision == 'f64' else 0.95)
+        den = np.maximum(np.abs(o['amp'][0]), 5 * o['ampres'])
+        assert np.max((np.abs(got[f'amp_{name}'] - o['amp'][0]) / den)[same]) < tol[0]
+        # (the noiseless event's chi2 is ~1e-7 of chi0: compare on the scale the subtraction chi0 - amp^2 norm works on)
+        cden = np.maximum(np.abs(o['chi2'][0]), 1e-3 * o['chi0'])
+        assert np.max((np.abs(got[f'chi2_{name}'] - o['chi2'][0]) / cden)[same]) < tol[1]
+        big = same & (np.abs(o['amp'][0]) > 20 * o['ampres'])       # the vertex of a flat parabola is ill-conditioned
+        assert np.max(np.abs(got[f't0_{name}'] - o['t0'][0])[big]) < tol[2]
+    # sub-sample recovery on the noiseless event
+    assert abs(got_c['t0_con'][0] * fs - frac) < 0.05 and abs(plain['t0_con'][0] * fs - frac) > 0.3
+    # the plain fit of the same base is untouched by the interpolating one
+    op = of1x1_batch(traces, S.template, S.psd, fs, pre, windows=[(pre - 500, pre + 500, False)])
+    assert np.allclose(plain['t0_con'], op['t0'][0], atol=1e-15)

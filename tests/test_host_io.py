@@ -59,3 +59,15 @@ def test_feature_writer_dumps_by_memory_limit(tmp_path):
     back = pd.concat([pd.read_parquet(f) for f in files], ignore_index=True)
     assert back.equals(pd.concat(frames, ignore_index=True))
     assert FeatureWriter(str(tmp_path / 'empty')).close() == []
+
+
+def test_pytesio_reader_is_import_guarded():
+    """the HDF5-backed EventReader subclass exists and fails loudly where pytesio is absent"""
+    from detprocess_b200.io.h5 import PytesioReader
+    from detprocess_b200.io import EventReader
+    assert issubclass(PytesioReader, EventReader)
+    try:
+        import pytesio  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match='pytesio'):
+            PytesioReader(['whatever.hdf5'])
