@@ -35,7 +35,7 @@ def test_plan_argument_errors_without_gpu():
     import numpy as np
     from detprocess_b200.core.plans import OFPlan, ReducePlan
     with pytest.raises(NotImplementedError):
-        OFPlan(25000, 1.25e6)                     # non power-of-two trace length
+        OFPlan(25002, 1.25e6)                     # half does not factor into 2, 3, 4, 5
     with pytest.raises(ValueError):
         OFPlan(4096, 1.25e6, precision='f16')
     p = OFPlan(4096, 1.25e6)
