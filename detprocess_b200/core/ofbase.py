@@ -271,29 +271,40 @@ class OFBaseBatch:
     def calc_signal_filt_td(self, channel, template_tag=None):
         return None   # fused into the kernel (inverse FFT)
 
-    def _run(self):
+    def launch(self):
+        """Start the fused kernel for every requested fit of the stored batch and return the device result block
+        [B, n_out] (float64) WITHOUT waiting for it: the pipeline copies it to pinned host memory behind the kernel and
+        hands it back with ``set_results`` once the copy has completed (the next batch is launched in between)."""
         import torch
         self._ensure_plan()
         chans = self._plan_chans
         if self._batch is not None and all(c in self._batch_rows for c in chans):
-            out = self._plan.run_layout(self._batch, [self._batch_rows[c] for c in chans], self._batch_starts)
-            self._out = out.cpu().numpy()
-            return
+            return self._plan.run_layout(self._batch, [self._batch_rows[c] for c in chans], self._batch_starts)
         if self._batch is not None and self._batch_starts is None:
-            import torch as _t
             for c in chans:       # mixed case: a plain channel next to a combined (float64) one -> float64 amps
                 if c not in self._signals and c in self._batch_rows:
                     x = self._batch[:, self._batch_rows[c], :]
-                    if x.dtype == _t.int16 and c in self._adc:
-                        x = x.to(_t.float64) * self._adc[c][0] + self._adc[c][1]     # numpy's two roundings
-                    self._signals[c] = x.to(_t.float64)
+                    if x.dtype == torch.int16 and c in self._adc:
+                        x = x.to(torch.float64) * self._adc[c][0] + self._adc[c][1]     # numpy's two roundings
+                    self._signals[c] = x.to(torch.float64)
         missing = [c for c in chans if c not in self._signals]
         if missing:
             raise ValueError(f'ERROR: no signal stored for channel(s) {missing}')
         dev = self._plan.device
         cols = [self._signals[c].to(dev, non_blocking=True) for c in chans]
         x = cols[0] if len(cols) == 1 else torch.stack(cols, dim=1)
-        self._out = self._plan.run(x.contiguous()).cpu().numpy()
+        return self._plan.run(x.contiguous())
+
+    def set_results(self, out):
+        """host ndarray [B, n_out] of a ``launch()``: what the extractors index into"""
+        self._out = out
+
+    @property
+    def has_of1x1(self):
+        return bool(self._fits)
+
+    def _run(self):
+        self._out = self.launch().cpu().numpy()
 
     @staticmethod
     def _parabola(v_prev, v_best, v_next, delta, t_interp=None):

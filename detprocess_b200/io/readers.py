@@ -34,16 +34,15 @@ class EventReader:
         """events [i0, i1) as stored: torch tensor [B, n_chan, N] on the host (pinned when requested and possible)."""
         raise NotImplementedError
 
-    def upload(self, i0, i1, device, stream=None):
+    def upload(self, i0, i1, device, stream=None, out=None):
         """events [i0, i1) on ``device`` (asynchronous copy from pinned memory on ``stream`` / the current stream).
         This, not ``read_batch(...).to(device, non_blocking=True)``, is what the pipelines call: a reader that reuses
-        its host staging orders the next overwrite of a buffer after the copy that still reads it."""
+        its host staging orders the next overwrite of a buffer after the copy that still reads it.  ``out``: a device
+        tensor [>= B, n_chan, N] of the stored dtype to copy into (the pipeline's own staging: no allocator call per
+        batch); events that already live on the device are returned as they are."""
         import torch
         host = self.read_batch(i0, i1)
-        if stream is None:
-            return host.to(device, non_blocking=True)
-        with torch.cuda.stream(stream):
-            return host.to(device, non_blocking=True)
+        return _to_device(host, device, stream, out)
 
     def admin(self, i0, i1):
         """dict of per-event columns (event_number, series_number, trigger_index, ...) for events [i0, i1)"""
@@ -67,6 +66,19 @@ class EventReader:
         gain = torch.tensor(self.metadata.get('adc_gain', [1.0] * batch.shape[1]), dtype=torch.float64, device=batch.device)
         off = torch.tensor(self.metadata.get('adc_offset', [0.0] * batch.shape[1]), dtype=torch.float64, device=batch.device)
         return batch.to(torch.float64) * gain[None, :, None] + off[None, :, None]
+
+
+def _to_device(host, device, stream, out):
+    import torch
+    if host.is_cuda:
+        return host
+    st = torch.cuda.current_stream(device) if stream is None else stream
+    with torch.cuda.stream(st):
+        if out is not None and out.dtype == host.dtype and out.shape[0] >= host.shape[0] and out.shape[1:] == host.shape[1:]:
+            dst = out[:host.shape[0]]
+            dst.copy_(host, non_blocking=True)
+            return dst
+        return host.to(device, non_blocking=True)
 
 
 def _pin(t, pinned):
@@ -175,15 +187,14 @@ class RawBinaryReader(EventReader):
         out.numpy()[...] = self._mm[i0:i1]
         return out
 
-    def upload(self, i0, i1, device, stream=None):
+    def upload(self, i0, i1, device, stream=None, out=None):
         import torch
         host = self.read_batch(i0, i1)
         k = self._last
         st = torch.cuda.current_stream(device) if stream is None else stream
-        with torch.cuda.stream(st):
-            dev = host.to(device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(st)
+        dev = _to_device(host, device, st, out)
+        ev = torch.cuda.Event()
+        ev.record(st)
         self._copied[k] = ev
         return dev
 

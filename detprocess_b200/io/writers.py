@@ -20,20 +20,26 @@ class FeatureWriter:
         self._dump = 1
         self.files = []
 
-    def add(self, df):
-        """queue a batch of rows; dumps when the queued rows exceed the memory limit"""
-        if df is None or len(df) == 0:
+    def add(self, rows):
+        """queue a batch of rows (a DataFrame or a dict column name -> ndarray); dumps when the queued rows exceed the
+        memory limit"""
+        import numpy as np
+        if rows is None or len(rows) == 0:
             return
-        self._frames.append(df)
-        self._bytes += int(df.memory_usage(index=False, deep=True).sum())
+        if isinstance(rows, dict):
+            self._bytes += int(sum(np.asarray(v).nbytes for v in rows.values()))
+        else:
+            self._bytes += int(rows.memory_usage(index=False, deep=True).sum())
+            rows = {c: rows[c].to_numpy() for c in rows.columns}
+        self._frames.append(rows)
         if self._bytes >= self._limit:
             self.flush()
 
     def flush(self):
-        import pandas as pd
+        from ..utils.utils import columns_to_frame
         if not self._frames:
             return None
-        df = pd.concat(self._frames, ignore_index=True)
+        df = columns_to_frame(self._frames)
         name = os.path.join(self._dir, f'{self._prefix}_F{self._dump:04d}.parquet')
         df.to_parquet(name)
         self.files.append(name)

@@ -22,6 +22,7 @@ from ..core.algorithms import FeatureExtractors as FE
 from ..core.ofbase import OFBaseBatch
 from ..core.plans import ReducePlan
 from ..utils import utils
+from ..utils.utils import columns_to_frame
 from .config import YamlConfig
 
 __all__ = ['FeatureProcessing']
@@ -383,8 +384,12 @@ class FeatureProcessing:
         amps inside the kernels), sharded over ranks in contiguous blocks.  lgc_save: every rank writes its own dumps
         ``<prefix>_rank<r>_F000k.parquet`` when ``memory_limit`` (GB) of rows is queued (reference features.py:584-629:
         one file set per worker, no merge); lgc_output: the gathered table is returned.  With a trigger dataframe the
-        reader's events are continuous streams and the rows of the table are the events (see ``__init__``)."""
-        import pandas as pd
+        reader's events are continuous streams and the rows of the table are the events (see ``__init__``).
+
+        Three batches are in flight: while batch k's kernels run, batch k+1 crosses PCIe into the pipeline's own device
+        staging (three reused buffers: no allocator call per batch) and the host turns the results of batch k-1 -- copied
+        to pinned memory behind their kernels -- into table columns.  Columns stay numpy arrays until the table (or a
+        dump) is assembled: one DataFrame construction per table, not per batch."""
         import torch
         rank, world = dist_info()
         writer = None
@@ -392,14 +397,14 @@ class FeatureProcessing:
             from ..io.writers import FeatureWriter
             writer = FeatureWriter(save_path or '.', prefix=self._processing_id or 'feature',
                                    series_name=(f'rank{rank}' if world > 1 else None), memory_limit_gb=memory_limit)
-        frames = []
+        parts = []
         dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
 
-        def emit(df):
+        def emit(cols):
             if writer is not None:
-                writer.add(df)
+                writer.add(cols)
             if lgc_output:
-                frames.append(df)
+                parts.append(cols)
 
         if self._triggers is not None:
             self._process_triggers(nevents, dev, rank, world, emit)
@@ -408,32 +413,51 @@ class FeatureProcessing:
             nev_total = len(reader) if nevents is None or nevents < 0 else min(nevents, len(reader))
             lo, hi = shard_range(nev_total, rank, world)      # contiguous blocks, one process per GPU
             copy_stream = torch.cuda.Stream(dev)
+            main = torch.cuda.current_stream(dev)
+            meta = reader.metadata
+            shape = (min(batch_size, max(hi - lo, 1)), len(meta['channels']), int(meta['nb_samples']))
+            key = (shape, meta['dtype'], str(dev))
+            if getattr(self, '_stage_key', None) != key:
+                self._stage = [torch.empty(shape, dtype=getattr(torch, meta['dtype']), device=dev) for _ in range(3)]
+                self._stage_free = [None] * 3       # event on the compute stream after the last kernel that read the buffer
+                self._stage_key = key
+            slot = 0
 
             def fetch(b0):
-                # the next batch is uploaded on a side stream while the current one is processed
+                nonlocal slot
                 b1 = min(b0 + batch_size, hi)
-                t = reader.upload(b0, b1, dev, stream=copy_stream)   # the reader orders its staging reuse after this copy
+                k, slot = slot, (slot + 1) % 3
+                if self._stage_free[k] is not None:
+                    copy_stream.wait_event(self._stage_free[k])
+                t = reader.upload(b0, b1, dev, stream=copy_stream, out=self._stage[k])
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-                return t, ev, b0, b1
+                return t, ev, b0, b1, k
 
             nxt = fetch(lo) if lo < hi else None
+            pending = None
             while nxt is not None:
-                t, ev, b0, b1 = nxt
+                t, ev, b0, b1, k = nxt
                 nxt = fetch(b1) if b1 < hi else None
-                torch.cuda.current_stream(dev).wait_event(ev)
-                t.record_stream(torch.cuda.current_stream(dev))
-                emit(self._process_batch(t, b0, b1))
+                main.wait_event(ev)
+                ticket = self._launch_batch(t, b0, b1)
+                done = torch.cuda.Event()
+                done.record(main)
+                self._stage_free[k] = done
+                if pending is not None:
+                    emit(self._collect(pending))
+                pending = ticket
+            if pending is not None:
+                emit(self._collect(pending))
         self.output_files = writer.close() if writer is not None else []
         if not lgc_output:
             return None
-        df = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame()
+        df = columns_to_frame(parts)
         return gather_frames(df) if gather else df
 
     def _process_triggers(self, nevents, dev, rank, world, emit):
         """trigger-dataframe mode: rows are grouped by the continuous event they point into; each stream is uploaded once
         and all of its windows are processed by one launch per plan.  Streams (not rows) are sharded over the ranks."""
-        import pandas as pd
         import torch
         trig = self._triggers
         if nevents is not None and nevents >= 0:
@@ -447,38 +471,57 @@ class FeatureProcessing:
         if 'event_number' not in keys:
             raise ValueError('ERROR: trigger dataframe and reader need an "event_number" column to find the continuous event')
         index_of = {tuple(int(adm[k][i]) for k in keys): i for i in range(len(reader))}
-        stream_of_row = np.array([index_of.get(tuple(int(trig[k].iloc[i]) for k in keys), -1) for i in range(len(trig))])
+        trig_keys = np.stack([trig[k].to_numpy(dtype=np.int64) for k in keys], axis=1)
+        stream_of_row = np.array([index_of.get(tuple(r), -1) for r in trig_keys.tolist()], dtype=np.int64)
         if (stream_of_row < 0).any():
             raise ValueError('ERROR: trigger dataframe rows point to events the raw data does not hold')
         streams = np.unique(stream_of_row)
         lo, hi = shard_range(len(streams), rank, world)
+        tindex = trig['trigger_index'].to_numpy(dtype=np.int64)
         for si in streams[lo:hi]:
             rows = np.nonzero(stream_of_row == si)[0]
             batch = reader.upload(int(si), int(si) + 1, dev)[0]              # [n_chan, L] as stored
-            tidx = torch.from_numpy(trig['trigger_index'].to_numpy(dtype=np.int64)[rows]).to(dev)
-            df = self._process_batch(batch, None, None, trigger_index=tidx)
-            tab = trig.iloc[rows].reset_index(drop=True)                      # the trigger rows verbatim (:795-804)
-            for c in df.columns:
-                tab[c] = df[c].to_numpy()
-            emit(tab)
+            tidx = torch.from_numpy(tindex[rows]).to(dev)
+            cols = self._collect(self._launch_batch(batch, None, None, trigger_index=tidx))
+            tab = trig.iloc[rows]                                             # the trigger rows verbatim (:795-804)
+            out = {c: tab[c].to_numpy() for c in tab.columns}
+            out.update(cols)
+            emit(out)
 
     def _process_batch(self, batch, ev0, ev1, trigger_index=None):
-        """batch mode: ``batch`` [B, n_chan, N] events ev0..ev1 of the reader; window mode: ``batch`` [n_chan, L] one
+        """one batch, start to finish -> DataFrame (see ``_launch_batch`` for the arguments)"""
+        return columns_to_frame([self._collect(self._launch_batch(batch, ev0, ev1, trigger_index=trigger_index))])
+
+    def _result_staging(self, n_doubles):
+        """pinned host block for the results of one batch (three rotate: a block is reused two batches later, after its
+        columns were copied out by ``_collect``)"""
+        import torch
+        st = getattr(self, '_res_stage', None)
+        if st is None:
+            st = self._res_stage = {'bufs': [None] * 3, 'k': 0}
+        k = st['k']
+        st['k'] = (k + 1) % 3
+        buf = st['bufs'][k]
+        if buf is None or buf.numel() < n_doubles:
+            buf = st['bufs'][k] = torch.empty(max(n_doubles, 1), dtype=torch.float64).pin_memory()
+        return buf
+
+    def _launch_batch(self, batch, ev0, ev1, trigger_index=None):
+        """Queue everything batch-shaped on the device and return a ticket for ``_collect``.
+        batch mode: ``batch`` [B, n_chan, N] events ev0..ev1 of the reader; window mode: ``batch`` [n_chan, L] one
         continuous event and ``trigger_index`` int64 [B] (device)."""
-        import pandas as pd
         import torch
         dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
         batch = batch.to(dev, non_blocking=True)
         window_mode = trigger_index is not None
         rows = {c: i for i, c in enumerate(self._channels)}
+        cols = {}
         if window_mode:
             nb, n = int(trigger_index.shape[0]), None
-            cols = {}
             if self._combined or self._ext_jobs:
                 raise NotImplementedError('combined channels / external extractors in trigger-dataframe mode are not built')
         else:
             nb, _, n = batch.shape
-            cols = {}
         if self._processing_id is not None:
             cols['processing_id'] = np.full(nb, self._processing_id)
         if not window_mode:
@@ -507,7 +550,8 @@ class FeatureProcessing:
             return amps
 
         # ---- hand the batch to every OF base (reference update_signal_OF, :712-772): plain channels are read where the
-        # reader put them, combined ones from the channel-algebra output
+        # reader put them, combined ones from the channel-algebra output; the fused kernel of every base is queued
+        blocks = []          # (kind, object, device result block)
         for key, entry in self._of_bases.items():
             ofb = entry['OF']
             ofb.clear_signal()
@@ -525,9 +569,14 @@ class FeatureProcessing:
                     ofb.update_signal(chan, comb[:, self._combined.index(chan), :], calc_fft=True)
                 else:
                     ofb.update_signal(chan, self._channel_trace(float_batch(), chan), calc_fft=True)
-        for channel, extractor, entry, kw, feature_channel in self._of_jobs:
-            for name, val in extractor(channel, entry['OF'], **kw).items():
-                cols[f'{name}_{feature_channel}'] = val
+            if ofb.has_of1x1:
+                blocks.append(('of', ofb, ofb.launch()))
+        # joint-channel (NxM) fits run when their extractor asks (one launch per fit): evaluated now, while the signals
+        # of THIS batch are stored
+        eager = {}
+        for j, (channel, extractor, entry, kw, feature_channel) in enumerate(self._of_jobs):
+            if '|' in channel:
+                eager[j] = extractor(channel, entry['OF'], **kw)
 
         # ---- trace-window features: cached plans, inputs consumed in place --------------------------------------------
         for geom, plans in self._red_plans.items():
@@ -542,10 +591,20 @@ class FeatureProcessing:
                     out = plan.run_layout(batch, [rows[c] for c in d['chans']], starts)
                 else:
                     out = plan.run_layout(comb, [self._combined.index(c) for c in d['chans']])
-                out = out.cpu().numpy()
-                for h, name in zip(d['handles'], d['columns']):
-                    cols[name] = out[:, plan.column(h)]
+                blocks.append(('red', d, out))
+        # ---- all result blocks of the batch -> one pinned host block, behind the kernels
+        total = sum(int(b[2].numel()) for b in blocks)
+        host = self._result_staging(total)
+        views, o = [], 0
+        for _, _, t in blocks:
+            v = host[o:o + t.numel()].view(t.shape)
+            v.copy_(t, non_blocking=True)
+            views.append(v)
+            o += t.numel()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
         # user-supplied extractors keep the reference's per-event numpy calling convention
+        ext = {}
         for channel, extractor, kw, feature_channel, geom in self._ext_jobs:
             if channel in self._combined:
                 tr = comb[:, self._combined.index(channel), :].cpu().numpy()
@@ -553,5 +612,28 @@ class FeatureProcessing:
                 tr = self._channel_trace(float_batch(), channel).cpu().numpy()
             rows_out = [extractor(tr[i], **kw) for i in range(nb)]
             for name in rows_out[0]:
-                cols[f'{name}_{feature_channel}'] = np.array([r[name] for r in rows_out])
-        return pd.DataFrame(cols)
+                ext[f'{name}_{feature_channel}'] = np.array([r[name] for r in rows_out])
+        return {'cols': cols, 'blocks': blocks, 'views': views, 'ready': ready, 'eager': eager, 'ext': ext, 'keep': (batch, comb)}
+
+    def _collect(self, ticket):
+        """wait for the batch's results and turn them into table columns (dict name -> ndarray [B])"""
+        ticket['ready'].synchronize()
+        cols = ticket['cols']
+        reds = []
+        for (kind, obj, _), v in zip(ticket['blocks'], ticket['views']):
+            arr = v.numpy().copy()          # the pinned block is reused two batches later
+            if kind == 'of':
+                obj.set_results(arr)
+            else:
+                reds.append((obj, arr))
+        for j, (channel, extractor, entry, kw, feature_channel) in enumerate(self._of_jobs):
+            res = ticket['eager'][j] if j in ticket['eager'] else extractor(channel, entry['OF'], **kw)
+            for name, val in res.items():
+                cols[f'{name}_{feature_channel}'] = val
+        for d, arr in reds:
+            plan = d['plan']
+            for h, name in zip(d['handles'], d['columns']):
+                cols[name] = arr[:, plan.column(h)]
+        cols.update(ticket['ext'])
+        ticket['keep'] = None
+        return cols

@@ -3,6 +3,7 @@ Host-side helpers with the semantics of the reference's ``detprocess/utils/utils
 (channel-name algebra :70-184, window indices :189-301) and pytesio's
 ``convert_length_msec_to_samples`` (used by ``process/config.py:10``).
 """
+import numpy as np
 
 ALLOWED_SEPARATORS = [',', '|', '+', '-']
 
@@ -103,3 +104,18 @@ def get_window_indices(nb_samples, nb_pretrigger_samples, fs,
     if hi < lo:
         raise ValueError('ERROR window calculation: max index smaller than min!Check configuration!')
     return lo, hi
+
+
+def columns_to_frame(parts):
+    """ONE DataFrame from the per-batch column dicts (name -> ndarray [B] or scalar)"""
+    import pandas as pd
+    parts = [p for p in parts if p]
+    if not parts:
+        return pd.DataFrame()
+    names = list(parts[0].keys())
+    sizes = [next((len(v) for v in p.values() if isinstance(v, np.ndarray) and v.ndim), 1) for p in parts]
+    out = {}
+    for c in names:
+        vals = [np.asarray(p[c]) if np.ndim(p[c]) else np.full(nb, p[c]) for p, nb in zip(parts, sizes)]
+        out[c] = vals[0] if len(vals) == 1 else np.concatenate(vals)
+    return pd.DataFrame(out)
