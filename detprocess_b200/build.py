@@ -91,9 +91,15 @@ def build(force=False, verbose=True):
     obj_dir = os.path.join(OUT_DIR, 'obj' + ('_' + os.path.basename(LIB) if EXTRA_DEFS else ''))
     os.makedirs(obj_dir, exist_ok=True)
 
+    only = os.environ.get('DP_BUILD_UNITS', '').split()
+    main_obj_dir = os.path.join(OUT_DIR, 'obj')
+
     def compile_unit(unit):
         name, src, defs = unit
         obj = os.path.join(obj_dir, name + '.o')
+        if EXTRA_DEFS and only and not any(o in name for o in only):
+            # development A/B build: units the experiment does not touch come from the main build
+            return name, os.path.join(main_obj_dir, name + '.o'), '# reused from the main build', 0, ''
         cmd = [nvcc] + NVCC_FLAGS + EXTRA_DEFS + defs + ['-c', '-o', obj, os.path.join(CSRC, src)]
         # an object newer than its source, every header it includes and this script is reused
         deps = list(_unit_deps(os.path.join(CSRC, src))) + [os.path.abspath(__file__)]

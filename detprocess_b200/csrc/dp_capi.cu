@@ -96,6 +96,7 @@ struct dp_of_plan {
     dpplan::Geometry geom;
     int v2_r1 = 0;  // != 0: the v2 kernels (dp_of2_kernel.cuh) serve this plan, M = v2_r1 * 4096
     int v2_multi = 0;  // some channel has more than one template
+    int v2_narrow = 0;  // every template's delay windows span at most two pass-1' columns per thread (column-wise scan)
     int neighbours = 0;    // every fit also reports the amplitude one sample before / after its best delay (interpolate_t0)
     bool generic = false;  // nb_samples is not a power of two: the mixed-radix kernel (dp_ofg_kernel.cuh) serves this plan
     const void *g_tw = nullptr, *g_wn = nullptr, *g_pos_k = nullptr, *g_pos_m = nullptr;
@@ -383,6 +384,32 @@ template <class T> int of2_finalize(dp_of_plan* p) {
     }
     p->scratch_per_cta = per_cta;
     p->v2_multi = max_templ > 1 ? 1 : 0;
+    {
+        // mirrors the kernel's window union per template (dp_of2_kernel.cuh, "fits of this template"): complex points
+        // [nlo, nhi] that some fit can select, widened by one point when the neighbour amplitudes are reported
+        const int M = p->N / 2, nb = std::min(p->v2_r1, std::is_same<T, double>::value ? 2 : DP2_NBMAX_F32);   // blocks per phase (Dp2Geom::NB)
+        const int bound = 2 * nb * 256 - 1;                                         // 2 * NT * VL - 1
+        bool narrow = true, any = false;
+        for (int c = 0; c < p->n_chan; ++c)
+            for (int t = 0; t < (int)p->chans[c].templ.size(); ++t) {
+                int nlo = 0x7fffffff, nhi = -1;
+                for (const auto& f : p->chans[c].fits) {
+                    if (f.templ != t) continue;
+                    const bool everything = f.outside || (f.lo == 0 && f.hi == p->N);
+                    const int a = everything ? 0 : (f.lo >> 1), b = everything ? 0x7fffffff : ((f.hi - 1) >> 1);
+                    nlo = std::min(nlo, a);
+                    nhi = std::max(nhi, b);
+                }
+                if (nhi < 0) continue;       // template without fits
+                any = true;
+                if (p->neighbours && nhi >= nlo && nhi - nlo < 4095) {
+                    nlo = nlo > 0 ? nlo - 1 : 0;
+                    nhi = nhi < M - 1 ? nhi + 1 : M - 1;
+                }
+                narrow = narrow && nhi >= nlo && (nhi - nlo) < bound;
+            }
+        p->v2_narrow = (any && narrow) ? 1 : 0;
+    }
     const size_t scratch_bytes = sizeof(cx<T>) * (size_t)per_cta * (size_t)p->grid_max;
     DP_CUDA(cudaMalloc(&p->scratch, scratch_bytes));
     p->owned.push_back(p->scratch);
@@ -443,7 +470,7 @@ int of2_run(dp_of_plan* p, const void* traces_dev, int in_dtype, long long n_eve
     const int grid = (int)std::min<long long>(prm.n_rows, p->grid_max);
     if (timed) DP_CUDA(cudaEventRecord(p->ev0, st));
     const int prec = sizeof(S) == 8 ? 0 : 1;
-    const int rc = dp_of2_launch_table[prec][in_dtype](p->v2_r1, p->v2_multi, &prm, grid, p->smem, st, p->persist_bytes);
+    const int rc = dp_of2_launch_table[prec][in_dtype](p->v2_r1, p->v2_multi | (p->v2_narrow << 1), &prm, grid, p->smem, st, p->persist_bytes);
     if (rc == -1) return fail(DP_ERR_UNSUPPORTED, "unsupported trace length");
     if (rc != 0) return fail(DP_ERR_CUDA, std::string("OF kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     if (timed) DP_CUDA(cudaEventRecord(p->ev1, st));

@@ -25,13 +25,19 @@ using InstT = f2;
 namespace {
 template <int R1> int setup_one(int device, size_t* smem, int* grid_max, int* occ_out, int* threads) {
     using K = Dp2OfKernel<InstT, R1, DP_INST_IN>;
-    auto kern = dp_of2_kernel<InstT, R1, DP_INST_IN, false>;
-    auto kern_m = dp_of2_kernel<InstT, R1, DP_INST_IN, true>;
+    auto kern = dp_of2_kernel<InstT, R1, DP_INST_IN, false, false>;
+    auto kern_m = dp_of2_kernel<InstT, R1, DP_INST_IN, true, false>;
+    auto kern_n = dp_of2_kernel<InstT, R1, DP_INST_IN, false, true>;
+    auto kern_mn = dp_of2_kernel<InstT, R1, DP_INST_IN, true, true>;
     *smem = K::SMEM_BYTES;
     *threads = K::NT;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(kern_n, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(kern_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     int occ = 0, sms = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern_m, K::NT, K::SMEM_BYTES);
@@ -63,10 +69,13 @@ template <int R1> int launch_one(const Dp2Params<InstT>& prm, int multi, int gri
         cfg.numAttrs = 1;
     }
     cudaError_t e;
-    if (multi)
-        e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, true>, prm);
-    else
-        e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, false>, prm);
+    // bit 0: some channel has more than one template; bit 1: every template's delay windows are narrow (column-wise scan)
+    switch (multi & 3) {
+        case 3: e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, true, true>, prm); break;
+        case 2: e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, false, true>, prm); break;
+        case 1: e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, true, false>, prm); break;
+        default: e = cudaLaunchKernelEx(&cfg, dp_of2_kernel<InstT, R1, DP_INST_IN, false, false>, prm); break;
+    }
     return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 }  // namespace

@@ -476,8 +476,8 @@ template <int IN> DP_DEV cx<f2> dp2_convert(const Dp2Raw<IN, 2>& r, double x0, d
 
 // tie-aware running best (|val| larger, or equal and smaller index)
 template <class S> DP_DEV void dp2_consider(DpBest<S>& b, S kabs, S v, int idx) {
-    const S kb = dp_abs(b.val);
-    if (b.idx < 0 || kabs > kb || (kabs == kb && idx < b.idx)) {
+    const S kb = dp_abs(b.val);  // (an empty best holds val = 0, idx = -1; a NaN candidate is never taken)
+    if (kabs > kb || (kabs == kb && (b.idx < 0 || idx < b.idx))) {
         b.val = v;
         b.idx = idx;
     }
@@ -527,6 +527,16 @@ template <class T, int R1, int IN> struct Dp2Core {
         // columns loaded back to back: <= 64 registers of raw float64 samples in flight
         constexpr int CBW = ((VL == 2) ? 8 : 16) / R1;
         constexpr int CB = CBW < 1 ? 1 : (CBW > NC ? NC : CBW);
+        // twiddle of column c = tid + j*NT: tw1[tid] * exp(-2 pi i j / (16*NPH)) -- ONE table value per thread and phase
+        // (8 KB per CTA: stays in L1) times a compile-time constant instead of a 64 KB table streamed through L1 / L2.
+        // Measured (C2, 32768 samples): packed fp32 +3 %, fp64 -2 % (four more FP64 instructions per column); the product
+        // costs one more rounding of every pass-1 twiddle, which the fp32 mode cannot spare -> off.
+#ifndef DP2_TW1_REG
+#define DP2_TW1_REG 0
+#endif
+        constexpr bool TW1_REG = DP2_TW1_REG;
+        [[maybe_unused]] V twb;
+        if constexpr (TW1_REG) twb = dp_ldg(tw1 + tid);
 #pragma unroll
         for (int i0 = 0; i0 < NC; i0 += CB) {
             Dp2Raw<IN, VL> raw[CB][R1];
@@ -544,7 +554,14 @@ template <class T, int R1, int IN> struct Dp2Core {
                 for (int n = 0; n < R1; ++n) v[n] = dp2_convert<IN>(raw[i][n], x0, sc);
                 dp_dft<R1, -1, T>::run(v);
                 V pw[R1];
-                dp2_powers<R1, T>(dp_ldg(tw1 + c), pw);
+                if constexpr (TW1_REG) {
+                    constexpr int STEP64 = 4 / NPH;   // exp(-2 pi i VL NT j / M) = W_64^(j * STEP64)
+                    const int j = i0 + i;
+                    const V wc = (j == 0) ? twb : cmul(twb, V{T((S)dp_cos64(j * STEP64)), T((S)(-dp_sin64(j * STEP64)))});
+                    dp2_powers<R1, T>(wc, pw);
+                } else {
+                    dp2_powers<R1, T>(dp_ldg(tw1 + c), pw);
+                }
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     const int k1 = G::k1_of(PH, b);
@@ -727,20 +744,46 @@ template <class T, int R1, int IN> struct Dp2Core {
         w.im = -w.im;
         [[maybe_unused]] V* dst = scr + (long long)(p * NB + b) * VPB + cc;
         [[maybe_unused]] const unsigned long long pol = dp2_policy_keep();
-#pragma unroll 1
-        for (unsigned m = rowmask; m != 0; m &= m - 1) {
-            const int n = __ffs((int)m) - 1;
+        auto root = [&](int n) {
             const T orr = (T)(S)dp2_w16_tab[n][0], oi = (T)(S)dp2_w16_tab[n][1];
-            const V u = V{dp_fma(w.re, orr, -(w.im * oi)), dp_fma(w.re, oi, w.im * orr)};
-            V acc = in[15];
-#pragma unroll
-            for (int k = 14; k >= 0; --k)
-                acc = V{dp_fma(acc.re, u.re, dp_fma(-acc.im, u.im, in[k].re)), dp_fma(acc.re, u.im, dp_fma(acc.im, u.re, in[k].im))};
+            return V{dp_fma(w.re, orr, -(w.im * oi)), dp_fma(w.re, oi, w.im * orr)};
+        };
+        auto put = [&](int n, const V& acc) {
             if constexpr (PARK)
                 dp2_st_keep(dst + n * CV, acc, pol);
             else
                 pb[n * PC] = acc;
+        };
+        const int n0 = __ffs((int)rowmask) - 1;
+        const unsigned rest = rowmask & (rowmask - 1);
+#ifndef DP2_HORNER_SEQ
+        if (rest != 0 && (rest & (rest - 1)) == 0) {
+            // two rows (the usual case of a narrow window): the two Horner chains are independent -- interleaved they
+            // hide each other's FMA latency
+            const int n1 = __ffs((int)rest) - 1;
+            const V u0 = root(n0), u1 = root(n1);
+            V a0 = in[15], a1 = in[15];
+#pragma unroll
+            for (int k = 14; k >= 0; --k) {
+                a0 = V{dp_fma(a0.re, u0.re, dp_fma(-a0.im, u0.im, in[k].re)), dp_fma(a0.re, u0.im, dp_fma(a0.im, u0.re, in[k].im))};
+                a1 = V{dp_fma(a1.re, u1.re, dp_fma(-a1.im, u1.im, in[k].re)), dp_fma(a1.re, u1.im, dp_fma(a1.im, u1.re, in[k].im))};
+            }
+            put(n0, a0);
+            put(n1, a1);
+            return;
         }
+#endif
+#pragma unroll 1
+        for (unsigned m = rowmask; m != 0; m &= m - 1) {
+            const int n = __ffs((int)m) - 1;
+            const V u = root(n);
+            V acc = in[15];
+#pragma unroll
+            for (int k = 14; k >= 0; --k)
+                acc = V{dp_fma(acc.re, u.re, dp_fma(-acc.im, u.im, in[k].re)), dp_fma(acc.re, u.im, dp_fma(acc.im, u.re, in[k].im))};
+            put(n, acc);
+        }
+        (void)n0;
     }
     // pass-2' outputs -> smem (own positions, in place)
     static DP_DEV void store_pass2(V* buf, const V (&z)[16]) {
@@ -1287,11 +1330,13 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
 
     // MULTI: some channel has more than one template (X goes through the warp's scratch column and comes back by
     // bulk copy for the second and later templates)
-    template <bool MULTI> static DP_DEV void run(const Dp2Params<T>& prm, unsigned char* smem_raw);
+    // SCAN: how the delay search walks the pass-1' outputs -- 0: blocks of GC columns (wide windows), 1: column by column
+    // (the host guarantees narrow windows: dp_capi.cu of2_narrow), 2: chosen per template at run time (emulator builds)
+    template <bool MULTI, int SCAN = 2> static DP_DEV void run(const Dp2Params<T>& prm, unsigned char* smem_raw);
 };
 
 template <class T, int R1, int IN>
-template <bool MULTI>
+template <bool MULTI, int SCAN>
 DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* smem_raw) {
     const Smem sm = carve(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1432,6 +1477,11 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     S chin = (S)0;
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
+#ifndef DP2_PAIR_SPLIT
+#define DP2_PAIR_SPLIT 4
+#endif
+                        // keeps the scheduler from hoisting all eight partner exchanges to the top (17 spilled doubles)
+                        if (DP2_PAIR_SPLIT > 0 && r > 0 && r % (DP2_PAIR_SPLIT > 0 ? DP2_PAIR_SPLIT : 1) == 0) __syncwarp();
                         const V Zm = dp2_swap1(z[15 - r]);  // the partner's element 15 - r
                         const cx<S> w = cmul(wn, dp_w64_rt<S>(2 * r));
                         cx<S> Xk, Xm;
@@ -1540,6 +1590,54 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
 #pragma unroll
                     for (int q = 0; q < DP_MAX_TSLOTS; ++q) tb[q] = DpBest<S>{(S)0, -1};
                     const unsigned colneed = Core::need_cols(nlo, nhi);
+                    // narrow delay windows (at most two columns per thread hold a candidate; CTA-uniform)
+                    const bool narrow = SCAN == 1 || (SCAN == 2 && nhi >= nlo && (nhi - nlo) < 2 * NT * VL - 1);
+                    if (narrow) {
+                    // column by column: pass 1' of a column that holds a candidate delay, then its R1 * 2 * VL samples are
+                    // offered to every fit of this template (tie-aware: the columns are not visited in ascending delay
+                    // order).  A +-500-sample window leaves one column per thread.
+                    bool whole[DP_MAX_TSLOTS];
+                    int wlo[DP_MAX_TSLOTS];
+                    unsigned wlen[DP_MAX_TSLOTS];
+                    bool wout[DP_MAX_TSLOTS];
+#pragma unroll
+                    for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                        whole[q] = false, wlo[q] = 0, wlen[q] = 0u, wout[q] = false;
+                        if (q < nts) {
+                            const DpSlot sl = ch.slots[slot_of[q]];
+                            whole[q] = sl.lo == 0 && sl.hi == N && !sl.outside;
+                            wlo[q] = sl.lo, wlen[q] = (unsigned)(sl.hi - sl.lo), wout[q] = sl.outside != 0;
+                        }
+                    }
+#pragma unroll 1
+                    for (unsigned cm = colneed; cm != 0; cm &= cm - 1) {
+                        const int c = tid + (__ffs((int)cm) - 1) * NT;
+                        V u[R1];
+                        Core::inv_pass1_col(sm.buf, park, prm.tw1, c, u);
+#pragma unroll
+                        for (int q = 0; q < DP_MAX_TSLOTS; ++q) {
+                            if (q >= nts) continue;
+#pragma unroll
+                            for (int n = 0; n < R1; ++n) {
+                                const int r0 = 2 * (n * 4096 + VL * c);
+#define DP2_CAND(val, rr)                                                                          \
+    {                                                                                              \
+        const S a_ = (val);                                                                        \
+        const int r_ = (rr);                                                                       \
+        const bool in_ = whole[q] || ((((unsigned)(r_ - wlo[q]) < wlen[q])) != wout[q]);           \
+        if (in_) dp2_consider(tb[q], dp_abs(a_), a_, r_);                                          \
+    }
+                                DP2_CAND((Dp2Scan<T, R1>::template re_of<0>(u[n])), r0)
+                                DP2_CAND((Dp2Scan<T, R1>::template im_of<0>(u[n])), r0 + 1)
+                                if constexpr (VL == 2) {
+                                    DP2_CAND((Dp2Scan<T, R1>::template re_of<1>(u[n])), r0 + 2)
+                                    DP2_CAND((Dp2Scan<T, R1>::template im_of<1>(u[n])), r0 + 3)
+                                }
+#undef DP2_CAND
+                            }
+                        }
+                    }
+                    } else {
 #pragma unroll 1
                     for (int i0 = 0; i0 < NC; i0 += GC) {
                         const unsigned computed = (colneed >> i0) & ((1u << GC) - 1u);
@@ -1560,6 +1658,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                                     Dp2Scan<T, R1>::window(y, tid, i0, sl.lo, (unsigned)(sl.hi - sl.lo), sl.outside != 0, tb[q], computed);
                             }
                         }
+                    }
                     }
                     DpBest<S>* best = sm.best(par);
                     double* red = sm.red(par);
@@ -1690,11 +1789,21 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     if constexpr (VL == 2) {
 #pragma unroll
                         for (int r = 0; r < 16; ++r) z[r] = tb.x(r);
-                        filter_st<false>(z, tb, wn);
+                        cx<S> wn2 = wn;
+#if !defined(DP2_WN_CSE) && !defined(DP_HOST_EMU)
+                        asm volatile("" : "+f"(wn2.re), "+f"(wn2.im));   // see the fp64 branch
+#endif
+                        filter_st<false>(z, tb, wn2);
                     } else {
+                        cx<S> wn2 = wn;
+#if !defined(DP2_WN_CSE) && !defined(DP_HOST_EMU)
+                        // the pair twiddles are recomputed from an opaque copy: common-subexpression elimination with the
+                        // first template's round kept all eight of them alive across the inverse passes (14 spilled doubles)
+                        asm volatile("" : "+d"(wn2.re), "+d"(wn2.im));
+#endif
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            const cx<S> w = cmul(wn, dp_w64_rt<S>(2 * r));
+                            const cx<S> w = cmul(wn2, dp_w64_rt<S>(2 * r));
                             pair_filter(z, r, tb.x(2 * r), tb.x(2 * r + 1), tb.phi_b(2 * r), tb.phi_b(2 * r + 1), w);
                         }
                     }
@@ -1706,9 +1815,9 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
 }
 
 #ifndef DP_HOST_EMU
-template <class T, int R1, int IN, bool MULTI>
+template <class T, int R1, int IN, bool MULTI, bool NARROW = false>
 __global__ void __launch_bounds__(Dp2Geom<T, R1>::NT, Dp2Geom<T, R1>::NT <= 256 ? 2 : 1) dp_of2_kernel(const Dp2Params<T> prm) {
     extern __shared__ __align__(16) unsigned char dp_smem_raw[];
-    Dp2OfKernel<T, R1, IN>::template run<MULTI>(prm, dp_smem_raw);
+    Dp2OfKernel<T, R1, IN>::template run<MULTI, NARROW ? 1 : 0>(prm, dp_smem_raw);
 }
 #endif
