@@ -1251,7 +1251,7 @@ int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* p, float* ms) {
 // ========================================================================== PSD plan
 struct dp_psd_plan {
     int v2_r1 = 0;  // != 0: v2 FFT core (dp_psd2_kernel.cuh)
-    const void *tw3 = nullptr, *groups = nullptr;
+    const void *tw3 = nullptr, *groups = nullptr, *chunk3 = nullptr;
     int N = 0;
     double fs = 0;
     int precision = DP_PREC_F64;
@@ -1350,6 +1350,9 @@ template <class T, int R1> int psd2_tables(dp_psd_plan* p) {
     const int2* dg;
     if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
     p->groups = dg;
+    const int* dc3;
+    if ((rc = upload(p->owned, dt.chunk3, &dc3))) return rc;
+    p->chunk3 = dc3;
     // natural bin k -> slot in one CTA's partial array
     const std::vector<int> loc = dpplan2::partial_slot_of_bin<G>();
     if ((rc = upload(p->owned, loc, &p->loc))) return rc;
@@ -1479,6 +1482,7 @@ int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long
             prm.n_rows = (int)n_traces;
             prm.mask = mask_dev;
             prm.groups = reinterpret_cast<const int2*>(p->groups);
+            prm.chunk3 = reinterpret_cast<const int*>(p->chunk3);
             prm.partial = p->partial;
             prm.partial_per_cta = p->partial_per_cta;
             prm.count = p->count;
@@ -1562,7 +1566,7 @@ struct dp_trigger_plan {
     std::vector<double> phi_td;
     bool tables_ok = false;
     std::vector<void*> owned;
-    const void *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twn = nullptr, *groups = nullptr;
+    const void *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twn = nullptr, *groups = nullptr, *chunk3 = nullptr;
     void* phi = nullptr;       // re-uploaded when the scale changes
     void* phi_self = nullptr;
     size_t phi_bytes = 0, phi_self_bytes = 0;
@@ -1572,6 +1576,10 @@ struct dp_trigger_plan {
     double* cand_amp = nullptr;
     int* cand_count = nullptr;
     long long* chunk_offset = nullptr;
+    double* taps_dev = nullptr;   // phi_td on the device (dp_trigger_filtered_at)
+    double* cand_val = nullptr;   // residual delta chi2 of the candidates (allocated by the first residual pass)
+    int last_chunks = 0;          // chunk count of the last dp_trigger_run (the candidate list the follow-up calls use)
+    bool resid_list = false;      // the candidate list holds residual survivors (cand_val is valid)
     // parallel grouping workspace
     int* tile_heads = nullptr;
     unsigned long long *best_key = nullptr, *best_g = nullptr;
@@ -1628,6 +1636,9 @@ template <class T, int R1> int trig_tables(dp_trigger_plan* p, bool filter_only)
         const int2* dg;
         if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
         p->groups = dg;
+        const int* dc3;
+        if ((rc = upload(p->owned, dt.chunk3, &dc3))) return rc;
+        p->chunk3 = dc3;
     }
     std::vector<cx<T>> phi;
     std::vector<cx<S>> phi_self;
@@ -1774,6 +1785,7 @@ int dp_trigger_run_raw(dp_trigger_plan* p, const void* trace_dev, int in_dtype, 
         prm.valid_lo = vlo;
         prm.valid_hi = vhi;
         prm.groups = reinterpret_cast<const int2*>(p->groups);
+        prm.chunk3 = reinterpret_cast<const int*>(p->chunk3);
         prm.scratch_per_cta = p->scratch_per_cta;
         prm.w = p->w;
         prm.thr = chi2_threshold;
@@ -1821,6 +1833,9 @@ int dp_trigger_run_raw(dp_trigger_plan* p, const void* trace_dev, int in_dtype, 
     gp.n_triggers = n_triggers_dev;
     gp.chunk_offset = p->chunk_offset;
     gp.tile_heads = p->tile_heads;
+    gp.cand_val = nullptr;
+    p->last_chunks = n_chunks;
+    p->resid_list = false;
     if (!p->group_serial && p->best_cap < max_triggers) {
         void* a = nullptr;
         void* b = nullptr;
@@ -1846,6 +1861,150 @@ int dp_trigger_plan_last_kernel_ms(dp_trigger_plan* p, float* filter_ms, float* 
     DP_CUDA(cudaEventSynchronize(p->ev2));
     if (filter_ms) DP_CUDA(cudaEventElapsedTime(filter_ms, p->ev0, p->ev1));
     if (group_ms) DP_CUDA(cudaEventElapsedTime(group_ms, p->ev1, p->ev2));
+    return DP_OK;
+}
+
+}  // extern "C"
+
+
+namespace {
+int trig_best_buffers(dp_trigger_plan* p, int max_triggers) {
+    if (p->best_cap >= max_triggers) return DP_OK;
+    void* a = nullptr;
+    void* b = nullptr;
+    DP_CUDA(cudaMalloc(&a, sizeof(unsigned long long) * (size_t)std::max(max_triggers, 1)));
+    p->owned.push_back(a);
+    DP_CUDA(cudaMalloc(&b, sizeof(unsigned long long) * (size_t)std::max(max_triggers, 1)));
+    p->owned.push_back(b);
+    p->best_key = reinterpret_cast<unsigned long long*>(a);
+    p->best_g = reinterpret_cast<unsigned long long*>(b);
+    p->best_cap = max_triggers;
+    return DP_OK;
+}
+void trig_group_params(const dp_trigger_plan* p, DpTrigGroupParams& gp) {
+    std::memset(&gp, 0, sizeof(gp));
+    gp.cand_idx = p->cand_idx;
+    gp.cand_amp = p->cand_amp;
+    gp.cand_count = p->cand_count;
+    gp.n_chunks = p->last_chunks;
+    gp.hop = p->hop;
+    gp.w = p->w;
+    gp.chunk_offset = p->chunk_offset;
+    gp.tile_heads = p->tile_heads;
+    gp.best_key = p->best_key;
+    gp.best_g = p->best_g;
+    gp.cand_val = p->resid_list ? p->cand_val : nullptr;
+}
+}  // namespace
+
+extern "C" {
+
+int dp_trigger_candidates(dp_trigger_plan* p, long long* idx_dev, double* amp_dev, double* dchi2_dev, long long max_candidates,
+                          long long* n_candidates_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->last_chunks <= 0) return fail(DP_ERR_STATE, "dp_trigger_run has not been called on this plan");
+    if (!idx_dev || !amp_dev || !n_candidates_dev || max_candidates < 0) return fail(DP_ERR_INVALID, "bad argument");
+    DP_ON_DEVICE(p->device);
+    DpTrigGroupParams gp;
+    trig_group_params(p, gp);
+    DpTrigFlattenParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.cand_idx = p->cand_idx;
+    fp.cand_amp = p->cand_amp;
+    fp.cand_val = p->resid_list ? p->cand_val : nullptr;
+    fp.cand_count = p->cand_count;
+    fp.chunk_offset = p->chunk_offset;
+    fp.n_chunks = p->last_chunks;
+    fp.hop = p->hop;
+    fp.w = p->w;
+    fp.out_idx = idx_dev;
+    fp.out_amp = amp_dev;
+    fp.out_val = dchi2_dev;
+    fp.max_out = max_candidates;
+    fp.n_out = n_candidates_dev;
+    const int rc = dp_trig_flatten_launch(&gp, &fp, std::max(1, std::min(p->last_chunks, 4 * std::max(p->n_sm, 1))), stream);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger candidate list: ") + cudaGetErrorString((cudaError_t)rc));
+    return DP_OK;
+}
+
+int dp_trigger_filtered_at(dp_trigger_plan* p, const void* trace_dev, int in_dtype, long long n_samples, const long long* idx_dev,
+                           int n_idx, double* filtered_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
+    if (!trace_dev || !idx_dev || !filtered_dev || n_idx < 0 || n_samples < 1) return fail(DP_ERR_INVALID, "bad argument");
+    if (n_idx == 0) return DP_OK;
+    DP_ON_DEVICE(p->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!p->taps_dev) {  // the taps go to the device with the first call
+        void* taps = nullptr;
+        DP_CUDA(cudaMalloc(&taps, sizeof(double) * (size_t)p->nb_filter));
+        p->owned.push_back(taps);
+        DP_CUDA(cudaMemcpyAsync(taps, p->phi_td.data(), sizeof(double) * (size_t)p->nb_filter, cudaMemcpyHostToDevice, st));
+        p->taps_dev = reinterpret_cast<double*>(taps);
+    }
+    DpTrigAtParams ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.trace = trace_dev;
+    ap.in_dtype = in_dtype;
+    ap.n_samples = n_samples;
+    ap.phi_td = p->taps_dev;
+    ap.nt = p->nb_filter;
+    ap.iw = p->iw;
+    ap.idx = idx_dev;
+    ap.n_idx = n_idx;
+    ap.out = filtered_dev;
+    const int rc = dp_trig_filtered_at_launch(&ap, stream);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger filtered_at launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return DP_OK;
+}
+
+int dp_trigger_residual_run(dp_trigger_plan* p, const long long* pulse_start_dev, const double* pulse_amp2_dev, int n_pulses,
+                            const double* shape_dev, int n_shape, double chi2_threshold, long long pileup_window_samples,
+                            long long index_shift, long long* trig_index_dev, double* trig_amp_dev, double* trig_dchi2_dev,
+                            int max_triggers, int* n_triggers_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (p->last_chunks <= 0) return fail(DP_ERR_STATE, "dp_trigger_run has not been called on this plan");
+    if (n_pulses < 0 || n_shape < 1 || max_triggers < 0 || pileup_window_samples < 0) return fail(DP_ERR_INVALID, "bad argument");
+    if (n_pulses > 0 && (!pulse_start_dev || !pulse_amp2_dev)) return fail(DP_ERR_INVALID, "null pulse list");
+    if (!shape_dev || !trig_index_dev || !trig_amp_dev || !trig_dchi2_dev || !n_triggers_dev) return fail(DP_ERR_INVALID, "null buffer");
+    DP_ON_DEVICE(p->device);
+    if (!p->cand_val) {
+        void* v = nullptr;
+        DP_CUDA(cudaMalloc(&v, sizeof(double) * (size_t)p->max_chunks * (size_t)p->hop));
+        p->owned.push_back(v);
+        p->cand_val = reinterpret_cast<double*>(v);
+    }
+    int rc = trig_best_buffers(p, max_triggers);
+    if (rc) return rc;
+    DpTrigResidParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.cand_idx = p->cand_idx;
+    rp.cand_amp = p->cand_amp;
+    rp.cand_val = p->cand_val;
+    rp.cand_count = p->cand_count;
+    rp.n_chunks = p->last_chunks;
+    rp.hop = p->hop;
+    rp.w = p->w;
+    rp.thr = chi2_threshold;
+    rp.pulse_start = pulse_start_dev;
+    rp.pulse_a2 = pulse_amp2_dev;
+    rp.n_pulses = n_pulses;
+    rp.shape = shape_dev;
+    rp.n_shape = n_shape;
+    rc = dp_trig_residual_launch(&rp, std::max(1, std::min(p->last_chunks, 2 * std::max(p->n_sm, 1))), stream);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger residual launch: ") + cudaGetErrorString((cudaError_t)rc));
+    p->resid_list = true;
+    DpTrigGroupParams gp;
+    trig_group_params(p, gp);
+    gp.pileup_window = pileup_window_samples;
+    gp.index_shift = index_shift;
+    gp.trig_index = trig_index_dev;
+    gp.trig_amp = trig_amp_dev;
+    gp.trig_dchi2 = trig_dchi2_dev;
+    gp.max_triggers = max_triggers;
+    gp.n_triggers = n_triggers_dev;
+    rc = dp_trig_group_par_launch(&gp, std::max(1, 2 * p->n_sm), stream);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger group launch: ") + cudaGetErrorString((cudaError_t)rc));
     return DP_OK;
 }
 

@@ -9,6 +9,26 @@
 #pragma once
 #include "dp_of2_kernel.cuh"
 
+// DP_PSD_V3 (round 2): passes 3 / 4 warp-local like the OF kernel (one set barrier after pass 2 instead of a block and a set
+// barrier; the warps drift through pass 3, pass 4 and the untangle), and the partial sums updated by fire-and-forget
+// reductions (RED.ADD.F64 at the L2: the thread-private slots need no load, so no thread waits on an L2 round trip before
+// its add).  0 = the round-1 kernel (lock-step passes, load / add / store).
+#ifndef DP_PSD_V3
+#define DP_PSD_V3 1
+#endif
+
+#if !defined(DP_HOST_EMU)
+DP_DEV void dp_psd_acc(double* slot, double v) {
+#if DP_PSD_V3
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(slot), "d"(v) : "memory");
+#else
+    *slot += v;
+#endif
+}
+#else
+static inline void dp_psd_acc(double* slot, double v) { *slot += v; }
+#endif
+
 template <class T> struct DpPsd2Params {
     using S = typename Dp2Traits<T>::S;
     const void* traces;
@@ -20,6 +40,7 @@ template <class T> struct DpPsd2Params {
     const cx<T>* tw3;
     const cx<S>* twn;
     const int2* groups;
+    const int* chunk3;          // [NPH][NT] pass-3 chunk of the thread (warp-local passes, dpplan2::build_chunks)
     double* partial;            // [grid][partial_per_cta]: [NPH][16][NT][VL] thread order, then [17][2] self lanes
     long long partial_per_cta;
     unsigned long long* count;  // [grid] accepted traces per CTA
@@ -65,7 +86,17 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
 #ifndef DP_HOST_EMU
                 if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);  // see dp_of2_kernel.cuh
 #endif
+#if DP_PSD_V3
+                Core::fwd_2(buf, prm.tw2, z);
+                dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 3 reads the chunks of the warp's block set
+                Core::fwd_3w(buf, prm.tw3, prm.chunk3[p * NT + tid], z);
+                __syncwarp();
+                Core::load_groups(buf, gg.x, gg.y, z);
+                __syncwarp();  // pw_publish rewrites the warp's group rows
+                dp_dft<16, -1, T>::run(z);
+#else
                 Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+#endif
                 if (p == 0 && tid < 32) {
                     if constexpr (VL == 2) {
                         if (tid == 0) {
@@ -92,8 +123,8 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
                             const double dc = (double)Xk.re / (2.0 * prm.scale) + (double)N * x0;
                             pk = dc * dc;
                         }
-                        part_self[2 * tid] += pk;
-                        part_self[2 * tid + 1] += pm;
+                        dp_psd_acc(part_self + 2 * tid, pk);
+                        dp_psd_acc(part_self + 2 * tid + 1, pm);
                     }
                     __syncwarp();
                 }
@@ -104,10 +135,15 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
                             const f2 pw = cnorm2(z[r]);
+#if DP_PSD_V3
+                            dp_psd_acc(&dst[r * NT].x, (double)pw.x * inv_s2);
+                            dp_psd_acc(&dst[r * NT].y, (double)pw.y * inv_s2);
+#else
                             double2 a = dst[r * NT];
                             a.x += (double)pw.x * inv_s2;
                             a.y += (double)pw.y * inv_s2;
                             dst[r * NT] = a;
+#endif
                         }
                     }
                 } else {
@@ -116,8 +152,8 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
                     OF::pw_publish(buf, z, gg.x);
                     OF::pw_untangle(buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) {
                         if (!special) {
-                            dst[(2 * r) * NT] += cnorm2(Xk) * inv_s2;
-                            dst[(2 * r + 1) * NT] += cnorm2(Xm) * inv_s2;
+                            dp_psd_acc(dst + (2 * r) * NT, cnorm2(Xk) * inv_s2);
+                            dp_psd_acc(dst + (2 * r + 1) * NT, cnorm2(Xm) * inv_s2);
                         }
                     });
                 }

@@ -99,4 +99,24 @@ int dp_trig_group_par_launch(const void* prm_v, int grid, void* st_v) {
     dp_trig_par_emit_kernel<<<64, 256, 0, st>>>(prm);
     return (int)cudaGetLastError();
 }
+// residual pass: residuals + in-place compaction of the candidate list (then dp_trig_group_par_launch with cand_val)
+int dp_trig_residual_launch(const void* prm_v, int grid, void* st_v) {
+    const DpTrigResidParams& prm = *reinterpret_cast<const DpTrigResidParams*>(prm_v);
+    dp_trig_residual_kernel<<<grid, 1024, 0, reinterpret_cast<cudaStream_t>(st_v)>>>(prm);
+    return (int)cudaGetLastError();
+}
+// chunk offsets of the current candidate counts, then the flat ordered list
+int dp_trig_flatten_launch(const void* group_prm_v, const void* prm_v, int grid, void* st_v) {
+    const DpTrigGroupParams& gp = *reinterpret_cast<const DpTrigGroupParams*>(group_prm_v);
+    const DpTrigFlattenParams& prm = *reinterpret_cast<const DpTrigFlattenParams*>(prm_v);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(st_v);
+    dp_trig_par_offsets_kernel<<<1, 1024, 0, st>>>(gp);
+    dp_trig_flatten_kernel<<<grid, 256, 0, st>>>(prm);
+    return (int)cudaGetLastError();
+}
+int dp_trig_filtered_at_launch(const void* prm_v, void* st_v) {
+    const DpTrigAtParams& prm = *reinterpret_cast<const DpTrigAtParams*>(prm_v);
+    dp_trig_filtered_at_kernel<<<prm.n_idx < 1024 ? prm.n_idx : 1024, 256, 0, reinterpret_cast<cudaStream_t>(st_v)>>>(prm);
+    return (int)cudaGetLastError();
+}
 #endif

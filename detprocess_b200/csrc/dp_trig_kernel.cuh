@@ -21,6 +21,13 @@
 #pragma once
 #include "dp_of2_kernel.cuh"
 
+// DP_TRIG_V3 (round 2): passes 3 / 4 / 4' / 3' warp-local like the OF kernel -- between the set barrier after pass 2 and the
+// one before pass 2' a warp only needs __syncwarp() (it owns whole chunks), so the warps overlap each other's shared-memory
+// and FP phases.  0 = the lock-step passes of round 1.
+#ifndef DP_TRIG_V3
+#define DP_TRIG_V3 1
+#endif
+
 template <class T> struct DpTrigParams {
     using S = typename Dp2Traits<T>::S;
     const void* trace;      // continuous stream (in_dtype samples)
@@ -34,6 +41,7 @@ template <class T> struct DpTrigParams {
     const cx<T>* tw3;
     const cx<S>* twn;
     const int2* groups;
+    const int* chunk3;      // [NPH][NT] pass-3 chunk of the thread (warp-local passes)
     const cx<T>* phi;       // [NPH][16][NT] filter spectrum, thread order
     const cx<S>* phi_self;  // [17][2]
     cx<T>* scratch;         // [grid][(NPH-1)*NB*VPB] parked block results
@@ -115,7 +123,18 @@ template <class T, int R1, int IN> struct DpTrigKernel {
 #ifndef DP_HOST_EMU
                 if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);  // see dp_of2_kernel.cuh
 #endif
+#if DP_TRIG_V3
+                const int chunk = prm.chunk3[p * NT + tid];
+                Core::fwd_2(buf, prm.tw2, z);
+                dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 3 reads the chunks of the warp's block set
+                Core::fwd_3w(buf, prm.tw3, chunk, z);
+                __syncwarp();
+                Core::load_groups(buf, gg.x, gg.y, z);
+                __syncwarp();  // the point-wise stage rewrites the warp's group rows
+                dp_dft<16, -1, T>::run(z);
+#else
                 Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+#endif
                 if (p == 0 && tid < 32) {
                     if constexpr (VL == 2) {
                         if (tid == 0) {
@@ -178,7 +197,16 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                     }
                     __syncwarp();
                 }
+#if DP_TRIG_V3
+                dp_dft<16, +1, T>::run(z);
+                Core::store_groups(buf, gg.x, gg.y, z);
+                __syncwarp();  // pass 3' reads the warp's own chunks
+                Core::inv_3w(buf, prm.tw3, chunk, z);
+                dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 2' reads columns across the set's chunks
+                Core::inv_2(buf, prm.tw2, z);
+#else
                 Core::inv_432(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+#endif
                 if (p < NPH - 1) {
                     Core::park_pass2(park, p, z);
                     __syncthreads();
@@ -284,6 +312,51 @@ struct DpTrigGroupParams {
     int* tile_heads;               // [max_tiles + 1] group heads per tile of 1024 candidates -> exclusive prefix
     unsigned long long* best_key;  // [max_triggers] ordered bits of the largest |amp| of the group
     unsigned long long* best_g;    // [max_triggers] smallest candidate number attaining it
+    // residual re-trigger (oftrigger.py:752-845): when set, [n_chunks][hop] delta-chi2 values (> 0) that rank the
+    // candidates and are reported instead of amp^2 w (parallel grouping only)
+    const double* cand_val;
+};
+
+// parameters of the follow-up kernels on the candidate list (residual re-trigger, flat list, filtered amplitude at an index)
+struct DpTrigResidParams {
+    int* cand_idx;            // [n_chunks][hop], compacted in place
+    double* cand_amp;
+    double* cand_val;         // [n_chunks][hop] residual delta chi2 of the survivors
+    int* cand_count;          // [n_chunks], updated
+    int n_chunks;
+    int hop;
+    double w, thr;
+    const long long* pulse_start;  // [n_pulses] ascending: stream index of shape[0] for every subtracted pulse
+    const double* pulse_a2;        // [n_pulses] squared filtered amplitude
+    int n_pulses;
+    const double* shape;           // [n_shape] D
+    int n_shape;
+};
+struct DpTrigFlattenParams {
+    const int* cand_idx;
+    const double* cand_amp;
+    const double* cand_val;   // may be null
+    const int* cand_count;
+    const long long* chunk_offset;
+    int n_chunks;
+    int hop;
+    double w;
+    long long* out_idx;
+    double* out_amp;
+    double* out_val;          // may be null
+    long long max_out;
+    long long* n_out;         // [1] total number of candidates (may exceed max_out)
+};
+struct DpTrigAtParams {
+    const void* trace;
+    int in_dtype;
+    long long n_samples;
+    const double* phi_td;
+    int nt;
+    double iw;
+    const long long* idx;
+    int n_idx;
+    double* out;
 };
 
 #ifndef DP_HOST_EMU
@@ -485,9 +558,11 @@ struct DpTrigTile {
     long long g;     // candidate number
     long long idx;   // stream index
     double amp;
+    double val;      // what the group maximises: |amp|, or the residual delta chi2
     bool head;
 };
-__device__ __forceinline__ void dp_trig_locate(const DpTrigGroupParams& prm, const long long* coff, long long g, long long& idx, double& amp) {
+__device__ __forceinline__ void dp_trig_locate(const DpTrigGroupParams& prm, const long long* coff, long long g, long long& idx, double& amp,
+                                               double& val) {
     int lo = 0, hi = prm.n_chunks - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -496,6 +571,7 @@ __device__ __forceinline__ void dp_trig_locate(const DpTrigGroupParams& prm, con
     const long long pos = (long long)lo * prm.hop + (g - coff[lo]);
     idx = (long long)lo * prm.hop + prm.cand_idx[pos];
     amp = prm.cand_amp[pos];
+    val = prm.cand_val ? prm.cand_val[pos] : fabs(amp);
 }
 // candidate tid of tile t, and whether it starts a group (needs its predecessor's index)
 __device__ __forceinline__ DpTrigTile dp_trig_tile_load(const DpTrigGroupParams& prm, const long long* coff, long long K, long long t,
@@ -506,13 +582,14 @@ __device__ __forceinline__ DpTrigTile dp_trig_tile_load(const DpTrigGroupParams&
     c.have = c.g < K;
     c.idx = 0;
     c.amp = 0.0;
-    if (c.have) dp_trig_locate(prm, coff, c.g, c.idx, c.amp);
+    c.val = 0.0;
+    if (c.have) dp_trig_locate(prm, coff, c.g, c.idx, c.amp, c.val);
     __syncthreads();  // previous users of s_idx are done
     s_idx[tid + 1] = c.idx;
     if (tid == 0) {
         long long pi = 0;
-        double pa;
-        if (c.g > 0 && c.have) dp_trig_locate(prm, coff, c.g - 1, pi, pa);
+        double pa, pv;
+        if (c.g > 0 && c.have) dp_trig_locate(prm, coff, c.g - 1, pi, pa, pv);
         s_idx[0] = pi;
     }
     __syncthreads();
@@ -593,7 +670,7 @@ template <int PHASE> __global__ void __launch_bounds__(1024, 1) dp_trig_par_best
         const int seg = use ? (int)gid : -1;
         const int seg_next = __shfl_down_sync(0xffffffffu, seg, 1);
         const bool seg_tail = use && (lane == 31 || seg_next != seg);
-        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(c.amp));
+        const unsigned long long key = (unsigned long long)__double_as_longlong(c.val);
         if (PHASE == 0) {
             unsigned long long k = use ? key : 0ull;
 #pragma unroll
@@ -619,11 +696,112 @@ __global__ void dp_trig_par_emit_kernel(const DpTrigGroupParams prm) {
     const int n = *prm.n_triggers < prm.max_triggers ? *prm.n_triggers : prm.max_triggers;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
         long long idx;
-        double amp;
-        dp_trig_locate(prm, prm.chunk_offset, (long long)prm.best_g[o], idx, amp);
+        double amp, val;
+        dp_trig_locate(prm, prm.chunk_offset, (long long)prm.best_g[o], idx, amp, val);
         prm.trig_index[o] = idx + prm.index_shift;
         prm.trig_amp[o] = amp;
-        prm.trig_dchi2[o] = amp * amp * prm.w;
+        prm.trig_dchi2[o] = prm.cand_val ? val : amp * amp * prm.w;
+    }
+}
+// ---- residual re-trigger (oftrigger.py:752-845) on the candidate list.  A first-pass pulse of filtered amplitude A
+// produces the delta-chi2 shape A^2 D[j] (D = w (iw oaconvolve(template, phi_td, 'same'))^2: the chi2 trace of a unit
+// pulse); the reference subtracts that shape from the WHOLE delta-chi2 trace and thresholds again.  D >= 0, so the
+// second-pass candidates are a subset of the first-pass ones: only the list is revisited -- every candidate gets its
+// residual (the shapes of the pulses that cover it, subtracted in trigger order like the reference's loop), survivors
+// are compacted in place, chunk by chunk, still ordered by stream index, and the grouping kernels run on them.
+__global__ void __launch_bounds__(1024, 1) dp_trig_residual_kernel(const DpTrigResidParams prm) {
+    __shared__ int s_warp[33];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    for (int q = blockIdx.x; q < prm.n_chunks; q += gridDim.x) {
+        const int cnt = prm.cand_count[q];
+        const long long row = (long long)q * prm.hop;
+        if (tid == 0) s_base = 0;
+        __syncthreads();
+        for (int j0 = 0; j0 < cnt; j0 += 1024) {
+            const int j = j0 + tid;
+            const bool have = j < cnt;
+            int r = 0;
+            double a = 0.0, val = 0.0;
+            if (have) {
+                r = prm.cand_idx[row + j];
+                a = prm.cand_amp[row + j];
+                val = a * a * prm.w;
+                const long long t = row + r;
+                // first pulse whose shape reaches t: start + n_shape > t
+                int lo = 0, hi = prm.n_pulses;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (prm.pulse_start[mid] + prm.n_shape > t) hi = mid; else lo = mid + 1;
+                }
+                for (int i = lo; i < prm.n_pulses; ++i) {
+                    const long long st = prm.pulse_start[i];
+                    if (st > t) break;
+                    val -= prm.pulse_a2[i] * prm.shape[t - st];
+                }
+            }
+            const bool keep = have && val > prm.thr;
+            int tot;
+            const int inc = dp_trig_scan1024(keep ? 1 : 0, s_warp, tot);  // its barriers also order this tile's reads before the writes
+            const int base = s_base;
+            if (keep) {
+                const long long o = row + base + inc - 1;
+                prm.cand_idx[o] = r;
+                prm.cand_amp[o] = a;
+                prm.cand_val[o] = val;
+            }
+            __syncthreads();
+            if (tid == 0) s_base = base + tot;
+            __syncthreads();
+        }
+        if (tid == 0) prm.cand_count[q] = s_base;
+        __syncthreads();
+    }
+}
+// the ordered candidate list as flat arrays (stream index, filtered amplitude[, residual delta chi2])
+__global__ void dp_trig_flatten_kernel(const DpTrigFlattenParams prm) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *prm.n_out = prm.chunk_offset[prm.n_chunks];
+    for (int q = blockIdx.x; q < prm.n_chunks; q += gridDim.x) {
+        const int cnt = prm.cand_count[q];
+        const long long off = prm.chunk_offset[q], row = (long long)q * prm.hop;
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+            const long long g = off + j;
+            if (g >= prm.max_out) break;
+            prm.out_idx[g] = row + prm.cand_idx[row + j];
+            prm.out_amp[g] = prm.cand_amp[row + j];
+            if (prm.out_val) prm.out_val[g] = prm.cand_val ? prm.cand_val[row + j] : prm.cand_amp[row + j] * prm.cand_amp[row + j] * prm.w;
+        }
+    }
+}
+// filtered amplitude iw * oaconvolve(trace, phi_td, 'same')[t] at a handful of stream indices: direct sum, one CTA per index
+// (the residual pass reads the filtered trace at the SHIFTED trigger indices, oftrigger.py:794, which need not be candidates)
+__global__ void __launch_bounds__(256) dp_trig_filtered_at_kernel(const DpTrigAtParams prm) {
+    __shared__ double s_part[8];
+    const int tid = threadIdx.x;
+    for (int b = blockIdx.x; b < prm.n_idx; b += gridDim.x) {
+        const long long t = prm.idx[b];
+        const long long top = t + (prm.nt - 1) / 2;  // sample that meets tap 0
+        double acc = 0.0;
+        for (int k = tid; k < prm.nt; k += 256) {
+            const long long j = top - k;
+            if (j >= 0 && j < prm.n_samples) {
+                double x;
+                if (prm.in_dtype == 0) x = reinterpret_cast<const double*>(prm.trace)[j];
+                else if (prm.in_dtype == 1) x = (double)reinterpret_cast<const float*>(prm.trace)[j];
+                else x = (double)reinterpret_cast<const short*>(prm.trace)[j];
+                acc = fma(x, prm.phi_td[k], acc);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        __syncthreads();
+        if ((tid & 31) == 0) s_part[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int i = 0; i < 8; ++i) s += s_part[i];
+            prm.out[b] = (t >= 0 && t < prm.n_samples) ? prm.iw * s : 0.0;
+        }
     }
 }
 #undef DP_TRIG_OFFSETS

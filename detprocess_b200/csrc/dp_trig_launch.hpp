@@ -7,3 +7,6 @@ int dp_trig_launch_p0(int R1, int in_dtype, const void* prm, int grid, size_t sm
 int dp_trig_launch_p1(int R1, int in_dtype, const void* prm, int grid, size_t smem, void* stream);
 int dp_trig_group_launch(const void* prm, void* stream);
 int dp_trig_group_par_launch(const void* prm, int grid, void* stream);
+int dp_trig_residual_launch(const void* prm, int grid, void* stream);
+int dp_trig_flatten_launch(const void* group_prm, const void* prm, int grid, void* stream);
+int dp_trig_filtered_at_launch(const void* prm, void* stream);

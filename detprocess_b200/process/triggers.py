@@ -124,12 +124,13 @@ class TriggerProcessing:
                     thr = float(td['threshold'])
                 else:
                     raise ValueError('ERROR: "treshold_sigma" missing in yaml configuration file')
-                if td.get('run_residual', False):
-                    raise NotImplementedError('run_residual: True is not built')
+                run_residual = bool(td.get('run_residual', False))      # process/triggers.py:742-751
+                sat_amps = [float(a) for a in td['sat_amps_50kHz']] if run_residual and 'sat_amps_50kHz' in td else None
                 eb.acquire_triggers(trig_chan, self._channel_trace(x, td['channel_name']), thr,
                                     pileup_window_msec=(float(td['pileup_window_msec']) if 'pileup_window_msec' in td else None),
                                     pileup_window_samples=(int(td['pileup_window_samples']) if 'pileup_window_samples' in td else None),
                                     positive_pulses=td.get('positive_pulses', True),
+                                    run_residual=run_residual, sat_amps_50kHz=sat_amps,
                                     edge_exclusion_msec=self._edge_exclusion_msec, livetime=self._livetime)
             if admin is not None:
                 info = copy.deepcopy(admin[ev])

@@ -254,6 +254,29 @@ int dp_trigger_run_raw(dp_trigger_plan* plan, const void* trace_dev, int in_dtyp
                        double* trig_amp_dev, double* trig_dchi2_dev, int max_triggers, int* n_triggers_dev, void* stream);
 int dp_trigger_plan_last_kernel_ms(dp_trigger_plan* plan, float* filter_ms, float* group_ms);
 
+/* Follow-up calls on the candidate list of the last dp_trigger_run(_raw) of the plan (the samples above threshold, ordered by
+ * stream index) -- what OptimumFilterTrigger.find_triggers adds around find_triggers_once (oftrigger.py:682-845):
+ *
+ * dp_trigger_candidates      the list as flat arrays: unshifted stream index, filtered amplitude and (dchi2_dev may be NULL)
+ *                            delta chi2 -- amp^2 w, or the residual delta chi2 once dp_trigger_residual_run has run.
+ *                            *n_candidates_dev = length of the list (only the first max_candidates entries are stored).
+ *                            The dynamic pile-up window (oftrigger.py:78-141, a Python callable per candidate) groups it on the host.
+ * dp_trigger_filtered_at     filtered = iw * oaconvolve(trace, phi_td, 'same') at n_idx arbitrary stream indices (direct sums):
+ *                            the residual pass takes the pulse amplitude at the SHIFTED trigger index (oftrigger.py:794).
+ * dp_trigger_residual_run    the second pass of residual=True (oftrigger.py:772-824): every listed pulse subtracts
+ *                            pulse_amp2[i] * shape[t - pulse_start[i]] (shape = delta chi2 trace of a unit pulse, pulse_start ascending,
+ *                            subtraction in list order) from the candidates it covers; candidates whose residual still exceeds
+ *                            chi2_threshold are kept (the list is compacted in place), grouped by pileup_window_samples and
+ *                            reported like dp_trigger_run (trig_dchi2 = the residual delta chi2 at the arg-max). */
+int dp_trigger_candidates(dp_trigger_plan* plan, long long* idx_dev, double* amp_dev, double* dchi2_dev, long long max_candidates,
+                          long long* n_candidates_dev, void* stream);
+int dp_trigger_filtered_at(dp_trigger_plan* plan, const void* trace_dev, int in_dtype, long long n_samples, const long long* idx_dev,
+                           int n_idx, double* filtered_dev, void* stream);
+int dp_trigger_residual_run(dp_trigger_plan* plan, const long long* pulse_start_dev, const double* pulse_amp2_dev, int n_pulses,
+                            const double* shape_dev, int n_shape, double chi2_threshold, long long pileup_window_samples,
+                            long long index_shift, long long* trig_index_dev, double* trig_amp_dev, double* trig_dchi2_dev,
+                            int max_triggers, int* n_triggers_dev, void* stream);
+
 /* ------------------------------------------------------------------ NxM optimal filter
  * Replaces qp.OFnxm(of_base, channels, template_tag).calc() + get_fit_withdelay(window...) + get_fit_nodelay() as driven
  * per event by FeatureExtractors.ofnxm (reference detprocess/core/algorithms.py:141-274): n channels with an n x n

@@ -71,3 +71,75 @@ def find_triggers_once(dchi2, filtered, thr_chi2, pileup_window, index_shift, fs
             out['trigger_amplitude'].append(filtered[evt_ind])
             out['trigger_delta_chi2'].append(dchi2[evt_ind])
     return {k: np.asarray(v) for k, v in out.items()}
+
+
+def getchangeslessthandynamicthresh(x, amplitudes, threshold_function):
+    """oftrigger.py:78-141: ranges of `x` whose consecutive gaps stay within a window that depends on the largest
+    delta-chi2 met so far in the open range (`threshold_function(max)` -> window in samples)."""
+    start_inds, end_inds = [], []
+    current_start = 0
+    for i in range(1, len(x)):
+        max_amplitude = np.max(amplitudes[current_start:i + 1])
+        if (x[i] - x[i - 1]) > threshold_function(max_amplitude):
+            start_inds.append(current_start)
+            end_inds.append(i)
+            current_start = i
+    start_inds.append(current_start)
+    end_inds.append(len(x))
+    return np.array(list(zip(start_inds, end_inds)))
+
+
+def find_triggers_once_dynamic(dchi2, filtered, thr_chi2, threshold_function, index_shift, fs):
+    """find_triggers_once with dynamic=True (oftrigger.py:975-979): same arg-max per range, dynamic ranges."""
+    mask = dchi2 > thr_chi2
+    triggers = np.where(mask)[0]
+    out = {'trigger_index': [], 'trigger_time': [], 'trigger_amplitude': [], 'trigger_delta_chi2': []}
+    for a, b in getchangeslessthandynamicthresh(triggers, dchi2[mask], threshold_function):
+        if b > a:
+            evt_inds = triggers[a:b]
+            evt_ind = evt_inds[np.argmax(dchi2[evt_inds])]
+            out['trigger_index'].append(evt_ind + index_shift)
+            out['trigger_time'].append((evt_ind + index_shift) / fs)
+            out['trigger_amplitude'].append(filtered[evt_ind])
+            out['trigger_delta_chi2'].append(dchi2[evt_ind])
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
+def residual_delta_chi2(dchi2, filtered, first_pass_index, template, phi_td, iw, w, saturated=None):
+    """oftrigger.py:772-820 for one channel / one amplitude: for every first-pass trigger (their *shifted* indices, as
+    the reference uses them) that is not saturated, the delta-chi2 trace a pulse of the filtered amplitude at that index
+    would produce (template x amplitude -> same FIR -> iw, w) is subtracted, aligned so that its maximum sits on the
+    trigger index.  Returns the residual trace (a copy)."""
+    res = np.array(dchi2, dtype=np.float64)
+    nt = len(template)
+    for k, trigger_index in enumerate(first_pass_index):
+        if saturated is not None and saturated[k]:
+            continue
+        amp = filtered[trigger_index]
+        trigger_trace = np.asarray(template, dtype=np.float64) * amp
+        v_td = oaconvolve(trigger_trace[None, :], np.asarray(phi_td)[None, :], mode='same', axes=-1)[0]
+        f = iw * v_td
+        d = f * w * f
+        j = int(np.argmax(d))
+        res[trigger_index - j:trigger_index - j + nt] -= d
+    return res
+
+
+def saturated_flags(raw_lpf, first_pass_index, nt, saturation_amplitude, positive_pulses=True):
+    """oftrigger.py:776-786: a trigger is saturated when the low-passed raw trace crosses the saturation amplitude
+    within nt/4 samples of it."""
+    flags = []
+    for trigger_index in first_pass_index:
+        seg = raw_lpf[trigger_index - int(nt / 4):trigger_index + int(nt / 4)]
+        if positive_pulses:
+            flags.append(bool(np.sum(seg > saturation_amplitude) > 0))
+        else:
+            flags.append(bool(np.sum(seg < -1 * saturation_amplitude) > 0))
+    return np.asarray(flags, dtype=bool)
+
+
+def combine_triggers(first, second):
+    """combine_trigger_data (oftrigger.py:262-320): the first-pass triggers followed by those second-pass triggers
+    whose index is not among the first-pass indices."""
+    new = ~np.isin(second['trigger_index'], first['trigger_index'])
+    return {k: np.concatenate([np.asarray(first[k]), np.asarray(second[k])[new]]) for k in first}

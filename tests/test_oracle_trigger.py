@@ -58,3 +58,51 @@ def test_injected_pulses_are_found_with_their_amplitude():
         assert np.isclose(out['trigger_delta_chi2'][j], out['trigger_amplitude'][j] ** 2 * norm)
         found += 1
     assert found >= 3
+
+
+def test_dynamic_ranges_product_loop_equals_the_reference_loop():
+    """host logic of dynamic=True: the product's running-maximum loop == the restated reference loop (oftrigger.py:78-141)"""
+    from detprocess_b200.core.oftrigger import _dynamic_ranges
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n = int(rng.integers(0, 400))
+        x = np.cumsum(rng.integers(1, 60, size=n))
+        vals = rng.exponential(50.0, size=n) + 25.0
+        fn = lambda c: 5.0 + 0.5 * c    # noqa: E731
+        a = _dynamic_ranges(x, vals, fn)
+        b = T.getchangeslessthandynamicthresh(x, vals, fn)
+        assert [tuple(r) for r in a] == [tuple(int(v) for v in r) for r in b]
+    # constant window == the static grouping
+    x = np.array([3, 4, 5, 20, 21, 50, 51, 52, 53, 200])
+    assert [tuple(r) for r in _dynamic_ranges(x, np.ones(len(x)), lambda c: 10)] == [(0, 3), (3, 5), (5, 9), (9, 10)]
+
+
+def test_residual_pass_recovers_a_pulse_hidden_in_the_tail_of_a_large_one():
+    n, fs = 4096, 1.25e6
+    template, psd, ofb = _setup(n, fs)
+    phi_td = T.phi_td_from_phi_fd(ofb.phi('c', 'default'))
+    norm = ofb.norm('c', 'default')
+    rng = np.random.default_rng(5)
+    x = make_continuous(100_000, template, psd, fs, rng, pulse_rate_hz=0.0)
+    sig = 1.0 / np.sqrt(norm)
+    t_big, t_small = 40_000, 40_000 + 600
+    x[t_big - n // 2:t_big + n // 2] += 300 * sig * template
+    x[t_small - n // 2:t_small + n // 2] += 60 * sig * template
+    filtered, dchi2 = T.filter_trace(x, phi_td, 1.0 / norm, norm)
+    thr, win = T.chi2_threshold(6.0), 1250
+    first = T.find_triggers_once(dchi2, filtered, thr, win, 0, fs)
+    assert len(first['trigger_index']) == 1 and abs(first['trigger_index'][0] - t_big) <= 1
+    res = T.residual_delta_chi2(dchi2, filtered, first['trigger_index'], template, phi_td, 1.0 / norm, norm)
+    assert np.all(res <= dchi2 + 1e-9 * dchi2.max())        # the subtracted shapes are non-negative
+    second = T.find_triggers_once(res, filtered, thr, win, 0, fs)
+    # the subtraction happens in delta-chi2 space (cross terms of the two pulses stay), so the second pass sees an excess
+    # after the large pulse -- a new trigger in its tail -- not a clean copy of the small pulse
+    new = np.setdiff1d(second['trigger_index'], first['trigger_index'])
+    assert len(new) >= 1 and np.all((new > t_big) & (new < t_big + n // 2))
+    both = T.combine_triggers(first, second)
+    assert len(both['trigger_index']) == 1 + np.sum(~np.isin(second['trigger_index'], first['trigger_index']))
+    # a saturated first-pass trigger is left alone
+    flags = T.saturated_flags(x, first['trigger_index'], n, 100 * sig)
+    assert flags.all()
+    assert np.array_equal(T.residual_delta_chi2(dchi2, filtered, first['trigger_index'], template, phi_td, 1.0 / norm, norm,
+                                                saturated=flags), dchi2)
