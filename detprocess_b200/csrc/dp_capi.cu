@@ -1252,6 +1252,8 @@ int dp_reduce_plan_last_kernel_ms(dp_reduce_plan* p, float* ms) {
 struct dp_psd_plan {
     int v2_r1 = 0;  // != 0: v2 FFT core (dp_psd2_kernel.cuh)
     const void *tw3 = nullptr, *groups = nullptr, *chunk3 = nullptr;
+    void* park1 = nullptr;          // first-pass outputs that do not fit into TMEM (fp64, 65536 samples)
+    long long park1_per_cta = 0;
     int N = 0;
     double fs = 0;
     int precision = DP_PREC_F64;
@@ -1353,6 +1355,7 @@ template <class T, int R1> int psd2_tables(dp_psd_plan* p) {
     const int* dc3;
     if ((rc = upload(p->owned, dt.chunk3, &dc3))) return rc;
     p->chunk3 = dc3;
+    p->park1_per_cta = Dp2Core<T, R1, 0>::CAN_PARK ? Dp2Core<T, R1, 0>::PARK1_V : 0;
     // natural bin k -> slot in one CTA's partial array
     const std::vector<int> loc = dpplan2::partial_slot_of_bin<G>();
     if ((rc = upload(p->owned, loc, &p->loc))) return rc;
@@ -1376,6 +1379,10 @@ template <class T> int psd2_finalize(dp_psd_plan* p) {
     }
     DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->partial), sizeof(double) * (size_t)p->partial_per_cta * (size_t)p->grid_max));
     p->owned.push_back(p->partial);
+    if (p->park1_per_cta > 0) {
+        DP_CUDA(cudaMalloc(&p->park1, 16 * (size_t)p->park1_per_cta * (size_t)p->grid_max));
+        p->owned.push_back(p->park1);
+    }
     DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->count), sizeof(unsigned long long) * (size_t)(p->grid_max + 1)));
     p->owned.push_back(p->count);
     p->count_out = p->count + p->grid_max;
@@ -1484,6 +1491,7 @@ int dp_psd_accumulate(dp_psd_plan* p, const void* traces_dev, int in_dtype, long
             prm.groups = reinterpret_cast<const int2*>(p->groups);
             prm.chunk3 = reinterpret_cast<const int*>(p->chunk3);
             prm.partial = p->partial;
+            prm.park1 = reinterpret_cast<decltype(prm.park1)>(p->park1);
             prm.partial_per_cta = p->partial_per_cta;
             prm.count = p->count;
             prm.scale = p->scale;
@@ -1576,6 +1584,7 @@ struct dp_trigger_plan {
     double* cand_amp = nullptr;
     int* cand_count = nullptr;
     long long* chunk_offset = nullptr;
+    void* park1 = nullptr;        // first-pass outputs that do not fit into TMEM (fp64, F = 65536)
     double* taps_dev = nullptr;   // phi_td on the device (dp_trigger_filtered_at)
     double* cand_val = nullptr;   // residual delta chi2 of the candidates (allocated by the first residual pass)
     int last_chunks = 0;          // chunk count of the last dp_trigger_run (the candidate list the follow-up calls use)
@@ -1704,6 +1713,8 @@ int dp_trigger_plan_create(dp_trigger_plan** plan, const double* phi_td, int nb_
         p->owned.push_back(*ptr);
     };
     alloc(&p->scratch, 16 * (size_t)std::max<long long>(p->scratch_per_cta, 1) * (size_t)std::max(p->grid_max, 1));
+    if (precision == DP_PREC_F64 && p->r1 == 8)   // Dp2Core<double, 8>::PARK1_V: one phase of two blocks
+        alloc(&p->park1, 16 * (size_t)Dp2Core<double, 8, 0>::PARK1_V * (size_t)std::max(p->grid_max, 1));
     alloc(reinterpret_cast<void**>(&p->cand_idx), sizeof(int) * (size_t)p->max_chunks * (size_t)p->hop);
     alloc(reinterpret_cast<void**>(&p->cand_amp), sizeof(double) * (size_t)p->max_chunks * (size_t)p->hop);
     alloc(reinterpret_cast<void**>(&p->cand_count), sizeof(int) * (size_t)p->max_chunks);
@@ -1786,6 +1797,7 @@ int dp_trigger_run_raw(dp_trigger_plan* p, const void* trace_dev, int in_dtype, 
         prm.valid_hi = vhi;
         prm.groups = reinterpret_cast<const int2*>(p->groups);
         prm.chunk3 = reinterpret_cast<const int*>(p->chunk3);
+        prm.park1 = reinterpret_cast<decltype(prm.park1)>(p->park1);
         prm.scratch_per_cta = p->scratch_per_cta;
         prm.w = p->w;
         prm.thr = chi2_threshold;

@@ -507,6 +507,50 @@ static __constant__ double dp2_w16_tab[16][2] = {
     {0.70710678118654752440, -0.70710678118654752440},
     {0.92387953251128675613, -0.38268343236508977173}};
 
+// ---- tensor memory as a thread-private parking space (fp64 kernels whose transform is split into phases).
+// Every phase of the split transform needs ALL samples of the trace for its radix-8 first pass; round 1 re-read the trace
+// in every phase (4 x 512 KB through the SM's L2 port: 45 % of the kernel waiting on those loads, profiles/
+// r2_prof_psd2_f64_64k_before.txt).  The first pass of a column is thread-private -- thread t handles columns t + i NT
+// in every phase -- so phase 0 computes all eight outputs of its columns once, keeps its own two blocks in shared memory
+// and parks the two blocks of each of the next two phases in TMEM: 256 KB per SM that this kernel (no tensor-core work)
+// would otherwise leave idle, written at 256 B/clk and read back at 64 B/clk with ~12 clk latency.  A warp reaches the
+// 32 lanes of its quarter (warp % 4); the four warps of a quarter take 128 columns each = 32 cx<double> per thread =
+// 2 phases x 8 columns x 2 blocks.  The last phase (TMEM is full) still reads the trace.
+#if !defined(DP_HOST_EMU)
+DP_DEV void dp_tmem_alloc512(unsigned* smem_slot) {  // one whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((unsigned)__cvta_generic_to_shared(smem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+DP_DEV void dp_tmem_dealloc512(unsigned addr) {      // one whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+}
+DP_DEV void dp_tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DP_DEV void dp_tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+DP_DEV void dp_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+DP_DEV void dp_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// two complex doubles (8 x 32 bit) of this thread's lane at column `addr`
+DP_DEV void dp_tmem_st2(unsigned addr, const cx<double>& a, const cx<double>& b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr),
+                 "r"(__double2loint(a.re)), "r"(__double2hiint(a.re)), "r"(__double2loint(a.im)), "r"(__double2hiint(a.im)),
+                 "r"(__double2loint(b.re)), "r"(__double2hiint(b.re)), "r"(__double2loint(b.im)), "r"(__double2hiint(b.im))
+                 : "memory");
+}
+// the load is asynchronous: dp_tmem_wait_ld() before the first use of the registers
+struct DpTmemRaw8 { int r[8]; };
+DP_DEV DpTmemRaw8 dp_tmem_ld8(unsigned addr) {
+    DpTmemRaw8 t;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(t.r[0]), "=r"(t.r[1]), "=r"(t.r[2]), "=r"(t.r[3]), "=r"(t.r[4]), "=r"(t.r[5]), "=r"(t.r[6]), "=r"(t.r[7])
+                 : "r"(addr)
+                 : "memory");
+    return t;
+}
+DP_DEV cx<double> dp_tmem_cx(const DpTmemRaw8& t, int j) {
+    return cx<double>{__hiloint2double(t.r[4 * j + 1], t.r[4 * j]), __hiloint2double(t.r[4 * j + 3], t.r[4 * j + 2])};
+}
+#endif
+
+
 // ======================================================================== core
 template <class T, int R1, int IN> struct Dp2Core {
     using G = Dp2Geom<T, R1>;
@@ -588,6 +632,109 @@ template <class T, int R1, int IN> struct Dp2Core {
                 default: pass1<3, CLAMP>(row, x0, sc, buf, tw1, jbase, jmax); break;
             }
         }
+    }
+
+    // ---- first pass computed ONCE per event (fp64, multi-phase geometries): thread t handles the same columns t + i NT in
+    // every phase, so phase 0 runs the radix-R1 butterfly of its columns, keeps its own blocks in shared memory and parks
+    // the blocks of the later phases where the thread finds them again: phases 1 .. TM_PHASES in its TMEM columns
+    // [((ph-1) * NC + i) * 4 NB, +4 NB), a further phase (R1 = 8: phase 3) in an L2-resident scratch row of the CTA.
+    // tm = this thread's TMEM address (dp_tmem_thread_base).  Replaces NPH reads of the trace + NPH butterflies by one.
+    static constexpr bool CAN_PARK = (VL == 1) && (NPH > 1) && (NT == 512) && (NB == 2);
+    static constexpr int TM_PHASES = (NPH - 1) < 128 / (4 * NB * NC) ? (NPH - 1) : 128 / (4 * NB * NC);  // phases parked in TMEM
+    static constexpr int TM_COLS = TM_PHASES * NC * NB * 4;             // TMEM columns used per thread (of 128)
+    static constexpr long long PARK1_V = (NPH - 1 - TM_PHASES) > 0 ? (long long)(NPH - 1 - TM_PHASES) * NB * VPB : 0;
+    template <bool CLAMP = false>
+    static DP_DEV void pass1_all(const void* row, double x0, double sc, V* buf, const V* DP_RESTRICT tw1, unsigned tm, V* park,
+                                 long long jbase = 0, long long jmax = 0) {
+#ifndef DP_HOST_EMU
+        if constexpr (CAN_PARK) {
+            const int tid = threadIdx.x;
+            const unsigned long long pol = dp2_policy_stream(true);  // the trace's only read
+            [[maybe_unused]] const unsigned long long keep = dp2_policy_keep();
+            constexpr int CBW = 16 / R1;
+            constexpr int CB = CBW < 1 ? 1 : (CBW > NC ? NC : CBW);
+#pragma unroll
+            for (int i0 = 0; i0 < NC; i0 += CB) {
+                Dp2Raw<IN, VL> raw[CB][R1];
+#pragma unroll
+                for (int i = 0; i < CB; ++i)
+#pragma unroll
+                    for (int n = 0; n < R1; ++n)
+                        raw[i][n] = CLAMP ? dp2_load_raw_clamped<IN, VL>(row, jbase, jmax, n, tid + (i0 + i) * NT, pol)
+                                          : dp2_load_raw<IN, VL>(row, n, tid + (i0 + i) * NT, pol);
+#pragma unroll
+                for (int i = 0; i < CB; ++i) {
+                    const int c = tid + (i0 + i) * NT;
+                    V v[R1];
+#pragma unroll
+                    for (int n = 0; n < R1; ++n) v[n] = dp2_convert<IN>(raw[i][n], x0, sc);
+                    dp_dft<R1, -1, T>::run(v);
+                    V pw[R1];
+                    dp2_powers<R1, T>(dp_ldg(tw1 + c), pw);
+#pragma unroll
+                    for (int ph = 0; ph < NPH; ++ph) {
+                        V o[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            const int k1 = G::k1_of(ph, b);
+                            o[b] = (k1 == 0) ? v[k1] : cmul(v[k1], pw[k1]);
+                        }
+                        if (ph == 0) {
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) buf[G::phys(c) + b * PB] = o[b];
+                        } else if (ph <= TM_PHASES) {
+                            dp_tmem_st2(tm + (unsigned)(((ph - 1) * NC + (i0 + i)) * 8), o[0], o[1]);
+                        } else {
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) dp2_st_keep(park + (long long)((ph - 1 - TM_PHASES) * NB + b) * VPB + c, o[b], keep);
+                        }
+                    }
+                }
+            }
+            dp_tmem_wait_st();
+        }
+#endif
+    }
+    // phase p >= 1: the parked first-pass outputs -> shared memory
+    static DP_DEV void pass1_fetch(int p, V* buf, unsigned tm, const V* park) {
+#ifndef DP_HOST_EMU
+        if constexpr (CAN_PARK) {
+            const int tid = threadIdx.x;
+            if (p <= TM_PHASES) {
+                constexpr int LB = NC < 4 ? NC : 4;  // loads in flight before one wait (32 registers)
+#pragma unroll
+                for (int i0 = 0; i0 < NC; i0 += LB) {
+                    DpTmemRaw8 t[LB];
+#pragma unroll
+                    for (int i = 0; i < LB; ++i) t[i] = dp_tmem_ld8(tm + (unsigned)(((p - 1) * NC + i0 + i) * 8));
+                    dp_tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < LB; ++i) {
+                        const int c = tid + (i0 + i) * NT;
+                        buf[G::phys(c)] = dp_tmem_cx(t[i], 0);
+                        buf[G::phys(c) + PB] = dp_tmem_cx(t[i], 1);
+                    }
+                }
+            } else {
+                const unsigned long long keep = dp2_policy_keep();
+                const V* src = park + (long long)(p - 1 - TM_PHASES) * NB * VPB;
+                V t[NC * NB];
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) t[i * NB + b] = dp2_ld_keep(src + (long long)b * VPB + tid + i * NT, keep);
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) buf[G::phys(tid + i * NT) + b * PB] = t[i * NB + b];
+            }
+        }
+#endif
+    }
+    // TMEM address of this thread's 128 private columns: the warp's lane quarter, one column range per warp of the quarter
+    static DP_DEV unsigned tm_thread_base(unsigned tm_base) {
+        const int warp = threadIdx.x >> 5;
+        return tm_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(128 * (warp >> 2));
     }
 
     // ---- passes 2..4 (caller has synchronised after pass 1); result: pass-4 outputs of the
@@ -1024,12 +1171,22 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
     static_assert(sizeof(T) == 8 && sizeof(V) == 16, "table rows are 256 / 512 bytes per warp");
     static constexpr size_t SMEM_BYTES = sizeof(V) * G::SMEM_V + sizeof(cx<S>) * (DP_NLOW_MAX + SP_ELEMS) +
                                          2 * (sizeof(double) * RED_DOUBLES + sizeof(DpBest<S>) * BEST_ELEMS + sizeof(int) * DP_MAX_TSLOTS) +
-                                         2 * sizeof(int) * CH_WORDS + 64 + sizeof(double) * 4 * DP_MAX_TSLOTS + (size_t)NW * NSP * DP2_PIECE + sizeof(Dp2Mbar) * NW + 16;
+                                         2 * sizeof(int) * CH_WORDS + 64 + sizeof(double) * 4 * DP_MAX_TSLOTS + (size_t)NW * NSP * DP2_PIECE + sizeof(Dp2Mbar) * NW + 16 + 16;
     // scratch per CTA (V units): X spill [NW][16][32] (multi-template; warp-sliced so that a warp's column is one
     // contiguous 8 KB block) + per template the parked block results of the non-final phases [(NPH-1)*NB][VPB]
     static constexpr long long SCR_X = (long long)16 * NT;
     static constexpr long long SCR_PARK = (long long)(NPH - 1) * NB * VPB;
-    static DP_HD long long scratch_v(int n_templ) { return SCR_X + SCR_PARK * n_templ; }
+    // (+ the first-pass outputs of the phase that does not fit into TMEM, Dp2Core::PARK1_V, in front)
+#ifndef DP_OF_TMEM
+#ifdef DP_HOST_EMU
+#define DP_OF_TMEM 0   // the host-thread emulator has no tensor memory: it runs the per-phase first pass
+#else
+#define DP_OF_TMEM 1
+#endif
+#endif
+    static constexpr bool TM = DP_OF_TMEM && Core::CAN_PARK;   // fp64, split transform: first pass computed once (pass1_all)
+    static constexpr long long SCR_1 = TM ? Core::PARK1_V : 0;
+    static DP_HD long long scratch_v(int n_templ) { return SCR_1 + SCR_X + SCR_PARK * n_templ; }
     // first element of warp w's rows in a thread-order table [NPH][NW][16][32]
     static DP_HD long long tab_block(int p, int w) { return ((long long)(p * NW + w) * 16) * 32; }
 
@@ -1341,7 +1498,8 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
     const Smem sm = carve(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr size_t ESZ = sizeof(typename DpRaw<IN>::scalar);
-    V* scr_x = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;  // [NW][16][32] X of the current phase (multi-template)
+    [[maybe_unused]] V* const scr_1 = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;  // first-pass outputs parked in L2 (R1 = 8)
+    V* scr_x = scr_1 + SCR_1;                                              // [NW][16][32] X of the current phase (multi-template)
     V* scr_park = scr_x + SCR_X;                                           // [n_templ][(NPH-1)*NB][VPB] parked block results
     V* const xs = scr_x + (long long)warp * 16 * 32 + lane;                // this lane's X column (rows 32 apart)
     // special threads: the self-paired groups (0,0,0) and (0,0,8) of block 0 (phase 0)
@@ -1357,7 +1515,21 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
     unsigned spar = 0;  // parity of the warp's next staging round
     if (lane == 0) dp2_mbar_init(bar);
     dp2_mbar_init_fence();
+    [[maybe_unused]] unsigned* const tmslot = reinterpret_cast<unsigned*>(sm.mbar + NW);
+    [[maybe_unused]] unsigned tm_thread = 0;  // this thread's 128 private TMEM columns
+#ifndef DP_HOST_EMU
+    if constexpr (TM) {
+        if (warp == 0) dp_tmem_alloc512(tmslot);
+        dp_tmem_fence_before();
+    }
+#endif
     __syncthreads();
+#ifndef DP_HOST_EMU
+    if constexpr (TM) {
+        dp_tmem_fence_after();
+        tm_thread = Core::tm_thread_base(*tmslot);
+    }
+#endif
 
     for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
         const int chan = row % prm.n_chan;
@@ -1400,7 +1572,15 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             const int chunk = prm.chunk3[p * NT + tid];
             const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
             const bool special = (p == 0) && (tid < NSPECIAL);
-            Core::pass1_any(p, xrow, x0, xsc, sm.buf, prm.tw1);
+            if constexpr (TM) {
+                // the trace is read once: phase 0 computes the first pass of all blocks, the later phases find theirs in TMEM / L2
+                if (p == 0)
+                    Core::pass1_all(xrow, x0, xsc, sm.buf, prm.tw1, tm_thread, scr_1);
+                else
+                    Core::pass1_fetch(p, sm.buf, tm_thread, scr_1);
+            } else {
+                Core::pass1_any(p, xrow, x0, xsc, sm.buf, prm.tw1);
+            }
             __syncthreads();
 #ifndef DP_HOST_EMU
             // every second block starts its passes a little late so that the block sets' LDS / FP / STS phases
@@ -1812,6 +1992,14 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
             }
         }
     }
+#ifndef DP_HOST_EMU
+    if constexpr (TM) {
+        dp_tmem_fence_before();
+        __syncthreads();
+        dp_tmem_fence_after();
+        if (warp == 0) dp_tmem_dealloc512(*tmslot);
+    }
+#endif
 }
 
 #ifndef DP_HOST_EMU

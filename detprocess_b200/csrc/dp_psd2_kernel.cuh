@@ -16,6 +16,13 @@
 #ifndef DP_PSD_V3
 #define DP_PSD_V3 1
 #endif
+// DP_PSD_TMEM (round 2, fp64 at 32768 / 65536 samples): the first pass of every column is computed once per trace; the later
+// phases find their blocks in tensor memory (and, at 65536 samples, the last phase in an L2-resident row) instead of reading
+// the whole trace again -- Dp2Core::pass1_all / pass1_fetch.  Round 1 read the trace in every phase: 4 x 512 KB through the
+// SM's L2 port at 65536 samples, 45 % of the kernel's samples waiting on those loads (profiles/r2_prof_psd2_f64_64k_before.txt).
+#ifndef DP_PSD_TMEM
+#define DP_PSD_TMEM 1
+#endif
 
 #if !defined(DP_HOST_EMU)
 DP_DEV void dp_psd_acc(double* slot, double v) {
@@ -29,6 +36,7 @@ DP_DEV void dp_psd_acc(double* slot, double v) {
 static inline void dp_psd_acc(double* slot, double v) { *slot += v; }
 #endif
 
+
 template <class T> struct DpPsd2Params {
     using S = typename Dp2Traits<T>::S;
     const void* traces;
@@ -40,6 +48,7 @@ template <class T> struct DpPsd2Params {
     const cx<T>* tw3;
     const cx<S>* twn;
     const int2* groups;
+    cx<T>* park1;               // [grid][Dp2Core::PARK1_V] first-pass outputs that do not fit into TMEM (L2 resident)
     const int* chunk3;          // [NPH][NT] pass-3 chunk of the thread (warp-local passes, dpplan2::build_chunks)
     double* partial;            // [grid][partial_per_cta]: [NPH][16][NT][VL] thread order, then [17][2] self lanes
     long long partial_per_cta;
@@ -68,6 +77,18 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
         double* part_self = part + (long long)NPH * 16 * NT * VL;
         const double inv_s2 = 1.0 / (4.0 * prm.scale * prm.scale);  // kernel values are 2*scale*X
         unsigned long long n_acc = 0;
+        [[maybe_unused]] V* const park1 = prm.park1 + (long long)blockIdx.x * Core::PARK1_V;  // first-pass outputs of the last phase
+        // fp64 at 65536 samples: the first pass of phases 1 and 2 comes out of tensor memory (see above)
+        constexpr bool TM = DP_PSD_TMEM && Core::CAN_PARK;
+        [[maybe_unused]] unsigned tm_thread = 0;  // this thread's TMEM address: lane quarter of the warp, 128 columns of its own
+        if constexpr (TM) {
+            unsigned* slot = reinterpret_cast<unsigned*>(sp + 32);
+            if (tid < 32) dp_tmem_alloc512(slot);
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            tm_thread = Core::tm_thread_base(*slot);
+        }
 
         for (int row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
             if (prm.mask != nullptr && prm.mask[row] == 0) continue;  // CTA-uniform
@@ -81,7 +102,14 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
                 const int2 gg = prm.groups[p * NT + tid];
                 const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
                 const bool special = (p == 0) && (tid < NSPECIAL);
-                Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
+                if constexpr (TM) {
+                    if (p == 0)
+                        Core::pass1_all(xrow, x0, prm.scale, buf, prm.tw1, tm_thread, park1);
+                    else
+                        Core::pass1_fetch(p, buf, tm_thread, park1);
+                } else {
+                    Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
+                }
                 __syncthreads();
 #ifndef DP_HOST_EMU
                 if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);  // see dp_of2_kernel.cuh
@@ -135,15 +163,11 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
                             const f2 pw = cnorm2(z[r]);
-#if DP_PSD_V3
-                            dp_psd_acc(&dst[r * NT].x, (double)pw.x * inv_s2);
-                            dp_psd_acc(&dst[r * NT].y, (double)pw.y * inv_s2);
-#else
+                            // (one 16-byte load / store per pair of bins; two 8-byte reductions each were slower: -5 %)
                             double2 a = dst[r * NT];
                             a.x += (double)pw.x * inv_s2;
                             a.y += (double)pw.y * inv_s2;
                             dst[r * NT] = a;
-#endif
                         }
                     }
                 } else {
@@ -161,6 +185,12 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
             }
         }
         if (tid == 0) prm.count[blockIdx.x] += n_acc;
+        if constexpr (TM) {
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            if (tid < 32) dp_tmem_dealloc512(*reinterpret_cast<unsigned*>(sp + 32));
+        }
     }
 };
 

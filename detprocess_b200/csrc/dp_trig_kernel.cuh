@@ -27,6 +27,11 @@
 #ifndef DP_TRIG_V3
 #define DP_TRIG_V3 1
 #endif
+// DP_TRIG_TMEM (round 2, fp64): the first pass of a chunk is computed once; the later phases take their blocks from tensor
+// memory / the CTA's L2-resident row (Dp2Core::pass1_all / pass1_fetch) instead of reading the chunk's samples in every phase.
+#ifndef DP_TRIG_TMEM
+#define DP_TRIG_TMEM 1
+#endif
 
 template <class T> struct DpTrigParams {
     using S = typename Dp2Traits<T>::S;
@@ -42,6 +47,7 @@ template <class T> struct DpTrigParams {
     const cx<S>* twn;
     const int2* groups;
     const int* chunk3;      // [NPH][NT] pass-3 chunk of the thread (warp-local passes)
+    cx<T>* park1;           // [grid][Dp2Core::PARK1_V] first-pass outputs that do not fit into TMEM
     const cx<T>* phi;       // [NPH][16][NT] filter spectrum, thread order
     const cx<S>* phi_self;  // [17][2]
     cx<T>* scratch;         // [grid][(NPH-1)*NB*VPB] parked block results
@@ -97,6 +103,17 @@ template <class T, int R1, int IN> struct DpTrigKernel {
         V* park = prm.scratch + (long long)blockIdx.x * prm.scratch_per_cta;
         const S wS = (S)prm.w, thrS = (S)prm.thr;
         const long long jmax = prm.n_samples;  // the clamped loader bounds by the sample count
+        constexpr bool TM = DP_TRIG_TMEM && Core::CAN_PARK;
+        [[maybe_unused]] unsigned tm_thread = 0;
+        [[maybe_unused]] V* const park1 = prm.park1 + (long long)blockIdx.x * Core::PARK1_V;
+        if constexpr (TM) {
+            unsigned* slot = wsum + 48;
+            if (tid < 32) dp_tmem_alloc512(slot);
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            tm_thread = Core::tm_thread_base(*slot);
+        }
 
         for (int q = blockIdx.x; q < prm.n_chunks; q += gridDim.x) {
             const long long s0 = (long long)q * prm.hop - prm.lead;  // first sample of the chunk (even)
@@ -115,7 +132,14 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                 const int2 gg = prm.groups[p * NT + tid];
                 const cx<S> wn = dp_ldg(prm.twn + p * NT + tid);
                 const bool special = (p == 0) && (tid < NSPECIAL);
-                if (edge)
+                if constexpr (TM) {
+                    if (p > 0)
+                        Core::pass1_fetch(p, buf, tm_thread, park1);
+                    else if (edge)
+                        Core::template pass1_all<true>(prm.trace, x0, prm.scale, buf, prm.tw1, tm_thread, park1, jbase, jmax);
+                    else
+                        Core::template pass1_all<false>(xrow, x0, prm.scale, buf, prm.tw1, tm_thread, park1);
+                } else if (edge)
                     Core::template pass1_any<true>(p, prm.trace, x0, prm.scale, buf, prm.tw1, jbase, jmax);
                 else
                     Core::template pass1_any<false>(p, xrow, x0, prm.scale, buf, prm.tw1);
@@ -288,6 +312,12 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                 }
             }
             __syncthreads();  // mask / buf are rewritten by the next chunk
+        }
+        if constexpr (TM) {
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            if (tid < 32) dp_tmem_dealloc512(*(wsum + 48));
         }
     }
 };

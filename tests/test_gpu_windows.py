@@ -63,3 +63,30 @@ def test_trigger_then_features_on_device():
     d = feats[ok, off + 1] - S.nb_pretrigger
     assert np.max(np.abs(d)) <= 3
     assert np.allclose(feats[ok, off], amp.cpu().numpy()[ok], rtol=0.05)
+
+
+@pytest.mark.parametrize('n,prec', [(16384, 'f64'), (32768, 'f32')])
+def test_windows_against_the_oracle_directly(n, prec):
+    """window mode meets the CPU oracle itself (not only the gathered GPU batch): odd and even starts, both stream ends,
+    and the sentinel rows of windows that leave the stream"""
+    from oracle.of1x1 import of1x1_batch
+    S = SynthSetup(n)
+    pre = S.nb_pretrigger
+    L = 9 * n + 3
+    x = make_continuous(L, S.template, S.psd, S.fs, np.random.default_rng(14), pulse_rate_hz=400.0, offset=-2e-7)
+    starts = np.array([0, 1, 2, 12345, 12346, 3 * n + 77, L - n - 1, L - n, -1, L - n + 1, L + 5])
+    good = (starts >= 0) & (starts + n <= L)
+    plan = _plan(S, prec, two_templates=True)
+    out = plan.run_windows(torch.from_numpy(x).cuda(), torch.from_numpy(starts).cuda()).cpu().numpy()
+    assert np.all(out[~good] == -999999.0)
+    traces = np.stack([x[s:s + n] for s in starts[good]])
+    tol_amp, tol_chi = (1e-9, 1e-9) if prec == 'f64' else (1e-5, 1e-4)
+    wins = [(pre - 500, pre + 500, False), (None, None, False)]
+    for templ, fits in ((S.template, (0, 1)), (S.template_glitch, (2,))):
+        o = of1x1_batch(traces, templ, S.psd, S.fs, pre, windows=wins[:len(fits)])
+        for iw, f in enumerate(fits):
+            off = plan.fit_offset(0, f)
+            g = out[good]
+            assert np.array_equal(g[:, off + 1].astype(np.int64), o['ind'][iw])
+            assert np.max(np.abs(g[:, off] - o['amp'][iw]) / np.maximum(np.abs(o['amp'][iw]), 5 * o['ampres'])) < tol_amp
+            assert np.max(np.abs(g[:, off + 2] / o['chi2'][iw] - 1)) < tol_chi
