@@ -1186,6 +1186,15 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
 #endif
     static constexpr bool TM = DP_OF_TMEM && Core::CAN_PARK;   // fp64, split transform: first pass computed once (pass1_all)
     static constexpr long long SCR_1 = TM ? Core::PARK1_V : 0;
+    // multi-template plans, fp64: the thread's X column (16 values) lives in the TMEM columns the first pass leaves free, and
+    // the rows the X column used to be copied back into take the next template's 16 filter rows instead (round 2: X went
+    // to an L2 scratch column by 16-byte stores, came back by bulk copy behind a proxy fence, and the filter rows of the
+    // second template were read through L2 when they were used)
+#ifndef DP_OF_TMX
+#define DP_OF_TMX 1
+#endif
+    static constexpr bool TMX = DP_OF_TMX && TM && STAGE && (Core::TM_COLS + 64 <= 128);
+    static constexpr unsigned XCOL = Core::TM_COLS;
     static DP_HD long long scratch_v(int n_templ) { return SCR_1 + SCR_X + SCR_PARK * n_templ; }
     // first element of warp w's rows in a thread-order table [NPH][NW][16][32]
     static DP_HD long long tab_block(int p, int w) { return ((long long)(p * NW + w) * 16) * 32; }
@@ -1670,12 +1679,21 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         chin = dp_fma(tb.wj(2 * r + 1), cnorm2(Xm), chin);
                         if (r == 0 && stash0) sm.stash[kA] = Xk;
                         if constexpr (MULTI) {
-                            dp2_st_keep(xs + (2 * r) * 32, Xk, pol);
-                            dp2_st_keep(xs + (2 * r + 1) * 32, Xm, pol);
+                            if constexpr (TMX) {
+#ifndef DP_HOST_EMU
+                                dp_tmem_st2(tm_thread + XCOL + 8 * r, Xk, Xm);
+#endif
+                            } else {
+                                dp2_st_keep(xs + (2 * r) * 32, Xk, pol);
+                                dp2_st_keep(xs + (2 * r + 1) * 32, Xm, pol);
+                            }
                         }
                         pair_filter(z, r, Xk, Xm, tb.phi_a(2 * r), tb.phi_a(2 * r + 1), w);
                     }
                     if (!special) chi += chin;
+#ifndef DP_HOST_EMU
+                    if constexpr (MULTI && TMX) dp_tmem_wait_st();  // the X column is read back for the next template
+#endif
                 }
             }
             __syncwarp();  // every lane is done with the staged tables before the rows take the pass-4' group values
@@ -1752,10 +1770,10 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         Core::inv_2(sm.buf, prm.tw2, z);
                         Core::park_pass2(park, p, z, rowmask);
                     }
-                    if (STAGE && MULTI && it == 0) dp2_fence_async();  // the X column (stored long ago: cheap by now) is read back by bulk copy
+                    if (STAGE && MULTI && it == 0 && !TMX) dp2_fence_async();  // the X column (stored long ago: cheap by now) is read back by bulk copy
                     __syncthreads();  // pass-2' reads of buf precede the next group / pass-1 stores
                     if (STAGE && more && lane == 0)
-                        issue_b(bar, bufb, prm.zones[p * NW + warp], spw, scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
+                        issue_b(bar, bufb, prm.zones[p * NW + warp], spw, TMX ? ch.templ[it + 1].phi + tab_block(p, warp) : scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
                 } else {
                     // ------------ last phase: pass 1' over all blocks, arg-max, outputs --------------
                     if (few_rows) {
@@ -1764,7 +1782,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         Core::inv_2(sm.buf, prm.tw2, z);
                         Core::store_pass2(sm.buf, z, rowmask);
                     }
-                    if (STAGE && MULTI && it == 0) dp2_fence_async();
+                    if (STAGE && MULTI && it == 0 && !TMX) dp2_fence_async();
                     __syncthreads();  // also orders the parked block results (global memory) within the CTA
                     DpBest<S> tb[DP_MAX_TSLOTS];
 #pragma unroll
@@ -1880,7 +1898,7 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                     }
                     // the FFT buffer is free: the next template's X column and filter rows land while the outputs are formed
                     if (STAGE && more && lane == 0)
-                        issue_b(bar, bufb, prm.zones[p * NW + warp], spw, scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
+                        issue_b(bar, bufb, prm.zones[p * NW + warp], spw, TMX ? ch.templ[it + 1].phi + tab_block(p, warp) : scr_x + (long long)warp * 16 * 32, ch.templ[it + 1].phi + tab_block(p, warp));
                     // ---- low-frequency chi2 at each fit's (amp, delay); chi0; outputs ----------------
                     double part[DP_MAX_TSLOTS + 1];
 #pragma unroll
@@ -1981,10 +1999,29 @@ DP_DEV void Dp2OfKernel<T, R1, IN>::run(const Dp2Params<T>& prm, unsigned char* 
                         // first template's round kept all eight of them alive across the inverse passes (14 spilled doubles)
                         asm volatile("" : "+d"(wn2.re), "+d"(wn2.im));
 #endif
+                        if constexpr (TMX) {
+#ifndef DP_HOST_EMU
+                            // X pairs out of TMEM, four at a time; the staged rows hold this template's filter
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                DpTmemRaw8 xr[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) xr[j] = dp_tmem_ld8(tm_thread + XCOL + 8 * (4 * h + j));
+                                dp_tmem_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int r = 4 * h + j;
+                                    const cx<S> w = cmul(wn2, dp_w64_rt<S>(2 * r));
+                                    pair_filter(z, r, dp_tmem_cx(xr[j], 0), dp_tmem_cx(xr[j], 1), tb.x(2 * r), tb.x(2 * r + 1), w);
+                                }
+                            }
+#endif
+                        } else {
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
                             const cx<S> w = cmul(wn2, dp_w64_rt<S>(2 * r));
                             pair_filter(z, r, tb.x(2 * r), tb.x(2 * r + 1), tb.phi_b(2 * r), tb.phi_b(2 * r + 1), w);
+                        }
                         }
                     }
                 }
