@@ -660,7 +660,7 @@ def gpu_main(a):
     summ = ncu_summary('r2_ncu_of2_f64_c2.json')
     roofline = {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': r['achieved_gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                'kernel': 'dp_of2_kernel<double,4,0,true>', 'kernel_ms': r['kernel_ms'],
+                'kernel': 'dp_of2_kernel<double,4,0,true,true>', 'kernel_ms': r['kernel_ms'],
                 'algorithmic_bytes_per_event': BYTES_PER_EVENT,
                 'note': 'the FFT path is FP64-issue / latency bound, not HBM bound (10 FLOP/B): fp_issue_frac is the share '
                         'of the launch the FP64 instructions alone need at the measured pipe rates (DESIGN.md 4.1)'}
@@ -695,7 +695,7 @@ def gpu_main(a):
         summ32 = ncu_summary('r2_ncu_of2_f32_c2.json')
         line['fast_mode'] = {'dtype': 'f32', 'value': f['value'], 'unit': UNIT, 'ms_per_step': f['ms_per_step'],
                              'roofline_frac': f['achieved_gbs'] / hbm_peak, 'achieved_gbs': f['achieved_gbs'],
-                             'kernel': 'dp_of2_kernel<f2,4,0,true>', 'e2e': f['e2e']['value'],
+                             'kernel': 'dp_of2_kernel<f2,4,0,true,true>', 'e2e': f['e2e']['value'],
                              'e2e_f64_host': f['e2e_f64']['value'],
                              'traffic': (summ32['dram_bytes_per_event'] * B) if summ32 else None,
                              'tolerance': 'amp 1e-5, chi2 1e-4 rel vs float64 oracle'}

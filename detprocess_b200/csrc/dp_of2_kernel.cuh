@@ -528,11 +528,20 @@ DP_DEV void dp_tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_
 DP_DEV void dp_tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 DP_DEV void dp_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 DP_DEV void dp_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// two complex doubles (8 x 32 bit) of this thread's lane at column `addr`
-DP_DEV void dp_tmem_st2(unsigned addr, const cx<double>& a, const cx<double>& b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr),
-                 "r"(__double2loint(a.re)), "r"(__double2hiint(a.re)), "r"(__double2loint(a.im)), "r"(__double2hiint(a.im)),
-                 "r"(__double2loint(b.re)), "r"(__double2hiint(b.re)), "r"(__double2loint(b.im)), "r"(__double2hiint(b.im))
+// one register vector V (cx<double> or packed cx<f2>: 16 bytes) <-> four 32-bit TMEM columns
+DP_DEV void dp_tmem_words(const cx<double>& a, int (&w)[4]) {
+    w[0] = __double2loint(a.re), w[1] = __double2hiint(a.re), w[2] = __double2loint(a.im), w[3] = __double2hiint(a.im);
+}
+DP_DEV void dp_tmem_words(const cx<f2>& a, int (&w)[4]) {
+    w[0] = __float_as_int(a.re.x), w[1] = __float_as_int(a.re.y), w[2] = __float_as_int(a.im.x), w[3] = __float_as_int(a.im.y);
+}
+// two vectors (8 x 32 bit) of this thread's lane at column `addr`
+template <class V> DP_DEV void dp_tmem_st2(unsigned addr, const V& a, const V& b) {
+    int x[4], y[4];
+    dp_tmem_words(a, x);
+    dp_tmem_words(b, y);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(x[0]), "r"(x[1]), "r"(x[2]),
+                 "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3])
                  : "memory");
 }
 // the load is asynchronous: dp_tmem_wait_ld() before the first use of the registers
@@ -547,6 +556,11 @@ DP_DEV DpTmemRaw8 dp_tmem_ld8(unsigned addr) {
 }
 DP_DEV cx<double> dp_tmem_cx(const DpTmemRaw8& t, int j) {
     return cx<double>{__hiloint2double(t.r[4 * j + 1], t.r[4 * j]), __hiloint2double(t.r[4 * j + 3], t.r[4 * j + 2])};
+}
+template <class V> DP_DEV V dp_tmem_get(const DpTmemRaw8& t, int j);
+template <> DP_DEV cx<double> dp_tmem_get<cx<double>>(const DpTmemRaw8& t, int j) { return dp_tmem_cx(t, j); }
+template <> DP_DEV cx<f2> dp_tmem_get<cx<f2>>(const DpTmemRaw8& t, int j) {
+    return cx<f2>{f2(__int_as_float(t.r[4 * j]), __int_as_float(t.r[4 * j + 1])), f2(__int_as_float(t.r[4 * j + 2]), __int_as_float(t.r[4 * j + 3]))};
 }
 #endif
 
@@ -639,7 +653,7 @@ template <class T, int R1, int IN> struct Dp2Core {
     // the blocks of the later phases where the thread finds them again: phases 1 .. TM_PHASES in its TMEM columns
     // [((ph-1) * NC + i) * 4 NB, +4 NB), a further phase (R1 = 8: phase 3) in an L2-resident scratch row of the CTA.
     // tm = this thread's TMEM address (dp_tmem_thread_base).  Replaces NPH reads of the trace + NPH butterflies by one.
-    static constexpr bool CAN_PARK = (VL == 1) && (NPH > 1) && (NT == 512) && (NB == 2);
+    static constexpr bool CAN_PARK = (NPH > 1) && (NT == 512) && (NB % 2 == 0);   // fp64 at 32768 / 65536, packed fp32 at 65536 samples
     static constexpr int TM_PHASES = (NPH - 1) < 128 / (4 * NB * NC) ? (NPH - 1) : 128 / (4 * NB * NC);  // phases parked in TMEM
     static constexpr int TM_COLS = TM_PHASES * NC * NB * 4;             // TMEM columns used per thread (of 128)
     static constexpr long long PARK1_V = (NPH - 1 - TM_PHASES) > 0 ? (long long)(NPH - 1 - TM_PHASES) * NB * VPB : 0;
@@ -651,7 +665,7 @@ template <class T, int R1, int IN> struct Dp2Core {
             const int tid = threadIdx.x;
             const unsigned long long pol = dp2_policy_stream(true);  // the trace's only read
             [[maybe_unused]] const unsigned long long keep = dp2_policy_keep();
-            constexpr int CBW = 16 / R1;
+            constexpr int CBW = ((VL == 2) ? 8 : 16) / R1;
             constexpr int CB = CBW < 1 ? 1 : (CBW > NC ? NC : CBW);
 #pragma unroll
             for (int i0 = 0; i0 < NC; i0 += CB) {
@@ -683,7 +697,9 @@ template <class T, int R1, int IN> struct Dp2Core {
 #pragma unroll
                             for (int b = 0; b < NB; ++b) buf[G::phys(c) + b * PB] = o[b];
                         } else if (ph <= TM_PHASES) {
-                            dp_tmem_st2(tm + (unsigned)(((ph - 1) * NC + (i0 + i)) * 8), o[0], o[1]);
+#pragma unroll
+                            for (int b = 0; b < NB; b += 2)
+                                dp_tmem_st2(tm + (unsigned)(((ph - 1) * NC + (i0 + i)) * 4 * NB + 4 * b), o[b], o[b + 1]);
                         } else {
 #pragma unroll
                             for (int b = 0; b < NB; ++b) dp2_st_keep(park + (long long)((ph - 1 - TM_PHASES) * NB + b) * VPB + c, o[b], keep);
@@ -701,18 +717,20 @@ template <class T, int R1, int IN> struct Dp2Core {
         if constexpr (CAN_PARK) {
             const int tid = threadIdx.x;
             if (p <= TM_PHASES) {
-                constexpr int LB = NC < 4 ? NC : 4;  // loads in flight before one wait (32 registers)
+                constexpr int NL = NC * NB / 2;      // 8-column loads of this phase
+                constexpr int LB = NL < 4 ? NL : 4;  // loads in flight before one wait (32 registers)
 #pragma unroll
-                for (int i0 = 0; i0 < NC; i0 += LB) {
+                for (int l0 = 0; l0 < NL; l0 += LB) {
                     DpTmemRaw8 t[LB];
 #pragma unroll
-                    for (int i = 0; i < LB; ++i) t[i] = dp_tmem_ld8(tm + (unsigned)(((p - 1) * NC + i0 + i) * 8));
+                    for (int l = 0; l < LB; ++l) t[l] = dp_tmem_ld8(tm + (unsigned)((p - 1) * NC * 4 * NB + (l0 + l) * 8));
                     dp_tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < LB; ++i) {
-                        const int c = tid + (i0 + i) * NT;
-                        buf[G::phys(c)] = dp_tmem_cx(t[i], 0);
-                        buf[G::phys(c) + PB] = dp_tmem_cx(t[i], 1);
+                    for (int l = 0; l < LB; ++l) {
+                        const int i = (l0 + l) / (NB / 2), b = 2 * ((l0 + l) % (NB / 2));
+                        const int c = tid + i * NT;
+                        buf[G::phys(c) + b * PB] = dp_tmem_get<V>(t[l], 0);
+                        buf[G::phys(c) + (b + 1) * PB] = dp_tmem_get<V>(t[l], 1);
                     }
                 }
             } else {
@@ -1193,7 +1211,7 @@ template <class T, int R1, int IN> struct Dp2OfKernel {
 #ifndef DP_OF_TMX
 #define DP_OF_TMX 1
 #endif
-    static constexpr bool TMX = DP_OF_TMX && TM && STAGE && (Core::TM_COLS + 64 <= 128);
+    static constexpr bool TMX = DP_OF_TMX && TM && STAGE && VL == 1 && (Core::TM_COLS + 64 <= 128);
     static constexpr unsigned XCOL = Core::TM_COLS;
     static DP_HD long long scratch_v(int n_templ) { return SCR_1 + SCR_X + SCR_PARK * n_templ; }
     // first element of warp w's rows in a thread-order table [NPH][NW][16][32]

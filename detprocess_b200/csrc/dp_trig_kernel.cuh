@@ -143,6 +143,8 @@ template <class T, int R1, int IN> struct DpTrigKernel {
                     Core::template pass1_any<true>(p, prm.trace, x0, prm.scale, buf, prm.tw1, jbase, jmax);
                 else
                     Core::template pass1_any<false>(p, xrow, x0, prm.scale, buf, prm.tw1);
+                // (a bulk L2 prefetch of the CTA's next chunk was measured and not kept: 0.251 -> 0.265 ms fp64 -- the chunks overlap
+                // and the neighbouring CTAs have just pulled most of those lines in)
                 __syncthreads();
 #ifndef DP_HOST_EMU
                 if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);  // see dp_of2_kernel.cuh

@@ -131,3 +131,37 @@ def test_filtered_at_equals_the_filtered_trace():
         got = trig._plan.filtered_at(xs, torch.from_numpy(idx)).cpu().numpy()
         ref = filtered if dt is np.float64 else T.filter_trace(x.astype(dt).astype(np.float64), trig._phi_td, trig._iw_matrix, trig._w_matrix)[0]
         assert np.allclose(got, ref[idx], rtol=1e-9, atol=1e-12 * np.max(np.abs(ref)))
+
+
+def test_yaml_run_residual_adds_the_second_pass_triggers(tmp_path):
+    """`run_residual: True` / `sat_amps_50kHz` of the YAML trigger section (reference process/triggers.py:742-751) reach
+    find_triggers: the table holds the first-pass triggers and the new second-pass ones, like the oracle's two passes"""
+    from detprocess_b200.core.filterdata import FilterData
+    from detprocess_b200.core.oftrigger import OptimumFilterTrigger
+    from detprocess_b200.process import TriggerProcessing
+    nt, pre, L = 4096, 2048, 300_000
+    fs, template, psd, x = _pileup_stream(nt, L, 21, pre)
+    text = '''
+trigger:
+    chanA:
+        run: True
+        threshold_sigma: 6
+        pileup_window_msec: 1
+        run_residual: %s
+'''
+    fd = FilterData()
+    fd.set_psd('chanA', psd, sample_rate=fs)
+    fd.set_template('chanA', template, sample_rate=fs, pretrigger_length_samples=pre)
+    tables = {}
+    for flag in ('False', 'True'):
+        yml = tmp_path / f'trig_{flag}.yaml'
+        yml.write_text(text % flag)
+        tp = TriggerProcessing({'traces': torch.from_numpy(x[None, None, :]), 'channels': ['chanA'], 'sample_rate': fs,
+                                'admin': [{'event_time': 1_700_000_000, 'series_num': 1, 'event_num': 1, 'dump_num': 1}]},
+                               str(yml), filter_data=fd, processing_id='unit', verbose=False)
+        tables[flag] = tp.process()
+    trig = OptimumFilterTrigger('chanA', fs, template, psd, pre, max_samples=L)
+    first, second, combined, _ = _oracle_two_pass(trig, x, 6.0, int(1.0 * fs / 1000))
+    assert sorted(tables['False']['trigger_index']) == sorted(first['trigger_index'])
+    assert sorted(tables['True']['trigger_index']) == sorted(combined['trigger_index'])
+    assert len(tables['True']) > len(tables['False'])
