@@ -2064,6 +2064,7 @@ template <class T> int nxm_finalize(dp_nxm_plan* p, DpNxmParams<T>& prm) {
     if ((rc = upload(p->owned, dt.tw3, &prm.tw3))) return rc;
     if ((rc = upload(p->owned, dt.twn, &prm.twn))) return rc;
     if ((rc = upload(p->owned, dt.groups, &prm.groups))) return rc;
+    if ((rc = upload(p->owned, dt.chunk3, &prm.chunk3))) return rc;
     if ((rc = upload(p->owned, dt.g, &prm.g))) return rc;
     if ((rc = upload(p->owned, dt.g_self, &prm.g_self))) return rc;
     for (int a = 0; a < p->n; ++a) {
@@ -2235,7 +2236,7 @@ struct dp_csd_plan {
     int N = 0, n = 0, precision = DP_PREC_F64, r1 = 0, device = 0;
     double fs = 0, scale = 1.0;
     std::vector<void*> owned;
-    const void *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twn = nullptr, *groups = nullptr;
+    const void *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twn = nullptr, *groups = nullptr, *chunk3 = nullptr;
     const int* loc = nullptr;
     void* scratch = nullptr;
     long long scratch_per_cta = 0;
@@ -2274,6 +2275,9 @@ template <class T, int R1> int csd_tables(dp_csd_plan* p) {
     const int2* dg;
     if ((rc = upload(p->owned, dt.groups, &dg))) return rc;
     p->groups = dg;
+    const int* dc3;
+    if ((rc = upload(p->owned, dt.chunk3, &dc3))) return rc;
+    p->chunk3 = dc3;
     // natural bin k -> slot of one component in a CTA's partial array (same map as the PSD plan)
     const std::vector<int> loc = dpplan2::partial_slot_of_bin<G>();
     if ((rc = upload(p->owned, loc, &p->loc))) return rc;
@@ -2315,6 +2319,7 @@ template <class T> int csd_launch(dp_csd_plan* p, const double* traces, long lon
     prm.tw3 = (const cx<T>*)p->tw3;
     prm.twn = (const cx<S>*)p->twn;
     prm.groups = (const int2*)p->groups;
+    prm.chunk3 = (const int*)p->chunk3;
     prm.scratch = (cx<T>*)p->scratch;
     prm.scratch_per_cta = p->scratch_per_cta;
     prm.partial = p->partial;

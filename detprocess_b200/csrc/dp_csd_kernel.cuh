@@ -10,6 +10,17 @@
 #pragma once
 #include "dp_of2_kernel.cuh"
 
+#ifndef DP_CSD_V3
+#define DP_CSD_V3 1
+#endif
+#ifndef DP_CSD_TMEM
+#ifdef DP_HOST_EMU
+#define DP_CSD_TMEM 0
+#else
+#define DP_CSD_TMEM 1
+#endif
+#endif
+
 #define DP_CSD_MAX_CHAN 4
 
 template <class T> struct DpCsdParams {
@@ -24,6 +35,7 @@ template <class T> struct DpCsdParams {
     const cx<T>* tw3;
     const cx<S>* twn;
     const int2* groups;
+    const int* chunk3;          // [NPH][NT] pass-3 chunk of the thread (warp-local passes)
     cx<T>* scratch;
     long long scratch_per_cta;  // V units
     double* partial;            // [grid][PARTIAL slots][NCP components]
@@ -61,11 +73,37 @@ template <class T, int R1, int NCH> struct DpCsdKernel {
         const double inv_s2 = 1.0 / (4.0 * prm.scale * prm.scale);  // kernel values are 2*scale*X
         const unsigned long long pol = dp2_policy_keep();
         unsigned long long n_acc = 0;
+        // round 2 (as in the PSD kernel): warp-local passes 3 / 4; with at most two channels the first pass of every channel
+        // is computed once and phase 1 finds its blocks in the thread's TMEM columns (channel a: [a * TM_COLS, +TM_COLS));
+        // the CTA's next event goes to L2 by bulk prefetch behind this event's last read
+        constexpr bool TMC = DP_CSD_TMEM && Core::CAN_PARK && Core::PARK1_V == 0 && NCH * Core::TM_COLS <= 128;
+        [[maybe_unused]] unsigned tm_thread = 0;
+#ifndef DP_HOST_EMU
+        if constexpr (TMC) {
+            unsigned* slot = reinterpret_cast<unsigned*>(dcv + NCH);
+            if (tid < 32) dp_tmem_alloc512(slot);
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            tm_thread = Core::tm_thread_base(*slot);
+        }
+#endif
 
         for (int ev = blockIdx.x; ev < prm.n_events; ev += gridDim.x) {
             if (prm.mask != nullptr && prm.mask[ev] == 0) continue;  // CTA-uniform
             ++n_acc;
             const double* xev = prm.traces + (long long)ev * prm.ev_stride;
+            auto prefetch_next_event = [&]() {
+#ifndef DP_HOST_EMU
+                int nev = ev + gridDim.x;
+                while (prm.mask != nullptr && nev < prm.n_events && prm.mask[nev] == 0) nev += gridDim.x;
+                if (tid < NCH && nev < prm.n_events) {
+                    const double* nx = prm.traces + (long long)nev * prm.ev_stride + (long long)tid * prm.chan_stride;
+                    if ((reinterpret_cast<unsigned long long>(nx) & 15ull) == 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"((unsigned)(N * sizeof(double))) : "memory");
+                }
+#endif
+            };
 #pragma unroll 1
             for (int p = 0; p < NPH; ++p) {
                 V z[16];
@@ -79,14 +117,33 @@ template <class T, int R1, int NCH> struct DpCsdKernel {
                 for (int a = 0; a < NCH; ++a) {
                     const double* xrow = xev + (long long)a * prm.chan_stride;
                     const double x0 = prm.subtract_first ? dp_load_first<0>(xrow) : 0.0;
-                    Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
+                    if constexpr (TMC) {
+                        if (p == 0)
+                            Core::pass1_all(xrow, x0, prm.scale, buf, prm.tw1, tm_thread + (unsigned)(a * Core::TM_COLS), nullptr);
+                        else
+                            Core::pass1_fetch(p, buf, tm_thread + (unsigned)(a * Core::TM_COLS), nullptr);
+                        if (p == 0 && a == NCH - 1) prefetch_next_event();
+                    } else {
+                        Core::pass1_any(p, xrow, x0, prm.scale, buf, prm.tw1);
+                        if (p == NPH - 1 && a == NCH - 1) prefetch_next_event();
+                    }
                     __syncthreads();
 #ifndef DP_HOST_EMU
                     // every second block starts its passes a little late (see dp_of2_kernel.cuh: the block sets' LDS / FP /
                     // STS phases interleave instead of hitting the same pipe at the same time)
                     if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);
 #endif
+#if DP_CSD_V3
+                    Core::fwd_2(buf, prm.tw2, z);
+                    dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 3 reads the chunks of the warp's block set
+                    Core::fwd_3w(buf, prm.tw3, prm.chunk3[p * NT + tid], z);
+                    __syncwarp();
+                    Core::load_groups(buf, gg.x, gg.y, z);
+                    __syncwarp();  // the point-wise stage rewrites the warp's group rows
+                    dp_dft<16, -1, T>::run(z);
+#else
                     Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+#endif
                     if (p == 0 && tid < 32) {
                         if constexpr (VL == 2) {
                             if (tid == 0) {
@@ -196,6 +253,14 @@ template <class T, int R1, int NCH> struct DpCsdKernel {
             }
         }
         if (tid == 0) prm.count[blockIdx.x] += n_acc;
+#ifndef DP_HOST_EMU
+        if constexpr (TMC) {
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            if (tid < 32) dp_tmem_dealloc512(*reinterpret_cast<unsigned*>(dcv + NCH));
+        }
+#endif
     }
 };
 

@@ -15,6 +15,21 @@
 #pragma once
 #include "dp_of2_kernel.cuh"
 
+// DP_NXM_V3 (round 2): passes 3 / 4 / 4' / 3' warp-local like the OF kernel (0 = the lock-step passes of round 1)
+#ifndef DP_NXM_V3
+#define DP_NXM_V3 1
+#endif
+// DP_NXM_TMEM (round 2, at most two channels, 512-thread geometries): the X_a columns of the current phase (16 values per
+// thread and channel, re-read by every template's filter pass) live in the thread's tensor-memory columns [64 a, 64 a + 64)
+// instead of an L2 scratch column (profiles/r1_regions_nxm_*: the filter stage spent 25 % of its samples waiting on those loads)
+#ifndef DP_NXM_TMEM
+#ifdef DP_HOST_EMU
+#define DP_NXM_TMEM 0
+#else
+#define DP_NXM_TMEM 1
+#endif
+#endif
+
 #define DP_NXM_MAX_CHAN 4
 #define DP_NXM_MAX_TEMPL 3
 #define DP_NXM_MAX_PAIRS (DP_NXM_MAX_CHAN * (DP_NXM_MAX_CHAN - 1) / 2)
@@ -31,6 +46,7 @@ template <class T> struct DpNxmParams {
     const cx<T>* tw3;
     const cx<S>* twn;
     const int2* groups;
+    const int* chunk3;      // [NPH][NT] pass-3 chunk of the thread (warp-local passes)
     const cx<T>* g;       // [n_templ][n_chan][NPH][16][NT] thread-order filters (one array: no run-time indexed
     const cx<S>* g_self;  // [n_templ][n_chan][17][2]          kernel-parameter pointers)
     const T* wd[DP_NXM_MAX_CHAN];                            // chi0 weights, diagonal (real)
@@ -111,6 +127,18 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
         V* const scr_q = scr_park + SCR_PARK * ntm;
         constexpr int NSPECIAL = (VL == 2) ? 1 : 2;
         const unsigned long long pol = dp2_policy_keep();
+        constexpr bool TMN = DP_NXM_TMEM && NT == 512 && NCH * 64 <= 128;
+        [[maybe_unused]] unsigned tm_thread = 0;
+#ifndef DP_HOST_EMU
+        if constexpr (TMN) {
+            unsigned* slot = reinterpret_cast<unsigned*>(best + 64);
+            if (tid < 32) dp_tmem_alloc512(slot);
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            tm_thread = Core::tm_thread_base(*slot);
+        }
+#endif
 
         for (int ev = blockIdx.x; ev < prm.n_events; ev += gridDim.x) {
             const double* xev = prm.traces + (long long)ev * prm.ev_stride;
@@ -154,7 +182,17 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                     // STS phases interleave instead of hitting the same pipe at the same time)
                     if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);
 #endif
+#if DP_NXM_V3
+                    Core::fwd_2(buf, prm.tw2, z);
+                    dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 3 reads the chunks of the warp's block set
+                    Core::fwd_3w(buf, prm.tw3, prm.chunk3[p * NT + tid], z);
+                    __syncwarp();
+                    Core::load_groups(buf, gg.x, gg.y, z);
+                    __syncwarp();  // the point-wise stage rewrites the warp's group rows
+                    dp_dft<16, -1, T>::run(z);
+#else
                     Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+#endif
                     if (p == 0 && tid < 32) {
                         if constexpr (VL == 2) {
                             if (tid == 0) {
@@ -183,15 +221,31 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                     V* dst = scr_x + SCR_X * a + tid;
                     if constexpr (VL == 2) {
                         (void)OF::template untangle_all<false>(buf, z, zm, nullptr, wn, gg.x, special);
+                        if constexpr (TMN) {
+#ifndef DP_HOST_EMU
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
+                            for (int r = 0; r < 16; r += 2) dp_tmem_st2(tm_thread + (unsigned)(64 * a + 4 * r), z[r], z[r + 1]);
+#endif
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) dp2_st_keep(dst + r * NT, z[r], pol);
+                        }
                     } else {
                         OF::pw_publish(buf, z, gg.x);
                         OF::pw_untangle(buf, z, wn, Gp, [&](int r, cx<S> Xk, cx<S> Xm) {
-                            dp2_st_keep(dst + (2 * r) * NT, Xk, pol);
-                            dp2_st_keep(dst + (2 * r + 1) * NT, Xm, pol);
+                            if constexpr (TMN) {
+#ifndef DP_HOST_EMU
+                                dp_tmem_st2(tm_thread + (unsigned)(64 * a + 8 * r), Xk, Xm);   // entry e at column 4 e
+#endif
+                            } else {
+                                dp2_st_keep(dst + (2 * r) * NT, Xk, pol);
+                                dp2_st_keep(dst + (2 * r + 1) * NT, Xm, pol);
+                            }
                         });
                     }
+#ifndef DP_HOST_EMU
+                    if constexpr (TMN) dp_tmem_wait_st();
+#endif
                     __syncthreads();  // group-row reads of this channel precede the next pass-1 stores
                 }
 
@@ -242,10 +296,29 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                     // X_a of one table entry -> registers; the first template's pass also takes the CSD quadratic form
                     // sum_ab conj(X_a) W_ab X_b (chi0) from them
                     T chi_acc = (T)0.0f;
-                    auto entry = [&](int ent) -> V {
-                        V X[NCH];
+                    // X_a of the entry pair (2 q, 2 q + 1): out of tensor memory (one 8-column load per channel) or the scratch columns
+                    auto load_pair = [&](int q, V (&Xa)[NCH], V (&Xb)[NCH]) {
+                        if constexpr (TMN) {
+#ifndef DP_HOST_EMU
+                            DpTmemRaw8 t[NCH];
 #pragma unroll
-                        for (int a = 0; a < NCH; ++a) X[a] = dp2_ld_keep(scr_x + SCR_X * a + ent * NT + tid, pol);
+                            for (int a = 0; a < NCH; ++a) t[a] = dp_tmem_ld8(tm_thread + (unsigned)(64 * a + 8 * q));
+                            dp_tmem_wait_ld();
+#pragma unroll
+                            for (int a = 0; a < NCH; ++a) {
+                                Xa[a] = dp_tmem_get<V>(t[a], 0);
+                                Xb[a] = dp_tmem_get<V>(t[a], 1);
+                            }
+#endif
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < NCH; ++a) {
+                                Xa[a] = dp2_ld_keep(scr_x + SCR_X * a + (2 * q) * NT + tid, pol);
+                                Xb[a] = dp2_ld_keep(scr_x + SCR_X * a + (2 * q + 1) * NT + tid, pol);
+                            }
+                        }
+                    };
+                    auto entry = [&](int ent, const V (&X)[NCH]) -> V {
                         const long long e = e0 + (long long)ent * NT;
                         if (it == 0) {
 #pragma unroll
@@ -271,13 +344,20 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                     };
                     if constexpr (VL == 2) {
 #pragma unroll
-                        for (int r = 0; r < 16; ++r) z[r] = entry(r);
+                        for (int q = 0; q < 8; ++q) {
+                            V Xa[NCH], Xb[NCH];
+                            load_pair(q, Xa, Xb);
+                            z[2 * q] = entry(2 * q, Xa);
+                            z[2 * q + 1] = entry(2 * q + 1, Xb);
+                        }
                         retangle_all(z, wn);
                     } else {
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
-                            const V Fk = entry(2 * r);
-                            const V Fm = entry(2 * r + 1);
+                            V Xa[NCH], Xb[NCH];
+                            load_pair(r, Xa, Xb);
+                            const V Fk = entry(2 * r, Xa);
+                            const V Fm = entry(2 * r + 1, Xb);
                             cx<S> Ck, Cm;
                             dp_retangle(Fk, Fm, cmul(wn, dp_w64_rt<S>(2 * r)), Ck, Cm);
                             z[r] = Ck;
@@ -303,7 +383,16 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                         }
                         __syncwarp();
                     }
+#if DP_NXM_V3
+                    dp_dft<16, +1, T>::run(z);
+                    Core::store_groups(buf, gg.x, gg.y, z);
+                    __syncwarp();  // pass 3' reads the warp's own chunks
+                    Core::inv_3w(buf, prm.tw3, prm.chunk3[p * NT + tid], z);
+                    dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 2' reads columns across the set's chunks
+                    Core::inv_2(buf, prm.tw2, z);
+#else
                     Core::inv_432(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
+#endif
                     if (p < NPH - 1) {
                         Core::park_pass2(park, p, z);
                         __syncthreads();
@@ -433,6 +522,14 @@ template <class T, int R1, int NCH> struct DpNxmKernel {
                 }
             }
         }
+#ifndef DP_HOST_EMU
+        if constexpr (TMN) {
+            dp_tmem_fence_before();
+            __syncthreads();
+            dp_tmem_fence_after();
+            if (tid < 32) dp_tmem_dealloc512(*reinterpret_cast<unsigned*>(best + 64));
+        }
+#endif
     }
 };
 

@@ -141,6 +141,7 @@ template <class T> struct Tables {
     std::vector<cx<T>> tw1, tw2, tw3;
     std::vector<cx<S>> twn;
     std::vector<int2> groups;
+    std::vector<int> chunk3;   // per-thread pass-3 chunk ids (warp-local passes)
     std::vector<cx<T>> g;       // [m][n][NPH*16*NT]
     std::vector<cx<S>> g_self;  // [m][n][17*2]
     std::vector<std::vector<T>> wd;          // [n]
@@ -165,6 +166,7 @@ template <class T, int R1> Tables<T> build_tables(const Setup& s, double scale) 
         dt.tw3 = std::move(base.tw3);
         dt.twn = std::move(base.twn);
         dt.groups = std::move(base.groups);
+        dt.chunk3 = std::move(base.chunk3);
     }
     const double df = s.fs / N;
     const int n = s.n, m = s.m;

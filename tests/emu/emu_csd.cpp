@@ -58,6 +58,7 @@ static void run_all(double fs, double scale, int subtract_first, const std::vect
     prm.tw3 = dt.tw3.data();
     prm.twn = dt.twn.data();
     prm.groups = dt.groups.data();
+    prm.chunk3 = dt.chunk3.data();
     prm.scratch = scratch.data();
     prm.scratch_per_cta = K::scratch_v();
     prm.partial = partial.data();

@@ -52,6 +52,7 @@ static void run_all(const dpnxm::Setup& s, double scale, int subtract_first, int
     prm.tw3 = dt.tw3.data();
     prm.twn = dt.twn.data();
     prm.groups = dt.groups.data();
+    prm.chunk3 = dt.chunk3.data();
     prm.g = dt.g.data();
     prm.g_self = dt.g_self.data();
     for (int a = 0; a < s.n; ++a) {
