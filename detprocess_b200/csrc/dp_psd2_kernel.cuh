@@ -130,7 +130,10 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
 #ifndef DP_HOST_EMU
                 if (DP2_SKEW_NS > 0 && ((tid / G::CV) & 1)) __nanosleep(DP2_SKEW_NS);  // see dp_of2_kernel.cuh
 #endif
-#if DP_PSD_V3
+#ifndef DP_PSD_V3_F32
+#define DP_PSD_V3_F32 0
+#endif
+                if constexpr (DP_PSD_V3 && (VL == 1 || DP_PSD_V3_F32)) {
                 Core::fwd_2(buf, prm.tw2, z);
                 dp_bar_sync(G::bar_set_id(p, tid), G::bar_set_count(p, tid));  // pass 3 reads the chunks of the warp's block set
                 Core::fwd_3w(buf, prm.tw3, prm.chunk3[p * NT + tid], z);
@@ -138,9 +141,9 @@ template <class T, int R1, int IN> struct DpPsd2Kernel {
                 Core::load_groups(buf, gg.x, gg.y, z);
                 __syncwarp();  // pw_publish rewrites the warp's group rows
                 dp_dft<16, -1, T>::run(z);
-#else
+                } else {
                 Core::fwd_234(buf, prm.tw2, prm.tw3, gg.x, gg.y, z, p);
-#endif
+                }
                 if (p == 0 && tid < 32) {
                     if constexpr (VL == 2) {
                         if (tid == 0) {
