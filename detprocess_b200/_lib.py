@@ -104,6 +104,9 @@ SIGNATURES = {
     'dp_trigger_run': (_i, [_vp, _vp, _ll, _d, _ll, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'dp_trigger_run_raw': (_i, [_vp, _vp, _i, _ll, _d, _ll, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'dp_trigger_plan_last_kernel_ms': (_i, [_vp, _fp, _fp]),
+    'dp_band_plan_create': (_i, [C.POINTER(_vp), _i, _d, _vp, _vp, _i, _i]),
+    'dp_band_plan_destroy': (None, [_vp]),
+    'dp_band_amplitudes': (_i, [_vp, _vp, _i, _ll, _ll, _d, _d, _vp, _vp]),
     'dp_trigger_candidates': (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     'dp_trigger_filtered_at': (_i, [_vp, _vp, _i, _ll, _vp, _i, _vp, _vp]),
     'dp_trigger_residual_run': (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _ll, _ll, _vp, _vp, _vp, _i, _vp, _vp]),

@@ -23,7 +23,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3',
 
 # (object name, source, extra defines): the OF kernel is instantiated per
 # (precision, input type) in separate translation units so they compile in parallel
-UNITS = [('dp_capi', 'dp_capi.cu', []), ('dp_ofg_inst', 'dp_ofg_inst.cu', [])] + [
+UNITS = [('dp_capi', 'dp_capi.cu', []), ('dp_ofg_inst', 'dp_ofg_inst.cu', []), ('dp_band_inst', 'dp_band_inst.cu', [])] + [
     (f'dp_of2_inst_p{p}_{i}', 'dp_of2_inst.cu', [f'-DDP_INST_PREC={p}', f'-DDP_INST_IN={i}'])
     for p in (1, 0) for i in (0, 1, 2, 3, 4, 5)] + [
     (f'dp_trig_inst_p{p}', 'dp_trig_inst.cu', [f'-DDP_INST_PREC={p}']) for p in (1, 0)] + [

@@ -187,6 +187,27 @@ class FeatureExtractors:
         return _scalarize(of_base, retdict)
 
     @staticmethod
+    def _psd_amp_ranges(nb_samples, fs, f_lims):
+        """(feature-name suffixes, one-sided bin ranges with the DC bin at 0) of a ``psd_amp`` block: the reference's
+        ``cleanup_freq_ranges`` / ``get_ind_freq_ranges`` on the DC-less folded frequencies (core/algorithms.py:993-1021)"""
+        from ..utils import utils
+        if not f_lims:
+            raise ValueError('ERROR: "f_lims" required for algorithm psd_amps')
+        freq_ranges, names = utils.cleanup_freq_ranges(f_lims)
+        freqs = np.fft.rfftfreq(int(nb_samples), d=1.0 / fs)[1:]
+        return names, [(lo + 1, hi + 1) for lo, hi in utils.get_ind_freq_ranges(freq_ranges, freqs)]
+
+    @staticmethod
+    def psd_amp(channel, of_base, f_lims=[], feature_base_name='psd_amp', **kwargs):
+        """Average of sqrt(folded PSD) of the event over frequency ranges (reference core/algorithms.py:953-1042)."""
+        fs = kwargs.get('fs', of_base.sample_rate())
+        names, bins = FeatureExtractors._psd_amp_ranges(of_base.nb_samples(), fs, f_lims)
+        if not of_base.is_signal_stored(channel):
+            return {f'{feature_base_name}_{n}': _SENTINEL for n in names}
+        amps = of_base.band_amplitudes(channel, bins)
+        return _scalarize(of_base, {f'{feature_base_name}_{n}': amps[:, i] for i, n in enumerate(names)})
+
+    @staticmethod
     def baseline(trace, window_min_index=None, window_max_index=None,
                  feature_base_name='baseline', **kwargs):
         if _empty(trace):

@@ -265,6 +265,29 @@ class OFBaseBatch:
     def signal(self, channel):
         return self._signals.get(channel)
 
+    def band_amplitudes(self, channel, bin_ranges):
+        """sqrt(folded PSD) of the stored signal of ``channel`` averaged over one-sided bin ranges (``psd_amp``): ndarray
+        [B, n_bands].  The event spectrum is not kept by the fused OF kernel; the few bins of the bands are evaluated
+        directly by ``dp_band_amplitudes``."""
+        from .plans import BandPlan
+        if channel in self._batch_rows and self._batch is not None and self._batch_starts is None:
+            x = self._batch[:, self._batch_rows[channel], :]
+        elif channel in self._signals:
+            x = self._signals[channel]
+        else:
+            raise ValueError(f'ERROR: no signal stored for channel {channel}')
+        import torch
+        dev = torch.device('cuda', torch.cuda.current_device()) if self._device is None else torch.device(self._device)
+        x = x.to(dev)
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        key = (int(x.shape[-1]), tuple((int(a), int(b)) for a, b in bin_ranges))
+        cache = self.__dict__.setdefault('_band_plans', {})
+        if key not in cache:
+            cache[key] = BandPlan(key[0], self._fs, key[1], device=dev)
+        adc = self._adc.get(channel) if x.dtype == torch.int16 else None
+        return cache[key].run(x, adc=adc).cpu().numpy()
+
     def calc_signal_filt(self, channel, template_tag=None):
         return None   # fused into the kernel (phi * v / norm)
 

@@ -477,6 +477,48 @@ class ReducePlan:
         return ms.value
 
 
+class BandPlan:
+    """``dp_band_plan``: averages of sqrt(folded event PSD) over one-sided bin ranges -- ``FeatureExtractors.psd_amp``
+    (reference core/algorithms.py:953-1042).  ``bin_ranges``: [(lo, hi)] with the DC bin at 0 (the reference's indices into
+    the DC-less folded spectrum + 1)."""
+
+    def __init__(self, nb_samples, sample_rate, bin_ranges, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.DetprocessB200Error('no CUDA device: detprocess_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        self.nb_samples, self.sample_rate = int(nb_samples), float(sample_rate)
+        lo = np.ascontiguousarray([int(a) for a, _ in bin_ranges], dtype=np.int32)
+        hi = np.ascontiguousarray([int(b) for _, b in bin_ranges], dtype=np.int32)
+        self.n_bands = len(lo)
+        self._h = C.c_void_p()
+        check(lib.dp_band_plan_create(C.byref(self._h), self.nb_samples, self.sample_rate, lo.ctypes.data, hi.ctypes.data,
+                                      self.n_bands, self.device.index or 0))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            lib.dp_band_plan_destroy(h)
+            self._h = C.c_void_p()
+
+    def run(self, x, adc=None, out=None):
+        """x: CUDA tensor [B, N] (f64 / f32 / i16), rows may be strided (e.g. ``batch[:, row, :]`` of a reader batch);
+        adc = (gain, offset) of int16 samples.  Returns float64 [B, n_bands] on the device."""
+        torch = _torch()
+        if not x.is_cuda or x.ndim != 2 or x.shape[1] != self.nb_samples or x.stride(1) != 1:
+            raise ValueError('run() takes a CUDA tensor [B, nb_samples] with contiguous samples')
+        nb = int(x.shape[0])
+        if out is None:
+            out = torch.empty((nb, self.n_bands), dtype=torch.float64, device=x.device)
+        gain, offset = (1.0, 0.0) if adc is None else (float(adc[0]), float(adc[1]))
+        stride = int(x.stride(0)) if nb > 1 else self.nb_samples
+        check(lib.dp_band_amplitudes(self._h, C.c_void_p(x.data_ptr()), _in_dtype_of(x), nb, stride, gain, offset,
+                                     C.c_void_p(out.data_ptr()), _stream_ptr(x.device)))
+        return out
+
+
 def combine_channels(batch, terms, adc=None, out=None):
     """Weighted channel algebra on the device in ONE launch (``dp_channel_combine``; reference
     ``ProcessingData.get_channel_trace``, processing_data.py:1033-1047).

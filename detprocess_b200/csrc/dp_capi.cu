@@ -24,6 +24,8 @@
 #include "dp_plan.hpp"
 #include "dp_plan2.hpp"
 #include "dp_psd2_kernel.cuh"
+#include "dp_band_kernel.cuh"
+#include "dp_band_launch.hpp"
 #include "dp_psd_kernel.cuh"
 #include "dp_reduce_plan.hpp"
 #include "dp_trig_kernel.cuh"
@@ -2017,6 +2019,87 @@ int dp_trigger_residual_run(dp_trigger_plan* p, const long long* pulse_start_dev
     gp.n_triggers = n_triggers_dev;
     rc = dp_trig_group_par_launch(&gp, std::max(1, 2 * p->n_sm), stream);
     if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger group launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return DP_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================= band amplitudes (psd_amp)
+struct dp_band_plan {
+    int N = 0, n_bands = 0, device = 0;
+    double fs = 0;
+    int* bin_lo = nullptr;
+    int* bin_hi = nullptr;
+    double2* roots = nullptr;
+    int n_sm = 0;
+    std::vector<void*> owned;
+};
+
+extern "C" {
+
+int dp_band_plan_create(dp_band_plan** plan, int nb_samples, double sample_rate, const int* bin_lo, const int* bin_hi, int n_bands,
+                        int device) {
+    if (!plan || !bin_lo || !bin_hi) return fail(DP_ERR_INVALID, "null pointer");
+    if (nb_samples < 2 || !(sample_rate > 0) || n_bands < 1) return fail(DP_ERR_INVALID, "bad argument");
+    for (int b = 0; b < n_bands; ++b)
+        if (bin_lo[b] < 0 || bin_hi[b] <= bin_lo[b] || bin_hi[b] > nb_samples / 2 + 1) return fail(DP_ERR_INVALID, "bin range outside the one-sided spectrum");
+    auto p = std::make_unique<dp_band_plan>();
+    p->N = nb_samples;
+    p->fs = sample_rate;
+    p->n_bands = n_bands;
+    p->device = device;
+    DP_ON_DEVICE(device);
+    std::vector<double2> roots((size_t)nb_samples);
+    for (int j = 0; j < nb_samples; ++j) {
+        const dpplan::cplx w = dpplan::unit_root(j, nb_samples);   // exp(-2 pi i j / N), exact octant symmetry
+        roots[(size_t)j] = make_double2(w.real(), w.imag());
+    }
+    int rc;
+    const double2* dr;
+    if ((rc = upload(p->owned, roots, &dr))) return rc;
+    p->roots = const_cast<double2*>(dr);
+    const std::vector<int> lo(bin_lo, bin_lo + n_bands), hi(bin_hi, bin_hi + n_bands);
+    const int* di;
+    if ((rc = upload(p->owned, lo, &di))) return rc;
+    p->bin_lo = const_cast<int*>(di);
+    if ((rc = upload(p->owned, hi, &di))) return rc;
+    p->bin_hi = const_cast<int*>(di);
+    cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device);
+    *plan = p.release();
+    return DP_OK;
+}
+
+void dp_band_plan_destroy(dp_band_plan* p) {
+    if (!p) return;
+    for (void* d : p->owned) cudaFree(d);
+    delete p;
+}
+
+int dp_band_amplitudes(dp_band_plan* p, const void* base_dev, int in_dtype, long long n_events, long long event_stride, double adc_gain,
+                       double adc_offset, double* out_dev, void* stream) {
+    if (!p) return fail(DP_ERR_INVALID, "null plan");
+    if (in_dtype < DP_IN_F64 || in_dtype > DP_IN_I16) return fail(DP_ERR_INVALID, "unknown in_dtype");
+    if (!base_dev || !out_dev || n_events < 0 || event_stride < p->N) return fail(DP_ERR_INVALID, "bad argument");
+    if (n_events == 0) return DP_OK;
+    DP_ON_DEVICE(p->device);
+    DpBandParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.base = base_dev;
+    prm.in_dtype = in_dtype;
+    prm.n_events = n_events;
+    prm.event_stride = event_stride;
+    prm.N = p->N;
+    prm.gain = adc_gain;
+    prm.offset = adc_offset;
+    prm.bin_lo = p->bin_lo;
+    prm.bin_hi = p->bin_hi;
+    prm.n_bands = p->n_bands;
+    prm.roots = p->roots;
+    prm.norm = (double)p->N / (p->fs * p->fs * p->fs);
+    prm.out = out_dev;
+    const int grid = (int)std::min<long long>(n_events, 8LL * std::max(p->n_sm, 1));
+    const int rc = dp_band_launch(&prm, grid, stream);
+    if (rc != 0) return fail(DP_ERR_CUDA, std::string("band amplitude launch: ") + cudaGetErrorString((cudaError_t)rc));
     return DP_OK;
 }
 

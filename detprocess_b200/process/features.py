@@ -240,6 +240,8 @@ class FeatureProcessing:
                 base = params.get('base_algorithm', algo)
                 if not any(p in base for p in _OF_PREFIXES):
                     continue
+                if base == 'psd_amp':
+                    continue        # no template / csd (reference processing_data.py:288-289): a band job of _compile_jobs
                 if not (base.startswith('of1x1') or base == 'ofnxm'):
                     raise NotImplementedError(f'algorithm "{base}" is outside the built hot path')
                 key = self._of_key(params)
@@ -288,6 +290,7 @@ class FeatureProcessing:
         table build, one launch per batch whatever the blocks' windows and ``lowchi2_fcutoff``); the window reductions
         share cached ReducePlans; the combined channels ('a+b', 'a-b') are listed for the channel-algebra kernel."""
         self._of_jobs, self._ext_jobs = [], []
+        self._band_jobs = []    # psd_amp blocks: dicts (channel, columns, bin ranges, nb_samples), one BandPlan each
         red_jobs = {}           # (nb_samples, nb_pretrigger) -> list of (channel, op, lo, hi, column)
         self._combined = []     # combined channel names, in the order of the combine kernel's output rows
         n_reader = int(self._reader.metadata['nb_samples'])
@@ -325,6 +328,12 @@ class FeatureProcessing:
                         entry['OF'].request_fit(channel, *spec)
                 elif base in _TRACE_OPS and extractor is getattr(FE, base):
                     red_jobs.setdefault(geom, []).append((channel, base, wmin, wmax, f'{algorithm}_{feature_channel}'))
+                elif base == 'psd_amp' and extractor is FE.psd_amp:
+                    if not self._is_plain(channel):
+                        raise NotImplementedError(f'psd_amp on the combined / joint channel "{channel}" is outside the built hot path')
+                    names, bins = FE._psd_amp_ranges(geom[0], self._fs, params.get('f_lims', []))
+                    self._band_jobs.append({'channel': channel, 'bins': bins, 'nb_samples': geom[0], 'plan': None,
+                                            'columns': [f'{algorithm}_{nm}_{feature_channel}' for nm in names]})
                 else:
                     self._ext_jobs.append((channel, extractor, kw, feature_channel, geom))
         # cached reduction plans: per trace geometry one plan over the plain channels (read in place from the reader
@@ -518,8 +527,8 @@ class FeatureProcessing:
         cols = {}
         if window_mode:
             nb, n = int(trigger_index.shape[0]), None
-            if self._combined or self._ext_jobs:
-                raise NotImplementedError('combined channels / external extractors in trigger-dataframe mode are not built')
+            if self._combined or self._ext_jobs or self._band_jobs:
+                raise NotImplementedError('combined channels / external extractors / psd_amp in trigger-dataframe mode are not built')
         else:
             nb, _, n = batch.shape
         if self._processing_id is not None:
@@ -592,6 +601,15 @@ class FeatureProcessing:
                 else:
                     out = plan.run_layout(comb, [self._combined.index(c) for c in d['chans']])
                 blocks.append(('red', d, out))
+        # ---- psd_amp: band amplitudes of the plain channels, read where the reader put them --------------------------
+        for job in self._band_jobs:
+            if job['nb_samples'] != n:
+                raise ValueError(f'ERROR: trace length {n} != configured nb_samples {job["nb_samples"]}')
+            if job['plan'] is None:
+                from ..core.plans import BandPlan
+                job['plan'] = BandPlan(n, self._fs, job['bins'], device=dev)
+            adc = self._adc.get(job['channel']) if (self._adc is not None and batch.dtype == torch.int16) else None
+            blocks.append(('band', job, job['plan'].run(batch[:, rows[job['channel']], :], adc=adc)))
         # ---- all result blocks of the batch -> one pinned host block, behind the kernels
         total = sum(int(b[2].numel()) for b in blocks)
         host = self._result_staging(total)
@@ -624,6 +642,9 @@ class FeatureProcessing:
             arr = v.numpy().copy()          # the pinned block is reused two batches later
             if kind == 'of':
                 obj.set_results(arr)
+            elif kind == 'band':
+                for i, name in enumerate(obj['columns']):
+                    cols[name] = arr[:, i]
             else:
                 reds.append((obj, arr))
         for j, (channel, extractor, entry, kw, feature_channel) in enumerate(self._of_jobs):

@@ -119,3 +119,47 @@ def columns_to_frame(parts):
         vals = [np.asarray(p[c]) if np.ndim(p[c]) else np.full(nb, p[c]) for p, nb in zip(parts, sizes)]
         out[c] = vals[0] if len(vals) == 1 else np.concatenate(vals)
     return pd.DataFrame(out)
+
+
+def cleanup_freq_ranges(f_lims):
+    """Frequency ranges of ``psd_amp`` / ``psd_peaks`` and their feature-name suffixes (reference utils/utils.py:437-470):
+    a number or a one-element list is a single frequency (name ``'<f>'``), a pair is ordered low -> high (name
+    ``'<lo>_<hi>'``, rounded); signs are dropped and a name that came before is skipped."""
+    if not isinstance(f_lims, list):
+        f_lims = [f_lims]
+    ranges, names = [], []
+    for item in f_lims:
+        vals = [item] if isinstance(item, (int, float)) else list(item)
+        lo = abs(vals[0])
+        if len(vals) == 2:
+            hi = abs(vals[1])
+            lo, hi = min(lo, hi), max(lo, hi)
+            name, rng = f'{round(lo)}_{round(hi)}', [lo, hi]
+        else:
+            name, rng = f'{round(lo)}', [lo]
+        if name not in names:
+            names.append(name)
+            ranges.append(rng)
+    return ranges, names
+
+
+def get_ind_freq_ranges(freq_ranges, freqs):
+    """``[ind_low, ind_high)`` into ``freqs`` for every range (reference utils/utils.py:475-505): nearest bins of the two
+    edges (single frequency: its nearest bin), ordered; an empty range is widened by one bin upwards, or downwards at the
+    end of the array."""
+    freqs = np.asarray(freqs)
+    out = []
+    for rng in freq_ranges:
+        lo = int(np.argmin(np.abs(freqs - abs(rng[0]))))
+        hi = lo + 1 if len(rng) != 2 else int(np.argmin(np.abs(freqs - abs(rng[1]))))
+        if lo > hi:
+            lo, hi = hi, lo
+        if lo == hi:
+            if hi < len(freqs) - 1:
+                hi += 1
+            elif lo > 0:
+                lo -= 1
+            else:
+                raise ValueError('Frequency range too narrow or outside bounds.')
+        out.append([lo, hi])
+    return out

@@ -277,6 +277,19 @@ int dp_trigger_residual_run(dp_trigger_plan* plan, const long long* pulse_start_
                             long long index_shift, long long* trig_index_dev, double* trig_amp_dev, double* trig_dchi2_dev,
                             int max_triggers, int* n_triggers_dev, void* stream);
 
+/* ------------------------------------------------------------------ band amplitudes of the event spectrum
+ * FeatureExtractors.psd_amp (detprocess/core/algorithms.py:953-1042) and the average_range / single-frequency case of psd_peaks
+ * (:1045-1150): out[event][b] = mean over the one-sided bins k in [bin_lo[b], bin_hi[b]) of sqrt(psd_fold[k]), with
+ * psd = |fft(x) / N / df|^2 * N / fs folded to one side (every bin but DC and Nyquist doubled).  The host turns f_lims into bin
+ * ranges like utils.get_ind_freq_ranges (+1: the reference drops the DC bin first).  One channel per call: base_dev = first sample of
+ * event 0 of that channel, event_stride in elements; int16 samples are converted as adc * gain + offset. */
+typedef struct dp_band_plan dp_band_plan;
+int dp_band_plan_create(dp_band_plan** plan, int nb_samples, double sample_rate, const int* bin_lo, const int* bin_hi, int n_bands,
+                        int device);
+void dp_band_plan_destroy(dp_band_plan* plan);
+int dp_band_amplitudes(dp_band_plan* plan, const void* base_dev, int in_dtype, long long n_events, long long event_stride, double adc_gain,
+                       double adc_offset, double* out_dev /* [n_events][n_bands] */, void* stream);
+
 /* ------------------------------------------------------------------ NxM optimal filter
  * Replaces qp.OFnxm(of_base, channels, template_tag).calc() + get_fit_withdelay(window...) + get_fit_nodelay() as driven
  * per event by FeatureExtractors.ofnxm (reference detprocess/core/algorithms.py:141-274): n channels with an n x n

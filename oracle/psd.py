@@ -67,3 +67,77 @@ def calc_csd(traces, fs, cut=None):
         X = np.fft.fft(x, axis=-1)
         acc += X[:, None, :] * np.conj(X[None, :, :])
     return np.fft.fftfreq(N, 1.0 / fs), acc / (ne * N * fs)
+
+
+# ---- psd_amp (detprocess/core/algorithms.py:953-1042) -------------------------------------------------------------
+def fold_spectrum(spectrum, fs):
+    """``qp.utils.fold_spectrum`` as recalled (QETpy is not in the tree: parity unpinned): the one-sided half of a two-sided
+    spectrum with every bin but DC (and Nyquist, even length) doubled; returns (rfftfreq, folded)."""
+    n = spectrum.shape[-1]
+    f = np.fft.rfftfreq(n, d=1.0 / fs)
+    out = np.array(spectrum[..., :len(f)], dtype=np.float64)
+    out[..., 1:n // 2 + n % 2] *= 2.0
+    return f, out
+
+
+def cleanup_freq_ranges(f_lims):
+    """utils/utils.py:437-470."""
+    if not isinstance(f_lims, list):
+        f_lims = [f_lims]
+    freq_ranges, range_names = [], []
+    for freq_range in f_lims:
+        if isinstance(freq_range, (float, int)):
+            freq_range = [freq_range]
+        f_low = abs(freq_range[0])
+        if len(freq_range) == 2:
+            f_high = abs(freq_range[1])
+            if f_low > f_high:
+                f_low, f_high = f_high, f_low
+            name = f'{round(f_low)}_{round(f_high)}'
+            if name not in range_names:
+                freq_ranges.append([f_low, f_high])
+                range_names.append(name)
+        else:
+            name = f'{round(f_low)}'
+            if name not in range_names:
+                freq_ranges.append([f_low])
+                range_names.append(name)
+    return freq_ranges, range_names
+
+
+def get_ind_freq_ranges(freq_ranges, freqs):
+    """utils/utils.py:475-505."""
+    idx_ranges = []
+    for freq_range in freq_ranges:
+        ind_low = int(np.argmin(np.abs(freqs - abs(freq_range[0]))))
+        ind_high = ind_low + 1
+        if len(freq_range) == 2:
+            ind_high = int(np.argmin(np.abs(freqs - abs(freq_range[1]))))
+        if ind_low > ind_high:
+            ind_low, ind_high = ind_high, ind_low
+        if ind_low == ind_high:
+            if ind_high < len(freqs) - 1:
+                ind_high += 1
+            elif ind_low > 0:
+                ind_low -= 1
+            else:
+                raise ValueError('Frequency range too narrow or outside bounds.')
+        idx_ranges.append([ind_low, ind_high])
+    return idx_ranges
+
+
+def psd_amp(trace, fs, f_lims, feature_base_name='psd_amp'):
+    """algorithms.py:993-1040 on one trace: dict feature name -> average of sqrt(folded psd) over each range."""
+    trace = np.asarray(trace, dtype=np.float64)
+    nbins = trace.shape[-1]
+    df = fs / nbins
+    trace_fft = np.fft.fft(trace) / nbins / df            # OFBase.signal_fft (oracle/of1x1.py::_fft_norm)
+    psd = (np.abs(trace_fft) ** 2.0) * nbins / fs
+    freqs_fold, psd_fold = fold_spectrum(psd, fs)
+    psd_fold = np.sqrt(psd_fold[1:])
+    freqs_fold = freqs_fold[1:]
+    freq_ranges, range_names = cleanup_freq_ranges(f_lims)
+    out = {}
+    for it, (lo, hi) in enumerate(get_ind_freq_ranges(freq_ranges, freqs_fold)):
+        out[f'{feature_base_name}_{range_names[it]}'] = float(np.average(psd_fold[lo:hi]))
+    return out
