@@ -57,6 +57,7 @@ def main(out_path, nb_samples=4096, n_events=16, seed=12345):
              psd_of_traces=psd, **{k: np.asarray(v) for k, v in res.items()})
     print('wrote', out_path)
     dump_nxm(qp, os.path.join(os.path.dirname(out_path), 'ofnxm_qetpy.npz'), nb_samples, n_events, seed)
+    dump_utils(qp, os.path.join(os.path.dirname(out_path), 'utils_qetpy.npz'), nb_samples, seed)
 
 
 def dump_nxm(qp, out_path, nb_samples, n_events, seed):
@@ -85,6 +86,22 @@ def dump_nxm(qp, out_path, nb_samples, n_events, seed):
     _, csd = qp.calc_csd(noise, fs=S.fs, folded_over=False)
     np.savez(out_path, nb_samples=nb_samples, n_events=n_events, seed=seed, csd_of_noise=csd,
              **{k: np.asarray(v) for k, v in res.items()})
+    print('wrote', out_path)
+
+
+def dump_utils(qp, out_path, nb_samples, seed):
+    """The two QETpy helpers the round-2 additions lean on: ``qp.utils.fold_spectrum`` (psd_amp, algorithms.py:1019) and
+    ``qp.utils.lowpassfilter(x, cut_off_freq=50e3, fs)`` (saturation test of the residual re-trigger, oftrigger.py:622-627).
+    Settles oracle/psd.py::fold_spectrum and the first-order Butterworth + filtfilt the product recalls."""
+    rng = np.random.default_rng(seed)
+    fs = 1.25e6
+    spec = rng.random(nb_samples)
+    spec_odd = rng.random(nb_samples - 1)
+    f_even, fold_even = qp.utils.fold_spectrum(spec, fs)
+    f_odd, fold_odd = qp.utils.fold_spectrum(spec_odd, fs)
+    x = rng.standard_normal(8 * nb_samples)
+    np.savez(out_path, seed=seed, spec=spec, spec_odd=spec_odd, f_even=f_even, fold_even=fold_even, f_odd=f_odd, fold_odd=fold_odd,
+             lpf_in=x, lpf_out=qp.utils.lowpassfilter(x, cut_off_freq=50e3, fs=fs))
     print('wrote', out_path)
 
 

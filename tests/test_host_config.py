@@ -127,7 +127,8 @@ def test_extractor_sentinels_and_errors_without_gpu():
     from detprocess_b200.core.ofbase import OFBaseBatch
     # only the in-scope names are public (the pipeline treats every public name as an algorithm)
     assert sorted(m for m in dir(FE) if not m.startswith('_')) == sorted(
-        ['of1x1_nodelay', 'of1x1_unconstrained', 'of1x1_constrained', 'ofnxm', 'baseline', 'integral', 'maximum', 'minimum'])
+        ['of1x1_nodelay', 'of1x1_unconstrained', 'of1x1_constrained', 'ofnxm', 'baseline', 'integral', 'maximum', 'minimum',
+         'psd_amp'])
     assert FE.baseline(None) == {'baseline': -999999.0}
     assert FE.integral(np.array([]), 1.25e6, feature_base_name='x') == {'x': -999999.0}
     assert FE.maximum(None, feature_base_name='m') == {'m': -999999.0}

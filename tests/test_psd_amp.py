@@ -137,3 +137,18 @@ def test_yaml_psd_amp_blocks_become_band_jobs(tmp_path):
     freqs = np.fft.rfftfreq(n, d=1.0 / fs)[1:]
     ref = P.get_ind_freq_ranges(P.cleanup_freq_ranges([[300.0, 3000.0], 50000.0])[0], freqs)
     assert jobs[0]['bins'] == [(a + 1, b + 1) for a, b in ref] and jobs[0]['channel'] == 'chanA'
+
+
+def test_fold_spectrum_against_qetpy_golden():
+    """pins oracle/psd.py::fold_spectrum (and the recalled low-pass filter of the trigger's saturation test) to upstream QETpy
+    where ``oracle/dump_golden.py`` has been run; skipped otherwise (QETpy is not installable in this image)"""
+    path = os.path.join(HERE, 'golden', 'utils_qetpy.npz')
+    if not os.path.exists(path):
+        pytest.skip('tests/golden/utils_qetpy.npz is generated by oracle/dump_golden.py where QETpy is installed')
+    g = np.load(path)
+    for spec, f, fold in ((g['spec'], g['f_even'], g['fold_even']), (g['spec_odd'], g['f_odd'], g['fold_odd'])):
+        fo, fold_o = P.fold_spectrum(spec, 1.25e6)
+        assert np.allclose(fo, f) and np.allclose(fold_o, fold, rtol=1e-14)
+    from scipy.signal import butter, filtfilt
+    b, a = butter(1, 50e3 / (0.5 * 1.25e6))
+    assert np.allclose(filtfilt(b, a, g['lpf_in'], padtype='even'), g['lpf_out'], rtol=1e-10, atol=1e-12)
