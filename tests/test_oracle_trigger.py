@@ -106,3 +106,21 @@ def test_residual_pass_recovers_a_pulse_hidden_in_the_tail_of_a_large_one():
     assert flags.all()
     assert np.array_equal(T.residual_delta_chi2(dchi2, filtered, first['trigger_index'], template, phi_td, 1.0 / norm, norm,
                                                 saturated=flags), dchi2)
+
+
+def test_saturation_lowpass_on_a_window_equals_the_whole_trace_filter():
+    """the product low-passes a window with a 4096-sample margin around each trigger instead of the whole stream
+    (core/oftrigger.py::_saturated): a first-order Butterworth run forward and backward forgets its past within a few
+    hundred samples, so both give the same values where the reference looks (oftrigger.py:776-786)"""
+    from scipy.signal import butter, filtfilt
+    fs, L, nt = 1.25e6, 400_000, 4096
+    rng = np.random.default_rng(8)
+    x = np.cumsum(rng.standard_normal(L)) * 1e-9 + rng.standard_normal(L) * 1e-8     # drifting baseline + noise
+    b, a = butter(1, 50e3 / (0.5 * fs))
+    full = filtfilt(b, a, x, padtype='even')
+    q, margin = int(nt / 4), 4096
+    for t in (nt, 5000, 123_456, L - nt, L - 1500):
+        lo, hi = max(t - q, 0), min(t + q, L)
+        wlo, whi = max(lo - margin, 0), min(hi + margin, L)
+        seg = filtfilt(b, a, x[wlo:whi], padtype='even')[lo - wlo:hi - wlo]
+        assert np.max(np.abs(seg - full[lo:hi])) < 1e-12 * np.max(np.abs(full))
