@@ -2005,8 +2005,12 @@ int dp_trigger_residual_run(dp_trigger_plan* p, const long long* pulse_start_dev
     rp.n_pulses = n_pulses;
     rp.shape = shape_dev;
     rp.n_shape = n_shape;
-    rc = dp_trig_residual_launch(&rp, std::max(1, std::min(p->last_chunks, 2 * std::max(p->n_sm, 1))), stream);
-    if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger residual launch: ") + cudaGetErrorString((cudaError_t)rc));
+    // an empty pulse list on a list that already holds residual survivors only regroups it (the caller's retry with larger
+    // output buffers): running the kernel again would replace the stored residuals by amp^2 w
+    if (!(n_pulses == 0 && p->resid_list)) {
+        rc = dp_trig_residual_launch(&rp, std::max(1, std::min(p->last_chunks, 2 * std::max(p->n_sm, 1))), stream);
+        if (rc != 0) return fail(DP_ERR_CUDA, std::string("trigger residual launch: ") + cudaGetErrorString((cudaError_t)rc));
+    }
     p->resid_list = true;
     DpTrigGroupParams gp;
     trig_group_params(p, gp);
