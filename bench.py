@@ -55,6 +55,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fast-mode', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the C4 (trigger) / C5 (PSD) side measurements')
+    ap.add_argument('--extras-at-scale', action='store_true',
+                    help='run the per-GPU side measurements (other_rows) under torchrun as well; by default they are the N=1 line\'s')
     return ap.parse_args()
 
 
@@ -646,7 +648,9 @@ def gpu_main(a):
         del aplan, ahost
 
     ex = None
-    if not a.no_extras:
+    # the side rows are per-GPU measurements without a collective: the N = 1 line carries them; under torchrun every rank
+    # would repeat them (minutes of plan building and pinned-memory set-up on a shared host) for no new information
+    if not a.no_extras and (world == 1 or a.extras_at_scale):
         ex = extras(device, dist, world, hbm_peak)
     coll = collective_rows(device, dist, world)
     if sampler:
